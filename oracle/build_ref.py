@@ -1,0 +1,168 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE: build the real reference (HM 16.14 as shipped in
+omricarmi/FastHEVC) into oracle/_ref/ so it can pin the C restatement in
+oracle/hm_intra.c and serve as the CPU baseline (`cpu_baseline.kind = "reference"`).
+
+Nothing from /root/reference is copied into the repository history: the
+sources are compiled where they lie, except for the handful of files that need
+the HARP/OpenCV dataset-dump hooks stubbed; those are patched
+into a scratch directory under oracle/_ref/ that is deleted after the build.
+
+Outputs (all git-ignored, all under oracle/_ref/):
+  TAppEncoder      stock encoder, HARP hooks removed
+  TAppEncoderDump  same + oracle/ref_dump_hook.cpp (per-CTU golden dumps via FHC_DUMP=file)
+  TAppDecoder      stock decoder (conformance checker: MD5 SEI)
+  cfg/             the two cfg files the metric uses (tiny text files, needed on the GPU box)
+
+Patched sites (reference file:line):
+  source/App/TAppEncoder/encmain.cpp:47-49,99-110   HARP includes + Global init + consts.json
+  source/App/TAppEncoder/TAppEncCfg.cpp:49,1587     HARP include + Global.inputFilename
+  source/Lib/TLibEncoder/TEncGOP.cpp:49,1562        HARP include + CShow_PredResiReco dump
+"""
+import os, re, shutil, subprocess, sys, concurrent.futures as cf
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("FHC_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+CXX = os.environ.get("CXX", "g++")
+CXXFLAGS = ["-std=c++11", "-O2", "-msse4.1", "-w"]
+
+
+def patched_sources(scratch):
+    """Return {orig_path: patched_path} for the files that need the HARP stub."""
+    src = os.path.join(REF, "source")
+    out = {}
+
+    def put(rel, text, tag=""):
+        # keep the directory layout so that quoted relative includes still resolve
+        dst = os.path.join(scratch, "source" + tag, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        open(dst, "w").write(text)
+        return dst
+
+    # encmain.cpp
+    rel = "App/TAppEncoder/encmain.cpp"
+    t = open(os.path.join(src, rel)).read()
+    t = re.sub(r'#include "\.\./\.\./\.\./Src_HARP/[^"]+"\n', "", t)
+    a = t.index("    //GLOBAL INIT")
+    b = t.index("    // starting time")
+    t = t[:a] + t[b:]
+    out[rel] = put(rel, t)
+
+    rel = "App/TAppEncoder/TAppEncCfg.cpp"
+    t = open(os.path.join(src, rel)).read()
+    t = re.sub(r'#include "\.\./\.\./\.\./Src_HARP/[^"]+"\n', "", t)
+    t = t.replace("Global.inputFilename = match[1];", "")
+    out[rel] = put(rel, t)
+
+    rel = "Lib/TLibEncoder/TEncGOP.cpp"
+    t = open(os.path.join(src, rel)).read()
+    t = re.sub(r'#include "\.\./\.\./\.\./Src_HARP/[^"]+"\n', "", t)
+    t = t.replace("CShow_PredResiReco Show_PredResiReco(pcPic);", "")
+    out[rel] = put(rel, t)
+    return out
+
+
+def dump_sources(scratch):
+    """Instrumented variants: one call per finished CTU / per slice into ref_dump_hook.cpp."""
+    src = os.path.join(REF, "source")
+    out = {}
+    rel = "Lib/TLibEncoder/TEncCu.cpp"
+    t = open(os.path.join(src, rel)).read()
+    t = t.replace("Void TEncCu::compressCtu( TComDataCU* pCtu )\n{",
+                  "void fhc_dump_ctu(TComDataCU*);\nVoid TEncCu::compressCtu( TComDataCU* pCtu )\n{\n  struct FhcAtExit { TComDataCU* c; ~FhcAtExit() { fhc_dump_ctu(c); } } fhcAtExit = { pCtu };", 1)
+    dst = os.path.join(scratch, "dump", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+
+    rel = "Lib/TLibEncoder/TEncSlice.cpp"
+    t = open(os.path.join(src, rel)).read()
+    marker = "  for( UInt ctuTsAddr = startCtuTsAddr; ctuTsAddr < boundingCtuTsAddr; ++ctuTsAddr )\n  {\n    const UInt ctuRsAddr = pcPic->getPicSym()->getCtuTsToRsAddrMap(ctuTsAddr);\n    // initialize CTU encoder"
+    assert t.count(marker) == 1, t.count(marker)
+    t = t.replace(marker, "  fhc_dump_slice(pcPic, pcSlice, m_pcRdCost, m_pcTrQuant);\n" + marker)
+    t = t.replace("Void TEncSlice::compressSlice(", "void fhc_dump_slice(TComPic*, TComSlice*, TComRdCost*, TComTrQuant*);\nVoid TEncSlice::compressSlice(", 1)
+    dst = os.path.join(scratch, "dump", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+    return out
+
+
+def compile_one(job):
+    srcfile, obj, incs, extra = job
+    if os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(srcfile):
+        return obj
+    cc = "gcc" if srcfile.endswith(".c") else CXX
+    flags = ["-O2", "-w"] if srcfile.endswith(".c") else CXXFLAGS
+    cmd = [cc] + flags + extra + incs + ["-c", srcfile, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("compile failed: %s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+    return obj
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "source")):
+        print("build_ref: %s not present; keeping prebuilt oracle/_ref" % REF)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    scratch = os.path.join(OUT, "scratch")
+    objdir = os.path.join(OUT, "obj")
+    shutil.rmtree(scratch, ignore_errors=True)
+    os.makedirs(scratch); os.makedirs(objdir, exist_ok=True)
+    src = os.path.join(REF, "source")
+    stub = patched_sources(scratch)
+    dump = dump_sources(scratch)
+    incs = ["-I" + os.path.join(src, "Lib"), "-I" + os.path.join(src, "App"), "-I" + os.path.join(src, "App/TAppEncoder")]
+
+    def listing(d, exts=(".cpp", ".c")):
+        return sorted(os.path.join(d, f) for f in os.listdir(os.path.join(src, d)) if f.endswith(exts))
+
+    common = listing("Lib/TLibCommon") + listing("Lib/TLibVideoIO") + listing("Lib/TAppCommon") + listing("Lib/libmd5")
+    enc = listing("Lib/TLibEncoder") + listing("App/TAppEncoder")
+    dec = listing("Lib/TLibDecoder") + listing("App/TAppDecoder")
+
+    jobs, objs = [], {"enc": [], "dump": [], "dec": []}
+    def add(rel, which):
+        tagged = rel.replace("/", "_")
+        if which == "dump" and rel in dump:
+            s, o = dump[rel], os.path.join(objdir, "dump_" + tagged + ".o")
+            # quoted relative includes resolve against the original directory
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        elif rel in stub:
+            s, o = stub[rel], os.path.join(objdir, "stub_" + tagged + ".o")
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        else:
+            s, o = os.path.join(src, rel), os.path.join(objdir, tagged + ".o")
+            extra = []
+        if (s, o, incs, extra) not in jobs and not any(j[1] == o for j in jobs):
+            jobs.append((s, o, incs, extra))
+        objs[which].append(o)
+
+    for rel in common:
+        add(rel, "enc"); add(rel, "dump"); add(rel, "dec")
+    for rel in enc:
+        add(rel, "enc"); add(rel, "dump")
+    for rel in dec:
+        add(rel, "dec")
+    hook_o = os.path.join(objdir, "ref_dump_hook.o")
+    jobs.append((os.path.join(HERE, "ref_dump_hook.cpp"), hook_o, incs, []))
+    objs["dump"].append(hook_o)
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        list(ex.map(compile_one, jobs))
+
+    for name, key in (("TAppEncoder", "enc"), ("TAppEncoderDump", "dump"), ("TAppDecoder", "dec")):
+        subprocess.check_call([CXX, "-O2", "-o", os.path.join(OUT, name)] + sorted(set(objs[key])) + ["-lm"])
+    os.makedirs(os.path.join(OUT, "cfg"), exist_ok=True)
+    for c in ("encoder_intra_main.cfg", "encoder_intra_main10.cfg"):
+        shutil.copy(os.path.join(REF, "cfg", c), os.path.join(OUT, "cfg", c))
+    shutil.rmtree(scratch, ignore_errors=True)
+    shutil.rmtree(objdir, ignore_errors=True)
+    print("build_ref: built", sorted(os.listdir(OUT)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
