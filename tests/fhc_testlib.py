@@ -1,0 +1,150 @@
+"""Shared helpers for the test-suite: record layouts, the oracle (ctypes), the
+reference binaries in oracle/_ref, synthetic content.  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# dump records written by oracle/ref_dump_hook.cpp (packed)
+SLICE_DT = np.dtype([("magic", "<u4"), ("poc", "<i4"), ("qp", "<i4"), ("width", "<i4"), ("height", "<i4"),
+                     ("bitDepthY", "<i4"), ("bitDepthC", "<i4"), ("lambda", "<f8"), ("sqrtLambda", "<f8"),
+                     ("distWeightCb", "<f8"), ("distWeightCr", "<f8"), ("rdoqLambda", "<f8", 3)])
+CTU_DUMP_DT = np.dtype([("magic", "<u4"), ("poc", "<i4"), ("ctuRsAddr", "<i4"),
+                        ("depth", "u1", 256), ("partSize", "u1", 256), ("predMode", "u1", 256), ("lumaDir", "u1", 256),
+                        ("chromaDir", "u1", 256), ("trIdx", "u1", 256), ("cbf", "u1", (3, 256)), ("tskip", "u1", (3, 256)),
+                        ("coefY", "<i4", 4096), ("coefCb", "<i4", 1024), ("coefCr", "<i4", 1024),
+                        ("recoY", "<i2", 4096), ("recoCb", "<i2", 1024), ("recoCr", "<i2", 1024),
+                        ("totalCost", "<f8"), ("totalDist", "<u4"), ("totalBits", "<u4"), ("totalBins", "<u4")])
+# one finished CTU as produced by the oracle and by the C-ABI (include/fasthevc_cuda.h: fhc_ctu_result)
+CTU_OUT_DT = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("predMode", "u1", 256), ("lumaDir", "u1", 256),
+                       ("chromaDir", "u1", 256), ("trIdx", "u1", 256), ("cbf", "u1", (3, 256)), ("tskip", "u1", (3, 256)),
+                       ("coefY", "<i2", 4096), ("coefCb", "<i2", 1024), ("coefCr", "<i2", 1024),
+                       ("recoY", "<i2", 4096), ("recoCb", "<i2", 1024), ("recoCr", "<i2", 1024),
+                       ("totalCost", "<f8"), ("totalDist", "<u4"), ("totalBits", "<u4"), ("totalBins", "<u4")], align=True)
+FIELDS = ["depth", "partSize", "predMode", "lumaDir", "chromaDir", "trIdx", "cbf", "tskip", "coefY", "coefCb", "coefCr",
+          "recoY", "recoCb", "recoCr", "totalCost", "totalDist", "totalBits", "totalBins"]
+
+
+class HmParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitDepth", C.c_int32), ("qp", C.c_int32),
+                ("lambda_", C.c_double), ("sqrtLambda", C.c_double), ("distWeight", C.c_double * 3),
+                ("rdoqLambda", C.c_double * 3)]
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "libhm_intra_oracle.so")
+    src = os.path.join(ORACLE_DIR, "hm_intra.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        lib.hm_params_from_qp.argtypes = [C.POINTER(HmParams), C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.hm_intra_compress_picture.argtypes = [C.POINTER(HmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hm_intra_compress_picture.restype = C.c_int
+        _oracle = lib
+    return _oracle
+
+
+def params_from_qp(width, height, bit_depth, qp):
+    p = HmParams()
+    oracle().hm_params_from_qp(C.byref(p), width, height, bit_depth, qp)
+    return p
+
+
+def params_from_slice(rec):
+    p = HmParams()
+    p.width, p.height, p.bitDepth, p.qp = int(rec["width"]), int(rec["height"]), int(rec["bitDepthY"]), int(rec["qp"])
+    p.lambda_, p.sqrtLambda = float(rec["lambda"]), float(rec["sqrtLambda"])
+    p.distWeight[0], p.distWeight[1], p.distWeight[2] = 1.0, float(rec["distWeightCb"]), float(rec["distWeightCr"])
+    for i in range(3):
+        p.rdoqLambda[i] = float(rec["rdoqLambda"][i])
+    return p
+
+
+def n_ctus(width, height):
+    return ((width + 63) // 64) * ((height + 63) // 64)
+
+
+def oracle_compress(params, y, u, v):
+    """y,u,v: 2-D arrays (any integer dtype).  Returns CTU_OUT_DT array."""
+    n = n_ctus(params.width, params.height)
+    out = np.zeros(n, CTU_OUT_DT)
+    planes = [np.ascontiguousarray(p, dtype=np.uint16) for p in (y, u, v)]
+    rc = oracle().hm_intra_compress_picture(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data,
+                                            planes[2].ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def parse_dump(path):
+    """Returns list of (slice_rec, ctu_recs) per picture."""
+    raw = open(path, "rb").read()
+    pos, pics = 0, []
+    while pos < len(raw):
+        magic = int(np.frombuffer(raw, "<u4", 1, pos)[0])
+        if magic == 0x53434846:
+            s = np.frombuffer(raw, SLICE_DT, 1, pos)[0]
+            pos += SLICE_DT.itemsize
+            pics.append((s, []))
+        elif magic == 0x43434846:
+            c = np.frombuffer(raw, CTU_DUMP_DT, 1, pos)[0]
+            pos += CTU_DUMP_DT.itemsize
+            pics[-1][1].append(c)
+        else:
+            raise ValueError("bad magic %x at %d" % (magic, pos))
+    return [(s, np.array(c, CTU_DUMP_DT)) for s, c in pics]
+
+
+def have_ref():
+    return os.path.exists(os.path.join(REF_DIR, "TAppEncoderDump"))
+
+
+def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dump=True, extra=()):
+    """Runs oracle/_ref/TAppEncoder[Dump]; returns (bitstream bytes, dump path or None, stdout)."""
+    exe = os.path.join(REF_DIR, "TAppEncoderDump" if dump else "TAppEncoder")
+    cfg = os.path.join(REF_DIR, "cfg", "encoder_intra_main.cfg" if bit_depth == 8 else "encoder_intra_main10.cfg")
+    bs = os.path.join(workdir, "out.bin")
+    dp = os.path.join(workdir, "dump.bin")
+    env = dict(os.environ)
+    if dump:
+        env["FHC_DUMP"] = dp
+    cmd = [exe, "-c", cfg, "-i", yuv_path, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),
+           "-q", str(qp), "-b", bs, "-o", os.path.join(workdir, "rec.yuv"), "--SEIDecodedPictureHash=1"]
+    if bit_depth != 8:
+        cmd += ["--InputBitDepth=%d" % bit_depth]
+    cmd += list(extra)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=workdir)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
+    return open(bs, "rb").read(), (dp if dump else None), r.stdout
+
+
+def compare_ctus(got, ref, what="", coef_from_dump=True):
+    """Field-by-field comparison of CTU records; returns list of mismatch strings."""
+    bad = []
+    for i in range(len(ref)):
+        for f in FIELDS:
+            a, b = got[i][f], ref[i][f]
+            if f == "totalCost":
+                ok = float(a) == float(b)
+            else:
+                ok = np.array_equal(np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64))
+            if not ok:
+                bad.append("%s ctu %d field %s" % (what, i, f))
+    return bad
