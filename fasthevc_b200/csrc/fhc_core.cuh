@@ -1,0 +1,2189 @@
+// fhc_core.cuh - device code of the B200 HEVC intra mode-decision engine.
+//
+// One thread block per picture (all-intra pictures are independent; inside a
+// picture the CABAC context chain of TEncSlice::compressSlice forces raster CTU
+// order).  Inside the block a MASTER thread walks the decision
+// recursion (quad-tree, candidate loops, RQT, RDOQ's sequential pass, CABAC bit
+// counting) on state held in shared memory, and hands every sample-parallel
+// stage (reference-sample build, 35-mode prediction + Hadamard SATD, residual,
+// DCT/DST, RDOQ pre-quantisation, dequant + inverse transform, reconstruction,
+// SSE, block copies) to the WORKER warps through a command slot + barriers.
+//
+// The file is written against a small portability layer (FHC_DEVICE_BUILD) so
+// that tests can compile the very same source for the host and step through it
+// without a GPU ("emulation build", tests/ only - the product library never
+// contains it and has no CPU path).
+//
+// Reference citations are to /root/reference/source/Lib (HM 16.14).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "../../include/fasthevc_cuda.h"
+
+#ifdef FHC_DEVICE_BUILD
+#define FHC_DH __device__ __forceinline__
+#define FHC_D __device__
+#define FHC_NOINLINE __device__ __noinline__
+#else
+#define FHC_DH static inline
+#define FHC_D static
+#define FHC_NOINLINE static
+#endif
+
+namespace fhc {
+
+// ----------------------------------------------------------------------------------------------
+// constants
+// ----------------------------------------------------------------------------------------------
+enum { MODE_INTRA = 1, MODE_NONE = 2 };
+enum { SIZE_2Nx2N = 0, SIZE_NxN = 3, SIZE_NONE = 8 };
+enum { PLANAR_IDX = 0, DC_IDX = 1, HOR_IDX = 10, VER_IDX = 26, DM_CHROMA_IDX = 36 };
+enum { SCAN_DIAG = 0, SCAN_HOR = 1, SCAN_VER = 2 };
+enum { CI_CURR_BEST = 0, CI_NEXT_BEST, CI_TEMP_BEST, CI_CHROMA_INTRA, CI_QT_TRAFO_TEST, CI_QT_TRAFO_ROOT, CI_NUM };
+enum {
+  CTX_SPLIT = 0, CTX_PART = 3, CTX_IPRED = 4, CTX_CPRED = 5, CTX_CBF = 7, CTX_SUBDIV = 17, CTX_SIGCG = 20, CTX_SIG = 24,
+  CTX_LASTX = 68, CTX_LASTY = 98, CTX_ONE = 128, CTX_ABS = 152, CTX_TS = 158, NUM_CTX = 160
+};
+#define FHC_MAX_COST 1.7e+308
+#define FHC_NWORK 128            /* worker threads per block (4 warps) */
+
+// layout of the 6144-sample "YUV" buffers: Y at 0, Cb at 4096, Cr at 5120
+FHC_DH int comp_off(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
+
+// ----------------------------------------------------------------------------------------------
+// tables (built on the host by fhc_build_tables, copied to shared memory by the kernel)
+// ----------------------------------------------------------------------------------------------
+struct Tables
+{
+  uint8_t  z2r[256], r2z[256];
+  uint16_t scan[1520];            // diag: 4,8,16,32 ; hor: 4,8 ; ver: 4,8
+  uint16_t scanOff[3][4];
+  uint8_t  scanCG[3][88];         // per type: 1,4,16,64 entries at offsets 0,1,5,21
+  int16_t  T32[32 * 32];
+  int32_t  entropyBits[128];
+  uint8_t  nextState[128][2];
+  uint8_t  ctxInit[NUM_CTX];
+  int16_t  dst4[16];              // 4x4 DST-VII (TComRom.cpp g_as_DST_MAT_4)
+  int16_t  angTable[9], invAngTable[9];
+  uint8_t  chromaScale[58];       // g_aucChromaScale[CHROMA_420]
+  uint8_t  ctxIndMap4x4[16];
+  uint8_t  intraFilterThr[5];
+  double   errScale[2][4][6];     // [chType][log2-2][qp rem]
+};
+FHC_DH int cg_off(int l) { return l == 0 ? 0 : (l == 1 ? 1 : (l == 2 ? 5 : 21)); }
+
+struct Sbac { uint8_t c[NUM_CTX]; uint64_t frac; };
+
+struct CUMeta
+{
+  int zidx, x, y, depth, nparts, width;
+  uint32_t dist, bits, bins, pad;
+  double cost;
+  uint8_t dep[256], part[256], pred[256], ldir[256], cdir[256], tridx[256], cbf[3][256], ts[3][256];
+};
+
+// per-picture state in global memory
+struct FrameGlobal
+{
+  const void* org[3];             // input planes (sampleBytes each)
+  int16_t* rec[3];                // reconstruction planes, stride = plane width
+  fhc_ctu_result* out;            // [numCtus]
+  fhc_slice_params sp;
+  int32_t width, height, bitDepth, sampleBytes, wc, hc;
+  int16_t cuCoef[4][2][6144];     // CU coefficient buffers per depth, best/temp
+  int16_t cuReco[4][2][6144];     // CU reconstruction buffers
+  int16_t predYuv[6144];          // prediction -> reconstruction scratch of the CU under test
+  int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
+  int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
+};
+
+enum Op {
+  OP_EXIT = 0, OP_REFS, OP_RMD, OP_PRED_RESI, OP_FWD_QUANT, OP_LEVELS_OUT, OP_INV_RECON, OP_COPY2D, OP_COPY16, OP_ZERO16,
+  OP_CTU_RECO_OUT, OP_CU_TO_OUT
+};
+
+struct Cmd
+{
+  int op;
+  int a[16];
+  const void* src;
+  void* dst;
+};
+
+struct Shared
+{
+  Tables t;
+  Sbac go;
+  Sbac slot[5][CI_NUM];
+  uint32_t bins;
+  int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
+  uint8_t bestIdx[4];
+  CUMeta cu[4][2];
+  Cmd cmd;
+  int16_t refU[260], refF[260];
+  uint8_t flags[72];
+  int refDc;
+  int16_t resi[1024];
+  int32_t tmp[1024];              // transform stage buffer / level scratch
+  int32_t tcoef[1024];            // transform coefficients (raster)
+  int32_t lvlD[1024];             // RDOQ: lLevelDouble per scan position
+  union
+  {
+    struct
+    {
+      double cost0[1024], costCoeff[1024], costSig[1024];
+      int32_t rateIncUp[1024], rateIncDown[1024], sigRateDelta[1024], deltaU[1024];
+    } rd;
+    int16_t rmdPred[20480];
+  } u;
+  uint32_t satd[36];
+  uint32_t sse;
+  int16_t tsCoef[3][16], tsRec[3][16], tsPred[3][16];
+  uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];
+  double rdoqLambda;
+};
+
+struct Ctx { FrameGlobal* g; Shared* s; };
+
+// ----------------------------------------------------------------------------------------------
+// portability layer: barriers and the command hand-off
+// ----------------------------------------------------------------------------------------------
+FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw);
+FHC_DH int num_phases(int op)
+{
+  switch (op)
+  {
+  case OP_REFS: return 2;
+  case OP_RMD: return 2;            // per mode group, see par_rmd
+  case OP_FWD_QUANT: return 3;
+  case OP_INV_RECON: return 4;
+  default: return 1;
+  }
+}
+
+#ifdef FHC_DEVICE_BUILD
+FHC_DH void bar_all() { __syncthreads(); }
+FHC_DH void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(FHC_NWORK) : "memory"); }
+// master side: publish the command, release the workers, wait for completion
+FHC_DH void par(const Ctx& c, int op)
+{
+  c.s->cmd.op = op;
+  bar_all();
+  bar_all();
+}
+#else
+FHC_DH void par(const Ctx& c, int op)
+{
+  c.s->cmd.op = op;
+  const int np = (op == OP_RMD) ? c.s->cmd.a[15] : num_phases(op);
+  for (int ph = 0; ph < np; ph++)
+    for (int w = 0; w < FHC_NWORK; w++) run_phase(c, op, ph, w, FHC_NWORK);
+}
+#endif
+
+FHC_DH int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+FHC_DH int iabs(int v) { return v < 0 ? -v : v; }
+FHC_DH int imin(int a, int b) { return a < b ? a : b; }
+FHC_DH int imax(int a, int b) { return a > b ? a : b; }
+FHC_DH int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+FHC_DH int org_at(const FrameGlobal* g, int comp, int idx)
+{
+  return g->sampleBytes == 1 ? (int)((const uint8_t*)g->org[comp])[idx] : (int)((const uint16_t*)g->org[comp])[idx];
+}
+FHC_DH int plane_stride(const FrameGlobal* g, int comp) { return g->width >> (comp ? 1 : 0); }
+FHC_DH const uint16_t* scan_tab(const Tables& t, int type, int log2n) { return t.scan + t.scanOff[type][log2n - 2]; }
+FHC_DH const uint8_t* scan_cg(const Tables& t, int type, int log2n) { return t.scanCG[type] + cg_off(log2n - 2); }
+FHC_DH int tcoefm(const Tables& t, int n, int k, int j, int useDst)
+{
+  // 4x4 DST-VII matrix or rows of the 32-point DCT matrix
+  if (useDst) return t.dst4[k * 4 + j];
+  return t.T32[(k * (32 / n)) * 32 + j];
+}
+
+// ----------------------------------------------------------------------------------------------
+// intra prediction of one sample (TComPrediction.cpp:229-473, :731-817), closed forms of HM's loops
+// line: 4n+1 reference samples, index 2n = corner, growing index = up the left column then along the top
+// ----------------------------------------------------------------------------------------------
+FHC_DH int pred_sample(const Tables& t, const int16_t* line, int n, int log2n, int mode, int x, int y, int isLuma, int bd, int dcval)
+{
+  const int c = 2 * n;
+  if (mode == PLANAR_IDX)
+  {
+    const int left = line[c - 1 - y], top = line[c + 1 + x], topRight = line[c + 1 + n], bottomLeft = line[c - 1 - n];
+    return ((n - 1 - x) * left + (x + 1) * topRight + (n - 1 - y) * top + (y + 1) * bottomLeft + n) >> (log2n + 1);
+  }
+  if (mode == DC_IDX)
+  {
+    if (isLuma && n <= 16)
+    {
+      if (x == 0 && y == 0) return (line[c + 1] + line[c - 1] + 2 * dcval + 2) >> 2;
+      if (y == 0) return (line[c + 1 + x] + 3 * dcval + 2) >> 2;
+      if (x == 0) return (line[c - 1 - y] + 3 * dcval + 2) >> 2;
+    }
+    return dcval;
+  }
+  {
+    const int isVer = mode >= 18;
+    const int angMode = isVer ? mode - VER_IDX : -(mode - HOR_IDX);
+    const int absA = iabs(angMode);
+    const int angle = angMode < 0 ? -t.angTable[absA] : t.angTable[absA];
+    const int invAngle = t.invAngTable[absA];
+    const int s = isVer ? 1 : -1;                 // main(k) = line[c + s*k], side(j) = line[c - s*j]
+    const int u = isVer ? x : y, v = isVer ? y : x;
+    if (angle == 0)
+    {
+      int val = line[c + s * (u + 1)];
+      if (isLuma && n <= 16 && u == 0) val = clip3(0, (1 << bd) - 1, val + ((line[c - s * (v + 1)] - line[c]) >> 1));
+      return val;
+    }
+    const int deltaPos = (v + 1) * angle, deltaInt = deltaPos >> 5, fract = deltaPos & 31;
+    const int k0 = u + deltaInt + 1;
+    int a = (k0 >= 0) ? line[c + s * k0] : line[c - s * ((128 + (-k0) * invAngle) >> 8)];
+    if (!fract) return a;
+    const int k1 = k0 + 1;
+    int b = (k1 >= 0) ? line[c + s * k1] : line[c - s * ((128 + (-k1) * invAngle) >> 8)];
+    return ((32 - fract) * a + fract * b + 16) >> 5;
+  }
+}
+
+// TComPrediction::filteringIntraReferenceSamples (TComPattern.cpp:541)
+FHC_DH int use_filtered_refs(const Tables& t, int comp, int mode, int log2n)
+{
+  if (comp != 0 || mode == DC_IDX) return 0;
+  const int diff = imin(iabs(mode - HOR_IDX), iabs(mode - VER_IDX));
+  return diff > t.intraFilterThr[log2n - 2];
+}
+
+// 8x8 / 4x4 Hadamard SATD of (org - pred) (TComRdCost.cpp:1549-1750)
+FHC_DH uint32_t had8(int* m)
+{
+  int s = 0;
+  for (int i = 0; i < 8; i++)
+    for (int k = 1; k < 8; k <<= 1)
+      for (int j = 0; j < 8; j++)
+        if (!(j & k)) { int a = m[i * 8 + j], b = m[i * 8 + j + k]; m[i * 8 + j] = a + b; m[i * 8 + j + k] = a - b; }
+  for (int j = 0; j < 8; j++)
+    for (int k = 1; k < 8; k <<= 1)
+      for (int i = 0; i < 8; i++)
+        if (!(i & k)) { int a = m[i * 8 + j], b = m[(i + k) * 8 + j]; m[i * 8 + j] = a + b; m[(i + k) * 8 + j] = a - b; }
+  for (int i = 0; i < 64; i++) s += iabs(m[i]);
+  return (uint32_t)((s + 2) >> 2);
+}
+FHC_DH uint32_t had4(int* d)
+{
+  int m[16], s = 0;
+  for (int i = 0; i < 4; i++)
+  {
+    int a = d[i * 4] + d[i * 4 + 3], b = d[i * 4 + 1] + d[i * 4 + 2], cc = d[i * 4 + 1] - d[i * 4 + 2], dd = d[i * 4] - d[i * 4 + 3];
+    m[i * 4] = a + b; m[i * 4 + 1] = a - b; m[i * 4 + 2] = dd + cc; m[i * 4 + 3] = dd - cc;
+  }
+  for (int j = 0; j < 4; j++)
+  {
+    int a = m[j] + m[12 + j], b = m[4 + j] + m[8 + j], cc = m[4 + j] - m[8 + j], dd = m[j] - m[12 + j];
+    s += iabs(a + b) + iabs(a - b) + iabs(dd + cc) + iabs(dd - cc);
+  }
+  return (uint32_t)((s + 1) >> 1);
+}
+
+FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v)
+{
+#ifdef FHC_DEVICE_BUILD
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------
+// worker phases
+// ----------------------------------------------------------------------------------------------
+// cmd.a[] conventions are documented at each master call site ("par_*" helpers below).
+FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g;
+  Shared* s = c.s;
+  const int* a = s->cmd.a;
+  switch (op)
+  {
+  case OP_REFS:
+  {
+    // a0 comp, a1 n, a2 nu, a3 us, a4 plane offset of the block origin, a5 wantFilt, a6 numAvail, a7 total units
+    const int comp = a[0], n = a[1], nu = a[2], us = a[3], org0 = a[4], total = a[7];
+    const int stride = plane_stride(g, comp);
+    const int16_t* origin = g->rec[comp] + org0;
+    if (phase == 0)
+    {
+      const int dc = 1 << (g->bitDepth - 1);
+      for (int i = w; i < 4 * n + 1; i += nw)
+      {
+        // unit of this sample: left part bottom-up, corner, top part
+        int uidx = i < 2 * n ? i / us : (i == 2 * n ? 2 * nu : 2 * nu + 1 + (i - 2 * n - 1) / us);
+        int v;
+        if (a[6] == 0) v = dc;
+        else
+        {
+          int src = i;
+          if (!s->flags[uidx])
+          {
+            int j = uidx - 1;
+            while (j >= 0 && !s->flags[j]) j--;
+            if (j >= 0) src = j < 2 * nu ? (j * us + us - 1) : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us + us - 1);
+            else
+            {
+              j = uidx + 1;
+              while (j < total && !s->flags[j]) j++;
+              src = j < 2 * nu ? j * us : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us);
+            }
+          }
+          if (src < 2 * n) v = origin[(2 * n - 1 - src) * stride - 1];
+          else if (src == 2 * n) v = origin[-stride - 1];
+          else v = origin[-stride + (src - 2 * n - 1)];
+        }
+        s->refU[i] = (int16_t)v;
+      }
+    }
+    else
+    {
+      // DC value of the unfiltered line + optional smoothing (TComPattern.cpp:191-296)
+      const int16_t* line = s->refU;
+      if (w == 0)
+      {
+        int sum = 0;
+        for (int i = 0; i < n; i++) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
+        s->refDc = (sum + n) / (n + n);
+      }
+      if (a[5])
+      {
+        const int bl = line[0], tl = line[2 * n], tr = line[4 * n];
+        int strong = (comp == 0) && n >= 32;
+        if (strong)
+        {
+          const int thr = 1 << (g->bitDepth - 5);
+          strong = (iabs((bl + tl) - 2 * line[n]) < thr) && (iabs((tl + tr) - 2 * line[3 * n]) < thr);
+        }
+        const int shift = ilog2(2 * n);
+        for (int i = w; i < 4 * n + 1; i += nw)
+        {
+          int v;
+          if (i == 0 || i == 4 * n) v = line[i];
+          else if (strong)
+          {
+            if (i < 2 * n) v = (((2 * n - i) * bl) + (i * tl) + n) >> shift;
+            else if (i == 2 * n) v = line[i];
+            else v = (((2 * n - (i - 2 * n)) * tl) + ((i - 2 * n) * tr) + n) >> shift;
+          }
+          else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
+          s->refF[i] = (int16_t)v;
+        }
+      }
+    }
+    break;
+  }
+  case OP_RMD:
+  {
+    // a0 log2n, a1 org plane offset, a2 modes per group; phases alternate predict(group) / satd(group)
+    const int log2n = a[0], n = 1 << log2n, n2 = n * n, mpg = a[2];
+    const int grp = phase >> 1, m0 = grp * mpg, m1 = imin(35, m0 + mpg);
+    if (!(phase & 1))
+    {
+      const int items = (m1 - m0) * n2;
+      for (int i = w; i < items; i += nw)
+      {
+        const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
+        const int x = sidx & (n - 1), y = sidx >> log2n;
+        const int16_t* line = use_filtered_refs(s->t, 0, mode, log2n) ? s->refF : s->refU;
+        s->u.rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, g->bitDepth, s->refDc);
+      }
+    }
+    else
+    {
+      const int stride = plane_stride(g, 0);
+      if (n >= 8)
+      {
+        const int tps = n >> 3, tiles = tps * tps, items = (m1 - m0) * tiles;
+        for (int i = w; i < items; i += nw)
+        {
+          const int mi = i / tiles, tl = i - mi * tiles, ty = tl / tps, tx = tl - ty * tps;
+          int m[64];
+          for (int yy = 0; yy < 8; yy++)
+            for (int xx = 0; xx < 8; xx++)
+              m[yy * 8 + xx] = org_at(g, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->u.rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
+          atomic_add_u32(&s->satd[m0 + mi], had8(m));
+        }
+      }
+      else
+      {
+        for (int mi = w; mi < m1 - m0; mi += nw)
+        {
+          int d[16];
+          for (int yy = 0; yy < 4; yy++)
+            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, 0, a[1] + yy * stride + xx) - s->u.rmdPred[mi * 16 + yy * 4 + xx];
+          atomic_add_u32(&s->satd[m0 + mi], had4(d));
+        }
+      }
+    }
+    break;
+  }
+  case OP_PRED_RESI:
+  {
+    // a0 comp, a1 log2n, a2 mode, a3 useFilt, a4 offset into predYuv, a5 stride in predYuv, a6 org plane offset,
+    // a7 save/load (0 none, 1 save to tsPred, 2 load from tsPred)
+    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n;
+    int16_t* pred = g->predYuv + a[4];
+    const int ps = a[5], stride = plane_stride(g, comp);
+    const int16_t* line = a[3] ? s->refF : s->refU;
+    for (int i = w; i < n2; i += nw)
+    {
+      const int x = i & (n - 1), y = i >> log2n;
+      int v;
+      if (a[7] == 2) v = s->tsPred[comp][i];
+      else
+      {
+        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, g->bitDepth, s->refDc);
+        if (a[7] == 1) s->tsPred[comp][i] = (int16_t)v;
+      }
+      pred[y * ps + x] = (int16_t)v;
+      s->resi[i] = (int16_t)(org_at(g, comp, a[6] + y * stride + x) - v);
+    }
+    break;
+  }
+  case OP_FWD_QUANT:
+  {
+    // a0 log2n, a1 useDst, a2 transformSkip, a3 scanType, a4 quantCoef, a5 qBits, a6 chType(0/1), a7 qp rem
+    // out: tcoef[] raster, lvlD[scanPos], rd.cost0[scanPos], tmp[blkPos] = uiMaxAbsLevel
+    const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = g->bitDepth;
+    if (a[2])
+    {
+      if (phase == 1)
+      {
+        const int shift = 15 - bd - log2n;
+        for (int i = w; i < n2; i += nw) s->tcoef[i] = (int32_t)s->resi[i] << shift;
+      }
+    }
+    else if (phase == 0)
+    {
+      // xTrMxN first stage (TComTrQuant.cpp:860): rows -> tmp[k][j]
+      const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
+      for (int i = w; i < n2; i += nw)
+      {
+        const int k = i >> log2n, j = i & (n - 1);
+        int acc = 0;
+        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * s->resi[j * n + q];
+        s->tmp[i] = (acc + add1) >> shift1;
+      }
+    }
+    else if (phase == 1)
+    {
+      const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
+      for (int i = w; i < n2; i += nw)
+      {
+        const int k = i >> log2n, j = i & (n - 1);
+        int acc = 0;
+        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * s->tmp[j * n + q];
+        s->tcoef[i] = (acc + add2) >> shift2;
+      }
+    }
+    if (phase == 2)
+    {
+      // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient
+      const uint16_t* scan = scan_tab(s->t, a[3], log2n);
+      const int qBits = a[5];
+      const double errScale = s->t.errScale[a[6]][log2n - 2][a[7]];
+      const int64_t cap = (int64_t)2147483647 - ((int64_t)1 << (qBits - 1));
+      for (int p = w; p < n2; p += nw)
+      {
+        const int blk = scan[p];
+        const int64_t tl = (int64_t)iabs(s->tcoef[blk]) * a[4];
+        const int ld = (int)(tl < cap ? tl : cap);
+        const uint32_t m = (uint32_t)((ld + (1 << (qBits - 1))) >> qBits);
+        const double err = (double)ld;
+        s->lvlD[p] = ld;
+        s->u.rd.cost0[p] = err * err * errScale;
+        s->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
+      }
+    }
+    break;
+  }
+  case OP_LEVELS_OUT:
+  {
+    // a0 n2, a1 qtCoef layer, a2 offset: tmp[] (int32 levels) -> qtCoef (int16)
+    int16_t* d = g->qtCoef[a[1]] + a[2];
+    for (int i = w; i < a[0]; i += nw) d[i] = (int16_t)s->tmp[i];
+    break;
+  }
+  case OP_INV_RECON:
+  {
+    // a0 comp, a1 log2n, a2 useDst, a3 transformSkip, a4 absSum>0, a5 qp per, a6 qp rem,
+    // a7 predYuv offset, a8 predYuv stride, a9 qt layer, a10 qtRec offset, a11 rec plane offset, a12 org plane offset
+    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = g->bitDepth;
+    if (a[4])
+    {
+      if (phase == 0)
+      {
+        // xDeQuant (TComTrQuant.cpp:1308), flat scaling; levels are in tmp[] -> tcoef[]
+        const int transformShift = 15 - bd - log2n, rightShift = 6 - (transformShift + a[5]);
+        const int scale = (a[6] == 0 ? 40 : a[6] == 1 ? 45 : a[6] == 2 ? 51 : a[6] == 3 ? 57 : a[6] == 4 ? 64 : 72);
+        const int targetBits = imin(16, 32 + rightShift - 7);
+        const int inMin = -(1 << (targetBits - 1)), inMax = (1 << (targetBits - 1)) - 1;
+        for (int i = w; i < n2; i += nw)
+        {
+          const int q = clip3(inMin, inMax, s->tmp[i]);
+          int v;
+          if (rightShift > 0) v = (q * scale + (1 << (rightShift - 1))) >> rightShift;
+          else v = (int)((uint32_t)(q * scale) << (-rightShift));
+          s->tcoef[i] = clip3(-32768, 32767, v);
+        }
+      }
+      else if (phase == 1)
+      {
+        if (a[3])
+        {
+          const int shift = 15 - bd - log2n, off = shift == 0 ? 0 : (1 << (shift - 1));
+          for (int i = w; i < n2; i += nw) s->resi[i] = (int16_t)((s->tcoef[i] + off) >> shift);
+        }
+        else
+        {
+          // xITrMxN first stage (TComTrQuant.cpp:927): columns -> lvlD[j][i] (reused as scratch)
+          for (int i = w; i < n2; i += nw)
+          {
+            const int j = i >> log2n, q = i & (n - 1);
+            int acc = 0;
+            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * s->tcoef[k * n + j];
+            s->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
+          }
+        }
+      }
+      else if (phase == 2)
+      {
+        if (!a[3])
+        {
+          const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
+          for (int i = w; i < n2; i += nw)
+          {
+            const int j = i >> log2n, q = i & (n - 1);
+            int acc = 0;
+            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * s->lvlD[k * n + j];
+            s->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
+          }
+        }
+      }
+    }
+    if (phase == 3)
+    {
+      // reconstruction into CU buffer, QT layer and picture (TEncSearch.cpp:1380-1393) + SSE (TComRdCost.cpp:1176)
+      int16_t* reco = g->predYuv + a[7];
+      int16_t* recQt = g->qtRec[a[9]] + a[10];
+      int16_t* recPic = g->rec[comp] + a[11];
+      const int ps = a[8], qs = 64 >> (comp ? 1 : 0), stride = plane_stride(g, comp), shift = (bd - 8) << 1;
+      uint32_t acc = 0;
+      for (int i = w; i < n2; i += nw)
+      {
+        const int x = i & (n - 1), y = i >> log2n;
+        const int r = a[4] ? s->resi[i] : 0;
+        const int v = clip3(0, (1 << bd) - 1, reco[y * ps + x] + r);
+        reco[y * ps + x] = (int16_t)v;
+        recQt[y * qs + x] = (int16_t)v;
+        recPic[y * stride + x] = (int16_t)v;
+        const int d = v - org_at(g, comp, a[12] + y * stride + x);
+        acc += (uint32_t)((d * d) >> shift);
+      }
+      if (acc) atomic_add_u32(&s->sse, acc);
+    }
+    break;
+  }
+  case OP_COPY2D:
+  {
+    // int16 block copy: a0 w, a1 h, a2 dst stride, a3 src stride
+    const int bw = a[0], bh = a[1];
+    int16_t* d = (int16_t*)s->cmd.dst;
+    const int16_t* sr = (const int16_t*)s->cmd.src;
+    for (int i = w; i < bw * bh; i += nw)
+    {
+      const int y = i / bw, x = i - y * bw;
+      d[y * a[2] + x] = sr[y * a[3] + x];
+    }
+    break;
+  }
+  case OP_COPY16:
+  {
+    int16_t* d = (int16_t*)s->cmd.dst;
+    const int16_t* sr = (const int16_t*)s->cmd.src;
+    for (int i = w; i < a[0]; i += nw) d[i] = sr[i];
+    break;
+  }
+  case OP_ZERO16:
+  {
+    int16_t* d = (int16_t*)s->cmd.dst;
+    for (int i = w; i < a[0]; i += nw) d[i] = 0;
+    break;
+  }
+  case OP_CTU_RECO_OUT:
+  {
+    // reconstruction of the finished CTU into its result record (0 outside the picture)
+    fhc_ctu_result* o = &g->out[s->ctuAddr];
+    for (int i = w; i < 6144; i += nw)
+    {
+      const int comp = i < 4096 ? 0 : (i < 5120 ? 1 : 2), sh = comp ? 1 : 0, nn = 64 >> sh;
+      const int k = i - comp_off(comp), xx = k & (nn - 1), yy = k / nn;
+      const int px = (s->ctuPelX >> sh) + xx, py = (s->ctuPelY >> sh) + yy;
+      int16_t* d = comp == 0 ? o->recoY : (comp == 1 ? o->recoCb : o->recoCr);
+      d[k] = (px < (g->width >> sh) && py < (g->height >> sh)) ? g->rec[comp][py * plane_stride(g, comp) + px] : (int16_t)0;
+    }
+    break;
+  }
+  case OP_CU_TO_OUT:
+  {
+    // copyToPic (TComDataCU.cpp:906): a0 depth, a1 buffer index, a2 zidx, a3 nparts, a4 width
+    const CUMeta* cu = &s->cu[a[0]][a[1]];
+    fhc_ctu_result* o = &g->out[s->ctuAddr];
+    const int z = a[2], np = a[3], wdt = a[4];
+    for (int i = w; i < np; i += nw)
+    {
+      o->partSize[z + i] = cu->part[i]; o->predMode[z + i] = cu->pred[i]; o->lumaDir[z + i] = cu->ldir[i];
+      o->chromaDir[z + i] = cu->cdir[i]; o->trIdx[z + i] = cu->tridx[i]; o->depth[z + i] = cu->dep[i];
+      for (int cc = 0; cc < 3; cc++) { o->cbf[cc][z + i] = cu->cbf[cc][i]; o->transformSkip[cc][z + i] = cu->ts[cc][i]; }
+    }
+    const int16_t* sc = g->cuCoef[a[0]][a[1]];
+    const int ny = wdt * wdt, nc = ny >> 2;
+    for (int i = w; i < ny; i += nw) o->coefY[z * 16 + i] = sc[i];
+    for (int i = w; i < nc; i += nw) { o->coefCb[z * 4 + i] = sc[4096 + i]; o->coefCr[z * 4 + i] = sc[5120 + i]; }
+    break;
+  }
+  default: break;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// master-side helpers that wrap commands
+// ----------------------------------------------------------------------------------------------
+FHC_DH void par_copy2d(const Ctx& c, int16_t* dst, int ds, const int16_t* src, int ss, int w, int h)
+{
+  Cmd& m = c.s->cmd;
+  m.a[0] = w; m.a[1] = h; m.a[2] = ds; m.a[3] = ss; m.dst = dst; m.src = src;
+  par(c, OP_COPY2D);
+}
+FHC_DH void par_copy16(const Ctx& c, int16_t* dst, const int16_t* src, int n)
+{
+  Cmd& m = c.s->cmd;
+  if (n <= 16) { for (int i = 0; i < n; i++) dst[i] = src[i]; return; }
+  m.a[0] = n; m.dst = dst; m.src = src;
+  par(c, OP_COPY16);
+}
+FHC_DH void par_zero16(const Ctx& c, int16_t* dst, int n)
+{
+  Cmd& m = c.s->cmd;
+  m.a[0] = n; m.dst = dst;
+  par(c, OP_ZERO16);
+}
+FHC_DH void set_range(uint8_t* a, int start, int count, int v) { for (int i = 0; i < count; i++) a[start + i] = (uint8_t)v; }
+FHC_DH void copy_bytes(uint8_t* d, const uint8_t* s, int n) { for (int i = 0; i < n; i++) d[i] = s[i]; }
+
+// ----------------------------------------------------------------------------------------------
+// CABAC bit counter (TEncBinCoderCABACCounter.cpp:57-140)
+// ----------------------------------------------------------------------------------------------
+FHC_DH void enc_bin(Shared* s, int ctx, int bin)
+{
+  const uint8_t st = s->go.c[ctx];
+  s->bins++;
+  s->go.frac += (uint64_t)s->t.entropyBits[st ^ bin];
+  s->go.c[ctx] = s->t.nextState[st][bin];
+}
+FHC_DH void enc_ep(Shared* s, int n) { s->bins += (uint32_t)n; s->go.frac += (uint64_t)32768 * (uint64_t)n; }
+FHC_DH void enc_trm(Shared* s, int bin) { s->bins++; s->go.frac += (uint64_t)s->t.entropyBits[126 ^ bin]; }
+FHC_DH void reset_bits(Shared* s) { s->go.frac &= 32767; s->bins = 0; }
+FHC_DH uint32_t num_bits(const Shared* s) { return (uint32_t)(s->go.frac >> 15); }
+FHC_DH int ctx_bits(const Shared* s, int ctx, int bin) { return s->t.entropyBits[s->go.c[ctx] ^ bin]; }
+FHC_DH void sb_copy(Sbac* d, const Sbac* sr)
+{
+  const uint64_t* a = (const uint64_t*)sr;
+  uint64_t* b = (uint64_t*)d;
+  for (int i = 0; i < (int)(sizeof(Sbac) / 8); i++) b[i] = a[i];
+}
+FHC_DH void sbac_reset(Shared* s, Sbac* sb, int qp)                        // ContextModel::init (ContextModel.cpp:56)
+{
+  qp = clip3(0, 51, qp);
+  for (int i = 0; i < NUM_CTX; i++)
+  {
+    const int iv = s->t.ctxInit[i], slope = (iv >> 4) * 5 - 45, offset = ((iv & 15) << 3) - 16;
+    const int st = imin(imax(1, ((slope * qp) >> 4) + offset), 126);
+    const int mps = st >= 64;
+    sb->c[i] = (uint8_t)(((mps ? (st - 64) : (63 - st)) << 1) + mps);
+  }
+  sb->frac = 0;
+}
+#ifdef FHC_DEVICE_BUILD
+FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return __dadd_rn((double)dist, __dmul_rn((double)bits, c.g->sp.lambda)); }
+FHC_DH double dmul(double a, double b) { return __dmul_rn(a, b); }
+FHC_DH double dadd(double a, double b) { return __dadd_rn(a, b); }
+FHC_DH double dsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return (double)dist + ((double)bits * c.g->sp.lambda); }
+FHC_DH double dmul(double a, double b) { return a * b; }
+FHC_DH double dadd(double a, double b) { return a + b; }
+FHC_DH double dsub(double a, double b) { return a - b; }
+#endif
+
+// ----------------------------------------------------------------------------------------------
+// neighbours (TComDataCU.cpp:985-1200, :1362-1461)
+// ----------------------------------------------------------------------------------------------
+enum { F_DEPTH, F_LDIR };
+FHC_DH int cu_field(const CUMeta* cu, int idx, int f) { return f == F_DEPTH ? cu->dep[idx] : (cu->pred[idx] == MODE_INTRA ? cu->ldir[idx] : DC_IDX); }
+FHC_DH int ctu_field(const fhc_ctu_result* o, int idx, int f) { return f == F_DEPTH ? o->depth[idx] : (o->predMode[idx] == MODE_INTRA ? o->lumaDir[idx] : DC_IDX); }
+
+FHC_DH int nb_left(const Ctx& c, const CUMeta* cu, int zabs, int f)
+{
+  const Shared* s = c.s;
+  const int r = s->t.z2r[zabs];
+  if (r & 15)
+  {
+    const int nz = s->t.r2z[r - 1];
+    if ((r & 15) == (s->t.z2r[cu->zidx] & 15)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
+    return cu_field(cu, nz - cu->zidx, f);
+  }
+  if (s->ctuX == 0) return -1;
+  return ctu_field(&c.g->out[s->ctuAddr - 1], s->t.r2z[r + 15], f);
+}
+FHC_DH int nb_above(const Ctx& c, const CUMeta* cu, int zabs, int f, int planarAtCtuBoundary)
+{
+  const Shared* s = c.s;
+  const int r = s->t.z2r[zabs];
+  if (r >> 4)
+  {
+    const int nz = s->t.r2z[r - 16];
+    if ((r >> 4) == (s->t.z2r[cu->zidx] >> 4)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
+    return cu_field(cu, nz - cu->zidx, f);
+  }
+  if (planarAtCtuBoundary || s->ctuY == 0) return -1;
+  return ctu_field(&c.g->out[s->ctuAddr - c.g->wc], s->t.r2z[r + 240], f);
+}
+FHC_DH int get_mpm(const Ctx& c, const CUMeta* cu, int relIdx, int mpm[3])
+{
+  const int zabs = cu->zidx + relIdx;
+  int l = nb_left(c, cu, zabs, F_LDIR), a = nb_above(c, cu, zabs, F_LDIR, 1);
+  if (l < 0) l = DC_IDX;
+  if (a < 0) a = DC_IDX;
+  if (l == a)
+  {
+    if (l > 1) { mpm[0] = l; mpm[1] = ((l + 29) % 32) + 2; mpm[2] = ((l - 1) % 32) + 2; }
+    else { mpm[0] = PLANAR_IDX; mpm[1] = DC_IDX; mpm[2] = VER_IDX; }
+    return 1;
+  }
+  mpm[0] = l; mpm[1] = a;
+  if (l && a) mpm[2] = PLANAR_IDX;
+  else mpm[2] = (l + a) < 2 ? VER_IDX : DC_IDX;
+  return 2;
+}
+FHC_DH int ctx_split(const Ctx& c, const CUMeta* cu, int relIdx, int depth)
+{
+  const int zabs = cu->zidx + relIdx;
+  const int l = nb_left(c, cu, zabs, F_DEPTH), a = nb_above(c, cu, zabs, F_DEPTH, 0);
+  return (l >= 0 && l > depth) + (a >= 0 && a > depth);
+}
+FHC_DH int coef_scan_idx(const CUMeta* cu, int relIdx, int n, int comp)       // TComDataCU.cpp:3109
+{
+  int dir;
+  if (n > (comp ? 4 : 8)) return SCAN_DIAG;
+  if (comp == 0) dir = cu->ldir[relIdx];
+  else
+  {
+    dir = cu->cdir[relIdx];
+    if (dir == DM_CHROMA_IDX) dir = cu->ldir[relIdx & ~3];
+  }
+  if (iabs(dir - VER_IDX) <= 4) return SCAN_HOR;
+  if (iabs(dir - HOR_IDX) <= 4) return SCAN_VER;
+  return SCAN_DIAG;
+}
+
+// ----------------------------------------------------------------------------------------------
+// syntax element bit counting (TEncSbac.cpp)
+// ----------------------------------------------------------------------------------------------
+FHC_DH void code_split_flag(const Ctx& c, const CUMeta* cu, int relIdx, int depth)
+{
+  if (depth == 3) return;
+  enc_bin(c.s, CTX_SPLIT + ctx_split(c, cu, relIdx, depth), cu->dep[relIdx] > depth ? 1 : 0);
+}
+FHC_DH void code_part_size(const Ctx& c, const CUMeta* cu, int relIdx, int depth)
+{
+  if (depth == 3) enc_bin(c.s, CTX_PART, cu->part[relIdx] == SIZE_2Nx2N ? 1 : 0);
+}
+FHC_D void code_luma_dir(const Ctx& c, const CUMeta* cu, int relIdx, int isMultiple)          // TEncSbac.cpp:643
+{
+  const int partNum = isMultiple ? (cu->part[relIdx] == SIZE_NxN ? 4 : 1) : 1;
+  const int partOffset = (256 >> (cu->dep[relIdx] << 1)) >> 2;
+  int predIdx[4];
+  for (int j = 0; j < partNum; j++)
+  {
+    int preds[3];
+    const int dir = cu->ldir[relIdx + partOffset * j];
+    get_mpm(c, cu, relIdx + partOffset * j, preds);
+    predIdx[j] = -1;
+    for (int i = 0; i < 3; i++) if (dir == preds[i]) predIdx[j] = i;
+    enc_bin(c.s, CTX_IPRED, predIdx[j] != -1 ? 1 : 0);
+  }
+  for (int j = 0; j < partNum; j++) enc_ep(c.s, predIdx[j] != -1 ? (predIdx[j] ? 2 : 1) : 5);
+}
+FHC_DH void code_chroma_dir(const Ctx& c, const CUMeta* cu, int relIdx)                        // TEncSbac.cpp:698
+{
+  if (cu->cdir[relIdx] == DM_CHROMA_IDX) enc_bin(c.s, CTX_CPRED, 0);
+  else { enc_bin(c.s, CTX_CPRED, 1); enc_ep(c.s, 2); }
+}
+FHC_DH int sig_ctx_inc(const Tables& t, int pat, int firstCtx, int rasterPos, int log2n, int isChroma)   // TComTrQuant.cpp:2707
+{
+  const int posY = rasterPos >> log2n, posX = rasterPos - (posY << log2n);
+  int cnt;
+  if (posX + posY == 0) return 0;
+  if (log2n == 2) return firstCtx + t.ctxIndMap4x4[4 * posY + posX];
+  switch (pat)
+  {
+  case 0: { const int t = (posX & 3) + (posY & 3); cnt = (t >= 3) ? 0 : ((t >= 1) ? 1 : 2); } break;
+  case 1: { const int y = posY & 3; cnt = (y >= 2) ? 0 : ((y >= 1) ? 1 : 2); } break;
+  case 2: { const int x = posX & 3; cnt = (x >= 2) ? 0 : ((x >= 1) ? 1 : 2); } break;
+  default: cnt = 2; break;
+  }
+  return firstCtx + ((((posX >> 2) + (posY >> 2)) > 0 ? (isChroma ? 0 : 3) : 0) + cnt);
+}
+FHC_DH int first_sig_ctx(int log2n, int scanType, int isChroma)
+{
+  if (log2n == 2) return 0;
+  if (log2n == 3) return 9 + ((scanType != SCAN_DIAG && !isChroma) ? 6 : 0);
+  return isChroma ? 12 : 21;
+}
+FHC_DH int pattern_sig_ctx(const uint8_t* cgFlag, int cgX, int cgY, int wg)
+{
+  int r = 0, l = 0;
+  if (wg <= 1) return 0;
+  if (cgX < wg - 1) r = cgFlag[cgY * wg + cgX + 1] != 0;
+  if (cgY < wg - 1) l = cgFlag[(cgY + 1) * wg + cgX] != 0;
+  return r + (l << 1);
+}
+FHC_DH int sig_cg_ctx(const uint8_t* cgFlag, int cgX, int cgY, int wg)
+{
+  int r = 0, l = 0;
+  if (cgX < wg - 1) r = cgFlag[cgY * wg + cgX + 1] != 0;
+  if (cgY < wg - 1) l = cgFlag[(cgY + 1) * wg + cgX] != 0;
+  return (r + l) != 0;
+}
+FHC_DH void last_ctx_params(int isChroma, int log2n, int* off, int* shift)
+{
+  const int cc = log2n - 2;
+  *off = isChroma ? 0 : (cc * 3 + ((cc + 1) >> 2));
+  *shift = isChroma ? cc : ((cc + 3) >> 2);
+}
+FHC_DH int group_idx(int p) { return p < 4 ? p : (p < 6 ? 4 : (p < 8 ? 5 : (p < 12 ? 6 : (p < 16 ? 7 : (p < 24 ? 8 : 9))))); }
+
+FHC_DH void code_remain(Shared* s, uint32_t symbol, uint32_t rParam)                            // TEncSbac.cpp:337
+{
+  int codeNumber = (int)symbol;
+  if (codeNumber < (3 << rParam)) enc_ep(s, (int)(((uint32_t)codeNumber >> rParam) + 1 + rParam));
+  else
+  {
+    uint32_t length = rParam;
+    codeNumber -= (3 << rParam);
+    while (codeNumber >= (1 << length)) codeNumber -= (1 << (length++));
+    enc_ep(s, (int)(3 + length + 1 - rParam + length));
+  }
+}
+
+// TEncSbac::codeCoeffNxN (TEncSbac.cpp:1181-1538); coef: int16 raster levels of this TU
+FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp, const int16_t* coef, int log2n, int comp)
+{
+  Shared* s = c.s;
+  const int isChroma = comp != 0, n = 1 << log2n;
+  const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
+  const uint16_t* scan = scan_tab(s->t, scanType, log2n);
+  const uint8_t* scanCG = scan_cg(s->t, scanType, log2n);
+  const int wg = n >> 2;
+  const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
+  const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
+  uint8_t cgFlag[64];
+  int scanPosLast = -1, posLast = 0;
+
+  if (log2n == 2) enc_bin(s, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
+  for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
+  // last significant position: highest scan index with a non-zero level
+  for (int p = n * n - 1; p >= 0; p--)
+    if (coef[scan[p]] != 0) { scanPosLast = p; break; }
+  posLast = scan[scanPosLast];
+  for (int g4 = 0; g4 <= (scanPosLast >> 4); g4++)
+  {
+    int any = 0;
+    for (int i = 0; i < 16; i++) any |= coef[scan[g4 * 16 + i]] != 0;
+    if (any) cgFlag[scanCG[g4]] = 1;
+  }
+  {
+    int posY = posLast >> log2n, posX = posLast - (posY << log2n), off, shift, cc;
+    if (scanType == SCAN_VER) { const int t = posX; posX = posY; posY = t; }
+    const int gx = group_idx(posX), gy = group_idx(posY), gmax = group_idx(n - 1);
+    last_ctx_params(isChroma, log2n, &off, &shift);
+    const int bx = CTX_LASTX + (isChroma ? 15 : 0) + off, by = CTX_LASTY + (isChroma ? 15 : 0) + off;
+    for (cc = 0; cc < gx; cc++) enc_bin(s, bx + (cc >> shift), 1);
+    if (gx < gmax) enc_bin(s, bx + (cc >> shift), 0);
+    for (cc = 0; cc < gy; cc++) enc_bin(s, by + (cc >> shift), 1);
+    if (gy < gmax) enc_bin(s, by + (cc >> shift), 0);
+    if (gx > 3) enc_ep(s, (gx - 2) >> 1);
+    if (gy > 3) enc_ep(s, (gy - 2) >> 1);
+  }
+  {
+    const int lastScanSet = scanPosLast >> 4;
+    uint32_t c1 = 1;
+    int scanPosSig = scanPosLast;
+    for (int subSet = lastScanSet; subSet >= 0; subSet--)
+    {
+      int numNonZero = 0, lastNZ = -1, firstNZ = 16, escape = 0;
+      const int subPos = subSet << 4;
+      int absCoeff[16];
+      uint32_t goRice = 0;
+      const int cgBlk = scanCG[subSet], cgY = cgBlk / wg, cgX = cgBlk - cgY * wg;
+      if (scanPosSig == scanPosLast)
+      {
+        absCoeff[0] = iabs(coef[posLast]);
+        numNonZero = 1; lastNZ = scanPosSig; firstNZ = scanPosSig; scanPosSig--;
+      }
+      if (subSet == lastScanSet || subSet == 0) cgFlag[cgBlk] = 1;
+      else enc_bin(s, CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg), cgFlag[cgBlk] != 0);
+      if (cgFlag[cgBlk])
+      {
+        const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
+        for (; scanPosSig >= subPos; scanPosSig--)
+        {
+          const int blkPos = scan[scanPosSig], sig = coef[blkPos] != 0;
+          if (scanPosSig > subPos || subSet == 0 || numNonZero)
+            enc_bin(s, sigBase + sig_ctx_inc(s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
+          if (sig)
+          {
+            absCoeff[numNonZero++] = iabs(coef[blkPos]);
+            if (lastNZ == -1) lastNZ = scanPosSig;
+            firstNZ = scanPosSig;
+          }
+        }
+      }
+      else scanPosSig = subPos - 1;
+      if (numNonZero > 0)
+      {
+        const int signHidden = (lastNZ - firstNZ) >= 4;
+        const int ctxSet = (isChroma ? 4 : 0) + ((!isChroma && subSet > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0);
+        const int numC1 = imin(numNonZero, 8);
+        int firstC2 = -1;
+        c1 = 1;
+        for (int idx = 0; idx < numC1; idx++)
+        {
+          const int sym = absCoeff[idx] > 1;
+          enc_bin(s, CTX_ONE + 4 * ctxSet + (int)c1, sym);
+          if (sym) { c1 = 0; if (firstC2 == -1) firstC2 = idx; else escape = 1; }
+          else if (c1 < 3 && c1 > 0) c1++;
+        }
+        if (c1 == 0 && firstC2 != -1)
+        {
+          const int sym = absCoeff[firstC2] > 2;
+          enc_bin(s, CTX_ABS + ctxSet, sym);
+          if (sym) escape = 1;
+        }
+        escape = escape || (numNonZero > 8);
+        enc_ep(s, signHidden ? numNonZero - 1 : numNonZero);
+        if (escape)
+        {
+          int firstCoeff2 = 1;
+          for (int idx = 0; idx < numNonZero; idx++)
+          {
+            const int baseLevel = (idx < 8) ? (2 + firstCoeff2) : 1;
+            if (absCoeff[idx] >= baseLevel)
+            {
+              code_remain(s, (uint32_t)(absCoeff[idx] - baseLevel), goRice);
+              if (absCoeff[idx] > (3 << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
+            }
+            if (absCoeff[idx] >= 2) firstCoeff2 = 0;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// RDOQ sequential pass (TComTrQuant.cpp:2119-2661).  Inputs from OP_FWD_QUANT: tcoef[], lvlD[], cost0[],
+// tmp[] = uiMaxAbsLevel; output: levels in tmp[] (raster, int32); returns uiAbsSum.
+// ----------------------------------------------------------------------------------------------
+struct QpParam { int per, rem; };
+FHC_DH QpParam qp_param(const Ctx& c, int comp)                                                // TComTrQuant.cpp:71-119
+{
+  const int bdOff = 6 * (c.g->bitDepth - 8);
+  int base;
+  if (comp == 0) base = c.g->sp.sliceQp + bdOff;
+  else
+  {
+    base = clip3(-bdOff, 57, c.g->sp.sliceQp);
+    base = base < 0 ? base + bdOff : c.s->t.chromaScale[base] + bdOff;
+  }
+  QpParam q; q.per = base / 6; q.rem = base % 6;
+  return q;
+}
+FHC_DH int quant_scale(int rem) { return rem == 0 ? 26214 : rem == 1 ? 23302 : rem == 2 ? 20560 : rem == 3 ? 18396 : rem == 4 ? 16384 : 14564; }
+FHC_DH int inv_quant_scale(int rem) { return rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72; }
+
+FHC_DH int ic_rate(const Shared* s, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx)
+{
+  int rate = 32768;
+  const uint32_t baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
+  if (absLevel >= baseLevel)
+  {
+    uint32_t symbol = absLevel - baseLevel, length;
+    if (symbol < (3u << goRice)) { length = symbol >> goRice; rate += (int)((length + 1 + goRice) << 15); }
+    else
+    {
+      length = goRice;
+      symbol = symbol - (3u << goRice);
+      while (symbol >= (1u << length)) symbol -= (1u << (length++));
+      rate += (int)((3 + length + 1 - goRice + length) << 15);
+    }
+    if (c1Idx < 8)
+    {
+      rate += ctx_bits(s, ctxOne, 1);
+      if (c2Idx < 1) rate += ctx_bits(s, ctxAbs, 1);
+    }
+  }
+  else if (absLevel == 1) rate += ctx_bits(s, ctxOne, 0);
+  else if (absLevel == 2) { rate += ctx_bits(s, ctxOne, 1); rate += ctx_bits(s, ctxAbs, 0); }
+  else rate = 0;
+  return rate;
+}
+FHC_DH uint32_t coded_level(const Shared* s, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
+                            uint32_t maxAbsLevel, int ctxSig, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx,
+                            int qBits, double errScale, int isLast)
+{
+  double currCostSig = 0;
+  uint32_t best = 0;
+  if (!isLast && maxAbsLevel < 3)
+  {
+    *codedCostSig = dmul(lambda, (double)ctx_bits(s, ctxSig, 0));
+    *codedCost = dadd(*codedCost0, *codedCostSig);
+    if (maxAbsLevel == 0) return 0;
+  }
+  else *codedCost = FHC_MAX_COST;
+  if (!isLast) currCostSig = dmul(lambda, (double)ctx_bits(s, ctxSig, 1));
+  const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
+  for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
+  {
+    const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
+    double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(s, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
+    cur = dadd(cur, currCostSig);
+    if (cur < *codedCost) { best = (uint32_t)absLevel; *codedCost = cur; *codedCostSig = currCostSig; }
+  }
+  return best;
+}
+
+FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
+{
+  Shared* s = c.s;
+  const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.g->bitDepth;
+  const QpParam q = qp_param(c, comp);
+  const int qBits = 14 + q.per + (15 - bd - log2n);
+  const double errScale = s->t.errScale[isChroma][log2n - 2][q.rem];
+  const double lambda = s->rdoqLambda;
+  const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
+  const uint16_t* scan = scan_tab(s->t, scanType, log2n);
+  const uint8_t* scanCG = scan_cg(s->t, scanType, log2n);
+  const int wg = n >> 2, cgNum = numCoef >> 4;
+  const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
+  const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
+  const int32_t* src = s->tcoef;
+  int32_t* dst = s->tmp;
+  double* costCoeff0 = s->u.rd.cost0; double* costCoeff = s->u.rd.costCoeff; double* costSig = s->u.rd.costSig;
+  int32_t* rateIncUp = s->u.rd.rateIncUp; int32_t* rateIncDown = s->u.rd.rateIncDown;
+  int32_t* sigRateDelta = s->u.rd.sigRateDelta; int32_t* deltaU = s->u.rd.deltaU;
+  double costCGSig[64];
+  uint8_t cgFlag[64];
+  double blockUncoded = 0, baseCost = 0;
+  int cgLastScanPos = -1, lastScanPos = -1, c1 = 1, c2 = 0;
+  uint32_t ctxSet = 0, c1Idx = 0, c2Idx = 0, goRice = 0, absSum = 0;
+  int bestLastIdxP1 = 0;
+
+  for (int i = 0; i < cgNum; i++) { costCGSig[i] = 0; cgFlag[i] = 0; }
+
+  for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
+  {
+    const int cgBlk = scanCG[cgScanPos], cgY = cgBlk / wg, cgX = cgBlk - cgY * wg;
+    const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
+    double sigCost = 0, sigCost0 = 0, codedLevelAndDist = 0, uncodedDist = 0;
+    int nnzBeforePos0 = 0;
+    for (int posInCG = 15; posInCG >= 0; posInCG--)
+    {
+      const int scanPos = cgScanPos * 16 + posInCG;
+      const uint32_t blkPos = scan[scanPos];
+      const int levelDouble = s->lvlD[scanPos];
+      const uint32_t maxAbsLevel = (uint32_t)dst[blkPos];
+      blockUncoded = dadd(blockUncoded, costCoeff0[scanPos]);
+      if (lastScanPos < 0)
+      {
+        if (maxAbsLevel == 0)
+        {
+          // before the first non-zero level nothing but the uncoded distortion accumulates; the per-position
+          // arrays read later (cost/sig/rate/delta) only matter for scanPos <= lastScanPos
+          baseCost = dadd(baseCost, costCoeff0[scanPos]);
+          continue;
+        }
+        lastScanPos = scanPos;
+        ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && (scanPos >> 4) > 0) ? 2 : 0));
+        cgLastScanPos = cgScanPos;
+      }
+      {
+        uint32_t level;
+        const int ctxOne = CTX_ONE + 4 * (int)ctxSet + c1;
+        const int ctxAbs = CTX_ABS + (int)ctxSet + c2;
+        costCoeff[scanPos] = 0; costSig[scanPos] = 0;
+        rateIncUp[blkPos] = 0; rateIncDown[blkPos] = 0; sigRateDelta[blkPos] = 0;
+        if (scanPos == lastScanPos)
+          level = coded_level(s, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+                              sigBase, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
+        else
+        {
+          const int ctxSig = sigBase + sig_ctx_inc(s->t, pat, firstSig, (int)blkPos, log2n, isChroma);
+          level = coded_level(s, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+                              ctxSig, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
+          sigRateDelta[blkPos] = ctx_bits(s, ctxSig, 1) - ctx_bits(s, ctxSig, 0);
+        }
+        deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
+        if (level > 0)
+        {
+          const int rateNow = ic_rate(s, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
+          rateIncUp[blkPos] = ic_rate(s, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+          rateIncDown[blkPos] = ic_rate(s, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+        }
+        else rateIncUp[blkPos] = ctx_bits(s, ctxOne, 0);
+        dst[blkPos] = (int32_t)level;
+        baseCost = dadd(baseCost, costCoeff[scanPos]);
+        const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
+        if ((int)level >= baseLevel)
+          if (level > 3u * (1u << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
+        if (level >= 1) c1Idx++;
+        if (level > 1) { c1 = 0; c2 += (c2 < 2); c2Idx++; }
+        else if (c1 < 3 && c1 > 0 && level) c1++;
+        if ((scanPos % 16 == 0) && scanPos > 0)
+        {
+          ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && ((scanPos - 1) >> 4) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
+          c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
+        }
+      }
+      sigCost = dadd(sigCost, costSig[scanPos]);
+      if (posInCG == 0) sigCost0 = costSig[scanPos];
+      if (dst[blkPos])
+      {
+        cgFlag[cgBlk] = 1;
+        codedLevelAndDist = dadd(codedLevelAndDist, dsub(costCoeff[scanPos], costSig[scanPos]));
+        uncodedDist = dadd(uncodedDist, costCoeff0[scanPos]);
+        if (posInCG != 0) nnzBeforePos0++;
+      }
+    }
+    if (cgLastScanPos >= 0)
+    {
+      if (cgScanPos)
+      {
+        if (cgFlag[cgBlk] == 0)
+        {
+          const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
+          baseCost = dadd(baseCost, dsub(dmul(lambda, (double)ctx_bits(s, cx, 0)), sigCost));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 0));
+        }
+        else if (cgScanPos < cgLastScanPos)
+        {
+          if (nnzBeforePos0 == 0) { baseCost = dsub(baseCost, sigCost0); sigCost = dsub(sigCost, sigCost0); }
+          double costZeroCG = baseCost;
+          const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
+          baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(s, cx, 1)));
+          costZeroCG = dadd(costZeroCG, dmul(lambda, (double)ctx_bits(s, cx, 0)));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 1));
+          costZeroCG = dadd(costZeroCG, uncodedDist);
+          costZeroCG = dsub(costZeroCG, codedLevelAndDist);
+          costZeroCG = dsub(costZeroCG, sigCost);
+          if (costZeroCG < baseCost)
+          {
+            cgFlag[cgBlk] = 0;
+            baseCost = costZeroCG;
+            costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 0));
+            for (int posInCG = 15; posInCG >= 0; posInCG--)
+            {
+              const int scanPos = cgScanPos * 16 + posInCG;
+              const uint32_t blkPos = scan[scanPos];
+              if (dst[blkPos]) { dst[blkPos] = 0; costCoeff[scanPos] = costCoeff0[scanPos]; costSig[scanPos] = 0; }
+            }
+          }
+        }
+      }
+      else cgFlag[cgBlk] = 1;
+    }
+  }
+  if (lastScanPos < 0) return 0;
+
+  double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(s, cbfCtx, 0)));
+  baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(s, cbfCtx, 1)));
+  {
+    int foundLast = 0, off, shift;
+    last_ctx_params(isChroma, log2n, &off, &shift);
+    const int bx0 = CTX_LASTX + (isChroma ? 15 : 0) + off, by0 = CTX_LASTY + (isChroma ? 15 : 0) + off, gmax = group_idx(n - 1);
+    for (int cgScanPos = cgLastScanPos; cgScanPos >= 0; cgScanPos--)
+    {
+      const int cgBlk = scanCG[cgScanPos];
+      baseCost = dsub(baseCost, costCGSig[cgScanPos]);
+      if (cgFlag[cgBlk])
+      {
+        for (int posInCG = 15; posInCG >= 0; posInCG--)
+        {
+          const int scanPos = cgScanPos * 16 + posInCG;
+          if (scanPos > lastScanPos) continue;
+          const uint32_t blkPos = scan[scanPos];
+          if (dst[blkPos])
+          {
+            const uint32_t posY = blkPos >> log2n, posX = blkPos - (posY << log2n);
+            const uint32_t lx = scanType == SCAN_VER ? posY : posX, ly = scanType == SCAN_VER ? posX : posY;
+            const int gx = group_idx((int)lx), gy = group_idx((int)ly);
+            int bx = 0, by = 0, cc;
+            for (cc = 0; cc < gx; cc++) bx += ctx_bits(s, bx0 + (cc >> shift), 1);
+            if (gx < gmax) bx += ctx_bits(s, bx0 + (gx >> shift), 0);
+            for (cc = 0; cc < gy; cc++) by += ctx_bits(s, by0 + (cc >> shift), 1);
+            if (gy < gmax) by += ctx_bits(s, by0 + (gy >> shift), 0);
+            double cost = (double)(bx + by);
+            if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
+            if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
+            const double costLast = dmul(lambda, cost);
+            const double totalCost = dsub(dadd(baseCost, costLast), costSig[scanPos]);
+            if (totalCost < bestCost) { bestLastIdxP1 = scanPos + 1; bestCost = totalCost; }
+            if (dst[blkPos] > 1) { foundLast = 1; break; }
+            baseCost = dsub(baseCost, costCoeff[scanPos]);
+            baseCost = dadd(baseCost, costCoeff0[scanPos]);
+          }
+          else baseCost = dsub(baseCost, costSig[scanPos]);
+        }
+        if (foundLast) break;
+      }
+    }
+  }
+  for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
+  {
+    const int blkPos = scan[scanPos];
+    const int32_t level = dst[blkPos];
+    absSum += (uint32_t)level;
+    dst[blkPos] = (src[blkPos] < 0) ? -level : level;
+  }
+  for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) dst[scan[scanPos]] = 0;
+
+  if (absSum >= 2)                                                             // sign bit hiding (TComTrQuant.cpp:2530)
+  {
+    const double invQ = (double)inv_quant_scale(q.rem);
+#ifdef FHC_DEVICE_BUILD
+    const double f = __dadd_rn(__ddiv_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(__dmul_rn(invQ, invQ), (double)(1 << (2 * q.per))), lambda), 16.0),
+                                         (double)(1 << (2 * (bd - 8)))), 0.5);
+#else
+    const double f = invQ * invQ * (double)(1 << (2 * q.per)) / lambda / 16 / (double)(1 << (2 * (bd - 8))) + 0.5;
+#endif
+    const int64_t rdFactor = (int64_t)f;
+    int lastCG = -1;
+    for (int subSet = (numCoef - 1) >> 4; subSet >= 0; subSet--)
+    {
+      const int subPos = subSet << 4;
+      int firstNZ = 16, lastNZ = -1, sum = 0, nn;
+      if (subPos > lastScanPos) continue;                                       // nothing coded up there (all levels are 0)
+      for (nn = 15; nn >= 0; --nn) if (dst[scan[nn + subPos]]) { lastNZ = nn; break; }
+      for (nn = 0; nn < 16; nn++) if (dst[scan[nn + subPos]]) { firstNZ = nn; break; }
+      for (nn = firstNZ; nn <= lastNZ; nn++) sum += dst[scan[nn + subPos]];
+      if (lastNZ >= 0 && lastCG == -1) lastCG = 1;
+      if (lastNZ - firstNZ >= 4)
+      {
+        const uint32_t signbit = dst[scan[subPos + firstNZ]] > 0 ? 0 : 1;
+        if (signbit != (uint32_t)(sum & 1))
+        {
+          int64_t minCostInc = INT64_MAX, curCost = INT64_MAX;
+          int minPos = -1, finalChange = 0, curChange = 0;
+          for (nn = (lastCG == 1 ? lastNZ : 15); nn >= 0; --nn)
+          {
+            const uint32_t blkPos = scan[nn + subPos];
+            if (dst[blkPos] != 0)
+            {
+              const int64_t costUp = rdFactor * (-deltaU[blkPos]) + rateIncUp[blkPos];
+              int64_t costDown = rdFactor * (deltaU[blkPos]) + rateIncDown[blkPos] - ((iabs(dst[blkPos]) == 1) ? sigRateDelta[blkPos] : 0);
+              if (lastCG == 1 && lastNZ == nn && iabs(dst[blkPos]) == 1) costDown -= (4 << 15);
+              if (costUp < costDown) { curCost = costUp; curChange = 1; }
+              else
+              {
+                curChange = -1;
+                if (nn == firstNZ && iabs(dst[blkPos]) == 1) curCost = INT64_MAX;
+                else curCost = costDown;
+              }
+            }
+            else
+            {
+              curCost = rdFactor * (-(iabs(deltaU[blkPos]))) + (1 << 15) + rateIncUp[blkPos] + sigRateDelta[blkPos];
+              curChange = 1;
+              if (nn < firstNZ)
+              {
+                const uint32_t thisSign = src[blkPos] >= 0 ? 0 : 1;
+                if (thisSign != signbit) curCost = INT64_MAX;
+              }
+            }
+            if (curCost < minCostInc) { minCostInc = curCost; finalChange = curChange; minPos = (int)blkPos; }
+          }
+          if (dst[minPos] == 32767 || dst[minPos] == -32768) finalChange = -1;
+          if (src[minPos] >= 0) dst[minPos] += finalChange; else dst[minPos] -= finalChange;
+        }
+      }
+      if (lastCG == 1) lastCG = 0;
+    }
+  }
+  return absSum;
+}
+
+// ----------------------------------------------------------------------------------------------
+// geometry helpers
+// ----------------------------------------------------------------------------------------------
+FHC_DH int rel_x(const Shared* s, int relIdx) { return (s->t.z2r[relIdx] & 15) * 4; }
+FHC_DH int rel_y(const Shared* s, int relIdx) { return (s->t.z2r[relIdx] >> 4) * 4; }
+FHC_DH CUMeta* best_cu(Shared* s, int d) { return &s->cu[d][s->bestIdx[d]]; }
+FHC_DH CUMeta* temp_cu(Shared* s, int d) { return &s->cu[d][1 - s->bestIdx[d]]; }
+FHC_DH int cu_buf_index(const Shared* s, const CUMeta* cu) { return (int)(cu - &s->cu[cu->depth][0]); }
+
+// ----------------------------------------------------------------------------------------------
+// reference samples: availability on the master, gather/substitute/filter on the workers
+// (TComPattern.cpp:115-745, TComDataCU.cpp:1090-1200)
+// ----------------------------------------------------------------------------------------------
+FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int n, int wantFilt)
+{
+  Shared* s = c.s;
+  const FrameGlobal* g = c.g;
+  const int zLT = cu->zidx + relIdx, rLT = s->t.z2r[zLT];
+  const int ux = rLT & 15, uy = rLT >> 4;
+  const int us = comp ? 2 : 4, nu = n / us, total = 4 * nu + 1;
+  uint8_t* flags = s->flags;
+  int numAvail = 0;
+  const int leftOk = (ux > 0 || s->ctuX > 0), aboveOk = (uy > 0 || s->ctuY > 0);
+  flags[2 * nu] = (uint8_t)(leftOk && aboveOk);
+  for (int i = 0; i < nu; i++) { flags[2 * nu + 1 + i] = (uint8_t)aboveOk; flags[2 * nu - 1 - i] = (uint8_t)leftOk; }
+  {
+    const int rRT = rLT + nu - 1, zRT = s->t.r2z[rRT];
+    for (int i = 1; i <= nu; i++)
+    {
+      int av;
+      if (s->ctuPelX + (rRT & 15) * 4 + 4 * i >= g->width) av = 0;
+      else if ((rRT & 15) < 16 - i) av = (uy != 0) ? (zRT > s->t.r2z[rRT - 16 + i]) : (s->ctuY > 0);
+      else if (uy != 0) av = 0;
+      else av = (s->ctuY > 0) && (s->ctuX + 1 < g->wc);
+      flags[3 * nu + i] = (uint8_t)av;
+    }
+    const int rLB = rLT + (nu - 1) * 16, zLB = s->t.r2z[rLB];
+    for (int i = 1; i <= nu; i++)
+    {
+      int av;
+      if (s->ctuPelY + (rLB >> 4) * 4 + 4 * i >= g->height) av = 0;
+      else if ((rLB >> 4) < 16 - i) av = (ux != 0) ? (zLB > s->t.r2z[rLB + 16 * i - 1]) : (s->ctuX > 0);
+      else av = 0;
+      flags[nu - i] = (uint8_t)av;
+    }
+  }
+  for (int i = 0; i < total; i++) numAvail += flags[i];
+  Cmd& m = s->cmd;
+  const int px = (s->ctuPelX + ux * 4) >> (comp ? 1 : 0), py = (s->ctuPelY + uy * 4) >> (comp ? 1 : 0);
+  m.a[0] = comp; m.a[1] = n; m.a[2] = nu; m.a[3] = us; m.a[4] = py * plane_stride(g, comp) + px; m.a[5] = wantFilt;
+  m.a[6] = numAvail; m.a[7] = total;
+  par(c, OP_REFS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// xIntraCodingTUBlock (TEncSearch.cpp:1104-1399)
+// ----------------------------------------------------------------------------------------------
+FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int log2n, int lumaLog2, int trDepthBit, int numParts,
+                             int predSaveLoad)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  const int n = 1 << log2n, isChroma = comp != 0;
+  const int cuW = cu->width >> isChroma;
+  const int bx = rel_x(s, relIdx) >> isChroma, by = rel_y(s, relIdx) >> isChroma;
+  const int qtLayer = 5 - lumaLog2;
+  const int picX = (cu->x >> isChroma) + bx, picY = (cu->y >> isChroma) + by;
+  const int stride = plane_stride(g, comp);
+  const int predOff = comp_off(comp) + by * cuW + bx;
+  const int qtOff = comp_off(comp) + by * (64 >> isChroma) + bx;
+  const int coefOff = comp_off(comp) + (isChroma ? relIdx * 4 : relIdx * 16);
+  const int ts = cu->ts[comp][relIdx];
+  const QpParam q = qp_param(c, comp);
+  int mode;
+  Cmd& m = s->cmd;
+
+  if (comp == 0) mode = cu->ldir[relIdx];
+  else
+  {
+    mode = cu->cdir[relIdx];
+    if (mode == DM_CHROMA_IDX) mode = cu->ldir[relIdx & ~3];
+  }
+  int useFilt = 0;
+  if (predSaveLoad != 2)
+  {
+    useFilt = use_filtered_refs(s->t, comp, mode, log2n);
+    build_refs(c, cu, relIdx, comp, n, useFilt);
+  }
+  m.a[0] = comp; m.a[1] = log2n; m.a[2] = mode; m.a[3] = useFilt; m.a[4] = predOff; m.a[5] = cuW;
+  m.a[6] = picY * stride + picX; m.a[7] = predSaveLoad;
+  par(c, OP_PRED_RESI);
+
+  // transform + RDOQ (TComTrQuant::transformNxN :1450)
+  s->rdoqLambda = g->sp.rdoqLambda[comp];
+  const int scanType = coef_scan_idx(cu, relIdx, n, comp);
+  m.a[0] = log2n; m.a[1] = (comp == 0 && log2n == 2); m.a[2] = ts; m.a[3] = scanType; m.a[4] = quant_scale(q.rem);
+  m.a[5] = 14 + q.per + (15 - g->bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
+  par(c, OP_FWD_QUANT);
+  const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
+  const uint32_t absSum = rdoq_pass(c, cu, relIdx, comp, log2n, cbfCtx);
+  set_range(cu->cbf[comp], relIdx, numParts, (absSum > 0 ? 1 : 0) << trDepthBit);
+
+  // levels -> QT coefficient layer
+  if (absSum > 0) { m.a[0] = n * n; m.a[1] = qtLayer; m.a[2] = coefOff; par(c, OP_LEVELS_OUT); }
+  else par_zero16(c, g->qtCoef[qtLayer] + coefOff, n * n);
+
+  // inverse + reconstruction + SSE
+  s->sse = 0;
+  m.a[0] = comp; m.a[1] = log2n; m.a[2] = (comp == 0 && log2n == 2); m.a[3] = ts; m.a[4] = absSum > 0; m.a[5] = q.per; m.a[6] = q.rem;
+  m.a[7] = predOff; m.a[8] = cuW; m.a[9] = qtLayer; m.a[10] = qtOff; m.a[11] = picY * stride + picX; m.a[12] = picY * stride + picX;
+  par(c, OP_INV_RECON);
+  uint32_t dist = s->sse;
+  if (isChroma) dist = (uint32_t)dmul(g->sp.chromaDistWeight[comp - 1], (double)dist);          // TComRdCost.cpp:352
+  return dist;
+}
+
+// ----------------------------------------------------------------------------------------------
+// search-time bit counting (TEncSearch.cpp:881-1102)
+// ----------------------------------------------------------------------------------------------
+FHC_DH int min_tu_log2_in_cu(const CUMeta* cu)                                                   // TComDataCU.cpp:1478
+{
+  const int log2Cb = ilog2(cu->width), split = cu->part[0] == SIZE_NxN;
+  if (log2Cb < 2 + 3 - 1 + split) return 2;
+  const int r = log2Cb - (3 - 1 + split);
+  return r > 5 ? 5 : r;
+}
+FHC_DH void enc_intra_header(const Ctx& c, const CUMeta* cu, int trDepth, int relIdx, int bLuma, int bChroma)
+{
+  if (bLuma)
+  {
+    if (relIdx == 0) code_part_size(c, cu, 0, cu->depth);
+    if (cu->part[0] == SIZE_2Nx2N) { if (relIdx == 0) code_luma_dir(c, cu, 0, 0); }
+    else if (trDepth > 0 && (relIdx % (cu->nparts >> 2)) == 0) code_luma_dir(c, cu, relIdx, 0);
+  }
+  if (bChroma && relIdx == 0) code_chroma_dir(c, cu, relIdx);
+}
+FHC_DH void code_qt_cbf(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int trDepth, int lowestLevel, int compLog2n)
+{
+  const int isChroma = comp != 0;
+  const int ctx = CTX_CBF + (isChroma ? 5 + trDepth : (trDepth == 0 ? 1 : 0));
+  const int lowest = trDepth + ((!lowestLevel && compLog2n < 3) ? 1 : 0);
+  enc_bin(c.s, ctx, (cu->cbf[comp][relIdxComp] >> lowest) & 1);
+}
+FHC_D void enc_subdiv_cbf(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int chromaCodeAll, int bLuma, int bChroma)
+{
+  const int subdiv = cu->tridx[relIdx] > trDepth;
+  if (cu->part[0] == SIZE_NxN && trDepth == 0) { }
+  else if (log2n > 5) { }
+  else if (log2n == 2) { }
+  else if (log2n == min_tu_log2_in_cu(cu)) { }
+  else if (bLuma) enc_bin(c.s, CTX_SUBDIV + (5 - log2n), subdiv);
+  if (bChroma)
+    for (int cc = 1; cc < 3; cc++)
+      if (chromaCodeAll && (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1)))
+        code_qt_cbf(c, cu, relIdx, cc, trDepth, subdiv == 0, log2n - 1);
+  if (subdiv)
+  {
+    const int q = (cu->nparts >> (2 * trDepth)) >> 2;
+    for (int i = 0; i < 4; i++) enc_subdiv_cbf(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1) > 2, bLuma, bChroma);
+  }
+  else if (bLuma) code_qt_cbf(c, cu, relIdx, 0, trDepth, 1, log2n);
+}
+FHC_D void enc_coeff_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int comp, int procChroma)
+{
+  if (cu->tridx[relIdx] > trDepth)
+  {
+    const int q = (cu->nparts >> (2 * trDepth)) >> 2;
+    for (int i = 0; i < 4; i++) enc_coeff_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, comp, (log2n - 1 > 2) ? 1 : (i == 0));
+  }
+  else if (comp == 0)
+  {
+    if ((cu->cbf[0][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, relIdx, c.g->qtCoef[5 - log2n] + relIdx * 16, log2n, 0);
+  }
+  else if (procChroma)
+  {
+    const int cl = log2n == 2 ? 2 : log2n - 1, ridx = log2n == 2 ? (relIdx & ~3) : relIdx;
+    if ((cu->cbf[comp][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, ridx, c.g->qtCoef[5 - log2n] + comp_off(comp) + ridx * 4, cl, comp);
+  }
+}
+FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int chromaCodeAll, int procChroma,
+                             int bLuma, int bChroma)
+{
+  reset_bits(c.s);
+  enc_intra_header(c, cu, trDepth, relIdx, bLuma, bChroma);
+  enc_subdiv_cbf(c, cu, relIdx, log2n, trDepth, chromaCodeAll, bLuma, bChroma);
+  if (bLuma) enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 0, procChroma);
+  if (bChroma) { enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 1, procChroma); enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 2, procChroma); }
+  return num_bits(c.s);
+}
+
+// ----------------------------------------------------------------------------------------------
+// luma RQT search (TEncSearch.cpp:1404-1713)
+// ----------------------------------------------------------------------------------------------
+FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, int checkFirst, uint32_t* distY, double* rdCost)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  const int fullDepth = cu->depth + trDepth;
+  const int numParts = cu->nparts >> (2 * trDepth);
+  const int checkFull = log2n <= 5;
+  int checkSplit = log2n > min_tu_log2_in_cu(cu);
+  double singleCost = FHC_MAX_COST;
+  uint32_t singleDist = 0, singleCbf = 0;
+  int bestModeId = 0;
+  const int checkTS = (log2n == 2) && (cu->part[relIdx] == SIZE_NxN);
+  const int layer = 5 - log2n;
+  int16_t* qtCoefBlk = g->qtCoef[layer < 0 ? 0 : layer] + relIdx * 16;
+  int16_t* qtRecBlk = g->qtRec[layer < 0 ? 0 : layer] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx);
+  int16_t* picBlk = g->rec[0] + (cu->y + rel_y(s, relIdx)) * plane_stride(g, 0) + cu->x + rel_x(s, relIdx);
+  if (checkFirst && checkFull) checkSplit = 0;
+
+  if (checkFull)
+  {
+    if (checkTS)
+    {
+      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      for (int modeId = 0; modeId < 2; modeId++)
+      {
+        double costTmp;
+        set_range(cu->ts[0], relIdx, numParts, modeId);
+        set_range(cu->tridx, relIdx, numParts, trDepth);
+        const uint32_t dTmp = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, modeId == 0 ? 1 : 2);
+        const uint32_t cbfTmp = (cu->cbf[0][relIdx] >> trDepth) & 1;
+        if (modeId == 1 && cbfTmp == 0) costTmp = FHC_MAX_COST;
+        else costTmp = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), dTmp);
+        if (costTmp < singleCost)
+        {
+          singleCost = costTmp; singleDist = dTmp; singleCbf = cbfTmp; bestModeId = modeId;
+          if (modeId == 0)
+          {
+            for (int i = 0; i < 16; i++) { s->tsCoef[0][i] = qtCoefBlk[i]; s->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
+            sb_copy(&s->slot[fullDepth][CI_TEMP_BEST], &s->go);
+          }
+        }
+        if (modeId == 0) sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+      }
+      set_range(cu->ts[0], relIdx, numParts, bestModeId);
+      if (bestModeId == 0)
+      {
+        const int ps = plane_stride(g, 0);
+        for (int i = 0; i < 16; i++)
+        {
+          qtCoefBlk[i] = s->tsCoef[0][i];
+          qtRecBlk[(i >> 2) * 64 + (i & 3)] = s->tsRec[0][i];
+          picBlk[(i >> 2) * ps + (i & 3)] = s->tsRec[0][i];
+        }
+        set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
+        sb_copy(&s->go, &s->slot[fullDepth][CI_TEMP_BEST]);
+      }
+    }
+    else
+    {
+      if (checkSplit) sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      set_range(cu->ts[0], relIdx, numParts, 0);
+      set_range(cu->tridx, relIdx, numParts, trDepth);
+      singleDist = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, 0);
+      if (checkSplit) singleCbf = (cu->cbf[0][relIdx] >> trDepth) & 1;
+      singleCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), singleDist);
+    }
+  }
+  if (checkSplit)
+  {
+    double splitCost = 0.0;
+    uint32_t splitDist = 0, splitCbf = 0;
+    const int q = numParts >> 2;
+    if (checkFull)
+    {
+      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_TEST], &s->go);
+      sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+    }
+    else sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+    for (int i = 0; i < 4; i++)
+    {
+      recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, checkFirst, &splitDist, &splitCost);
+      splitCbf |= (cu->cbf[0][relIdx + i * q] >> (trDepth + 1)) & 1;
+    }
+    if (splitCbf)
+      for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
+    sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+    splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
+    if (splitCost < singleCost)
+    {
+      *distY += splitDist;
+      *rdCost = dadd(*rdCost, splitCost);
+      return;
+    }
+    sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_TEST]);
+    set_range(cu->tridx, relIdx, numParts, trDepth);
+    set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
+    set_range(cu->ts[0], relIdx, numParts, bestModeId);
+    par_copy2d(c, picBlk, plane_stride(g, 0), qtRecBlk, 64, 1 << log2n, 1 << log2n);
+  }
+  *distY += singleDist;
+  *rdCost = dadd(*rdCost, singleCost);
+}
+
+// xSetIntraResultLumaQT (TEncSearch.cpp:1716): copy winning coefficients / reconstruction of a PU into the CU buffers
+FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth)
+{
+  Shared* s = c.s;
+  if (cu->tridx[relIdx] == trDepth)
+  {
+    const int n = 1 << log2n;
+    par_copy16(c, cuCoef + relIdx * 16, c.g->qtCoef[5 - log2n] + relIdx * 16, n * n);
+    par_copy2d(c, cuReco + rel_y(s, relIdx) * cu->width + rel_x(s, relIdx), cu->width,
+               c.g->qtRec[5 - log2n] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx), 64, n, n);
+  }
+  else
+  {
+    const int q = (cu->nparts >> (2 * trDepth)) >> 2;
+    for (int i = 0; i < 4; i++) set_luma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1);
+  }
+}
+
+// estIntraPredLumaQT (TEncSearch.cpp:2177-2557)
+FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  const int depth = cu->depth;
+  const int initTrDepth = cu->part[0] == SIZE_2Nx2N ? 0 : 1;
+  const int numPU = 1 << (2 * initTrDepth);
+  const int puParts = cu->nparts >> (2 * initTrDepth);
+  const int puSize = cu->width >> initTrDepth;
+  const int log2pu = ilog2(puSize);
+  const int ps = plane_stride(g, 0);
+  uint32_t overallDist = 0;
+
+  for (int pu = 0; pu < numPU; pu++)
+  {
+    const int partOffset = pu * puParts;
+    int numModesForFullRD = (log2pu <= 3) ? 8 : 3;                    // g_aucIntraModeNumFast_UseMPM (TComRom.cpp:545)
+    uint32_t rdModeList[12];
+    double candCost[12];
+    uint32_t bestPUMode = 0, bestPUDist = 0;
+    double bestPUCost = FHC_MAX_COST;
+    const int pox = cu->x + rel_x(s, partOffset), poy = cu->y + rel_y(s, partOffset);
+
+    // ---- rough mode decision: 35 predictions + SATD on the workers (TEncSearch.cpp:2271-2295)
+    build_refs(c, cu, partOffset, 0, puSize, 1);
+    {
+      Cmd& m = s->cmd;
+      const int mpg = imin(35, 20480 >> (2 * log2pu));
+      for (int i = 0; i < 35; i++) s->satd[i] = 0;
+      m.a[0] = log2pu; m.a[1] = poy * ps + pox; m.a[2] = mpg; m.a[15] = 2 * ((35 + mpg - 1) / mpg);
+      par(c, OP_RMD);
+    }
+    int preds[3];
+    const int numCand = get_mpm(c, cu, partOffset, preds);
+    {
+      // xModeBitsIntra (TEncSearch.cpp:5353): bin counter state + one context reloaded from CI_CURR_BEST
+      const Sbac* srcSb = &s->slot[depth][CI_CURR_BEST];
+      const uint64_t frac0 = srcSb->frac & 32767;
+      const uint8_t st = srcSb->c[CTX_IPRED];
+      for (int i = 0; i < numModesForFullRD; i++) candCost[i] = FHC_MAX_COST;
+      for (int mode = 0; mode < 35; mode++)
+      {
+        int idx = -1;
+        for (int i = 0; i < 3; i++) if (mode == preds[i]) idx = i;
+        const uint64_t frac = frac0 + (uint64_t)s->t.entropyBits[st ^ (idx != -1 ? 1 : 0)] + (uint64_t)32768 * (uint64_t)(idx != -1 ? (idx ? 2 : 1) : 5);
+        const uint32_t modeBits = (uint32_t)(frac >> 15);
+        const uint32_t sad = s->satd[mode] >> (g->bitDepth - 8);
+        const double cost = dadd((double)sad, dmul((double)modeBits, g->sp.sqrtLambda));
+        int shift = 0;                                                          // xUpdateCandList (TEncSearch.cpp:5385)
+        while (shift < numModesForFullRD && cost < candCost[numModesForFullRD - 1 - shift]) shift++;
+        if (shift != 0)
+        {
+          for (int i = 1; i < shift; i++)
+          {
+            rdModeList[numModesForFullRD - i] = rdModeList[numModesForFullRD - 1 - i];
+            candCost[numModesForFullRD - i] = candCost[numModesForFullRD - 1 - i];
+          }
+          rdModeList[numModesForFullRD - shift] = (uint32_t)mode;
+          candCost[numModesForFullRD - shift] = cost;
+        }
+      }
+    }
+    for (int j = 0; j < numCand; j++)
+    {
+      int included = 0;
+      for (int i = 0; i < numModesForFullRD; i++) included |= (preds[j] == (int)rdModeList[i]);
+      if (!included) rdModeList[numModesForFullRD++] = (uint32_t)preds[j];
+    }
+
+    // ---- full RD over the candidates, then the best mode once more with the full RQT
+    for (int i = 0; i < numModesForFullRD + 1; i++)
+    {
+      const int second = (i == numModesForFullRD);
+      const uint32_t orgMode = second ? bestPUMode : rdModeList[i];
+      uint32_t puDist = 0;
+      double puCost = 0.0;
+      set_range(cu->ldir, partOffset, puParts, (int)orgMode);
+      sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+      recur_luma_qt(c, cu, partOffset, log2pu, initTrDepth, second ? 0 : 1, &puDist, &puCost);
+      if (puCost < bestPUCost)
+      {
+        bestPUMode = orgMode; bestPUDist = puDist; bestPUCost = puCost;
+        set_luma_result(c, cu, cuCoef, cuReco, partOffset, log2pu, initTrDepth);
+        copy_bytes(s->qtTrIdx, cu->tridx + partOffset, puParts);
+        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], cu->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], cu->ts[j] + partOffset, puParts); }
+      }
+    }
+    overallDist += bestPUDist;
+    copy_bytes(cu->tridx + partOffset, s->qtTrIdx, puParts);
+    for (int j = 0; j < 3; j++) { copy_bytes(cu->cbf[j] + partOffset, s->qtCbf[j], puParts); copy_bytes(cu->ts[j] + partOffset, s->qtTs[j], puParts); }
+    if (pu != numPU - 1)
+      par_copy2d(c, g->rec[0] + poy * ps + pox, ps, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, puSize, puSize);
+    set_range(cu->ldir, partOffset, puParts, (int)bestPUMode);
+  }
+  if (numPU > 1)
+  {
+    uint32_t cY = 0, cU = 0, cV = 0;
+    for (int i = 0; i < 4; i++)
+    {
+      cY |= (cu->cbf[0][i * puParts] >> 1) & 1; cU |= (cu->cbf[1][i * puParts] >> 1) & 1; cV |= (cu->cbf[2][i * puParts] >> 1) & 1;
+    }
+    for (int i = 0; i < 4 * puParts; i++) { cu->cbf[0][i] |= (uint8_t)cY; cu->cbf[1][i] |= (uint8_t)cU; cu->cbf[2][i] |= (uint8_t)cV; }
+  }
+  sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+  cu->dist = overallDist;
+}
+
+// ----------------------------------------------------------------------------------------------
+// chroma search (TEncSearch.cpp:1915-2120, :2562-2712)
+// ----------------------------------------------------------------------------------------------
+FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, int procChroma, uint32_t* dist)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  const int numPartsLuma = cu->nparts >> (2 * trDepth);
+  if (cu->tridx[relIdx] == trDepth)
+  {
+    if (!procChroma) return;
+    const int fullDepth = cu->depth + trDepth;
+    const int stepped = (log2n == 2);
+    const int cl = stepped ? 2 : log2n - 1;
+    const int ridx = stepped ? (relIdx & ~3) : relIdx;
+    const int nparts = stepped ? numPartsLuma * 4 : numPartsLuma;
+    int checkTS = stepped;
+    if (checkTS)
+    {
+      int nb = 0;
+      for (int k = relIdx; k < relIdx + 4; k++) nb += cu->ts[0][k];
+      checkTS = nb > 0;
+    }
+    for (int cc = 1; cc < 3; cc++)
+    {
+      double singleCost = FHC_MAX_COST, costTmp = 0;
+      uint32_t singleDist = 0, singleCbf = 0;
+      int bestMode = 0, bestTS = 0, currMode = 0;
+      const int total = checkTS ? 2 : 1;
+      int16_t* qtCoefBlk = g->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4;
+      int16_t* qtRecBlk = g->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1);
+      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      for (int tsId = 0; tsId < total; tsId++)
+      {
+        const int isOne = total == 1;
+        set_range(cu->ts[cc], ridx, nparts, tsId);
+        currMode++;
+        const int isLast = currMode == total;
+        const uint32_t dTmp = code_tu_block(c, cu, ridx, cc, cl, log2n, trDepth, nparts, isOne ? 0 : (tsId == 0 ? 1 : 2));
+        const uint32_t cbfTmp = (cu->cbf[cc][ridx] >> trDepth) & 1;
+        if (tsId == 1 && cbfTmp == 0) costTmp = FHC_MAX_COST;
+        else if (!isOne)
+        {
+          reset_bits(s);                                                         // xGetIntraBitsQTChroma (TEncSearch.cpp:1094)
+          if (cbfTmp) code_coeff_nxn(c, cu, ridx, qtCoefBlk, cl, cc);
+          costTmp = rd_cost(c, num_bits(s), dTmp);
+        }
+        if (costTmp < singleCost)
+        {
+          singleCost = costTmp; singleDist = dTmp; bestTS = tsId; bestMode = currMode; singleCbf = cbfTmp;
+          if (!isOne && !isLast)
+          {
+            for (int i = 0; i < 16; i++) { s->tsCoef[cc][i] = qtCoefBlk[i]; s->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
+            sb_copy(&s->slot[fullDepth][CI_TEMP_BEST], &s->go);
+          }
+        }
+        if (!isOne && !isLast) sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+      }
+      if (bestMode < total)
+      {
+        const int ps = plane_stride(g, cc);
+        int16_t* picBlk = g->rec[cc] + ((cu->y + rel_y(s, ridx)) >> 1) * ps + ((cu->x + rel_x(s, ridx)) >> 1);
+        for (int i = 0; i < 16; i++)
+        {
+          qtCoefBlk[i] = s->tsCoef[cc][i];
+          qtRecBlk[(i >> 2) * 32 + (i & 3)] = s->tsRec[cc][i];
+          picBlk[(i >> 2) * ps + (i & 3)] = s->tsRec[cc][i];
+        }
+        set_range(cu->cbf[cc], ridx, nparts, (int)(singleCbf << trDepth));
+        sb_copy(&s->go, &s->slot[fullDepth][CI_TEMP_BEST]);
+      }
+      set_range(cu->ts[cc], ridx, nparts, bestTS);
+      *dist += singleDist;
+    }
+  }
+  else
+  {
+    uint32_t splitCbf[3] = { 0, 0, 0 };
+    const int q = numPartsLuma >> 2;
+    for (int i = 0; i < 4; i++)
+    {
+      const int childProc = (log2n - 1 > 2) ? 1 : (i == 0);
+      recur_chroma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, procChroma && childProc, dist);
+      for (int cc = 1; cc < 3; cc++) splitCbf[cc] |= (cu->cbf[cc][relIdx + i * q] >> (trDepth + 1)) & 1;
+    }
+    for (int cc = 1; cc < 3; cc++)
+      if (splitCbf[cc])
+        for (int i = 0; i < numPartsLuma; i++) cu->cbf[cc][relIdx + i] |= (uint8_t)(1 << trDepth);
+  }
+}
+FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth, int procChroma)
+{
+  Shared* s = c.s;
+  if (!procChroma) return;
+  if (cu->tridx[relIdx] == trDepth)
+  {
+    const int stepped = (log2n == 2), cl = stepped ? 2 : log2n - 1, n = 1 << cl, ridx = stepped ? (relIdx & ~3) : relIdx;
+    const int cw = cu->width >> 1;
+    for (int cc = 1; cc < 3; cc++)
+    {
+      par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, c.g->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4, n * n);
+      par_copy2d(c, cuReco + comp_off(cc) + (rel_y(s, ridx) >> 1) * cw + (rel_x(s, ridx) >> 1), cw,
+                 c.g->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1), 32, n, n);
+    }
+  }
+  else
+  {
+    const int q = (cu->nparts >> (2 * trDepth)) >> 2;
+    for (int i = 0; i < 4; i++) set_chroma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1 > 2) ? 1 : (i == 0));
+  }
+}
+FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
+{
+  Shared* s = c.s;
+  const int depth = cu->depth, nparts = cu->nparts, log2cu = ilog2(cu->width);
+  int modeList[5] = { PLANAR_IDX, VER_IDX, HOR_IDX, DC_IDX, DM_CHROMA_IDX };
+  uint32_t bestMode = 0, bestDist = 0;
+  double bestCost = FHC_MAX_COST;
+  for (int i = 0; i < 4; i++) if (modeList[i] == cu->ldir[0]) { modeList[i] = 34; break; }      // getAllowedChromaDir
+  for (int mi = 0; mi < 5; mi++)
+  {
+    uint32_t dist = 0;
+    sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+    set_range(cu->cdir, 0, nparts, modeList[mi]);
+    recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
+    sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+    const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
+    if (cost < bestCost)
+    {
+      bestCost = cost; bestDist = dist; bestMode = (uint32_t)modeList[mi];
+      set_chroma_result(c, cu, cuCoef, cuReco, 0, log2cu, 0, 1);
+      for (int cc = 1; cc < 3; cc++) { copy_bytes(s->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(s->qtTs[cc], cu->ts[cc], nparts); }
+    }
+  }
+  for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
+  set_range(cu->cdir, 0, nparts, (int)bestMode);
+  cu->dist += bestDist;
+  sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// final-syntax coding (TEncEntropy.cpp:200-448)
+// ----------------------------------------------------------------------------------------------
+FHC_D void encode_transform(const Ctx& c, const CUMeta* cu, const int16_t* coef, int relIdx, int log2n, int trDepth, int chromaCodeAll, int procChroma)
+{
+  const int subdiv = cu->tridx[relIdx] > trDepth;
+  int cbf[3];
+  for (int cc = 0; cc < 3; cc++) cbf[cc] = (cu->cbf[cc][relIdx] >> trDepth) & 1;
+  if (cu->part[relIdx] == SIZE_NxN && trDepth == 0) { }
+  else if (log2n > 5) { }
+  else if (log2n == 2) { }
+  else if (log2n == min_tu_log2_in_cu(cu)) { }
+  else enc_bin(c.s, CTX_SUBDIV + (5 - log2n), subdiv);
+  for (int cc = 1; cc < 3; cc++)
+    if (trDepth == 0 || chromaCodeAll)
+      if (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1))
+        code_qt_cbf(c, cu, relIdx, cc, trDepth, subdiv == 0, log2n - 1);
+  if (subdiv)
+  {
+    const int q = (cu->nparts >> (2 * trDepth)) >> 2;
+    for (int i = 0; i < 4; i++)
+      encode_transform(c, cu, coef, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1) > 2, (log2n - 1 > 2) ? 1 : (i == 3));
+  }
+  else
+  {
+    code_qt_cbf(c, cu, relIdx, 0, trDepth, 1, log2n);
+    if (cbf[0]) code_coeff_nxn(c, cu, relIdx, coef + relIdx * 16, log2n, 0);
+    if (procChroma)
+    {
+      const int cl = log2n == 2 ? 2 : log2n - 1, ridx = log2n == 2 ? (relIdx & ~3) : relIdx;
+      for (int cc = 1; cc < 3; cc++)
+        if (cbf[cc]) code_coeff_nxn(c, cu, ridx, coef + comp_off(cc) + ridx * 4, cl, cc);
+    }
+  }
+}
+FHC_D void encode_cu_syntax(const Ctx& c, const CUMeta* cu, const int16_t* coef)
+{
+  code_part_size(c, cu, 0, cu->depth);
+  code_luma_dir(c, cu, 0, 1);
+  code_chroma_dir(c, cu, 0);
+  encode_transform(c, cu, coef, 0, ilog2(cu->width), 0, 1, 1);
+}
+
+// ----------------------------------------------------------------------------------------------
+// CU level (TEncCu.cpp)
+// ----------------------------------------------------------------------------------------------
+FHC_D void cu_init_est(const Ctx& c, CUMeta* cu)                                                 // initEstData (TComDataCU.cpp:525)
+{
+  const int n = cu->nparts;
+  cu->cost = FHC_MAX_COST; cu->dist = 0; cu->bits = 0; cu->bins = 0;
+  set_range(cu->dep, 0, n, cu->depth); set_range(cu->tridx, 0, n, 0); set_range(cu->part, 0, n, SIZE_NONE);
+  set_range(cu->pred, 0, n, MODE_NONE); set_range(cu->ldir, 0, n, DC_IDX); set_range(cu->cdir, 0, n, 0);
+  for (int cc = 0; cc < 3; cc++) { set_range(cu->cbf[cc], 0, n, 0); set_range(cu->ts[cc], 0, n, 0); }
+  // coefficient buffers need no clearing here: every coded TU (re)writes its block, and blocks of a CU
+  // hypothesis are only read through cbf != 0 (coding) or copied as a whole after being written.
+  (void)c;
+}
+FHC_D void cu_position(const Ctx& c, CUMeta* cu, const CUMeta* parent, int partIdx, int depth)    // initSubCU (TComDataCU.cpp:575)
+{
+  cu->depth = depth; cu->nparts = parent->nparts >> 2; cu->width = 64 >> depth;
+  cu->zidx = parent->zidx + cu->nparts * partIdx;
+  cu->x = parent->x + cu->width * (partIdx & 1);
+  cu->y = parent->y + cu->width * (partIdx >> 1);
+  cu_init_est(c, cu);
+}
+FHC_D void cu_copy_part_from(const Ctx& c, CUMeta* dst, const CUMeta* src, int partIdx, int withCoef)   // copyPartFrom (TComDataCU.cpp:800)
+{
+  const int n = src->nparts, off = n * partIdx;
+  dst->cost = dadd(dst->cost, src->cost); dst->dist += src->dist; dst->bits += src->bits; dst->bins += src->bins;
+  copy_bytes(dst->part + off, src->part, n); copy_bytes(dst->pred + off, src->pred, n); copy_bytes(dst->ldir + off, src->ldir, n);
+  copy_bytes(dst->cdir + off, src->cdir, n); copy_bytes(dst->tridx + off, src->tridx, n); copy_bytes(dst->dep + off, src->dep, n);
+  for (int cc = 0; cc < 3; cc++) { copy_bytes(dst->cbf[cc] + off, src->cbf[cc], n); copy_bytes(dst->ts[cc] + off, src->ts[cc], n); }
+  if (withCoef)
+  {
+    int16_t* dc = c.g->cuCoef[dst->depth][cu_buf_index(c.s, dst)];
+    const int16_t* sc = c.g->cuCoef[src->depth][cu_buf_index(c.s, src)];
+    const int ny = src->width * src->width, nc = ny >> 2;
+    par_copy16(c, dc + partIdx * ny, sc, ny);
+    par_copy16(c, dc + 4096 + partIdx * nc, sc + 4096, nc);
+    par_copy16(c, dc + 5120 + partIdx * nc, sc + 5120, nc);
+  }
+}
+FHC_D void cu_copy_to_pic(const Ctx& c, const CUMeta* cu, int withCoef)                          // copyToPic (TComDataCU.cpp:906)
+{
+  Shared* s = c.s;
+  fhc_ctu_result* o = &c.g->out[s->ctuAddr];
+  o->totalCost = cu->cost; o->totalDist = cu->dist; o->totalBits = cu->bits; o->totalBins = cu->bins;
+  Cmd& m = s->cmd;
+  m.a[0] = cu->depth; m.a[1] = cu_buf_index(s, cu); m.a[2] = cu->zidx; m.a[3] = cu->nparts; m.a[4] = withCoef ? cu->width : 0;
+  par(c, OP_CU_TO_OUT);
+}
+FHC_D void copy_reco_to_pic(const Ctx& c, const CUMeta* cu)                                      // xCopyYuv2Pic (TEncCu.cpp:1729)
+{
+  const FrameGlobal* g = c.g;
+  const int16_t* y = g->cuReco[cu->depth][cu_buf_index(c.s, cu)];
+  for (int cc = 0; cc < 3; cc++)
+  {
+    const int sh = cc ? 1 : 0, w = cu->width >> sh, px = cu->x >> sh, py = cu->y >> sh;
+    const int cw = imin(w, (g->width >> sh) - px), ch = imin(w, (g->height >> sh) - py);
+    par_copy2d(c, g->rec[cc] + py * plane_stride(g, cc) + px, plane_stride(g, cc), y + comp_off(cc), w, cw, ch);
+  }
+}
+FHC_D void copy_reco_to_parent(const Ctx& c, const CUMeta* child, const CUMeta* parent, int partIdx)   // xCopyYuv2Tmp (TEncCu.cpp:1742)
+{
+  const int16_t* sy = c.g->cuReco[child->depth][cu_buf_index(c.s, child)];
+  int16_t* dy = c.g->cuReco[parent->depth][cu_buf_index(c.s, parent)];
+  for (int cc = 0; cc < 3; cc++)
+  {
+    const int w = child->width >> (cc ? 1 : 0), pw = parent->width >> (cc ? 1 : 0);
+    par_copy2d(c, dy + comp_off(cc) + (partIdx >> 1) * w * pw + (partIdx & 1) * w, pw, sy + comp_off(cc), w, w, w);
+  }
+}
+FHC_DH void check_best_mode(const Ctx& c, int depth)                                             // xCheckBestMode (TEncCu.cpp:1659)
+{
+  Shared* s = c.s;
+  if (temp_cu(s, depth)->cost < best_cu(s, depth)->cost)
+  {
+    s->bestIdx[depth] = (uint8_t)(1 - s->bestIdx[depth]);
+    sb_copy(&s->slot[depth][CI_NEXT_BEST], &s->slot[depth][CI_TEMP_BEST]);
+  }
+}
+FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)                            // xCheckRDCostIntra (TEncCu.cpp:1528)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  CUMeta* cu = temp_cu(s, depth);
+  const int bi = cu_buf_index(s, cu);
+  int16_t* cuCoef = g->cuCoef[depth][bi];
+  int16_t* cuReco = g->cuReco[depth][bi];
+  set_range(cu->part, 0, cu->nparts, partSize);
+  set_range(cu->pred, 0, cu->nparts, MODE_INTRA);
+  est_intra_luma(c, cu, cuCoef, cuReco);
+  par_copy2d(c, g->rec[0] + cu->y * plane_stride(g, 0) + cu->x, plane_stride(g, 0), cuReco, cu->width, cu->width, cu->width);
+  est_intra_chroma(c, cu, cuCoef, cuReco);
+  reset_bits(s);
+  encode_cu_syntax(c, cu, cuCoef);
+  sb_copy(&s->slot[depth][CI_TEMP_BEST], &s->go);
+  cu->bits = num_bits(s);
+  cu->bins = s->bins;
+  cu->cost = rd_cost(c, cu->bits, cu->dist);
+  check_best_mode(c, depth);
+}
+
+FHC_D void compress_cu(const Ctx& c, int depth)                                                  // xCompressCU (TEncCu.cpp:496-1058)
+{
+  Shared* s = c.s;
+  const FrameGlobal* g = c.g;
+  const int x = best_cu(s, depth)->x, y = best_cu(s, depth)->y, w = best_cu(s, depth)->width;
+  const int boundary = !(x + w - 1 < g->width && y + w - 1 < g->height);
+  if (!boundary)
+  {
+    cu_init_est(c, temp_cu(s, depth));
+    check_rd_cost_intra(c, depth, SIZE_2Nx2N);
+    cu_init_est(c, temp_cu(s, depth));
+    if (depth == 3)
+    {
+      check_rd_cost_intra(c, depth, SIZE_NxN);
+      cu_init_est(c, temp_cu(s, depth));
+    }
+    CUMeta* b = best_cu(s, depth);
+    sb_copy(&s->go, &s->slot[depth][CI_NEXT_BEST]);
+    reset_bits(s);
+    code_split_flag(c, b, 0, depth);
+    b->bits += num_bits(s);
+    b->bins += s->bins;
+    b->cost = rd_cost(c, b->bits, b->dist);
+    sb_copy(&s->slot[depth][CI_NEXT_BEST], &s->go);
+  }
+  if (depth < 3)
+  {
+    const int nd = depth + 1;
+    CUMeta* t = temp_cu(s, depth);
+    cu_init_est(c, t);
+    for (int i = 0; i < 4; i++)
+    {
+      cu_position(c, &s->cu[nd][0], t, i, nd);
+      cu_position(c, &s->cu[nd][1], t, i, nd);
+      if (s->cu[nd][0].x < g->width && s->cu[nd][0].y < g->height)
+      {
+        if (i == 0) sb_copy(&s->slot[nd][CI_CURR_BEST], &s->slot[depth][CI_CURR_BEST]);
+        else sb_copy(&s->slot[nd][CI_CURR_BEST], &s->slot[nd][CI_NEXT_BEST]);
+        compress_cu(c, nd);
+        cu_copy_part_from(c, t, best_cu(s, nd), i, 1);
+        copy_reco_to_parent(c, best_cu(s, nd), t, i);
+      }
+      else
+      {
+        cu_copy_to_pic(c, best_cu(s, nd), 0);
+        cu_copy_part_from(c, t, best_cu(s, nd), i, 0);
+        {
+          // initSubCU leaves zero coefficients for a sub-CU outside the picture (TComDataCU.cpp:651-660)
+          int16_t* dc = c.g->cuCoef[depth][cu_buf_index(s, t)];
+          const int ny = (w >> 1) * (w >> 1), nc = ny >> 2;
+          par_zero16(c, dc + i * ny, ny); par_zero16(c, dc + 4096 + i * nc, nc); par_zero16(c, dc + 5120 + i * nc, nc);
+        }
+      }
+    }
+    sb_copy(&s->go, &s->slot[nd][CI_NEXT_BEST]);
+    if (!boundary)
+    {
+      reset_bits(s);
+      code_split_flag(c, t, 0, depth);
+      t->bits += num_bits(s);
+      t->bins += s->bins;
+    }
+    t->cost = rd_cost(c, t->bits, t->dist);
+    sb_copy(&s->slot[depth][CI_TEMP_BEST], &s->go);
+    check_best_mode(c, depth);
+  }
+  cu_copy_to_pic(c, best_cu(s, depth), 1);
+  copy_reco_to_pic(c, best_cu(s, depth));
+}
+
+// xEncodeCU on the finished CTU (TEncCu.cpp:1124): advances the chain coder RD[0][CI_CURR_BEST]
+FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
+{
+  Shared* s = c.s;
+  const FrameGlobal* g = c.g;
+  const fhc_ctu_result* o = &g->out[s->ctuAddr];
+  const int r = s->t.z2r[zidx];
+  const int x = s->ctuPelX + (r & 15) * 4, y = s->ctuPelY + (r >> 4) * 4, w = 64 >> depth;
+  const int nparts = 256 >> (2 * depth);
+  int boundary = 0;
+  view->zidx = zidx; view->x = x; view->y = y; view->depth = depth; view->nparts = nparts; view->width = w;
+  copy_bytes(view->dep, o->depth + zidx, nparts); copy_bytes(view->part, o->partSize + zidx, nparts);
+  copy_bytes(view->pred, o->predMode + zidx, nparts); copy_bytes(view->ldir, o->lumaDir + zidx, nparts);
+  copy_bytes(view->cdir, o->chromaDir + zidx, nparts); copy_bytes(view->tridx, o->trIdx + zidx, nparts);
+  for (int cc = 0; cc < 3; cc++) { copy_bytes(view->cbf[cc], o->cbf[cc] + zidx, nparts); copy_bytes(view->ts[cc], o->transformSkip[cc] + zidx, nparts); }
+  if (x + w - 1 < g->width && y + w - 1 < g->height) code_split_flag(c, view, 0, depth);
+  else boundary = 1;
+  if ((depth < o->depth[zidx] && depth < 3) || boundary)
+  {
+    const int q = nparts >> 2;
+    for (int i = 0; i < 4; i++)
+    {
+      const int cz = zidx + i * q, cr = s->t.z2r[cz];
+      if (s->ctuPelX + (cr & 15) * 4 < g->width && s->ctuPelY + (cr >> 4) * 4 < g->height) encode_ctu_rec(c, view, cz, depth + 1);
+    }
+    return;
+  }
+  // coefficients of this CU: gather the three planes of the record into a CU-relative view (cuCoef[0][temp] is free here)
+  int16_t* cv = c.g->cuCoef[0][1 - s->bestIdx[0]];
+  par_copy16(c, cv, o->coefY + zidx * 16, w * w);
+  par_copy16(c, cv + 4096, o->coefCb + zidx * 4, (w * w) >> 2);
+  par_copy16(c, cv + 5120, o->coefCr + zidx * 4, (w * w) >> 2);
+  encode_cu_syntax(c, view, cv);
+  const int lastInCtu = ((x + w >= g->width) || (((r & 15) * 4 + w) == 64)) && ((y + w >= g->height) || (((r >> 4) * 4 + w) == 64));
+  if (lastInCtu && s->ctuAddr != g->wc * g->hc - 1) enc_trm(s, 0);                               // finishCU (TEncCu.cpp:1066)
+}
+
+// ----------------------------------------------------------------------------------------------
+// picture loop (TEncSlice::compressSlice, TEncSlice.cpp:698-983), executed by the master thread
+// ----------------------------------------------------------------------------------------------
+FHC_D void master_compress_picture(const Ctx& c)
+{
+  Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
+  sbac_reset(s, &s->slot[0][CI_CURR_BEST], g->sp.sliceQp);
+  const int numCtus = g->wc * g->hc;
+  for (int addr = 0; addr < numCtus; addr++)
+  {
+    fhc_ctu_result* o = &g->out[addr];
+    s->ctuAddr = addr; s->ctuX = addr % g->wc; s->ctuY = addr / g->wc;
+    s->ctuPelX = s->ctuX * 64; s->ctuPelY = s->ctuY * 64;
+    // initCtu (TComDataCU.cpp:422): the record doubles as the picture-level CTU
+    for (int d = 0; d < 2; d++)
+    {
+      CUMeta* cu = &s->cu[0][d];
+      cu->zidx = 0; cu->x = s->ctuPelX; cu->y = s->ctuPelY; cu->depth = 0; cu->nparts = 256; cu->width = 64;
+      cu_init_est(c, cu);
+    }
+    s->bestIdx[0] = 0;
+    {
+      // preset record: depth 0, partSize/predMode "none", lumaDir DC, everything else 0 (coefficients: zero)
+      CUMeta* cu = &s->cu[0][0];
+      Cmd& m = s->cmd;
+      par_zero16(c, o->coefY, 4096 + 1024 + 1024);
+      m.a[0] = 0; m.a[1] = 0; m.a[2] = 0; m.a[3] = 256; m.a[4] = 0;
+      set_range(cu->dep, 0, 256, 0);
+      par(c, OP_CU_TO_OUT);
+      cu_init_est(c, cu);
+    }
+    sb_copy(&s->go, &s->slot[0][CI_CURR_BEST]);
+    compress_cu(c, 0);
+    sb_copy(&s->go, &s->slot[0][CI_CURR_BEST]);
+    reset_bits(s);
+    encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
+    sb_copy(&s->slot[0][CI_CURR_BEST], &s->go);
+    par(c, OP_CTU_RECO_OUT);
+  }
+}
+
+}  // namespace fhc

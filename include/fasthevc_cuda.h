@@ -1,0 +1,114 @@
+/* fasthevc_cuda.h - C ABI of the B200 intra mode-decision engine (libfasthevc_cuda.so).
+ *
+ * This is the `source/Lib/TLibEncoderCUDA` boundary of BASELINE.json's north
+ * star: the unchanged HM/FastHEVC host (TEncTop/TEncGOP/TEncSlice, cfg parsing,
+ * bitstream writer) reaches the GPU only through these entry points.  The
+ * reference has no plugin/FFI interface for this path (everything is direct
+ * C++ member calls wired in TEncCu::init, source/Lib/TLibEncoder/TEncCu.cpp:227-243),
+ * so each entry point names the reference code it stands in for.
+ *
+ * Plain C, POD only, caller-owned host buffers, 0 = success, negative = error.
+ * One host thread per context.  See INTEGRATION.md for the TEncCu-side stub.
+ */
+#ifndef FASTHEVC_CUDA_H
+#define FASTHEVC_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHC_OK               0
+#define FHC_ERR_ARG         -1   /* bad argument / unsupported configuration */
+#define FHC_ERR_CUDA        -2   /* CUDA runtime error (no device, launch failure, ...) */
+#define FHC_ERR_STATE       -3   /* call sequence error (e.g. fetch before submit) */
+
+typedef struct fhc_ctx fhc_ctx;
+
+/* Sequence-level configuration: the subset of TEncCfg/TComSPS/TComPPS the hot
+ * path reads (reference: TEncTop::xInitSPS/xInitPPS, cfg/encoder_intra_main.cfg).
+ * Only the tool set of encoder_intra_main[10].cfg is implemented; anything
+ * else is rejected by fhc_create with FHC_ERR_ARG. */
+typedef struct fhc_seq_params
+{
+  int32_t width, height;            /* luma samples; multiples of 8 (MinCU) */
+  int32_t bitDepth;                 /* InternalBitDepth: 8 (Main) or 10 (Main10) */
+  int32_t chromaFormat;             /* must be 1 (4:2:0) */
+  int32_t ctuSize, maxCuDepth;      /* must be 64 and 4 (MaxCUWidth, MaxPartitionDepth) */
+  int32_t tuLog2Max, tuLog2Min;     /* must be 5 and 2 */
+  int32_t tuMaxDepthIntra;          /* must be 3 */
+  int32_t useRdoq, useRdoqTs;       /* must be 1, 1 */
+  int32_t useTransformSkip, useTransformSkipFast;   /* must be 1, 1 */
+  int32_t signHideFlag;             /* must be 1 */
+  int32_t strongIntraSmoothing;     /* must be 1 */
+  int32_t fastUdiUseMpm;            /* must be 1 */
+  int32_t maxFramesInFlight;        /* device buffers are sized for this many pictures per submit */
+} fhc_seq_params;
+
+/* Per-picture parameters computed by the UNCHANGED host code
+ * (TEncSlice::initEncSlice / setUpLambda, TEncSlice.cpp:112-144, :372):
+ * the doubles are passed through bit-for-bit, the device never recomputes them. */
+typedef struct fhc_slice_params
+{
+  int32_t sliceQp;
+  int32_t reserved;
+  double  lambda;                   /* TComRdCost::m_dLambda */
+  double  sqrtLambda;               /* TComRdCost::m_sqrtLambda */
+  double  chromaDistWeight[2];      /* TComRdCost::m_distortionWeight[Cb,Cr] */
+  double  rdoqLambda[3];            /* TComTrQuant::m_lambdas[Y,Cb,Cr] */
+} fhc_slice_params;
+
+/* One finished CTU = what TEncCu::compressCtu leaves behind
+ * (TComDataCU::copyToPic, TComDataCU.cpp:906-979; TEncCu::xCopyYuv2Pic, TEncCu.cpp:1729).
+ * Arrays are indexed by z-scan 4x4 partition; coefficients use HM's per-TU
+ * raster blocks at offset 16*absPartIdx (luma) / 4*absPartIdx (chroma). */
+typedef struct fhc_ctu_result
+{
+  uint8_t  depth[256], partSize[256], predMode[256], lumaDir[256], chromaDir[256], trIdx[256];
+  uint8_t  cbf[3][256], transformSkip[3][256];
+  int16_t  coefY[4096], coefCb[1024], coefCr[1024];
+  int16_t  recoY[4096], recoCb[1024], recoCr[1024];   /* pre-deblocking reconstruction; 0 outside the picture */
+  double   totalCost;
+  uint32_t totalDist, totalBits, totalBins;
+} fhc_ctu_result;
+
+/* TEncCu::create + TEncSearch::init equivalent: allocates device state. */
+int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out);
+int fhc_destroy(fhc_ctx* ctx);
+
+/* Hands n consecutive pictures (POC first_poc .. first_poc+n-1) to the device and starts
+ * their mode decision.  yuv420_planar: n pictures, each Y then Cb then Cr, sampleBytes 1 or 2
+ * (host memory).  Replaces the per-CTU calls of TEncSlice::compressSlice -> compressCtu
+ * (TEncSlice.cpp:879) for those pictures. Asynchronous. */
+int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
+                      const fhc_slice_params* per_frame);
+
+/* Blocks until picture `poc` is finished, then copies CTU `ctuRsAddr` into *out.
+ * This is the body of the replaced TEncCu::xCompressCU(depth 0) (TEncCu.cpp:496). */
+int fhc_fetch_ctu(fhc_ctx* ctx, int poc, int ctuRsAddr, fhc_ctu_result* out);
+
+/* Bulk variant: all CTUs of a picture in raster order (out has numCtus entries). */
+int fhc_fetch_picture(fhc_ctx* ctx, int poc, fhc_ctu_result* out);
+
+/* Number of CTUs per picture (TComPicSym::getNumberOfCtusInFrame). */
+int fhc_num_ctus(const fhc_ctx* ctx);
+
+/* Lambda derivation for callers without an HM host (tests, bench): identical arithmetic to
+ * TEncSlice::calculateLambda/setUpLambda for the all-intra cfg, evaluated on the host. */
+int fhc_slice_params_from_qp(int qp, fhc_slice_params* out);
+
+/* --- device-resident interface (bench `value`: inputs already in HBM) ------------------ */
+/* Device pointer to the input planes of submit slot i (layout as fhc_submit_frames). */
+int fhc_device_input(fhc_ctx* ctx, void** dptr, uint64_t* bytes);
+/* Runs the decision kernel on n pictures whose samples are already in the device input
+ * buffer; returns after the kernel finished; *kernel_ms = CUDA-event time of the launch. */
+int fhc_run_resident(fhc_ctx* ctx, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms);
+/* Last CUDA error string for diagnostics. */
+const char* fhc_last_error(void);
+/* Number of kernels launched by this library so far (bench `gpu_launches`). */
+uint64_t fhc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,28 @@
+// TEST INFRASTRUCTURE: host "emulation build" of the kernel source.
+// Compiles fasthevc_b200/csrc/fhc_core.cuh for the CPU (FHC_DEVICE_BUILD undefined): the master code runs as an
+// ordinary function and every worker phase is executed for all FHC_NWORK virtual workers in turn.  This checks the
+// kernel's logic (partitioning of the parallel phases, buffer layouts, decision code) against the oracle without a
+// GPU.  It is built only by the tests into tests/_build/ and is never part of libfasthevc_cuda.so.
+#include <stdlib.h>
+#include "../fasthevc_b200/csrc/fhc_tables.h"
+
+extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                        const void* y, const void* cb, const void* cr, fhc_ctu_result* out)
+{
+  using namespace fhc;
+  FrameGlobal* g = (FrameGlobal*)calloc(1, sizeof(FrameGlobal));
+  Shared* s = (Shared*)calloc(1, sizeof(Shared));
+  build_tables(&s->t, bitDepth);
+  g->org[0] = y; g->org[1] = cb; g->org[2] = cr;
+  g->width = width; g->height = height; g->bitDepth = bitDepth; g->sampleBytes = sampleBytes;
+  g->wc = (width + 63) / 64; g->hc = (height + 63) / 64;
+  g->sp = *sp;
+  g->out = out;
+  for (int c = 0; c < 3; c++) g->rec[c] = (int16_t*)calloc((size_t)(width * height) >> (c ? 2 : 0), sizeof(int16_t));
+  Ctx ctx = { g, s };
+  master_compress_picture(ctx);
+  for (int c = 0; c < 3; c++) free(g->rec[c]);
+  free(g); free(s);
+  return 0;
+}
+extern "C" int fhc_emu_shared_bytes() { return (int)sizeof(fhc::Shared); }

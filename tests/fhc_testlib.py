@@ -148,3 +148,58 @@ def compare_ctus(got, ref, what="", coef_from_dump=True):
             if not ok:
                 bad.append("%s ctu %d field %s" % (what, i, f))
     return bad
+
+
+# --- C-ABI structs (include/fasthevc_cuda.h) -------------------------------------------------
+class FhcSliceParams(C.Structure):
+    _fields_ = [("sliceQp", C.c_int32), ("reserved", C.c_int32), ("lambda_", C.c_double), ("sqrtLambda", C.c_double),
+                ("chromaDistWeight", C.c_double * 2), ("rdoqLambda", C.c_double * 3)]
+
+
+class FhcSeqParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitDepth", "chromaFormat", "ctuSize", "maxCuDepth", "tuLog2Max",
+                                         "tuLog2Min", "tuMaxDepthIntra", "useRdoq", "useRdoqTs", "useTransformSkip",
+                                         "useTransformSkipFast", "signHideFlag", "strongIntraSmoothing", "fastUdiUseMpm",
+                                         "maxFramesInFlight")]
+
+
+def slice_params_from_hm(p):
+    sp = FhcSliceParams()
+    sp.sliceQp = p.qp
+    sp.lambda_, sp.sqrtLambda = p.lambda_, p.sqrtLambda
+    sp.chromaDistWeight[0], sp.chromaDistWeight[1] = p.distWeight[1], p.distWeight[2]
+    for i in range(3):
+        sp.rdoqLambda[i] = p.rdoqLambda[i]
+    return sp
+
+
+def build_emu():
+    """Host emulation build of the kernel source (tests only)."""
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "fhc_emu.so")
+    srcs = [os.path.join(ROOT, "tests", "emu_harness.cpp"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_core.cuh"),
+            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_tables.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, srcs[0], "-lm"])
+    return so
+
+
+_emu = None
+
+
+def emu_compress(params, y, u, v):
+    global _emu
+    if _emu is None:
+        _emu = C.CDLL(build_emu())
+        _emu.fhc_emu_compress_picture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(FhcSliceParams), C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    sb = 1 if params.bitDepth == 8 else 2
+    dt = np.uint8 if sb == 1 else np.uint16
+    planes = [np.ascontiguousarray(p, dtype=dt) for p in (y, u, v)]
+    out = np.zeros(n_ctus(params.width, params.height), CTU_OUT_DT)
+    sp = slice_params_from_hm(params)
+    rc = _emu.fhc_emu_compress_picture(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
+                                       planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out
