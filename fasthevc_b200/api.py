@@ -1,0 +1,173 @@
+"""ctypes mirror of include/fasthevc_cuda.h (the TLibEncoderCUDA boundary)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++14",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class FhcError(RuntimeError):
+    pass
+
+
+class SliceParams(C.Structure):
+    """fhc_slice_params: per-picture lambdas computed by the unchanged host (TEncSlice.cpp:112-144)."""
+    _fields_ = [("sliceQp", C.c_int32), ("reserved", C.c_int32), ("lambda_", C.c_double), ("sqrtLambda", C.c_double),
+                ("chromaDistWeight", C.c_double * 2), ("rdoqLambda", C.c_double * 3)]
+
+
+class SeqParams(C.Structure):
+    """fhc_seq_params."""
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitDepth", "chromaFormat", "ctuSize", "maxCuDepth", "tuLog2Max",
+                                         "tuLog2Min", "tuMaxDepthIntra", "useRdoq", "useRdoqTs", "useTransformSkip",
+                                         "useTransformSkipFast", "signHideFlag", "strongIntraSmoothing", "fastUdiUseMpm",
+                                         "maxFramesInFlight")]
+
+
+# fhc_ctu_result
+CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("predMode", "u1", 256), ("lumaDir", "u1", 256),
+                             ("chromaDir", "u1", 256), ("trIdx", "u1", 256), ("cbf", "u1", (3, 256)), ("tskip", "u1", (3, 256)),
+                             ("coefY", "<i2", 4096), ("coefCb", "<i2", 1024), ("coefCr", "<i2", 1024),
+                             ("recoY", "<i2", 4096), ("recoCb", "<i2", 1024), ("recoCr", "<i2", 1024),
+                             ("totalCost", "<f8"), ("totalDist", "<u4"), ("totalBits", "<u4"), ("totalBins", "<u4")], align=True)
+
+EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
+           "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
+           "fhc_last_error", "fhc_launch_count"]
+
+
+def library_path():
+    return os.path.join(_HERE, "libfasthevc_cuda.so")
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compiles for sm_100a; the .so stays in-tree (git-ignored) and travels with the snapshot."""
+    so = library_path()
+    srcs = [os.path.join(_CSRC, f) for f in ("fasthevc_cuda.cu", "fhc_core.cuh", "fhc_tables.h")]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "fasthevc_cuda.h"))
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
+        return so
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", so, srcs[0]]
+    subprocess.check_call(cmd)
+    return so
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libfasthevc_cuda.so; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = library_path()
+    if not os.path.exists(so):
+        raise FhcError("libfasthevc_cuda.so is missing: run __graft_entry__.build() (nvcc) first; there is no CPU path")
+    lib = C.CDLL(so)
+    lib.fhc_create.argtypes = [C.POINTER(SeqParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.fhc_destroy.argtypes = [C.c_void_p]
+    lib.fhc_submit_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams)]
+    lib.fhc_fetch_ctu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.fhc_fetch_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.fhc_num_ctus.argtypes = [C.c_void_p]
+    lib.fhc_slice_params_from_qp.argtypes = [C.c_int, C.POINTER(SliceParams)]
+    lib.fhc_device_input.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.fhc_run_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceParams), C.POINTER(C.c_float)]
+    lib.fhc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    lib.fhc_host_free.argtypes = [C.c_void_p]
+    lib.fhc_last_error.restype = C.c_char_p
+    lib.fhc_launch_count.restype = C.c_uint64
+    _lib = lib
+    return lib
+
+
+def slice_params_from_qp(qp):
+    sp = SliceParams()
+    rc = load_library().fhc_slice_params_from_qp(int(qp), C.byref(sp))
+    if rc != 0:
+        raise FhcError("fhc_slice_params_from_qp(%d) -> %d" % (qp, rc))
+    return sp
+
+
+class Encoder:
+    """One fhc_ctx: the mode-decision engine for one sequence geometry on one device."""
+
+    def __init__(self, width, height, bit_depth=8, max_frames=1, device=0):
+        self.lib = load_library()
+        sq = SeqParams(width, height, bit_depth, 1, 64, 4, 5, 2, 3, 1, 1, 1, 1, 1, 1, 1, max_frames)
+        self.seq = sq
+        self.ctx = C.c_void_p()
+        self._check(self.lib.fhc_create(C.byref(sq), device, C.byref(self.ctx)), "fhc_create")
+        self.num_ctus = self.lib.fhc_num_ctus(self.ctx)
+        self.sample_bytes = 1 if bit_depth == 8 else 2
+        self.frame_samples = width * height * 3 // 2
+        self._pinned = []
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise FhcError("%s failed (%d): %s" % (what, rc, (self.lib.fhc_last_error() or b"").decode()))
+
+    def close(self):
+        if self.ctx:
+            for p in self._pinned:
+                self.lib.fhc_host_free(p)
+            self._pinned = []
+            self.lib.fhc_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pinned_array(self, shape, dtype):
+        """numpy view on page-locked host memory (cudaHostAlloc)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self.lib.fhc_host_alloc(C.byref(p), n), "fhc_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    @staticmethod
+    def pack_frames(Y, U, V):
+        """(n,H,W),(n,H/2,W/2)x2 -> one planar 4:2:0 buffer, picture after picture."""
+        n = Y.shape[0]
+        return np.concatenate([Y.reshape(n, -1), U.reshape(n, -1), V.reshape(n, -1)], axis=1)
+
+    def submit(self, yuv, slice_params, first_poc=0):
+        """yuv: contiguous (n, frame_samples) uint8/uint16 host array; slice_params: list of SliceParams."""
+        n = len(slice_params)
+        arr = (SliceParams * n)(*slice_params)
+        assert yuv.flags["C_CONTIGUOUS"] and yuv.dtype.itemsize == self.sample_bytes and yuv.size == n * self.frame_samples
+        self._check(self.lib.fhc_submit_frames(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr), "fhc_submit_frames")
+
+    def fetch_picture(self, poc, out=None):
+        if out is None:
+            out = np.zeros(self.num_ctus, CTU_RESULT_DTYPE)
+        self._check(self.lib.fhc_fetch_picture(self.ctx, poc, out.ctypes.data), "fhc_fetch_picture")
+        return out
+
+    def fetch_ctu(self, poc, addr):
+        out = np.zeros(1, CTU_RESULT_DTYPE)
+        self._check(self.lib.fhc_fetch_ctu(self.ctx, poc, addr, out.ctypes.data), "fhc_fetch_ctu")
+        return out[0]
+
+    def device_input_ptr(self):
+        p, b = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.fhc_device_input(self.ctx, C.byref(p), C.byref(b)), "fhc_device_input")
+        return p.value, b.value
+
+    def run_resident(self, slice_params):
+        n = len(slice_params)
+        arr = (SliceParams * n)(*slice_params)
+        ms = C.c_float()
+        self._check(self.lib.fhc_run_resident(self.ctx, n, self.sample_bytes, arr, C.byref(ms)), "fhc_run_resident")
+        return ms.value

@@ -21,10 +21,12 @@
 #include "../../include/fasthevc_cuda.h"
 
 #ifdef FHC_DEVICE_BUILD
+#define FHC_HD __host__ __device__ __forceinline__
 #define FHC_DH __device__ __forceinline__
 #define FHC_D __device__
 #define FHC_NOINLINE __device__ __noinline__
 #else
+#define FHC_HD static inline
 #define FHC_DH static inline
 #define FHC_D static
 #define FHC_NOINLINE static
@@ -70,7 +72,7 @@ struct Tables
   uint8_t  intraFilterThr[5];
   double   errScale[2][4][6];     // [chType][log2-2][qp rem]
 };
-FHC_DH int cg_off(int l) { return l == 0 ? 0 : (l == 1 ? 1 : (l == 2 ? 5 : 21)); }
+FHC_HD int cg_off(int l) { return l == 0 ? 0 : (l == 1 ? 1 : (l == 2 ? 5 : 21)); }
 
 struct Sbac { uint8_t c[NUM_CTX]; uint64_t frac; };
 

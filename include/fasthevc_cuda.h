@@ -103,6 +103,9 @@ int fhc_device_input(fhc_ctx* ctx, void** dptr, uint64_t* bytes);
 /* Runs the decision kernel on n pictures whose samples are already in the device input
  * buffer; returns after the kernel finished; *kernel_ms = CUDA-event time of the launch. */
 int fhc_run_resident(fhc_ctx* ctx, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms);
+/* Page-locked host buffers for submit/fetch (optional; any host memory works). */
+int fhc_host_alloc(void** p, uint64_t bytes);
+int fhc_host_free(void* p);
 /* Last CUDA error string for diagnostics. */
 const char* fhc_last_error(void);
 /* Number of kernels launched by this library so far (bench `gpu_launches`). */
