@@ -9,11 +9,12 @@
 #include "fhc_tables.h"
 
 using namespace fhc;
+extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 
 // ----------------------------------------------------------------------------------------------
 // kernel: one block per picture; thread 0 = master, lanes 1..31 of warp 0 retire, warps 1.. = workers
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 + FHC_NWORK) fhc_compress_pictures_kernel(FrameGlobal* frames, const Tables* tables)
+__global__ void __launch_bounds__(32 + FHC_NWORK, 2) fhc_compress_pictures_kernel(FrameGlobal* frames, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared* s = reinterpret_cast<Shared*>(smem_raw);
@@ -23,14 +24,15 @@ __global__ void __launch_bounds__(32 + FHC_NWORK) fhc_compress_pictures_kernel(F
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s->t);
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
   }
+  if (threadIdx.x == 0) init_engines(g, s);
   __syncthreads();
   if (threadIdx.x >= 1 && threadIdx.x < 32) return;      // exited threads are not counted by later barriers
   Ctx c;
-  c.g = g; c.s = s;
+  c.g = g; c.s = s; c.e = &s->master;
   if (threadIdx.x == 0)
   {
     master_compress_picture(c);
-    s->cmd.op = OP_EXIT;
+    s->master.cmd.op = OP_EXIT;
     bar_all();
   }
   else
@@ -39,13 +41,29 @@ __global__ void __launch_bounds__(32 + FHC_NWORK) fhc_compress_pictures_kernel(F
     for (;;)
     {
       bar_all();
-      const int op = s->cmd.op;
+      const int op = s->master.cmd.op;
       if (op == OP_EXIT) break;
-      const int np = (op == OP_RMD) ? s->cmd.a[15] : num_phases(op);
-      for (int ph = 0; ph < np; ph++)
+      if (op == OP_TASKS)
       {
-        run_phase(c, op, ph, w, FHC_NWORK);
-        if (ph + 1 < np) bar_workers();
+        // every worker warp is an engine: lane 0 walks the candidate's decision code, lanes 1..31 run its sample phases
+        const int wi = w >> 5, lane = w & 31;
+        for (int t = wi; t < s->task.numTasks; t += FHC_NENG)
+        {
+          Ctx ec;
+          ec.g = g; ec.s = s; ec.e = &s->eng[wi];
+          if (lane == 0) { run_task(g, s, wi, t); engine_lanes_release(ec); }
+          else engine_lanes_loop(ec, lane);
+        }
+        __syncwarp();
+      }
+      else
+      {
+        const int np = (op == OP_RMD) ? s->master.cmd.a[15] : num_phases(op);
+        for (int ph = 0; ph < np; ph++)
+        {
+          run_phase(c, op, ph, w, FHC_NWORK);
+          if (ph + 1 < np) bar_workers();
+        }
       }
       bar_all();
     }
@@ -168,6 +186,7 @@ static int launch(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params* sp
   }
   CK(cudaMemcpy2DAsync(c->dFrames, sizeof(FrameGlobal), c->hostHeaders.data(), c->headerBytes, c->headerBytes, (size_t)n,
                        cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemset2DAsync(reinterpret_cast<unsigned char*>(c->dFrames) + offsetof(FrameGlobal, prof), sizeof(FrameGlobal), 0, 32 * sizeof(long long), (size_t)n, c->stream));
   CK(cudaEventRecord(c->evStart, c->stream));
   fhc_compress_pictures_kernel<<<n, 32 + FHC_NWORK, sizeof(Shared), c->stream>>>(c->dFrames, c->dTables);
   CK(cudaGetLastError());
@@ -255,5 +274,14 @@ int fhc_host_alloc(void** p, uint64_t bytes)
 int fhc_host_free(void* p)
 {
   CK(cudaFreeHost(p));
+  return FHC_OK;
+}
+
+// debug: cycle counters of picture `slot` (FHC_PROFILE builds; zeros otherwise)
+int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
+{
+  if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
+  CK(cudaMemcpy(cycles16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, profN), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return FHC_OK;
 }

@@ -47,7 +47,7 @@ enum {
   CTX_LASTX = 68, CTX_LASTY = 98, CTX_ONE = 128, CTX_ABS = 152, CTX_TS = 158, NUM_CTX = 160
 };
 #define FHC_MAX_COST 1.7e+308
-#define FHC_NWORK 128            /* worker threads per block (4 warps) */
+#define FHC_NWORK 320            /* worker threads per block (10 warps); lane 0 of each warp doubles as a thread engine */
 
 // layout of the 6144-sample "YUV" buffers: Y at 0, Cb at 4096, Cr at 5120
 FHC_DH int comp_off(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
@@ -84,6 +84,18 @@ struct CUMeta
   uint8_t dep[256], part[256], pred[256], ldir[256], cdir[256], tridx[256], cbf[3][256], ts[3][256];
 };
 
+#define FHC_NENG (FHC_NWORK / 32)   /* thread engines = lane 0 of every worker warp */
+#define FHC_ENG_COEFS 64           /* thread engines handle blocks up to 8x8 */
+
+// private global scratch of one thread engine (same layouts as the master's buffers)
+struct EngineGlobal
+{
+  int16_t predYuv[6144];
+  int16_t qtRec[4][6144];
+  int16_t qtCoef[4][6144];
+  CUMeta cu;
+};
+
 // per-picture state in global memory
 struct FrameGlobal
 {
@@ -97,12 +109,19 @@ struct FrameGlobal
   int16_t predYuv[6144];          // prediction -> reconstruction scratch of the CU under test
   int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
   int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
+  // RDOQ per-coefficient state of the master (up to 32x32); L1-resident
+  double rdCost0[1024], rdCostCoeff[1024], rdCostSig[1024];
+  int32_t rdRateIncUp[1024], rdRateIncDown[1024], rdSigRateDelta[1024], rdDeltaU[1024];
+  EngineGlobal eng[FHC_NENG];
+  long long prof[16], profN[16];  // cycle counters of the master thread (FHC_PROFILE builds)
 };
 
 enum Op {
   OP_EXIT = 0, OP_REFS, OP_RMD, OP_PRED_RESI, OP_FWD_QUANT, OP_LEVELS_OUT, OP_INV_RECON, OP_COPY2D, OP_COPY16, OP_ZERO16,
-  OP_CTU_RECO_OUT, OP_CU_TO_OUT
+  OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_TASKS
 };
+enum { ENG_MASTER = 0, ENG_THREAD = 1 };
+enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1 };
 
 struct Cmd
 {
@@ -112,40 +131,85 @@ struct Cmd
   void* dst;
 };
 
+// One evaluation engine: the master (kind ENG_MASTER: parallel phases go to the block's workers) or a thread engine
+// (kind ENG_THREAD: lane 0 of a worker warp evaluating one independent candidate on private scratch, phases run inline).
+struct Engine
+{
+  int kind;
+  uint32_t bins, sse;
+  int refDc;
+  double rdoqLambda;
+  const Tables* t;
+  Sbac go;
+  Sbac* slots;                    // master: [5][CI_NUM]; thread engine: [CI_NUM] shared by all depths
+  Cmd cmd;
+  int16_t *refU, *refF;
+  uint8_t* flags;
+  int16_t* resi;
+  int32_t *tmp, *tcoef, *lvlD;
+  double *cost0, *costCoeff, *costSig;
+  int32_t *rateIncUp, *rateIncDown, *sigRateDelta, *deltaU;
+  int16_t tsCoef[3][16], tsRec[3][16], tsPred[3][16];
+  int16_t* predYuv;
+  int16_t (*qtRec)[6144];
+  int16_t (*qtCoef)[6144];
+  int writePic;                   // reconstruct into the picture plane too (master only)
+  // task result (thread engines)
+  double resCost;
+  uint32_t resDist;
+};
+
+struct EngineShared                // shared-memory arrays of one thread engine
+{
+  Sbac slots[3];                  // CI_QT_TRAFO_ROOT, CI_TEMP_BEST, CI_QT_TRAFO_TEST
+  int16_t refU[36], refF[36];
+  uint8_t flags[24];
+  int16_t resi[FHC_ENG_COEFS];
+  int32_t tmp[FHC_ENG_COEFS], tcoef[FHC_ENG_COEFS], lvlD[FHC_ENG_COEFS];
+  double cost0[FHC_ENG_COEFS], costCoeff[FHC_ENG_COEFS], costSig[FHC_ENG_COEFS];
+  int32_t rateIncUp[FHC_ENG_COEFS], rateIncDown[FHC_ENG_COEFS], sigRateDelta[FHC_ENG_COEFS], deltaU[FHC_ENG_COEFS];
+};
+
+struct TaskDesc
+{
+  int kind, numTasks;
+  int depth, bufIdx;              // the CU under test: s->cu[depth][bufIdx]
+  int partOffset, log2pu, initTrDepth;
+  int mode[12];
+};
+
 struct Shared
 {
   Tables t;
-  Sbac go;
   Sbac slot[5][CI_NUM];
-  uint32_t bins;
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
   uint8_t bestIdx[4];
   CUMeta cu[4][2];
-  Cmd cmd;
+  Engine master;
+  Engine eng[FHC_NENG];
+  EngineShared engSh[FHC_NENG];
+  TaskDesc task;
+  // master scratch
   int16_t refU[260], refF[260];
   uint8_t flags[72];
-  int refDc;
   int16_t resi[1024];
-  int32_t tmp[1024];              // transform stage buffer / level scratch
-  int32_t tcoef[1024];            // transform coefficients (raster)
-  int32_t lvlD[1024];             // RDOQ: lLevelDouble per scan position
-  union
-  {
-    struct
-    {
-      double cost0[1024], costCoeff[1024], costSig[1024];
-      int32_t rateIncUp[1024], rateIncDown[1024], sigRateDelta[1024], deltaU[1024];
-    } rd;
-    int16_t rmdPred[20480];
-  } u;
+  int32_t tmp[1024], tcoef[1024], lvlD[1024];
+  int16_t rmdPred[4096];
   uint32_t satd[36];
-  uint32_t sse;
-  int16_t tsCoef[3][16], tsRec[3][16], tsPred[3][16];
   uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];
-  double rdoqLambda;
 };
 
-struct Ctx { FrameGlobal* g; Shared* s; };
+struct Ctx { FrameGlobal* g; Shared* s; Engine* e; };
+
+#if defined(FHC_DEVICE_BUILD) && defined(FHC_PROFILE)
+#define FHC_TIC(k) const long long tic_##k = clock64()
+#define FHC_TOC2(c, nm, k) do { if ((c).e->kind == ENG_MASTER) { const volatile int fence_ = *(volatile int*)&(c).e->cmd.op; (void)fence_; (c).g->prof[k] += clock64() - tic_##nm; (c).g->profN[k]++; } } while (0)
+#else
+#define FHC_TIC(k) do { } while (0)
+#define FHC_TOC2(c, nm, k) do { } while (0)
+#endif
+enum { PF_TOTAL = 0, PF_PAR, PF_RDOQ, PF_COEFBITS, PF_REFS_MASTER, PF_RMD_MASTER, PF_TUBLOCK, PF_BITSQT, PF_CUCOPY, PF_RMD_PAR, PF_ENCODE, PF_TASKS_LUMA, PF_TASKS_CHROMA, PF_LUMA, PF_CHROMA, PF_NUM = 16 };
+
 
 // ----------------------------------------------------------------------------------------------
 // portability layer: barriers and the command hand-off
@@ -169,15 +233,57 @@ FHC_DH void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(FHC_NWORK) : "m
 // master side: publish the command, release the workers, wait for completion
 FHC_DH void par(const Ctx& c, int op)
 {
-  c.s->cmd.op = op;
+  if (c.e->kind == ENG_THREAD)
+  {
+    // warp engine: lane 0 (here) publishes the command, lanes 1..31 (engine_lanes_loop) join the phases
+    c.e->cmd.op = op;
+    __syncwarp();
+    const int np = num_phases(op);
+    for (int ph = 0; ph < np; ph++)
+    {
+      run_phase(c, op, ph, 0, 32);
+      if (ph + 1 < np) __syncwarp();
+    }
+    __syncwarp();
+    return;
+  }
+  FHC_TIC(par);
+  c.e->cmd.op = op;
   bar_all();
   bar_all();
+  FHC_TOC2(c, par, PF_PAR);
 }
+// lanes 1..31 of a warp whose lane 0 runs a task
+FHC_DH void engine_lanes_loop(const Ctx& c, int lane)
+{
+  for (;;)
+  {
+    __syncwarp();
+    const int op = c.e->cmd.op;
+    if (op == OP_EXIT) break;
+    const int np = num_phases(op);
+    for (int ph = 0; ph < np; ph++)
+    {
+      run_phase(c, op, ph, lane, 32);
+      if (ph + 1 < np) __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+FHC_DH void engine_lanes_release(const Ctx& c) { c.e->cmd.op = OP_EXIT; __syncwarp(); }
 #else
+FHC_D void run_tasks_emu(const Ctx& c);
 FHC_DH void par(const Ctx& c, int op)
 {
-  c.s->cmd.op = op;
-  const int np = (op == OP_RMD) ? c.s->cmd.a[15] : num_phases(op);
+  if (c.e->kind == ENG_THREAD)
+  {
+    const int np = num_phases(op);
+    for (int ph = 0; ph < np; ph++) run_phase(c, op, ph, 0, 1);
+    return;
+  }
+  c.e->cmd.op = op;
+  if (op == OP_TASKS) { run_tasks_emu(c); return; }
+  const int np = (op == OP_RMD) ? c.e->cmd.a[15] : num_phases(op);
   for (int ph = 0; ph < np; ph++)
     for (int w = 0; w < FHC_NWORK; w++) run_phase(c, op, ph, w, FHC_NWORK);
 }
@@ -305,7 +411,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
 {
   FrameGlobal* g = c.g;
   Shared* s = c.s;
-  const int* a = s->cmd.a;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
   switch (op)
   {
   case OP_REFS:
@@ -326,15 +433,15 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         else
         {
           int src = i;
-          if (!s->flags[uidx])
+          if (!e->flags[uidx])
           {
             int j = uidx - 1;
-            while (j >= 0 && !s->flags[j]) j--;
+            while (j >= 0 && !e->flags[j]) j--;
             if (j >= 0) src = j < 2 * nu ? (j * us + us - 1) : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us + us - 1);
             else
             {
               j = uidx + 1;
-              while (j < total && !s->flags[j]) j++;
+              while (j < total && !e->flags[j]) j++;
               src = j < 2 * nu ? j * us : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us);
             }
           }
@@ -342,18 +449,18 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           else if (src == 2 * n) v = origin[-stride - 1];
           else v = origin[-stride + (src - 2 * n - 1)];
         }
-        s->refU[i] = (int16_t)v;
+        e->refU[i] = (int16_t)v;
       }
     }
     else
     {
       // DC value of the unfiltered line + optional smoothing (TComPattern.cpp:191-296)
-      const int16_t* line = s->refU;
+      const int16_t* line = e->refU;
       if (w == 0)
       {
         int sum = 0;
         for (int i = 0; i < n; i++) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
-        s->refDc = (sum + n) / (n + n);
+        e->refDc = (sum + n) / (n + n);
       }
       if (a[5])
       {
@@ -376,7 +483,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
             else v = (((2 * n - (i - 2 * n)) * tl) + ((i - 2 * n) * tr) + n) >> shift;
           }
           else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
-          s->refF[i] = (int16_t)v;
+          e->refF[i] = (int16_t)v;
         }
       }
     }
@@ -394,8 +501,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
         const int x = sidx & (n - 1), y = sidx >> log2n;
-        const int16_t* line = use_filtered_refs(s->t, 0, mode, log2n) ? s->refF : s->refU;
-        s->u.rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, g->bitDepth, s->refDc);
+        const int16_t* line = use_filtered_refs(s->t, 0, mode, log2n) ? e->refF : e->refU;
+        s->rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, g->bitDepth, e->refDc);
       }
     }
     else
@@ -410,7 +517,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           int m[64];
           for (int yy = 0; yy < 8; yy++)
             for (int xx = 0; xx < 8; xx++)
-              m[yy * 8 + xx] = org_at(g, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->u.rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
+              m[yy * 8 + xx] = org_at(g, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
           atomic_add_u32(&s->satd[m0 + mi], had8(m));
         }
       }
@@ -420,7 +527,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         {
           int d[16];
           for (int yy = 0; yy < 4; yy++)
-            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, 0, a[1] + yy * stride + xx) - s->u.rmdPred[mi * 16 + yy * 4 + xx];
+            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, 0, a[1] + yy * stride + xx) - s->rmdPred[mi * 16 + yy * 4 + xx];
           atomic_add_u32(&s->satd[m0 + mi], had4(d));
         }
       }
@@ -432,21 +539,21 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     // a0 comp, a1 log2n, a2 mode, a3 useFilt, a4 offset into predYuv, a5 stride in predYuv, a6 org plane offset,
     // a7 save/load (0 none, 1 save to tsPred, 2 load from tsPred)
     const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n;
-    int16_t* pred = g->predYuv + a[4];
+    int16_t* pred = e->predYuv + a[4];
     const int ps = a[5], stride = plane_stride(g, comp);
-    const int16_t* line = a[3] ? s->refF : s->refU;
+    const int16_t* line = a[3] ? e->refF : e->refU;
     for (int i = w; i < n2; i += nw)
     {
       const int x = i & (n - 1), y = i >> log2n;
       int v;
-      if (a[7] == 2) v = s->tsPred[comp][i];
+      if (a[7] == 2) v = e->tsPred[comp][i];
       else
       {
-        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, g->bitDepth, s->refDc);
-        if (a[7] == 1) s->tsPred[comp][i] = (int16_t)v;
+        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, g->bitDepth, e->refDc);
+        if (a[7] == 1) e->tsPred[comp][i] = (int16_t)v;
       }
       pred[y * ps + x] = (int16_t)v;
-      s->resi[i] = (int16_t)(org_at(g, comp, a[6] + y * stride + x) - v);
+      e->resi[i] = (int16_t)(org_at(g, comp, a[6] + y * stride + x) - v);
     }
     break;
   }
@@ -460,7 +567,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       if (phase == 1)
       {
         const int shift = 15 - bd - log2n;
-        for (int i = w; i < n2; i += nw) s->tcoef[i] = (int32_t)s->resi[i] << shift;
+        for (int i = w; i < n2; i += nw) e->tcoef[i] = (int32_t)e->resi[i] << shift;
       }
     }
     else if (phase == 0)
@@ -471,8 +578,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
         int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * s->resi[j * n + q];
-        s->tmp[i] = (acc + add1) >> shift1;
+        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * e->resi[j * n + q];
+        e->tmp[i] = (acc + add1) >> shift1;
       }
     }
     else if (phase == 1)
@@ -482,8 +589,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
         int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * s->tmp[j * n + q];
-        s->tcoef[i] = (acc + add2) >> shift2;
+        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * e->tmp[j * n + q];
+        e->tcoef[i] = (acc + add2) >> shift2;
       }
     }
     if (phase == 2)
@@ -496,13 +603,13 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       for (int p = w; p < n2; p += nw)
       {
         const int blk = scan[p];
-        const int64_t tl = (int64_t)iabs(s->tcoef[blk]) * a[4];
+        const int64_t tl = (int64_t)iabs(e->tcoef[blk]) * a[4];
         const int ld = (int)(tl < cap ? tl : cap);
         const uint32_t m = (uint32_t)((ld + (1 << (qBits - 1))) >> qBits);
         const double err = (double)ld;
-        s->lvlD[p] = ld;
-        s->u.rd.cost0[p] = err * err * errScale;
-        s->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
+        e->lvlD[p] = ld;
+        e->cost0[p] = err * err * errScale;
+        e->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
       }
     }
     break;
@@ -510,8 +617,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   case OP_LEVELS_OUT:
   {
     // a0 n2, a1 qtCoef layer, a2 offset: tmp[] (int32 levels) -> qtCoef (int16)
-    int16_t* d = g->qtCoef[a[1]] + a[2];
-    for (int i = w; i < a[0]; i += nw) d[i] = (int16_t)s->tmp[i];
+    int16_t* d = e->qtCoef[a[1]] + a[2];
+    for (int i = w; i < a[0]; i += nw) d[i] = (int16_t)e->tmp[i];
     break;
   }
   case OP_INV_RECON:
@@ -530,11 +637,11 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         const int inMin = -(1 << (targetBits - 1)), inMax = (1 << (targetBits - 1)) - 1;
         for (int i = w; i < n2; i += nw)
         {
-          const int q = clip3(inMin, inMax, s->tmp[i]);
+          const int q = clip3(inMin, inMax, e->tmp[i]);
           int v;
           if (rightShift > 0) v = (q * scale + (1 << (rightShift - 1))) >> rightShift;
           else v = (int)((uint32_t)(q * scale) << (-rightShift));
-          s->tcoef[i] = clip3(-32768, 32767, v);
+          e->tcoef[i] = clip3(-32768, 32767, v);
         }
       }
       else if (phase == 1)
@@ -542,7 +649,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         if (a[3])
         {
           const int shift = 15 - bd - log2n, off = shift == 0 ? 0 : (1 << (shift - 1));
-          for (int i = w; i < n2; i += nw) s->resi[i] = (int16_t)((s->tcoef[i] + off) >> shift);
+          for (int i = w; i < n2; i += nw) e->resi[i] = (int16_t)((e->tcoef[i] + off) >> shift);
         }
         else
         {
@@ -551,8 +658,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
             int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * s->tcoef[k * n + j];
-            s->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
+            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
+            e->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
           }
         }
       }
@@ -565,8 +672,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
             int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * s->lvlD[k * n + j];
-            s->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
+            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
+            e->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
           }
         }
       }
@@ -574,23 +681,23 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     if (phase == 3)
     {
       // reconstruction into CU buffer, QT layer and picture (TEncSearch.cpp:1380-1393) + SSE (TComRdCost.cpp:1176)
-      int16_t* reco = g->predYuv + a[7];
-      int16_t* recQt = g->qtRec[a[9]] + a[10];
+      int16_t* reco = e->predYuv + a[7];
+      int16_t* recQt = e->qtRec[a[9]] + a[10];
       int16_t* recPic = g->rec[comp] + a[11];
       const int ps = a[8], qs = 64 >> (comp ? 1 : 0), stride = plane_stride(g, comp), shift = (bd - 8) << 1;
       uint32_t acc = 0;
       for (int i = w; i < n2; i += nw)
       {
         const int x = i & (n - 1), y = i >> log2n;
-        const int r = a[4] ? s->resi[i] : 0;
+        const int r = a[4] ? e->resi[i] : 0;
         const int v = clip3(0, (1 << bd) - 1, reco[y * ps + x] + r);
         reco[y * ps + x] = (int16_t)v;
         recQt[y * qs + x] = (int16_t)v;
-        recPic[y * stride + x] = (int16_t)v;
+        if (e->writePic) recPic[y * stride + x] = (int16_t)v;
         const int d = v - org_at(g, comp, a[12] + y * stride + x);
         acc += (uint32_t)((d * d) >> shift);
       }
-      if (acc) atomic_add_u32(&s->sse, acc);
+      if (acc) atomic_add_u32(&e->sse, acc);
     }
     break;
   }
@@ -598,8 +705,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   {
     // int16 block copy: a0 w, a1 h, a2 dst stride, a3 src stride
     const int bw = a[0], bh = a[1];
-    int16_t* d = (int16_t*)s->cmd.dst;
-    const int16_t* sr = (const int16_t*)s->cmd.src;
+    int16_t* d = (int16_t*)e->cmd.dst;
+    const int16_t* sr = (const int16_t*)e->cmd.src;
     for (int i = w; i < bw * bh; i += nw)
     {
       const int y = i / bw, x = i - y * bw;
@@ -609,14 +716,14 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   }
   case OP_COPY16:
   {
-    int16_t* d = (int16_t*)s->cmd.dst;
-    const int16_t* sr = (const int16_t*)s->cmd.src;
+    int16_t* d = (int16_t*)e->cmd.dst;
+    const int16_t* sr = (const int16_t*)e->cmd.src;
     for (int i = w; i < a[0]; i += nw) d[i] = sr[i];
     break;
   }
   case OP_ZERO16:
   {
-    int16_t* d = (int16_t*)s->cmd.dst;
+    int16_t* d = (int16_t*)e->cmd.dst;
     for (int i = w; i < a[0]; i += nw) d[i] = 0;
     break;
   }
@@ -661,20 +768,21 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
 // ----------------------------------------------------------------------------------------------
 FHC_DH void par_copy2d(const Ctx& c, int16_t* dst, int ds, const int16_t* src, int ss, int w, int h)
 {
-  Cmd& m = c.s->cmd;
+  Cmd& m = c.e->cmd;
+  if (w * h <= 16) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[y * ds + x] = src[y * ss + x]; return; }
   m.a[0] = w; m.a[1] = h; m.a[2] = ds; m.a[3] = ss; m.dst = dst; m.src = src;
   par(c, OP_COPY2D);
 }
 FHC_DH void par_copy16(const Ctx& c, int16_t* dst, const int16_t* src, int n)
 {
-  Cmd& m = c.s->cmd;
+  Cmd& m = c.e->cmd;
   if (n <= 16) { for (int i = 0; i < n; i++) dst[i] = src[i]; return; }
   m.a[0] = n; m.dst = dst; m.src = src;
   par(c, OP_COPY16);
 }
 FHC_DH void par_zero16(const Ctx& c, int16_t* dst, int n)
 {
-  Cmd& m = c.s->cmd;
+  Cmd& m = c.e->cmd;
   m.a[0] = n; m.dst = dst;
   par(c, OP_ZERO16);
 }
@@ -684,30 +792,30 @@ FHC_DH void copy_bytes(uint8_t* d, const uint8_t* s, int n) { for (int i = 0; i 
 // ----------------------------------------------------------------------------------------------
 // CABAC bit counter (TEncBinCoderCABACCounter.cpp:57-140)
 // ----------------------------------------------------------------------------------------------
-FHC_DH void enc_bin(Shared* s, int ctx, int bin)
+FHC_DH void enc_bin(Engine* e, int ctx, int bin)
 {
-  const uint8_t st = s->go.c[ctx];
-  s->bins++;
-  s->go.frac += (uint64_t)s->t.entropyBits[st ^ bin];
-  s->go.c[ctx] = s->t.nextState[st][bin];
+  const uint8_t st = e->go.c[ctx];
+  e->bins++;
+  e->go.frac += (uint64_t)e->t->entropyBits[st ^ bin];
+  e->go.c[ctx] = e->t->nextState[st][bin];
 }
-FHC_DH void enc_ep(Shared* s, int n) { s->bins += (uint32_t)n; s->go.frac += (uint64_t)32768 * (uint64_t)n; }
-FHC_DH void enc_trm(Shared* s, int bin) { s->bins++; s->go.frac += (uint64_t)s->t.entropyBits[126 ^ bin]; }
-FHC_DH void reset_bits(Shared* s) { s->go.frac &= 32767; s->bins = 0; }
-FHC_DH uint32_t num_bits(const Shared* s) { return (uint32_t)(s->go.frac >> 15); }
-FHC_DH int ctx_bits(const Shared* s, int ctx, int bin) { return s->t.entropyBits[s->go.c[ctx] ^ bin]; }
+FHC_DH void enc_ep(Engine* e, int n) { e->bins += (uint32_t)n; e->go.frac += (uint64_t)32768 * (uint64_t)n; }
+FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; e->go.frac += (uint64_t)e->t->entropyBits[126 ^ bin]; }
+FHC_DH void reset_bits(Engine* e) { e->go.frac &= 32767; e->bins = 0; }
+FHC_DH uint32_t num_bits(const Engine* e) { return (uint32_t)(e->go.frac >> 15); }
+FHC_DH int ctx_bits(const Engine* e, int ctx, int bin) { return e->t->entropyBits[e->go.c[ctx] ^ bin]; }
 FHC_DH void sb_copy(Sbac* d, const Sbac* sr)
 {
   const uint64_t* a = (const uint64_t*)sr;
   uint64_t* b = (uint64_t*)d;
   for (int i = 0; i < (int)(sizeof(Sbac) / 8); i++) b[i] = a[i];
 }
-FHC_DH void sbac_reset(Shared* s, Sbac* sb, int qp)                        // ContextModel::init (ContextModel.cpp:56)
+FHC_DH void sbac_reset(const Tables& t, Sbac* sb, int qp)                        // ContextModel::init (ContextModel.cpp:56)
 {
   qp = clip3(0, 51, qp);
   for (int i = 0; i < NUM_CTX; i++)
   {
-    const int iv = s->t.ctxInit[i], slope = (iv >> 4) * 5 - 45, offset = ((iv & 15) << 3) - 16;
+    const int iv = t.ctxInit[i], slope = (iv >> 4) * 5 - 45, offset = ((iv & 15) << 3) - 16;
     const int st = imin(imax(1, ((slope * qp) >> 4) + offset), 126);
     const int mps = st >= 64;
     sb->c[i] = (uint8_t)(((mps ? (st - 64) : (63 - st)) << 1) + mps);
@@ -726,6 +834,14 @@ FHC_DH double dadd(double a, double b) { return a + b; }
 FHC_DH double dsub(double a, double b) { return a - b; }
 #endif
 
+// context-set slots: the chain/CU-level slots live in shared memory (master); a thread engine aliases every depth of the
+// TU-level slots (CI_QT_TRAFO_*, CI_TEMP_BEST) onto its private set - a task only ever uses one depth of them.
+FHC_DH Sbac* slot_of(const Ctx& c, int depth, int ci)
+{
+  if (c.e->kind == ENG_MASTER || ci == CI_CURR_BEST) return &c.s->slot[depth][ci];
+  return &c.e->slots[ci == CI_QT_TRAFO_ROOT ? 0 : (ci == CI_TEMP_BEST ? 1 : 2)];
+}
+
 // ----------------------------------------------------------------------------------------------
 // neighbours (TComDataCU.cpp:985-1200, :1362-1461)
 // ----------------------------------------------------------------------------------------------
@@ -736,6 +852,7 @@ FHC_DH int ctu_field(const fhc_ctu_result* o, int idx, int f) { return f == F_DE
 FHC_DH int nb_left(const Ctx& c, const CUMeta* cu, int zabs, int f)
 {
   const Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const int r = s->t.z2r[zabs];
   if (r & 15)
   {
@@ -749,6 +866,7 @@ FHC_DH int nb_left(const Ctx& c, const CUMeta* cu, int zabs, int f)
 FHC_DH int nb_above(const Ctx& c, const CUMeta* cu, int zabs, int f, int planarAtCtuBoundary)
 {
   const Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const int r = s->t.z2r[zabs];
   if (r >> 4)
   {
@@ -803,11 +921,11 @@ FHC_DH int coef_scan_idx(const CUMeta* cu, int relIdx, int n, int comp)       //
 FHC_DH void code_split_flag(const Ctx& c, const CUMeta* cu, int relIdx, int depth)
 {
   if (depth == 3) return;
-  enc_bin(c.s, CTX_SPLIT + ctx_split(c, cu, relIdx, depth), cu->dep[relIdx] > depth ? 1 : 0);
+  enc_bin(c.e, CTX_SPLIT + ctx_split(c, cu, relIdx, depth), cu->dep[relIdx] > depth ? 1 : 0);
 }
 FHC_DH void code_part_size(const Ctx& c, const CUMeta* cu, int relIdx, int depth)
 {
-  if (depth == 3) enc_bin(c.s, CTX_PART, cu->part[relIdx] == SIZE_2Nx2N ? 1 : 0);
+  if (depth == 3) enc_bin(c.e, CTX_PART, cu->part[relIdx] == SIZE_2Nx2N ? 1 : 0);
 }
 FHC_D void code_luma_dir(const Ctx& c, const CUMeta* cu, int relIdx, int isMultiple)          // TEncSbac.cpp:643
 {
@@ -821,14 +939,14 @@ FHC_D void code_luma_dir(const Ctx& c, const CUMeta* cu, int relIdx, int isMulti
     get_mpm(c, cu, relIdx + partOffset * j, preds);
     predIdx[j] = -1;
     for (int i = 0; i < 3; i++) if (dir == preds[i]) predIdx[j] = i;
-    enc_bin(c.s, CTX_IPRED, predIdx[j] != -1 ? 1 : 0);
+    enc_bin(c.e, CTX_IPRED, predIdx[j] != -1 ? 1 : 0);
   }
-  for (int j = 0; j < partNum; j++) enc_ep(c.s, predIdx[j] != -1 ? (predIdx[j] ? 2 : 1) : 5);
+  for (int j = 0; j < partNum; j++) enc_ep(c.e, predIdx[j] != -1 ? (predIdx[j] ? 2 : 1) : 5);
 }
 FHC_DH void code_chroma_dir(const Ctx& c, const CUMeta* cu, int relIdx)                        // TEncSbac.cpp:698
 {
-  if (cu->cdir[relIdx] == DM_CHROMA_IDX) enc_bin(c.s, CTX_CPRED, 0);
-  else { enc_bin(c.s, CTX_CPRED, 1); enc_ep(c.s, 2); }
+  if (cu->cdir[relIdx] == DM_CHROMA_IDX) enc_bin(c.e, CTX_CPRED, 0);
+  else { enc_bin(c.e, CTX_CPRED, 1); enc_ep(c.e, 2); }
 }
 FHC_DH int sig_ctx_inc(const Tables& t, int pat, int firstCtx, int rasterPos, int log2n, int isChroma)   // TComTrQuant.cpp:2707
 {
@@ -874,23 +992,24 @@ FHC_DH void last_ctx_params(int isChroma, int log2n, int* off, int* shift)
 }
 FHC_DH int group_idx(int p) { return p < 4 ? p : (p < 6 ? 4 : (p < 8 ? 5 : (p < 12 ? 6 : (p < 16 ? 7 : (p < 24 ? 8 : 9))))); }
 
-FHC_DH void code_remain(Shared* s, uint32_t symbol, uint32_t rParam)                            // TEncSbac.cpp:337
+FHC_DH void code_remain(Engine* e, uint32_t symbol, uint32_t rParam)                            // TEncSbac.cpp:337
 {
   int codeNumber = (int)symbol;
-  if (codeNumber < (3 << rParam)) enc_ep(s, (int)(((uint32_t)codeNumber >> rParam) + 1 + rParam));
+  if (codeNumber < (3 << rParam)) enc_ep(e, (int)(((uint32_t)codeNumber >> rParam) + 1 + rParam));
   else
   {
     uint32_t length = rParam;
     codeNumber -= (3 << rParam);
     while (codeNumber >= (1 << length)) codeNumber -= (1 << (length++));
-    enc_ep(s, (int)(3 + length + 1 - rParam + length));
+    enc_ep(e, (int)(3 + length + 1 - rParam + length));
   }
 }
 
 // TEncSbac::codeCoeffNxN (TEncSbac.cpp:1181-1538); coef: int16 raster levels of this TU
-FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp, const int16_t* coef, int log2n, int comp)
+FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, const int16_t* coef, int log2n, int comp)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const int isChroma = comp != 0, n = 1 << log2n;
   const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
   const uint16_t* scan = scan_tab(s->t, scanType, log2n);
@@ -901,7 +1020,7 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
   uint8_t cgFlag[64];
   int scanPosLast = -1, posLast = 0;
 
-  if (log2n == 2) enc_bin(s, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
+  if (log2n == 2) enc_bin(e, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
   for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
   // last significant position: highest scan index with a non-zero level
   for (int p = n * n - 1; p >= 0; p--)
@@ -919,12 +1038,12 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
     const int gx = group_idx(posX), gy = group_idx(posY), gmax = group_idx(n - 1);
     last_ctx_params(isChroma, log2n, &off, &shift);
     const int bx = CTX_LASTX + (isChroma ? 15 : 0) + off, by = CTX_LASTY + (isChroma ? 15 : 0) + off;
-    for (cc = 0; cc < gx; cc++) enc_bin(s, bx + (cc >> shift), 1);
-    if (gx < gmax) enc_bin(s, bx + (cc >> shift), 0);
-    for (cc = 0; cc < gy; cc++) enc_bin(s, by + (cc >> shift), 1);
-    if (gy < gmax) enc_bin(s, by + (cc >> shift), 0);
-    if (gx > 3) enc_ep(s, (gx - 2) >> 1);
-    if (gy > 3) enc_ep(s, (gy - 2) >> 1);
+    for (cc = 0; cc < gx; cc++) enc_bin(e, bx + (cc >> shift), 1);
+    if (gx < gmax) enc_bin(e, bx + (cc >> shift), 0);
+    for (cc = 0; cc < gy; cc++) enc_bin(e, by + (cc >> shift), 1);
+    if (gy < gmax) enc_bin(e, by + (cc >> shift), 0);
+    if (gx > 3) enc_ep(e, (gx - 2) >> 1);
+    if (gy > 3) enc_ep(e, (gy - 2) >> 1);
   }
   {
     const int lastScanSet = scanPosLast >> 4;
@@ -943,7 +1062,7 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
         numNonZero = 1; lastNZ = scanPosSig; firstNZ = scanPosSig; scanPosSig--;
       }
       if (subSet == lastScanSet || subSet == 0) cgFlag[cgBlk] = 1;
-      else enc_bin(s, CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg), cgFlag[cgBlk] != 0);
+      else enc_bin(e, CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg), cgFlag[cgBlk] != 0);
       if (cgFlag[cgBlk])
       {
         const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
@@ -951,7 +1070,7 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
         {
           const int blkPos = scan[scanPosSig], sig = coef[blkPos] != 0;
           if (scanPosSig > subPos || subSet == 0 || numNonZero)
-            enc_bin(s, sigBase + sig_ctx_inc(s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
+            enc_bin(e, sigBase + sig_ctx_inc(s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
           if (sig)
           {
             absCoeff[numNonZero++] = iabs(coef[blkPos]);
@@ -971,18 +1090,18 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
         for (int idx = 0; idx < numC1; idx++)
         {
           const int sym = absCoeff[idx] > 1;
-          enc_bin(s, CTX_ONE + 4 * ctxSet + (int)c1, sym);
+          enc_bin(e, CTX_ONE + 4 * ctxSet + (int)c1, sym);
           if (sym) { c1 = 0; if (firstC2 == -1) firstC2 = idx; else escape = 1; }
           else if (c1 < 3 && c1 > 0) c1++;
         }
         if (c1 == 0 && firstC2 != -1)
         {
           const int sym = absCoeff[firstC2] > 2;
-          enc_bin(s, CTX_ABS + ctxSet, sym);
+          enc_bin(e, CTX_ABS + ctxSet, sym);
           if (sym) escape = 1;
         }
         escape = escape || (numNonZero > 8);
-        enc_ep(s, signHidden ? numNonZero - 1 : numNonZero);
+        enc_ep(e, signHidden ? numNonZero - 1 : numNonZero);
         if (escape)
         {
           int firstCoeff2 = 1;
@@ -991,7 +1110,7 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
             const int baseLevel = (idx < 8) ? (2 + firstCoeff2) : 1;
             if (absCoeff[idx] >= baseLevel)
             {
-              code_remain(s, (uint32_t)(absCoeff[idx] - baseLevel), goRice);
+              code_remain(e, (uint32_t)(absCoeff[idx] - baseLevel), goRice);
               if (absCoeff[idx] > (3 << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
             }
             if (absCoeff[idx] >= 2) firstCoeff2 = 0;
@@ -1000,6 +1119,13 @@ FHC_NOINLINE void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp,
       }
     }
   }
+}
+
+FHC_DH void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp, const int16_t* coef, int log2n, int comp)
+{
+  FHC_TIC(cc);
+  code_coeff_nxn_impl(c, cu, relIdxComp, coef, log2n, comp);
+  FHC_TOC2(c, cc, PF_COEFBITS);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1023,7 +1149,7 @@ FHC_DH QpParam qp_param(const Ctx& c, int comp)                                 
 FHC_DH int quant_scale(int rem) { return rem == 0 ? 26214 : rem == 1 ? 23302 : rem == 2 ? 20560 : rem == 3 ? 18396 : rem == 4 ? 16384 : 14564; }
 FHC_DH int inv_quant_scale(int rem) { return rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72; }
 
-FHC_DH int ic_rate(const Shared* s, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx)
+FHC_DH int ic_rate(const Engine* e, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx)
 {
   int rate = 32768;
   const uint32_t baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
@@ -1040,16 +1166,16 @@ FHC_DH int ic_rate(const Shared* s, uint32_t absLevel, int ctxOne, int ctxAbs, u
     }
     if (c1Idx < 8)
     {
-      rate += ctx_bits(s, ctxOne, 1);
-      if (c2Idx < 1) rate += ctx_bits(s, ctxAbs, 1);
+      rate += ctx_bits(e, ctxOne, 1);
+      if (c2Idx < 1) rate += ctx_bits(e, ctxAbs, 1);
     }
   }
-  else if (absLevel == 1) rate += ctx_bits(s, ctxOne, 0);
-  else if (absLevel == 2) { rate += ctx_bits(s, ctxOne, 1); rate += ctx_bits(s, ctxAbs, 0); }
+  else if (absLevel == 1) rate += ctx_bits(e, ctxOne, 0);
+  else if (absLevel == 2) { rate += ctx_bits(e, ctxOne, 1); rate += ctx_bits(e, ctxAbs, 0); }
   else rate = 0;
   return rate;
 }
-FHC_DH uint32_t coded_level(const Shared* s, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
+FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
                             uint32_t maxAbsLevel, int ctxSig, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx,
                             int qBits, double errScale, int isLast)
 {
@@ -1057,42 +1183,43 @@ FHC_DH uint32_t coded_level(const Shared* s, double lambda, double* codedCost, d
   uint32_t best = 0;
   if (!isLast && maxAbsLevel < 3)
   {
-    *codedCostSig = dmul(lambda, (double)ctx_bits(s, ctxSig, 0));
+    *codedCostSig = dmul(lambda, (double)ctx_bits(e, ctxSig, 0));
     *codedCost = dadd(*codedCost0, *codedCostSig);
     if (maxAbsLevel == 0) return 0;
   }
   else *codedCost = FHC_MAX_COST;
-  if (!isLast) currCostSig = dmul(lambda, (double)ctx_bits(s, ctxSig, 1));
+  if (!isLast) currCostSig = dmul(lambda, (double)ctx_bits(e, ctxSig, 1));
   const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
   for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
   {
     const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
-    double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(s, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
+    double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(e, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
     cur = dadd(cur, currCostSig);
     if (cur < *codedCost) { best = (uint32_t)absLevel; *codedCost = cur; *codedCostSig = currCostSig; }
   }
   return best;
 }
 
-FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
+FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.g->bitDepth;
   const QpParam q = qp_param(c, comp);
   const int qBits = 14 + q.per + (15 - bd - log2n);
   const double errScale = s->t.errScale[isChroma][log2n - 2][q.rem];
-  const double lambda = s->rdoqLambda;
+  const double lambda = e->rdoqLambda;
   const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
   const uint16_t* scan = scan_tab(s->t, scanType, log2n);
   const uint8_t* scanCG = scan_cg(s->t, scanType, log2n);
   const int wg = n >> 2, cgNum = numCoef >> 4;
   const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
-  const int32_t* src = s->tcoef;
-  int32_t* dst = s->tmp;
-  double* costCoeff0 = s->u.rd.cost0; double* costCoeff = s->u.rd.costCoeff; double* costSig = s->u.rd.costSig;
-  int32_t* rateIncUp = s->u.rd.rateIncUp; int32_t* rateIncDown = s->u.rd.rateIncDown;
-  int32_t* sigRateDelta = s->u.rd.sigRateDelta; int32_t* deltaU = s->u.rd.deltaU;
+  const int32_t* src = e->tcoef;
+  int32_t* dst = e->tmp;
+  double* costCoeff0 = e->cost0; double* costCoeff = e->costCoeff; double* costSig = e->costSig;
+  int32_t* rateIncUp = e->rateIncUp; int32_t* rateIncDown = e->rateIncDown;
+  int32_t* sigRateDelta = e->sigRateDelta; int32_t* deltaU = e->deltaU;
   double costCGSig[64];
   uint8_t cgFlag[64];
   double blockUncoded = 0, baseCost = 0;
@@ -1112,7 +1239,7 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
     {
       const int scanPos = cgScanPos * 16 + posInCG;
       const uint32_t blkPos = scan[scanPos];
-      const int levelDouble = s->lvlD[scanPos];
+      const int levelDouble = e->lvlD[scanPos];
       const uint32_t maxAbsLevel = (uint32_t)dst[blkPos];
       blockUncoded = dadd(blockUncoded, costCoeff0[scanPos]);
       if (lastScanPos < 0)
@@ -1135,23 +1262,23 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
         costCoeff[scanPos] = 0; costSig[scanPos] = 0;
         rateIncUp[blkPos] = 0; rateIncDown[blkPos] = 0; sigRateDelta[blkPos] = 0;
         if (scanPos == lastScanPos)
-          level = coded_level(s, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+          level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               sigBase, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
         else
         {
           const int ctxSig = sigBase + sig_ctx_inc(s->t, pat, firstSig, (int)blkPos, log2n, isChroma);
-          level = coded_level(s, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+          level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               ctxSig, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
-          sigRateDelta[blkPos] = ctx_bits(s, ctxSig, 1) - ctx_bits(s, ctxSig, 0);
+          sigRateDelta[blkPos] = ctx_bits(e, ctxSig, 1) - ctx_bits(e, ctxSig, 0);
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
         if (level > 0)
         {
-          const int rateNow = ic_rate(s, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
-          rateIncUp[blkPos] = ic_rate(s, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
-          rateIncDown[blkPos] = ic_rate(s, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+          const int rateNow = ic_rate(e, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
+          rateIncUp[blkPos] = ic_rate(e, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+          rateIncDown[blkPos] = ic_rate(e, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
         }
-        else rateIncUp[blkPos] = ctx_bits(s, ctxOne, 0);
+        else rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0);
         dst[blkPos] = (int32_t)level;
         baseCost = dadd(baseCost, costCoeff[scanPos]);
         const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
@@ -1183,17 +1310,17 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
         if (cgFlag[cgBlk] == 0)
         {
           const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
-          baseCost = dadd(baseCost, dsub(dmul(lambda, (double)ctx_bits(s, cx, 0)), sigCost));
-          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 0));
+          baseCost = dadd(baseCost, dsub(dmul(lambda, (double)ctx_bits(e, cx, 0)), sigCost));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 0));
         }
         else if (cgScanPos < cgLastScanPos)
         {
           if (nnzBeforePos0 == 0) { baseCost = dsub(baseCost, sigCost0); sigCost = dsub(sigCost, sigCost0); }
           double costZeroCG = baseCost;
           const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
-          baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(s, cx, 1)));
-          costZeroCG = dadd(costZeroCG, dmul(lambda, (double)ctx_bits(s, cx, 0)));
-          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 1));
+          baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(e, cx, 1)));
+          costZeroCG = dadd(costZeroCG, dmul(lambda, (double)ctx_bits(e, cx, 0)));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 1));
           costZeroCG = dadd(costZeroCG, uncodedDist);
           costZeroCG = dsub(costZeroCG, codedLevelAndDist);
           costZeroCG = dsub(costZeroCG, sigCost);
@@ -1201,7 +1328,7 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
           {
             cgFlag[cgBlk] = 0;
             baseCost = costZeroCG;
-            costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(s, cx, 0));
+            costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 0));
             for (int posInCG = 15; posInCG >= 0; posInCG--)
             {
               const int scanPos = cgScanPos * 16 + posInCG;
@@ -1216,8 +1343,8 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
   }
   if (lastScanPos < 0) return 0;
 
-  double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(s, cbfCtx, 0)));
-  baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(s, cbfCtx, 1)));
+  double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(e, cbfCtx, 0)));
+  baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(e, cbfCtx, 1)));
   {
     int foundLast = 0, off, shift;
     last_ctx_params(isChroma, log2n, &off, &shift);
@@ -1239,10 +1366,10 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
             const uint32_t lx = scanType == SCAN_VER ? posY : posX, ly = scanType == SCAN_VER ? posX : posY;
             const int gx = group_idx((int)lx), gy = group_idx((int)ly);
             int bx = 0, by = 0, cc;
-            for (cc = 0; cc < gx; cc++) bx += ctx_bits(s, bx0 + (cc >> shift), 1);
-            if (gx < gmax) bx += ctx_bits(s, bx0 + (gx >> shift), 0);
-            for (cc = 0; cc < gy; cc++) by += ctx_bits(s, by0 + (cc >> shift), 1);
-            if (gy < gmax) by += ctx_bits(s, by0 + (gy >> shift), 0);
+            for (cc = 0; cc < gx; cc++) bx += ctx_bits(e, bx0 + (cc >> shift), 1);
+            if (gx < gmax) bx += ctx_bits(e, bx0 + (gx >> shift), 0);
+            for (cc = 0; cc < gy; cc++) by += ctx_bits(e, by0 + (cc >> shift), 1);
+            if (gy < gmax) by += ctx_bits(e, by0 + (gy >> shift), 0);
             double cost = (double)(bx + by);
             if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
             if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
@@ -1333,6 +1460,14 @@ FHC_NOINLINE uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, 
   return absSum;
 }
 
+FHC_DH uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
+{
+  FHC_TIC(r);
+  const uint32_t v = rdoq_pass_impl(c, cu, relIdxComp, comp, log2n, cbfCtx);
+  FHC_TOC2(c, r, PF_RDOQ);
+  return v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // geometry helpers
 // ----------------------------------------------------------------------------------------------
@@ -1349,12 +1484,14 @@ FHC_DH int cu_buf_index(const Shared* s, const CUMeta* cu) { return (int)(cu - &
 FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int n, int wantFilt)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
   const int zLT = cu->zidx + relIdx, rLT = s->t.z2r[zLT];
   const int ux = rLT & 15, uy = rLT >> 4;
   const int us = comp ? 2 : 4, nu = n / us, total = 4 * nu + 1;
-  uint8_t* flags = s->flags;
+  uint8_t* flags = e->flags;
   int numAvail = 0;
+  FHC_TIC(rf);
   const int leftOk = (ux > 0 || s->ctuX > 0), aboveOk = (uy > 0 || s->ctuY > 0);
   flags[2 * nu] = (uint8_t)(leftOk && aboveOk);
   for (int i = 0; i < nu; i++) { flags[2 * nu + 1 + i] = (uint8_t)aboveOk; flags[2 * nu - 1 - i] = (uint8_t)leftOk; }
@@ -1380,10 +1517,11 @@ FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int 
     }
   }
   for (int i = 0; i < total; i++) numAvail += flags[i];
-  Cmd& m = s->cmd;
+  Cmd& m = e->cmd;
   const int px = (s->ctuPelX + ux * 4) >> (comp ? 1 : 0), py = (s->ctuPelY + uy * 4) >> (comp ? 1 : 0);
   m.a[0] = comp; m.a[1] = n; m.a[2] = nu; m.a[3] = us; m.a[4] = py * plane_stride(g, comp) + px; m.a[5] = wantFilt;
   m.a[6] = numAvail; m.a[7] = total;
+  FHC_TOC2(c, rf, PF_REFS_MASTER);
   par(c, OP_REFS);
 }
 
@@ -1394,6 +1532,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
                              int predSaveLoad)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   const int n = 1 << log2n, isChroma = comp != 0;
   const int cuW = cu->width >> isChroma;
@@ -1407,7 +1546,8 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   const int ts = cu->ts[comp][relIdx];
   const QpParam q = qp_param(c, comp);
   int mode;
-  Cmd& m = s->cmd;
+  Cmd& m = e->cmd;
+  FHC_TIC(tu);
 
   if (comp == 0) mode = cu->ldir[relIdx];
   else
@@ -1426,7 +1566,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   par(c, OP_PRED_RESI);
 
   // transform + RDOQ (TComTrQuant::transformNxN :1450)
-  s->rdoqLambda = g->sp.rdoqLambda[comp];
+  e->rdoqLambda = g->sp.rdoqLambda[comp];
   const int scanType = coef_scan_idx(cu, relIdx, n, comp);
   m.a[0] = log2n; m.a[1] = (comp == 0 && log2n == 2); m.a[2] = ts; m.a[3] = scanType; m.a[4] = quant_scale(q.rem);
   m.a[5] = 14 + q.per + (15 - g->bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
@@ -1437,15 +1577,16 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
 
   // levels -> QT coefficient layer
   if (absSum > 0) { m.a[0] = n * n; m.a[1] = qtLayer; m.a[2] = coefOff; par(c, OP_LEVELS_OUT); }
-  else par_zero16(c, g->qtCoef[qtLayer] + coefOff, n * n);
+  else par_zero16(c, e->qtCoef[qtLayer] + coefOff, n * n);
 
   // inverse + reconstruction + SSE
-  s->sse = 0;
+  e->sse = 0;
   m.a[0] = comp; m.a[1] = log2n; m.a[2] = (comp == 0 && log2n == 2); m.a[3] = ts; m.a[4] = absSum > 0; m.a[5] = q.per; m.a[6] = q.rem;
   m.a[7] = predOff; m.a[8] = cuW; m.a[9] = qtLayer; m.a[10] = qtOff; m.a[11] = picY * stride + picX; m.a[12] = picY * stride + picX;
   par(c, OP_INV_RECON);
-  uint32_t dist = s->sse;
+  uint32_t dist = e->sse;
   if (isChroma) dist = (uint32_t)dmul(g->sp.chromaDistWeight[comp - 1], (double)dist);          // TComRdCost.cpp:352
+  FHC_TOC2(c, tu, PF_TUBLOCK);
   return dist;
 }
 
@@ -1474,7 +1615,7 @@ FHC_DH void code_qt_cbf(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp
   const int isChroma = comp != 0;
   const int ctx = CTX_CBF + (isChroma ? 5 + trDepth : (trDepth == 0 ? 1 : 0));
   const int lowest = trDepth + ((!lowestLevel && compLog2n < 3) ? 1 : 0);
-  enc_bin(c.s, ctx, (cu->cbf[comp][relIdxComp] >> lowest) & 1);
+  enc_bin(c.e, ctx, (cu->cbf[comp][relIdxComp] >> lowest) & 1);
 }
 FHC_D void enc_subdiv_cbf(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int chromaCodeAll, int bLuma, int bChroma)
 {
@@ -1483,7 +1624,7 @@ FHC_D void enc_subdiv_cbf(const Ctx& c, const CUMeta* cu, int relIdx, int log2n,
   else if (log2n > 5) { }
   else if (log2n == 2) { }
   else if (log2n == min_tu_log2_in_cu(cu)) { }
-  else if (bLuma) enc_bin(c.s, CTX_SUBDIV + (5 - log2n), subdiv);
+  else if (bLuma) enc_bin(c.e, CTX_SUBDIV + (5 - log2n), subdiv);
   if (bChroma)
     for (int cc = 1; cc < 3; cc++)
       if (chromaCodeAll && (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1)))
@@ -1504,23 +1645,25 @@ FHC_D void enc_coeff_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, i
   }
   else if (comp == 0)
   {
-    if ((cu->cbf[0][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, relIdx, c.g->qtCoef[5 - log2n] + relIdx * 16, log2n, 0);
+    if ((cu->cbf[0][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, relIdx, c.e->qtCoef[5 - log2n] + relIdx * 16, log2n, 0);
   }
   else if (procChroma)
   {
     const int cl = log2n == 2 ? 2 : log2n - 1, ridx = log2n == 2 ? (relIdx & ~3) : relIdx;
-    if ((cu->cbf[comp][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, ridx, c.g->qtCoef[5 - log2n] + comp_off(comp) + ridx * 4, cl, comp);
+    if ((cu->cbf[comp][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, ridx, c.e->qtCoef[5 - log2n] + comp_off(comp) + ridx * 4, cl, comp);
   }
 }
 FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int chromaCodeAll, int procChroma,
                              int bLuma, int bChroma)
 {
-  reset_bits(c.s);
+  FHC_TIC(bq);
+  reset_bits(c.e);
   enc_intra_header(c, cu, trDepth, relIdx, bLuma, bChroma);
   enc_subdiv_cbf(c, cu, relIdx, log2n, trDepth, chromaCodeAll, bLuma, bChroma);
   if (bLuma) enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 0, procChroma);
   if (bChroma) { enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 1, procChroma); enc_coeff_qt(c, cu, relIdx, log2n, trDepth, 2, procChroma); }
-  return num_bits(c.s);
+  FHC_TOC2(c, bq, PF_BITSQT);
+  return num_bits(c.e);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1529,6 +1672,7 @@ FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log
 FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, int checkFirst, uint32_t* distY, double* rdCost)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   const int fullDepth = cu->depth + trDepth;
   const int numParts = cu->nparts >> (2 * trDepth);
@@ -1539,8 +1683,8 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   int bestModeId = 0;
   const int checkTS = (log2n == 2) && (cu->part[relIdx] == SIZE_NxN);
   const int layer = 5 - log2n;
-  int16_t* qtCoefBlk = g->qtCoef[layer < 0 ? 0 : layer] + relIdx * 16;
-  int16_t* qtRecBlk = g->qtRec[layer < 0 ? 0 : layer] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx);
+  int16_t* qtCoefBlk = e->qtCoef[layer < 0 ? 0 : layer] + relIdx * 16;
+  int16_t* qtRecBlk = e->qtRec[layer < 0 ? 0 : layer] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx);
   int16_t* picBlk = g->rec[0] + (cu->y + rel_y(s, relIdx)) * plane_stride(g, 0) + cu->x + rel_x(s, relIdx);
   if (checkFirst && checkFull) checkSplit = 0;
 
@@ -1548,7 +1692,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   {
     if (checkTS)
     {
-      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
       for (int modeId = 0; modeId < 2; modeId++)
       {
         double costTmp;
@@ -1563,11 +1707,11 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
           singleCost = costTmp; singleDist = dTmp; singleCbf = cbfTmp; bestModeId = modeId;
           if (modeId == 0)
           {
-            for (int i = 0; i < 16; i++) { s->tsCoef[0][i] = qtCoefBlk[i]; s->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
-            sb_copy(&s->slot[fullDepth][CI_TEMP_BEST], &s->go);
+            for (int i = 0; i < 16; i++) { e->tsCoef[0][i] = qtCoefBlk[i]; e->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
+            sb_copy(slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
           }
         }
-        if (modeId == 0) sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+        if (modeId == 0) sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       set_range(cu->ts[0], relIdx, numParts, bestModeId);
       if (bestModeId == 0)
@@ -1575,17 +1719,17 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
         const int ps = plane_stride(g, 0);
         for (int i = 0; i < 16; i++)
         {
-          qtCoefBlk[i] = s->tsCoef[0][i];
-          qtRecBlk[(i >> 2) * 64 + (i & 3)] = s->tsRec[0][i];
-          picBlk[(i >> 2) * ps + (i & 3)] = s->tsRec[0][i];
+          qtCoefBlk[i] = e->tsCoef[0][i];
+          qtRecBlk[(i >> 2) * 64 + (i & 3)] = e->tsRec[0][i];
+          if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[0][i];
         }
         set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
-        sb_copy(&s->go, &s->slot[fullDepth][CI_TEMP_BEST]);
+        sb_copy(&e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
     }
     else
     {
-      if (checkSplit) sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      if (checkSplit) sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
       set_range(cu->ts[0], relIdx, numParts, 0);
       set_range(cu->tridx, relIdx, numParts, trDepth);
       singleDist = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, 0);
@@ -1600,10 +1744,10 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     const int q = numParts >> 2;
     if (checkFull)
     {
-      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_TEST], &s->go);
-      sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_TEST), &e->go);
+      sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     }
-    else sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+    else sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
     for (int i = 0; i < 4; i++)
     {
       recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, checkFirst, &splitDist, &splitCost);
@@ -1611,7 +1755,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     }
     if (splitCbf)
       for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
-    sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+    sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
     if (splitCost < singleCost)
     {
@@ -1619,7 +1763,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
       *rdCost = dadd(*rdCost, splitCost);
       return;
     }
-    sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_TEST]);
+    sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_TEST));
     set_range(cu->tridx, relIdx, numParts, trDepth);
     set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
     set_range(cu->ts[0], relIdx, numParts, bestModeId);
@@ -1633,12 +1777,13 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
 FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   if (cu->tridx[relIdx] == trDepth)
   {
     const int n = 1 << log2n;
-    par_copy16(c, cuCoef + relIdx * 16, c.g->qtCoef[5 - log2n] + relIdx * 16, n * n);
+    par_copy16(c, cuCoef + relIdx * 16, c.e->qtCoef[5 - log2n] + relIdx * 16, n * n);
     par_copy2d(c, cuReco + rel_y(s, relIdx) * cu->width + rel_x(s, relIdx), cu->width,
-               c.g->qtRec[5 - log2n] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx), 64, n, n);
+               c.e->qtRec[5 - log2n] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx), 64, n, n);
   }
   else
   {
@@ -1651,6 +1796,7 @@ FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
 FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   const int depth = cu->depth;
   const int initTrDepth = cu->part[0] == SIZE_2Nx2N ? 0 : 1;
@@ -1674,17 +1820,20 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     // ---- rough mode decision: 35 predictions + SATD on the workers (TEncSearch.cpp:2271-2295)
     build_refs(c, cu, partOffset, 0, puSize, 1);
     {
-      Cmd& m = s->cmd;
-      const int mpg = imin(35, 20480 >> (2 * log2pu));
+      Cmd& m = e->cmd;
+      const int mpg = imin(35, 4096 >> (2 * log2pu));
       for (int i = 0; i < 35; i++) s->satd[i] = 0;
       m.a[0] = log2pu; m.a[1] = poy * ps + pox; m.a[2] = mpg; m.a[15] = 2 * ((35 + mpg - 1) / mpg);
+      FHC_TIC(rp);
       par(c, OP_RMD);
+      FHC_TOC2(c, rp, PF_RMD_PAR);
     }
+    FHC_TIC(rm);
     int preds[3];
     const int numCand = get_mpm(c, cu, partOffset, preds);
     {
       // xModeBitsIntra (TEncSearch.cpp:5353): bin counter state + one context reloaded from CI_CURR_BEST
-      const Sbac* srcSb = &s->slot[depth][CI_CURR_BEST];
+      const Sbac* srcSb = slot_of(c, depth, CI_CURR_BEST);
       const uint64_t frac0 = srcSb->frac & 32767;
       const uint8_t st = srcSb->c[CTX_IPRED];
       for (int i = 0; i < numModesForFullRD; i++) candCost[i] = FHC_MAX_COST;
@@ -1716,16 +1865,44 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       for (int i = 0; i < numModesForFullRD; i++) included |= (preds[j] == (int)rdModeList[i]);
       if (!included) rdModeList[numModesForFullRD++] = (uint32_t)preds[j];
     }
+    FHC_TOC2(c, rm, PF_RMD_MASTER);
 
     // ---- full RD over the candidates, then the best mode once more with the full RQT
-    for (int i = 0; i < numModesForFullRD + 1; i++)
+    int firstSerial = 0;
+    if (log2pu <= 3 && e->kind == ENG_MASTER)
+    {
+      // small PUs (4x4 of NxN, 8x8): every candidate is a single TU, independent of the others (same start contexts,
+      // neighbours outside the PU) -> one thread engine per candidate, results compared in list order afterwards
+      TaskDesc& td = s->task;
+      td.kind = TASK_LUMA_PU; td.numTasks = numModesForFullRD; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
+      td.partOffset = partOffset; td.log2pu = log2pu; td.initTrDepth = initTrDepth;
+      for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
+      { FHC_TIC(tl); par(c, OP_TASKS); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
+      int bi = -1;
+      for (int i = 0; i < numModesForFullRD; i++)
+        if (s->eng[i].resCost < bestPUCost) { bestPUCost = s->eng[i].resCost; bestPUDist = s->eng[i].resDist; bestPUMode = rdModeList[i]; bi = i; }
+      {
+        // xSetIntraResultLumaQT + the saved trIdx/cbf/tskip arrays of the winner
+        const Engine* w = &s->eng[bi];
+        const CUMeta* wc = &g->eng[bi].cu;
+        const int layer = 5 - log2pu, n = 1 << log2pu;
+        par_copy16(c, cuCoef + partOffset * 16, w->qtCoef[layer] + partOffset * 16, n * n);
+        par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width,
+                   w->qtRec[layer] + rel_y(s, partOffset) * 64 + rel_x(s, partOffset), 64, n, n);
+        copy_bytes(s->qtTrIdx, wc->tridx + partOffset, puParts);
+        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wc->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], wc->ts[j] + partOffset, puParts); }
+      }
+      // second pass: a 4x4 PU cannot split, re-coding the best mode reproduces the same cost (never strictly smaller)
+      firstSerial = (log2pu == 2) ? numModesForFullRD + 1 : numModesForFullRD;
+    }
+    for (int i = firstSerial; i < numModesForFullRD + 1; i++)
     {
       const int second = (i == numModesForFullRD);
       const uint32_t orgMode = second ? bestPUMode : rdModeList[i];
       uint32_t puDist = 0;
       double puCost = 0.0;
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
-      sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+      sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
       recur_luma_qt(c, cu, partOffset, log2pu, initTrDepth, second ? 0 : 1, &puDist, &puCost);
       if (puCost < bestPUCost)
       {
@@ -1751,7 +1928,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     }
     for (int i = 0; i < 4 * puParts; i++) { cu->cbf[0][i] |= (uint8_t)cY; cu->cbf[1][i] |= (uint8_t)cU; cu->cbf[2][i] |= (uint8_t)cV; }
   }
-  sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+  sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
   cu->dist = overallDist;
 }
 
@@ -1761,6 +1938,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
 FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, int procChroma, uint32_t* dist)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   const int numPartsLuma = cu->nparts >> (2 * trDepth);
   if (cu->tridx[relIdx] == trDepth)
@@ -1784,9 +1962,9 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
       uint32_t singleDist = 0, singleCbf = 0;
       int bestMode = 0, bestTS = 0, currMode = 0;
       const int total = checkTS ? 2 : 1;
-      int16_t* qtCoefBlk = g->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4;
-      int16_t* qtRecBlk = g->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1);
-      sb_copy(&s->slot[fullDepth][CI_QT_TRAFO_ROOT], &s->go);
+      int16_t* qtCoefBlk = e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4;
+      int16_t* qtRecBlk = e->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1);
+      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
       for (int tsId = 0; tsId < total; tsId++)
       {
         const int isOne = total == 1;
@@ -1798,20 +1976,20 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
         if (tsId == 1 && cbfTmp == 0) costTmp = FHC_MAX_COST;
         else if (!isOne)
         {
-          reset_bits(s);                                                         // xGetIntraBitsQTChroma (TEncSearch.cpp:1094)
+          reset_bits(e);                                                         // xGetIntraBitsQTChroma (TEncSearch.cpp:1094)
           if (cbfTmp) code_coeff_nxn(c, cu, ridx, qtCoefBlk, cl, cc);
-          costTmp = rd_cost(c, num_bits(s), dTmp);
+          costTmp = rd_cost(c, num_bits(e), dTmp);
         }
         if (costTmp < singleCost)
         {
           singleCost = costTmp; singleDist = dTmp; bestTS = tsId; bestMode = currMode; singleCbf = cbfTmp;
           if (!isOne && !isLast)
           {
-            for (int i = 0; i < 16; i++) { s->tsCoef[cc][i] = qtCoefBlk[i]; s->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
-            sb_copy(&s->slot[fullDepth][CI_TEMP_BEST], &s->go);
+            for (int i = 0; i < 16; i++) { e->tsCoef[cc][i] = qtCoefBlk[i]; e->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
+            sb_copy(slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
           }
         }
-        if (!isOne && !isLast) sb_copy(&s->go, &s->slot[fullDepth][CI_QT_TRAFO_ROOT]);
+        if (!isOne && !isLast) sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       if (bestMode < total)
       {
@@ -1819,12 +1997,12 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
         int16_t* picBlk = g->rec[cc] + ((cu->y + rel_y(s, ridx)) >> 1) * ps + ((cu->x + rel_x(s, ridx)) >> 1);
         for (int i = 0; i < 16; i++)
         {
-          qtCoefBlk[i] = s->tsCoef[cc][i];
-          qtRecBlk[(i >> 2) * 32 + (i & 3)] = s->tsRec[cc][i];
-          picBlk[(i >> 2) * ps + (i & 3)] = s->tsRec[cc][i];
+          qtCoefBlk[i] = e->tsCoef[cc][i];
+          qtRecBlk[(i >> 2) * 32 + (i & 3)] = e->tsRec[cc][i];
+          if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[cc][i];
         }
         set_range(cu->cbf[cc], ridx, nparts, (int)(singleCbf << trDepth));
-        sb_copy(&s->go, &s->slot[fullDepth][CI_TEMP_BEST]);
+        sb_copy(&e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
       set_range(cu->ts[cc], ridx, nparts, bestTS);
       *dist += singleDist;
@@ -1848,6 +2026,7 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
 FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth, int procChroma)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   if (!procChroma) return;
   if (cu->tridx[relIdx] == trDepth)
   {
@@ -1855,9 +2034,9 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
     const int cw = cu->width >> 1;
     for (int cc = 1; cc < 3; cc++)
     {
-      par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, c.g->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4, n * n);
+      par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, c.e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4, n * n);
       par_copy2d(c, cuReco + comp_off(cc) + (rel_y(s, ridx) >> 1) * cw + (rel_x(s, ridx) >> 1), cw,
-                 c.g->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1), 32, n, n);
+                 c.e->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1), 32, n, n);
     }
   }
   else
@@ -1869,18 +2048,42 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
 FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
 {
   Shared* s = c.s;
+  FrameGlobal* g = c.g;
+  Engine* e = c.e; (void)e;
   const int depth = cu->depth, nparts = cu->nparts, log2cu = ilog2(cu->width);
   int modeList[5] = { PLANAR_IDX, VER_IDX, HOR_IDX, DC_IDX, DM_CHROMA_IDX };
   uint32_t bestMode = 0, bestDist = 0;
   double bestCost = FHC_MAX_COST;
   for (int i = 0; i < 4; i++) if (modeList[i] == cu->ldir[0]) { modeList[i] = 34; break; }      // getAllowedChromaDir
+  if (log2cu == 3 && e->kind == ENG_MASTER)
+  {
+    // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> thread engines
+    TaskDesc& td = s->task;
+    td.kind = TASK_CHROMA_CU; td.numTasks = 5; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
+    td.partOffset = 0; td.log2pu = log2cu; td.initTrDepth = 0;
+    for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
+    { FHC_TIC(tc); par(c, OP_TASKS); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
+    int bi = -1;
+    for (int mi = 0; mi < 5; mi++)
+      if (s->eng[mi].resCost < bestCost) { bestCost = s->eng[mi].resCost; bestDist = s->eng[mi].resDist; bestMode = (uint32_t)modeList[mi]; bi = mi; }
+    const Engine* w = &s->eng[bi];
+    const CUMeta* wc = &g->eng[bi].cu;
+    const int layer = 5 - (3 - (int)cu->tridx[0]);               // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
+    for (int cc = 1; cc < 3; cc++)
+    {
+      par_copy16(c, cuCoef + comp_off(cc), w->qtCoef[layer] + comp_off(cc), 16);
+      par_copy2d(c, cuReco + comp_off(cc), 4, w->qtRec[layer] + comp_off(cc), 32, 4, 4);
+      copy_bytes(s->qtCbf[cc], wc->cbf[cc], nparts); copy_bytes(s->qtTs[cc], wc->ts[cc], nparts);
+    }
+  }
+  else
   for (int mi = 0; mi < 5; mi++)
   {
     uint32_t dist = 0;
-    sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+    sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, nparts, modeList[mi]);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
-    sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+    sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
     if (cost < bestCost)
     {
@@ -1892,7 +2095,7 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
   for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
   set_range(cu->cdir, 0, nparts, (int)bestMode);
   cu->dist += bestDist;
-  sb_copy(&s->go, &s->slot[depth][CI_CURR_BEST]);
+  sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1907,7 +2110,7 @@ FHC_D void encode_transform(const Ctx& c, const CUMeta* cu, const int16_t* coef,
   else if (log2n > 5) { }
   else if (log2n == 2) { }
   else if (log2n == min_tu_log2_in_cu(cu)) { }
-  else enc_bin(c.s, CTX_SUBDIV + (5 - log2n), subdiv);
+  else enc_bin(c.e, CTX_SUBDIV + (5 - log2n), subdiv);
   for (int cc = 1; cc < 3; cc++)
     if (trDepth == 0 || chromaCodeAll)
       if (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1))
@@ -1980,9 +2183,10 @@ FHC_D void cu_copy_part_from(const Ctx& c, CUMeta* dst, const CUMeta* src, int p
 FHC_D void cu_copy_to_pic(const Ctx& c, const CUMeta* cu, int withCoef)                          // copyToPic (TComDataCU.cpp:906)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   fhc_ctu_result* o = &c.g->out[s->ctuAddr];
   o->totalCost = cu->cost; o->totalDist = cu->dist; o->totalBits = cu->bits; o->totalBins = cu->bins;
-  Cmd& m = s->cmd;
+  Cmd& m = e->cmd;
   m.a[0] = cu->depth; m.a[1] = cu_buf_index(s, cu); m.a[2] = cu->zidx; m.a[3] = cu->nparts; m.a[4] = withCoef ? cu->width : 0;
   par(c, OP_CU_TO_OUT);
 }
@@ -2010,15 +2214,17 @@ FHC_D void copy_reco_to_parent(const Ctx& c, const CUMeta* child, const CUMeta* 
 FHC_DH void check_best_mode(const Ctx& c, int depth)                                             // xCheckBestMode (TEncCu.cpp:1659)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   if (temp_cu(s, depth)->cost < best_cu(s, depth)->cost)
   {
     s->bestIdx[depth] = (uint8_t)(1 - s->bestIdx[depth]);
-    sb_copy(&s->slot[depth][CI_NEXT_BEST], &s->slot[depth][CI_TEMP_BEST]);
+    sb_copy(slot_of(c, depth, CI_NEXT_BEST), slot_of(c, depth, CI_TEMP_BEST));
   }
 }
 FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)                            // xCheckRDCostIntra (TEncCu.cpp:1528)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   CUMeta* cu = temp_cu(s, depth);
   const int bi = cu_buf_index(s, cu);
@@ -2026,14 +2232,14 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   int16_t* cuReco = g->cuReco[depth][bi];
   set_range(cu->part, 0, cu->nparts, partSize);
   set_range(cu->pred, 0, cu->nparts, MODE_INTRA);
-  est_intra_luma(c, cu, cuCoef, cuReco);
+  { FHC_TIC(el); est_intra_luma(c, cu, cuCoef, cuReco); FHC_TOC2(c, el, PF_LUMA); }
   par_copy2d(c, g->rec[0] + cu->y * plane_stride(g, 0) + cu->x, plane_stride(g, 0), cuReco, cu->width, cu->width, cu->width);
-  est_intra_chroma(c, cu, cuCoef, cuReco);
-  reset_bits(s);
+  { FHC_TIC(ec); est_intra_chroma(c, cu, cuCoef, cuReco); FHC_TOC2(c, ec, PF_CHROMA); }
+  reset_bits(e);
   encode_cu_syntax(c, cu, cuCoef);
-  sb_copy(&s->slot[depth][CI_TEMP_BEST], &s->go);
-  cu->bits = num_bits(s);
-  cu->bins = s->bins;
+  sb_copy(slot_of(c, depth, CI_TEMP_BEST), &e->go);
+  cu->bits = num_bits(e);
+  cu->bins = e->bins;
   cu->cost = rd_cost(c, cu->bits, cu->dist);
   check_best_mode(c, depth);
 }
@@ -2041,6 +2247,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
 FHC_D void compress_cu(const Ctx& c, int depth)                                                  // xCompressCU (TEncCu.cpp:496-1058)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
   const int x = best_cu(s, depth)->x, y = best_cu(s, depth)->y, w = best_cu(s, depth)->width;
   const int boundary = !(x + w - 1 < g->width && y + w - 1 < g->height);
@@ -2055,13 +2262,13 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       cu_init_est(c, temp_cu(s, depth));
     }
     CUMeta* b = best_cu(s, depth);
-    sb_copy(&s->go, &s->slot[depth][CI_NEXT_BEST]);
-    reset_bits(s);
+    sb_copy(&e->go, slot_of(c, depth, CI_NEXT_BEST));
+    reset_bits(e);
     code_split_flag(c, b, 0, depth);
-    b->bits += num_bits(s);
-    b->bins += s->bins;
+    b->bits += num_bits(e);
+    b->bins += e->bins;
     b->cost = rd_cost(c, b->bits, b->dist);
-    sb_copy(&s->slot[depth][CI_NEXT_BEST], &s->go);
+    sb_copy(slot_of(c, depth, CI_NEXT_BEST), &e->go);
   }
   if (depth < 3)
   {
@@ -2074,8 +2281,8 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       cu_position(c, &s->cu[nd][1], t, i, nd);
       if (s->cu[nd][0].x < g->width && s->cu[nd][0].y < g->height)
       {
-        if (i == 0) sb_copy(&s->slot[nd][CI_CURR_BEST], &s->slot[depth][CI_CURR_BEST]);
-        else sb_copy(&s->slot[nd][CI_CURR_BEST], &s->slot[nd][CI_NEXT_BEST]);
+        if (i == 0) sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, depth, CI_CURR_BEST));
+        else sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, nd, CI_NEXT_BEST));
         compress_cu(c, nd);
         cu_copy_part_from(c, t, best_cu(s, nd), i, 1);
         copy_reco_to_parent(c, best_cu(s, nd), t, i);
@@ -2092,16 +2299,16 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
         }
       }
     }
-    sb_copy(&s->go, &s->slot[nd][CI_NEXT_BEST]);
+    sb_copy(&e->go, slot_of(c, nd, CI_NEXT_BEST));
     if (!boundary)
     {
-      reset_bits(s);
+      reset_bits(e);
       code_split_flag(c, t, 0, depth);
-      t->bits += num_bits(s);
-      t->bins += s->bins;
+      t->bits += num_bits(e);
+      t->bins += e->bins;
     }
     t->cost = rd_cost(c, t->bits, t->dist);
-    sb_copy(&s->slot[depth][CI_TEMP_BEST], &s->go);
+    sb_copy(slot_of(c, depth, CI_TEMP_BEST), &e->go);
     check_best_mode(c, depth);
   }
   cu_copy_to_pic(c, best_cu(s, depth), 1);
@@ -2112,6 +2319,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
 FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
   const fhc_ctu_result* o = &g->out[s->ctuAddr];
   const int r = s->t.z2r[zidx];
@@ -2142,8 +2350,81 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
   par_copy16(c, cv + 5120, o->coefCr + zidx * 4, (w * w) >> 2);
   encode_cu_syntax(c, view, cv);
   const int lastInCtu = ((x + w >= g->width) || (((r & 15) * 4 + w) == 64)) && ((y + w >= g->height) || (((r >> 4) * 4 + w) == 64));
-  if (lastInCtu && s->ctuAddr != g->wc * g->hc - 1) enc_trm(s, 0);                               // finishCU (TEncCu.cpp:1066)
+  if (lastInCtu && s->ctuAddr != g->wc * g->hc - 1) enc_trm(e, 0);                               // finishCU (TEncCu.cpp:1066)
 }
+
+// ----------------------------------------------------------------------------------------------
+// engines and candidate tasks
+// ----------------------------------------------------------------------------------------------
+FHC_D void init_engines(FrameGlobal* g, Shared* s)
+{
+  Engine* m = &s->master;
+  m->kind = ENG_MASTER; m->t = &s->t; m->slots = &s->slot[0][0];
+  m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->resi = s->resi; m->tmp = s->tmp; m->tcoef = s->tcoef; m->lvlD = s->lvlD;
+  m->cost0 = g->rdCost0; m->costCoeff = g->rdCostCoeff; m->costSig = g->rdCostSig;
+  m->rateIncUp = g->rdRateIncUp; m->rateIncDown = g->rdRateIncDown; m->sigRateDelta = g->rdSigRateDelta; m->deltaU = g->rdDeltaU;
+  m->predYuv = g->predYuv; m->qtRec = g->qtRec; m->qtCoef = g->qtCoef; m->writePic = 1;
+  for (int i = 0; i < FHC_NENG; i++)
+  {
+    Engine* e = &s->eng[i];
+    EngineShared* x = &s->engSh[i];
+    e->kind = ENG_THREAD; e->t = &s->t; e->slots = x->slots;
+    e->refU = x->refU; e->refF = x->refF; e->flags = x->flags; e->resi = x->resi; e->tmp = x->tmp; e->tcoef = x->tcoef; e->lvlD = x->lvlD;
+    e->cost0 = x->cost0; e->costCoeff = x->costCoeff; e->costSig = x->costSig;
+    e->rateIncUp = x->rateIncUp; e->rateIncDown = x->rateIncDown; e->sigRateDelta = x->sigRateDelta; e->deltaU = x->deltaU;
+    e->predYuv = g->eng[i].predYuv; e->qtRec = g->eng[i].qtRec; e->qtCoef = g->eng[i].qtCoef; e->writePic = 0;
+  }
+}
+
+// One candidate evaluated by thread engine `engIdx` (task t of s->task).  Everything it writes is private
+// (engine scratch + g->eng[engIdx]); it reads the picture planes, the picture-level CTU records, the CU under test
+// and the CU's CI_CURR_BEST contexts, none of which change while tasks run.
+FHC_D void run_task(FrameGlobal* g, Shared* s, int engIdx, int t)
+{
+  Ctx c;
+  c.g = g; c.s = s; c.e = &s->eng[engIdx];
+  Engine* e = c.e;
+  const TaskDesc& td = s->task;
+  const CUMeta* src = &s->cu[td.depth][td.bufIdx];
+  CUMeta* cu = &g->eng[engIdx].cu;
+  const int np = src->nparts;
+  cu->zidx = src->zidx; cu->x = src->x; cu->y = src->y; cu->depth = src->depth; cu->nparts = np; cu->width = src->width;
+  for (int i = 0; i < np; i++)
+  {
+    cu->dep[i] = src->dep[i]; cu->part[i] = src->part[i]; cu->pred[i] = src->pred[i]; cu->ldir[i] = src->ldir[i];
+    cu->cdir[i] = src->cdir[i]; cu->tridx[i] = src->tridx[i];
+    for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
+  }
+  const int mode = td.mode[t];
+  if (td.kind == TASK_LUMA_PU)
+  {
+    // one iteration of the candidate loop of estIntraPredLumaQT (TEncSearch.cpp:2349-2418), bCheckFirst = true
+    uint32_t dist = 0;
+    double cost = 0.0;
+    set_range(cu->ldir, td.partOffset, np >> (2 * td.initTrDepth), mode);
+    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
+    e->resCost = cost; e->resDist = dist;
+  }
+  else
+  {
+    // one iteration of the chroma mode loop of estIntraPredChromaQT (TEncSearch.cpp:2612-2648)
+    uint32_t dist = 0;
+    const int log2cu = ilog2(cu->width);
+    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    set_range(cu->cdir, 0, np, mode);
+    recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
+    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    e->resCost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
+    e->resDist = dist;
+  }
+}
+#ifndef FHC_DEVICE_BUILD
+FHC_D void run_tasks_emu(const Ctx& c)
+{
+  for (int t = 0; t < c.s->task.numTasks; t++) run_task(c.g, c.s, t, t);
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // picture loop (TEncSlice::compressSlice, TEncSlice.cpp:698-983), executed by the master thread
@@ -2151,9 +2432,12 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
 FHC_D void master_compress_picture(const Ctx& c)
 {
   Shared* s = c.s;
+  Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
+  FHC_TIC(tot);
   for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
-  sbac_reset(s, &s->slot[0][CI_CURR_BEST], g->sp.sliceQp);
+  // engines were initialised by the caller (init_engines) before the workers started
+  sbac_reset(s->t, &s->slot[0][CI_CURR_BEST], g->sp.sliceQp);
   const int numCtus = g->wc * g->hc;
   for (int addr = 0; addr < numCtus; addr++)
   {
@@ -2171,21 +2455,26 @@ FHC_D void master_compress_picture(const Ctx& c)
     {
       // preset record: depth 0, partSize/predMode "none", lumaDir DC, everything else 0 (coefficients: zero)
       CUMeta* cu = &s->cu[0][0];
-      Cmd& m = s->cmd;
+      Cmd& m = e->cmd;
       par_zero16(c, o->coefY, 4096 + 1024 + 1024);
       m.a[0] = 0; m.a[1] = 0; m.a[2] = 0; m.a[3] = 256; m.a[4] = 0;
       set_range(cu->dep, 0, 256, 0);
       par(c, OP_CU_TO_OUT);
       cu_init_est(c, cu);
     }
-    sb_copy(&s->go, &s->slot[0][CI_CURR_BEST]);
+    sb_copy(&e->go, slot_of(c, 0, CI_CURR_BEST));
     compress_cu(c, 0);
-    sb_copy(&s->go, &s->slot[0][CI_CURR_BEST]);
-    reset_bits(s);
-    encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
-    sb_copy(&s->slot[0][CI_CURR_BEST], &s->go);
+    sb_copy(&e->go, slot_of(c, 0, CI_CURR_BEST));
+    reset_bits(e);
+    {
+      FHC_TIC(en);
+      encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
+      FHC_TOC2(c, en, PF_ENCODE);
+    }
+    sb_copy(slot_of(c, 0, CI_CURR_BEST), &e->go);
     par(c, OP_CTU_RECO_OUT);
   }
+  FHC_TOC2(c, tot, PF_TOTAL);
 }
 
 }  // namespace fhc

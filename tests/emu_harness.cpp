@@ -19,7 +19,8 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
   g->sp = *sp;
   g->out = out;
   for (int c = 0; c < 3; c++) g->rec[c] = (int16_t*)calloc((size_t)(width * height) >> (c ? 2 : 0), sizeof(int16_t));
-  Ctx ctx = { g, s };
+  init_engines(g, s);
+  Ctx ctx = { g, s, &s->master };
   master_compress_picture(ctx);
   for (int c = 0; c < 3; c++) free(g->rec[c]);
   free(g); free(s);

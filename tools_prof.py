@@ -1,0 +1,20 @@
+import sys, time, ctypes as C; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np
+import fasthevc_b200 as fh, fasthevc_b200.api as api
+api.library_path = lambda: 'fasthevc_b200/libfasthevc_cuda_prof.so'
+from fasthevc_b200.synth import synth_frames
+names=['TOTAL','PAR','RDOQ','COEFBITS','REFS_MASTER','RMD_MASTER','TUBLOCK','BITSQT','CUCOPY','RMD_PAR','ENCODE','TASKS_LUMA','TASKS_CHROMA','LUMA','CHROMA']
+def run(w,h,qp,sigma=6.0):
+    Y,U,V=synth_frames(w,h,1,sigma=sigma)
+    enc=fh.Encoder(w,h,8,max_frames=1)
+    sp=[fh.slice_params_from_qp(qp)]
+    enc.submit(enc.pack_frames(Y,U,V),sp); o=enc.fetch_picture(0)
+    cyc=(C.c_longlong*16)(); cnt=(C.c_longlong*16)()
+    enc.lib.fhc_debug_profile.argtypes=[C.c_void_p,C.c_int,C.c_void_p,C.c_void_p]
+    enc.lib.fhc_debug_profile(enc.ctx,0,cyc,cnt)
+    tot=cyc[0]
+    print('%dx%d qp %d sigma %.0f: total %.1f Mcycles, %d CTUs'%(w,h,qp,sigma,tot/1e6,enc.num_ctus))
+    for i,nm in enumerate(names):
+        if cnt[i]: print('  %-12s %6.1f%%  n=%8d  avg %8.0f cyc'%(nm,100.0*cyc[i]/tot,cnt[i],cyc[i]/cnt[i]))
+    enc.close()
+run(192,128,32)

@@ -1,0 +1,18 @@
+import sys, time; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np
+import fasthevc_b200 as fh
+import __graft_entry__ as ge
+ge.smoke()
+from fasthevc_b200.synth import synth_frames
+def run(w,h,n,qp):
+    Y,U,V=synth_frames(w,h,min(n,4))
+    reps=(n+Y.shape[0]-1)//Y.shape[0]
+    Y=np.concatenate([Y]*reps)[:n]; U=np.concatenate([U]*reps)[:n]; V=np.concatenate([V]*reps)[:n]
+    enc=fh.Encoder(w,h,8,max_frames=n)
+    sp=[fh.slice_params_from_qp(qp)]*n
+    enc.submit(enc.pack_frames(Y,U,V),sp); o=enc.fetch_picture(0)
+    ms=enc.run_resident(sp)
+    print('%dx%d n=%d qp=%d: kernel %.1f ms -> %.2f fps, %.1f CTU/s'%(w,h,n,qp,ms,n/(ms/1e3),n*enc.num_ctus/(ms/1e3)), flush=True)
+    enc.close()
+for n in [int(a) for a in sys.argv[1:]] or [1,148,296]:
+    run(416,240,n,32)
