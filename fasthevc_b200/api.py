@@ -42,7 +42,7 @@ EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "f
 
 
 def library_path():
-    return os.path.join(_HERE, "libfasthevc_cuda.so")
+    return os.environ.get("FHC_LIBRARY", os.path.join(_HERE, "libfasthevc_cuda.so"))
 
 
 def build_library(force=False, verbose=False):

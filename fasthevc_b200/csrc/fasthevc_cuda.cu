@@ -9,12 +9,15 @@
 #include "fhc_tables.h"
 
 using namespace fhc;
+#ifndef FHC_MIN_BLOCKS
+#define FHC_MIN_BLOCKS 2
+#endif
 extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 
 // ----------------------------------------------------------------------------------------------
 // kernel: one block per picture; thread 0 = master, lanes 1..31 of warp 0 retire, warps 1.. = workers
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 + FHC_NWORK, 2) fhc_compress_pictures_kernel(FrameGlobal* frames, const Tables* tables)
+__global__ void __launch_bounds__(32 + FHC_NWORK, FHC_MIN_BLOCKS) fhc_compress_pictures_kernel(FrameGlobal* frames, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared* s = reinterpret_cast<Shared*>(smem_raw);

@@ -69,6 +69,7 @@ struct Tables
   int16_t  angTable[9], invAngTable[9];
   uint8_t  chromaScale[58];       // g_aucChromaScale[CHROMA_420]
   uint8_t  ctxIndMap4x4[16];
+  uint8_t  sigCnt[4][16];         // getSigCtxInc neighbourhood term by (patternSigCtx, position inside the 4x4 group)
   uint8_t  intraFilterThr[5];
   double   errScale[2][4][6];     // [chType][log2-2][qp rem]
 };
@@ -154,6 +155,7 @@ struct Engine
   int16_t (*qtRec)[6144];
   int16_t (*qtCoef)[6144];
   int writePic;                   // reconstruct into the picture plane too (master only)
+  uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
   // task result (thread engines)
   double resCost;
   uint32_t resDist;
@@ -394,6 +396,14 @@ FHC_DH uint32_t had4(int* d)
   return (uint32_t)((s + 1) >> 1);
 }
 
+FHC_DH void atomic_or_u32(uint32_t* p, uint32_t v)
+{
+#ifdef FHC_DEVICE_BUILD
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
 FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v)
 {
 #ifdef FHC_DEVICE_BUILD
@@ -610,6 +620,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         e->lvlD[p] = ld;
         e->cost0[p] = err * err * errScale;
         e->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
+        if (m) atomic_or_u32(&e->cgNZ[p >> 9], 1u << ((p >> 4) & 31));
       }
     }
     break;
@@ -950,18 +961,11 @@ FHC_DH void code_chroma_dir(const Ctx& c, const CUMeta* cu, int relIdx)         
 }
 FHC_DH int sig_ctx_inc(const Tables& t, int pat, int firstCtx, int rasterPos, int log2n, int isChroma)   // TComTrQuant.cpp:2707
 {
+  if (rasterPos == 0) return 0;
+  if (log2n == 2) return firstCtx + t.ctxIndMap4x4[rasterPos];
   const int posY = rasterPos >> log2n, posX = rasterPos - (posY << log2n);
-  int cnt;
-  if (posX + posY == 0) return 0;
-  if (log2n == 2) return firstCtx + t.ctxIndMap4x4[4 * posY + posX];
-  switch (pat)
-  {
-  case 0: { const int t = (posX & 3) + (posY & 3); cnt = (t >= 3) ? 0 : ((t >= 1) ? 1 : 2); } break;
-  case 1: { const int y = posY & 3; cnt = (y >= 2) ? 0 : ((y >= 1) ? 1 : 2); } break;
-  case 2: { const int x = posX & 3; cnt = (x >= 2) ? 0 : ((x >= 1) ? 1 : 2); } break;
-  default: cnt = 2; break;
-  }
-  return firstCtx + ((((posX >> 2) + (posY >> 2)) > 0 ? (isChroma ? 0 : 3) : 0) + cnt);
+  const int cnt = t.sigCnt[pat][((posY & 3) << 2) | (posX & 3)];
+  return firstCtx + ((((posX | posY) >> 2) != 0 && !isChroma) ? 3 : 0) + cnt;
 }
 FHC_DH int first_sig_ctx(int log2n, int scanType, int isChroma)
 {
@@ -1176,19 +1180,20 @@ FHC_DH int ic_rate(const Engine* e, uint32_t absLevel, int ctxOne, int ctxAbs, u
   return rate;
 }
 FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
-                            uint32_t maxAbsLevel, int ctxSig, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx,
-                            int qBits, double errScale, int isLast)
+                            uint32_t maxAbsLevel, double sigCost0, double sigCost1, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx,
+                            uint32_t c2Idx, int qBits, double errScale, int isLast)
 {
+  // sigCost0/1 = lambda * bits(sig_coeff_flag = 0/1) of this position's context (xGetRateSigCoef)
   double currCostSig = 0;
   uint32_t best = 0;
   if (!isLast && maxAbsLevel < 3)
   {
-    *codedCostSig = dmul(lambda, (double)ctx_bits(e, ctxSig, 0));
+    *codedCostSig = sigCost0;
     *codedCost = dadd(*codedCost0, *codedCostSig);
     if (maxAbsLevel == 0) return 0;
   }
   else *codedCost = FHC_MAX_COST;
-  if (!isLast) currCostSig = dmul(lambda, (double)ctx_bits(e, ctxSig, 1));
+  if (!isLast) currCostSig = sigCost1;
   const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
   for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
   {
@@ -1229,10 +1234,57 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
 
   for (int i = 0; i < cgNum; i++) { costCGSig[i] = 0; cgFlag[i] = 0; }
 
+  // lambda * bits of sig_coeff_flag = 0 / 1 and the rate difference, per context of this channel (contexts do not
+  // change while a TU is being quantised): replaces estBitsSbacStruct::significantBits (TEncSbac.cpp:1772)
+  double sigC0[28], sigC1[28];
+  int sigDelta[28];
+  {
+    const int nSig = isChroma ? 16 : 28;
+    for (int i = 0; i < nSig; i++)
+    {
+      const int b0 = ctx_bits(e, sigBase + i, 0), b1 = ctx_bits(e, sigBase + i, 1);
+      sigC0[i] = dmul(lambda, (double)b0); sigC1[i] = dmul(lambda, (double)b1); sigDelta[i] = b1 - b0;
+    }
+  }
+
   for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
   {
     const int cgBlk = scanCG[cgScanPos], cgY = cgBlk / wg, cgX = cgBlk - cgY * wg;
+    const int cgHasLevel = (e->cgNZ[cgScanPos >> 5] >> (cgScanPos & 31)) & 1;
+    if (!cgHasLevel && lastScanPos < 0)
+    {
+      // nothing coded yet and nothing to code here: only the uncoded distortion accumulates
+      for (int posInCG = 15; posInCG >= 0; posInCG--)
+      {
+        const double c0 = costCoeff0[cgScanPos * 16 + posInCG];
+        blockUncoded = dadd(blockUncoded, c0);
+        baseCost = dadd(baseCost, c0);
+      }
+      continue;
+    }
     const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
+    if (!cgHasLevel && cgScanPos > 0)
+    {
+      // group without any candidate level below the last position: every coefficient takes "level 0" and the group
+      // ends up with coded_sub_block_flag = 0; none of the per-coefficient arrays of this group is read again
+      double sigCost = 0;
+      for (int posInCG = 15; posInCG >= 0; posInCG--)
+      {
+        const int scanPos = cgScanPos * 16 + posInCG;
+        const double c0 = costCoeff0[scanPos];
+        const double cs = sigC0[sig_ctx_inc(*e->t, pat, firstSig, (int)scan[scanPos], log2n, isChroma)];
+        blockUncoded = dadd(blockUncoded, c0);
+        baseCost = dadd(baseCost, dadd(c0, cs));
+        sigCost = dadd(sigCost, cs);
+      }
+      ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && (cgScanPos - 1) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
+      c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
+      const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
+      const double cgc = dmul(lambda, (double)ctx_bits(e, cx, 0));
+      baseCost = dadd(baseCost, dsub(cgc, sigCost));
+      costCGSig[cgScanPos] = cgc;
+      continue;
+    }
     double sigCost = 0, sigCost0 = 0, codedLevelAndDist = 0, uncodedDist = 0;
     int nnzBeforePos0 = 0;
     for (int posInCG = 15; posInCG >= 0; posInCG--)
@@ -1246,8 +1298,6 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       {
         if (maxAbsLevel == 0)
         {
-          // before the first non-zero level nothing but the uncoded distortion accumulates; the per-position
-          // arrays read later (cost/sig/rate/delta) only matter for scanPos <= lastScanPos
           baseCost = dadd(baseCost, costCoeff0[scanPos]);
           continue;
         }
@@ -1255,21 +1305,40 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
         ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && (scanPos >> 4) > 0) ? 2 : 0));
         cgLastScanPos = cgScanPos;
       }
+      const int ctxOne = CTX_ONE + 4 * (int)ctxSet + c1;
+      if (maxAbsLevel == 0)
+      {
+        // "level 0" is the only candidate (xGetCodedLevel returns early); no state of the level coder changes
+        const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
+        const double cs = sigC0[sc], cc = dadd(costCoeff0[scanPos], cs);
+        costSig[scanPos] = cs; costCoeff[scanPos] = cc;
+        sigRateDelta[blkPos] = sigDelta[sc];
+        deltaU[blkPos] = levelDouble >> (qBits - 8);
+        rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0); rateIncDown[blkPos] = 0;
+        baseCost = dadd(baseCost, cc);
+        if (posInCG == 0 && scanPos > 0)
+        {
+          ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && ((scanPos - 1) >> 4) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
+          c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
+        }
+        sigCost = dadd(sigCost, cs);
+        if (posInCG == 0) sigCost0 = cs;
+        continue;
+      }
       {
         uint32_t level;
-        const int ctxOne = CTX_ONE + 4 * (int)ctxSet + c1;
         const int ctxAbs = CTX_ABS + (int)ctxSet + c2;
         costCoeff[scanPos] = 0; costSig[scanPos] = 0;
         rateIncUp[blkPos] = 0; rateIncDown[blkPos] = 0; sigRateDelta[blkPos] = 0;
         if (scanPos == lastScanPos)
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
-                              sigBase, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
+                              0.0, 0.0, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
         else
         {
-          const int ctxSig = sigBase + sig_ctx_inc(s->t, pat, firstSig, (int)blkPos, log2n, isChroma);
+          const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
-                              ctxSig, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
-          sigRateDelta[blkPos] = ctx_bits(e, ctxSig, 1) - ctx_bits(e, ctxSig, 0);
+                              sigC0[sc], sigC1[sc], ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
+          sigRateDelta[blkPos] = sigDelta[sc];
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
         if (level > 0)
@@ -1570,6 +1639,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   const int scanType = coef_scan_idx(cu, relIdx, n, comp);
   m.a[0] = log2n; m.a[1] = (comp == 0 && log2n == 2); m.a[2] = ts; m.a[3] = scanType; m.a[4] = quant_scale(q.rem);
   m.a[5] = 14 + q.per + (15 - g->bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
+  e->cgNZ[0] = 0; e->cgNZ[1] = 0;
   par(c, OP_FWD_QUANT);
   const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
   const uint32_t absSum = rdoq_pass(c, cu, relIdx, comp, log2n, cbfCtx);

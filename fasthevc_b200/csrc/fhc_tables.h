@@ -74,6 +74,17 @@ static void build_tables(Tables* t, int bitDepth)
   memcpy(t->chromaScale, cs, sizeof(cs));
   static const uint8_t map4[16] = { 0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8 };
   memcpy(t->ctxIndMap4x4, map4, sizeof(map4));
+  for (int pat = 0; pat < 4; pat++)
+    for (int yy = 0; yy < 4; yy++)
+      for (int xx = 0; xx < 4; xx++)
+      {
+        int cnt;
+        if (pat == 0) { const int tt = xx + yy; cnt = (tt >= 3) ? 0 : ((tt >= 1) ? 1 : 2); }
+        else if (pat == 1) cnt = (yy >= 2) ? 0 : ((yy >= 1) ? 1 : 2);
+        else if (pat == 2) cnt = (xx >= 2) ? 0 : ((xx >= 1) ? 1 : 2);
+        else cnt = 2;
+        t->sigCnt[pat][yy * 4 + xx] = (uint8_t)cnt;
+      }
   static const uint8_t thr[5] = { 10, 7, 1, 0, 10 };
   memcpy(t->intraFilterThr, thr, sizeof(thr));
   static const uint8_t nextMps[128] = {
