@@ -10,7 +10,7 @@
 
 using namespace fhc;
 #ifndef FHC_MIN_BLOCKS
-#define FHC_MIN_BLOCKS 2
+#define FHC_MIN_BLOCKS 1
 #endif
 extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 

@@ -47,7 +47,9 @@ enum {
   CTX_LASTX = 68, CTX_LASTY = 98, CTX_ONE = 128, CTX_ABS = 152, CTX_TS = 158, NUM_CTX = 160
 };
 #define FHC_MAX_COST 1.7e+308
-#define FHC_NWORK 320            /* worker threads per block (10 warps); lane 0 of each warp doubles as a thread engine */
+#ifndef FHC_NWORK
+#define FHC_NWORK 320            /* worker threads per block; every worker warp doubles as a candidate engine */
+#endif
 
 // layout of the 6144-sample "YUV" buffers: Y at 0, Cb at 4096, Cr at 5120
 FHC_DH int comp_off(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
@@ -82,10 +84,19 @@ struct CUMeta
   int zidx, x, y, depth, nparts, width;
   uint32_t dist, bits, bins, pad;
   double cost;
-  uint8_t dep[256], part[256], pred[256], ldir[256], cdir[256], tridx[256], cbf[3][256], ts[3][256];
+  // per-partition arrays (z-scan inside the CU); storage is sized by depth: 256 >> 2*depth entries each
+  uint8_t *dep, *part, *pred, *ldir, *cdir, *tridx;
+  uint8_t* cbf[3];
+  uint8_t* ts[3];
 };
+FHC_HD void cu_bind(CUMeta* cu, uint8_t* store, int cap)
+{
+  cu->dep = store; cu->part = store + cap; cu->pred = store + 2 * cap; cu->ldir = store + 3 * cap; cu->cdir = store + 4 * cap;
+  cu->tridx = store + 5 * cap;
+  for (int c = 0; c < 3; c++) { cu->cbf[c] = store + (6 + c) * cap; cu->ts[c] = store + (9 + c) * cap; }
+}
 
-#define FHC_NENG (FHC_NWORK / 32)   /* thread engines = lane 0 of every worker warp */
+#define FHC_NENG (FHC_NWORK / 32)   /* one engine per worker warp */
 #define FHC_ENG_COEFS 64           /* thread engines handle blocks up to 8x8 */
 
 // private global scratch of one thread engine (same layouts as the master's buffers)
@@ -95,6 +106,10 @@ struct EngineGlobal
   int16_t qtRec[4][6144];
   int16_t qtCoef[4][6144];
   CUMeta cu;
+  uint8_t cuStore[12 * 4];        // engines only see depth-3 CUs (4 partitions)
+  // result of the engine's best task of the current dispatch (task order, strict <)
+  int16_t bestCoef[3][64], bestReco[3][64];
+  uint8_t bestTrIdx[4], bestCbf[3][4], bestTs[3][4];
 };
 
 // per-picture state in global memory
@@ -110,9 +125,6 @@ struct FrameGlobal
   int16_t predYuv[6144];          // prediction -> reconstruction scratch of the CU under test
   int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
   int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
-  // RDOQ per-coefficient state of the master (up to 32x32); L1-resident
-  double rdCost0[1024], rdCostCoeff[1024], rdCostSig[1024];
-  int32_t rdRateIncUp[1024], rdRateIncDown[1024], rdSigRateDelta[1024], rdDeltaU[1024];
   EngineGlobal eng[FHC_NENG];
   long long prof[16], profN[16];  // cycle counters of the master thread (FHC_PROFILE builds)
 };
@@ -156,9 +168,14 @@ struct Engine
   int16_t (*qtCoef)[6144];
   int writePic;                   // reconstruct into the picture plane too (master only)
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
-  // task result (thread engines)
+  double* costCGSig;               // RDOQ per-group / per-context scratch (kept out of local memory: a single active
+  uint8_t *cgFlag, *cgFlagCode;    // lane wastes 7/8 of every local-memory sector)
+  double *sigC0, *sigC1;
+  int32_t* sigDelta;
+  // engine result: best task of the current dispatch
   double resCost;
   uint32_t resDist;
+  int resTask;
 };
 
 struct EngineShared                // shared-memory arrays of one thread engine
@@ -170,6 +187,9 @@ struct EngineShared                // shared-memory arrays of one thread engine
   int32_t tmp[FHC_ENG_COEFS], tcoef[FHC_ENG_COEFS], lvlD[FHC_ENG_COEFS];
   double cost0[FHC_ENG_COEFS], costCoeff[FHC_ENG_COEFS], costSig[FHC_ENG_COEFS];
   int32_t rateIncUp[FHC_ENG_COEFS], rateIncDown[FHC_ENG_COEFS], sigRateDelta[FHC_ENG_COEFS], deltaU[FHC_ENG_COEFS];
+  double costCGSig[4], sigC0[28], sigC1[28];
+  int32_t sigDelta[28];
+  uint8_t cgFlag[4], cgFlagCode[4];
 };
 
 struct TaskDesc
@@ -180,13 +200,21 @@ struct TaskDesc
   int mode[12];
 };
 
+struct FrameParams                 // hot read-only copy of the picture header (shared memory)
+{
+  int32_t width, height, bitDepth, sampleBytes, wc, hc;
+  fhc_slice_params sp;
+};
+
 struct Shared
 {
   Tables t;
+  FrameParams fp;
   Sbac slot[5][CI_NUM];
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
   uint8_t bestIdx[4];
   CUMeta cu[4][2];
+  uint8_t cuStore[2 * 12 * (256 + 64 + 16 + 4)];
   Engine master;
   Engine eng[FHC_NENG];
   EngineShared engSh[FHC_NENG];
@@ -199,6 +227,12 @@ struct Shared
   int16_t rmdPred[4096];
   uint32_t satd[36];
   uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];
+  double costCGSig[64], sigC0[28], sigC1[28];
+  int32_t sigDelta[28];
+  uint8_t cgFlag[64], cgFlagCode[64];
+  // RDOQ per-coefficient state of the master (up to 32x32)
+  double rdCost0[1024], rdCostCoeff[1024], rdCostSig[1024];
+  int32_t rdRateIncUp[1024], rdRateIncDown[1024], rdSigRateDelta[1024], rdDeltaU[1024];
 };
 
 struct Ctx { FrameGlobal* g; Shared* s; Engine* e; };
@@ -256,7 +290,7 @@ FHC_DH void par(const Ctx& c, int op)
   FHC_TOC2(c, par, PF_PAR);
 }
 // lanes 1..31 of a warp whose lane 0 runs a task
-FHC_DH void engine_lanes_loop(const Ctx& c, int lane)
+FHC_NOINLINE void engine_lanes_loop(const Ctx& c, int lane)
 {
   for (;;)
   {
@@ -297,11 +331,11 @@ FHC_DH int imin(int a, int b) { return a < b ? a : b; }
 FHC_DH int imax(int a, int b) { return a > b ? a : b; }
 FHC_DH int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 
-FHC_DH int org_at(const FrameGlobal* g, int comp, int idx)
+FHC_DH int org_at(const FrameGlobal* g, int sampleBytes, int comp, int idx)
 {
-  return g->sampleBytes == 1 ? (int)((const uint8_t*)g->org[comp])[idx] : (int)((const uint16_t*)g->org[comp])[idx];
+  return sampleBytes == 1 ? (int)((const uint8_t*)g->org[comp])[idx] : (int)((const uint16_t*)g->org[comp])[idx];
 }
-FHC_DH int plane_stride(const FrameGlobal* g, int comp) { return g->width >> (comp ? 1 : 0); }
+FHC_DH int plane_stride(const Shared* s, int comp) { return s->fp.width >> (comp ? 1 : 0); }
 FHC_DH const uint16_t* scan_tab(const Tables& t, int type, int log2n) { return t.scan + t.scanOff[type][log2n - 2]; }
 FHC_DH const uint8_t* scan_cg(const Tables& t, int type, int log2n) { return t.scanCG[type] + cg_off(log2n - 2); }
 FHC_DH int tcoefm(const Tables& t, int n, int k, int j, int useDst)
@@ -429,11 +463,11 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   {
     // a0 comp, a1 n, a2 nu, a3 us, a4 plane offset of the block origin, a5 wantFilt, a6 numAvail, a7 total units
     const int comp = a[0], n = a[1], nu = a[2], us = a[3], org0 = a[4], total = a[7];
-    const int stride = plane_stride(g, comp);
+    const int stride = plane_stride(s, comp);
     const int16_t* origin = g->rec[comp] + org0;
     if (phase == 0)
     {
-      const int dc = 1 << (g->bitDepth - 1);
+      const int dc = 1 << (s->fp.bitDepth - 1);
       for (int i = w; i < 4 * n + 1; i += nw)
       {
         // unit of this sample: left part bottom-up, corner, top part
@@ -478,7 +512,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         int strong = (comp == 0) && n >= 32;
         if (strong)
         {
-          const int thr = 1 << (g->bitDepth - 5);
+          const int thr = 1 << (s->fp.bitDepth - 5);
           strong = (iabs((bl + tl) - 2 * line[n]) < thr) && (iabs((tl + tr) - 2 * line[3 * n]) < thr);
         }
         const int shift = ilog2(2 * n);
@@ -512,12 +546,12 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
         const int x = sidx & (n - 1), y = sidx >> log2n;
         const int16_t* line = use_filtered_refs(s->t, 0, mode, log2n) ? e->refF : e->refU;
-        s->rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, g->bitDepth, e->refDc);
+        s->rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, s->fp.bitDepth, e->refDc);
       }
     }
     else
     {
-      const int stride = plane_stride(g, 0);
+      const int stride = plane_stride(s, 0);
       if (n >= 8)
       {
         const int tps = n >> 3, tiles = tps * tps, items = (m1 - m0) * tiles;
@@ -527,7 +561,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           int m[64];
           for (int yy = 0; yy < 8; yy++)
             for (int xx = 0; xx < 8; xx++)
-              m[yy * 8 + xx] = org_at(g, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
+              m[yy * 8 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
           atomic_add_u32(&s->satd[m0 + mi], had8(m));
         }
       }
@@ -537,7 +571,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         {
           int d[16];
           for (int yy = 0; yy < 4; yy++)
-            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, 0, a[1] + yy * stride + xx) - s->rmdPred[mi * 16 + yy * 4 + xx];
+            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + yy * stride + xx) - s->rmdPred[mi * 16 + yy * 4 + xx];
           atomic_add_u32(&s->satd[m0 + mi], had4(d));
         }
       }
@@ -550,7 +584,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     // a7 save/load (0 none, 1 save to tsPred, 2 load from tsPred)
     const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n;
     int16_t* pred = e->predYuv + a[4];
-    const int ps = a[5], stride = plane_stride(g, comp);
+    const int ps = a[5], stride = plane_stride(s, comp);
     const int16_t* line = a[3] ? e->refF : e->refU;
     for (int i = w; i < n2; i += nw)
     {
@@ -559,11 +593,11 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       if (a[7] == 2) v = e->tsPred[comp][i];
       else
       {
-        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, g->bitDepth, e->refDc);
+        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, s->fp.bitDepth, e->refDc);
         if (a[7] == 1) e->tsPred[comp][i] = (int16_t)v;
       }
       pred[y * ps + x] = (int16_t)v;
-      e->resi[i] = (int16_t)(org_at(g, comp, a[6] + y * stride + x) - v);
+      e->resi[i] = (int16_t)(org_at(g, s->fp.sampleBytes, comp, a[6] + y * stride + x) - v);
     }
     break;
   }
@@ -571,7 +605,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   {
     // a0 log2n, a1 useDst, a2 transformSkip, a3 scanType, a4 quantCoef, a5 qBits, a6 chType(0/1), a7 qp rem
     // out: tcoef[] raster, lvlD[scanPos], rd.cost0[scanPos], tmp[blkPos] = uiMaxAbsLevel
-    const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = g->bitDepth;
+    const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
     if (a[2])
     {
       if (phase == 1)
@@ -636,7 +670,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   {
     // a0 comp, a1 log2n, a2 useDst, a3 transformSkip, a4 absSum>0, a5 qp per, a6 qp rem,
     // a7 predYuv offset, a8 predYuv stride, a9 qt layer, a10 qtRec offset, a11 rec plane offset, a12 org plane offset
-    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = g->bitDepth;
+    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
     if (a[4])
     {
       if (phase == 0)
@@ -695,7 +729,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       int16_t* reco = e->predYuv + a[7];
       int16_t* recQt = e->qtRec[a[9]] + a[10];
       int16_t* recPic = g->rec[comp] + a[11];
-      const int ps = a[8], qs = 64 >> (comp ? 1 : 0), stride = plane_stride(g, comp), shift = (bd - 8) << 1;
+      const int ps = a[8], qs = 64 >> (comp ? 1 : 0), stride = plane_stride(s, comp), shift = (bd - 8) << 1;
       uint32_t acc = 0;
       for (int i = w; i < n2; i += nw)
       {
@@ -705,7 +739,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         reco[y * ps + x] = (int16_t)v;
         recQt[y * qs + x] = (int16_t)v;
         if (e->writePic) recPic[y * stride + x] = (int16_t)v;
-        const int d = v - org_at(g, comp, a[12] + y * stride + x);
+        const int d = v - org_at(g, s->fp.sampleBytes, comp, a[12] + y * stride + x);
         acc += (uint32_t)((d * d) >> shift);
       }
       if (acc) atomic_add_u32(&e->sse, acc);
@@ -748,7 +782,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       const int k = i - comp_off(comp), xx = k & (nn - 1), yy = k / nn;
       const int px = (s->ctuPelX >> sh) + xx, py = (s->ctuPelY >> sh) + yy;
       int16_t* d = comp == 0 ? o->recoY : (comp == 1 ? o->recoCb : o->recoCr);
-      d[k] = (px < (g->width >> sh) && py < (g->height >> sh)) ? g->rec[comp][py * plane_stride(g, comp) + px] : (int16_t)0;
+      d[k] = (px < (s->fp.width >> sh) && py < (s->fp.height >> sh)) ? g->rec[comp][py * plane_stride(s, comp) + px] : (int16_t)0;
     }
     break;
   }
@@ -834,12 +868,12 @@ FHC_DH void sbac_reset(const Tables& t, Sbac* sb, int qp)                       
   sb->frac = 0;
 }
 #ifdef FHC_DEVICE_BUILD
-FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return __dadd_rn((double)dist, __dmul_rn((double)bits, c.g->sp.lambda)); }
+FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return __dadd_rn((double)dist, __dmul_rn((double)bits, c.s->fp.sp.lambda)); }
 FHC_DH double dmul(double a, double b) { return __dmul_rn(a, b); }
 FHC_DH double dadd(double a, double b) { return __dadd_rn(a, b); }
 FHC_DH double dsub(double a, double b) { return __dsub_rn(a, b); }
 #else
-FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return (double)dist + ((double)bits * c.g->sp.lambda); }
+FHC_DH double rd_cost(const Ctx& c, uint32_t bits, uint32_t dist) { return (double)dist + ((double)bits * c.s->fp.sp.lambda); }
 FHC_DH double dmul(double a, double b) { return a * b; }
 FHC_DH double dadd(double a, double b) { return a + b; }
 FHC_DH double dsub(double a, double b) { return a - b; }
@@ -851,6 +885,16 @@ FHC_DH Sbac* slot_of(const Ctx& c, int depth, int ci)
 {
   if (c.e->kind == ENG_MASTER || ci == CI_CURR_BEST) return &c.s->slot[depth][ci];
   return &c.e->slots[ci == CI_QT_TRAFO_ROOT ? 0 : (ci == CI_TEMP_BEST ? 1 : 2)];
+}
+
+// winner of a dispatch: lowest cost, ties to the lowest task index (= the sequential strict-< scan of the reference)
+FHC_DH int best_engine(const Shared* s)
+{
+  const int ne = imin(FHC_NENG, s->task.numTasks);
+  int be = 0;
+  for (int i = 1; i < ne; i++)
+    if (s->eng[i].resCost < s->eng[be].resCost || (s->eng[i].resCost == s->eng[be].resCost && s->eng[i].resTask < s->eng[be].resTask)) be = i;
+  return be;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -886,7 +930,7 @@ FHC_DH int nb_above(const Ctx& c, const CUMeta* cu, int zabs, int f, int planarA
     return cu_field(cu, nz - cu->zidx, f);
   }
   if (planarAtCtuBoundary || s->ctuY == 0) return -1;
-  return ctu_field(&c.g->out[s->ctuAddr - c.g->wc], s->t.r2z[r + 240], f);
+  return ctu_field(&c.g->out[s->ctuAddr - c.s->fp.wc], s->t.r2z[r + 240], f);
 }
 FHC_DH int get_mpm(const Ctx& c, const CUMeta* cu, int relIdx, int mpm[3])
 {
@@ -1021,7 +1065,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   const int wg = n >> 2;
   const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
-  uint8_t cgFlag[64];
+  uint8_t* cgFlag = e->cgFlagCode;
   int scanPosLast = -1, posLast = 0;
 
   if (log2n == 2) enc_bin(e, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
@@ -1139,12 +1183,12 @@ FHC_DH void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp, const
 struct QpParam { int per, rem; };
 FHC_DH QpParam qp_param(const Ctx& c, int comp)                                                // TComTrQuant.cpp:71-119
 {
-  const int bdOff = 6 * (c.g->bitDepth - 8);
+  const int bdOff = 6 * (c.s->fp.bitDepth - 8);
   int base;
-  if (comp == 0) base = c.g->sp.sliceQp + bdOff;
+  if (comp == 0) base = c.s->fp.sp.sliceQp + bdOff;
   else
   {
-    base = clip3(-bdOff, 57, c.g->sp.sliceQp);
+    base = clip3(-bdOff, 57, c.s->fp.sp.sliceQp);
     base = base < 0 ? base + bdOff : c.s->t.chromaScale[base] + bdOff;
   }
   QpParam q; q.per = base / 6; q.rem = base % 6;
@@ -1209,7 +1253,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
-  const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.g->bitDepth;
+  const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.s->fp.bitDepth;
   const QpParam q = qp_param(c, comp);
   const int qBits = 14 + q.per + (15 - bd - log2n);
   const double errScale = s->t.errScale[isChroma][log2n - 2][q.rem];
@@ -1225,8 +1269,8 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
   double* costCoeff0 = e->cost0; double* costCoeff = e->costCoeff; double* costSig = e->costSig;
   int32_t* rateIncUp = e->rateIncUp; int32_t* rateIncDown = e->rateIncDown;
   int32_t* sigRateDelta = e->sigRateDelta; int32_t* deltaU = e->deltaU;
-  double costCGSig[64];
-  uint8_t cgFlag[64];
+  double* costCGSig = e->costCGSig;
+  uint8_t* cgFlag = e->cgFlag;
   double blockUncoded = 0, baseCost = 0;
   int cgLastScanPos = -1, lastScanPos = -1, c1 = 1, c2 = 0;
   uint32_t ctxSet = 0, c1Idx = 0, c2Idx = 0, goRice = 0, absSum = 0;
@@ -1236,8 +1280,8 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
 
   // lambda * bits of sig_coeff_flag = 0 / 1 and the rate difference, per context of this channel (contexts do not
   // change while a TU is being quantised): replaces estBitsSbacStruct::significantBits (TEncSbac.cpp:1772)
-  double sigC0[28], sigC1[28];
-  int sigDelta[28];
+  double* sigC0 = e->sigC0; double* sigC1 = e->sigC1;
+  int32_t* sigDelta = e->sigDelta;
   {
     const int nSig = isChroma ? 16 : 28;
     for (int i = 0; i < nSig; i++)
@@ -1569,17 +1613,17 @@ FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int 
     for (int i = 1; i <= nu; i++)
     {
       int av;
-      if (s->ctuPelX + (rRT & 15) * 4 + 4 * i >= g->width) av = 0;
+      if (s->ctuPelX + (rRT & 15) * 4 + 4 * i >= s->fp.width) av = 0;
       else if ((rRT & 15) < 16 - i) av = (uy != 0) ? (zRT > s->t.r2z[rRT - 16 + i]) : (s->ctuY > 0);
       else if (uy != 0) av = 0;
-      else av = (s->ctuY > 0) && (s->ctuX + 1 < g->wc);
+      else av = (s->ctuY > 0) && (s->ctuX + 1 < s->fp.wc);
       flags[3 * nu + i] = (uint8_t)av;
     }
     const int rLB = rLT + (nu - 1) * 16, zLB = s->t.r2z[rLB];
     for (int i = 1; i <= nu; i++)
     {
       int av;
-      if (s->ctuPelY + (rLB >> 4) * 4 + 4 * i >= g->height) av = 0;
+      if (s->ctuPelY + (rLB >> 4) * 4 + 4 * i >= s->fp.height) av = 0;
       else if ((rLB >> 4) < 16 - i) av = (ux != 0) ? (zLB > s->t.r2z[rLB + 16 * i - 1]) : (s->ctuX > 0);
       else av = 0;
       flags[nu - i] = (uint8_t)av;
@@ -1588,7 +1632,7 @@ FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int 
   for (int i = 0; i < total; i++) numAvail += flags[i];
   Cmd& m = e->cmd;
   const int px = (s->ctuPelX + ux * 4) >> (comp ? 1 : 0), py = (s->ctuPelY + uy * 4) >> (comp ? 1 : 0);
-  m.a[0] = comp; m.a[1] = n; m.a[2] = nu; m.a[3] = us; m.a[4] = py * plane_stride(g, comp) + px; m.a[5] = wantFilt;
+  m.a[0] = comp; m.a[1] = n; m.a[2] = nu; m.a[3] = us; m.a[4] = py * plane_stride(s, comp) + px; m.a[5] = wantFilt;
   m.a[6] = numAvail; m.a[7] = total;
   FHC_TOC2(c, rf, PF_REFS_MASTER);
   par(c, OP_REFS);
@@ -1608,7 +1652,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   const int bx = rel_x(s, relIdx) >> isChroma, by = rel_y(s, relIdx) >> isChroma;
   const int qtLayer = 5 - lumaLog2;
   const int picX = (cu->x >> isChroma) + bx, picY = (cu->y >> isChroma) + by;
-  const int stride = plane_stride(g, comp);
+  const int stride = plane_stride(s, comp);
   const int predOff = comp_off(comp) + by * cuW + bx;
   const int qtOff = comp_off(comp) + by * (64 >> isChroma) + bx;
   const int coefOff = comp_off(comp) + (isChroma ? relIdx * 4 : relIdx * 16);
@@ -1635,10 +1679,10 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   par(c, OP_PRED_RESI);
 
   // transform + RDOQ (TComTrQuant::transformNxN :1450)
-  e->rdoqLambda = g->sp.rdoqLambda[comp];
+  e->rdoqLambda = s->fp.sp.rdoqLambda[comp];
   const int scanType = coef_scan_idx(cu, relIdx, n, comp);
   m.a[0] = log2n; m.a[1] = (comp == 0 && log2n == 2); m.a[2] = ts; m.a[3] = scanType; m.a[4] = quant_scale(q.rem);
-  m.a[5] = 14 + q.per + (15 - g->bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
+  m.a[5] = 14 + q.per + (15 - s->fp.bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
   e->cgNZ[0] = 0; e->cgNZ[1] = 0;
   par(c, OP_FWD_QUANT);
   const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
@@ -1655,7 +1699,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   m.a[7] = predOff; m.a[8] = cuW; m.a[9] = qtLayer; m.a[10] = qtOff; m.a[11] = picY * stride + picX; m.a[12] = picY * stride + picX;
   par(c, OP_INV_RECON);
   uint32_t dist = e->sse;
-  if (isChroma) dist = (uint32_t)dmul(g->sp.chromaDistWeight[comp - 1], (double)dist);          // TComRdCost.cpp:352
+  if (isChroma) dist = (uint32_t)dmul(s->fp.sp.chromaDistWeight[comp - 1], (double)dist);          // TComRdCost.cpp:352
   FHC_TOC2(c, tu, PF_TUBLOCK);
   return dist;
 }
@@ -1755,7 +1799,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   const int layer = 5 - log2n;
   int16_t* qtCoefBlk = e->qtCoef[layer < 0 ? 0 : layer] + relIdx * 16;
   int16_t* qtRecBlk = e->qtRec[layer < 0 ? 0 : layer] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx);
-  int16_t* picBlk = g->rec[0] + (cu->y + rel_y(s, relIdx)) * plane_stride(g, 0) + cu->x + rel_x(s, relIdx);
+  int16_t* picBlk = g->rec[0] + (cu->y + rel_y(s, relIdx)) * plane_stride(s, 0) + cu->x + rel_x(s, relIdx);
   if (checkFirst && checkFull) checkSplit = 0;
 
   if (checkFull)
@@ -1786,7 +1830,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
       set_range(cu->ts[0], relIdx, numParts, bestModeId);
       if (bestModeId == 0)
       {
-        const int ps = plane_stride(g, 0);
+        const int ps = plane_stride(s, 0);
         for (int i = 0; i < 16; i++)
         {
           qtCoefBlk[i] = e->tsCoef[0][i];
@@ -1837,7 +1881,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     set_range(cu->tridx, relIdx, numParts, trDepth);
     set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
     set_range(cu->ts[0], relIdx, numParts, bestModeId);
-    par_copy2d(c, picBlk, plane_stride(g, 0), qtRecBlk, 64, 1 << log2n, 1 << log2n);
+    par_copy2d(c, picBlk, plane_stride(s, 0), qtRecBlk, 64, 1 << log2n, 1 << log2n);
   }
   *distY += singleDist;
   *rdCost = dadd(*rdCost, singleCost);
@@ -1874,7 +1918,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
   const int puParts = cu->nparts >> (2 * initTrDepth);
   const int puSize = cu->width >> initTrDepth;
   const int log2pu = ilog2(puSize);
-  const int ps = plane_stride(g, 0);
+  const int ps = plane_stride(s, 0);
   uint32_t overallDist = 0;
 
   for (int pu = 0; pu < numPU; pu++)
@@ -1913,8 +1957,8 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
         for (int i = 0; i < 3; i++) if (mode == preds[i]) idx = i;
         const uint64_t frac = frac0 + (uint64_t)s->t.entropyBits[st ^ (idx != -1 ? 1 : 0)] + (uint64_t)32768 * (uint64_t)(idx != -1 ? (idx ? 2 : 1) : 5);
         const uint32_t modeBits = (uint32_t)(frac >> 15);
-        const uint32_t sad = s->satd[mode] >> (g->bitDepth - 8);
-        const double cost = dadd((double)sad, dmul((double)modeBits, g->sp.sqrtLambda));
+        const uint32_t sad = s->satd[mode] >> (s->fp.bitDepth - 8);
+        const double cost = dadd((double)sad, dmul((double)modeBits, s->fp.sp.sqrtLambda));
         int shift = 0;                                                          // xUpdateCandList (TEncSearch.cpp:5385)
         while (shift < numModesForFullRD && cost < candCost[numModesForFullRD - 1 - shift]) shift++;
         if (shift != 0)
@@ -1948,19 +1992,15 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       td.partOffset = partOffset; td.log2pu = log2pu; td.initTrDepth = initTrDepth;
       for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
       { FHC_TIC(tl); par(c, OP_TASKS); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
-      int bi = -1;
-      for (int i = 0; i < numModesForFullRD; i++)
-        if (s->eng[i].resCost < bestPUCost) { bestPUCost = s->eng[i].resCost; bestPUDist = s->eng[i].resDist; bestPUMode = rdModeList[i]; bi = i; }
       {
         // xSetIntraResultLumaQT + the saved trIdx/cbf/tskip arrays of the winner
-        const Engine* w = &s->eng[bi];
-        const CUMeta* wc = &g->eng[bi].cu;
-        const int layer = 5 - log2pu, n = 1 << log2pu;
-        par_copy16(c, cuCoef + partOffset * 16, w->qtCoef[layer] + partOffset * 16, n * n);
-        par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width,
-                   w->qtRec[layer] + rel_y(s, partOffset) * 64 + rel_x(s, partOffset), 64, n, n);
-        copy_bytes(s->qtTrIdx, wc->tridx + partOffset, puParts);
-        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wc->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], wc->ts[j] + partOffset, puParts); }
+        const int be = best_engine(s), n = 1 << log2pu;
+        const EngineGlobal* wg = &g->eng[be];
+        bestPUCost = s->eng[be].resCost; bestPUDist = s->eng[be].resDist; bestPUMode = rdModeList[s->eng[be].resTask];
+        par_copy16(c, cuCoef + partOffset * 16, wg->bestCoef[0], n * n);
+        par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, wg->bestReco[0], n, n, n);
+        copy_bytes(s->qtTrIdx, wg->bestTrIdx, puParts);
+        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wg->bestCbf[j], puParts); copy_bytes(s->qtTs[j], wg->bestTs[j], puParts); }
       }
       // second pass: a 4x4 PU cannot split, re-coding the best mode reproduces the same cost (never strictly smaller)
       firstSerial = (log2pu == 2) ? numModesForFullRD + 1 : numModesForFullRD;
@@ -2063,7 +2103,7 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
       }
       if (bestMode < total)
       {
-        const int ps = plane_stride(g, cc);
+        const int ps = plane_stride(s, cc);
         int16_t* picBlk = g->rec[cc] + ((cu->y + rel_y(s, ridx)) >> 1) * ps + ((cu->x + rel_x(s, ridx)) >> 1);
         for (int i = 0; i < 16; i++)
         {
@@ -2133,17 +2173,14 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
     td.partOffset = 0; td.log2pu = log2cu; td.initTrDepth = 0;
     for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
     { FHC_TIC(tc); par(c, OP_TASKS); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
-    int bi = -1;
-    for (int mi = 0; mi < 5; mi++)
-      if (s->eng[mi].resCost < bestCost) { bestCost = s->eng[mi].resCost; bestDist = s->eng[mi].resDist; bestMode = (uint32_t)modeList[mi]; bi = mi; }
-    const Engine* w = &s->eng[bi];
-    const CUMeta* wc = &g->eng[bi].cu;
-    const int layer = 5 - (3 - (int)cu->tridx[0]);               // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
+    const int be = best_engine(s);
+    const EngineGlobal* wg = &g->eng[be];
+    bestCost = s->eng[be].resCost; bestDist = s->eng[be].resDist; bestMode = (uint32_t)modeList[s->eng[be].resTask];
     for (int cc = 1; cc < 3; cc++)
     {
-      par_copy16(c, cuCoef + comp_off(cc), w->qtCoef[layer] + comp_off(cc), 16);
-      par_copy2d(c, cuReco + comp_off(cc), 4, w->qtRec[layer] + comp_off(cc), 32, 4, 4);
-      copy_bytes(s->qtCbf[cc], wc->cbf[cc], nparts); copy_bytes(s->qtTs[cc], wc->ts[cc], nparts);
+      par_copy16(c, cuCoef + comp_off(cc), wg->bestCoef[cc], 16);
+      par_copy2d(c, cuReco + comp_off(cc), 4, wg->bestReco[cc], 4, 4, 4);
+      copy_bytes(s->qtCbf[cc], wg->bestCbf[cc], nparts); copy_bytes(s->qtTs[cc], wg->bestTs[cc], nparts);
     }
   }
   else
@@ -2263,12 +2300,13 @@ FHC_D void cu_copy_to_pic(const Ctx& c, const CUMeta* cu, int withCoef)         
 FHC_D void copy_reco_to_pic(const Ctx& c, const CUMeta* cu)                                      // xCopyYuv2Pic (TEncCu.cpp:1729)
 {
   const FrameGlobal* g = c.g;
+  const Shared* s = c.s;
   const int16_t* y = g->cuReco[cu->depth][cu_buf_index(c.s, cu)];
   for (int cc = 0; cc < 3; cc++)
   {
     const int sh = cc ? 1 : 0, w = cu->width >> sh, px = cu->x >> sh, py = cu->y >> sh;
-    const int cw = imin(w, (g->width >> sh) - px), ch = imin(w, (g->height >> sh) - py);
-    par_copy2d(c, g->rec[cc] + py * plane_stride(g, cc) + px, plane_stride(g, cc), y + comp_off(cc), w, cw, ch);
+    const int cw = imin(w, (s->fp.width >> sh) - px), ch = imin(w, (s->fp.height >> sh) - py);
+    par_copy2d(c, g->rec[cc] + py * plane_stride(s, cc) + px, plane_stride(s, cc), y + comp_off(cc), w, cw, ch);
   }
 }
 FHC_D void copy_reco_to_parent(const Ctx& c, const CUMeta* child, const CUMeta* parent, int partIdx)   // xCopyYuv2Tmp (TEncCu.cpp:1742)
@@ -2303,7 +2341,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   set_range(cu->part, 0, cu->nparts, partSize);
   set_range(cu->pred, 0, cu->nparts, MODE_INTRA);
   { FHC_TIC(el); est_intra_luma(c, cu, cuCoef, cuReco); FHC_TOC2(c, el, PF_LUMA); }
-  par_copy2d(c, g->rec[0] + cu->y * plane_stride(g, 0) + cu->x, plane_stride(g, 0), cuReco, cu->width, cu->width, cu->width);
+  par_copy2d(c, g->rec[0] + cu->y * plane_stride(s, 0) + cu->x, plane_stride(s, 0), cuReco, cu->width, cu->width, cu->width);
   { FHC_TIC(ec); est_intra_chroma(c, cu, cuCoef, cuReco); FHC_TOC2(c, ec, PF_CHROMA); }
   reset_bits(e);
   encode_cu_syntax(c, cu, cuCoef);
@@ -2320,7 +2358,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
   Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
   const int x = best_cu(s, depth)->x, y = best_cu(s, depth)->y, w = best_cu(s, depth)->width;
-  const int boundary = !(x + w - 1 < g->width && y + w - 1 < g->height);
+  const int boundary = !(x + w - 1 < s->fp.width && y + w - 1 < s->fp.height);
   if (!boundary)
   {
     cu_init_est(c, temp_cu(s, depth));
@@ -2349,7 +2387,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
     {
       cu_position(c, &s->cu[nd][0], t, i, nd);
       cu_position(c, &s->cu[nd][1], t, i, nd);
-      if (s->cu[nd][0].x < g->width && s->cu[nd][0].y < g->height)
+      if (s->cu[nd][0].x < s->fp.width && s->cu[nd][0].y < s->fp.height)
       {
         if (i == 0) sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, depth, CI_CURR_BEST));
         else sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, nd, CI_NEXT_BEST));
@@ -2401,7 +2439,7 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
   copy_bytes(view->pred, o->predMode + zidx, nparts); copy_bytes(view->ldir, o->lumaDir + zidx, nparts);
   copy_bytes(view->cdir, o->chromaDir + zidx, nparts); copy_bytes(view->tridx, o->trIdx + zidx, nparts);
   for (int cc = 0; cc < 3; cc++) { copy_bytes(view->cbf[cc], o->cbf[cc] + zidx, nparts); copy_bytes(view->ts[cc], o->transformSkip[cc] + zidx, nparts); }
-  if (x + w - 1 < g->width && y + w - 1 < g->height) code_split_flag(c, view, 0, depth);
+  if (x + w - 1 < s->fp.width && y + w - 1 < s->fp.height) code_split_flag(c, view, 0, depth);
   else boundary = 1;
   if ((depth < o->depth[zidx] && depth < 3) || boundary)
   {
@@ -2409,7 +2447,7 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
     for (int i = 0; i < 4; i++)
     {
       const int cz = zidx + i * q, cr = s->t.z2r[cz];
-      if (s->ctuPelX + (cr & 15) * 4 < g->width && s->ctuPelY + (cr >> 4) * 4 < g->height) encode_ctu_rec(c, view, cz, depth + 1);
+      if (s->ctuPelX + (cr & 15) * 4 < s->fp.width && s->ctuPelY + (cr >> 4) * 4 < s->fp.height) encode_ctu_rec(c, view, cz, depth + 1);
     }
     return;
   }
@@ -2419,8 +2457,8 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
   par_copy16(c, cv + 4096, o->coefCb + zidx * 4, (w * w) >> 2);
   par_copy16(c, cv + 5120, o->coefCr + zidx * 4, (w * w) >> 2);
   encode_cu_syntax(c, view, cv);
-  const int lastInCtu = ((x + w >= g->width) || (((r & 15) * 4 + w) == 64)) && ((y + w >= g->height) || (((r >> 4) * 4 + w) == 64));
-  if (lastInCtu && s->ctuAddr != g->wc * g->hc - 1) enc_trm(e, 0);                               // finishCU (TEncCu.cpp:1066)
+  const int lastInCtu = ((x + w >= s->fp.width) || (((r & 15) * 4 + w) == 64)) && ((y + w >= s->fp.height) || (((r >> 4) * 4 + w) == 64));
+  if (lastInCtu && s->ctuAddr != s->fp.wc * s->fp.hc - 1) enc_trm(e, 0);                               // finishCU (TEncCu.cpp:1066)
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -2429,11 +2467,19 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
 FHC_D void init_engines(FrameGlobal* g, Shared* s)
 {
   Engine* m = &s->master;
+  s->fp.width = g->width; s->fp.height = g->height; s->fp.bitDepth = g->bitDepth; s->fp.sampleBytes = g->sampleBytes;
+  s->fp.wc = g->wc; s->fp.hc = g->hc; s->fp.sp = g->sp;
   m->kind = ENG_MASTER; m->t = &s->t; m->slots = &s->slot[0][0];
   m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->resi = s->resi; m->tmp = s->tmp; m->tcoef = s->tcoef; m->lvlD = s->lvlD;
-  m->cost0 = g->rdCost0; m->costCoeff = g->rdCostCoeff; m->costSig = g->rdCostSig;
-  m->rateIncUp = g->rdRateIncUp; m->rateIncDown = g->rdRateIncDown; m->sigRateDelta = g->rdSigRateDelta; m->deltaU = g->rdDeltaU;
+  m->cost0 = s->rdCost0; m->costCoeff = s->rdCostCoeff; m->costSig = s->rdCostSig;
+  m->rateIncUp = s->rdRateIncUp; m->rateIncDown = s->rdRateIncDown; m->sigRateDelta = s->rdSigRateDelta; m->deltaU = s->rdDeltaU;
   m->predYuv = g->predYuv; m->qtRec = g->qtRec; m->qtCoef = g->qtCoef; m->writePic = 1;
+  m->costCGSig = s->costCGSig; m->cgFlag = s->cgFlag; m->cgFlagCode = s->cgFlagCode; m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta;
+  {
+    uint8_t* st = s->cuStore;
+    for (int d = 0; d < 4; d++)
+      for (int b = 0; b < 2; b++) { cu_bind(&s->cu[d][b], st, 256 >> (2 * d)); st += 12 * (256 >> (2 * d)); }
+  }
   for (int i = 0; i < FHC_NENG; i++)
   {
     Engine* e = &s->eng[i];
@@ -2443,6 +2489,8 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s)
     e->cost0 = x->cost0; e->costCoeff = x->costCoeff; e->costSig = x->costSig;
     e->rateIncUp = x->rateIncUp; e->rateIncDown = x->rateIncDown; e->sigRateDelta = x->sigRateDelta; e->deltaU = x->deltaU;
     e->predYuv = g->eng[i].predYuv; e->qtRec = g->eng[i].qtRec; e->qtCoef = g->eng[i].qtCoef; e->writePic = 0;
+    e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->sigC0 = x->sigC0; e->sigC1 = x->sigC1; e->sigDelta = x->sigDelta;
+    cu_bind(&g->eng[i].cu, g->eng[i].cuStore, 4);
   }
 }
 
@@ -2466,15 +2514,29 @@ FHC_D void run_task(FrameGlobal* g, Shared* s, int engIdx, int t)
     for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
   }
   const int mode = td.mode[t];
+  EngineGlobal* eg = &g->eng[engIdx];
+  const int firstOfDispatch = t < FHC_NENG;
   if (td.kind == TASK_LUMA_PU)
   {
     // one iteration of the candidate loop of estIntraPredLumaQT (TEncSearch.cpp:2349-2418), bCheckFirst = true
     uint32_t dist = 0;
     double cost = 0.0;
-    set_range(cu->ldir, td.partOffset, np >> (2 * td.initTrDepth), mode);
+    const int puParts = np >> (2 * td.initTrDepth);
+    set_range(cu->ldir, td.partOffset, puParts, mode);
     sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
     recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
-    e->resCost = cost; e->resDist = dist;
+    if (firstOfDispatch || cost < e->resCost)
+    {
+      const int layer = 5 - td.log2pu, n = 1 << td.log2pu;
+      e->resCost = cost; e->resDist = dist; e->resTask = t;
+      par_copy16(c, eg->bestCoef[0], e->qtCoef[layer] + td.partOffset * 16, n * n);
+      par_copy2d(c, eg->bestReco[0], n, e->qtRec[layer] + rel_y(s, td.partOffset) * 64 + rel_x(s, td.partOffset), 64, n, n);
+      for (int i = 0; i < puParts; i++)
+      {
+        eg->bestTrIdx[i] = cu->tridx[td.partOffset + i];
+        for (int cc = 0; cc < 3; cc++) { eg->bestCbf[cc][i] = cu->cbf[cc][td.partOffset + i]; eg->bestTs[cc][i] = cu->ts[cc][td.partOffset + i]; }
+      }
+    }
   }
   else
   {
@@ -2485,14 +2547,24 @@ FHC_D void run_task(FrameGlobal* g, Shared* s, int engIdx, int t)
     set_range(cu->cdir, 0, np, mode);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
     sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
-    e->resCost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
-    e->resDist = dist;
+    const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
+    if (firstOfDispatch || cost < e->resCost)
+    {
+      const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
+      e->resCost = cost; e->resDist = dist; e->resTask = t;
+      for (int cc = 1; cc < 3; cc++)
+      {
+        par_copy16(c, eg->bestCoef[cc], e->qtCoef[layer] + comp_off(cc), 16);
+        par_copy2d(c, eg->bestReco[cc], 4, e->qtRec[layer] + comp_off(cc), 32, 4, 4);
+        for (int i = 0; i < np; i++) { eg->bestCbf[cc][i] = cu->cbf[cc][i]; eg->bestTs[cc][i] = cu->ts[cc][i]; }
+      }
+    }
   }
 }
 #ifndef FHC_DEVICE_BUILD
 FHC_D void run_tasks_emu(const Ctx& c)
 {
-  for (int t = 0; t < c.s->task.numTasks; t++) run_task(c.g, c.s, t, t);
+  for (int t = 0; t < c.s->task.numTasks; t++) run_task(c.g, c.s, t % FHC_NENG, t);
 }
 #endif
 
@@ -2507,12 +2579,12 @@ FHC_D void master_compress_picture(const Ctx& c)
   FHC_TIC(tot);
   for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
   // engines were initialised by the caller (init_engines) before the workers started
-  sbac_reset(s->t, &s->slot[0][CI_CURR_BEST], g->sp.sliceQp);
-  const int numCtus = g->wc * g->hc;
+  sbac_reset(s->t, &s->slot[0][CI_CURR_BEST], s->fp.sp.sliceQp);
+  const int numCtus = s->fp.wc * s->fp.hc;
   for (int addr = 0; addr < numCtus; addr++)
   {
     fhc_ctu_result* o = &g->out[addr];
-    s->ctuAddr = addr; s->ctuX = addr % g->wc; s->ctuY = addr / g->wc;
+    s->ctuAddr = addr; s->ctuX = addr % s->fp.wc; s->ctuY = addr / s->fp.wc;
     s->ctuPelX = s->ctuX * 64; s->ctuPelY = s->ctuY * 64;
     // initCtu (TComDataCU.cpp:422): the record doubles as the picture-level CTU
     for (int d = 0; d < 2; d++)
