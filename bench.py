@@ -1,0 +1,271 @@
+#!/usr/bin/env python3
+"""bench.py - 1080p all-intra mode-decision throughput of the B200 engine (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = one pass of the hot path (TEncCu::xCompressCU and below, for every CTU of every picture) over one batch of
+synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, one
+thread block per (picture, QP) job, `--jobs` jobs per GPU per step (default 148 = one per SM; 256 = the whole config).
+`value` is whole-job fps with the samples already resident in HBM (CUDA-event time of the kernel launches, max over
+ranks); `e2e` is the same through the C ABI with host buffers (pinned H2D of the pictures + D2H of every CTU result
+inside the timed region).  N > 1: one process per GPU (torchrun), every rank encodes its own contiguous frame group,
+no collective on the data path - torch.distributed only provides the barrier and the max over ranks.
+
+`--impl reference` times the UNMODIFIED reference encoder (oracle/_ref/TAppEncoder, HM 16.14 with the OpenCV dump
+stubbed) on the host cores: one process per core, one 1080p picture each per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+W, H, CLIP = 1920, 1080, 64
+QPS = [22, 27, 32, 37]
+CTUS = 30 * 17
+# algorithmic bytes per CTU = 6144 source + 12288 reconstruction + 12288 levels + ~6 KB metadata
+ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
+INT_OPS_PER_CTU = 40.0e6            # SURVEY.md 8(d) W_ctu (integer-equivalent ops, content dependent)
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10)
+                self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.5)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def job_list(first_frame, n_frames, n_jobs):
+    """(frame, qp) jobs of one rank: its frame group at every QP, QP-major, truncated/cycled to n_jobs."""
+    all_jobs = [(first_frame + f, q) for q in QPS for f in range(n_frames)]
+    return [all_jobs[i % len(all_jobs)] for i in range(n_jobs)]
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import fasthevc_b200 as fh
+    from fasthevc_b200.sharding import frame_group
+    from fasthevc_b200.synth import synth_frames
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
+    first, last = frame_group(CLIP * world, rank, world)
+    jobs = job_list(first, last - first, args.jobs)
+    frames_needed = sorted({f for f, _ in jobs})
+    # distinct synthetic pictures are expensive to synthesise on the host; 8 distinct pictures per rank, cycled
+    distinct = frames_needed[:8]
+    Y, U, V = synth_frames(W, H, len(distinct), first_frame=distinct[0])
+    enc = fh.Encoder(W, H, 8, max_frames=args.jobs, device=local_rank)
+    host_in = enc.pinned_array((args.jobs, enc.frame_samples), np.uint8)
+    packed = enc.pack_frames(Y, U, V)
+    for j, (f, _) in enumerate(jobs):
+        host_in[j] = packed[(f - first) % len(distinct)]
+    sps = [fh.slice_params_from_qp(q) for _, q in jobs]
+    host_out = enc.pinned_array((args.jobs, enc.num_ctus), fh.CTU_RESULT_DTYPE)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return enc.run_resident(sps)                       # CUDA events around the launch, on the library's stream
+
+    def step_e2e():
+        t0 = time.perf_counter()
+        enc.submit(host_in, sps)                           # pinned H2D + launch
+        for j in range(args.jobs):
+            enc.fetch_picture(j, host_out[j])              # D2H of every CTU record
+        return (time.perf_counter() - t0) * 1e3
+
+    # inputs resident in HBM: one upload outside the timed region
+    enc.submit(host_in, sps)
+    enc.fetch_picture(0, host_out[0])                      # = warm-up step 1 (also checks the launch)
+    for _ in range(max(0, args.warmup - 1)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    kernel_ms = [step_resident() for _ in range(args.steps)]
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    sampler.stop_flag = True
+    launches = int(enc.lib.fhc_launch_count())
+    # e2e: the same step through submit/fetch with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    e2e_ms = [step_e2e() for _ in range(e2e_steps)]
+    barrier()
+    check_bits = int(host_out["totalBits"].sum())
+    enc.close()
+
+    my_ms = float(np.sum(kernel_ms))
+    my_e2e = float(np.sum(e2e_ms))
+    if dist is not None:
+        t = torch.tensor([my_ms, my_e2e, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        my_ms, my_e2e, wall_ms = [float(v) for v in t.tolist()]
+    if rank == 0:
+        total_jobs = args.jobs * world
+        ms_per_step = my_ms / args.steps
+        fps = total_jobs / (ms_per_step / 1e3)
+        e2e_fps = total_jobs / (my_e2e / e2e_steps / 1e3)
+        peak, peak_src = load_peaks()
+        achieved = ALGO_BYTES_PER_CTU * CTUS * args.jobs / (ms_per_step / 1e3) / 1e9      # per launch (= per rank)
+        line = {
+            "metric": "1080p all-intra encode fps (byte-identical CTU decisions)", "value": round(fps, 4), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64 (u8 samples, i16 levels)",
+            "data": "synthetic",
+            "config": {"workload": "encoder_intra_main.cfg 1920x1080 8-bit, 64-frame synthetic clip per GPU x QP{22,27,32,37}; "
+                                   "%d picture jobs per GPU per step, one thread block per picture" % args.jobs,
+                       "jobs_per_gpu": args.jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective" % world,
+                       "l2_policy": "inputs+results per step (%.0f MB) exceed the 126 MB L2" % (args.jobs * (3.1 + 14.0))},
+            "ctu_per_s": round(fps * CTUS, 1),
+            "e2e": {"value": round(e2e_fps, 4), "unit": "frames/s", "h2d_bytes_per_step": int(host_in.nbytes) * world,
+                    "d2h_bytes_per_step": int(host_out.nbytes) * world, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "latency/issue-bound integer+fp64 decision kernel: HBM is not the limiter (SURVEY 8d); "
+                                 "integer-equivalent work %.2f Gop/s vs ~37,000 Gop/s nominal int32 issue" % (INT_OPS_PER_CTU * fps * CTUS / world / 1e9)},
+            "wall_ms_timed_region": round(wall_ms, 1), "check_total_bits": check_bits,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_sample(1, 0)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified HM encoder on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def ref_paths():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return os.path.join(d, "TAppEncoder"), os.path.join(d, "cfg", "encoder_intra_main.cfg")
+
+
+def cpu_reference_step(workdir, cores, step_idx):
+    """One picture per core, all cores in parallel; returns (pictures, seconds)."""
+    from fasthevc_b200.synth import synth_frames, write_yuv
+    exe, cfg = ref_paths()
+    procs = []
+    yuv = os.path.join(workdir, "clip.yuv")
+    if not os.path.exists(yuv):
+        Y, U, V = synth_frames(W, H, 4)
+        write_yuv(yuv, Y, U, V)
+    t0 = time.perf_counter()
+    for c in range(cores):
+        qp = QPS[(c + step_idx) % 4]
+        cmd = [exe, "-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-fs", str(c % 4), "-f", "1", "-q", str(qp),
+               "-b", os.path.join(workdir, "o%d.bin" % c), "-o", ""]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=workdir))
+    for p in procs:
+        p.wait()
+    return cores, time.perf_counter() - t0
+
+
+def cpu_reference_sample(steps, warmup):
+    exe, _ = ref_paths()
+    if not os.path.exists(exe):
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/TAppEncoder not built"}
+    cores = max(1, len(os.sched_getaffinity(0)))
+    d = tempfile.mkdtemp()
+    for i in range(warmup):
+        cpu_reference_step(d, cores, i)
+    n, t = 0, 0.0
+    for i in range(steps):
+        a, b = cpu_reference_step(d, cores, warmup + i)
+        n += a
+        t += b
+    return {"value": round(n / t, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": "oracle/_ref/TAppEncoder (HM 16.14, g++ -O2 -msse4.1): %d step(s) of one 1080p picture per core, QP 22/27/32/37 "
+                      "cycled over cores, one process per core" % steps,
+            "ms_per_step": round(t / steps * 1e3, 1)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    exe, _ = ref_paths()
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/TAppEncoder missing (build with oracle/build_ref.py)"}))
+        return
+    cb = cpu_reference_sample(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "1080p all-intra encode fps (byte-identical CTU decisions)", "value": cb["value"],
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "config": {"workload": "encoder_intra_main.cfg 1920x1080 8-bit synthetic, QP{22,27,32,37}; bounded sample: one picture "
+                                   "per host core per step, whole TAppEncoder (the hot path is 98.8 % of it, SURVEY F10)"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--jobs", type=int, default=148, help="picture jobs per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -189,7 +189,7 @@ static int launch(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params* sp
   }
   CK(cudaMemcpy2DAsync(c->dFrames, sizeof(FrameGlobal), c->hostHeaders.data(), c->headerBytes, c->headerBytes, (size_t)n,
                        cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemset2DAsync(reinterpret_cast<unsigned char*>(c->dFrames) + offsetof(FrameGlobal, prof), sizeof(FrameGlobal), 0, 32 * sizeof(long long), (size_t)n, c->stream));
+  CK(cudaMemset2DAsync(reinterpret_cast<unsigned char*>(c->dFrames) + offsetof(FrameGlobal, prof), sizeof(FrameGlobal), 0, 64 * sizeof(long long), (size_t)n, c->stream));
   CK(cudaEventRecord(c->evStart, c->stream));
   fhc_compress_pictures_kernel<<<n, 32 + FHC_NWORK, sizeof(Shared), c->stream>>>(c->dFrames, c->dTables);
   CK(cudaGetLastError());
@@ -286,5 +286,12 @@ int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* coun
   if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
   CK(cudaMemcpy(cycles16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(counts16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, profN), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return FHC_OK;
+}
+extern "C" int fhc_debug_profile2(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
+{
+  if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
+  CK(cudaMemcpy(cycles16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof2), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof2N), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return FHC_OK;
 }

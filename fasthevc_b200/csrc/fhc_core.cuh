@@ -127,6 +127,7 @@ struct FrameGlobal
   int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
   EngineGlobal eng[FHC_NENG];
   long long prof[16], profN[16];  // cycle counters of the master thread (FHC_PROFILE builds)
+  long long prof2[16], prof2N[16];
 };
 
 enum Op {
@@ -239,12 +240,15 @@ struct Ctx { FrameGlobal* g; Shared* s; Engine* e; };
 
 #if defined(FHC_DEVICE_BUILD) && defined(FHC_PROFILE)
 #define FHC_TIC(k) const long long tic_##k = clock64()
+#define FHC_TOC3(c, nm, k) do { if ((c).e->kind == ENG_MASTER) { const volatile int fence_ = *(volatile int*)&(c).e->cmd.op; (void)fence_; (c).g->prof2[k] += clock64() - tic_##nm; (c).g->prof2N[k]++; } } while (0)
 #define FHC_TOC2(c, nm, k) do { if ((c).e->kind == ENG_MASTER) { const volatile int fence_ = *(volatile int*)&(c).e->cmd.op; (void)fence_; (c).g->prof[k] += clock64() - tic_##nm; (c).g->profN[k]++; } } while (0)
 #else
 #define FHC_TIC(k) do { } while (0)
+#define FHC_TOC3(c, nm, k) do { } while (0)
 #define FHC_TOC2(c, nm, k) do { } while (0)
 #endif
 enum { PF_TOTAL = 0, PF_PAR, PF_RDOQ, PF_COEFBITS, PF_REFS_MASTER, PF_RMD_MASTER, PF_TUBLOCK, PF_BITSQT, PF_CUCOPY, PF_RMD_PAR, PF_ENCODE, PF_TASKS_LUMA, PF_TASKS_CHROMA, PF_LUMA, PF_CHROMA, PF_NUM = 16 };
+enum { PF2_CHECK_D0 = 0, PF2_CHECK_D1, PF2_CHECK_D2, PF2_CHECK_D3_2N, PF2_CHECK_D3_NXN, PF2_LUMA2ND, PF2_CHROMA_BIG, PF2_LUMA1ST_BIG, PF2_NUM = 16 };
 
 
 // ----------------------------------------------------------------------------------------------
@@ -1887,6 +1891,32 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   *rdCost = dadd(*rdCost, singleCost);
 }
 
+// Second pass of estIntraPredLumaQT (TEncSearch.cpp:2420-2488) for a PU whose size is a legal TU size (8..32): the
+// "single TU" branch of xRecurIntraCodingLumaQT(bCheckFirst=false) repeats, instruction for instruction, the first-pass
+// evaluation of the same mode (same start contexts CI_CURR_BEST, same neighbours), so its cost is the first-pass best
+// cost.  Only the split branch is new work; it wins iff splitCost < that cost.  Returns 1 when the split wins.
+FHC_D int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, double singleCost, uint32_t* dist, double* cost)
+{
+  Engine* e = c.e;
+  if (!(log2n > min_tu_log2_in_cu(cu))) return 0;
+  const int fullDepth = cu->depth + trDepth;
+  const int numParts = cu->nparts >> (2 * trDepth), q = numParts >> 2;
+  double splitCost = 0.0;
+  uint32_t splitDist = 0, splitCbf = 0;
+  sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+  for (int i = 0; i < 4; i++)
+  {
+    recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, 0, &splitDist, &splitCost);
+    splitCbf |= (cu->cbf[0][relIdx + i * q] >> (trDepth + 1)) & 1;
+  }
+  if (splitCbf)
+    for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
+  sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+  splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
+  if (splitCost < singleCost) { *dist = splitDist; *cost = splitCost; return 1; }
+  return 0;
+}
+
 // xSetIntraResultLumaQT (TEncSearch.cpp:1716): copy winning coefficients / reconstruction of a PU into the CU buffers
 FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth)
 {
@@ -2013,7 +2043,19 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       double puCost = 0.0;
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
       sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
-      recur_luma_qt(c, cu, partOffset, log2pu, initTrDepth, second ? 0 : 1, &puDist, &puCost);
+      if (second && log2pu >= 3 && log2pu <= 5)
+      {
+        FHC_TIC(sp);
+        const int won = second_pass_split_only(c, cu, partOffset, log2pu, initTrDepth, bestPUCost, &puDist, &puCost);
+        FHC_TOC3(c, sp, PF2_LUMA2ND);
+        if (!won) continue;
+      }
+      else
+      {
+        FHC_TIC(fp);
+        recur_luma_qt(c, cu, partOffset, log2pu, initTrDepth, second ? 0 : 1, &puDist, &puCost);
+        FHC_TOC3(c, fp, (second ? PF2_LUMA2ND : PF2_LUMA1ST_BIG));
+      }
       if (puCost < bestPUCost)
       {
         bestPUMode = orgMode; bestPUDist = puDist; bestPUCost = puCost;
@@ -2187,6 +2229,7 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
   for (int mi = 0; mi < 5; mi++)
   {
     uint32_t dist = 0;
+    FHC_TIC(cb);
     sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, nparts, modeList[mi]);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
@@ -2198,6 +2241,7 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
       set_chroma_result(c, cu, cuCoef, cuReco, 0, log2cu, 0, 1);
       for (int cc = 1; cc < 3; cc++) { copy_bytes(s->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(s->qtTs[cc], cu->ts[cc], nparts); }
     }
+    FHC_TOC3(c, cb, PF2_CHROMA_BIG);
   }
   for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
   set_range(cu->cdir, 0, nparts, (int)bestMode);
@@ -2338,6 +2382,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   const int bi = cu_buf_index(s, cu);
   int16_t* cuCoef = g->cuCoef[depth][bi];
   int16_t* cuReco = g->cuReco[depth][bi];
+  FHC_TIC(chk);
   set_range(cu->part, 0, cu->nparts, partSize);
   set_range(cu->pred, 0, cu->nparts, MODE_INTRA);
   { FHC_TIC(el); est_intra_luma(c, cu, cuCoef, cuReco); FHC_TOC2(c, el, PF_LUMA); }
@@ -2350,6 +2395,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   cu->bins = e->bins;
   cu->cost = rd_cost(c, cu->bits, cu->dist);
   check_best_mode(c, depth);
+  FHC_TOC3(c, chk, (depth < 3 ? depth : (partSize == SIZE_NxN ? PF2_CHECK_D3_NXN : PF2_CHECK_D3_2N)));
 }
 
 FHC_D void compress_cu(const Ctx& c, int depth)                                                  // xCompressCU (TEncCu.cpp:496-1058)

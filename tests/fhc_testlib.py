@@ -164,7 +164,8 @@ class FhcSeqParams(C.Structure):
 
 
 def slice_params_from_hm(p):
-    sp = FhcSliceParams()
+    from fasthevc_b200.api import SliceParams
+    sp = SliceParams()
     sp.sliceQp = p.qp
     sp.lambda_, sp.sqrtLambda = p.lambda_, p.sqrtLambda
     sp.chromaDistWeight[0], sp.chromaDistWeight[1] = p.distWeight[1], p.distWeight[2]
@@ -192,7 +193,7 @@ def emu_compress(params, y, u, v):
     global _emu
     if _emu is None:
         _emu = C.CDLL(build_emu())
-        _emu.fhc_emu_compress_picture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(FhcSliceParams), C.c_void_p,
+        _emu.fhc_emu_compress_picture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p, C.c_void_p]
     sb = 1 if params.bitDepth == 8 else 2
     dt = np.uint8 if sb == 1 else np.uint16

@@ -16,5 +16,10 @@ def run(w,h,qp,sigma=6.0):
     print('%dx%d qp %d sigma %.0f: total %.1f Mcycles, %d CTUs'%(w,h,qp,sigma,tot/1e6,enc.num_ctus))
     for i,nm in enumerate(names):
         if cnt[i]: print('  %-12s %6.1f%%  n=%8d  avg %8.0f cyc'%(nm,100.0*cyc[i]/tot,cnt[i],cyc[i]/cnt[i]))
+    names2=['CHECK_D0','CHECK_D1','CHECK_D2','CHECK_D3_2N','CHECK_D3_NXN','LUMA2ND','CHROMA_BIG','LUMA1ST_BIG']
+    enc.lib.fhc_debug_profile2.argtypes=[C.c_void_p,C.c_int,C.c_void_p,C.c_void_p]
+    enc.lib.fhc_debug_profile2(enc.ctx,0,cyc,cnt)
+    for i,nm in enumerate(names2):
+        if cnt[i]: print('  %-12s %6.1f%%  n=%8d  avg %8.0f cyc'%(nm,100.0*cyc[i]/tot,cnt[i],cyc[i]/cnt[i]))
     enc.close()
 run(192,128,32)
