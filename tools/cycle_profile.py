@@ -1,4 +1,4 @@
-import sys, time, ctypes as C; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import sys, time, ctypes as C; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import numpy as np
 import fasthevc_b200 as fh, fasthevc_b200.api as api
 api.library_path = lambda: 'fasthevc_b200/libfasthevc_cuda_prof.so'

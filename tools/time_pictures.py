@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import sys, time; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import numpy as np
 import fasthevc_b200 as fh
 import __graft_entry__ as ge
