@@ -12,64 +12,78 @@ using namespace fhc;
 #ifndef FHC_MIN_BLOCKS
 #define FHC_MIN_BLOCKS 1
 #endif
+#define FHC_BLOCK_THREADS (32 * FHC_WARPS_PER_BLOCK)
 extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 
+#define FHC_PICS_PER_WARP (32 / FHC_GROUP)
+#define FHC_PICS_PER_BLOCK (FHC_PICS_PER_WARP * FHC_WARPS_PER_BLOCK)
+static size_t tables_smem_bytes() { return (sizeof(Tables) + 15) & ~(size_t)15; }
+static size_t kernel_smem_bytes() { return tables_smem_bytes() + sizeof(Shared) * FHC_PICS_PER_BLOCK + 16 * FHC_WARPS_PER_BLOCK; }
+
 // ----------------------------------------------------------------------------------------------
-// kernel: one block per picture; thread 0 = master, lanes 1..31 of warp 0 retire, warps 1.. = workers
+// kernel: persistent warps; a warp encodes FHC_PICS_PER_WARP pictures side by side (FHC_GROUP lanes each), the
+// groups of a warp start their pictures together so that they walk the same code at the same time
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 + FHC_NWORK, FHC_MIN_BLOCKS) fhc_compress_pictures_kernel(FrameGlobal* frames, const Tables* tables)
+__global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_MIN_BLOCKS)
+fhc_compress_pictures_kernel(PicDesc* pics, int numPics, int* queue, FrameGlobal* scratch, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Shared* s = reinterpret_cast<Shared*>(smem_raw);
-  FrameGlobal* g = frames + blockIdx.x;
+  Tables* t = reinterpret_cast<Tables*>(smem_raw);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&s->t);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(t);
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
   }
-  if (threadIdx.x == 0) init_engines(g, s);
+  int* rvz = reinterpret_cast<int*>(smem_raw + ((sizeof(Tables) + 15) & ~(size_t)15) + sizeof(Shared) * FHC_PICS_PER_BLOCK);
+  if (threadIdx.x < 4 * FHC_WARPS_PER_BLOCK) rvz[threadIdx.x] = 0;
   __syncthreads();
-  if (threadIdx.x >= 1 && threadIdx.x < 32) return;      // exited threads are not counted by later barriers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / FHC_GROUP, slot = warp * FHC_PICS_PER_WARP + grp;
+  Shared* s = reinterpret_cast<Shared*>(smem_raw + ((sizeof(Tables) + 15) & ~(size_t)15)) + slot;
+  FrameGlobal* g = scratch + (size_t)blockIdx.x * FHC_PICS_PER_BLOCK + slot;
   Ctx c;
-  c.g = g; c.s = s; c.e = &s->master;
-  if (threadIdx.x == 0)
+  c.g = g; c.s = s; c.e = &s->master; c.lane = lane % FHC_GROUP; c.nl = FHC_GROUP;
+  c.mask = (FHC_GROUP == 32) ? FHC_FULL_MASK : (((1u << FHC_GROUP) - 1u) << (grp * FHC_GROUP));
+  if (c.lane == 0) init_engines(g, s, t);
+  group_sync(c);
+  // Rendezvous of the warp's groups between pictures.  It must not be a full-mask __syncwarp: groups that are still
+  // encoding execute __syncwarp(group mask), and waiting on a different mask that names them is undefined.  The last
+  // group to arrive pulls the next FHC_PICS_PER_WARP pictures and opens the next round; the others spin on the round.
+  volatile int* rv = reinterpret_cast<volatile int*>(rvz) + warp * 4;   // [0] arrivals, [1] round, [2] first picture of the round
+  for (int round = 1;; round++)
   {
-    master_compress_picture(c);
-    s->master.cmd.op = OP_EXIT;
-    bar_all();
-  }
-  else
-  {
-    const int w = threadIdx.x - 32;
-    for (;;)
+    if (c.lane == 0)
     {
-      bar_all();
-      const int op = s->master.cmd.op;
-      if (op == OP_EXIT) break;
-      if (op == OP_TASKS)
+      const int old = atomicAdd(const_cast<int*>(&rv[0]), 1);
+      if (old == round * FHC_PICS_PER_WARP - 1)
       {
-        // every worker warp is an engine: lane 0 walks the candidate's decision code, lanes 1..31 run its sample phases
-        const int wi = w >> 5, lane = w & 31;
-        for (int t = wi; t < s->task.numTasks; t += FHC_NENG)
-        {
-          Ctx ec;
-          ec.g = g; ec.s = s; ec.e = &s->eng[wi];
-          if (lane == 0) { run_task(g, s, wi, t); engine_lanes_release(ec); }
-          else engine_lanes_loop(ec, lane);
-        }
-        __syncwarp();
+        rv[2] = atomicAdd(queue, FHC_PICS_PER_WARP);
+        __threadfence_block();
+        rv[1] = round;
       }
-      else
-      {
-        const int np = (op == OP_RMD) ? s->master.cmd.a[15] : num_phases(op);
-        for (int ph = 0; ph < np; ph++)
-        {
-          run_phase(c, op, ph, w, FHC_NWORK);
-          if (ph + 1 < np) bar_workers();
-        }
-      }
-      bar_all();
     }
+    while (rv[1] < round) __nanosleep(100);
+    group_sync(c);
+    int p = rv[2];
+    if (p >= numPics) break;
+    p += grp;
+    if (p < numPics)
+    {
+      if (c.lane == 0)
+      {
+        // the group's leader walks the decision code; the other lanes serve its COOP sections and LANE dispatches
+        load_picture(c, &pics[p]);
+        compress_picture(c);
+        release_followers(c);
+        for (int i = 0; i < 16; i++)
+        {
+          pics[p].prof[i] = g->prof[i]; pics[p].profN[i] = g->profN[i];
+          pics[p].prof2[i] = g->prof2[i]; pics[p].prof2N[i] = g->prof2N[i];
+        }
+      }
+      else follower_loop(c);
+    }
+    group_sync(c);
   }
 }
 
@@ -93,7 +107,10 @@ struct fhc_ctx
   fhc_seq_params seq;
   int device, numCtus, maxFrames;
   size_t lumaSamples, frameSamples;       // per picture
-  FrameGlobal* dFrames;                   // [maxFrames]
+  PicDesc* dPics;                         // [maxFrames] picture queue of the current submit
+  FrameGlobal* dScratch;                  // [maxBlocks * FHC_WARPS_PER_BLOCK] per-warp scratch
+  int* dQueue;                            // next picture index
+  int maxBlocks;                          // resident blocks of the persistent kernel
   Tables* dTables;
   uint8_t* dIn;                           // maxFrames * frameSamples * 2 bytes
   int16_t* dRec;                          // maxFrames * frameSamples
@@ -101,8 +118,7 @@ struct fhc_ctx
   cudaStream_t stream;
   cudaEvent_t evStart, evStop;
   int firstPoc, nSubmitted, pending;
-  size_t headerBytes;
-  std::vector<unsigned char> hostHeaders;
+  std::vector<PicDesc> hostPics;
 };
 
 const char* fhc_last_error(void) { return g_err; }
@@ -138,9 +154,22 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   c->lumaSamples = (size_t)seq->width * seq->height;
   c->frameSamples = c->lumaSamples * 3 / 2;
   c->firstPoc = 0; c->nSubmitted = 0; c->pending = 0;
-  c->headerBytes = offsetof(FrameGlobal, cuCoef);
-  c->hostHeaders.resize(c->headerBytes * (size_t)c->maxFrames);
-  CK(cudaMalloc(&c->dFrames, sizeof(FrameGlobal) * (size_t)c->maxFrames));
+  c->hostPics.resize((size_t)c->maxFrames);
+  {
+    // persistent grid: as many blocks as fit on the device, but never more warps than pictures
+    cudaDeviceProp prop;
+    int perSm = 0;
+    CK(cudaGetDeviceProperties(&prop, device));
+    CK(cudaFuncSetAttribute(fhc_compress_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kernel_smem_bytes()));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_compress_pictures_kernel, FHC_BLOCK_THREADS, kernel_smem_bytes()));
+    if (perSm < 1) { snprintf(g_err, sizeof(g_err), "fhc_create: kernel does not fit an SM"); delete c; return FHC_ERR_CUDA; }
+    const int need = (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
+    c->maxBlocks = prop.multiProcessorCount * perSm;
+    if (c->maxBlocks > need) c->maxBlocks = need;
+  }
+  CK(cudaMalloc(&c->dPics, sizeof(PicDesc) * (size_t)c->maxFrames));
+  CK(cudaMalloc(&c->dScratch, sizeof(FrameGlobal) * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK));
+  CK(cudaMalloc(&c->dQueue, sizeof(int)));
   CK(cudaMalloc(&c->dTables, sizeof(Tables)));
   CK(cudaMalloc(&c->dIn, c->frameSamples * 2 * (size_t)c->maxFrames));
   CK(cudaMalloc(&c->dRec, c->frameSamples * sizeof(int16_t) * (size_t)c->maxFrames));
@@ -151,7 +180,6 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   Tables t;
   build_tables(&t, seq->bitDepth);
   CK(cudaMemcpy(c->dTables, &t, sizeof(t), cudaMemcpyHostToDevice));
-  CK(cudaFuncSetAttribute(fhc_compress_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
   *out = c;
   return FHC_OK;
@@ -162,36 +190,35 @@ int fhc_destroy(fhc_ctx* c)
   if (!c) return FHC_ERR_ARG;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->dFrames); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dRec); cudaFree(c->dOut);
+  cudaFree(c->dPics); cudaFree(c->dScratch); cudaFree(c->dQueue); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dRec); cudaFree(c->dOut);
   cudaEventDestroy(c->evStart); cudaEventDestroy(c->evStop);
   cudaStreamDestroy(c->stream);
   delete c;
   return FHC_OK;
 }
 
-// fills the per-picture headers and launches the kernel on c->stream
+// fills the picture queue and launches the persistent kernel on c->stream
 static int launch(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params* sp)
 {
   for (int i = 0; i < n; i++)
   {
     const uint8_t* in = c->dIn + (size_t)i * c->frameSamples * (size_t)sampleBytes;
     int16_t* rec = c->dRec + (size_t)i * c->frameSamples;
-    unsigned char* hb = c->hostHeaders.data() + c->headerBytes * (size_t)i;   // header prefix of FrameGlobal only
-    const void* org[3] = { in, in + c->lumaSamples * (size_t)sampleBytes, in + (c->lumaSamples + c->lumaSamples / 4) * (size_t)sampleBytes };
-    int16_t* recp[3] = { rec, rec + c->lumaSamples, rec + c->lumaSamples + c->lumaSamples / 4 };
-    fhc_ctu_result* outp = c->dOut + (size_t)i * c->numCtus;
-    memcpy(hb + offsetof(FrameGlobal, org), org, sizeof(org));
-    memcpy(hb + offsetof(FrameGlobal, rec), recp, sizeof(recp));
-    memcpy(hb + offsetof(FrameGlobal, out), &outp, sizeof(outp));
-    memcpy(hb + offsetof(FrameGlobal, sp), &sp[i], sizeof(fhc_slice_params));
-    int32_t v[6] = { c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, (c->seq.width + 63) / 64, (c->seq.height + 63) / 64 };
-    memcpy(hb + offsetof(FrameGlobal, width), v, sizeof(v));
+    PicDesc& d = c->hostPics[(size_t)i];
+    memset(&d, 0, sizeof(d));
+    d.org[0] = in; d.org[1] = in + c->lumaSamples * (size_t)sampleBytes; d.org[2] = in + (c->lumaSamples + c->lumaSamples / 4) * (size_t)sampleBytes;
+    d.rec[0] = rec; d.rec[1] = rec + c->lumaSamples; d.rec[2] = rec + c->lumaSamples + c->lumaSamples / 4;
+    d.out = c->dOut + (size_t)i * c->numCtus;
+    d.sp = sp[i];
+    d.width = c->seq.width; d.height = c->seq.height; d.bitDepth = c->seq.bitDepth; d.sampleBytes = sampleBytes;
+    d.wc = (c->seq.width + 63) / 64; d.hc = (c->seq.height + 63) / 64;
   }
-  CK(cudaMemcpy2DAsync(c->dFrames, sizeof(FrameGlobal), c->hostHeaders.data(), c->headerBytes, c->headerBytes, (size_t)n,
-                       cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemset2DAsync(reinterpret_cast<unsigned char*>(c->dFrames) + offsetof(FrameGlobal, prof), sizeof(FrameGlobal), 0, 64 * sizeof(long long), (size_t)n, c->stream));
+  CK(cudaMemcpyAsync(c->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->dQueue, 0, sizeof(int), c->stream));
+  int blocks = (n + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
+  if (blocks > c->maxBlocks) blocks = c->maxBlocks;
   CK(cudaEventRecord(c->evStart, c->stream));
-  fhc_compress_pictures_kernel<<<n, 32 + FHC_NWORK, sizeof(Shared), c->stream>>>(c->dFrames, c->dTables);
+  fhc_compress_pictures_kernel<<<blocks, FHC_BLOCK_THREADS, kernel_smem_bytes(), c->stream>>>(c->dPics, n, c->dQueue, c->dScratch, c->dTables);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->evStop, c->stream));
   g_launches++;
@@ -284,14 +311,21 @@ int fhc_host_free(void* p)
 int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
 {
   if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
-  CK(cudaMemcpy(cycles16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(counts16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, profN), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cycles16, c->dPics[slot].prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts16, c->dPics[slot].profN, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return FHC_OK;
 }
 extern "C" int fhc_debug_profile2(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
 {
   if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
-  CK(cudaMemcpy(cycles16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof2), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(counts16, reinterpret_cast<unsigned char*>(c->dFrames + slot) + offsetof(FrameGlobal, prof2N), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cycles16, c->dPics[slot].prof2, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts16, c->dPics[slot].prof2N, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return FHC_OK;
+}
+// debug: launch geometry {blocks, warps per block, dynamic shared memory bytes, per-warp global scratch bytes}
+extern "C" int fhc_debug_geometry(fhc_ctx* c, long long* out4)
+{
+  if (!c || !out4) return FHC_ERR_ARG;
+  out4[0] = c->maxBlocks; out4[1] = FHC_WARPS_PER_BLOCK * 1000 + FHC_GROUP; out4[2] = (long long)kernel_smem_bytes(); out4[3] = (long long)sizeof(FrameGlobal);
   return FHC_OK;
 }

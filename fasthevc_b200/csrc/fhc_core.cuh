@@ -1,13 +1,24 @@
 // fhc_core.cuh - device code of the B200 HEVC intra mode-decision engine.
 //
-// One thread block per picture (all-intra pictures are independent; inside a
-// picture the CABAC context chain of TEncSlice::compressSlice forces raster CTU
-// order).  Inside the block a MASTER thread walks the decision
-// recursion (quad-tree, candidate loops, RQT, RDOQ's sequential pass, CABAC bit
-// counting) on state held in shared memory, and hands every sample-parallel
-// stage (reference-sample build, 35-mode prediction + Hadamard SATD, residual,
-// DCT/DST, RDOQ pre-quantisation, dequant + inverse transform, reconstruction,
-// SSE, block copies) to the WORKER warps through a command slot + barriers.
+// A LANE GROUP PER PICTURE.  All-intra pictures are independent; inside a picture the
+// CABAC context chain of TEncSlice::compressSlice forces raster CTU order
+// (SURVEY.md F5), so a picture is one long dependent chain and the GPU is filled
+// by running many pictures at once: persistent warps pull pictures from a queue
+// and every warp encodes 32 / FHC_GROUP pictures side by side, FHC_GROUP lanes
+// each.  The groups of a warp start their pictures together and follow the same
+// (almost static) decision schedule, so they share one instruction stream - the
+// kernel is instruction-fetch bound, not ALU or HBM bound (profiles/).
+//
+// Inside a group the LEADER lane walks the decision recursion (quad-tree,
+// candidate loops, RQT, RDOQ's sequential pass, CABAC bit counting) on state kept
+// in the group's shared-memory slice.  The other lanes serve it:
+//   * COOP sections (par / run_phase): sample-parallel stages of one block
+//     (reference build, 35-mode prediction + SATD, residual, DCT/DST, RDOQ
+//     pre-quantisation, dequant + inverse, reconstruction, SSE, copies) are striped
+//     over the group's lanes and fenced with __syncwarp(group mask);
+//   * LANE sections (dispatch_tasks): independent candidates (full-RD luma modes
+//     of small PUs, chroma modes of 8x8 CUs) are evaluated one per lane on
+//     lane-private scratch, then compared in list order.
 //
 // The file is written against a small portability layer (FHC_DEVICE_BUILD) so
 // that tests can compile the very same source for the host and step through it
@@ -23,13 +34,15 @@
 #ifdef FHC_DEVICE_BUILD
 #define FHC_HD __host__ __device__ __forceinline__
 #define FHC_DH __device__ __forceinline__
-#define FHC_D __device__
+#define FHC_D __device__ __noinline__   /* one copy of every sizeable function: the kernel is instruction-cache bound otherwise */
 #define FHC_NOINLINE __device__ __noinline__
+#define FHC_NOUNROLL _Pragma("unroll 1")
 #else
 #define FHC_HD static inline
 #define FHC_DH static inline
 #define FHC_D static
 #define FHC_NOINLINE static
+#define FHC_NOUNROLL
 #endif
 
 namespace fhc {
@@ -47,15 +60,22 @@ enum {
   CTX_LASTX = 68, CTX_LASTY = 98, CTX_ONE = 128, CTX_ABS = 152, CTX_TS = 158, NUM_CTX = 160
 };
 #define FHC_MAX_COST 1.7e+308
-#ifndef FHC_NWORK
-#define FHC_NWORK 320            /* worker threads per block; every worker warp doubles as a candidate engine */
+#ifndef FHC_WARPS_PER_BLOCK
+#define FHC_WARPS_PER_BLOCK 4    /* warps per thread block; each encodes 32 / FHC_GROUP pictures */
 #endif
+#ifndef FHC_GROUP
+#define FHC_GROUP 32             /* lanes per picture: a warp encodes 32 / FHC_GROUP pictures side by side (sub-warp groups serialise) */
+#endif
+#define FHC_MAX_TASKS 12         /* the longest candidate list (8 RMD survivors + MPMs) */
+#define FHC_NENG (FHC_GROUP < FHC_MAX_TASKS ? FHC_GROUP : FHC_MAX_TASKS)   /* lane engines per picture */
+#define FHC_SMALL_COEFS 64       /* TUs up to 8x8 use the warp's shared-memory scratch, larger ones the global scratch */
+#define FHC_FULL_MASK 0xffffffffu
 
 // layout of the 6144-sample "YUV" buffers: Y at 0, Cb at 4096, Cr at 5120
 FHC_DH int comp_off(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
 
 // ----------------------------------------------------------------------------------------------
-// tables (built on the host by fhc_build_tables, copied to shared memory by the kernel)
+// tables (built on the host by fhc_build_tables, copied to shared memory once per block)
 // ----------------------------------------------------------------------------------------------
 struct Tables
 {
@@ -96,45 +116,11 @@ FHC_HD void cu_bind(CUMeta* cu, uint8_t* store, int cap)
   for (int c = 0; c < 3; c++) { cu->cbf[c] = store + (6 + c) * cap; cu->ts[c] = store + (9 + c) * cap; }
 }
 
-#define FHC_NENG (FHC_NWORK / 32)   /* one engine per worker warp */
-#define FHC_ENG_COEFS 64           /* thread engines handle blocks up to 8x8 */
-
-// private global scratch of one thread engine (same layouts as the master's buffers)
-struct EngineGlobal
-{
-  int16_t predYuv[6144];
-  int16_t qtRec[4][6144];
-  int16_t qtCoef[4][6144];
-  CUMeta cu;
-  uint8_t cuStore[12 * 4];        // engines only see depth-3 CUs (4 partitions)
-  // result of the engine's best task of the current dispatch (task order, strict <)
-  int16_t bestCoef[3][64], bestReco[3][64];
-  uint8_t bestTrIdx[4], bestCbf[3][4], bestTs[3][4];
-};
-
-// per-picture state in global memory
-struct FrameGlobal
-{
-  const void* org[3];             // input planes (sampleBytes each)
-  int16_t* rec[3];                // reconstruction planes, stride = plane width
-  fhc_ctu_result* out;            // [numCtus]
-  fhc_slice_params sp;
-  int32_t width, height, bitDepth, sampleBytes, wc, hc;
-  int16_t cuCoef[4][2][6144];     // CU coefficient buffers per depth, best/temp
-  int16_t cuReco[4][2][6144];     // CU reconstruction buffers
-  int16_t predYuv[6144];          // prediction -> reconstruction scratch of the CU under test
-  int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
-  int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
-  EngineGlobal eng[FHC_NENG];
-  long long prof[16], profN[16];  // cycle counters of the master thread (FHC_PROFILE builds)
-  long long prof2[16], prof2N[16];
-};
-
 enum Op {
   OP_EXIT = 0, OP_REFS, OP_RMD, OP_PRED_RESI, OP_FWD_QUANT, OP_LEVELS_OUT, OP_INV_RECON, OP_COPY2D, OP_COPY16, OP_ZERO16,
   OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_TASKS
 };
-enum { ENG_MASTER = 0, ENG_THREAD = 1 };
+enum { ENG_MASTER = 0, ENG_LANE = 1 };
 enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1 };
 
 struct Cmd
@@ -145,8 +131,18 @@ struct Cmd
   void* dst;
 };
 
-// One evaluation engine: the master (kind ENG_MASTER: parallel phases go to the block's workers) or a thread engine
-// (kind ENG_THREAD: lane 0 of a worker warp evaluating one independent candidate on private scratch, phases run inline).
+// per-coefficient scratch of one engine (TU pipeline + RDOQ), sized by the engine's largest TU
+template <int N>
+struct CoefScratch
+{
+  int16_t resi[N];
+  int32_t tmp[N], tcoef[N], lvlD[N];
+  double cost0[N], costCoeff[N], costSig[N];
+  int32_t rateIncUp[N], rateIncDown[N], sigRateDelta[N], deltaU[N];
+};
+
+// One evaluation engine.  ENG_MASTER: the warp itself (COOP sections use all lanes); ENG_LANE: one lane evaluating one
+// independent candidate on private scratch, every stage executed by that lane alone.
 struct Engine
 {
   int kind;
@@ -155,7 +151,7 @@ struct Engine
   double rdoqLambda;
   const Tables* t;
   Sbac go;
-  Sbac* slots;                    // master: [5][CI_NUM]; thread engine: [CI_NUM] shared by all depths
+  Sbac* slots;                    // master: [5][CI_NUM]; lane engine: [3] shared by all depths (TU-level slots only)
   Cmd cmd;
   int16_t *refU, *refF;
   uint8_t* flags;
@@ -169,8 +165,8 @@ struct Engine
   int16_t (*qtCoef)[6144];
   int writePic;                   // reconstruct into the picture plane too (master only)
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
-  double* costCGSig;               // RDOQ per-group / per-context scratch (kept out of local memory: a single active
-  uint8_t *cgFlag, *cgFlagCode;    // lane wastes 7/8 of every local-memory sector)
+  double* costCGSig;              // RDOQ per-group / per-context scratch
+  uint8_t *cgFlag, *cgFlagCode;
   double *sigC0, *sigC1;
   int32_t* sigDelta;
   // engine result: best task of the current dispatch
@@ -179,18 +175,56 @@ struct Engine
   int resTask;
 };
 
-struct EngineShared                // shared-memory arrays of one thread engine
+// private global scratch of one lane engine (same layouts as the master's buffers; engines only see depth-3 CUs)
+struct EngineGlobal
 {
+  Engine eng;
   Sbac slots[3];                  // CI_QT_TRAFO_ROOT, CI_TEMP_BEST, CI_QT_TRAFO_TEST
   int16_t refU[36], refF[36];
   uint8_t flags[24];
-  int16_t resi[FHC_ENG_COEFS];
-  int32_t tmp[FHC_ENG_COEFS], tcoef[FHC_ENG_COEFS], lvlD[FHC_ENG_COEFS];
-  double cost0[FHC_ENG_COEFS], costCoeff[FHC_ENG_COEFS], costSig[FHC_ENG_COEFS];
-  int32_t rateIncUp[FHC_ENG_COEFS], rateIncDown[FHC_ENG_COEFS], sigRateDelta[FHC_ENG_COEFS], deltaU[FHC_ENG_COEFS];
+  CoefScratch<FHC_SMALL_COEFS> cs;
   double costCGSig[4], sigC0[28], sigC1[28];
   int32_t sigDelta[28];
   uint8_t cgFlag[4], cgFlagCode[4];
+  CUMeta cu;
+  uint8_t cuStore[12 * 4];
+  int16_t bestCoef[3][64], bestReco[3][64];
+  uint8_t bestTrIdx[4], bestCbf[3][4], bestTs[3][4];
+  int16_t predYuv[6144];
+  int16_t qtRec[4][6144];
+  int16_t qtCoef[4][6144];
+};
+
+// picture descriptor (global memory, filled by the host per submitted picture)
+struct PicDesc
+{
+  const void* org[3];             // input planes (sampleBytes each)
+  int16_t* rec[3];                // reconstruction planes, stride = plane width
+  fhc_ctu_result* out;            // [numCtus]
+  fhc_slice_params sp;
+  int32_t width, height, bitDepth, sampleBytes, wc, hc;
+  long long prof[16], profN[16];  // cycle counters of the picture's warp (FHC_PROFILE builds)
+  long long prof2[16], prof2N[16];
+};
+
+// per-warp state in global memory: the picture being encoded + scratch that does not fit the warp's shared-memory slice
+struct FrameGlobal
+{
+  const void* org[3];
+  int16_t* rec[3];
+  fhc_ctu_result* out;
+  fhc_slice_params sp;
+  int32_t width, height, bitDepth, sampleBytes, wc, hc;
+  long long prof[16], profN[16];
+  long long prof2[16], prof2N[16];
+  int16_t cuCoef[4][2][6144];     // CU coefficient buffers per depth, best/temp
+  int16_t cuReco[4][2][6144];     // CU reconstruction buffers
+  int16_t predYuv[6144];          // prediction -> reconstruction scratch of the CU under test
+  int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
+  int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
+  int16_t rmdPred[4096];          // one group of predicted modes of the rough mode decision
+  CoefScratch<1024> big;          // TU pipeline + RDOQ scratch of 16x16 / 32x32 TUs
+  EngineGlobal eng[FHC_NENG];
 };
 
 struct TaskDesc
@@ -207,9 +241,10 @@ struct FrameParams                 // hot read-only copy of the picture header (
   fhc_slice_params sp;
 };
 
+// the warp's shared-memory slice
 struct Shared
 {
-  Tables t;
+  const Tables* t;
   FrameParams fp;
   Sbac slot[5][CI_NUM];
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
@@ -217,31 +252,26 @@ struct Shared
   CUMeta cu[4][2];
   uint8_t cuStore[2 * 12 * (256 + 64 + 16 + 4)];
   Engine master;
-  Engine eng[FHC_NENG];
-  EngineShared engSh[FHC_NENG];
   TaskDesc task;
   // master scratch
   int16_t refU[260], refF[260];
   uint8_t flags[72];
-  int16_t resi[1024];
-  int32_t tmp[1024], tcoef[1024], lvlD[1024];
-  int16_t rmdPred[4096];
+  CoefScratch<FHC_SMALL_COEFS> cs;
   uint32_t satd[36];
   uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];
   double costCGSig[64], sigC0[28], sigC1[28];
   int32_t sigDelta[28];
   uint8_t cgFlag[64], cgFlagCode[64];
-  // RDOQ per-coefficient state of the master (up to 32x32)
-  double rdCost0[1024], rdCostCoeff[1024], rdCostSig[1024];
-  int32_t rdRateIncUp[1024], rdRateIncDown[1024], rdSigRateDelta[1024], rdDeltaU[1024];
 };
 
-struct Ctx { FrameGlobal* g; Shared* s; Engine* e; };
+// lane/nl: this thread's index and the size of the lane group that executes COOP sections together (32 = the warp,
+// 1 = a lane engine on its own); mask = the group's __syncwarp mask
+struct Ctx { FrameGlobal* g; Shared* s; Engine* e; int lane, nl; unsigned mask; };
 
 #if defined(FHC_DEVICE_BUILD) && defined(FHC_PROFILE)
 #define FHC_TIC(k) const long long tic_##k = clock64()
-#define FHC_TOC3(c, nm, k) do { if ((c).e->kind == ENG_MASTER) { const volatile int fence_ = *(volatile int*)&(c).e->cmd.op; (void)fence_; (c).g->prof2[k] += clock64() - tic_##nm; (c).g->prof2N[k]++; } } while (0)
-#define FHC_TOC2(c, nm, k) do { if ((c).e->kind == ENG_MASTER) { const volatile int fence_ = *(volatile int*)&(c).e->cmd.op; (void)fence_; (c).g->prof[k] += clock64() - tic_##nm; (c).g->profN[k]++; } } while (0)
+#define FHC_TOC3(c, nm, k) do { if ((c).e->kind == ENG_MASTER && (c).lane == 0) { (c).g->prof2[k] += clock64() - tic_##nm; (c).g->prof2N[k]++; } } while (0)
+#define FHC_TOC2(c, nm, k) do { if ((c).e->kind == ENG_MASTER && (c).lane == 0) { (c).g->prof[k] += clock64() - tic_##nm; (c).g->profN[k]++; } } while (0)
 #else
 #define FHC_TIC(k) do { } while (0)
 #define FHC_TOC3(c, nm, k) do { } while (0)
@@ -252,15 +282,17 @@ enum { PF2_CHECK_D0 = 0, PF2_CHECK_D1, PF2_CHECK_D2, PF2_CHECK_D3_2N, PF2_CHECK_
 
 
 // ----------------------------------------------------------------------------------------------
-// portability layer: barriers and the command hand-off
+// portability layer: COOP sections
 // ----------------------------------------------------------------------------------------------
 FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw);
+FHC_D void dispatch_tasks(const Ctx& c);
+FHC_D void run_tasks(const Ctx& c);
 FHC_DH int num_phases(int op)
 {
   switch (op)
   {
   case OP_REFS: return 2;
-  case OP_RMD: return 2;            // per mode group, see par_rmd
+  case OP_RMD: return 2;            // per mode group, see OP_RMD
   case OP_FWD_QUANT: return 3;
   case OP_INV_RECON: return 4;
   default: return 1;
@@ -268,64 +300,56 @@ FHC_DH int num_phases(int op)
 }
 
 #ifdef FHC_DEVICE_BUILD
-FHC_DH void bar_all() { __syncthreads(); }
-FHC_DH void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(FHC_NWORK) : "memory"); }
-// master side: publish the command, release the workers, wait for completion
+FHC_DH void group_sync(const Ctx& c) { if (c.nl > 1) __syncwarp(c.mask); }
+// A COOP section, called by the group's LEADER (lane 0 of the group) only: the followers sit in follower_loop.  The
+// leader publishes the command (its arguments are already in e->cmd), every phase is striped over the group's lanes
+// and fenced.  Nothing in the decision code is executed redundantly, so no lane ever depends on running in lockstep
+// with another one.  A lane engine (nl == 1) runs the phases inline.
 FHC_DH void par(const Ctx& c, int op)
 {
-  if (c.e->kind == ENG_THREAD)
-  {
-    // warp engine: lane 0 (here) publishes the command, lanes 1..31 (engine_lanes_loop) join the phases
-    c.e->cmd.op = op;
-    __syncwarp();
-    const int np = num_phases(op);
-    for (int ph = 0; ph < np; ph++)
-    {
-      run_phase(c, op, ph, 0, 32);
-      if (ph + 1 < np) __syncwarp();
-    }
-    __syncwarp();
-    return;
-  }
   FHC_TIC(par);
-  c.e->cmd.op = op;
-  bar_all();
-  bar_all();
+  const int np = (op == OP_RMD) ? c.e->cmd.a[15] : num_phases(op);
+  if (c.nl > 1)
+  {
+    c.e->cmd.op = op;
+    __syncwarp(c.mask);
+  }
+  FHC_NOUNROLL for (int ph = 0; ph < np; ph++)
+  {
+    run_phase(c, op, ph, c.lane, c.nl);
+    group_sync(c);
+  }
   FHC_TOC2(c, par, PF_PAR);
 }
-// lanes 1..31 of a warp whose lane 0 runs a task
-FHC_NOINLINE void engine_lanes_loop(const Ctx& c, int lane)
+// lanes 1.. of a group: execute the leader's COOP sections and LANE dispatches until it publishes OP_EXIT
+FHC_D void follower_loop(const Ctx& c)
 {
   for (;;)
   {
-    __syncwarp();
+    __syncwarp(c.mask);
     const int op = c.e->cmd.op;
     if (op == OP_EXIT) break;
-    const int np = num_phases(op);
-    for (int ph = 0; ph < np; ph++)
+    if (op == OP_TASKS) { run_tasks(c); __syncwarp(c.mask); continue; }
+    const int np = (op == OP_RMD) ? c.e->cmd.a[15] : num_phases(op);
+    FHC_NOUNROLL for (int ph = 0; ph < np; ph++)
     {
-      run_phase(c, op, ph, lane, 32);
-      if (ph + 1 < np) __syncwarp();
+      run_phase(c, op, ph, c.lane, c.nl);
+      __syncwarp(c.mask);
     }
-    __syncwarp();
   }
 }
-FHC_DH void engine_lanes_release(const Ctx& c) { c.e->cmd.op = OP_EXIT; __syncwarp(); }
+FHC_DH void release_followers(const Ctx& c)
+{
+  if (c.nl > 1) { c.e->cmd.op = OP_EXIT; __syncwarp(c.mask); }
+}
 #else
-FHC_D void run_tasks_emu(const Ctx& c);
+FHC_DH void group_sync(const Ctx& c) { (void)c; }
+// emulation: the group's lanes are executed one after the other, phase by phase
 FHC_DH void par(const Ctx& c, int op)
 {
-  if (c.e->kind == ENG_THREAD)
-  {
-    const int np = num_phases(op);
-    for (int ph = 0; ph < np; ph++) run_phase(c, op, ph, 0, 1);
-    return;
-  }
-  c.e->cmd.op = op;
-  if (op == OP_TASKS) { run_tasks_emu(c); return; }
   const int np = (op == OP_RMD) ? c.e->cmd.a[15] : num_phases(op);
   for (int ph = 0; ph < np; ph++)
-    for (int w = 0; w < FHC_NWORK; w++) run_phase(c, op, ph, w, FHC_NWORK);
+    for (int w = 0; w < c.nl; w++) run_phase(c, op, ph, w, c.nl);
 }
 #endif
 
@@ -434,25 +458,26 @@ FHC_DH uint32_t had4(int* d)
   return (uint32_t)((s + 1) >> 1);
 }
 
-FHC_DH void atomic_or_u32(uint32_t* p, uint32_t v)
+// accumulations from a striped phase: atomic when several lanes of a group contribute, plain for a lane engine
+FHC_DH void atomic_or_u32(uint32_t* p, uint32_t v, int nw)
 {
 #ifdef FHC_DEVICE_BUILD
-  atomicOr(p, v);
-#else
+  if (nw > 1) { atomicOr(p, v); return; }
+#endif
+  (void)nw;
   *p |= v;
-#endif
 }
-FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v)
+FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v, int nw)
 {
 #ifdef FHC_DEVICE_BUILD
-  atomicAdd(p, v);
-#else
-  *p += v;
+  if (nw > 1) { atomicAdd(p, v); return; }
 #endif
+  (void)nw;
+  *p += v;
 }
 
 // ----------------------------------------------------------------------------------------------
-// worker phases
+// COOP phases (striped over the lanes of the calling group: w = lane index, nw = group size)
 // ----------------------------------------------------------------------------------------------
 // cmd.a[] conventions are documented at each master call site ("par_*" helpers below).
 FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
@@ -549,8 +574,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
         const int x = sidx & (n - 1), y = sidx >> log2n;
-        const int16_t* line = use_filtered_refs(s->t, 0, mode, log2n) ? e->refF : e->refU;
-        s->rmdPred[i] = (int16_t)pred_sample(s->t, line, n, log2n, mode, x, y, 1, s->fp.bitDepth, e->refDc);
+        const int16_t* line = use_filtered_refs(*s->t, 0, mode, log2n) ? e->refF : e->refU;
+        g->rmdPred[i] = (int16_t)pred_sample(*s->t, line, n, log2n, mode, x, y, 1, s->fp.bitDepth, e->refDc);
       }
     }
     else
@@ -565,8 +590,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           int m[64];
           for (int yy = 0; yy < 8; yy++)
             for (int xx = 0; xx < 8; xx++)
-              m[yy * 8 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - s->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
-          atomic_add_u32(&s->satd[m0 + mi], had8(m));
+              m[yy * 8 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - g->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
+          atomic_add_u32(&s->satd[m0 + mi], had8(m), nw);
         }
       }
       else
@@ -575,8 +600,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         {
           int d[16];
           for (int yy = 0; yy < 4; yy++)
-            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + yy * stride + xx) - s->rmdPred[mi * 16 + yy * 4 + xx];
-          atomic_add_u32(&s->satd[m0 + mi], had4(d));
+            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + yy * stride + xx) - g->rmdPred[mi * 16 + yy * 4 + xx];
+          atomic_add_u32(&s->satd[m0 + mi], had4(d), nw);
         }
       }
     }
@@ -597,7 +622,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       if (a[7] == 2) v = e->tsPred[comp][i];
       else
       {
-        v = pred_sample(s->t, line, n, log2n, a[2], x, y, comp == 0, s->fp.bitDepth, e->refDc);
+        v = pred_sample(*s->t, line, n, log2n, a[2], x, y, comp == 0, s->fp.bitDepth, e->refDc);
         if (a[7] == 1) e->tsPred[comp][i] = (int16_t)v;
       }
       pred[y * ps + x] = (int16_t)v;
@@ -626,7 +651,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
         int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * e->resi[j * n + q];
+        for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->resi[j * n + q];
         e->tmp[i] = (acc + add1) >> shift1;
       }
     }
@@ -637,16 +662,16 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
         int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(s->t, n, k, q, a[1]) * e->tmp[j * n + q];
+        for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->tmp[j * n + q];
         e->tcoef[i] = (acc + add2) >> shift2;
       }
     }
     if (phase == 2)
     {
       // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient
-      const uint16_t* scan = scan_tab(s->t, a[3], log2n);
+      const uint16_t* scan = scan_tab(*s->t, a[3], log2n);
       const int qBits = a[5];
-      const double errScale = s->t.errScale[a[6]][log2n - 2][a[7]];
+      const double errScale = s->t->errScale[a[6]][log2n - 2][a[7]];
       const int64_t cap = (int64_t)2147483647 - ((int64_t)1 << (qBits - 1));
       for (int p = w; p < n2; p += nw)
       {
@@ -658,7 +683,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         e->lvlD[p] = ld;
         e->cost0[p] = err * err * errScale;
         e->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
-        if (m) atomic_or_u32(&e->cgNZ[p >> 9], 1u << ((p >> 4) & 31));
+        if (m) atomic_or_u32(&e->cgNZ[p >> 9], 1u << ((p >> 4) & 31), nw);
       }
     }
     break;
@@ -707,7 +732,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
             int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
+            for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
             e->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
           }
         }
@@ -721,7 +746,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
             int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
+            for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
             e->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
           }
         }
@@ -746,7 +771,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         const int d = v - org_at(g, s->fp.sampleBytes, comp, a[12] + y * stride + x);
         acc += (uint32_t)((d * d) >> shift);
       }
-      if (acc) atomic_add_u32(&e->sse, acc);
+      if (acc) atomic_add_u32(&e->sse, acc, nw);
     }
     break;
   }
@@ -853,16 +878,20 @@ FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; e->go.frac += (uint64_t)e->
 FHC_DH void reset_bits(Engine* e) { e->go.frac &= 32767; e->bins = 0; }
 FHC_DH uint32_t num_bits(const Engine* e) { return (uint32_t)(e->go.frac >> 15); }
 FHC_DH int ctx_bits(const Engine* e, int ctx, int bin) { return e->t->entropyBits[e->go.c[ctx] ^ bin]; }
-FHC_DH void sb_copy(Sbac* d, const Sbac* sr)
+FHC_DH void sb_copy(const Ctx& c, Sbac* d, const Sbac* sr)
 {
   const uint64_t* a = (const uint64_t*)sr;
   uint64_t* b = (uint64_t*)d;
+  (void)c;
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll
+#endif
   for (int i = 0; i < (int)(sizeof(Sbac) / 8); i++) b[i] = a[i];
 }
 FHC_DH void sbac_reset(const Tables& t, Sbac* sb, int qp)                        // ContextModel::init (ContextModel.cpp:56)
 {
   qp = clip3(0, 51, qp);
-  for (int i = 0; i < NUM_CTX; i++)
+  FHC_NOUNROLL for (int i = 0; i < NUM_CTX; i++)
   {
     const int iv = t.ctxInit[i], slope = (iv >> 4) * 5 - 45, offset = ((iv & 15) << 3) - 16;
     const int st = imin(imax(1, ((slope * qp) >> 4) + offset), 126);
@@ -892,12 +921,17 @@ FHC_DH Sbac* slot_of(const Ctx& c, int depth, int ci)
 }
 
 // winner of a dispatch: lowest cost, ties to the lowest task index (= the sequential strict-< scan of the reference)
-FHC_DH int best_engine(const Shared* s)
+FHC_DH int best_engine(const Ctx& c)
 {
-  const int ne = imin(FHC_NENG, s->task.numTasks);
+  const FrameGlobal* g = c.g;
+  const int ne = imin(FHC_NENG, c.s->task.numTasks);
   int be = 0;
-  for (int i = 1; i < ne; i++)
-    if (s->eng[i].resCost < s->eng[be].resCost || (s->eng[i].resCost == s->eng[be].resCost && s->eng[i].resTask < s->eng[be].resTask)) be = i;
+  FHC_NOUNROLL for (int i = 1; i < ne; i++)
+  {
+    const Engine* a = &g->eng[i].eng;
+    const Engine* b = &g->eng[be].eng;
+    if (a->resCost < b->resCost || (a->resCost == b->resCost && a->resTask < b->resTask)) be = i;
+  }
   return be;
 }
 
@@ -912,29 +946,29 @@ FHC_DH int nb_left(const Ctx& c, const CUMeta* cu, int zabs, int f)
 {
   const Shared* s = c.s;
   Engine* e = c.e; (void)e;
-  const int r = s->t.z2r[zabs];
+  const int r = s->t->z2r[zabs];
   if (r & 15)
   {
-    const int nz = s->t.r2z[r - 1];
-    if ((r & 15) == (s->t.z2r[cu->zidx] & 15)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
+    const int nz = s->t->r2z[r - 1];
+    if ((r & 15) == (s->t->z2r[cu->zidx] & 15)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
     return cu_field(cu, nz - cu->zidx, f);
   }
   if (s->ctuX == 0) return -1;
-  return ctu_field(&c.g->out[s->ctuAddr - 1], s->t.r2z[r + 15], f);
+  return ctu_field(&c.g->out[s->ctuAddr - 1], s->t->r2z[r + 15], f);
 }
 FHC_DH int nb_above(const Ctx& c, const CUMeta* cu, int zabs, int f, int planarAtCtuBoundary)
 {
   const Shared* s = c.s;
   Engine* e = c.e; (void)e;
-  const int r = s->t.z2r[zabs];
+  const int r = s->t->z2r[zabs];
   if (r >> 4)
   {
-    const int nz = s->t.r2z[r - 16];
-    if ((r >> 4) == (s->t.z2r[cu->zidx] >> 4)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
+    const int nz = s->t->r2z[r - 16];
+    if ((r >> 4) == (s->t->z2r[cu->zidx] >> 4)) return ctu_field(&c.g->out[s->ctuAddr], nz, f);
     return cu_field(cu, nz - cu->zidx, f);
   }
   if (planarAtCtuBoundary || s->ctuY == 0) return -1;
-  return ctu_field(&c.g->out[s->ctuAddr - c.s->fp.wc], s->t.r2z[r + 240], f);
+  return ctu_field(&c.g->out[s->ctuAddr - c.s->fp.wc], s->t->r2z[r + 240], f);
 }
 FHC_DH int get_mpm(const Ctx& c, const CUMeta* cu, int relIdx, int mpm[3])
 {
@@ -991,16 +1025,16 @@ FHC_D void code_luma_dir(const Ctx& c, const CUMeta* cu, int relIdx, int isMulti
   const int partNum = isMultiple ? (cu->part[relIdx] == SIZE_NxN ? 4 : 1) : 1;
   const int partOffset = (256 >> (cu->dep[relIdx] << 1)) >> 2;
   int predIdx[4];
-  for (int j = 0; j < partNum; j++)
+  FHC_NOUNROLL for (int j = 0; j < partNum; j++)
   {
     int preds[3];
     const int dir = cu->ldir[relIdx + partOffset * j];
     get_mpm(c, cu, relIdx + partOffset * j, preds);
     predIdx[j] = -1;
-    for (int i = 0; i < 3; i++) if (dir == preds[i]) predIdx[j] = i;
+    FHC_NOUNROLL for (int i = 0; i < 3; i++) if (dir == preds[i]) predIdx[j] = i;
     enc_bin(c.e, CTX_IPRED, predIdx[j] != -1 ? 1 : 0);
   }
-  for (int j = 0; j < partNum; j++) enc_ep(c.e, predIdx[j] != -1 ? (predIdx[j] ? 2 : 1) : 5);
+  FHC_NOUNROLL for (int j = 0; j < partNum; j++) enc_ep(c.e, predIdx[j] != -1 ? (predIdx[j] ? 2 : 1) : 5);
 }
 FHC_DH void code_chroma_dir(const Ctx& c, const CUMeta* cu, int relIdx)                        // TEncSbac.cpp:698
 {
@@ -1052,7 +1086,7 @@ FHC_DH void code_remain(Engine* e, uint32_t symbol, uint32_t rParam)            
   {
     uint32_t length = rParam;
     codeNumber -= (3 << rParam);
-    while (codeNumber >= (1 << length)) codeNumber -= (1 << (length++));
+    FHC_NOUNROLL while (codeNumber >= (1 << length)) codeNumber -= (1 << (length++));
     enc_ep(e, (int)(3 + length + 1 - rParam + length));
   }
 }
@@ -1064,8 +1098,8 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   Engine* e = c.e; (void)e;
   const int isChroma = comp != 0, n = 1 << log2n;
   const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
-  const uint16_t* scan = scan_tab(s->t, scanType, log2n);
-  const uint8_t* scanCG = scan_cg(s->t, scanType, log2n);
+  const uint16_t* scan = scan_tab(*s->t, scanType, log2n);
+  const uint8_t* scanCG = scan_cg(*s->t, scanType, log2n);
   const int wg = n >> 2;
   const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
@@ -1073,15 +1107,15 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   int scanPosLast = -1, posLast = 0;
 
   if (log2n == 2) enc_bin(e, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
-  for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
+  FHC_NOUNROLL for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
   // last significant position: highest scan index with a non-zero level
-  for (int p = n * n - 1; p >= 0; p--)
+  FHC_NOUNROLL for (int p = n * n - 1; p >= 0; p--)
     if (coef[scan[p]] != 0) { scanPosLast = p; break; }
   posLast = scan[scanPosLast];
-  for (int g4 = 0; g4 <= (scanPosLast >> 4); g4++)
+  FHC_NOUNROLL for (int g4 = 0; g4 <= (scanPosLast >> 4); g4++)
   {
     int any = 0;
-    for (int i = 0; i < 16; i++) any |= coef[scan[g4 * 16 + i]] != 0;
+    FHC_NOUNROLL for (int i = 0; i < 16; i++) any |= coef[scan[g4 * 16 + i]] != 0;
     if (any) cgFlag[scanCG[g4]] = 1;
   }
   {
@@ -1090,9 +1124,9 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
     const int gx = group_idx(posX), gy = group_idx(posY), gmax = group_idx(n - 1);
     last_ctx_params(isChroma, log2n, &off, &shift);
     const int bx = CTX_LASTX + (isChroma ? 15 : 0) + off, by = CTX_LASTY + (isChroma ? 15 : 0) + off;
-    for (cc = 0; cc < gx; cc++) enc_bin(e, bx + (cc >> shift), 1);
+    FHC_NOUNROLL for (cc = 0; cc < gx; cc++) enc_bin(e, bx + (cc >> shift), 1);
     if (gx < gmax) enc_bin(e, bx + (cc >> shift), 0);
-    for (cc = 0; cc < gy; cc++) enc_bin(e, by + (cc >> shift), 1);
+    FHC_NOUNROLL for (cc = 0; cc < gy; cc++) enc_bin(e, by + (cc >> shift), 1);
     if (gy < gmax) enc_bin(e, by + (cc >> shift), 0);
     if (gx > 3) enc_ep(e, (gx - 2) >> 1);
     if (gy > 3) enc_ep(e, (gy - 2) >> 1);
@@ -1101,7 +1135,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
     const int lastScanSet = scanPosLast >> 4;
     uint32_t c1 = 1;
     int scanPosSig = scanPosLast;
-    for (int subSet = lastScanSet; subSet >= 0; subSet--)
+    FHC_NOUNROLL for (int subSet = lastScanSet; subSet >= 0; subSet--)
     {
       int numNonZero = 0, lastNZ = -1, firstNZ = 16, escape = 0;
       const int subPos = subSet << 4;
@@ -1118,11 +1152,11 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
       if (cgFlag[cgBlk])
       {
         const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
-        for (; scanPosSig >= subPos; scanPosSig--)
+        FHC_NOUNROLL for (; scanPosSig >= subPos; scanPosSig--)
         {
           const int blkPos = scan[scanPosSig], sig = coef[blkPos] != 0;
           if (scanPosSig > subPos || subSet == 0 || numNonZero)
-            enc_bin(e, sigBase + sig_ctx_inc(s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
+            enc_bin(e, sigBase + sig_ctx_inc(*s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
           if (sig)
           {
             absCoeff[numNonZero++] = iabs(coef[blkPos]);
@@ -1139,7 +1173,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
         const int numC1 = imin(numNonZero, 8);
         int firstC2 = -1;
         c1 = 1;
-        for (int idx = 0; idx < numC1; idx++)
+        FHC_NOUNROLL for (int idx = 0; idx < numC1; idx++)
         {
           const int sym = absCoeff[idx] > 1;
           enc_bin(e, CTX_ONE + 4 * ctxSet + (int)c1, sym);
@@ -1157,7 +1191,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
         if (escape)
         {
           int firstCoeff2 = 1;
-          for (int idx = 0; idx < numNonZero; idx++)
+          FHC_NOUNROLL for (int idx = 0; idx < numNonZero; idx++)
           {
             const int baseLevel = (idx < 8) ? (2 + firstCoeff2) : 1;
             if (absCoeff[idx] >= baseLevel)
@@ -1193,7 +1227,7 @@ FHC_DH QpParam qp_param(const Ctx& c, int comp)                                 
   else
   {
     base = clip3(-bdOff, 57, c.s->fp.sp.sliceQp);
-    base = base < 0 ? base + bdOff : c.s->t.chromaScale[base] + bdOff;
+    base = base < 0 ? base + bdOff : c.s->t->chromaScale[base] + bdOff;
   }
   QpParam q; q.per = base / 6; q.rem = base % 6;
   return q;
@@ -1213,7 +1247,7 @@ FHC_DH int ic_rate(const Engine* e, uint32_t absLevel, int ctxOne, int ctxAbs, u
     {
       length = goRice;
       symbol = symbol - (3u << goRice);
-      while (symbol >= (1u << length)) symbol -= (1u << (length++));
+      FHC_NOUNROLL while (symbol >= (1u << length)) symbol -= (1u << (length++));
       rate += (int)((3 + length + 1 - goRice + length) << 15);
     }
     if (c1Idx < 8)
@@ -1243,7 +1277,7 @@ FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, d
   else *codedCost = FHC_MAX_COST;
   if (!isLast) currCostSig = sigCost1;
   const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
-  for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
+  FHC_NOUNROLL for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
   {
     const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
     double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(e, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
@@ -1260,11 +1294,11 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
   const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.s->fp.bitDepth;
   const QpParam q = qp_param(c, comp);
   const int qBits = 14 + q.per + (15 - bd - log2n);
-  const double errScale = s->t.errScale[isChroma][log2n - 2][q.rem];
+  const double errScale = s->t->errScale[isChroma][log2n - 2][q.rem];
   const double lambda = e->rdoqLambda;
   const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
-  const uint16_t* scan = scan_tab(s->t, scanType, log2n);
-  const uint8_t* scanCG = scan_cg(s->t, scanType, log2n);
+  const uint16_t* scan = scan_tab(*s->t, scanType, log2n);
+  const uint8_t* scanCG = scan_cg(*s->t, scanType, log2n);
   const int wg = n >> 2, cgNum = numCoef >> 4;
   const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
@@ -1280,7 +1314,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
   uint32_t ctxSet = 0, c1Idx = 0, c2Idx = 0, goRice = 0, absSum = 0;
   int bestLastIdxP1 = 0;
 
-  for (int i = 0; i < cgNum; i++) { costCGSig[i] = 0; cgFlag[i] = 0; }
+  FHC_NOUNROLL for (int i = 0; i < cgNum; i++) { costCGSig[i] = 0; cgFlag[i] = 0; }
 
   // lambda * bits of sig_coeff_flag = 0 / 1 and the rate difference, per context of this channel (contexts do not
   // change while a TU is being quantised): replaces estBitsSbacStruct::significantBits (TEncSbac.cpp:1772)
@@ -1288,21 +1322,21 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
   int32_t* sigDelta = e->sigDelta;
   {
     const int nSig = isChroma ? 16 : 28;
-    for (int i = 0; i < nSig; i++)
+    FHC_NOUNROLL for (int i = 0; i < nSig; i++)
     {
       const int b0 = ctx_bits(e, sigBase + i, 0), b1 = ctx_bits(e, sigBase + i, 1);
       sigC0[i] = dmul(lambda, (double)b0); sigC1[i] = dmul(lambda, (double)b1); sigDelta[i] = b1 - b0;
     }
   }
 
-  for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
+  FHC_NOUNROLL for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
   {
     const int cgBlk = scanCG[cgScanPos], cgY = cgBlk / wg, cgX = cgBlk - cgY * wg;
     const int cgHasLevel = (e->cgNZ[cgScanPos >> 5] >> (cgScanPos & 31)) & 1;
     if (!cgHasLevel && lastScanPos < 0)
     {
       // nothing coded yet and nothing to code here: only the uncoded distortion accumulates
-      for (int posInCG = 15; posInCG >= 0; posInCG--)
+      FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
       {
         const double c0 = costCoeff0[cgScanPos * 16 + posInCG];
         blockUncoded = dadd(blockUncoded, c0);
@@ -1316,7 +1350,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       // group without any candidate level below the last position: every coefficient takes "level 0" and the group
       // ends up with coded_sub_block_flag = 0; none of the per-coefficient arrays of this group is read again
       double sigCost = 0;
-      for (int posInCG = 15; posInCG >= 0; posInCG--)
+      FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
       {
         const int scanPos = cgScanPos * 16 + posInCG;
         const double c0 = costCoeff0[scanPos];
@@ -1335,7 +1369,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
     }
     double sigCost = 0, sigCost0 = 0, codedLevelAndDist = 0, uncodedDist = 0;
     int nnzBeforePos0 = 0;
-    for (int posInCG = 15; posInCG >= 0; posInCG--)
+    FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
     {
       const int scanPos = cgScanPos * 16 + posInCG;
       const uint32_t blkPos = scan[scanPos];
@@ -1446,7 +1480,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
             cgFlag[cgBlk] = 0;
             baseCost = costZeroCG;
             costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 0));
-            for (int posInCG = 15; posInCG >= 0; posInCG--)
+            FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
             {
               const int scanPos = cgScanPos * 16 + posInCG;
               const uint32_t blkPos = scan[scanPos];
@@ -1466,13 +1500,13 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
     int foundLast = 0, off, shift;
     last_ctx_params(isChroma, log2n, &off, &shift);
     const int bx0 = CTX_LASTX + (isChroma ? 15 : 0) + off, by0 = CTX_LASTY + (isChroma ? 15 : 0) + off, gmax = group_idx(n - 1);
-    for (int cgScanPos = cgLastScanPos; cgScanPos >= 0; cgScanPos--)
+    FHC_NOUNROLL for (int cgScanPos = cgLastScanPos; cgScanPos >= 0; cgScanPos--)
     {
       const int cgBlk = scanCG[cgScanPos];
       baseCost = dsub(baseCost, costCGSig[cgScanPos]);
       if (cgFlag[cgBlk])
       {
-        for (int posInCG = 15; posInCG >= 0; posInCG--)
+        FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
         {
           const int scanPos = cgScanPos * 16 + posInCG;
           if (scanPos > lastScanPos) continue;
@@ -1483,9 +1517,9 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
             const uint32_t lx = scanType == SCAN_VER ? posY : posX, ly = scanType == SCAN_VER ? posX : posY;
             const int gx = group_idx((int)lx), gy = group_idx((int)ly);
             int bx = 0, by = 0, cc;
-            for (cc = 0; cc < gx; cc++) bx += ctx_bits(e, bx0 + (cc >> shift), 1);
+            FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ctx_bits(e, bx0 + (cc >> shift), 1);
             if (gx < gmax) bx += ctx_bits(e, bx0 + (gx >> shift), 0);
-            for (cc = 0; cc < gy; cc++) by += ctx_bits(e, by0 + (cc >> shift), 1);
+            FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ctx_bits(e, by0 + (cc >> shift), 1);
             if (gy < gmax) by += ctx_bits(e, by0 + (gy >> shift), 0);
             double cost = (double)(bx + by);
             if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
@@ -1503,14 +1537,14 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       }
     }
   }
-  for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
+  FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
   {
     const int blkPos = scan[scanPos];
     const int32_t level = dst[blkPos];
     absSum += (uint32_t)level;
     dst[blkPos] = (src[blkPos] < 0) ? -level : level;
   }
-  for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) dst[scan[scanPos]] = 0;
+  FHC_NOUNROLL for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) dst[scan[scanPos]] = 0;
 
   if (absSum >= 2)                                                             // sign bit hiding (TComTrQuant.cpp:2530)
   {
@@ -1523,14 +1557,14 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
 #endif
     const int64_t rdFactor = (int64_t)f;
     int lastCG = -1;
-    for (int subSet = (numCoef - 1) >> 4; subSet >= 0; subSet--)
+    FHC_NOUNROLL for (int subSet = (numCoef - 1) >> 4; subSet >= 0; subSet--)
     {
       const int subPos = subSet << 4;
       int firstNZ = 16, lastNZ = -1, sum = 0, nn;
       if (subPos > lastScanPos) continue;                                       // nothing coded up there (all levels are 0)
-      for (nn = 15; nn >= 0; --nn) if (dst[scan[nn + subPos]]) { lastNZ = nn; break; }
-      for (nn = 0; nn < 16; nn++) if (dst[scan[nn + subPos]]) { firstNZ = nn; break; }
-      for (nn = firstNZ; nn <= lastNZ; nn++) sum += dst[scan[nn + subPos]];
+      FHC_NOUNROLL for (nn = 15; nn >= 0; --nn) if (dst[scan[nn + subPos]]) { lastNZ = nn; break; }
+      FHC_NOUNROLL for (nn = 0; nn < 16; nn++) if (dst[scan[nn + subPos]]) { firstNZ = nn; break; }
+      FHC_NOUNROLL for (nn = firstNZ; nn <= lastNZ; nn++) sum += dst[scan[nn + subPos]];
       if (lastNZ >= 0 && lastCG == -1) lastCG = 1;
       if (lastNZ - firstNZ >= 4)
       {
@@ -1539,7 +1573,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
         {
           int64_t minCostInc = INT64_MAX, curCost = INT64_MAX;
           int minPos = -1, finalChange = 0, curChange = 0;
-          for (nn = (lastCG == 1 ? lastNZ : 15); nn >= 0; --nn)
+          FHC_NOUNROLL for (nn = (lastCG == 1 ? lastNZ : 15); nn >= 0; --nn)
           {
             const uint32_t blkPos = scan[nn + subPos];
             if (dst[blkPos] != 0)
@@ -1588,8 +1622,8 @@ FHC_DH uint32_t rdoq_pass(const Ctx& c, const CUMeta* cu, int relIdxComp, int co
 // ----------------------------------------------------------------------------------------------
 // geometry helpers
 // ----------------------------------------------------------------------------------------------
-FHC_DH int rel_x(const Shared* s, int relIdx) { return (s->t.z2r[relIdx] & 15) * 4; }
-FHC_DH int rel_y(const Shared* s, int relIdx) { return (s->t.z2r[relIdx] >> 4) * 4; }
+FHC_DH int rel_x(const Shared* s, int relIdx) { return (s->t->z2r[relIdx] & 15) * 4; }
+FHC_DH int rel_y(const Shared* s, int relIdx) { return (s->t->z2r[relIdx] >> 4) * 4; }
 FHC_DH CUMeta* best_cu(Shared* s, int d) { return &s->cu[d][s->bestIdx[d]]; }
 FHC_DH CUMeta* temp_cu(Shared* s, int d) { return &s->cu[d][1 - s->bestIdx[d]]; }
 FHC_DH int cu_buf_index(const Shared* s, const CUMeta* cu) { return (int)(cu - &s->cu[cu->depth][0]); }
@@ -1603,7 +1637,7 @@ FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int 
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
-  const int zLT = cu->zidx + relIdx, rLT = s->t.z2r[zLT];
+  const int zLT = cu->zidx + relIdx, rLT = s->t->z2r[zLT];
   const int ux = rLT & 15, uy = rLT >> 4;
   const int us = comp ? 2 : 4, nu = n / us, total = 4 * nu + 1;
   uint8_t* flags = e->flags;
@@ -1611,35 +1645,43 @@ FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int 
   FHC_TIC(rf);
   const int leftOk = (ux > 0 || s->ctuX > 0), aboveOk = (uy > 0 || s->ctuY > 0);
   flags[2 * nu] = (uint8_t)(leftOk && aboveOk);
-  for (int i = 0; i < nu; i++) { flags[2 * nu + 1 + i] = (uint8_t)aboveOk; flags[2 * nu - 1 - i] = (uint8_t)leftOk; }
+  FHC_NOUNROLL for (int i = 0; i < nu; i++) { flags[2 * nu + 1 + i] = (uint8_t)aboveOk; flags[2 * nu - 1 - i] = (uint8_t)leftOk; }
   {
-    const int rRT = rLT + nu - 1, zRT = s->t.r2z[rRT];
-    for (int i = 1; i <= nu; i++)
+    const int rRT = rLT + nu - 1, zRT = s->t->r2z[rRT];
+    FHC_NOUNROLL for (int i = 1; i <= nu; i++)
     {
       int av;
       if (s->ctuPelX + (rRT & 15) * 4 + 4 * i >= s->fp.width) av = 0;
-      else if ((rRT & 15) < 16 - i) av = (uy != 0) ? (zRT > s->t.r2z[rRT - 16 + i]) : (s->ctuY > 0);
+      else if ((rRT & 15) < 16 - i) av = (uy != 0) ? (zRT > s->t->r2z[rRT - 16 + i]) : (s->ctuY > 0);
       else if (uy != 0) av = 0;
       else av = (s->ctuY > 0) && (s->ctuX + 1 < s->fp.wc);
       flags[3 * nu + i] = (uint8_t)av;
     }
-    const int rLB = rLT + (nu - 1) * 16, zLB = s->t.r2z[rLB];
-    for (int i = 1; i <= nu; i++)
+    const int rLB = rLT + (nu - 1) * 16, zLB = s->t->r2z[rLB];
+    FHC_NOUNROLL for (int i = 1; i <= nu; i++)
     {
       int av;
       if (s->ctuPelY + (rLB >> 4) * 4 + 4 * i >= s->fp.height) av = 0;
-      else if ((rLB >> 4) < 16 - i) av = (ux != 0) ? (zLB > s->t.r2z[rLB + 16 * i - 1]) : (s->ctuX > 0);
+      else if ((rLB >> 4) < 16 - i) av = (ux != 0) ? (zLB > s->t->r2z[rLB + 16 * i - 1]) : (s->ctuX > 0);
       else av = 0;
       flags[nu - i] = (uint8_t)av;
     }
   }
-  for (int i = 0; i < total; i++) numAvail += flags[i];
+  FHC_NOUNROLL for (int i = 0; i < total; i++) numAvail += flags[i];
   Cmd& m = e->cmd;
   const int px = (s->ctuPelX + ux * 4) >> (comp ? 1 : 0), py = (s->ctuPelY + uy * 4) >> (comp ? 1 : 0);
   m.a[0] = comp; m.a[1] = n; m.a[2] = nu; m.a[3] = us; m.a[4] = py * plane_stride(s, comp) + px; m.a[5] = wantFilt;
   m.a[6] = numAvail; m.a[7] = total;
   FHC_TOC2(c, rf, PF_REFS_MASTER);
   par(c, OP_REFS);
+}
+
+template <int N>
+FHC_DH void bind_coef_scratch(Engine* e, CoefScratch<N>* x)
+{
+  e->resi = x->resi; e->tmp = x->tmp; e->tcoef = x->tcoef; e->lvlD = x->lvlD;
+  e->cost0 = x->cost0; e->costCoeff = x->costCoeff; e->costSig = x->costSig;
+  e->rateIncUp = x->rateIncUp; e->rateIncDown = x->rateIncDown; e->sigRateDelta = x->sigRateDelta; e->deltaU = x->deltaU;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1665,6 +1707,11 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   int mode;
   Cmd& m = e->cmd;
   FHC_TIC(tu);
+  if (e->kind == ENG_MASTER)
+  {
+    // TUs up to 8x8 run on the warp's shared-memory scratch, 16x16 / 32x32 on the global one
+    if (n * n <= FHC_SMALL_COEFS) bind_coef_scratch(e, &s->cs); else bind_coef_scratch(e, &g->big);
+  }
 
   if (comp == 0) mode = cu->ldir[relIdx];
   else
@@ -1675,7 +1722,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   int useFilt = 0;
   if (predSaveLoad != 2)
   {
-    useFilt = use_filtered_refs(s->t, comp, mode, log2n);
+    useFilt = use_filtered_refs(*s->t, comp, mode, log2n);
     build_refs(c, cu, relIdx, comp, n, useFilt);
   }
   m.a[0] = comp; m.a[1] = log2n; m.a[2] = mode; m.a[3] = useFilt; m.a[4] = predOff; m.a[5] = cuW;
@@ -1744,13 +1791,13 @@ FHC_D void enc_subdiv_cbf(const Ctx& c, const CUMeta* cu, int relIdx, int log2n,
   else if (log2n == min_tu_log2_in_cu(cu)) { }
   else if (bLuma) enc_bin(c.e, CTX_SUBDIV + (5 - log2n), subdiv);
   if (bChroma)
-    for (int cc = 1; cc < 3; cc++)
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
       if (chromaCodeAll && (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1)))
         code_qt_cbf(c, cu, relIdx, cc, trDepth, subdiv == 0, log2n - 1);
   if (subdiv)
   {
     const int q = (cu->nparts >> (2 * trDepth)) >> 2;
-    for (int i = 0; i < 4; i++) enc_subdiv_cbf(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1) > 2, bLuma, bChroma);
+    FHC_NOUNROLL for (int i = 0; i < 4; i++) enc_subdiv_cbf(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1) > 2, bLuma, bChroma);
   }
   else if (bLuma) code_qt_cbf(c, cu, relIdx, 0, trDepth, 1, log2n);
 }
@@ -1759,7 +1806,7 @@ FHC_D void enc_coeff_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, i
   if (cu->tridx[relIdx] > trDepth)
   {
     const int q = (cu->nparts >> (2 * trDepth)) >> 2;
-    for (int i = 0; i < 4; i++) enc_coeff_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, comp, (log2n - 1 > 2) ? 1 : (i == 0));
+    FHC_NOUNROLL for (int i = 0; i < 4; i++) enc_coeff_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, comp, (log2n - 1 > 2) ? 1 : (i == 0));
   }
   else if (comp == 0)
   {
@@ -1810,8 +1857,8 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   {
     if (checkTS)
     {
-      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
-      for (int modeId = 0; modeId < 2; modeId++)
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      FHC_NOUNROLL for (int modeId = 0; modeId < 2; modeId++)
       {
         double costTmp;
         set_range(cu->ts[0], relIdx, numParts, modeId);
@@ -1825,29 +1872,29 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
           singleCost = costTmp; singleDist = dTmp; singleCbf = cbfTmp; bestModeId = modeId;
           if (modeId == 0)
           {
-            for (int i = 0; i < 16; i++) { e->tsCoef[0][i] = qtCoefBlk[i]; e->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
-            sb_copy(slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
+            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[0][i] = qtCoefBlk[i]; e->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
+            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
           }
         }
-        if (modeId == 0) sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+        if (modeId == 0) sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       set_range(cu->ts[0], relIdx, numParts, bestModeId);
       if (bestModeId == 0)
       {
         const int ps = plane_stride(s, 0);
-        for (int i = 0; i < 16; i++)
+        FHC_NOUNROLL for (int i = 0; i < 16; i++)
         {
           qtCoefBlk[i] = e->tsCoef[0][i];
           qtRecBlk[(i >> 2) * 64 + (i & 3)] = e->tsRec[0][i];
           if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[0][i];
         }
         set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
-        sb_copy(&e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
+        sb_copy(c, &e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
     }
     else
     {
-      if (checkSplit) sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      if (checkSplit) sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
       set_range(cu->ts[0], relIdx, numParts, 0);
       set_range(cu->tridx, relIdx, numParts, trDepth);
       singleDist = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, 0);
@@ -1862,18 +1909,18 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     const int q = numParts >> 2;
     if (checkFull)
     {
-      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_TEST), &e->go);
-      sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_TEST), &e->go);
+      sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     }
-    else sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
-    for (int i = 0; i < 4; i++)
+    else sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
       recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, checkFirst, &splitDist, &splitCost);
       splitCbf |= (cu->cbf[0][relIdx + i * q] >> (trDepth + 1)) & 1;
     }
     if (splitCbf)
-      for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
-    sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+      FHC_NOUNROLL for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
+    sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
     if (splitCost < singleCost)
     {
@@ -1881,7 +1928,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
       *rdCost = dadd(*rdCost, splitCost);
       return;
     }
-    sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_TEST));
+    sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_TEST));
     set_range(cu->tridx, relIdx, numParts, trDepth);
     set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
     set_range(cu->ts[0], relIdx, numParts, bestModeId);
@@ -1903,15 +1950,15 @@ FHC_D int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n
   const int numParts = cu->nparts >> (2 * trDepth), q = numParts >> 2;
   double splitCost = 0.0;
   uint32_t splitDist = 0, splitCbf = 0;
-  sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
-  for (int i = 0; i < 4; i++)
+  sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+  FHC_NOUNROLL for (int i = 0; i < 4; i++)
   {
     recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, 0, &splitDist, &splitCost);
     splitCbf |= (cu->cbf[0][relIdx + i * q] >> (trDepth + 1)) & 1;
   }
   if (splitCbf)
-    for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
-  sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+    FHC_NOUNROLL for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
+  sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
   splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
   if (splitCost < singleCost) { *dist = splitDist; *cost = splitCost; return 1; }
   return 0;
@@ -1932,7 +1979,7 @@ FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
   else
   {
     const int q = (cu->nparts >> (2 * trDepth)) >> 2;
-    for (int i = 0; i < 4; i++) set_luma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1);
+    FHC_NOUNROLL for (int i = 0; i < 4; i++) set_luma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1);
   }
 }
 
@@ -1951,7 +1998,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
   const int ps = plane_stride(s, 0);
   uint32_t overallDist = 0;
 
-  for (int pu = 0; pu < numPU; pu++)
+  FHC_NOUNROLL for (int pu = 0; pu < numPU; pu++)
   {
     const int partOffset = pu * puParts;
     int numModesForFullRD = (log2pu <= 3) ? 8 : 3;                    // g_aucIntraModeNumFast_UseMPM (TComRom.cpp:545)
@@ -1966,7 +2013,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     {
       Cmd& m = e->cmd;
       const int mpg = imin(35, 4096 >> (2 * log2pu));
-      for (int i = 0; i < 35; i++) s->satd[i] = 0;
+      FHC_NOUNROLL for (int i = 0; i < 35; i++) s->satd[i] = 0;
       m.a[0] = log2pu; m.a[1] = poy * ps + pox; m.a[2] = mpg; m.a[15] = 2 * ((35 + mpg - 1) / mpg);
       FHC_TIC(rp);
       par(c, OP_RMD);
@@ -1980,20 +2027,20 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       const Sbac* srcSb = slot_of(c, depth, CI_CURR_BEST);
       const uint64_t frac0 = srcSb->frac & 32767;
       const uint8_t st = srcSb->c[CTX_IPRED];
-      for (int i = 0; i < numModesForFullRD; i++) candCost[i] = FHC_MAX_COST;
-      for (int mode = 0; mode < 35; mode++)
+      FHC_NOUNROLL for (int i = 0; i < numModesForFullRD; i++) candCost[i] = FHC_MAX_COST;
+      FHC_NOUNROLL for (int mode = 0; mode < 35; mode++)
       {
         int idx = -1;
-        for (int i = 0; i < 3; i++) if (mode == preds[i]) idx = i;
-        const uint64_t frac = frac0 + (uint64_t)s->t.entropyBits[st ^ (idx != -1 ? 1 : 0)] + (uint64_t)32768 * (uint64_t)(idx != -1 ? (idx ? 2 : 1) : 5);
+        FHC_NOUNROLL for (int i = 0; i < 3; i++) if (mode == preds[i]) idx = i;
+        const uint64_t frac = frac0 + (uint64_t)s->t->entropyBits[st ^ (idx != -1 ? 1 : 0)] + (uint64_t)32768 * (uint64_t)(idx != -1 ? (idx ? 2 : 1) : 5);
         const uint32_t modeBits = (uint32_t)(frac >> 15);
         const uint32_t sad = s->satd[mode] >> (s->fp.bitDepth - 8);
         const double cost = dadd((double)sad, dmul((double)modeBits, s->fp.sp.sqrtLambda));
         int shift = 0;                                                          // xUpdateCandList (TEncSearch.cpp:5385)
-        while (shift < numModesForFullRD && cost < candCost[numModesForFullRD - 1 - shift]) shift++;
+        FHC_NOUNROLL while (shift < numModesForFullRD && cost < candCost[numModesForFullRD - 1 - shift]) shift++;
         if (shift != 0)
         {
-          for (int i = 1; i < shift; i++)
+          FHC_NOUNROLL for (int i = 1; i < shift; i++)
           {
             rdModeList[numModesForFullRD - i] = rdModeList[numModesForFullRD - 1 - i];
             candCost[numModesForFullRD - i] = candCost[numModesForFullRD - 1 - i];
@@ -2003,10 +2050,10 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
         }
       }
     }
-    for (int j = 0; j < numCand; j++)
+    FHC_NOUNROLL for (int j = 0; j < numCand; j++)
     {
       int included = 0;
-      for (int i = 0; i < numModesForFullRD; i++) included |= (preds[j] == (int)rdModeList[i]);
+      FHC_NOUNROLL for (int i = 0; i < numModesForFullRD; i++) included |= (preds[j] == (int)rdModeList[i]);
       if (!included) rdModeList[numModesForFullRD++] = (uint32_t)preds[j];
     }
     FHC_TOC2(c, rm, PF_RMD_MASTER);
@@ -2020,29 +2067,29 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       TaskDesc& td = s->task;
       td.kind = TASK_LUMA_PU; td.numTasks = numModesForFullRD; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
       td.partOffset = partOffset; td.log2pu = log2pu; td.initTrDepth = initTrDepth;
-      for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
-      { FHC_TIC(tl); par(c, OP_TASKS); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
+      FHC_NOUNROLL for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
+      { FHC_TIC(tl); dispatch_tasks(c); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
       {
         // xSetIntraResultLumaQT + the saved trIdx/cbf/tskip arrays of the winner
-        const int be = best_engine(s), n = 1 << log2pu;
+        const int be = best_engine(c), n = 1 << log2pu;
         const EngineGlobal* wg = &g->eng[be];
-        bestPUCost = s->eng[be].resCost; bestPUDist = s->eng[be].resDist; bestPUMode = rdModeList[s->eng[be].resTask];
+        bestPUCost = wg->eng.resCost; bestPUDist = wg->eng.resDist; bestPUMode = rdModeList[wg->eng.resTask];
         par_copy16(c, cuCoef + partOffset * 16, wg->bestCoef[0], n * n);
         par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, wg->bestReco[0], n, n, n);
         copy_bytes(s->qtTrIdx, wg->bestTrIdx, puParts);
-        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wg->bestCbf[j], puParts); copy_bytes(s->qtTs[j], wg->bestTs[j], puParts); }
+        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wg->bestCbf[j], puParts); copy_bytes(s->qtTs[j], wg->bestTs[j], puParts); }
       }
       // second pass: a 4x4 PU cannot split, re-coding the best mode reproduces the same cost (never strictly smaller)
       firstSerial = (log2pu == 2) ? numModesForFullRD + 1 : numModesForFullRD;
     }
-    for (int i = firstSerial; i < numModesForFullRD + 1; i++)
+    FHC_NOUNROLL for (int i = firstSerial; i < numModesForFullRD + 1; i++)
     {
       const int second = (i == numModesForFullRD);
       const uint32_t orgMode = second ? bestPUMode : rdModeList[i];
       uint32_t puDist = 0;
       double puCost = 0.0;
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
-      sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
+      sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
       if (second && log2pu >= 3 && log2pu <= 5)
       {
         FHC_TIC(sp);
@@ -2061,12 +2108,12 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
         bestPUMode = orgMode; bestPUDist = puDist; bestPUCost = puCost;
         set_luma_result(c, cu, cuCoef, cuReco, partOffset, log2pu, initTrDepth);
         copy_bytes(s->qtTrIdx, cu->tridx + partOffset, puParts);
-        for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], cu->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], cu->ts[j] + partOffset, puParts); }
+        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], cu->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], cu->ts[j] + partOffset, puParts); }
       }
     }
     overallDist += bestPUDist;
     copy_bytes(cu->tridx + partOffset, s->qtTrIdx, puParts);
-    for (int j = 0; j < 3; j++) { copy_bytes(cu->cbf[j] + partOffset, s->qtCbf[j], puParts); copy_bytes(cu->ts[j] + partOffset, s->qtTs[j], puParts); }
+    FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(cu->cbf[j] + partOffset, s->qtCbf[j], puParts); copy_bytes(cu->ts[j] + partOffset, s->qtTs[j], puParts); }
     if (pu != numPU - 1)
       par_copy2d(c, g->rec[0] + poy * ps + pox, ps, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, puSize, puSize);
     set_range(cu->ldir, partOffset, puParts, (int)bestPUMode);
@@ -2074,13 +2121,13 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
   if (numPU > 1)
   {
     uint32_t cY = 0, cU = 0, cV = 0;
-    for (int i = 0; i < 4; i++)
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
       cY |= (cu->cbf[0][i * puParts] >> 1) & 1; cU |= (cu->cbf[1][i * puParts] >> 1) & 1; cV |= (cu->cbf[2][i * puParts] >> 1) & 1;
     }
-    for (int i = 0; i < 4 * puParts; i++) { cu->cbf[0][i] |= (uint8_t)cY; cu->cbf[1][i] |= (uint8_t)cU; cu->cbf[2][i] |= (uint8_t)cV; }
+    FHC_NOUNROLL for (int i = 0; i < 4 * puParts; i++) { cu->cbf[0][i] |= (uint8_t)cY; cu->cbf[1][i] |= (uint8_t)cU; cu->cbf[2][i] |= (uint8_t)cV; }
   }
-  sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
+  sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
   cu->dist = overallDist;
 }
 
@@ -2105,10 +2152,10 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
     if (checkTS)
     {
       int nb = 0;
-      for (int k = relIdx; k < relIdx + 4; k++) nb += cu->ts[0][k];
+      FHC_NOUNROLL for (int k = relIdx; k < relIdx + 4; k++) nb += cu->ts[0][k];
       checkTS = nb > 0;
     }
-    for (int cc = 1; cc < 3; cc++)
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
       double singleCost = FHC_MAX_COST, costTmp = 0;
       uint32_t singleDist = 0, singleCbf = 0;
@@ -2116,8 +2163,8 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
       const int total = checkTS ? 2 : 1;
       int16_t* qtCoefBlk = e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4;
       int16_t* qtRecBlk = e->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1);
-      sb_copy(slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
-      for (int tsId = 0; tsId < total; tsId++)
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      FHC_NOUNROLL for (int tsId = 0; tsId < total; tsId++)
       {
         const int isOne = total == 1;
         set_range(cu->ts[cc], ridx, nparts, tsId);
@@ -2137,24 +2184,24 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
           singleCost = costTmp; singleDist = dTmp; bestTS = tsId; bestMode = currMode; singleCbf = cbfTmp;
           if (!isOne && !isLast)
           {
-            for (int i = 0; i < 16; i++) { e->tsCoef[cc][i] = qtCoefBlk[i]; e->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
-            sb_copy(slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
+            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[cc][i] = qtCoefBlk[i]; e->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
+            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
           }
         }
-        if (!isOne && !isLast) sb_copy(&e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+        if (!isOne && !isLast) sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       if (bestMode < total)
       {
         const int ps = plane_stride(s, cc);
         int16_t* picBlk = g->rec[cc] + ((cu->y + rel_y(s, ridx)) >> 1) * ps + ((cu->x + rel_x(s, ridx)) >> 1);
-        for (int i = 0; i < 16; i++)
+        FHC_NOUNROLL for (int i = 0; i < 16; i++)
         {
           qtCoefBlk[i] = e->tsCoef[cc][i];
           qtRecBlk[(i >> 2) * 32 + (i & 3)] = e->tsRec[cc][i];
           if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[cc][i];
         }
         set_range(cu->cbf[cc], ridx, nparts, (int)(singleCbf << trDepth));
-        sb_copy(&e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
+        sb_copy(c, &e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
       set_range(cu->ts[cc], ridx, nparts, bestTS);
       *dist += singleDist;
@@ -2164,15 +2211,15 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
   {
     uint32_t splitCbf[3] = { 0, 0, 0 };
     const int q = numPartsLuma >> 2;
-    for (int i = 0; i < 4; i++)
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
       const int childProc = (log2n - 1 > 2) ? 1 : (i == 0);
       recur_chroma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, procChroma && childProc, dist);
-      for (int cc = 1; cc < 3; cc++) splitCbf[cc] |= (cu->cbf[cc][relIdx + i * q] >> (trDepth + 1)) & 1;
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) splitCbf[cc] |= (cu->cbf[cc][relIdx + i * q] >> (trDepth + 1)) & 1;
     }
-    for (int cc = 1; cc < 3; cc++)
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
       if (splitCbf[cc])
-        for (int i = 0; i < numPartsLuma; i++) cu->cbf[cc][relIdx + i] |= (uint8_t)(1 << trDepth);
+        FHC_NOUNROLL for (int i = 0; i < numPartsLuma; i++) cu->cbf[cc][relIdx + i] |= (uint8_t)(1 << trDepth);
   }
 }
 FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco, int relIdx, int log2n, int trDepth, int procChroma)
@@ -2184,7 +2231,7 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
   {
     const int stepped = (log2n == 2), cl = stepped ? 2 : log2n - 1, n = 1 << cl, ridx = stepped ? (relIdx & ~3) : relIdx;
     const int cw = cu->width >> 1;
-    for (int cc = 1; cc < 3; cc++)
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
       par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, c.e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4, n * n);
       par_copy2d(c, cuReco + comp_off(cc) + (rel_y(s, ridx) >> 1) * cw + (rel_x(s, ridx) >> 1), cw,
@@ -2194,7 +2241,7 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
   else
   {
     const int q = (cu->nparts >> (2 * trDepth)) >> 2;
-    for (int i = 0; i < 4; i++) set_chroma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1 > 2) ? 1 : (i == 0));
+    FHC_NOUNROLL for (int i = 0; i < 4; i++) set_chroma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1 > 2) ? 1 : (i == 0));
   }
 }
 FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
@@ -2206,19 +2253,19 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
   int modeList[5] = { PLANAR_IDX, VER_IDX, HOR_IDX, DC_IDX, DM_CHROMA_IDX };
   uint32_t bestMode = 0, bestDist = 0;
   double bestCost = FHC_MAX_COST;
-  for (int i = 0; i < 4; i++) if (modeList[i] == cu->ldir[0]) { modeList[i] = 34; break; }      // getAllowedChromaDir
+  FHC_NOUNROLL for (int i = 0; i < 4; i++) if (modeList[i] == cu->ldir[0]) { modeList[i] = 34; break; }      // getAllowedChromaDir
   if (log2cu == 3 && e->kind == ENG_MASTER)
   {
     // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> thread engines
     TaskDesc& td = s->task;
     td.kind = TASK_CHROMA_CU; td.numTasks = 5; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
     td.partOffset = 0; td.log2pu = log2cu; td.initTrDepth = 0;
-    for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
-    { FHC_TIC(tc); par(c, OP_TASKS); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
-    const int be = best_engine(s);
+    FHC_NOUNROLL for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
+    { FHC_TIC(tc); dispatch_tasks(c); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
+    const int be = best_engine(c);
     const EngineGlobal* wg = &g->eng[be];
-    bestCost = s->eng[be].resCost; bestDist = s->eng[be].resDist; bestMode = (uint32_t)modeList[s->eng[be].resTask];
-    for (int cc = 1; cc < 3; cc++)
+    bestCost = wg->eng.resCost; bestDist = wg->eng.resDist; bestMode = (uint32_t)modeList[wg->eng.resTask];
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
       par_copy16(c, cuCoef + comp_off(cc), wg->bestCoef[cc], 16);
       par_copy2d(c, cuReco + comp_off(cc), 4, wg->bestReco[cc], 4, 4, 4);
@@ -2226,27 +2273,27 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
     }
   }
   else
-  for (int mi = 0; mi < 5; mi++)
+  FHC_NOUNROLL for (int mi = 0; mi < 5; mi++)
   {
     uint32_t dist = 0;
     FHC_TIC(cb);
-    sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
+    sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, nparts, modeList[mi]);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
-    sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
+    sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
     if (cost < bestCost)
     {
       bestCost = cost; bestDist = dist; bestMode = (uint32_t)modeList[mi];
       set_chroma_result(c, cu, cuCoef, cuReco, 0, log2cu, 0, 1);
-      for (int cc = 1; cc < 3; cc++) { copy_bytes(s->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(s->qtTs[cc], cu->ts[cc], nparts); }
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(s->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(s->qtTs[cc], cu->ts[cc], nparts); }
     }
     FHC_TOC3(c, cb, PF2_CHROMA_BIG);
   }
-  for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
+  FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
   set_range(cu->cdir, 0, nparts, (int)bestMode);
   cu->dist += bestDist;
-  sb_copy(&e->go, slot_of(c, depth, CI_CURR_BEST));
+  sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -2256,20 +2303,20 @@ FHC_D void encode_transform(const Ctx& c, const CUMeta* cu, const int16_t* coef,
 {
   const int subdiv = cu->tridx[relIdx] > trDepth;
   int cbf[3];
-  for (int cc = 0; cc < 3; cc++) cbf[cc] = (cu->cbf[cc][relIdx] >> trDepth) & 1;
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) cbf[cc] = (cu->cbf[cc][relIdx] >> trDepth) & 1;
   if (cu->part[relIdx] == SIZE_NxN && trDepth == 0) { }
   else if (log2n > 5) { }
   else if (log2n == 2) { }
   else if (log2n == min_tu_log2_in_cu(cu)) { }
   else enc_bin(c.e, CTX_SUBDIV + (5 - log2n), subdiv);
-  for (int cc = 1; cc < 3; cc++)
+  FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     if (trDepth == 0 || chromaCodeAll)
       if (trDepth == 0 || ((cu->cbf[cc][relIdx] >> (trDepth - 1)) & 1))
         code_qt_cbf(c, cu, relIdx, cc, trDepth, subdiv == 0, log2n - 1);
   if (subdiv)
   {
     const int q = (cu->nparts >> (2 * trDepth)) >> 2;
-    for (int i = 0; i < 4; i++)
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
       encode_transform(c, cu, coef, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1) > 2, (log2n - 1 > 2) ? 1 : (i == 3));
   }
   else
@@ -2279,7 +2326,7 @@ FHC_D void encode_transform(const Ctx& c, const CUMeta* cu, const int16_t* coef,
     if (procChroma)
     {
       const int cl = log2n == 2 ? 2 : log2n - 1, ridx = log2n == 2 ? (relIdx & ~3) : relIdx;
-      for (int cc = 1; cc < 3; cc++)
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
         if (cbf[cc]) code_coeff_nxn(c, cu, ridx, coef + comp_off(cc) + ridx * 4, cl, cc);
     }
   }
@@ -2301,7 +2348,7 @@ FHC_D void cu_init_est(const Ctx& c, CUMeta* cu)                                
   cu->cost = FHC_MAX_COST; cu->dist = 0; cu->bits = 0; cu->bins = 0;
   set_range(cu->dep, 0, n, cu->depth); set_range(cu->tridx, 0, n, 0); set_range(cu->part, 0, n, SIZE_NONE);
   set_range(cu->pred, 0, n, MODE_NONE); set_range(cu->ldir, 0, n, DC_IDX); set_range(cu->cdir, 0, n, 0);
-  for (int cc = 0; cc < 3; cc++) { set_range(cu->cbf[cc], 0, n, 0); set_range(cu->ts[cc], 0, n, 0); }
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { set_range(cu->cbf[cc], 0, n, 0); set_range(cu->ts[cc], 0, n, 0); }
   // coefficient buffers need no clearing here: every coded TU (re)writes its block, and blocks of a CU
   // hypothesis are only read through cbf != 0 (coding) or copied as a whole after being written.
   (void)c;
@@ -2320,7 +2367,7 @@ FHC_D void cu_copy_part_from(const Ctx& c, CUMeta* dst, const CUMeta* src, int p
   dst->cost = dadd(dst->cost, src->cost); dst->dist += src->dist; dst->bits += src->bits; dst->bins += src->bins;
   copy_bytes(dst->part + off, src->part, n); copy_bytes(dst->pred + off, src->pred, n); copy_bytes(dst->ldir + off, src->ldir, n);
   copy_bytes(dst->cdir + off, src->cdir, n); copy_bytes(dst->tridx + off, src->tridx, n); copy_bytes(dst->dep + off, src->dep, n);
-  for (int cc = 0; cc < 3; cc++) { copy_bytes(dst->cbf[cc] + off, src->cbf[cc], n); copy_bytes(dst->ts[cc] + off, src->ts[cc], n); }
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { copy_bytes(dst->cbf[cc] + off, src->cbf[cc], n); copy_bytes(dst->ts[cc] + off, src->ts[cc], n); }
   if (withCoef)
   {
     int16_t* dc = c.g->cuCoef[dst->depth][cu_buf_index(c.s, dst)];
@@ -2346,7 +2393,7 @@ FHC_D void copy_reco_to_pic(const Ctx& c, const CUMeta* cu)                     
   const FrameGlobal* g = c.g;
   const Shared* s = c.s;
   const int16_t* y = g->cuReco[cu->depth][cu_buf_index(c.s, cu)];
-  for (int cc = 0; cc < 3; cc++)
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++)
   {
     const int sh = cc ? 1 : 0, w = cu->width >> sh, px = cu->x >> sh, py = cu->y >> sh;
     const int cw = imin(w, (s->fp.width >> sh) - px), ch = imin(w, (s->fp.height >> sh) - py);
@@ -2357,7 +2404,7 @@ FHC_D void copy_reco_to_parent(const Ctx& c, const CUMeta* child, const CUMeta* 
 {
   const int16_t* sy = c.g->cuReco[child->depth][cu_buf_index(c.s, child)];
   int16_t* dy = c.g->cuReco[parent->depth][cu_buf_index(c.s, parent)];
-  for (int cc = 0; cc < 3; cc++)
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++)
   {
     const int w = child->width >> (cc ? 1 : 0), pw = parent->width >> (cc ? 1 : 0);
     par_copy2d(c, dy + comp_off(cc) + (partIdx >> 1) * w * pw + (partIdx & 1) * w, pw, sy + comp_off(cc), w, w, w);
@@ -2370,7 +2417,7 @@ FHC_DH void check_best_mode(const Ctx& c, int depth)                            
   if (temp_cu(s, depth)->cost < best_cu(s, depth)->cost)
   {
     s->bestIdx[depth] = (uint8_t)(1 - s->bestIdx[depth]);
-    sb_copy(slot_of(c, depth, CI_NEXT_BEST), slot_of(c, depth, CI_TEMP_BEST));
+    sb_copy(c, slot_of(c, depth, CI_NEXT_BEST), slot_of(c, depth, CI_TEMP_BEST));
   }
 }
 FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)                            // xCheckRDCostIntra (TEncCu.cpp:1528)
@@ -2390,7 +2437,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   { FHC_TIC(ec); est_intra_chroma(c, cu, cuCoef, cuReco); FHC_TOC2(c, ec, PF_CHROMA); }
   reset_bits(e);
   encode_cu_syntax(c, cu, cuCoef);
-  sb_copy(slot_of(c, depth, CI_TEMP_BEST), &e->go);
+  sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), &e->go);
   cu->bits = num_bits(e);
   cu->bins = e->bins;
   cu->cost = rd_cost(c, cu->bits, cu->dist);
@@ -2416,27 +2463,27 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       cu_init_est(c, temp_cu(s, depth));
     }
     CUMeta* b = best_cu(s, depth);
-    sb_copy(&e->go, slot_of(c, depth, CI_NEXT_BEST));
+    sb_copy(c, &e->go, slot_of(c, depth, CI_NEXT_BEST));
     reset_bits(e);
     code_split_flag(c, b, 0, depth);
     b->bits += num_bits(e);
     b->bins += e->bins;
     b->cost = rd_cost(c, b->bits, b->dist);
-    sb_copy(slot_of(c, depth, CI_NEXT_BEST), &e->go);
+    sb_copy(c, slot_of(c, depth, CI_NEXT_BEST), &e->go);
   }
   if (depth < 3)
   {
     const int nd = depth + 1;
     CUMeta* t = temp_cu(s, depth);
     cu_init_est(c, t);
-    for (int i = 0; i < 4; i++)
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
       cu_position(c, &s->cu[nd][0], t, i, nd);
       cu_position(c, &s->cu[nd][1], t, i, nd);
       if (s->cu[nd][0].x < s->fp.width && s->cu[nd][0].y < s->fp.height)
       {
-        if (i == 0) sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, depth, CI_CURR_BEST));
-        else sb_copy(slot_of(c, nd, CI_CURR_BEST), slot_of(c, nd, CI_NEXT_BEST));
+        if (i == 0) sb_copy(c, slot_of(c, nd, CI_CURR_BEST), slot_of(c, depth, CI_CURR_BEST));
+        else sb_copy(c, slot_of(c, nd, CI_CURR_BEST), slot_of(c, nd, CI_NEXT_BEST));
         compress_cu(c, nd);
         cu_copy_part_from(c, t, best_cu(s, nd), i, 1);
         copy_reco_to_parent(c, best_cu(s, nd), t, i);
@@ -2453,7 +2500,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
         }
       }
     }
-    sb_copy(&e->go, slot_of(c, nd, CI_NEXT_BEST));
+    sb_copy(c, &e->go, slot_of(c, nd, CI_NEXT_BEST));
     if (!boundary)
     {
       reset_bits(e);
@@ -2462,7 +2509,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       t->bins += e->bins;
     }
     t->cost = rd_cost(c, t->bits, t->dist);
-    sb_copy(slot_of(c, depth, CI_TEMP_BEST), &e->go);
+    sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), &e->go);
     check_best_mode(c, depth);
   }
   cu_copy_to_pic(c, best_cu(s, depth), 1);
@@ -2476,7 +2523,7 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
   Engine* e = c.e; (void)e;
   const FrameGlobal* g = c.g;
   const fhc_ctu_result* o = &g->out[s->ctuAddr];
-  const int r = s->t.z2r[zidx];
+  const int r = s->t->z2r[zidx];
   const int x = s->ctuPelX + (r & 15) * 4, y = s->ctuPelY + (r >> 4) * 4, w = 64 >> depth;
   const int nparts = 256 >> (2 * depth);
   int boundary = 0;
@@ -2484,15 +2531,15 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
   copy_bytes(view->dep, o->depth + zidx, nparts); copy_bytes(view->part, o->partSize + zidx, nparts);
   copy_bytes(view->pred, o->predMode + zidx, nparts); copy_bytes(view->ldir, o->lumaDir + zidx, nparts);
   copy_bytes(view->cdir, o->chromaDir + zidx, nparts); copy_bytes(view->tridx, o->trIdx + zidx, nparts);
-  for (int cc = 0; cc < 3; cc++) { copy_bytes(view->cbf[cc], o->cbf[cc] + zidx, nparts); copy_bytes(view->ts[cc], o->transformSkip[cc] + zidx, nparts); }
+  FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { copy_bytes(view->cbf[cc], o->cbf[cc] + zidx, nparts); copy_bytes(view->ts[cc], o->transformSkip[cc] + zidx, nparts); }
   if (x + w - 1 < s->fp.width && y + w - 1 < s->fp.height) code_split_flag(c, view, 0, depth);
   else boundary = 1;
   if ((depth < o->depth[zidx] && depth < 3) || boundary)
   {
     const int q = nparts >> 2;
-    for (int i = 0; i < 4; i++)
+    FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
-      const int cz = zidx + i * q, cr = s->t.z2r[cz];
+      const int cz = zidx + i * q, cr = s->t->z2r[cz];
       if (s->ctuPelX + (cr & 15) * 4 < s->fp.width && s->ctuPelY + (cr >> 4) * 4 < s->fp.height) encode_ctu_rec(c, view, cz, depth + 1);
     }
     return;
@@ -2510,77 +2557,78 @@ FHC_D void encode_ctu_rec(const Ctx& c, CUMeta* view, int zidx, int depth)
 // ----------------------------------------------------------------------------------------------
 // engines and candidate tasks
 // ----------------------------------------------------------------------------------------------
-FHC_D void init_engines(FrameGlobal* g, Shared* s)
+// executed by the group's leader: binds the picture's engines to their scratch
+FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
 {
   Engine* m = &s->master;
-  s->fp.width = g->width; s->fp.height = g->height; s->fp.bitDepth = g->bitDepth; s->fp.sampleBytes = g->sampleBytes;
-  s->fp.wc = g->wc; s->fp.hc = g->hc; s->fp.sp = g->sp;
-  m->kind = ENG_MASTER; m->t = &s->t; m->slots = &s->slot[0][0];
-  m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->resi = s->resi; m->tmp = s->tmp; m->tcoef = s->tcoef; m->lvlD = s->lvlD;
-  m->cost0 = s->rdCost0; m->costCoeff = s->rdCostCoeff; m->costSig = s->rdCostSig;
-  m->rateIncUp = s->rdRateIncUp; m->rateIncDown = s->rdRateIncDown; m->sigRateDelta = s->rdSigRateDelta; m->deltaU = s->rdDeltaU;
+  s->t = tables;
+  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0];
+  m->refU = s->refU; m->refF = s->refF; m->flags = s->flags;
+  bind_coef_scratch(m, &s->cs);
   m->predYuv = g->predYuv; m->qtRec = g->qtRec; m->qtCoef = g->qtCoef; m->writePic = 1;
   m->costCGSig = s->costCGSig; m->cgFlag = s->cgFlag; m->cgFlagCode = s->cgFlagCode; m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta;
   {
     uint8_t* st = s->cuStore;
-    for (int d = 0; d < 4; d++)
-      for (int b = 0; b < 2; b++) { cu_bind(&s->cu[d][b], st, 256 >> (2 * d)); st += 12 * (256 >> (2 * d)); }
+    FHC_NOUNROLL for (int d = 0; d < 4; d++)
+      FHC_NOUNROLL for (int b = 0; b < 2; b++) { cu_bind(&s->cu[d][b], st, 256 >> (2 * d)); st += 12 * (256 >> (2 * d)); }
   }
-  for (int i = 0; i < FHC_NENG; i++)
+  FHC_NOUNROLL for (int i = 0; i < FHC_NENG; i++)
   {
-    Engine* e = &s->eng[i];
-    EngineShared* x = &s->engSh[i];
-    e->kind = ENG_THREAD; e->t = &s->t; e->slots = x->slots;
-    e->refU = x->refU; e->refF = x->refF; e->flags = x->flags; e->resi = x->resi; e->tmp = x->tmp; e->tcoef = x->tcoef; e->lvlD = x->lvlD;
-    e->cost0 = x->cost0; e->costCoeff = x->costCoeff; e->costSig = x->costSig;
-    e->rateIncUp = x->rateIncUp; e->rateIncDown = x->rateIncDown; e->sigRateDelta = x->sigRateDelta; e->deltaU = x->deltaU;
-    e->predYuv = g->eng[i].predYuv; e->qtRec = g->eng[i].qtRec; e->qtCoef = g->eng[i].qtCoef; e->writePic = 0;
+    EngineGlobal* x = &g->eng[i];
+    Engine* e = &x->eng;
+    e->kind = ENG_LANE; e->t = tables; e->slots = x->slots;
+    e->refU = x->refU; e->refF = x->refF; e->flags = x->flags;
+    bind_coef_scratch(e, &x->cs);
+    e->predYuv = x->predYuv; e->qtRec = x->qtRec; e->qtCoef = x->qtCoef; e->writePic = 0;
     e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->sigC0 = x->sigC0; e->sigC1 = x->sigC1; e->sigDelta = x->sigDelta;
-    cu_bind(&g->eng[i].cu, g->eng[i].cuStore, 4);
+    cu_bind(&x->cu, x->cuStore, 4);
   }
 }
 
-// One candidate evaluated by thread engine `engIdx` (task t of s->task).  Everything it writes is private
-// (engine scratch + g->eng[engIdx]); it reads the picture planes, the picture-level CTU records, the CU under test
-// and the CU's CI_CURR_BEST contexts, none of which change while tasks run.
-FHC_D void run_task(FrameGlobal* g, Shared* s, int engIdx, int t)
+// Candidate t of s->task evaluated by ONE lane on lane engine engIdx (an engine runs its tasks in increasing order and
+// keeps the best: strict <).  Everything it writes is private (g->eng[engIdx]); it reads the picture planes, the
+// picture-level CTU records, the CU under test and the CU's CI_CURR_BEST contexts, none of which change while a
+// dispatch runs.
+FHC_D void run_task(const Ctx& mc, int engIdx, int t)
 {
+  FrameGlobal* g = mc.g;
+  Shared* s = mc.s;
+  EngineGlobal* eg = &g->eng[engIdx];
+  const int firstOfDispatch = t < FHC_NENG;
   Ctx c;
-  c.g = g; c.s = s; c.e = &s->eng[engIdx];
+  c.g = g; c.s = s; c.e = &eg->eng; c.lane = 0; c.nl = 1; c.mask = 0;
   Engine* e = c.e;
   const TaskDesc& td = s->task;
   const CUMeta* src = &s->cu[td.depth][td.bufIdx];
-  CUMeta* cu = &g->eng[engIdx].cu;
+  CUMeta* cu = &eg->cu;
   const int np = src->nparts;
   cu->zidx = src->zidx; cu->x = src->x; cu->y = src->y; cu->depth = src->depth; cu->nparts = np; cu->width = src->width;
-  for (int i = 0; i < np; i++)
+  FHC_NOUNROLL for (int i = 0; i < np; i++)
   {
     cu->dep[i] = src->dep[i]; cu->part[i] = src->part[i]; cu->pred[i] = src->pred[i]; cu->ldir[i] = src->ldir[i];
     cu->cdir[i] = src->cdir[i]; cu->tridx[i] = src->tridx[i];
-    for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
+    FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
   }
   const int mode = td.mode[t];
-  EngineGlobal* eg = &g->eng[engIdx];
-  const int firstOfDispatch = t < FHC_NENG;
   if (td.kind == TASK_LUMA_PU)
   {
     // one iteration of the candidate loop of estIntraPredLumaQT (TEncSearch.cpp:2349-2418), bCheckFirst = true
     uint32_t dist = 0;
     double cost = 0.0;
     const int puParts = np >> (2 * td.initTrDepth);
+    const int layer = 5 - td.log2pu, n = 1 << td.log2pu;
     set_range(cu->ldir, td.partOffset, puParts, mode);
-    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
     recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
     if (firstOfDispatch || cost < e->resCost)
     {
-      const int layer = 5 - td.log2pu, n = 1 << td.log2pu;
       e->resCost = cost; e->resDist = dist; e->resTask = t;
       par_copy16(c, eg->bestCoef[0], e->qtCoef[layer] + td.partOffset * 16, n * n);
       par_copy2d(c, eg->bestReco[0], n, e->qtRec[layer] + rel_y(s, td.partOffset) * 64 + rel_x(s, td.partOffset), 64, n, n);
-      for (int i = 0; i < puParts; i++)
+      FHC_NOUNROLL for (int i = 0; i < puParts; i++)
       {
         eg->bestTrIdx[i] = cu->tridx[td.partOffset + i];
-        for (int cc = 0; cc < 3; cc++) { eg->bestCbf[cc][i] = cu->cbf[cc][td.partOffset + i]; eg->bestTs[cc][i] = cu->ts[cc][td.partOffset + i]; }
+        FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { eg->bestCbf[cc][i] = cu->cbf[cc][td.partOffset + i]; eg->bestTs[cc][i] = cu->ts[cc][td.partOffset + i]; }
       }
     }
   }
@@ -2589,51 +2637,75 @@ FHC_D void run_task(FrameGlobal* g, Shared* s, int engIdx, int t)
     // one iteration of the chroma mode loop of estIntraPredChromaQT (TEncSearch.cpp:2612-2648)
     uint32_t dist = 0;
     const int log2cu = ilog2(cu->width);
-    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
     set_range(cu->cdir, 0, np, mode);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
-    sb_copy(&e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
+    const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
     if (firstOfDispatch || cost < e->resCost)
     {
-      const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
       e->resCost = cost; e->resDist = dist; e->resTask = t;
-      for (int cc = 1; cc < 3; cc++)
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
       {
         par_copy16(c, eg->bestCoef[cc], e->qtCoef[layer] + comp_off(cc), 16);
         par_copy2d(c, eg->bestReco[cc], 4, e->qtRec[layer] + comp_off(cc), 32, 4, 4);
-        for (int i = 0; i < np; i++) { eg->bestCbf[cc][i] = cu->cbf[cc][i]; eg->bestTs[cc][i] = cu->ts[cc][i]; }
+        FHC_NOUNROLL for (int i = 0; i < np; i++) { eg->bestCbf[cc][i] = cu->cbf[cc][i]; eg->bestTs[cc][i] = cu->ts[cc][i]; }
       }
     }
   }
 }
-#ifndef FHC_DEVICE_BUILD
-FHC_D void run_tasks_emu(const Ctx& c)
+
+// LANE section: lane l of the group runs tasks l, l + FHC_NENG, ... of s->task on lane engine l
+FHC_D void run_tasks(const Ctx& c)
 {
-  for (int t = 0; t < c.s->task.numTasks; t++) run_task(c.g, c.s, t % FHC_NENG, t);
+  const int n = c.s->task.numTasks;
+  if (c.lane < FHC_NENG)
+    FHC_NOUNROLL for (int t = c.lane; t < n; t += FHC_NENG) run_task(c, c.lane, t);
 }
+// called by the leader: publishes the dispatch, takes part in it, and waits for the group before comparing results
+FHC_D void dispatch_tasks(const Ctx& c)
+{
+#ifdef FHC_DEVICE_BUILD
+  if (c.nl > 1) { c.e->cmd.op = OP_TASKS; __syncwarp(c.mask); }
+  run_tasks(c);
+  group_sync(c);
+#else
+  FHC_NOUNROLL for (int t = 0; t < c.s->task.numTasks; t++) run_task(c, t % FHC_NENG, t);
 #endif
+}
 
 // ----------------------------------------------------------------------------------------------
-// picture loop (TEncSlice::compressSlice, TEncSlice.cpp:698-983), executed by the master thread
+// picture loop (TEncSlice::compressSlice, TEncSlice.cpp:698-983), executed by the group leader
 // ----------------------------------------------------------------------------------------------
-FHC_D void master_compress_picture(const Ctx& c)
+FHC_D void load_picture(const Ctx& c, const PicDesc* p)
+{
+  FrameGlobal* g = c.g;
+  Shared* s = c.s;
+  FHC_NOUNROLL for (int i = 0; i < 3; i++) { g->org[i] = p->org[i]; g->rec[i] = p->rec[i]; }
+  g->out = p->out; g->sp = p->sp;
+  g->width = p->width; g->height = p->height; g->bitDepth = p->bitDepth; g->sampleBytes = p->sampleBytes; g->wc = p->wc; g->hc = p->hc;
+  FHC_NOUNROLL for (int i = 0; i < 16; i++) { g->prof[i] = 0; g->profN[i] = 0; g->prof2[i] = 0; g->prof2N[i] = 0; }
+  s->fp.width = p->width; s->fp.height = p->height; s->fp.bitDepth = p->bitDepth; s->fp.sampleBytes = p->sampleBytes;
+  s->fp.wc = p->wc; s->fp.hc = p->hc; s->fp.sp = p->sp;
+}
+
+FHC_D void compress_picture(const Ctx& c)
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
   FrameGlobal* g = c.g;
   FHC_TIC(tot);
-  for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
-  // engines were initialised by the caller (init_engines) before the workers started
-  sbac_reset(s->t, &s->slot[0][CI_CURR_BEST], s->fp.sp.sliceQp);
+  FHC_NOUNROLL for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
+  sbac_reset(*s->t, &s->slot[0][CI_CURR_BEST], s->fp.sp.sliceQp);
   const int numCtus = s->fp.wc * s->fp.hc;
-  for (int addr = 0; addr < numCtus; addr++)
+  FHC_NOUNROLL for (int addr = 0; addr < numCtus; addr++)
   {
     fhc_ctu_result* o = &g->out[addr];
     s->ctuAddr = addr; s->ctuX = addr % s->fp.wc; s->ctuY = addr / s->fp.wc;
     s->ctuPelX = s->ctuX * 64; s->ctuPelY = s->ctuY * 64;
     // initCtu (TComDataCU.cpp:422): the record doubles as the picture-level CTU
-    for (int d = 0; d < 2; d++)
+    FHC_NOUNROLL for (int d = 0; d < 2; d++)
     {
       CUMeta* cu = &s->cu[0][d];
       cu->zidx = 0; cu->x = s->ctuPelX; cu->y = s->ctuPelY; cu->depth = 0; cu->nparts = 256; cu->width = 64;
@@ -2650,16 +2722,16 @@ FHC_D void master_compress_picture(const Ctx& c)
       par(c, OP_CU_TO_OUT);
       cu_init_est(c, cu);
     }
-    sb_copy(&e->go, slot_of(c, 0, CI_CURR_BEST));
+    sb_copy(c, &e->go, slot_of(c, 0, CI_CURR_BEST));
     compress_cu(c, 0);
-    sb_copy(&e->go, slot_of(c, 0, CI_CURR_BEST));
+    sb_copy(c, &e->go, slot_of(c, 0, CI_CURR_BEST));
     reset_bits(e);
     {
       FHC_TIC(en);
       encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
       FHC_TOC2(c, en, PF_ENCODE);
     }
-    sb_copy(slot_of(c, 0, CI_CURR_BEST), &e->go);
+    sb_copy(c, slot_of(c, 0, CI_CURR_BEST), &e->go);
     par(c, OP_CTU_RECO_OUT);
   }
   FHC_TOC2(c, tot, PF_TOTAL);

@@ -1,11 +1,9 @@
 import sys, time; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import numpy as np
 import fasthevc_b200 as fh
-import __graft_entry__ as ge
-ge.smoke()
 from fasthevc_b200.synth import synth_frames
 def run(w,h,n,qp):
-    Y,U,V=synth_frames(w,h,min(n,4))
+    Y,U,V=synth_frames(w,h,min(n,int(os.environ.get('FHC_DISTINCT','4'))))
     reps=(n+Y.shape[0]-1)//Y.shape[0]
     Y=np.concatenate([Y]*reps)[:n]; U=np.concatenate([U]*reps)[:n]; V=np.concatenate([V]*reps)[:n]
     enc=fh.Encoder(w,h,8,max_frames=n)
