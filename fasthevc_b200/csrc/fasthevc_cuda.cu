@@ -46,32 +46,23 @@ fhc_compress_pictures_kernel(PicDesc* pics, int numPics, int* queue, FrameGlobal
   c.mask = (FHC_GROUP == 32) ? FHC_FULL_MASK : (((1u << FHC_GROUP) - 1u) << (grp * FHC_GROUP));
   if (c.lane == 0) init_engines(g, s, t);
   group_sync(c);
-  // Rendezvous of the warp's groups between pictures.  It must not be a full-mask __syncwarp: groups that are still
-  // encoding execute __syncwarp(group mask), and waiting on a different mask that names them is undefined.  The last
-  // group to arrive pulls the next FHC_PICS_PER_WARP pictures and opens the next round; the others spin on the round.
-  volatile int* rv = reinterpret_cast<volatile int*>(rvz) + warp * 4;   // [0] arrivals, [1] round, [2] first picture of the round
-  for (int round = 1;; round++)
+  // Rounds: the block pulls FHC_PICS_PER_BLOCK pictures at a time, so that its pictures start together and can be
+  // kept aligned (block_align).  __syncthreads is safe here: every lane is back in this loop between rounds.
+  for (;;)
   {
-    if (c.lane == 0)
-    {
-      const int old = atomicAdd(const_cast<int*>(&rv[0]), 1);
-      if (old == round * FHC_PICS_PER_WARP - 1)
-      {
-        rv[2] = atomicAdd(queue, FHC_PICS_PER_WARP);
-        __threadfence_block();
-        rv[1] = round;
-      }
-    }
-    while (rv[1] < round) __nanosleep(100);
-    group_sync(c);
-    int p = rv[2];
-    if (p >= numPics) break;
-    p += grp;
+    __syncthreads();
+    if (threadIdx.x == 0) rvz[0] = atomicAdd(queue, FHC_PICS_PER_BLOCK);
+    __syncthreads();
+    const int base = rvz[0];
+    if (base >= numPics) break;
+    const int active = (numPics - base < FHC_PICS_PER_BLOCK) ? numPics - base : FHC_PICS_PER_BLOCK;
+    const int p = base + slot;
     if (p < numPics)
     {
       if (c.lane == 0)
       {
         // the group's leader walks the decision code; the other lanes serve its COOP sections and LANE dispatches
+        s->alignThreads = (FHC_GROUP == 32) ? 32 * active : 0;
         load_picture(c, &pics[p]);
         compress_picture(c);
         release_followers(c);
@@ -83,7 +74,6 @@ fhc_compress_pictures_kernel(PicDesc* pics, int numPics, int* queue, FrameGlobal
       }
       else follower_loop(c);
     }
-    group_sync(c);
   }
 }
 

@@ -61,7 +61,7 @@ enum {
 };
 #define FHC_MAX_COST 1.7e+308
 #ifndef FHC_WARPS_PER_BLOCK
-#define FHC_WARPS_PER_BLOCK 4    /* warps per thread block; each encodes 32 / FHC_GROUP pictures */
+#define FHC_WARPS_PER_BLOCK 8    /* warps (= pictures, FHC_GROUP 32) per thread block; the block keeps them aligned */
 #endif
 #ifndef FHC_GROUP
 #define FHC_GROUP 32             /* lanes per picture: a warp encodes 32 / FHC_GROUP pictures side by side (sub-warp groups serialise) */
@@ -118,7 +118,7 @@ FHC_HD void cu_bind(CUMeta* cu, uint8_t* store, int cap)
 
 enum Op {
   OP_EXIT = 0, OP_REFS, OP_RMD, OP_PRED_RESI, OP_FWD_QUANT, OP_LEVELS_OUT, OP_INV_RECON, OP_COPY2D, OP_COPY16, OP_ZERO16,
-  OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_TASKS
+  OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_TASKS, OP_BLOCKBAR
 };
 enum { ENG_MASTER = 0, ENG_LANE = 1 };
 enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1 };
@@ -164,6 +164,7 @@ struct Engine
   int16_t (*qtRec)[6144];
   int16_t (*qtCoef)[6144];
   int writePic;                   // reconstruct into the picture plane too (master only)
+  int noAlign;                    // inside a section whose TU count depends on the picture: no block alignment
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
   double* costCGSig;              // RDOQ per-group / per-context scratch
   uint8_t *cgFlag, *cgFlagCode;
@@ -245,6 +246,7 @@ struct FrameParams                 // hot read-only copy of the picture header (
 struct Shared
 {
   const Tables* t;
+  int alignThreads;               // threads of the block that take part in block_align (32 x pictures of this round)
   FrameParams fp;
   Sbac slot[5][CI_NUM];
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
@@ -330,6 +332,7 @@ FHC_D void follower_loop(const Ctx& c)
     const int op = c.e->cmd.op;
     if (op == OP_EXIT) break;
     if (op == OP_TASKS) { run_tasks(c); __syncwarp(c.mask); continue; }
+    if (op == OP_BLOCKBAR) { asm volatile("barrier.sync 1, %0;" ::"r"(c.s->alignThreads) : "memory"); continue; }
     const int np = (op == OP_RMD) ? c.e->cmd.a[15] : num_phases(op);
     FHC_NOUNROLL for (int ph = 0; ph < np; ph++)
     {
@@ -338,12 +341,32 @@ FHC_D void follower_loop(const Ctx& c)
     }
   }
 }
+// BLOCK ALIGNMENT.  The kernel is bound by instruction delivery (profiles/): warps that run different routines evict
+// each other's code from the SM's instruction caches and the fill path from L2 saturates chip-wide.  All pictures of
+// one size walk the same static schedule of routines (candidate counts are padded, see ghost_first_pass), so the
+// pictures of a thread block are aligned at the entry of every routine of that schedule with a named barrier: the
+// block's warps then execute the same code at the same time.  Sections whose TU count depends on the picture
+// (chroma trees, the final CTU coding) set noAlign.  Lane engines never align.
+FHC_DH void block_align(const Ctx& c)
+{
+#ifndef FHC_NO_ALIGN
+  if (c.e->kind != ENG_MASTER || c.e->noAlign) return;
+  const int n = c.s->alignThreads;
+  if (n <= 32) return;
+  c.e->cmd.op = OP_BLOCKBAR;
+  __syncwarp(c.mask);
+  asm volatile("barrier.sync 1, %0;" ::"r"(n) : "memory");
+#else
+  (void)c;
+#endif
+}
 FHC_DH void release_followers(const Ctx& c)
 {
   if (c.nl > 1) { c.e->cmd.op = OP_EXIT; __syncwarp(c.mask); }
 }
 #else
 FHC_DH void group_sync(const Ctx& c) { (void)c; }
+FHC_DH void block_align(const Ctx& c) { (void)c; }
 // emulation: the group's lanes are executed one after the other, phase by phase
 FHC_DH void par(const Ctx& c, int op)
 {
@@ -1695,6 +1718,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   FrameGlobal* g = c.g;
   const int n = 1 << log2n, isChroma = comp != 0;
   const int cuW = cu->width >> isChroma;
+  block_align(c);
   const int bx = rel_x(s, relIdx) >> isChroma, by = rel_y(s, relIdx) >> isChroma;
   const int qtLayer = 5 - lumaLog2;
   const int picX = (cu->x >> isChroma) + bx, picY = (cu->y >> isChroma) + by;
@@ -1737,6 +1761,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   e->cgNZ[0] = 0; e->cgNZ[1] = 0;
   par(c, OP_FWD_QUANT);
   const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
+  block_align(c);
   const uint32_t absSum = rdoq_pass(c, cu, relIdx, comp, log2n, cbfCtx);
   set_range(cu->cbf[comp], relIdx, numParts, (absSum > 0 ? 1 : 0) << trDepthBit);
 
@@ -1822,6 +1847,7 @@ FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log
                              int bLuma, int bChroma)
 {
   FHC_TIC(bq);
+  block_align(c);
   reset_bits(c.e);
   enc_intra_header(c, cu, trDepth, relIdx, bLuma, bChroma);
   enc_subdiv_cbf(c, cu, relIdx, log2n, trDepth, chromaCodeAll, bLuma, bChroma);
@@ -1983,6 +2009,19 @@ FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
   }
 }
 
+// The alignment points of one first-pass candidate (recur_luma_qt with bCheckFirst) without its work: pictures whose
+// candidate list is shorter than the longest possible one (3 RMD survivors + 2 MPMs for PUs >= 16) pad with these so
+// that every picture of a block passes the same number of block_align calls.
+FHC_D void ghost_first_pass(const Ctx& c, int log2n)
+{
+  if (log2n <= 5) { block_align(c); block_align(c); block_align(c); }       // code_tu_block entry, RDOQ, intra_bits_qt
+  else
+  {
+    FHC_NOUNROLL for (int i = 0; i < 4; i++) ghost_first_pass(c, log2n - 1);
+    block_align(c);                                                          // intra_bits_qt of the split node
+  }
+}
+
 // estIntraPredLumaQT (TEncSearch.cpp:2177-2557)
 FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
 {
@@ -2009,6 +2048,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     const int pox = cu->x + rel_x(s, partOffset), poy = cu->y + rel_y(s, partOffset);
 
     // ---- rough mode decision: 35 predictions + SATD on the workers (TEncSearch.cpp:2271-2295)
+    block_align(c);
     build_refs(c, cu, partOffset, 0, puSize, 1);
     {
       Cmd& m = e->cmd;
@@ -2086,6 +2126,8 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     {
       const int second = (i == numModesForFullRD);
       const uint32_t orgMode = second ? bestPUMode : rdModeList[i];
+      if (second && log2pu >= 4)
+        FHC_NOUNROLL for (int k = numModesForFullRD; k < 5; k++) ghost_first_pass(c, log2pu);   // pad the list to 3 + 2 MPMs
       uint32_t puDist = 0;
       double puCost = 0.0;
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
@@ -2277,11 +2319,14 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
   {
     uint32_t dist = 0;
     FHC_TIC(cb);
+    block_align(c);
+    e->noAlign = 1;                                  // the chroma TU tree follows the luma tree of this picture
     sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, nparts, modeList[mi]);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
     sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
+    e->noAlign = 0;
     if (cost < bestCost)
     {
       bestCost = cost; bestDist = dist; bestMode = (uint32_t)modeList[mi];
@@ -2435,6 +2480,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   { FHC_TIC(el); est_intra_luma(c, cu, cuCoef, cuReco); FHC_TOC2(c, el, PF_LUMA); }
   par_copy2d(c, g->rec[0] + cu->y * plane_stride(s, 0) + cu->x, plane_stride(s, 0), cuReco, cu->width, cu->width, cu->width);
   { FHC_TIC(ec); est_intra_chroma(c, cu, cuCoef, cuReco); FHC_TOC2(c, ec, PF_CHROMA); }
+  block_align(c);
   reset_bits(e);
   encode_cu_syntax(c, cu, cuCoef);
   sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), &e->go);
@@ -2562,7 +2608,7 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
 {
   Engine* m = &s->master;
   s->t = tables;
-  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0];
+  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0;
   m->refU = s->refU; m->refF = s->refF; m->flags = s->flags;
   bind_coef_scratch(m, &s->cs);
   m->predYuv = g->predYuv; m->qtRec = g->qtRec; m->qtCoef = g->qtCoef; m->writePic = 1;
@@ -2576,7 +2622,7 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
   {
     EngineGlobal* x = &g->eng[i];
     Engine* e = &x->eng;
-    e->kind = ENG_LANE; e->t = tables; e->slots = x->slots;
+    e->kind = ENG_LANE; e->t = tables; e->slots = x->slots; e->noAlign = 1;
     e->refU = x->refU; e->refF = x->refF; e->flags = x->flags;
     bind_coef_scratch(e, &x->cs);
     e->predYuv = x->predYuv; e->qtRec = x->qtRec; e->qtCoef = x->qtCoef; e->writePic = 0;
@@ -2666,6 +2712,7 @@ FHC_D void run_tasks(const Ctx& c)
 // called by the leader: publishes the dispatch, takes part in it, and waits for the group before comparing results
 FHC_D void dispatch_tasks(const Ctx& c)
 {
+  block_align(c);
 #ifdef FHC_DEVICE_BUILD
   if (c.nl > 1) { c.e->cmd.op = OP_TASKS; __syncwarp(c.mask); }
   run_tasks(c);
