@@ -61,12 +61,15 @@ enum {
 };
 #define FHC_MAX_COST 1.7e+308
 #ifndef FHC_WARPS_PER_BLOCK
-#define FHC_WARPS_PER_BLOCK 8    /* warps (= pictures, FHC_GROUP 32) per thread block; the block keeps them aligned */
+#define FHC_WARPS_PER_BLOCK 16   /* warps (= pictures, FHC_GROUP 32) per thread block; the block keeps them aligned */
 #endif
 #ifndef FHC_GROUP
 #define FHC_GROUP 32             /* lanes per picture: a warp encodes 32 / FHC_GROUP pictures side by side (sub-warp groups serialise) */
 #endif
-#define FHC_MAX_TASKS 12         /* the longest candidate list (8 RMD survivors + MPMs) */
+#define FHC_MAX_TASKS 10         /* the longest candidate list (8 RMD survivors + 2 MPMs) */
+#ifndef FHC_LANE_SMEM
+#define FHC_LANE_SMEM 0           /* 1: lane engines keep their CABAC state and 4x4 scratch in shared memory (costs L1) */
+#endif
 #define FHC_NENG (FHC_GROUP < FHC_MAX_TASKS ? FHC_GROUP : FHC_MAX_TASKS)   /* lane engines per picture */
 #define FHC_SMALL_COEFS 64       /* TUs up to 8x8 use the warp's shared-memory scratch, larger ones the global scratch */
 #define FHC_FULL_MASK 0xffffffffu
@@ -118,7 +121,7 @@ FHC_HD void cu_bind(CUMeta* cu, uint8_t* store, int cap)
 
 enum Op {
   OP_EXIT = 0, OP_REFS, OP_RMD, OP_PRED_RESI, OP_FWD_QUANT, OP_LEVELS_OUT, OP_INV_RECON, OP_COPY2D, OP_COPY16, OP_ZERO16,
-  OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_TASKS, OP_BLOCKBAR
+  OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_NZMASK, OP_TASKS, OP_BLOCKBAR
 };
 enum { ENG_MASTER = 0, ENG_LANE = 1 };
 enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1 };
@@ -150,7 +153,7 @@ struct Engine
   int refDc;
   double rdoqLambda;
   const Tables* t;
-  Sbac go;
+  Sbac* go;                       // the coder under work (shared memory: every bin reads and steps a context)
   Sbac* slots;                    // master: [5][CI_NUM]; lane engine: [3] shared by all depths (TU-level slots only)
   Cmd cmd;
   int16_t *refU, *refF;
@@ -160,9 +163,13 @@ struct Engine
   double *cost0, *costCoeff, *costSig;
   int32_t *rateIncUp, *rateIncDown, *sigRateDelta, *deltaU;
   int16_t tsCoef[3][16], tsRec[3][16], tsPred[3][16];
+  void *csSmall, *csLarge;        // coefficient scratch by TU size (master: <= 8x8 shared / larger global; lane: 4x4 shared / 8x8 global)
+  // engine buffers: prediction/reconstruction of the CU under test and the per-TU-size layers; layerSize samples per
+  // layer, component c at coff[c], luma rows qs apart (chroma qs / 2).  Master: 6144 / {0,4096,5120} / 64 (a CTU);
+  // lane engine: 96 / {0,64,80} / 8 (an 8x8 CU, dense)
   int16_t* predYuv;
-  int16_t (*qtRec)[6144];
-  int16_t (*qtCoef)[6144];
+  int16_t *qtRecBase, *qtCoefBase;
+  int layerSize, qs, coff[3];
   int writePic;                   // reconstruct into the picture plane too (master only)
   int noAlign;                    // inside a section whose TU count depends on the picture: no block alignment
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
@@ -170,30 +177,39 @@ struct Engine
   uint8_t *cgFlag, *cgFlagCode;
   double *sigC0, *sigC1;
   int32_t* sigDelta;
+  uint16_t* cgNzMask;             // per coefficient group (scan order): non-zero map of the levels
+  int32_t* cgAbs;                 // ... and their sum
   // engine result: best task of the current dispatch
   double resCost;
   uint32_t resDist;
   int resTask;
 };
 
+FHC_DH int16_t* qt_rec(const Engine* e, int layer) { return e->qtRecBase + layer * e->layerSize; }
+FHC_DH int16_t* qt_coef(const Engine* e, int layer) { return e->qtCoefBase + layer * e->layerSize; }
+
 // private global scratch of one lane engine (same layouts as the master's buffers; engines only see depth-3 CUs)
 struct EngineGlobal
 {
   Engine eng;
   Sbac slots[3];                  // CI_QT_TRAFO_ROOT, CI_TEMP_BEST, CI_QT_TRAFO_TEST
+  Sbac go;                        // used when FHC_LANE_SMEM is 0
+  CoefScratch<16> cs16;
   int16_t refU[36], refF[36];
   uint8_t flags[24];
   CoefScratch<FHC_SMALL_COEFS> cs;
   double costCGSig[4], sigC0[28], sigC1[28];
   int32_t sigDelta[28];
   uint8_t cgFlag[4], cgFlagCode[4];
+  uint16_t cgNzMask[4];
+  int32_t cgAbs[4];
   CUMeta cu;
   uint8_t cuStore[12 * 4];
   int16_t bestCoef[3][64], bestReco[3][64];
   uint8_t bestTrIdx[4], bestCbf[3][4], bestTs[3][4];
-  int16_t predYuv[6144];
-  int16_t qtRec[4][6144];
-  int16_t qtCoef[4][6144];
+  int16_t predYuv[96];
+  int16_t qtRec[4][96];
+  int16_t qtCoef[4][96];
 };
 
 // picture descriptor (global memory, filled by the host per submitted picture)
@@ -224,6 +240,8 @@ struct FrameGlobal
   int16_t qtRec[4][6144];         // per-TU-size reconstruction layers (Y stride 64, C stride 32)
   int16_t qtCoef[4][6144];        // per-TU-size coefficient layers
   int16_t rmdPred[4096];          // one group of predicted modes of the rough mode decision
+  uint8_t cuStoreBig[2 * 12 * (256 + 64)];   // CU metadata of depth 0 and 1
+  uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];   // best-so-far TU flags of the PU under test
   CoefScratch<1024> big;          // TU pipeline + RDOQ scratch of 16x16 / 32x32 TUs
   EngineGlobal eng[FHC_NENG];
 };
@@ -233,7 +251,7 @@ struct TaskDesc
   int kind, numTasks;
   int depth, bufIdx;              // the CU under test: s->cu[depth][bufIdx]
   int partOffset, log2pu, initTrDepth;
-  int mode[12];
+  int mode[FHC_MAX_TASKS];
 };
 
 struct FrameParams                 // hot read-only copy of the picture header (shared memory)
@@ -252,18 +270,29 @@ struct Shared
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
   uint8_t bestIdx[4];
   CUMeta cu[4][2];
-  uint8_t cuStore[2 * 12 * (256 + 64 + 16 + 4)];
+  uint8_t cuStore[2 * 12 * (16 + 4)];        // CU metadata of depth 2 and 3 (depth 0 and 1: FrameGlobal::cuStoreBig)
   Engine master;
   TaskDesc task;
+  Sbac masterGo;
+#if FHC_LANE_SMEM
+  Sbac laneGo[FHC_NENG];
+#endif
   // master scratch
   int16_t refU[260], refF[260];
   uint8_t flags[72];
-  CoefScratch<FHC_SMALL_COEFS> cs;
+  union                          // a dispatch and a COOP TU of the master never overlap in time
+  {
+    CoefScratch<FHC_SMALL_COEFS> cs;          // master: TUs up to 8x8
+#if FHC_LANE_SMEM
+    CoefScratch<16> laneCs[FHC_NENG];         // lane engines: 4x4 TUs
+#endif
+  } u;
   uint32_t satd[36];
-  uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];
   double costCGSig[64], sigC0[28], sigC1[28];
   int32_t sigDelta[28];
   uint8_t cgFlag[64], cgFlagCode[64];
+  uint16_t cgNzMask[64];
+  int32_t cgAbs[64];
 };
 
 // lane/nl: this thread's index and the size of the lane group that executes COOP sections together (32 = the warp,
@@ -360,6 +389,11 @@ FHC_DH void block_align(const Ctx& c)
   (void)c;
 #endif
 }
+#ifdef FHC_FINE_ALIGN
+FHC_DH void fine_align(const Ctx& c) { block_align(c); }
+#else
+FHC_DH void fine_align(const Ctx& c) { (void)c; }
+#endif
 FHC_DH void release_followers(const Ctx& c)
 {
   if (c.nl > 1) { c.e->cmd.op = OP_EXIT; __syncwarp(c.mask); }
@@ -367,6 +401,7 @@ FHC_DH void release_followers(const Ctx& c)
 #else
 FHC_DH void group_sync(const Ctx& c) { (void)c; }
 FHC_DH void block_align(const Ctx& c) { (void)c; }
+FHC_DH void fine_align(const Ctx& c) { (void)c; }
 // emulation: the group's lanes are executed one after the other, phase by phase
 FHC_DH void par(const Ctx& c, int op)
 {
@@ -381,6 +416,13 @@ FHC_DH int iabs(int v) { return v < 0 ? -v : v; }
 FHC_DH int imin(int a, int b) { return a < b ? a : b; }
 FHC_DH int imax(int a, int b) { return a > b ? a : b; }
 FHC_DH int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+#ifdef FHC_DEVICE_BUILD
+FHC_DH int msb_index(uint32_t v) { return 31 - __clz((int)v); }
+FHC_DH int lsb_index(uint32_t v) { return __ffs((int)v) - 1; }
+#else
+FHC_DH int msb_index(uint32_t v) { return 31 - __builtin_clz(v); }
+FHC_DH int lsb_index(uint32_t v) { return __builtin_ctz(v); }
+#endif
 
 FHC_DH int org_at(const FrameGlobal* g, int sampleBytes, int comp, int idx)
 {
@@ -714,7 +756,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
   case OP_LEVELS_OUT:
   {
     // a0 n2, a1 qtCoef layer, a2 offset: tmp[] (int32 levels) -> qtCoef (int16)
-    int16_t* d = e->qtCoef[a[1]] + a[2];
+    int16_t* d = qt_coef(e, a[1]) + a[2];
     for (int i = w; i < a[0]; i += nw) d[i] = (int16_t)e->tmp[i];
     break;
   }
@@ -779,9 +821,9 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     {
       // reconstruction into CU buffer, QT layer and picture (TEncSearch.cpp:1380-1393) + SSE (TComRdCost.cpp:1176)
       int16_t* reco = e->predYuv + a[7];
-      int16_t* recQt = e->qtRec[a[9]] + a[10];
+      int16_t* recQt = qt_rec(e, a[9]) + a[10];
       int16_t* recPic = g->rec[comp] + a[11];
-      const int ps = a[8], qs = 64 >> (comp ? 1 : 0), stride = plane_stride(s, comp), shift = (bd - 8) << 1;
+      const int ps = a[8], qs = e->qs >> (comp ? 1 : 0), stride = plane_stride(s, comp), shift = (bd - 8) << 1;
       uint32_t acc = 0;
       for (int i = w; i < n2; i += nw)
       {
@@ -795,6 +837,20 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         acc += (uint32_t)((d * d) >> shift);
       }
       if (acc) atomic_add_u32(&e->sse, acc, nw);
+    }
+    break;
+  }
+  case OP_NZMASK:
+  {
+    // a0 log2n, a1 scan type, src = int16 levels (raster): non-zero map of every coefficient group, in scan order
+    const uint16_t* scan = scan_tab(*s->t, a[1], a[0]);
+    const int16_t* coef = (const int16_t*)e->cmd.src;
+    const int ncg = 1 << (2 * a[0] - 4);
+    for (int cg = w; cg < ncg; cg += nw)
+    {
+      uint32_t mask = 0;
+      for (int i = 0; i < 16; i++) mask |= (uint32_t)(coef[scan[cg * 16 + i]] != 0) << i;
+      e->cgNzMask[cg] = (uint16_t)mask;
     }
     break;
   }
@@ -891,16 +947,16 @@ FHC_DH void copy_bytes(uint8_t* d, const uint8_t* s, int n) { for (int i = 0; i 
 // ----------------------------------------------------------------------------------------------
 FHC_DH void enc_bin(Engine* e, int ctx, int bin)
 {
-  const uint8_t st = e->go.c[ctx];
+  const uint8_t st = e->go->c[ctx];
   e->bins++;
-  e->go.frac += (uint64_t)e->t->entropyBits[st ^ bin];
-  e->go.c[ctx] = e->t->nextState[st][bin];
+  e->go->frac += (uint64_t)e->t->entropyBits[st ^ bin];
+  e->go->c[ctx] = e->t->nextState[st][bin];
 }
-FHC_DH void enc_ep(Engine* e, int n) { e->bins += (uint32_t)n; e->go.frac += (uint64_t)32768 * (uint64_t)n; }
-FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; e->go.frac += (uint64_t)e->t->entropyBits[126 ^ bin]; }
-FHC_DH void reset_bits(Engine* e) { e->go.frac &= 32767; e->bins = 0; }
-FHC_DH uint32_t num_bits(const Engine* e) { return (uint32_t)(e->go.frac >> 15); }
-FHC_DH int ctx_bits(const Engine* e, int ctx, int bin) { return e->t->entropyBits[e->go.c[ctx] ^ bin]; }
+FHC_DH void enc_ep(Engine* e, int n) { e->bins += (uint32_t)n; e->go->frac += (uint64_t)32768 * (uint64_t)n; }
+FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; e->go->frac += (uint64_t)e->t->entropyBits[126 ^ bin]; }
+FHC_DH void reset_bits(Engine* e) { e->go->frac &= 32767; e->bins = 0; }
+FHC_DH uint32_t num_bits(const Engine* e) { return (uint32_t)(e->go->frac >> 15); }
+FHC_DH int ctx_bits(const Engine* e, int ctx, int bin) { return e->t->entropyBits[e->go->c[ctx] ^ bin]; }
 FHC_DH void sb_copy(const Ctx& c, Sbac* d, const Sbac* sr)
 {
   const uint64_t* a = (const uint64_t*)sr;
@@ -1130,17 +1186,22 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   int scanPosLast = -1, posLast = 0;
 
   if (log2n == 2) enc_bin(e, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
-  FHC_NOUNROLL for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
-  // last significant position: highest scan index with a non-zero level
-  FHC_NOUNROLL for (int p = n * n - 1; p >= 0; p--)
-    if (coef[scan[p]] != 0) { scanPosLast = p; break; }
-  posLast = scan[scanPosLast];
-  FHC_NOUNROLL for (int g4 = 0; g4 <= (scanPosLast >> 4); g4++)
+  // non-zero map per coefficient group (COOP for TUs of 8x8 and up), then last position and group flags from the maps
+  const uint16_t* nzMask = e->cgNzMask;
   {
-    int any = 0;
-    FHC_NOUNROLL for (int i = 0; i < 16; i++) any |= coef[scan[g4 * 16 + i]] != 0;
-    if (any) cgFlag[scanCG[g4]] = 1;
+    Cmd& m = e->cmd;
+    m.a[0] = log2n; m.a[1] = scanType; m.src = coef;
+    if (log2n >= 3) par(c, OP_NZMASK); else run_phase(c, OP_NZMASK, 0, 0, 1);
   }
+  FHC_NOUNROLL for (int i = 0; i < wg * wg; i++) cgFlag[i] = 0;
+  FHC_NOUNROLL for (int g4 = wg * wg - 1; g4 >= 0; g4--)
+  {
+    const uint32_t mask = nzMask[g4];
+    if (!mask) continue;
+    if (scanPosLast < 0) scanPosLast = g4 * 16 + msb_index(mask);
+    cgFlag[scanCG[g4]] = 1;
+  }
+  posLast = scan[scanPosLast];
   {
     int posY = posLast >> log2n, posX = posLast - (posY << log2n), off, shift, cc;
     if (scanType == SCAN_VER) { const int t = posX; posX = posY; posY = t; }
@@ -1175,9 +1236,10 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
       if (cgFlag[cgBlk])
       {
         const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
+        const uint32_t cgMask = nzMask[subSet];
         FHC_NOUNROLL for (; scanPosSig >= subPos; scanPosSig--)
         {
-          const int blkPos = scan[scanPosSig], sig = coef[blkPos] != 0;
+          const int blkPos = scan[scanPosSig], sig = (int)((cgMask >> (scanPosSig - subPos)) & 1u);
           if (scanPosSig > subPos || subSet == 0 || numNonZero)
             enc_bin(e, sigBase + sig_ctx_inc(*s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
           if (sig)
@@ -1343,6 +1405,8 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
   // change while a TU is being quantised): replaces estBitsSbacStruct::significantBits (TEncSbac.cpp:1772)
   double* sigC0 = e->sigC0; double* sigC1 = e->sigC1;
   int32_t* sigDelta = e->sigDelta;
+  const int useTab = numCoef > 16;          // a 4x4 TU looks up at most 16 contexts: cheaper without the table
+  if (useTab)
   {
     const int nSig = isChroma ? 16 : 28;
     FHC_NOUNROLL for (int i = 0; i < nSig; i++)
@@ -1351,6 +1415,9 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       sigC0[i] = dmul(lambda, (double)b0); sigC1[i] = dmul(lambda, (double)b1); sigDelta[i] = b1 - b0;
     }
   }
+#define FHC_SIGC0(sc) (useTab ? sigC0[sc] : dmul(lambda, (double)ctx_bits(e, sigBase + (sc), 0)))
+#define FHC_SIGC1(sc) (useTab ? sigC1[sc] : dmul(lambda, (double)ctx_bits(e, sigBase + (sc), 1)))
+#define FHC_SIGDELTA(sc) (useTab ? sigDelta[sc] : ctx_bits(e, sigBase + (sc), 1) - ctx_bits(e, sigBase + (sc), 0))
 
   FHC_NOUNROLL for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
   {
@@ -1377,7 +1444,7 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       {
         const int scanPos = cgScanPos * 16 + posInCG;
         const double c0 = costCoeff0[scanPos];
-        const double cs = sigC0[sig_ctx_inc(*e->t, pat, firstSig, (int)scan[scanPos], log2n, isChroma)];
+        const double cs = FHC_SIGC0(sig_ctx_inc(*e->t, pat, firstSig, (int)scan[scanPos], log2n, isChroma));
         blockUncoded = dadd(blockUncoded, c0);
         baseCost = dadd(baseCost, dadd(c0, cs));
         sigCost = dadd(sigCost, cs);
@@ -1415,9 +1482,9 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       {
         // "level 0" is the only candidate (xGetCodedLevel returns early); no state of the level coder changes
         const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
-        const double cs = sigC0[sc], cc = dadd(costCoeff0[scanPos], cs);
+        const double cs = FHC_SIGC0(sc), cc = dadd(costCoeff0[scanPos], cs);
         costSig[scanPos] = cs; costCoeff[scanPos] = cc;
-        sigRateDelta[blkPos] = sigDelta[sc];
+        sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         deltaU[blkPos] = levelDouble >> (qBits - 8);
         rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0); rateIncDown[blkPos] = 0;
         baseCost = dadd(baseCost, cc);
@@ -1442,8 +1509,8 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
         {
           const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
-                              sigC0[sc], sigC1[sc], ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
-          sigRateDelta[blkPos] = sigDelta[sc];
+                              FHC_SIGC0(sc), FHC_SIGC1(sc), ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
+          sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
         if (level > 0)
@@ -1560,12 +1627,28 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
       }
     }
   }
-  FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
+  // signs, and per coefficient group of the coded range the non-zero map and the level sum (consumed by sign bit hiding)
+  uint16_t* nzMask = e->cgNzMask;
+  int32_t* cgAbs = e->cgAbs;
+  const int numCodedCG = (bestLastIdxP1 + 15) >> 4;
+  FHC_NOUNROLL for (int cgi = 0; cgi < numCodedCG; cgi++)
   {
-    const int blkPos = scan[scanPos];
-    const int32_t level = dst[blkPos];
-    absSum += (uint32_t)level;
-    dst[blkPos] = (src[blkPos] < 0) ? -level : level;
+    const int p0 = cgi << 4, p1 = imin(bestLastIdxP1, p0 + 16);
+    uint32_t mask = 0;
+    int sum = 0;
+    FHC_NOUNROLL for (int scanPos = p0; scanPos < p1; scanPos++)
+    {
+      const int blkPos = scan[scanPos];
+      const int32_t level = dst[blkPos];
+      if (level)
+      {
+        mask |= 1u << (scanPos - p0);
+        sum += level;
+        if (src[blkPos] < 0) dst[blkPos] = -level;
+      }
+    }
+    absSum += (uint32_t)sum;
+    nzMask[cgi] = (uint16_t)mask; cgAbs[cgi] = sum;
   }
   FHC_NOUNROLL for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) dst[scan[scanPos]] = 0;
 
@@ -1580,15 +1663,15 @@ FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxC
 #endif
     const int64_t rdFactor = (int64_t)f;
     int lastCG = -1;
-    FHC_NOUNROLL for (int subSet = (numCoef - 1) >> 4; subSet >= 0; subSet--)
+    // groups above the coded range hold no level and change nothing (TComTrQuant.cpp:2541-2564 would find lastNZ = -1)
+    FHC_NOUNROLL for (int subSet = numCodedCG - 1; subSet >= 0; subSet--)
     {
       const int subPos = subSet << 4;
-      int firstNZ = 16, lastNZ = -1, sum = 0, nn;
-      if (subPos > lastScanPos) continue;                                       // nothing coded up there (all levels are 0)
-      FHC_NOUNROLL for (nn = 15; nn >= 0; --nn) if (dst[scan[nn + subPos]]) { lastNZ = nn; break; }
-      FHC_NOUNROLL for (nn = 0; nn < 16; nn++) if (dst[scan[nn + subPos]]) { firstNZ = nn; break; }
-      FHC_NOUNROLL for (nn = firstNZ; nn <= lastNZ; nn++) sum += dst[scan[nn + subPos]];
-      if (lastNZ >= 0 && lastCG == -1) lastCG = 1;
+      const uint32_t mask = nzMask[subSet];
+      int nn;
+      if (!mask) continue;
+      const int lastNZ = msb_index(mask), firstNZ = lsb_index(mask), sum = cgAbs[subSet];     // sum: only its parity is used
+      if (lastCG == -1) lastCG = 1;
       if (lastNZ - firstNZ >= 4)
       {
         const uint32_t signbit = dst[scan[subPos + firstNZ]] > 0 ? 0 : 1;
@@ -1723,18 +1806,24 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   const int qtLayer = 5 - lumaLog2;
   const int picX = (cu->x >> isChroma) + bx, picY = (cu->y >> isChroma) + by;
   const int stride = plane_stride(s, comp);
-  const int predOff = comp_off(comp) + by * cuW + bx;
-  const int qtOff = comp_off(comp) + by * (64 >> isChroma) + bx;
-  const int coefOff = comp_off(comp) + (isChroma ? relIdx * 4 : relIdx * 16);
+  const int predOff = e->coff[comp] + by * cuW + bx;
+  const int qtOff = e->coff[comp] + by * (e->qs >> isChroma) + bx;
+  const int coefOff = e->coff[comp] + (isChroma ? relIdx * 4 : relIdx * 16);
   const int ts = cu->ts[comp][relIdx];
   const QpParam q = qp_param(c, comp);
   int mode;
   Cmd& m = e->cmd;
   FHC_TIC(tu);
+  // coefficient scratch by TU size: the small one lives in the warp's shared-memory slice
   if (e->kind == ENG_MASTER)
   {
-    // TUs up to 8x8 run on the warp's shared-memory scratch, 16x16 / 32x32 on the global one
-    if (n * n <= FHC_SMALL_COEFS) bind_coef_scratch(e, &s->cs); else bind_coef_scratch(e, &g->big);
+    if (n * n <= FHC_SMALL_COEFS) bind_coef_scratch(e, (CoefScratch<FHC_SMALL_COEFS>*)e->csSmall);
+    else bind_coef_scratch(e, (CoefScratch<1024>*)e->csLarge);
+  }
+  else
+  {
+    if (n * n <= 16) bind_coef_scratch(e, (CoefScratch<16>*)e->csSmall);
+    else bind_coef_scratch(e, (CoefScratch<FHC_SMALL_COEFS>*)e->csLarge);
   }
 
   if (comp == 0) mode = cu->ldir[relIdx];
@@ -1751,6 +1840,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   }
   m.a[0] = comp; m.a[1] = log2n; m.a[2] = mode; m.a[3] = useFilt; m.a[4] = predOff; m.a[5] = cuW;
   m.a[6] = picY * stride + picX; m.a[7] = predSaveLoad;
+  fine_align(c);
   par(c, OP_PRED_RESI);
 
   // transform + RDOQ (TComTrQuant::transformNxN :1450)
@@ -1759,6 +1849,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   m.a[0] = log2n; m.a[1] = (comp == 0 && log2n == 2); m.a[2] = ts; m.a[3] = scanType; m.a[4] = quant_scale(q.rem);
   m.a[5] = 14 + q.per + (15 - s->fp.bitDepth - log2n); m.a[6] = isChroma; m.a[7] = q.rem;
   e->cgNZ[0] = 0; e->cgNZ[1] = 0;
+  fine_align(c);
   par(c, OP_FWD_QUANT);
   const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
   block_align(c);
@@ -1766,10 +1857,12 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   set_range(cu->cbf[comp], relIdx, numParts, (absSum > 0 ? 1 : 0) << trDepthBit);
 
   // levels -> QT coefficient layer
+  fine_align(c);
   if (absSum > 0) { m.a[0] = n * n; m.a[1] = qtLayer; m.a[2] = coefOff; par(c, OP_LEVELS_OUT); }
-  else par_zero16(c, e->qtCoef[qtLayer] + coefOff, n * n);
+  else par_zero16(c, qt_coef(e, qtLayer) + coefOff, n * n);
 
   // inverse + reconstruction + SSE
+  fine_align(c);
   e->sse = 0;
   m.a[0] = comp; m.a[1] = log2n; m.a[2] = (comp == 0 && log2n == 2); m.a[3] = ts; m.a[4] = absSum > 0; m.a[5] = q.per; m.a[6] = q.rem;
   m.a[7] = predOff; m.a[8] = cuW; m.a[9] = qtLayer; m.a[10] = qtOff; m.a[11] = picY * stride + picX; m.a[12] = picY * stride + picX;
@@ -1835,12 +1928,12 @@ FHC_D void enc_coeff_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, i
   }
   else if (comp == 0)
   {
-    if ((cu->cbf[0][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, relIdx, c.e->qtCoef[5 - log2n] + relIdx * 16, log2n, 0);
+    if ((cu->cbf[0][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, relIdx, qt_coef(c.e, 5 - log2n) + relIdx * 16, log2n, 0);
   }
   else if (procChroma)
   {
     const int cl = log2n == 2 ? 2 : log2n - 1, ridx = log2n == 2 ? (relIdx & ~3) : relIdx;
-    if ((cu->cbf[comp][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, ridx, c.e->qtCoef[5 - log2n] + comp_off(comp) + ridx * 4, cl, comp);
+    if ((cu->cbf[comp][relIdx] >> trDepth) & 1) code_coeff_nxn(c, cu, ridx, qt_coef(c.e, 5 - log2n) + c.e->coff[comp] + ridx * 4, cl, comp);
   }
 }
 FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log2n, int trDepth, int chromaCodeAll, int procChroma,
@@ -1874,8 +1967,9 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   int bestModeId = 0;
   const int checkTS = (log2n == 2) && (cu->part[relIdx] == SIZE_NxN);
   const int layer = 5 - log2n;
-  int16_t* qtCoefBlk = e->qtCoef[layer < 0 ? 0 : layer] + relIdx * 16;
-  int16_t* qtRecBlk = e->qtRec[layer < 0 ? 0 : layer] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx);
+  int16_t* qtCoefBlk = qt_coef(e, layer < 0 ? 0 : layer) + relIdx * 16;
+  const int qs = e->qs;
+  int16_t* qtRecBlk = qt_rec(e, layer < 0 ? 0 : layer) + rel_y(s, relIdx) * qs + rel_x(s, relIdx);
   int16_t* picBlk = g->rec[0] + (cu->y + rel_y(s, relIdx)) * plane_stride(s, 0) + cu->x + rel_x(s, relIdx);
   if (checkFirst && checkFull) checkSplit = 0;
 
@@ -1883,7 +1977,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
   {
     if (checkTS)
     {
-      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
       FHC_NOUNROLL for (int modeId = 0; modeId < 2; modeId++)
       {
         double costTmp;
@@ -1898,11 +1992,11 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
           singleCost = costTmp; singleDist = dTmp; singleCbf = cbfTmp; bestModeId = modeId;
           if (modeId == 0)
           {
-            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[0][i] = qtCoefBlk[i]; e->tsRec[0][i] = qtRecBlk[(i >> 2) * 64 + (i & 3)]; }
-            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
+            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[0][i] = qtCoefBlk[i]; e->tsRec[0][i] = qtRecBlk[(i >> 2) * qs + (i & 3)]; }
+            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), e->go);
           }
         }
-        if (modeId == 0) sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+        if (modeId == 0) sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       set_range(cu->ts[0], relIdx, numParts, bestModeId);
       if (bestModeId == 0)
@@ -1911,16 +2005,16 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
         FHC_NOUNROLL for (int i = 0; i < 16; i++)
         {
           qtCoefBlk[i] = e->tsCoef[0][i];
-          qtRecBlk[(i >> 2) * 64 + (i & 3)] = e->tsRec[0][i];
+          qtRecBlk[(i >> 2) * qs + (i & 3)] = e->tsRec[0][i];
           if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[0][i];
         }
         set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
-        sb_copy(c, &e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
+        sb_copy(c, e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
     }
     else
     {
-      if (checkSplit) sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      if (checkSplit) sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
       set_range(cu->ts[0], relIdx, numParts, 0);
       set_range(cu->tridx, relIdx, numParts, trDepth);
       singleDist = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, 0);
@@ -1935,10 +2029,10 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     const int q = numParts >> 2;
     if (checkFull)
     {
-      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_TEST), &e->go);
-      sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_TEST), e->go);
+      sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     }
-    else sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+    else sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
     FHC_NOUNROLL for (int i = 0; i < 4; i++)
     {
       recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, checkFirst, &splitDist, &splitCost);
@@ -1946,7 +2040,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
     }
     if (splitCbf)
       FHC_NOUNROLL for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
-    sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+    sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
     splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
     if (splitCost < singleCost)
     {
@@ -1954,11 +2048,11 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
       *rdCost = dadd(*rdCost, splitCost);
       return;
     }
-    sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_TEST));
+    sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_TEST));
     set_range(cu->tridx, relIdx, numParts, trDepth);
     set_range(cu->cbf[0], relIdx, numParts, (int)(singleCbf << trDepth));
     set_range(cu->ts[0], relIdx, numParts, bestModeId);
-    par_copy2d(c, picBlk, plane_stride(s, 0), qtRecBlk, 64, 1 << log2n, 1 << log2n);
+    par_copy2d(c, picBlk, plane_stride(s, 0), qtRecBlk, qs, 1 << log2n, 1 << log2n);
   }
   *distY += singleDist;
   *rdCost = dadd(*rdCost, singleCost);
@@ -1976,7 +2070,7 @@ FHC_D int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n
   const int numParts = cu->nparts >> (2 * trDepth), q = numParts >> 2;
   double splitCost = 0.0;
   uint32_t splitDist = 0, splitCbf = 0;
-  sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+  sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
   FHC_NOUNROLL for (int i = 0; i < 4; i++)
   {
     recur_luma_qt(c, cu, relIdx + i * q, log2n - 1, trDepth + 1, 0, &splitDist, &splitCost);
@@ -1984,7 +2078,7 @@ FHC_D int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n
   }
   if (splitCbf)
     FHC_NOUNROLL for (int i = 0; i < numParts; i++) cu->cbf[0][relIdx + i] |= (uint8_t)(1 << trDepth);
-  sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+  sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
   splitCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), splitDist);
   if (splitCost < singleCost) { *dist = splitDist; *cost = splitCost; return 1; }
   return 0;
@@ -1998,9 +2092,9 @@ FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
   if (cu->tridx[relIdx] == trDepth)
   {
     const int n = 1 << log2n;
-    par_copy16(c, cuCoef + relIdx * 16, c.e->qtCoef[5 - log2n] + relIdx * 16, n * n);
+    par_copy16(c, cuCoef + relIdx * 16, qt_coef(c.e, 5 - log2n) + relIdx * 16, n * n);
     par_copy2d(c, cuReco + rel_y(s, relIdx) * cu->width + rel_x(s, relIdx), cu->width,
-               c.e->qtRec[5 - log2n] + rel_y(s, relIdx) * 64 + rel_x(s, relIdx), 64, n, n);
+               qt_rec(c.e, 5 - log2n) + rel_y(s, relIdx) * c.e->qs + rel_x(s, relIdx), c.e->qs, n, n);
   }
   else
   {
@@ -2014,7 +2108,11 @@ FHC_D void set_luma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
 // that every picture of a block passes the same number of block_align calls.
 FHC_D void ghost_first_pass(const Ctx& c, int log2n)
 {
-  if (log2n <= 5) { block_align(c); block_align(c); block_align(c); }       // code_tu_block entry, RDOQ, intra_bits_qt
+  if (log2n <= 5)
+  {
+    block_align(c); block_align(c); block_align(c);                         // code_tu_block entry, RDOQ, intra_bits_qt
+    fine_align(c); fine_align(c); fine_align(c); fine_align(c);             // the stages inside code_tu_block
+  }
   else
   {
     FHC_NOUNROLL for (int i = 0; i < 4; i++) ghost_first_pass(c, log2n - 1);
@@ -2116,8 +2214,8 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
         bestPUCost = wg->eng.resCost; bestPUDist = wg->eng.resDist; bestPUMode = rdModeList[wg->eng.resTask];
         par_copy16(c, cuCoef + partOffset * 16, wg->bestCoef[0], n * n);
         par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, wg->bestReco[0], n, n, n);
-        copy_bytes(s->qtTrIdx, wg->bestTrIdx, puParts);
-        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], wg->bestCbf[j], puParts); copy_bytes(s->qtTs[j], wg->bestTs[j], puParts); }
+        copy_bytes(g->qtTrIdx, wg->bestTrIdx, puParts);
+        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(g->qtCbf[j], wg->bestCbf[j], puParts); copy_bytes(g->qtTs[j], wg->bestTs[j], puParts); }
       }
       // second pass: a 4x4 PU cannot split, re-coding the best mode reproduces the same cost (never strictly smaller)
       firstSerial = (log2pu == 2) ? numModesForFullRD + 1 : numModesForFullRD;
@@ -2131,7 +2229,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       uint32_t puDist = 0;
       double puCost = 0.0;
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
-      sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
+      sb_copy(c, e->go, slot_of(c, depth, CI_CURR_BEST));
       if (second && log2pu >= 3 && log2pu <= 5)
       {
         FHC_TIC(sp);
@@ -2149,13 +2247,13 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       {
         bestPUMode = orgMode; bestPUDist = puDist; bestPUCost = puCost;
         set_luma_result(c, cu, cuCoef, cuReco, partOffset, log2pu, initTrDepth);
-        copy_bytes(s->qtTrIdx, cu->tridx + partOffset, puParts);
-        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(s->qtCbf[j], cu->cbf[j] + partOffset, puParts); copy_bytes(s->qtTs[j], cu->ts[j] + partOffset, puParts); }
+        copy_bytes(g->qtTrIdx, cu->tridx + partOffset, puParts);
+        FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(g->qtCbf[j], cu->cbf[j] + partOffset, puParts); copy_bytes(g->qtTs[j], cu->ts[j] + partOffset, puParts); }
       }
     }
     overallDist += bestPUDist;
-    copy_bytes(cu->tridx + partOffset, s->qtTrIdx, puParts);
-    FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(cu->cbf[j] + partOffset, s->qtCbf[j], puParts); copy_bytes(cu->ts[j] + partOffset, s->qtTs[j], puParts); }
+    copy_bytes(cu->tridx + partOffset, g->qtTrIdx, puParts);
+    FHC_NOUNROLL for (int j = 0; j < 3; j++) { copy_bytes(cu->cbf[j] + partOffset, g->qtCbf[j], puParts); copy_bytes(cu->ts[j] + partOffset, g->qtTs[j], puParts); }
     if (pu != numPU - 1)
       par_copy2d(c, g->rec[0] + poy * ps + pox, ps, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, puSize, puSize);
     set_range(cu->ldir, partOffset, puParts, (int)bestPUMode);
@@ -2169,7 +2267,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
     }
     FHC_NOUNROLL for (int i = 0; i < 4 * puParts; i++) { cu->cbf[0][i] |= (uint8_t)cY; cu->cbf[1][i] |= (uint8_t)cU; cu->cbf[2][i] |= (uint8_t)cV; }
   }
-  sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
+  sb_copy(c, e->go, slot_of(c, depth, CI_CURR_BEST));
   cu->dist = overallDist;
 }
 
@@ -2203,9 +2301,10 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
       uint32_t singleDist = 0, singleCbf = 0;
       int bestMode = 0, bestTS = 0, currMode = 0;
       const int total = checkTS ? 2 : 1;
-      int16_t* qtCoefBlk = e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4;
-      int16_t* qtRecBlk = e->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1);
-      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), &e->go);
+      const int qsc = e->qs >> 1;
+      int16_t* qtCoefBlk = qt_coef(e, 5 - log2n) + e->coff[cc] + ridx * 4;
+      int16_t* qtRecBlk = qt_rec(e, 5 - log2n) + e->coff[cc] + (rel_y(s, ridx) >> 1) * qsc + (rel_x(s, ridx) >> 1);
+      sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
       FHC_NOUNROLL for (int tsId = 0; tsId < total; tsId++)
       {
         const int isOne = total == 1;
@@ -2226,11 +2325,11 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
           singleCost = costTmp; singleDist = dTmp; bestTS = tsId; bestMode = currMode; singleCbf = cbfTmp;
           if (!isOne && !isLast)
           {
-            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[cc][i] = qtCoefBlk[i]; e->tsRec[cc][i] = qtRecBlk[(i >> 2) * 32 + (i & 3)]; }
-            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), &e->go);
+            FHC_NOUNROLL for (int i = 0; i < 16; i++) { e->tsCoef[cc][i] = qtCoefBlk[i]; e->tsRec[cc][i] = qtRecBlk[(i >> 2) * qsc + (i & 3)]; }
+            sb_copy(c, slot_of(c, fullDepth, CI_TEMP_BEST), e->go);
           }
         }
-        if (!isOne && !isLast) sb_copy(c, &e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
+        if (!isOne && !isLast) sb_copy(c, e->go, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT));
       }
       if (bestMode < total)
       {
@@ -2239,11 +2338,11 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
         FHC_NOUNROLL for (int i = 0; i < 16; i++)
         {
           qtCoefBlk[i] = e->tsCoef[cc][i];
-          qtRecBlk[(i >> 2) * 32 + (i & 3)] = e->tsRec[cc][i];
+          qtRecBlk[(i >> 2) * qsc + (i & 3)] = e->tsRec[cc][i];
           if (e->writePic) picBlk[(i >> 2) * ps + (i & 3)] = e->tsRec[cc][i];
         }
         set_range(cu->cbf[cc], ridx, nparts, (int)(singleCbf << trDepth));
-        sb_copy(c, &e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
+        sb_copy(c, e->go, slot_of(c, fullDepth, CI_TEMP_BEST));
       }
       set_range(cu->ts[cc], ridx, nparts, bestTS);
       *dist += singleDist;
@@ -2275,9 +2374,9 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
     const int cw = cu->width >> 1;
     FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
-      par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, c.e->qtCoef[5 - log2n] + comp_off(cc) + ridx * 4, n * n);
+      par_copy16(c, cuCoef + comp_off(cc) + ridx * 4, qt_coef(c.e, 5 - log2n) + c.e->coff[cc] + ridx * 4, n * n);
       par_copy2d(c, cuReco + comp_off(cc) + (rel_y(s, ridx) >> 1) * cw + (rel_x(s, ridx) >> 1), cw,
-                 c.e->qtRec[5 - log2n] + comp_off(cc) + (rel_y(s, ridx) >> 1) * 32 + (rel_x(s, ridx) >> 1), 32, n, n);
+                 qt_rec(c.e, 5 - log2n) + c.e->coff[cc] + (rel_y(s, ridx) >> 1) * (c.e->qs >> 1) + (rel_x(s, ridx) >> 1), c.e->qs >> 1, n, n);
     }
   }
   else
@@ -2311,7 +2410,7 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
     {
       par_copy16(c, cuCoef + comp_off(cc), wg->bestCoef[cc], 16);
       par_copy2d(c, cuReco + comp_off(cc), 4, wg->bestReco[cc], 4, 4, 4);
-      copy_bytes(s->qtCbf[cc], wg->bestCbf[cc], nparts); copy_bytes(s->qtTs[cc], wg->bestTs[cc], nparts);
+      copy_bytes(g->qtCbf[cc], wg->bestCbf[cc], nparts); copy_bytes(g->qtTs[cc], wg->bestTs[cc], nparts);
     }
   }
   else
@@ -2321,24 +2420,24 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
     FHC_TIC(cb);
     block_align(c);
     e->noAlign = 1;                                  // the chroma TU tree follows the luma tree of this picture
-    sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
+    sb_copy(c, e->go, slot_of(c, depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, nparts, modeList[mi]);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
-    sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
+    sb_copy(c, e->go, slot_of(c, depth, CI_CURR_BEST));
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
     e->noAlign = 0;
     if (cost < bestCost)
     {
       bestCost = cost; bestDist = dist; bestMode = (uint32_t)modeList[mi];
       set_chroma_result(c, cu, cuCoef, cuReco, 0, log2cu, 0, 1);
-      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(s->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(s->qtTs[cc], cu->ts[cc], nparts); }
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(g->qtCbf[cc], cu->cbf[cc], nparts); copy_bytes(g->qtTs[cc], cu->ts[cc], nparts); }
     }
     FHC_TOC3(c, cb, PF2_CHROMA_BIG);
   }
-  FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], s->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], s->qtTs[cc], nparts); }
+  FHC_NOUNROLL for (int cc = 1; cc < 3; cc++) { copy_bytes(cu->cbf[cc], g->qtCbf[cc], nparts); copy_bytes(cu->ts[cc], g->qtTs[cc], nparts); }
   set_range(cu->cdir, 0, nparts, (int)bestMode);
   cu->dist += bestDist;
-  sb_copy(c, &e->go, slot_of(c, depth, CI_CURR_BEST));
+  sb_copy(c, e->go, slot_of(c, depth, CI_CURR_BEST));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -2483,7 +2582,7 @@ FHC_D void check_rd_cost_intra(const Ctx& c, int depth, int partSize)           
   block_align(c);
   reset_bits(e);
   encode_cu_syntax(c, cu, cuCoef);
-  sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), &e->go);
+  sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), e->go);
   cu->bits = num_bits(e);
   cu->bins = e->bins;
   cu->cost = rd_cost(c, cu->bits, cu->dist);
@@ -2509,13 +2608,13 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       cu_init_est(c, temp_cu(s, depth));
     }
     CUMeta* b = best_cu(s, depth);
-    sb_copy(c, &e->go, slot_of(c, depth, CI_NEXT_BEST));
+    sb_copy(c, e->go, slot_of(c, depth, CI_NEXT_BEST));
     reset_bits(e);
     code_split_flag(c, b, 0, depth);
     b->bits += num_bits(e);
     b->bins += e->bins;
     b->cost = rd_cost(c, b->bits, b->dist);
-    sb_copy(c, slot_of(c, depth, CI_NEXT_BEST), &e->go);
+    sb_copy(c, slot_of(c, depth, CI_NEXT_BEST), e->go);
   }
   if (depth < 3)
   {
@@ -2546,7 +2645,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
         }
       }
     }
-    sb_copy(c, &e->go, slot_of(c, nd, CI_NEXT_BEST));
+    sb_copy(c, e->go, slot_of(c, nd, CI_NEXT_BEST));
     if (!boundary)
     {
       reset_bits(e);
@@ -2555,7 +2654,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
       t->bins += e->bins;
     }
     t->cost = rd_cost(c, t->bits, t->dist);
-    sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), &e->go);
+    sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), e->go);
     check_best_mode(c, depth);
   }
   cu_copy_to_pic(c, best_cu(s, depth), 1);
@@ -2609,14 +2708,19 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
   Engine* m = &s->master;
   s->t = tables;
   m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0;
-  m->refU = s->refU; m->refF = s->refF; m->flags = s->flags;
-  bind_coef_scratch(m, &s->cs);
-  m->predYuv = g->predYuv; m->qtRec = g->qtRec; m->qtCoef = g->qtCoef; m->writePic = 1;
-  m->costCGSig = s->costCGSig; m->cgFlag = s->cgFlag; m->cgFlagCode = s->cgFlagCode; m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta;
+  m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->go = &s->masterGo;
+  m->csSmall = &s->u.cs; m->csLarge = &g->big;
+  bind_coef_scratch(m, &s->u.cs);
+  m->predYuv = g->predYuv; m->qtRecBase = &g->qtRec[0][0]; m->qtCoefBase = &g->qtCoef[0][0]; m->writePic = 1;
+  m->layerSize = 6144; m->qs = 64; m->coff[0] = 0; m->coff[1] = 4096; m->coff[2] = 5120;
+  m->costCGSig = s->costCGSig; m->cgFlag = s->cgFlag; m->cgFlagCode = s->cgFlagCode; m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta; m->cgNzMask = s->cgNzMask; m->cgAbs = s->cgAbs;
   {
-    uint8_t* st = s->cuStore;
+    uint8_t* st = g->cuStoreBig;
     FHC_NOUNROLL for (int d = 0; d < 4; d++)
+    {
+      if (d == 2) st = s->cuStore;
       FHC_NOUNROLL for (int b = 0; b < 2; b++) { cu_bind(&s->cu[d][b], st, 256 >> (2 * d)); st += 12 * (256 >> (2 * d)); }
+    }
   }
   FHC_NOUNROLL for (int i = 0; i < FHC_NENG; i++)
   {
@@ -2624,9 +2728,16 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
     Engine* e = &x->eng;
     e->kind = ENG_LANE; e->t = tables; e->slots = x->slots; e->noAlign = 1;
     e->refU = x->refU; e->refF = x->refF; e->flags = x->flags;
+#if FHC_LANE_SMEM
+    e->go = &s->laneGo[i]; e->csSmall = &s->u.laneCs[i];
+#else
+    e->go = &x->go; e->csSmall = &x->cs16;
+#endif
+    e->csLarge = &x->cs;
     bind_coef_scratch(e, &x->cs);
-    e->predYuv = x->predYuv; e->qtRec = x->qtRec; e->qtCoef = x->qtCoef; e->writePic = 0;
-    e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->sigC0 = x->sigC0; e->sigC1 = x->sigC1; e->sigDelta = x->sigDelta;
+    e->predYuv = x->predYuv; e->qtRecBase = &x->qtRec[0][0]; e->qtCoefBase = &x->qtCoef[0][0]; e->writePic = 0;
+    e->layerSize = 96; e->qs = 8; e->coff[0] = 0; e->coff[1] = 64; e->coff[2] = 80;
+    e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->sigC0 = x->sigC0; e->sigC1 = x->sigC1; e->sigDelta = x->sigDelta; e->cgNzMask = x->cgNzMask; e->cgAbs = x->cgAbs;
     cu_bind(&x->cu, x->cuStore, 4);
   }
 }
@@ -2664,13 +2775,13 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     const int puParts = np >> (2 * td.initTrDepth);
     const int layer = 5 - td.log2pu, n = 1 << td.log2pu;
     set_range(cu->ldir, td.partOffset, puParts, mode);
-    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
     if (firstOfDispatch || cost < e->resCost)
     {
       e->resCost = cost; e->resDist = dist; e->resTask = t;
-      par_copy16(c, eg->bestCoef[0], e->qtCoef[layer] + td.partOffset * 16, n * n);
-      par_copy2d(c, eg->bestReco[0], n, e->qtRec[layer] + rel_y(s, td.partOffset) * 64 + rel_x(s, td.partOffset), 64, n, n);
+      par_copy16(c, eg->bestCoef[0], qt_coef(e, layer) + td.partOffset * 16, n * n);
+      par_copy2d(c, eg->bestReco[0], n, qt_rec(e, layer) + rel_y(s, td.partOffset) * e->qs + rel_x(s, td.partOffset), e->qs, n, n);
       FHC_NOUNROLL for (int i = 0; i < puParts; i++)
       {
         eg->bestTrIdx[i] = cu->tridx[td.partOffset + i];
@@ -2683,10 +2794,10 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     // one iteration of the chroma mode loop of estIntraPredChromaQT (TEncSearch.cpp:2612-2648)
     uint32_t dist = 0;
     const int log2cu = ilog2(cu->width);
-    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     set_range(cu->cdir, 0, np, mode);
     recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
-    sb_copy(c, &e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
     const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
     if (firstOfDispatch || cost < e->resCost)
@@ -2694,8 +2805,8 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
       e->resCost = cost; e->resDist = dist; e->resTask = t;
       FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
       {
-        par_copy16(c, eg->bestCoef[cc], e->qtCoef[layer] + comp_off(cc), 16);
-        par_copy2d(c, eg->bestReco[cc], 4, e->qtRec[layer] + comp_off(cc), 32, 4, 4);
+        par_copy16(c, eg->bestCoef[cc], qt_coef(e, layer) + e->coff[cc], 16);
+        par_copy2d(c, eg->bestReco[cc], 4, qt_rec(e, layer) + e->coff[cc], e->qs >> 1, 4, 4);
         FHC_NOUNROLL for (int i = 0; i < np; i++) { eg->bestCbf[cc][i] = cu->cbf[cc][i]; eg->bestTs[cc][i] = cu->ts[cc][i]; }
       }
     }
@@ -2769,16 +2880,16 @@ FHC_D void compress_picture(const Ctx& c)
       par(c, OP_CU_TO_OUT);
       cu_init_est(c, cu);
     }
-    sb_copy(c, &e->go, slot_of(c, 0, CI_CURR_BEST));
+    sb_copy(c, e->go, slot_of(c, 0, CI_CURR_BEST));
     compress_cu(c, 0);
-    sb_copy(c, &e->go, slot_of(c, 0, CI_CURR_BEST));
+    sb_copy(c, e->go, slot_of(c, 0, CI_CURR_BEST));
     reset_bits(e);
     {
       FHC_TIC(en);
       encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
       FHC_TOC2(c, en, PF_ENCODE);
     }
-    sb_copy(c, slot_of(c, 0, CI_CURR_BEST), &e->go);
+    sb_copy(c, slot_of(c, 0, CI_CURR_BEST), e->go);
     par(c, OP_CTU_RECO_OUT);
   }
   FHC_TOC2(c, tot, PF_TOTAL);
