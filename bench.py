@@ -4,12 +4,14 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 A step = one pass of the hot path (TEncCu::xCompressCU and below, for every CTU of every picture) over one batch of
-synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, one
-thread block per (picture, QP) job, `--jobs` jobs per GPU per step (default 148 = one per SM; 256 = the whole config).
-`value` is whole-job fps with the samples already resident in HBM (CUDA-event time of the kernel launches, max over
-ranks); `e2e` is the same through the C ABI with host buffers (pinned H2D of the pictures + D2H of every CTU result
-inside the timed region).  N > 1: one process per GPU (torchrun), every rank encodes its own contiguous frame group,
-no collective on the data path - torch.distributed only provides the barrier and the max over ranks.
+synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, cycled to
+as many (picture, QP) jobs as the persistent kernel keeps in flight (`--jobs`, default fhc_pictures_in_flight = 148 SMs x
+16 pictures per block), one warp per picture.  Every timed step goes through the C ABI with host buffers (pinned H2D
+of the pictures, kernel, D2H of every CTU record): `e2e` is the wall time of that, `value` the CUDA-event time of the
+kernel inside the same steps (inputs resident in HBM when it starts), max over ranks.  N > 1: one process per GPU
+(torchrun), every rank encodes its own contiguous frame group, no collective on the data path -
+torch.distributed only provides the barrier and the max over ranks.  A 1080p picture is one dependent chain of 510 CTUs
+and takes minutes whatever the batch size, so a step takes minutes; warm-up steps use 1920x72 strips.
 
 `--impl reference` times the UNMODIFIED reference encoder (oracle/_ref/TAppEncoder, HM 16.14 with the OpenCV dump
 stubbed) on the host cores: one process per core, one 1080p picture each per step.
@@ -33,6 +35,8 @@ CTUS = 30 * 17
 # algorithmic bytes per CTU = 6144 source + 12288 reconstruction + 12288 levels + ~6 KB metadata
 ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
 INT_OPS_PER_CTU = 40.0e6            # SURVEY.md 8(d) W_ctu (integer-equivalent ops, content dependent)
+WARM_H = 72                         # height of the warm-up strips
+NCU_DRAM_BYTES_PER_CTU = (223.78e9 + 151.52e9) / 2368     # profiles/r01_v3_aligned_w16_loaded.md
 
 
 def load_peaks():
@@ -90,90 +94,101 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_jobs = args.jobs if args.jobs > 0 else fh.pictures_in_flight(local_rank)
     # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
     first, last = frame_group(CLIP * world, rank, world)
-    jobs = job_list(first, last - first, args.jobs)
-    frames_needed = sorted({f for f, _ in jobs})
-    # distinct synthetic pictures are expensive to synthesise on the host; 8 distinct pictures per rank, cycled
-    distinct = frames_needed[:8]
-    Y, U, V = synth_frames(W, H, len(distinct), first_frame=distinct[0])
-    enc = fh.Encoder(W, H, 8, max_frames=args.jobs, device=local_rank)
-    host_in = enc.pinned_array((args.jobs, enc.frame_samples), np.uint8)
-    packed = enc.pack_frames(Y, U, V)
-    for j, (f, _) in enumerate(jobs):
-        host_in[j] = packed[(f - first) % len(distinct)]
+    jobs = job_list(first, last - first, n_jobs)
+    # distinct synthetic pictures are expensive to synthesise on the host: 8 distinct pictures per rank, cycled
+    n_distinct = 8
+    Y, U, V = synth_frames(W, H, n_distinct, first_frame=first)
     sps = [fh.slice_params_from_qp(q) for _, q in jobs]
-    host_out = enc.pinned_array((args.jobs, enc.num_ctus), fh.CTU_RESULT_DTYPE)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        return enc.run_resident(sps)                       # CUDA events around the launch, on the library's stream
+    # ---- warm-up: the same kernel, the same number of pictures, on 1920x72 strips (one full CTU row + the 8-line bottom
+    # row) of the same content: a full 1080p step takes minutes because a picture is one dependent chain of 510 CTUs
+    wenc = fh.Encoder(W, WARM_H, 8, max_frames=n_jobs, device=local_rank)
+    wpacked = wenc.pack_frames(Y[:, :WARM_H], U[:, :WARM_H // 2], V[:, :WARM_H // 2])
+    whost = wenc.pinned_array((n_jobs, wenc.frame_samples), np.uint8)
+    for j, (f, _) in enumerate(jobs):
+        whost[j] = wpacked[(f - first) % n_distinct]
+    wout = np.zeros(wenc.num_ctus, fh.CTU_RESULT_DTYPE)
+    for _ in range(args.warmup):
+        wenc.submit(whost, sps)
+        wenc.fetch_picture(n_jobs - 1, wout)
+    wenc.close()
 
-    def step_e2e():
-        t0 = time.perf_counter()
-        enc.submit(host_in, sps)                           # pinned H2D + launch
-        for j in range(args.jobs):
-            enc.fetch_picture(j, host_out[j])              # D2H of every CTU record
-        return (time.perf_counter() - t0) * 1e3
+    enc = fh.Encoder(W, H, 8, max_frames=n_jobs, device=local_rank)
+    host_in = enc.pinned_array((n_jobs, enc.frame_samples), np.uint8)
+    packed = enc.pack_frames(Y, U, V)
+    for j, (f, _) in enumerate(jobs):
+        host_in[j] = packed[(f - first) % n_distinct]
+    host_out = enc.pinned_array((enc.num_ctus,), fh.CTU_RESULT_DTYPE)      # one picture's records, reused
+    rec_bytes = int(host_out.nbytes)
 
-    # inputs resident in HBM: one upload outside the timed region
-    enc.submit(host_in, sps)
-    enc.fetch_picture(0, host_out[0])                      # = warm-up step 1 (also checks the launch)
-    for _ in range(max(0, args.warmup - 1)):
-        step_resident()
+    # ---- timed region: K steps through the C ABI with host buffers (pinned H2D of every picture, kernel, D2H of every
+    # CTU record).  `value` uses the CUDA-event time of the kernel of the same steps (inputs resident when it starts).
     sampler = ClockSampler(local_rank)
+    launches0 = int(enc.lib.fhc_launch_count())
+    check_bits, kernel_ms = 0, []
     sampler.start()
     barrier()
-    t_wall0 = time.perf_counter()
-    kernel_ms = [step_resident() for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        enc.submit(host_in, sps)
+        for j in range(n_jobs):
+            enc.fetch_picture(j, host_out)
+            check_bits += int(host_out["totalBits"].sum(dtype=np.int64))
+        kernel_ms.append(enc.last_kernel_ms())
     barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    e2e_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
-    launches = int(enc.lib.fhc_launch_count())
-    # e2e: the same step through submit/fetch with host buffers
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    barrier()
-    e2e_ms = [step_e2e() for _ in range(e2e_steps)]
-    barrier()
-    check_bits = int(host_out["totalBits"].sum())
+    launches = int(enc.lib.fhc_launch_count()) - launches0
     enc.close()
 
     my_ms = float(np.sum(kernel_ms))
-    my_e2e = float(np.sum(e2e_ms))
     if dist is not None:
-        t = torch.tensor([my_ms, my_e2e, wall_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([my_ms, e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        my_ms, my_e2e, wall_ms = [float(v) for v in t.tolist()]
+        my_ms, e2e_ms = [float(v) for v in t.tolist()]
     if rank == 0:
-        total_jobs = args.jobs * world
+        total_jobs = n_jobs * world
         ms_per_step = my_ms / args.steps
+        print("bench: %d jobs/GPU x %d GPU(s), kernel %.1f ms/step, e2e %.1f ms/step" % (n_jobs, world, ms_per_step, e2e_ms / args.steps),
+              file=sys.stderr, flush=True)
         fps = total_jobs / (ms_per_step / 1e3)
-        e2e_fps = total_jobs / (my_e2e / e2e_steps / 1e3)
+        e2e_fps = total_jobs / (e2e_ms / args.steps / 1e3)
         peak, peak_src = load_peaks()
-        achieved = ALGO_BYTES_PER_CTU * CTUS * args.jobs / (ms_per_step / 1e3) / 1e9      # per launch (= per rank)
+        ctus_per_launch = CTUS * n_jobs
+        achieved = ALGO_BYTES_PER_CTU * ctus_per_launch / (ms_per_step / 1e3) / 1e9      # per launch (= per rank)
         line = {
-            "metric": "1080p all-intra encode fps (byte-identical CTU decisions)", "value": round(fps, 4), "unit": "frames/s",
+            "metric": "1080p all-intra encode fps (byte-identical CTU decisions)" if (W, H) == (1920, 1080) else "SELF-TEST %dx%d (not the metric)" % (W, H),
+            "value": round(fps, 4), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64 (u8 samples, i16 levels)",
             "data": "synthetic",
-            "config": {"workload": "encoder_intra_main.cfg 1920x1080 8-bit, 64-frame synthetic clip per GPU x QP{22,27,32,37}; "
-                                   "%d picture jobs per GPU per step, one thread block per picture" % args.jobs,
-                       "jobs_per_gpu": args.jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective" % world,
-                       "l2_policy": "inputs+results per step (%.0f MB) exceed the 126 MB L2" % (args.jobs * (3.1 + 14.0))},
+            "config": {"workload": "encoder_intra_main.cfg %dx%d 8-bit, 64-frame synthetic clip per GPU x QP{22,27,32,37}, cycled to " % (W, H) +
+                                   "%d picture jobs per GPU per step (= the pictures the persistent kernel keeps in flight, one warp "
+                                   "each); warm-up steps run the same kernel and job count on %dx%d strips" % (n_jobs, W, WARM_H),
+                       "jobs_per_gpu": n_jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective" % world,
+                       "l2_policy": "inputs+results per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (n_jobs * (3.1 + 14.1) / 1e3)},
             "ctu_per_s": round(fps * CTUS, 1),
             "e2e": {"value": round(e2e_fps, 4), "unit": "frames/s", "h2d_bytes_per_step": int(host_in.nbytes) * world,
-                    "d2h_bytes_per_step": int(host_out.nbytes) * world, "steps": e2e_steps},
+                    "d2h_bytes_per_step": rec_bytes * n_jobs * world, "ms_per_step": round(e2e_ms / args.steps, 2)},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "latency/issue-bound integer+fp64 decision kernel: HBM is not the limiter (SURVEY 8d); "
-                                 "integer-equivalent work %.2f Gop/s vs ~37,000 Gop/s nominal int32 issue" % (INT_OPS_PER_CTU * fps * CTUS / world / 1e9)},
-            "wall_ms_timed_region": round(wall_ms, 1), "check_total_bits": check_bits,
+                         "traffic": round(NCU_DRAM_BYTES_PER_CTU * ctus_per_launch), "peak_source": peak_src,
+                         "traffic_note": "dram read+write of profiles/r01_v3_aligned_w16_loaded.md (2368 one-CTU pictures) scaled "
+                                         "by the CTUs of this launch: scratch and stack spill traffic, ~4300x the algorithmic bytes",
+                         "note": "the kernel is bound by instruction delivery and memory latency of one dependent chain per "
+                                 "picture, not by HBM or the tensor pipe (DESIGN.md 4): ncu issue-slot utilisation 18.7 %%; "
+                                 "integer-equivalent work %.1f Gop/s of ~37,000 Gop/s nominal int32 issue"
+                                 % (INT_OPS_PER_CTU * fps * CTUS / world / 1e9)},
+            "check_total_bits": check_bits,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(1, 0)
@@ -254,10 +269,13 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--jobs", type=int, default=148, help="picture jobs per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--jobs", type=int, default=0, help="picture jobs per GPU per step (0 = pictures the kernel keeps in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")
     args = ap.parse_args()
+    global W, H, CTUS
+    W, H = [int(v) for v in args.size.split("x")]
+    CTUS = ((W + 63) // 64) * ((H + 63) // 64)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

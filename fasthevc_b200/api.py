@@ -38,7 +38,7 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
 
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
-           "fhc_last_error", "fhc_launch_count"]
+           "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight"]
 
 
 def library_path():
@@ -80,10 +80,20 @@ def load_library():
     lib.fhc_run_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SliceParams), C.POINTER(C.c_float)]
     lib.fhc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.fhc_host_free.argtypes = [C.c_void_p]
+    lib.fhc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.fhc_pictures_in_flight.argtypes = [C.c_int]
     lib.fhc_last_error.restype = C.c_char_p
     lib.fhc_launch_count.restype = C.c_uint64
     _lib = lib
     return lib
+
+
+def pictures_in_flight(device=0):
+    """Pictures the persistent kernel keeps in flight on `device` (a submit of that many fills the GPU)."""
+    n = load_library().fhc_pictures_in_flight(int(device))
+    if n <= 0:
+        raise FhcError("fhc_pictures_in_flight(%d) -> %d: %s" % (device, n, (load_library().fhc_last_error() or b"").decode()))
+    return n
 
 
 def slice_params_from_qp(qp):
@@ -164,6 +174,11 @@ class Encoder:
         p, b = C.c_void_p(), C.c_uint64()
         self._check(self.lib.fhc_device_input(self.ctx, C.byref(p), C.byref(b)), "fhc_device_input")
         return p.value, b.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.fhc_last_kernel_ms(self.ctx, C.byref(ms)), "fhc_last_kernel_ms")
+        return ms.value
 
     def run_resident(self, slice_params):
         n = len(slice_params)

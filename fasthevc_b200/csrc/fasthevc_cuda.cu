@@ -285,6 +285,30 @@ int fhc_run_resident(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params*
   return FHC_OK;
 }
 
+int fhc_last_kernel_ms(fhc_ctx* c, float* kernel_ms)
+{
+  if (!c || !kernel_ms) return FHC_ERR_ARG;
+  if (c->nSubmitted == 0) return FHC_ERR_STATE;
+  CK(cudaSetDevice(c->device));
+  int rc = wait_done(c);
+  if (rc != FHC_OK) return rc;
+  CK(cudaEventElapsedTime(kernel_ms, c->evStart, c->evStop));
+  return FHC_OK;
+}
+
+int fhc_pictures_in_flight(int device)
+{
+  int ndev = 0, perSm = 0;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return FHC_ERR_ARG;
+  CK(cudaSetDevice(device));
+  CK(cudaGetDeviceProperties(&prop, device));
+  CK(cudaFuncSetAttribute(fhc_compress_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kernel_smem_bytes()));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_compress_pictures_kernel, FHC_BLOCK_THREADS, kernel_smem_bytes()));
+  return prop.multiProcessorCount * perSm * FHC_PICS_PER_BLOCK;
+}
+
 int fhc_host_alloc(void** p, uint64_t bytes)
 {
   if (!p) return FHC_ERR_ARG;

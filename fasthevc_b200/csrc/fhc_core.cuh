@@ -389,6 +389,14 @@ FHC_DH void block_align(const Ctx& c)
   (void)c;
 #endif
 }
+#ifndef FHC_ALIGN_LEVEL
+#define FHC_ALIGN_LEVEL 2        /* 1: routine entries only; 2: + RDOQ and bit counting inside a TU; FHC_FINE_ALIGN: + every stage */
+#endif
+#if FHC_ALIGN_LEVEL >= 2
+FHC_DH void mid_align(const Ctx& c) { block_align(c); }
+#else
+FHC_DH void mid_align(const Ctx& c) { (void)c; }
+#endif
 #ifdef FHC_FINE_ALIGN
 FHC_DH void fine_align(const Ctx& c) { block_align(c); }
 #else
@@ -401,6 +409,7 @@ FHC_DH void release_followers(const Ctx& c)
 #else
 FHC_DH void group_sync(const Ctx& c) { (void)c; }
 FHC_DH void block_align(const Ctx& c) { (void)c; }
+FHC_DH void mid_align(const Ctx& c) { (void)c; }
 FHC_DH void fine_align(const Ctx& c) { (void)c; }
 // emulation: the group's lanes are executed one after the other, phase by phase
 FHC_DH void par(const Ctx& c, int op)
@@ -539,6 +548,34 @@ FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v, int nw)
 #endif
   (void)nw;
   *p += v;
+}
+
+// One stage of a separable NxN transform executed by ONE lane (lane engines, N <= 8): out[k][j] = (sum_q M(k,q) * in[j][q]
+// + add) >> shift with the input row held in registers (N loads per row instead of N per output).  inverse: M(q,k)
+// and clipping to 16 bits (TComTrQuant.cpp:860-985).  Same sums in the same order as the striped phases.
+template <typename TIn, typename TOut>
+FHC_DH void lane_transform_stage(const Tables& t, int n, int useDst, int inverse, const TIn* in, TOut* out, int add, int shift)
+{
+  for (int j = 0; j < n; j++)
+  {
+    int r[8];
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; q++) r[q] = q < n ? (int)(inverse ? in[q * n + j] : in[j * n + q]) : 0;
+    for (int k = 0; k < n; k++)
+    {
+      int acc = 0;
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll
+#endif
+      for (int q = 0; q < 8; q++)
+        if (q < n) acc += (inverse ? tcoefm(t, n, q, k, useDst) : tcoefm(t, n, k, q, useDst)) * r[q];
+      const int v = (acc + add) >> shift;
+      if (inverse) out[j * n + k] = (TOut)clip3(-32768, 32767, v);
+      else out[k * n + j] = (TOut)v;
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -712,6 +749,7 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     {
       // xTrMxN first stage (TComTrQuant.cpp:860): rows -> tmp[k][j]
       const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
+      if (nw == 1 && n <= 8) { lane_transform_stage(*s->t, n, a[1], 0, e->resi, e->tmp, add1, shift1); break; }
       for (int i = w; i < n2; i += nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
@@ -723,6 +761,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
     else if (phase == 1)
     {
       const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
+      if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[1], 0, e->tmp, e->tcoef, add2, shift2);
+      else
       for (int i = w; i < n2; i += nw)
       {
         const int k = i >> log2n, j = i & (n - 1);
@@ -793,6 +833,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         else
         {
           // xITrMxN first stage (TComTrQuant.cpp:927): columns -> lvlD[j][i] (reused as scratch)
+          if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->tcoef, e->lvlD, 64, 7);
+          else
           for (int i = w; i < n2; i += nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
@@ -807,6 +849,8 @@ FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
         if (!a[3])
         {
           const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
+          if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->lvlD, e->resi, add2, shift2);
+          else
           for (int i = w; i < n2; i += nw)
           {
             const int j = i >> log2n, q = i & (n - 1);
@@ -1852,7 +1896,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   fine_align(c);
   par(c, OP_FWD_QUANT);
   const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
-  block_align(c);
+  mid_align(c);
   const uint32_t absSum = rdoq_pass(c, cu, relIdx, comp, log2n, cbfCtx);
   set_range(cu->cbf[comp], relIdx, numParts, (absSum > 0 ? 1 : 0) << trDepthBit);
 
@@ -1940,7 +1984,7 @@ FHC_D uint32_t intra_bits_qt(const Ctx& c, const CUMeta* cu, int relIdx, int log
                              int bLuma, int bChroma)
 {
   FHC_TIC(bq);
-  block_align(c);
+  mid_align(c);
   reset_bits(c.e);
   enc_intra_header(c, cu, trDepth, relIdx, bLuma, bChroma);
   enc_subdiv_cbf(c, cu, relIdx, log2n, trDepth, chromaCodeAll, bLuma, bChroma);
@@ -2110,13 +2154,13 @@ FHC_D void ghost_first_pass(const Ctx& c, int log2n)
 {
   if (log2n <= 5)
   {
-    block_align(c); block_align(c); block_align(c);                         // code_tu_block entry, RDOQ, intra_bits_qt
+    block_align(c); mid_align(c); mid_align(c);                             // code_tu_block entry, RDOQ, intra_bits_qt
     fine_align(c); fine_align(c); fine_align(c); fine_align(c);             // the stages inside code_tu_block
   }
   else
   {
     FHC_NOUNROLL for (int i = 0; i < 4; i++) ghost_first_pass(c, log2n - 1);
-    block_align(c);                                                          // intra_bits_qt of the split node
+    mid_align(c);                                                            // intra_bits_qt of the split node
   }
 }
 

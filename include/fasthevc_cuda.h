@@ -103,6 +103,11 @@ int fhc_device_input(fhc_ctx* ctx, void** dptr, uint64_t* bytes);
 /* Runs the decision kernel on n pictures whose samples are already in the device input
  * buffer; returns after the kernel finished; *kernel_ms = CUDA-event time of the launch. */
 int fhc_run_resident(fhc_ctx* ctx, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms);
+/* CUDA-event time of the kernel of the last submit (waits for it to finish). */
+int fhc_last_kernel_ms(fhc_ctx* ctx, float* kernel_ms);
+/* Number of pictures the persistent kernel encodes concurrently on `device` (SMs x resident blocks x pictures per
+ * block): submits of at least this many pictures keep the whole device busy.  Negative = error. */
+int fhc_pictures_in_flight(int device);
 /* Page-locked host buffers for submit/fetch (optional; any host memory works). */
 int fhc_host_alloc(void** p, uint64_t bytes);
 int fhc_host_free(void* p);
