@@ -66,7 +66,8 @@ enum {
 #ifndef FHC_GROUP
 #define FHC_GROUP 32             /* lanes per picture: a warp encodes 32 / FHC_GROUP pictures side by side (sub-warp groups serialise) */
 #endif
-#define FHC_MAX_TASKS 10         /* the longest candidate list (8 RMD survivors + 2 MPMs) */
+#define FHC_MAX_MODES 10         /* the longest candidate list (8 RMD survivors + 2 MPMs) */
+#define FHC_MAX_TASKS 20         /* ... times the transform-skip pair of a 4x4 PU */
 #ifndef FHC_LANE_SMEM
 #define FHC_LANE_SMEM 0           /* 1: lane engines keep their CABAC state and 4x4 scratch in shared memory (costs L1) */
 #endif
@@ -171,6 +172,7 @@ struct Engine
   int16_t *qtRecBase, *qtCoefBase;
   int layerSize, qs, coff[3];
   int writePic;                   // reconstruct into the picture plane too (master only)
+  int forceTs;                    // >= 0: evaluate only this transform_skip_flag of a 4x4 luma TU (lane tasks of a 4x4 PU)
   int noAlign;                    // inside a section whose TU count depends on the picture: no block alignment
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
   double* costCGSig;              // RDOQ per-group / per-context scratch
@@ -251,7 +253,8 @@ struct TaskDesc
   int kind, numTasks;
   int depth, bufIdx;              // the CU under test: s->cu[depth][bufIdx]
   int partOffset, log2pu, initTrDepth;
-  int mode[FHC_MAX_TASKS];
+  int tsSplit;                     // 4x4 PU: task t = candidate t >> 1 with transform_skip_flag = t & 1
+  int mode[FHC_MAX_MODES];
 };
 
 struct FrameParams                 // hot read-only copy of the picture header (shared memory)
@@ -582,306 +585,336 @@ FHC_DH void lane_transform_stage(const Tables& t, int n, int useDst, int inverse
 // COOP phases (striped over the lanes of the calling group: w = lane index, nw = group size)
 // ----------------------------------------------------------------------------------------------
 // cmd.a[] conventions are documented at each master call site ("par_*" helpers below).
-FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
+// one copy per heavy operation: a phase call saves only the registers that operation needs
+FHC_D void phase_refs(const Ctx& c, int phase, int w, int nw)
 {
-  FrameGlobal* g = c.g;
-  Shared* s = c.s;
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
   Engine* e = c.e;
   const int* a = e->cmd.a;
-  switch (op)
+  // a0 comp, a1 n, a2 nu, a3 us, a4 plane offset of the block origin, a5 wantFilt, a6 numAvail, a7 total units
+  const int comp = a[0], n = a[1], nu = a[2], us = a[3], org0 = a[4], total = a[7];
+  const int stride = plane_stride(s, comp);
+  const int16_t* origin = g->rec[comp] + org0;
+  if (phase == 0)
   {
-  case OP_REFS:
-  {
-    // a0 comp, a1 n, a2 nu, a3 us, a4 plane offset of the block origin, a5 wantFilt, a6 numAvail, a7 total units
-    const int comp = a[0], n = a[1], nu = a[2], us = a[3], org0 = a[4], total = a[7];
-    const int stride = plane_stride(s, comp);
-    const int16_t* origin = g->rec[comp] + org0;
-    if (phase == 0)
+    const int dc = 1 << (s->fp.bitDepth - 1);
+    for (int i = w; i < 4 * n + 1; i += nw)
     {
-      const int dc = 1 << (s->fp.bitDepth - 1);
+      // unit of this sample: left part bottom-up, corner, top part
+      int uidx = i < 2 * n ? i / us : (i == 2 * n ? 2 * nu : 2 * nu + 1 + (i - 2 * n - 1) / us);
+      int v;
+      if (a[6] == 0) v = dc;
+      else
+      {
+        int src = i;
+        if (!e->flags[uidx])
+        {
+          int j = uidx - 1;
+          while (j >= 0 && !e->flags[j]) j--;
+          if (j >= 0) src = j < 2 * nu ? (j * us + us - 1) : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us + us - 1);
+          else
+          {
+            j = uidx + 1;
+            while (j < total && !e->flags[j]) j++;
+            src = j < 2 * nu ? j * us : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us);
+          }
+        }
+        if (src < 2 * n) v = origin[(2 * n - 1 - src) * stride - 1];
+        else if (src == 2 * n) v = origin[-stride - 1];
+        else v = origin[-stride + (src - 2 * n - 1)];
+      }
+      e->refU[i] = (int16_t)v;
+    }
+  }
+  else
+  {
+    // DC value of the unfiltered line + optional smoothing (TComPattern.cpp:191-296)
+    const int16_t* line = e->refU;
+    if (w == 0)
+    {
+      int sum = 0;
+      for (int i = 0; i < n; i++) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
+      e->refDc = (sum + n) / (n + n);
+    }
+    if (a[5])
+    {
+      const int bl = line[0], tl = line[2 * n], tr = line[4 * n];
+      int strong = (comp == 0) && n >= 32;
+      if (strong)
+      {
+        const int thr = 1 << (s->fp.bitDepth - 5);
+        strong = (iabs((bl + tl) - 2 * line[n]) < thr) && (iabs((tl + tr) - 2 * line[3 * n]) < thr);
+      }
+      const int shift = ilog2(2 * n);
       for (int i = w; i < 4 * n + 1; i += nw)
       {
-        // unit of this sample: left part bottom-up, corner, top part
-        int uidx = i < 2 * n ? i / us : (i == 2 * n ? 2 * nu : 2 * nu + 1 + (i - 2 * n - 1) / us);
         int v;
-        if (a[6] == 0) v = dc;
-        else
+        if (i == 0 || i == 4 * n) v = line[i];
+        else if (strong)
         {
-          int src = i;
-          if (!e->flags[uidx])
-          {
-            int j = uidx - 1;
-            while (j >= 0 && !e->flags[j]) j--;
-            if (j >= 0) src = j < 2 * nu ? (j * us + us - 1) : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us + us - 1);
-            else
-            {
-              j = uidx + 1;
-              while (j < total && !e->flags[j]) j++;
-              src = j < 2 * nu ? j * us : (j == 2 * nu ? 2 * n : 2 * n + 1 + (j - 2 * nu - 1) * us);
-            }
-          }
-          if (src < 2 * n) v = origin[(2 * n - 1 - src) * stride - 1];
-          else if (src == 2 * n) v = origin[-stride - 1];
-          else v = origin[-stride + (src - 2 * n - 1)];
+          if (i < 2 * n) v = (((2 * n - i) * bl) + (i * tl) + n) >> shift;
+          else if (i == 2 * n) v = line[i];
+          else v = (((2 * n - (i - 2 * n)) * tl) + ((i - 2 * n) * tr) + n) >> shift;
         }
-        e->refU[i] = (int16_t)v;
+        else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
+        e->refF[i] = (int16_t)v;
       }
     }
-    else
-    {
-      // DC value of the unfiltered line + optional smoothing (TComPattern.cpp:191-296)
-      const int16_t* line = e->refU;
-      if (w == 0)
-      {
-        int sum = 0;
-        for (int i = 0; i < n; i++) sum += line[2 * n + 1 + i] + line[2 * n - 1 - i];
-        e->refDc = (sum + n) / (n + n);
-      }
-      if (a[5])
-      {
-        const int bl = line[0], tl = line[2 * n], tr = line[4 * n];
-        int strong = (comp == 0) && n >= 32;
-        if (strong)
-        {
-          const int thr = 1 << (s->fp.bitDepth - 5);
-          strong = (iabs((bl + tl) - 2 * line[n]) < thr) && (iabs((tl + tr) - 2 * line[3 * n]) < thr);
-        }
-        const int shift = ilog2(2 * n);
-        for (int i = w; i < 4 * n + 1; i += nw)
-        {
-          int v;
-          if (i == 0 || i == 4 * n) v = line[i];
-          else if (strong)
-          {
-            if (i < 2 * n) v = (((2 * n - i) * bl) + (i * tl) + n) >> shift;
-            else if (i == 2 * n) v = line[i];
-            else v = (((2 * n - (i - 2 * n)) * tl) + ((i - 2 * n) * tr) + n) >> shift;
-          }
-          else v = (line[i - 1] + 2 * line[i] + line[i + 1] + 2) >> 2;
-          e->refF[i] = (int16_t)v;
-        }
-      }
-    }
-    break;
   }
-  case OP_RMD:
+}
+
+// one copy per heavy operation: a phase call saves only the registers that operation needs
+FHC_D void phase_rmd(const Ctx& c, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
+  // a0 log2n, a1 org plane offset, a2 modes per group; phases alternate predict(group) / satd(group)
+  const int log2n = a[0], n = 1 << log2n, n2 = n * n, mpg = a[2];
+  const int grp = phase >> 1, m0 = grp * mpg, m1 = imin(35, m0 + mpg);
+  if (!(phase & 1))
   {
-    // a0 log2n, a1 org plane offset, a2 modes per group; phases alternate predict(group) / satd(group)
-    const int log2n = a[0], n = 1 << log2n, n2 = n * n, mpg = a[2];
-    const int grp = phase >> 1, m0 = grp * mpg, m1 = imin(35, m0 + mpg);
-    if (!(phase & 1))
+    const int items = (m1 - m0) * n2;
+    for (int i = w; i < items; i += nw)
     {
-      const int items = (m1 - m0) * n2;
+      const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
+      const int x = sidx & (n - 1), y = sidx >> log2n;
+      const int16_t* line = use_filtered_refs(*s->t, 0, mode, log2n) ? e->refF : e->refU;
+      g->rmdPred[i] = (int16_t)pred_sample(*s->t, line, n, log2n, mode, x, y, 1, s->fp.bitDepth, e->refDc);
+    }
+  }
+  else
+  {
+    const int stride = plane_stride(s, 0);
+    if (n >= 8)
+    {
+      const int tps = n >> 3, tiles = tps * tps, items = (m1 - m0) * tiles;
       for (int i = w; i < items; i += nw)
       {
-        const int mi = i >> (2 * log2n), sidx = i & (n2 - 1), mode = m0 + mi;
-        const int x = sidx & (n - 1), y = sidx >> log2n;
-        const int16_t* line = use_filtered_refs(*s->t, 0, mode, log2n) ? e->refF : e->refU;
-        g->rmdPred[i] = (int16_t)pred_sample(*s->t, line, n, log2n, mode, x, y, 1, s->fp.bitDepth, e->refDc);
+        const int mi = i / tiles, tl = i - mi * tiles, ty = tl / tps, tx = tl - ty * tps;
+        int m[64];
+        for (int yy = 0; yy < 8; yy++)
+          for (int xx = 0; xx < 8; xx++)
+            m[yy * 8 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - g->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
+        atomic_add_u32(&s->satd[m0 + mi], had8(m), nw);
       }
     }
     else
     {
-      const int stride = plane_stride(s, 0);
-      if (n >= 8)
+      for (int mi = w; mi < m1 - m0; mi += nw)
       {
-        const int tps = n >> 3, tiles = tps * tps, items = (m1 - m0) * tiles;
-        for (int i = w; i < items; i += nw)
-        {
-          const int mi = i / tiles, tl = i - mi * tiles, ty = tl / tps, tx = tl - ty * tps;
-          int m[64];
-          for (int yy = 0; yy < 8; yy++)
-            for (int xx = 0; xx < 8; xx++)
-              m[yy * 8 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + (ty * 8 + yy) * stride + tx * 8 + xx) - g->rmdPred[mi * n2 + (ty * 8 + yy) * n + tx * 8 + xx];
-          atomic_add_u32(&s->satd[m0 + mi], had8(m), nw);
-        }
-      }
-      else
-      {
-        for (int mi = w; mi < m1 - m0; mi += nw)
-        {
-          int d[16];
-          for (int yy = 0; yy < 4; yy++)
-            for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + yy * stride + xx) - g->rmdPred[mi * 16 + yy * 4 + xx];
-          atomic_add_u32(&s->satd[m0 + mi], had4(d), nw);
-        }
+        int d[16];
+        for (int yy = 0; yy < 4; yy++)
+          for (int xx = 0; xx < 4; xx++) d[yy * 4 + xx] = org_at(g, s->fp.sampleBytes, 0, a[1] + yy * stride + xx) - g->rmdPred[mi * 16 + yy * 4 + xx];
+        atomic_add_u32(&s->satd[m0 + mi], had4(d), nw);
       }
     }
-    break;
   }
-  case OP_PRED_RESI:
+}
+
+// one copy per heavy operation: a phase call saves only the registers that operation needs
+FHC_D void phase_pred_resi(const Ctx& c, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
+  // a0 comp, a1 log2n, a2 mode, a3 useFilt, a4 offset into predYuv, a5 stride in predYuv, a6 org plane offset,
+  // a7 save/load (0 none, 1 save to tsPred, 2 load from tsPred)
+  const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n;
+  int16_t* pred = e->predYuv + a[4];
+  const int ps = a[5], stride = plane_stride(s, comp);
+  const int16_t* line = a[3] ? e->refF : e->refU;
+  for (int i = w; i < n2; i += nw)
   {
-    // a0 comp, a1 log2n, a2 mode, a3 useFilt, a4 offset into predYuv, a5 stride in predYuv, a6 org plane offset,
-    // a7 save/load (0 none, 1 save to tsPred, 2 load from tsPred)
-    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n;
-    int16_t* pred = e->predYuv + a[4];
-    const int ps = a[5], stride = plane_stride(s, comp);
-    const int16_t* line = a[3] ? e->refF : e->refU;
+    const int x = i & (n - 1), y = i >> log2n;
+    int v;
+    if (a[7] == 2) v = e->tsPred[comp][i];
+    else
+    {
+      v = pred_sample(*s->t, line, n, log2n, a[2], x, y, comp == 0, s->fp.bitDepth, e->refDc);
+      if (a[7] == 1) e->tsPred[comp][i] = (int16_t)v;
+    }
+    pred[y * ps + x] = (int16_t)v;
+    e->resi[i] = (int16_t)(org_at(g, s->fp.sampleBytes, comp, a[6] + y * stride + x) - v);
+  }
+}
+
+// one copy per heavy operation: a phase call saves only the registers that operation needs
+FHC_D void phase_fwd_quant(const Ctx& c, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
+  // a0 log2n, a1 useDst, a2 transformSkip, a3 scanType, a4 quantCoef, a5 qBits, a6 chType(0/1), a7 qp rem
+  // out: tcoef[] raster, lvlD[scanPos], rd.cost0[scanPos], tmp[blkPos] = uiMaxAbsLevel
+  const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
+  if (a[2])
+  {
+    if (phase == 1)
+    {
+      const int shift = 15 - bd - log2n;
+      for (int i = w; i < n2; i += nw) e->tcoef[i] = (int32_t)e->resi[i] << shift;
+    }
+  }
+  else if (phase == 0)
+  {
+    // xTrMxN first stage (TComTrQuant.cpp:860): rows -> tmp[k][j]
+    const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
+    if (nw == 1 && n <= 8) { lane_transform_stage(*s->t, n, a[1], 0, e->resi, e->tmp, add1, shift1); return; }
     for (int i = w; i < n2; i += nw)
     {
-      const int x = i & (n - 1), y = i >> log2n;
-      int v;
-      if (a[7] == 2) v = e->tsPred[comp][i];
-      else
-      {
-        v = pred_sample(*s->t, line, n, log2n, a[2], x, y, comp == 0, s->fp.bitDepth, e->refDc);
-        if (a[7] == 1) e->tsPred[comp][i] = (int16_t)v;
-      }
-      pred[y * ps + x] = (int16_t)v;
-      e->resi[i] = (int16_t)(org_at(g, s->fp.sampleBytes, comp, a[6] + y * stride + x) - v);
+      const int k = i >> log2n, j = i & (n - 1);
+      int acc = 0;
+      for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->resi[j * n + q];
+      e->tmp[i] = (acc + add1) >> shift1;
     }
-    break;
   }
-  case OP_FWD_QUANT:
+  else if (phase == 1)
   {
-    // a0 log2n, a1 useDst, a2 transformSkip, a3 scanType, a4 quantCoef, a5 qBits, a6 chType(0/1), a7 qp rem
-    // out: tcoef[] raster, lvlD[scanPos], rd.cost0[scanPos], tmp[blkPos] = uiMaxAbsLevel
-    const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
-    if (a[2])
+    const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
+    if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[1], 0, e->tmp, e->tcoef, add2, shift2);
+    else
+    for (int i = w; i < n2; i += nw)
     {
-      if (phase == 1)
-      {
-        const int shift = 15 - bd - log2n;
-        for (int i = w; i < n2; i += nw) e->tcoef[i] = (int32_t)e->resi[i] << shift;
-      }
+      const int k = i >> log2n, j = i & (n - 1);
+      int acc = 0;
+      for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->tmp[j * n + q];
+      e->tcoef[i] = (acc + add2) >> shift2;
     }
-    else if (phase == 0)
+  }
+  if (phase == 2)
+  {
+    // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient
+    const uint16_t* scan = scan_tab(*s->t, a[3], log2n);
+    const int qBits = a[5];
+    const double errScale = s->t->errScale[a[6]][log2n - 2][a[7]];
+    const int64_t cap = (int64_t)2147483647 - ((int64_t)1 << (qBits - 1));
+    for (int p = w; p < n2; p += nw)
     {
-      // xTrMxN first stage (TComTrQuant.cpp:860): rows -> tmp[k][j]
-      const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
-      if (nw == 1 && n <= 8) { lane_transform_stage(*s->t, n, a[1], 0, e->resi, e->tmp, add1, shift1); break; }
+      const int blk = scan[p];
+      const int64_t tl = (int64_t)iabs(e->tcoef[blk]) * a[4];
+      const int ld = (int)(tl < cap ? tl : cap);
+      const uint32_t m = (uint32_t)((ld + (1 << (qBits - 1))) >> qBits);
+      const double err = (double)ld;
+      e->lvlD[p] = ld;
+      e->cost0[p] = err * err * errScale;
+      e->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
+      if (m) atomic_or_u32(&e->cgNZ[p >> 9], 1u << ((p >> 4) & 31), nw);
+    }
+  }
+}
+
+// one copy per heavy operation: a phase call saves only the registers that operation needs
+FHC_D void phase_inv_recon(const Ctx& c, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
+  // a0 comp, a1 log2n, a2 useDst, a3 transformSkip, a4 absSum>0, a5 qp per, a6 qp rem,
+  // a7 predYuv offset, a8 predYuv stride, a9 qt layer, a10 qtRec offset, a11 rec plane offset, a12 org plane offset
+  const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
+  if (a[4])
+  {
+    if (phase == 0)
+    {
+      // xDeQuant (TComTrQuant.cpp:1308), flat scaling; levels are in tmp[] -> tcoef[]
+      const int transformShift = 15 - bd - log2n, rightShift = 6 - (transformShift + a[5]);
+      const int scale = (a[6] == 0 ? 40 : a[6] == 1 ? 45 : a[6] == 2 ? 51 : a[6] == 3 ? 57 : a[6] == 4 ? 64 : 72);
+      const int targetBits = imin(16, 32 + rightShift - 7);
+      const int inMin = -(1 << (targetBits - 1)), inMax = (1 << (targetBits - 1)) - 1;
       for (int i = w; i < n2; i += nw)
       {
-        const int k = i >> log2n, j = i & (n - 1);
-        int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->resi[j * n + q];
-        e->tmp[i] = (acc + add1) >> shift1;
+        const int q = clip3(inMin, inMax, e->tmp[i]);
+        int v;
+        if (rightShift > 0) v = (q * scale + (1 << (rightShift - 1))) >> rightShift;
+        else v = (int)((uint32_t)(q * scale) << (-rightShift));
+        e->tcoef[i] = clip3(-32768, 32767, v);
       }
     }
     else if (phase == 1)
     {
-      const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
-      if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[1], 0, e->tmp, e->tcoef, add2, shift2);
+      if (a[3])
+      {
+        const int shift = 15 - bd - log2n, off = shift == 0 ? 0 : (1 << (shift - 1));
+        for (int i = w; i < n2; i += nw) e->resi[i] = (int16_t)((e->tcoef[i] + off) >> shift);
+      }
       else
-      for (int i = w; i < n2; i += nw)
       {
-        const int k = i >> log2n, j = i & (n - 1);
-        int acc = 0;
-        for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->tmp[j * n + q];
-        e->tcoef[i] = (acc + add2) >> shift2;
+        // xITrMxN first stage (TComTrQuant.cpp:927): columns -> lvlD[j][i] (reused as scratch)
+        if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->tcoef, e->lvlD, 64, 7);
+        else
+        for (int i = w; i < n2; i += nw)
+        {
+          const int j = i >> log2n, q = i & (n - 1);
+          int acc = 0;
+          for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
+          e->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
+        }
       }
     }
-    if (phase == 2)
+    else if (phase == 2)
     {
-      // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient
-      const uint16_t* scan = scan_tab(*s->t, a[3], log2n);
-      const int qBits = a[5];
-      const double errScale = s->t->errScale[a[6]][log2n - 2][a[7]];
-      const int64_t cap = (int64_t)2147483647 - ((int64_t)1 << (qBits - 1));
-      for (int p = w; p < n2; p += nw)
+      if (!a[3])
       {
-        const int blk = scan[p];
-        const int64_t tl = (int64_t)iabs(e->tcoef[blk]) * a[4];
-        const int ld = (int)(tl < cap ? tl : cap);
-        const uint32_t m = (uint32_t)((ld + (1 << (qBits - 1))) >> qBits);
-        const double err = (double)ld;
-        e->lvlD[p] = ld;
-        e->cost0[p] = err * err * errScale;
-        e->tmp[blk] = (int32_t)(m < 32767u ? m : 32767u);
-        if (m) atomic_or_u32(&e->cgNZ[p >> 9], 1u << ((p >> 4) & 31), nw);
+        const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
+        if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->lvlD, e->resi, add2, shift2);
+        else
+        for (int i = w; i < n2; i += nw)
+        {
+          const int j = i >> log2n, q = i & (n - 1);
+          int acc = 0;
+          for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
+          e->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
+        }
       }
     }
-    break;
   }
+  if (phase == 3)
+  {
+    // reconstruction into CU buffer, QT layer and picture (TEncSearch.cpp:1380-1393) + SSE (TComRdCost.cpp:1176)
+    int16_t* reco = e->predYuv + a[7];
+    int16_t* recQt = qt_rec(e, a[9]) + a[10];
+    int16_t* recPic = g->rec[comp] + a[11];
+    const int ps = a[8], qs = e->qs >> (comp ? 1 : 0), stride = plane_stride(s, comp), shift = (bd - 8) << 1;
+    uint32_t acc = 0;
+    for (int i = w; i < n2; i += nw)
+    {
+      const int x = i & (n - 1), y = i >> log2n;
+      const int r = a[4] ? e->resi[i] : 0;
+      const int v = clip3(0, (1 << bd) - 1, reco[y * ps + x] + r);
+      reco[y * ps + x] = (int16_t)v;
+      recQt[y * qs + x] = (int16_t)v;
+      if (e->writePic) recPic[y * stride + x] = (int16_t)v;
+      const int d = v - org_at(g, s->fp.sampleBytes, comp, a[12] + y * stride + x);
+      acc += (uint32_t)((d * d) >> shift);
+    }
+    if (acc) atomic_add_u32(&e->sse, acc, nw);
+  }
+}
+
+FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw)
+{
+  FrameGlobal* g = c.g; (void)g;
+  Shared* s = c.s; (void)s;
+  Engine* e = c.e;
+  const int* a = e->cmd.a;
+  switch (op)
+  {
+  case OP_REFS: phase_refs(c, phase, w, nw); break;
+  case OP_RMD: phase_rmd(c, phase, w, nw); break;
+  case OP_PRED_RESI: phase_pred_resi(c, phase, w, nw); break;
+  case OP_FWD_QUANT: phase_fwd_quant(c, phase, w, nw); break;
+  case OP_INV_RECON: phase_inv_recon(c, phase, w, nw); break;
   case OP_LEVELS_OUT:
   {
     // a0 n2, a1 qtCoef layer, a2 offset: tmp[] (int32 levels) -> qtCoef (int16)
     int16_t* d = qt_coef(e, a[1]) + a[2];
     for (int i = w; i < a[0]; i += nw) d[i] = (int16_t)e->tmp[i];
-    break;
-  }
-  case OP_INV_RECON:
-  {
-    // a0 comp, a1 log2n, a2 useDst, a3 transformSkip, a4 absSum>0, a5 qp per, a6 qp rem,
-    // a7 predYuv offset, a8 predYuv stride, a9 qt layer, a10 qtRec offset, a11 rec plane offset, a12 org plane offset
-    const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
-    if (a[4])
-    {
-      if (phase == 0)
-      {
-        // xDeQuant (TComTrQuant.cpp:1308), flat scaling; levels are in tmp[] -> tcoef[]
-        const int transformShift = 15 - bd - log2n, rightShift = 6 - (transformShift + a[5]);
-        const int scale = (a[6] == 0 ? 40 : a[6] == 1 ? 45 : a[6] == 2 ? 51 : a[6] == 3 ? 57 : a[6] == 4 ? 64 : 72);
-        const int targetBits = imin(16, 32 + rightShift - 7);
-        const int inMin = -(1 << (targetBits - 1)), inMax = (1 << (targetBits - 1)) - 1;
-        for (int i = w; i < n2; i += nw)
-        {
-          const int q = clip3(inMin, inMax, e->tmp[i]);
-          int v;
-          if (rightShift > 0) v = (q * scale + (1 << (rightShift - 1))) >> rightShift;
-          else v = (int)((uint32_t)(q * scale) << (-rightShift));
-          e->tcoef[i] = clip3(-32768, 32767, v);
-        }
-      }
-      else if (phase == 1)
-      {
-        if (a[3])
-        {
-          const int shift = 15 - bd - log2n, off = shift == 0 ? 0 : (1 << (shift - 1));
-          for (int i = w; i < n2; i += nw) e->resi[i] = (int16_t)((e->tcoef[i] + off) >> shift);
-        }
-        else
-        {
-          // xITrMxN first stage (TComTrQuant.cpp:927): columns -> lvlD[j][i] (reused as scratch)
-          if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->tcoef, e->lvlD, 64, 7);
-          else
-          for (int i = w; i < n2; i += nw)
-          {
-            const int j = i >> log2n, q = i & (n - 1);
-            int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
-            e->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
-          }
-        }
-      }
-      else if (phase == 2)
-      {
-        if (!a[3])
-        {
-          const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
-          if (nw == 1 && n <= 8) lane_transform_stage(*s->t, n, a[2], 1, e->lvlD, e->resi, add2, shift2);
-          else
-          for (int i = w; i < n2; i += nw)
-          {
-            const int j = i >> log2n, q = i & (n - 1);
-            int acc = 0;
-            for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
-            e->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
-          }
-        }
-      }
-    }
-    if (phase == 3)
-    {
-      // reconstruction into CU buffer, QT layer and picture (TEncSearch.cpp:1380-1393) + SSE (TComRdCost.cpp:1176)
-      int16_t* reco = e->predYuv + a[7];
-      int16_t* recQt = qt_rec(e, a[9]) + a[10];
-      int16_t* recPic = g->rec[comp] + a[11];
-      const int ps = a[8], qs = e->qs >> (comp ? 1 : 0), stride = plane_stride(s, comp), shift = (bd - 8) << 1;
-      uint32_t acc = 0;
-      for (int i = w; i < n2; i += nw)
-      {
-        const int x = i & (n - 1), y = i >> log2n;
-        const int r = a[4] ? e->resi[i] : 0;
-        const int v = clip3(0, (1 << bd) - 1, reco[y * ps + x] + r);
-        reco[y * ps + x] = (int16_t)v;
-        recQt[y * qs + x] = (int16_t)v;
-        if (e->writePic) recPic[y * stride + x] = (int16_t)v;
-        const int d = v - org_at(g, s->fp.sampleBytes, comp, a[12] + y * stride + x);
-        acc += (uint32_t)((d * d) >> shift);
-      }
-      if (acc) atomic_add_u32(&e->sse, acc, nw);
-    }
     break;
   }
   case OP_NZMASK:
@@ -1416,7 +1449,7 @@ FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, d
   return best;
 }
 
-FHC_NOINLINE uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
+FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
@@ -2019,7 +2052,20 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
 
   if (checkFull)
   {
-    if (checkTS)
+    if (checkTS && e->forceTs >= 0)
+    {
+      // one half of the transform-skip pair (TEncSearch.cpp:1482-1560): both start from the same contexts and the same
+      // prediction, the pair is compared by the caller in the order of the loop below (DCT first, strict <)
+      const int modeId = e->forceTs;
+      set_range(cu->ts[0], relIdx, numParts, modeId);
+      set_range(cu->tridx, relIdx, numParts, trDepth);
+      singleDist = code_tu_block(c, cu, relIdx, 0, log2n, log2n, trDepth, numParts, 0);
+      singleCbf = (cu->cbf[0][relIdx] >> trDepth) & 1;
+      if (modeId == 1 && singleCbf == 0) singleCost = FHC_MAX_COST;
+      else singleCost = rd_cost(c, intra_bits_qt(c, cu, relIdx, log2n, trDepth, 1, 0, 1, 0), singleDist);
+      bestModeId = modeId;
+    }
+    else if (checkTS)
     {
       sb_copy(c, slot_of(c, fullDepth, CI_QT_TRAFO_ROOT), e->go);
       FHC_NOUNROLL for (int modeId = 0; modeId < 2; modeId++)
@@ -2106,7 +2152,7 @@ FHC_D void recur_luma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int tr
 // "single TU" branch of xRecurIntraCodingLumaQT(bCheckFirst=false) repeats, instruction for instruction, the first-pass
 // evaluation of the same mode (same start contexts CI_CURR_BEST, same neighbours), so its cost is the first-pass best
 // cost.  Only the split branch is new work; it wins iff splitCost < that cost.  Returns 1 when the split wins.
-FHC_D int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, double singleCost, uint32_t* dist, double* cost)
+FHC_DH int second_pass_split_only(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int trDepth, double singleCost, uint32_t* dist, double* cost)
 {
   Engine* e = c.e;
   if (!(log2n > min_tu_log2_in_cu(cu))) return 0;
@@ -2165,7 +2211,7 @@ FHC_D void ghost_first_pass(const Ctx& c, int log2n)
 }
 
 // estIntraPredLumaQT (TEncSearch.cpp:2177-2557)
-FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
+FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
@@ -2247,7 +2293,8 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
       // small PUs (4x4 of NxN, 8x8): every candidate is a single TU, independent of the others (same start contexts,
       // neighbours outside the PU) -> one thread engine per candidate, results compared in list order afterwards
       TaskDesc& td = s->task;
-      td.kind = TASK_LUMA_PU; td.numTasks = numModesForFullRD; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
+      td.tsSplit = (log2pu == 2);                     // a 4x4 PU exists only in an NxN CU: every candidate is a DCT/skip pair
+      td.kind = TASK_LUMA_PU; td.numTasks = numModesForFullRD << td.tsSplit; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
       td.partOffset = partOffset; td.log2pu = log2pu; td.initTrDepth = initTrDepth;
       FHC_NOUNROLL for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
       { FHC_TIC(tl); dispatch_tasks(c); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
@@ -2255,7 +2302,7 @@ FHC_D void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cu
         // xSetIntraResultLumaQT + the saved trIdx/cbf/tskip arrays of the winner
         const int be = best_engine(c), n = 1 << log2pu;
         const EngineGlobal* wg = &g->eng[be];
-        bestPUCost = wg->eng.resCost; bestPUDist = wg->eng.resDist; bestPUMode = rdModeList[wg->eng.resTask];
+        bestPUCost = wg->eng.resCost; bestPUDist = wg->eng.resDist; bestPUMode = rdModeList[wg->eng.resTask >> td.tsSplit];
         par_copy16(c, cuCoef + partOffset * 16, wg->bestCoef[0], n * n);
         par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, wg->bestReco[0], n, n, n);
         copy_bytes(g->qtTrIdx, wg->bestTrIdx, puParts);
@@ -2429,7 +2476,7 @@ FHC_D void set_chroma_result(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
     FHC_NOUNROLL for (int i = 0; i < 4; i++) set_chroma_result(c, cu, cuCoef, cuReco, relIdx + i * q, log2n - 1, trDepth + 1, (log2n - 1 > 2) ? 1 : (i == 0));
   }
 }
-FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
+FHC_DH void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* cuReco)
 {
   Shared* s = c.s;
   FrameGlobal* g = c.g;
@@ -2443,7 +2490,7 @@ FHC_D void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* 
   {
     // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> thread engines
     TaskDesc& td = s->task;
-    td.kind = TASK_CHROMA_CU; td.numTasks = 5; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
+    td.tsSplit = 0; td.kind = TASK_CHROMA_CU; td.numTasks = 5; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
     td.partOffset = 0; td.log2pu = log2cu; td.initTrDepth = 0;
     FHC_NOUNROLL for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
     { FHC_TIC(tc); dispatch_tasks(c); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
@@ -2751,7 +2798,7 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
 {
   Engine* m = &s->master;
   s->t = tables;
-  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0;
+  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0; m->forceTs = -1;
   m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->go = &s->masterGo;
   m->csSmall = &s->u.cs; m->csLarge = &g->big;
   bind_coef_scratch(m, &s->u.cs);
@@ -2810,7 +2857,8 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     cu->cdir[i] = src->cdir[i]; cu->tridx[i] = src->tridx[i];
     FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
   }
-  const int mode = td.mode[t];
+  const int mode = td.mode[t >> td.tsSplit];
+  e->forceTs = td.tsSplit ? (t & 1) : -1;
   if (td.kind == TASK_LUMA_PU)
   {
     // one iteration of the candidate loop of estIntraPredLumaQT (TEncSearch.cpp:2349-2418), bCheckFirst = true

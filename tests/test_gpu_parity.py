@@ -71,6 +71,36 @@ def test_cuda_mixed_qp_batch_is_independent():
     assert alone[0].tobytes() == got[2].tobytes()
 
 
+@pytest.mark.parametrize("n", [19, 37])
+def test_cuda_block_of_pictures_is_aligned_and_exact(n):
+    """A thread block keeps its 16 pictures (one warp each) on the same routine with a named barrier and pads shorter
+    candidate lists: different contents and QPs in one block, a partial last block (n not a multiple of 16), and every
+    picture must still equal the oracle."""
+    w, h = 136, 72
+    Y, U, V = synth_frames(w, h, n, sigma=11.0, seed=7)
+    qps = [22, 37, 27, 32]
+    ps = [T.params_from_qp(w, h, 8, qps[k % 4]) for k in range(n)]
+    got = cuda_compress(w, h, 8, [T.slice_params_from_hm(p) for p in ps], Y, U, V)
+    for k in range(n):
+        assert T.compare_ctus(got[k], T.oracle_compress(ps[k], Y[k], U[k], V[k]), "pic%d" % k) == []
+
+
+def test_cuda_more_pictures_than_resident_warps():
+    """More pictures than the persistent kernel keeps in flight: blocks pull further rounds from the queue."""
+    import fasthevc_b200 as fh
+    w, h, qp = 64, 64, 34
+    n = fh.pictures_in_flight(0) + 40
+    Yd, Ud, Vd = synth_frames(w, h, 6, sigma=9.0, seed=3)
+    idx = np.arange(n) % 6
+    p = T.params_from_qp(w, h, 8, qp)
+    got = cuda_compress(w, h, 8, [T.slice_params_from_hm(p)] * n, Yd[idx], Ud[idx], Vd[idx])
+    ref = [T.oracle_compress(p, Yd[k], Ud[k], Vd[k]) for k in range(6)]
+    for k in range(n):
+        assert got[k].tobytes() == got[int(idx[k])].tobytes()
+    for k in range(6):
+        assert T.compare_ctus(got[k], ref[k], "pic%d" % k) == []
+
+
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref did not travel")
 def test_cuda_matches_live_reference():
     """Same input through the real reference (TAppEncoderDump, host CPU) and through the CUDA path."""
