@@ -170,7 +170,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   Tables t;
   build_tables(&t, seq->bitDepth);
   CK(cudaMemcpy(c->dTables, &t, sizeof(t), cudaMemcpyHostToDevice));
-  CK(cudaDeviceSetLimit(cudaLimitStackSize, 16384));
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 24576));
   *out = c;
   return FHC_OK;
 }

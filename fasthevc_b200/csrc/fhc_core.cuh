@@ -68,9 +68,6 @@ enum {
 #endif
 #define FHC_MAX_MODES 10         /* the longest candidate list (8 RMD survivors + 2 MPMs) */
 #define FHC_MAX_TASKS 20         /* ... times the transform-skip pair of a 4x4 PU */
-#ifndef FHC_LANE_SMEM
-#define FHC_LANE_SMEM 0           /* 1: lane engines keep their CABAC state and 4x4 scratch in shared memory (costs L1) */
-#endif
 #define FHC_NENG (FHC_GROUP < FHC_MAX_TASKS ? FHC_GROUP : FHC_MAX_TASKS)   /* lane engines per picture */
 #define FHC_SMALL_COEFS 64       /* TUs up to 8x8 use the warp's shared-memory scratch, larger ones the global scratch */
 #define FHC_FULL_MASK 0xffffffffu
@@ -125,7 +122,7 @@ enum Op {
   OP_CTU_RECO_OUT, OP_CU_TO_OUT, OP_NZMASK, OP_TASKS, OP_BLOCKBAR
 };
 enum { ENG_MASTER = 0, ENG_LANE = 1 };
-enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1 };
+enum { TASK_LUMA_PU = 0, TASK_CHROMA_CU = 1, TASK_CHROMA_TU = 2, TASK_CHROMA_BITS = 3 };
 
 struct Cmd
 {
@@ -172,6 +169,9 @@ struct Engine
   int16_t *qtRecBase, *qtCoefBase;
   int layerSize, qs, coff[3];
   int writePic;                   // reconstruct into the picture plane too (master only)
+  int refsShared;                 // 1: luma TUs use the reference lines the leader built for the rough mode decision; 2: chroma
+                                  // TUs of an 8x8 CU use the lines the leader built before the dispatch (Shared::refC)
+  int onlyComp;                   // != 0: recur_chroma_qt codes only this component (lane tasks that split Cb / Cr)
   int forceTs;                    // >= 0: evaluate only this transform_skip_flag of a 4x4 luma TU (lane tasks of a 4x4 PU)
   int noAlign;                    // inside a section whose TU count depends on the picture: no block alignment
   uint32_t cgNZ[2];               // per coefficient group (scan order): any pre-quantised level != 0 (set by OP_FWD_QUANT)
@@ -180,7 +180,7 @@ struct Engine
   double *sigC0, *sigC1;
   int32_t* sigDelta;
   uint16_t* cgNzMask;             // per coefficient group (scan order): non-zero map of the levels
-  int32_t* cgAbs;                 // ... and their sum
+  uint8_t* cgAbs;                 // ... and the parity of their sum
   // engine result: best task of the current dispatch
   double resCost;
   uint32_t resDist;
@@ -190,25 +190,36 @@ struct Engine
 FHC_DH int16_t* qt_rec(const Engine* e, int layer) { return e->qtRecBase + layer * e->layerSize; }
 FHC_DH int16_t* qt_coef(const Engine* e, int layer) { return e->qtCoefBase + layer * e->layerSize; }
 
-// private global scratch of one lane engine (same layouts as the master's buffers; engines only see depth-3 CUs)
+// What one lane engine leaves behind for the leader (global memory) + the scratch that is too large for the lane's
+// stack.  An engine runs its tasks in increasing order and keeps the best (strict <).
 struct EngineGlobal
 {
-  Engine eng;
-  Sbac slots[3];                  // CI_QT_TRAFO_ROOT, CI_TEMP_BEST, CI_QT_TRAFO_TEST
-  Sbac go;                        // used when FHC_LANE_SMEM is 0
-  CoefScratch<16> cs16;
-  int16_t refU[36], refF[36];
-  uint8_t flags[24];
-  CoefScratch<FHC_SMALL_COEFS> cs;
-  double costCGSig[4], sigC0[28], sigC1[28];
-  int32_t sigDelta[28];
-  uint8_t cgFlag[4], cgFlagCode[4];
-  uint16_t cgNzMask[4];
-  int32_t cgAbs[4];
-  CUMeta cu;
-  uint8_t cuStore[12 * 4];
+  double resCost;
+  uint32_t resDist;
+  int resTask;
   int16_t bestCoef[3][64], bestReco[3][64];
   uint8_t bestTrIdx[4], bestCbf[3][4], bestTs[3][4];
+  CoefScratch<FHC_SMALL_COEFS> cs;     // 8x8 TUs
+  double sigC0[28], sigC1[28];
+  int32_t sigDelta[28];
+};
+
+// Working state of one lane engine: a local variable of run_task, i.e. in the lane's LOCAL memory, where the same
+// field of neighbouring lanes is adjacent - the lanes of a dispatch walk the same code, so their accesses coalesce
+// (private global structs cost one 32-byte sector per lane and access).  Engines only see depth-3 CUs: 96 samples.
+struct LaneLocal
+{
+  Engine eng;
+  Sbac go, slots[3];              // slots: CI_QT_TRAFO_ROOT, CI_TEMP_BEST, CI_QT_TRAFO_TEST
+  int16_t refU[36], refF[36];
+  uint8_t flags[24];
+  CoefScratch<16> cs16;           // 4x4 TUs
+  double costCGSig[4];
+  uint8_t cgFlag[4], cgFlagCode[4];
+  uint16_t cgNzMask[4];
+  uint8_t cgAbs[4];
+  CUMeta cu;
+  uint8_t cuStore[12 * 4];
   int16_t predYuv[96];
   int16_t qtRec[4][96];
   int16_t qtCoef[4][96];
@@ -253,6 +264,7 @@ struct TaskDesc
   int kind, numTasks;
   int depth, bufIdx;              // the CU under test: s->cu[depth][bufIdx]
   int partOffset, log2pu, initTrDepth;
+  int resBase;                     // lane engine that receives the result of task 0
   int tsSplit;                     // 4x4 PU: task t = candidate t >> 1 with transform_skip_flag = t & 1
   int mode[FHC_MAX_MODES];
 };
@@ -277,25 +289,21 @@ struct Shared
   Engine master;
   TaskDesc task;
   Sbac masterGo;
-#if FHC_LANE_SMEM
-  Sbac laneGo[FHC_NENG];
-#endif
   // master scratch
   int16_t refU[260], refF[260];
   uint8_t flags[72];
   union                          // a dispatch and a COOP TU of the master never overlap in time
   {
     CoefScratch<FHC_SMALL_COEFS> cs;          // master: TUs up to 8x8
-#if FHC_LANE_SMEM
-    CoefScratch<16> laneCs[FHC_NENG];         // lane engines: 4x4 TUs
-#endif
   } u;
   uint32_t satd[36];
+  int16_t refC[2][20];            // unfiltered reference lines of the 4x4 Cb / Cr block of an 8x8 CU
+  int dcC[2];
   double costCGSig[64], sigC0[28], sigC1[28];
   int32_t sigDelta[28];
   uint8_t cgFlag[64], cgFlagCode[64];
   uint16_t cgNzMask[64];
-  int32_t cgAbs[64];
+  uint8_t cgAbs[64];
 };
 
 // lane/nl: this thread's index and the size of the lane group that executes COOP sections together (32 = the warp,
@@ -319,7 +327,7 @@ enum { PF2_CHECK_D0 = 0, PF2_CHECK_D1, PF2_CHECK_D2, PF2_CHECK_D3_2N, PF2_CHECK_
 // portability layer: COOP sections
 // ----------------------------------------------------------------------------------------------
 FHC_D void run_phase(const Ctx& c, int op, int phase, int w, int nw);
-FHC_D void dispatch_tasks(const Ctx& c);
+FHC_D void dispatch_tasks(const Ctx& c, int align);
 FHC_D void run_tasks(const Ctx& c);
 FHC_DH int num_phases(int op)
 {
@@ -1080,12 +1088,12 @@ FHC_DH Sbac* slot_of(const Ctx& c, int depth, int ci)
 FHC_DH int best_engine(const Ctx& c)
 {
   const FrameGlobal* g = c.g;
-  const int ne = imin(FHC_NENG, c.s->task.numTasks);
-  int be = 0;
-  FHC_NOUNROLL for (int i = 1; i < ne; i++)
+  const int base = c.s->task.resBase, ne = base + imin(FHC_NENG, c.s->task.numTasks);
+  int be = base;
+  FHC_NOUNROLL for (int i = base + 1; i < ne; i++)
   {
-    const Engine* a = &g->eng[i].eng;
-    const Engine* b = &g->eng[be].eng;
+    const EngineGlobal* a = &g->eng[i];
+    const EngineGlobal* b = &g->eng[be];
     if (a->resCost < b->resCost || (a->resCost == b->resCost && a->resTask < b->resTask)) be = i;
   }
   return be;
@@ -1706,7 +1714,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
   }
   // signs, and per coefficient group of the coded range the non-zero map and the level sum (consumed by sign bit hiding)
   uint16_t* nzMask = e->cgNzMask;
-  int32_t* cgAbs = e->cgAbs;
+  uint8_t* cgAbs = e->cgAbs;
   const int numCodedCG = (bestLastIdxP1 + 15) >> 4;
   FHC_NOUNROLL for (int cgi = 0; cgi < numCodedCG; cgi++)
   {
@@ -1725,7 +1733,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
       }
     }
     absSum += (uint32_t)sum;
-    nzMask[cgi] = (uint16_t)mask; cgAbs[cgi] = sum;
+    nzMask[cgi] = (uint16_t)mask; cgAbs[cgi] = (uint8_t)(sum & 1);
   }
   FHC_NOUNROLL for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) dst[scan[scanPos]] = 0;
 
@@ -1913,7 +1921,8 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   if (predSaveLoad != 2)
   {
     useFilt = use_filtered_refs(*s->t, comp, mode, log2n);
-    build_refs(c, cu, relIdx, comp, n, useFilt);
+    if (e->refsShared == 2 && comp != 0) { e->refU = s->refC[comp - 1]; e->refDc = s->dcC[comp - 1]; }
+    else if (!(e->refsShared == 1 && comp == 0)) build_refs(c, cu, relIdx, comp, n, useFilt);
   }
   m.a[0] = comp; m.a[1] = log2n; m.a[2] = mode; m.a[3] = useFilt; m.a[4] = predOff; m.a[5] = cuW;
   m.a[6] = picY * stride + picX; m.a[7] = predSaveLoad;
@@ -2293,16 +2302,17 @@ FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
       // small PUs (4x4 of NxN, 8x8): every candidate is a single TU, independent of the others (same start contexts,
       // neighbours outside the PU) -> one thread engine per candidate, results compared in list order afterwards
       TaskDesc& td = s->task;
+      td.resBase = 0;
       td.tsSplit = (log2pu == 2);                     // a 4x4 PU exists only in an NxN CU: every candidate is a DCT/skip pair
       td.kind = TASK_LUMA_PU; td.numTasks = numModesForFullRD << td.tsSplit; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
       td.partOffset = partOffset; td.log2pu = log2pu; td.initTrDepth = initTrDepth;
       FHC_NOUNROLL for (int i = 0; i < numModesForFullRD; i++) td.mode[i] = (int)rdModeList[i];
-      { FHC_TIC(tl); dispatch_tasks(c); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
+      { FHC_TIC(tl); dispatch_tasks(c, 1); FHC_TOC2(c, tl, PF_TASKS_LUMA); }
       {
         // xSetIntraResultLumaQT + the saved trIdx/cbf/tskip arrays of the winner
         const int be = best_engine(c), n = 1 << log2pu;
         const EngineGlobal* wg = &g->eng[be];
-        bestPUCost = wg->eng.resCost; bestPUDist = wg->eng.resDist; bestPUMode = rdModeList[wg->eng.resTask >> td.tsSplit];
+        bestPUCost = wg->resCost; bestPUDist = wg->resDist; bestPUMode = rdModeList[wg->resTask >> td.tsSplit];
         par_copy16(c, cuCoef + partOffset * 16, wg->bestCoef[0], n * n);
         par_copy2d(c, cuReco + rel_y(s, partOffset) * cu->width + rel_x(s, partOffset), cu->width, wg->bestReco[0], n, n, n);
         copy_bytes(g->qtTrIdx, wg->bestTrIdx, puParts);
@@ -2388,6 +2398,7 @@ FHC_D void recur_chroma_qt(const Ctx& c, CUMeta* cu, int relIdx, int log2n, int 
     }
     FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
+      if (e->onlyComp && cc != e->onlyComp) continue;
       double singleCost = FHC_MAX_COST, costTmp = 0;
       uint32_t singleDist = 0, singleCbf = 0;
       int bestMode = 0, bestTS = 0, currMode = 0;
@@ -2490,13 +2501,34 @@ FHC_DH void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
   {
     // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> thread engines
     TaskDesc& td = s->task;
-    td.tsSplit = 0; td.kind = TASK_CHROMA_CU; td.numTasks = 5; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
+    // the 4x4 Cb / Cr blocks sit at the CU origin whatever the luma TU tree: their reference lines are built once
+    FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
+    {
+      build_refs(c, cu, 0, cc, 4, 0);
+      FHC_NOUNROLL for (int i = 0; i < 17; i++) s->refC[cc - 1][i] = s->refU[i];
+      s->dcC[cc - 1] = e->refDc;
+    }
+    td.tsSplit = 0; td.resBase = 0; td.depth = depth; td.bufIdx = cu_buf_index(s, cu);
     td.partOffset = 0; td.log2pu = log2cu; td.initTrDepth = 0;
     FHC_NOUNROLL for (int mi = 0; mi < 5; mi++) td.mode[mi] = modeList[mi];
-    { FHC_TIC(tc); dispatch_tasks(c); FHC_TOC2(c, tc, PF_TASKS_CHROMA); }
+    // transform skip is tried for chroma only below a 4x4 luma TU that chose it (TEncSearch.cpp:1943-1956); without
+    // it Cb and Cr of a mode are independent until their bits are counted: 10 TU tasks, then 5 bit-counting tasks
+#ifdef FHC_CHROMA_SPLIT
+    const int chromaTS = (cu->tridx[0] == 1) && (cu->ts[0][0] + cu->ts[0][1] + cu->ts[0][2] + cu->ts[0][3] > 0);
+#else
+    const int chromaTS = 1;       // measured: the two-phase dispatch costs as much as it saves; one task per mode
+#endif
+    FHC_TIC(tc);
+    if (chromaTS) { td.kind = TASK_CHROMA_CU; td.numTasks = 5; dispatch_tasks(c, 1); }
+    else
+    {
+      td.kind = TASK_CHROMA_TU; td.numTasks = 10; dispatch_tasks(c, 1);
+      td.kind = TASK_CHROMA_BITS; td.numTasks = 5; td.resBase = 10; dispatch_tasks(c, 0);
+    }
+    FHC_TOC2(c, tc, PF_TASKS_CHROMA);
     const int be = best_engine(c);
     const EngineGlobal* wg = &g->eng[be];
-    bestCost = wg->eng.resCost; bestDist = wg->eng.resDist; bestMode = (uint32_t)modeList[wg->eng.resTask];
+    bestCost = wg->resCost; bestDist = wg->resDist; bestMode = (uint32_t)modeList[wg->resTask];
     FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
     {
       par_copy16(c, cuCoef + comp_off(cc), wg->bestCoef[cc], 16);
@@ -2798,7 +2830,7 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
 {
   Engine* m = &s->master;
   s->t = tables;
-  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0; m->forceTs = -1;
+  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0; m->forceTs = -1; m->refsShared = 0; m->onlyComp = 0;
   m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->go = &s->masterGo;
   m->csSmall = &s->u.cs; m->csLarge = &g->big;
   bind_coef_scratch(m, &s->u.cs);
@@ -2813,24 +2845,6 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
       FHC_NOUNROLL for (int b = 0; b < 2; b++) { cu_bind(&s->cu[d][b], st, 256 >> (2 * d)); st += 12 * (256 >> (2 * d)); }
     }
   }
-  FHC_NOUNROLL for (int i = 0; i < FHC_NENG; i++)
-  {
-    EngineGlobal* x = &g->eng[i];
-    Engine* e = &x->eng;
-    e->kind = ENG_LANE; e->t = tables; e->slots = x->slots; e->noAlign = 1;
-    e->refU = x->refU; e->refF = x->refF; e->flags = x->flags;
-#if FHC_LANE_SMEM
-    e->go = &s->laneGo[i]; e->csSmall = &s->u.laneCs[i];
-#else
-    e->go = &x->go; e->csSmall = &x->cs16;
-#endif
-    e->csLarge = &x->cs;
-    bind_coef_scratch(e, &x->cs);
-    e->predYuv = x->predYuv; e->qtRecBase = &x->qtRec[0][0]; e->qtCoefBase = &x->qtCoef[0][0]; e->writePic = 0;
-    e->layerSize = 96; e->qs = 8; e->coff[0] = 0; e->coff[1] = 64; e->coff[2] = 80;
-    e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->sigC0 = x->sigC0; e->sigC1 = x->sigC1; e->sigDelta = x->sigDelta; e->cgNzMask = x->cgNzMask; e->cgAbs = x->cgAbs;
-    cu_bind(&x->cu, x->cuStore, 4);
-  }
 }
 
 // Candidate t of s->task evaluated by ONE lane on lane engine engIdx (an engine runs its tasks in increasing order and
@@ -2841,14 +2855,23 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
 {
   FrameGlobal* g = mc.g;
   Shared* s = mc.s;
-  EngineGlobal* eg = &g->eng[engIdx];
+  EngineGlobal* eg = &g->eng[s->task.resBase + engIdx];
   const int firstOfDispatch = t < FHC_NENG;
+  LaneLocal L;
+  Engine* e = &L.eng;
   Ctx c;
-  c.g = g; c.s = s; c.e = &eg->eng; c.lane = 0; c.nl = 1; c.mask = 0;
-  Engine* e = c.e;
+  c.g = g; c.s = s; c.e = e; c.lane = 0; c.nl = 1; c.mask = 0;
+  e->kind = ENG_LANE; e->t = s->t; e->slots = L.slots; e->go = &L.go; e->noAlign = 1; e->writePic = 0;
+  e->flags = L.flags; e->csSmall = &L.cs16; e->csLarge = &eg->cs;
+  bind_coef_scratch(e, &L.cs16);
+  e->predYuv = L.predYuv; e->qtRecBase = &L.qtRec[0][0]; e->qtCoefBase = &L.qtCoef[0][0];
+  e->layerSize = 96; e->qs = 8; e->coff[0] = 0; e->coff[1] = 64; e->coff[2] = 80;
+  e->costCGSig = L.costCGSig; e->cgFlag = L.cgFlag; e->cgFlagCode = L.cgFlagCode; e->cgNzMask = L.cgNzMask; e->cgAbs = L.cgAbs;
+  e->sigC0 = eg->sigC0; e->sigC1 = eg->sigC1; e->sigDelta = eg->sigDelta;
+  cu_bind(&L.cu, L.cuStore, 4);
   const TaskDesc& td = s->task;
   const CUMeta* src = &s->cu[td.depth][td.bufIdx];
-  CUMeta* cu = &eg->cu;
+  CUMeta* cu = &L.cu;
   const int np = src->nparts;
   cu->zidx = src->zidx; cu->x = src->x; cu->y = src->y; cu->depth = src->depth; cu->nparts = np; cu->width = src->width;
   FHC_NOUNROLL for (int i = 0; i < np; i++)
@@ -2857,8 +2880,15 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     cu->cdir[i] = src->cdir[i]; cu->tridx[i] = src->tridx[i];
     FHC_NOUNROLL for (int cc = 0; cc < 3; cc++) { cu->cbf[cc][i] = src->cbf[cc][i]; cu->ts[cc][i] = src->ts[cc][i]; }
   }
-  const int mode = td.mode[t >> td.tsSplit];
+  const int mode = td.mode[td.kind == TASK_CHROMA_TU ? (t >> 1) : (t >> td.tsSplit)];
   e->forceTs = td.tsSplit ? (t & 1) : -1;
+  e->onlyComp = 0;
+  if (td.kind == TASK_LUMA_PU)
+  {
+    // the PU is one TU at the position and size of the leader's rough mode decision: same reference lines
+    e->refsShared = 1; e->refU = s->refU; e->refF = s->refF; e->refDc = s->master.refDc;
+  }
+  else { e->refsShared = 2; e->refU = L.refU; e->refF = L.refF; }
   if (td.kind == TASK_LUMA_PU)
   {
     // one iteration of the candidate loop of estIntraPredLumaQT (TEncSearch.cpp:2349-2418), bCheckFirst = true
@@ -2869,9 +2899,9 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     set_range(cu->ldir, td.partOffset, puParts, mode);
     sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
-    if (firstOfDispatch || cost < e->resCost)
+    if (firstOfDispatch || cost < eg->resCost)
     {
-      e->resCost = cost; e->resDist = dist; e->resTask = t;
+      eg->resCost = cost; eg->resDist = dist; eg->resTask = t;
       par_copy16(c, eg->bestCoef[0], qt_coef(e, layer) + td.partOffset * 16, n * n);
       par_copy2d(c, eg->bestReco[0], n, qt_rec(e, layer) + rel_y(s, td.partOffset) * e->qs + rel_x(s, td.partOffset), e->qs, n, n);
       FHC_NOUNROLL for (int i = 0; i < puParts; i++)
@@ -2881,20 +2911,46 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
       }
     }
   }
-  else
+  else if (td.kind == TASK_CHROMA_TU)
   {
-    // one iteration of the chroma mode loop of estIntraPredChromaQT (TEncSearch.cpp:2612-2648)
+    // one component of one iteration of the chroma mode loop: the TU coding only (no context is touched when no
+    // transform skip is tried, TEncSearch.cpp:2022-2047), left in this task's engine for the bit-counting task
     uint32_t dist = 0;
-    const int log2cu = ilog2(cu->width);
+    const int cc = 1 + (t & 1);
     sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     set_range(cu->cdir, 0, np, mode);
-    recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
+    e->onlyComp = cc;
+    recur_chroma_qt(c, cu, 0, ilog2(cu->width), 0, 1, &dist);
+    const int layer = 5 - (3 - (int)cu->tridx[0]);
+    eg->resDist = dist;
+    par_copy16(c, eg->bestCoef[cc], qt_coef(e, layer) + e->coff[cc], 16);
+    par_copy2d(c, eg->bestReco[cc], 4, qt_rec(e, layer) + e->coff[cc], e->qs >> 1, 4, 4);
+    FHC_NOUNROLL for (int i = 0; i < np; i++) { eg->bestCbf[cc][i] = cu->cbf[cc][i]; eg->bestTs[cc][i] = cu->ts[cc][i]; }
+  }
+  else
+  {
+    // chroma mode loop of estIntraPredChromaQT (TEncSearch.cpp:2612-2648): TASK_CHROMA_CU = one whole iteration,
+    // TASK_CHROMA_BITS = its bit counting and cost from the two TU tasks of the mode (engines 2t, 2t+1)
+    uint32_t dist = 0;
+    const int log2cu = ilog2(cu->width);
+    const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
+    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    set_range(cu->cdir, 0, np, mode);
+    if (td.kind == TASK_CHROMA_CU) recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
+    else
+      FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
+      {
+        const EngineGlobal* a = &g->eng[2 * t + cc - 1];
+        dist += a->resDist;
+        par_copy16(c, qt_coef(e, layer) + e->coff[cc], a->bestCoef[cc], 16);
+        par_copy2d(c, qt_rec(e, layer) + e->coff[cc], e->qs >> 1, a->bestReco[cc], 4, 4, 4);
+        FHC_NOUNROLL for (int i = 0; i < np; i++) { cu->cbf[cc][i] = a->bestCbf[cc][i]; cu->ts[cc][i] = a->bestTs[cc][i]; }
+      }
     sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
-    const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
-    if (firstOfDispatch || cost < e->resCost)
+    if (firstOfDispatch || cost < eg->resCost)
     {
-      e->resCost = cost; e->resDist = dist; e->resTask = t;
+      eg->resCost = cost; eg->resDist = dist; eg->resTask = t;
       FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
       {
         par_copy16(c, eg->bestCoef[cc], qt_coef(e, layer) + e->coff[cc], 16);
@@ -2913,9 +2969,9 @@ FHC_D void run_tasks(const Ctx& c)
     FHC_NOUNROLL for (int t = c.lane; t < n; t += FHC_NENG) run_task(c, c.lane, t);
 }
 // called by the leader: publishes the dispatch, takes part in it, and waits for the group before comparing results
-FHC_D void dispatch_tasks(const Ctx& c)
+FHC_D void dispatch_tasks(const Ctx& c, int align)
 {
-  block_align(c);
+  if (align) block_align(c);       // every picture must pass the same number of alignment points (see block_align)
 #ifdef FHC_DEVICE_BUILD
   if (c.nl > 1) { c.e->cmd.op = OP_TASKS; __syncwarp(c.mask); }
   run_tasks(c);

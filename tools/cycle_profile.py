@@ -4,10 +4,12 @@ import fasthevc_b200 as fh, fasthevc_b200.api as api
 api.library_path = lambda: 'fasthevc_b200/libfasthevc_cuda_prof.so'
 from fasthevc_b200.synth import synth_frames
 names=['TOTAL','PAR','RDOQ','COEFBITS','REFS_MASTER','RMD_MASTER','TUBLOCK','BITSQT','CUCOPY','RMD_PAR','ENCODE','TASKS_LUMA','TASKS_CHROMA','LUMA','CHROMA']
-def run(w,h,qp,sigma=6.0):
-    Y,U,V=synth_frames(w,h,1,sigma=sigma)
-    enc=fh.Encoder(w,h,8,max_frames=1)
-    sp=[fh.slice_params_from_qp(qp)]
+def run(w,h,qp,sigma=6.0,n=1):
+    Y,U,V=synth_frames(w,h,min(n,16),sigma=sigma)
+    reps=(n+Y.shape[0]-1)//Y.shape[0]
+    Y=np.concatenate([Y]*reps)[:n]; U=np.concatenate([U]*reps)[:n]; V=np.concatenate([V]*reps)[:n]
+    enc=fh.Encoder(w,h,8,max_frames=n)
+    sp=[fh.slice_params_from_qp(qp)]*n
     enc.submit(enc.pack_frames(Y,U,V),sp); o=enc.fetch_picture(0)
     cyc=(C.c_longlong*16)(); cnt=(C.c_longlong*16)()
     enc.lib.fhc_debug_profile.argtypes=[C.c_void_p,C.c_int,C.c_void_p,C.c_void_p]
@@ -22,4 +24,4 @@ def run(w,h,qp,sigma=6.0):
     for i,nm in enumerate(names2):
         if cnt[i]: print('  %-12s %6.1f%%  n=%8d  avg %8.0f cyc'%(nm,100.0*cyc[i]/tot,cnt[i],cyc[i]/cnt[i]))
     enc.close()
-run(192,128,32)
+run(192,128,32,n=int(sys.argv[1]) if len(sys.argv)>1 else 1)
