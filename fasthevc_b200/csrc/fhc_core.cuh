@@ -61,7 +61,7 @@ enum {
 };
 #define FHC_MAX_COST 1.7e+308
 #ifndef FHC_WARPS_PER_BLOCK
-#define FHC_WARPS_PER_BLOCK 16   /* warps (= pictures, FHC_GROUP 32) per thread block; the block keeps them aligned */
+#define FHC_WARPS_PER_BLOCK 20   /* warps (= pictures, FHC_GROUP 32) per thread block; the block keeps them aligned (measured: 16 -> 4495, 20 -> 4833, 24 -> 4643 CTU/s) */
 #endif
 #ifndef FHC_GROUP
 #define FHC_GROUP 32             /* lanes per picture: a warp encodes 32 / FHC_GROUP pictures side by side (sub-warp groups serialise) */
@@ -69,7 +69,13 @@ enum {
 #define FHC_MAX_MODES 10         /* the longest candidate list (8 RMD survivors + 2 MPMs) */
 #define FHC_MAX_TASKS 20         /* ... times the transform-skip pair of a 4x4 PU */
 #define FHC_NENG (FHC_GROUP < FHC_MAX_TASKS ? FHC_GROUP : FHC_MAX_TASKS)   /* lane engines per picture */
-#define FHC_SMALL_COEFS 64       /* TUs up to 8x8 use the warp's shared-memory scratch, larger ones the global scratch */
+#define FHC_SMALL_COEFS 64       /* lane engines: largest TU (8x8) */
+#ifndef FHC_MASTER_SMALL
+#define FHC_MASTER_SMALL 16      /* leader: TUs up to this many coefficients use the warp's shared-memory scratch, larger ones the global one */
+#endif
+#ifndef FHC_SLOT_SMEM_DEPTH
+#define FHC_SLOT_SMEM_DEPTH 2     /* context-set slots of depth >= this live in shared memory, shallower ones in global memory */
+#endif
 #define FHC_FULL_MASK 0xffffffffu
 
 // layout of the 6144-sample "YUV" buffers: Y at 0, Cb at 4096, Cr at 5120
@@ -132,6 +138,16 @@ struct Cmd
   void* dst;
 };
 
+// per-coefficient-group scratch of RDOQ / coefficient coding, sized by the number of 4x4 groups of the TU
+template <int N>
+struct GroupScratch
+{
+  double costCGSig[N];
+  uint8_t cgFlag[N], cgFlagCode[N];
+  uint16_t cgNzMask[N];
+  uint8_t cgAbs[N];
+};
+
 // per-coefficient scratch of one engine (TU pipeline + RDOQ), sized by the engine's largest TU
 template <int N>
 struct CoefScratch
@@ -161,7 +177,7 @@ struct Engine
   double *cost0, *costCoeff, *costSig;
   int32_t *rateIncUp, *rateIncDown, *sigRateDelta, *deltaU;
   int16_t tsCoef[3][16], tsRec[3][16], tsPred[3][16];
-  void *csSmall, *csLarge;        // coefficient scratch by TU size (master: <= 8x8 shared / larger global; lane: 4x4 shared / 8x8 global)
+  void *csSmall, *csLarge, *gsSmall, *gsLarge;        // coefficient scratch by TU size (master: <= 8x8 shared / larger global; lane: 4x4 shared / 8x8 global)
   // engine buffers: prediction/reconstruction of the CU under test and the per-TU-size layers; layerSize samples per
   // layer, component c at coff[c], luma rows qs apart (chroma qs / 2).  Master: 6144 / {0,4096,5120} / 64 (a CTU);
   // lane engine: 96 / {0,64,80} / 8 (an 8x8 CU, dense)
@@ -187,6 +203,11 @@ struct Engine
   int resTask;
 };
 
+template <int N>
+FHC_DH void bind_group_scratch(Engine* e, GroupScratch<N>* x)
+{
+  e->costCGSig = x->costCGSig; e->cgFlag = x->cgFlag; e->cgFlagCode = x->cgFlagCode; e->cgNzMask = x->cgNzMask; e->cgAbs = x->cgAbs;
+}
 FHC_DH int16_t* qt_rec(const Engine* e, int layer) { return e->qtRecBase + layer * e->layerSize; }
 FHC_DH int16_t* qt_coef(const Engine* e, int layer) { return e->qtCoefBase + layer * e->layerSize; }
 
@@ -256,6 +277,8 @@ struct FrameGlobal
   uint8_t cuStoreBig[2 * 12 * (256 + 64)];   // CU metadata of depth 0 and 1
   uint8_t qtTrIdx[256], qtCbf[3][256], qtTs[3][256];   // best-so-far TU flags of the PU under test
   CoefScratch<1024> big;          // TU pipeline + RDOQ scratch of 16x16 / 32x32 TUs
+  GroupScratch<64> bigGs;
+  Sbac slotLow[FHC_SLOT_SMEM_DEPTH + 1][CI_NUM];
   EngineGlobal eng[FHC_NENG];
 };
 
@@ -281,7 +304,7 @@ struct Shared
   const Tables* t;
   int alignThreads;               // threads of the block that take part in block_align (32 x pictures of this round)
   FrameParams fp;
-  Sbac slot[5][CI_NUM];
+  Sbac slot[5 - FHC_SLOT_SMEM_DEPTH][CI_NUM];   // depth FHC_SLOT_SMEM_DEPTH.. ; shallower: FrameGlobal::slotLow
   int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY;
   uint8_t bestIdx[4];
   CUMeta cu[4][2];
@@ -294,16 +317,14 @@ struct Shared
   uint8_t flags[72];
   union                          // a dispatch and a COOP TU of the master never overlap in time
   {
-    CoefScratch<FHC_SMALL_COEFS> cs;          // master: TUs up to 8x8
+    CoefScratch<FHC_MASTER_SMALL> cs;         // master: small TUs
   } u;
   uint32_t satd[36];
   int16_t refC[2][20];            // unfiltered reference lines of the 4x4 Cb / Cr block of an 8x8 CU
   int dcC[2];
-  double costCGSig[64], sigC0[28], sigC1[28];
+  double sigC0[28], sigC1[28];
   int32_t sigDelta[28];
-  uint8_t cgFlag[64], cgFlagCode[64];
-  uint16_t cgNzMask[64];
-  uint8_t cgAbs[64];
+  GroupScratch<4> gs;             // per-coefficient-group scratch of TUs up to 8x8 (larger: FrameGlobal::bigGs)
 };
 
 // lane/nl: this thread's index and the size of the lane group that executes COOP sections together (32 = the warp,
@@ -1078,9 +1099,13 @@ FHC_DH double dsub(double a, double b) { return a - b; }
 
 // context-set slots: the chain/CU-level slots live in shared memory (master); a thread engine aliases every depth of the
 // TU-level slots (CI_QT_TRAFO_*, CI_TEMP_BEST) onto its private set - a task only ever uses one depth of them.
+FHC_DH Sbac* chain_slot(const Ctx& c, int depth, int ci)
+{
+  return depth >= FHC_SLOT_SMEM_DEPTH ? &c.s->slot[depth - FHC_SLOT_SMEM_DEPTH][ci] : &c.g->slotLow[depth][ci];
+}
 FHC_DH Sbac* slot_of(const Ctx& c, int depth, int ci)
 {
-  if (c.e->kind == ENG_MASTER || ci == CI_CURR_BEST) return &c.s->slot[depth][ci];
+  if (c.e->kind == ENG_MASTER || ci == CI_CURR_BEST) return chain_slot(c, depth, ci);
   return &c.e->slots[ci == CI_QT_TRAFO_ROOT ? 0 : (ci == CI_TEMP_BEST ? 1 : 2)];
 }
 
@@ -1267,6 +1292,11 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   const int wg = n >> 2;
   const int firstSig = first_sig_ctx(log2n, scanType, isChroma);
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
+  if (e->kind == ENG_MASTER)
+  {
+    // group scratch by TU size (this function is also called outside code_tu_block, for TUs of any size)
+    if (log2n <= 3) bind_group_scratch(e, (GroupScratch<4>*)e->gsSmall); else bind_group_scratch(e, (GroupScratch<64>*)e->gsLarge);
+  }
   uint8_t* cgFlag = e->cgFlagCode;
   int scanPosLast = -1, posLast = 0;
 
@@ -1902,8 +1932,9 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   // coefficient scratch by TU size: the small one lives in the warp's shared-memory slice
   if (e->kind == ENG_MASTER)
   {
-    if (n * n <= FHC_SMALL_COEFS) bind_coef_scratch(e, (CoefScratch<FHC_SMALL_COEFS>*)e->csSmall);
+    if (n * n <= FHC_MASTER_SMALL) bind_coef_scratch(e, (CoefScratch<FHC_MASTER_SMALL>*)e->csSmall);
     else bind_coef_scratch(e, (CoefScratch<1024>*)e->csLarge);
+    if (n * n <= 64) bind_group_scratch(e, (GroupScratch<4>*)e->gsSmall); else bind_group_scratch(e, (GroupScratch<64>*)e->gsLarge);
   }
   else
   {
@@ -2830,13 +2861,15 @@ FHC_D void init_engines(FrameGlobal* g, Shared* s, const Tables* tables)
 {
   Engine* m = &s->master;
   s->t = tables;
-  m->kind = ENG_MASTER; m->t = tables; m->slots = &s->slot[0][0]; m->noAlign = 0; m->forceTs = -1; m->refsShared = 0; m->onlyComp = 0;
+  m->kind = ENG_MASTER; m->t = tables; m->slots = 0; m->noAlign = 0; m->forceTs = -1; m->refsShared = 0; m->onlyComp = 0;
   m->refU = s->refU; m->refF = s->refF; m->flags = s->flags; m->go = &s->masterGo;
   m->csSmall = &s->u.cs; m->csLarge = &g->big;
   bind_coef_scratch(m, &s->u.cs);
   m->predYuv = g->predYuv; m->qtRecBase = &g->qtRec[0][0]; m->qtCoefBase = &g->qtCoef[0][0]; m->writePic = 1;
   m->layerSize = 6144; m->qs = 64; m->coff[0] = 0; m->coff[1] = 4096; m->coff[2] = 5120;
-  m->costCGSig = s->costCGSig; m->cgFlag = s->cgFlag; m->cgFlagCode = s->cgFlagCode; m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta; m->cgNzMask = s->cgNzMask; m->cgAbs = s->cgAbs;
+  m->sigC0 = s->sigC0; m->sigC1 = s->sigC1; m->sigDelta = s->sigDelta;
+  m->gsSmall = &s->gs; m->gsLarge = &g->bigGs;
+  bind_group_scratch(m, &s->gs);
   {
     uint8_t* st = g->cuStoreBig;
     FHC_NOUNROLL for (int d = 0; d < 4; d++)
@@ -2897,7 +2930,7 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     const int puParts = np >> (2 * td.initTrDepth);
     const int layer = 5 - td.log2pu, n = 1 << td.log2pu;
     set_range(cu->ldir, td.partOffset, puParts, mode);
-    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, chain_slot(c, td.depth, CI_CURR_BEST));
     recur_luma_qt(c, cu, td.partOffset, td.log2pu, td.initTrDepth, 1, &dist, &cost);
     if (firstOfDispatch || cost < eg->resCost)
     {
@@ -2917,7 +2950,7 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     // transform skip is tried, TEncSearch.cpp:2022-2047), left in this task's engine for the bit-counting task
     uint32_t dist = 0;
     const int cc = 1 + (t & 1);
-    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, chain_slot(c, td.depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, np, mode);
     e->onlyComp = cc;
     recur_chroma_qt(c, cu, 0, ilog2(cu->width), 0, 1, &dist);
@@ -2934,7 +2967,7 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
     uint32_t dist = 0;
     const int log2cu = ilog2(cu->width);
     const int layer = 5 - (3 - (int)cu->tridx[0]);             // luma TU 8x8 (layer 2) or 4x4 (layer 3); chroma is 4x4 at index 0
-    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, chain_slot(c, td.depth, CI_CURR_BEST));
     set_range(cu->cdir, 0, np, mode);
     if (td.kind == TASK_CHROMA_CU) recur_chroma_qt(c, cu, 0, log2cu, 0, 1, &dist);
     else
@@ -2946,7 +2979,7 @@ FHC_D void run_task(const Ctx& mc, int engIdx, int t)
         par_copy2d(c, qt_rec(e, layer) + e->coff[cc], e->qs >> 1, a->bestReco[cc], 4, 4, 4);
         FHC_NOUNROLL for (int i = 0; i < np; i++) { cu->cbf[cc][i] = a->bestCbf[cc][i]; cu->ts[cc][i] = a->bestTs[cc][i]; }
       }
-    sb_copy(c, e->go, &s->slot[td.depth][CI_CURR_BEST]);
+    sb_copy(c, e->go, chain_slot(c, td.depth, CI_CURR_BEST));
     const double cost = rd_cost(c, intra_bits_qt(c, cu, 0, log2cu, 0, 1, 1, 0, 1), dist);
     if (firstOfDispatch || cost < eg->resCost)
     {
@@ -3003,7 +3036,7 @@ FHC_D void compress_picture(const Ctx& c)
   FrameGlobal* g = c.g;
   FHC_TIC(tot);
   FHC_NOUNROLL for (int d = 0; d < 4; d++) s->bestIdx[d] = 0;
-  sbac_reset(*s->t, &s->slot[0][CI_CURR_BEST], s->fp.sp.sliceQp);
+  sbac_reset(*s->t, chain_slot(c, 0, CI_CURR_BEST), s->fp.sp.sliceQp);
   const int numCtus = s->fp.wc * s->fp.hc;
   FHC_NOUNROLL for (int addr = 0; addr < numCtus; addr++)
   {

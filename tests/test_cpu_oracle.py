@@ -213,3 +213,15 @@ def test_two_rank_sharding_gloo():
                         "--master-port", "29713", script], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARD_OK" in r.stdout
+
+
+def test_kernel_shared_memory_budget():
+    """The persistent kernel needs its constant tables + one shared-memory slice per picture of a block; the launch
+    fails on the GPU box if that exceeds the 227 KB a B200 block may use, so check it where the build happens."""
+    import ctypes as C
+    import re
+    emu = C.CDLL(T.build_emu())
+    src = open(os.path.join(T.ROOT, "fasthevc_b200", "csrc", "fhc_core.cuh")).read()
+    warps = int(re.search(r"#define FHC_WARPS_PER_BLOCK (\d+)", src).group(1))
+    total = emu.fhc_emu_shared_bytes() * warps + 8192            # tables (7.1 KB) + rendezvous words, rounded up
+    assert total <= 227 * 1024, total

@@ -73,9 +73,9 @@ def test_cuda_mixed_qp_batch_is_independent():
 
 @pytest.mark.parametrize("n", [19, 37])
 def test_cuda_block_of_pictures_is_aligned_and_exact(n):
-    """A thread block keeps its 16 pictures (one warp each) on the same routine with a named barrier and pads shorter
-    candidate lists: different contents and QPs in one block, a partial last block (n not a multiple of 16), and every
-    picture must still equal the oracle."""
+    """A thread block keeps its pictures (one warp each, 20 per block) on the same routine with a named barrier and pads
+    shorter candidate lists: different contents and QPs in one block, a partial last block, and every picture must
+    still equal the oracle."""
     w, h = 136, 72
     Y, U, V = synth_frames(w, h, n, sigma=11.0, seed=7)
     qps = [22, 37, 27, 32]
