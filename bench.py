@@ -6,7 +6,7 @@
 A step = one pass of the hot path (TEncCu::xCompressCU and below, for every CTU of every picture) over one batch of
 synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, cycled to
 as many (picture, QP) jobs as the persistent kernel keeps in flight (`--jobs`, default fhc_pictures_in_flight = 148 SMs x
-16 pictures per block), one warp per picture.  Every timed step goes through the C ABI with host buffers (pinned H2D
+20 pictures per block), one warp per picture.  Every timed step goes through the C ABI with host buffers (pinned H2D
 of the pictures, kernel, D2H of every CTU record): `e2e` is the wall time of that, `value` the CUDA-event time of the
 kernel inside the same steps (inputs resident in HBM when it starts), max over ranks.  N > 1: one process per GPU
 (torchrun), every rank encodes its own contiguous frame group, no collective on the data path -
