@@ -36,7 +36,7 @@ CTUS = 30 * 17
 ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
 INT_OPS_PER_CTU = 40.0e6            # SURVEY.md 8(d) W_ctu (integer-equivalent ops, content dependent)
 WARM_H = 72                         # height of the warm-up strips
-NCU_DRAM_BYTES_PER_CTU = (223.78e9 + 151.52e9) / 2368     # profiles/r01_v3_aligned_w16_loaded.md
+NCU_DRAM_BYTES_PER_CTU = (459.21e9 + 247.55e9) / 2960     # profiles/r01_final_w20_loaded.md
 
 
 def load_peaks():
@@ -182,10 +182,11 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": round(NCU_DRAM_BYTES_PER_CTU * ctus_per_launch), "peak_source": peak_src,
-                         "traffic_note": "dram read+write of profiles/r01_v3_aligned_w16_loaded.md (2368 one-CTU pictures) scaled "
-                                         "by the CTUs of this launch: scratch and stack spill traffic, ~4300x the algorithmic bytes",
+                         "traffic_note": "dram read+write of the ncu --set full capture profiles/r01_final_w20_loaded.md (one launch of "
+                                         "2960 one-CTU pictures) scaled by the CTUs of this launch: per-warp scratch and stack traffic "
+                                         "that misses L2, ~6500x the algorithmic bytes, ~0.8 TB/s = 13 %% of the HBM peak",
                          "note": "the kernel is bound by instruction delivery and memory latency of one dependent chain per "
-                                 "picture, not by HBM or the tensor pipe (DESIGN.md 4): ncu issue-slot utilisation 18.7 %%; "
+                                 "picture, not by HBM or the tensor pipe (DESIGN.md 4): ncu issue-slot utilisation 23.4 %%, long-scoreboard 41 %% of the stall samples; "
                                  "integer-equivalent work %.1f Gop/s of ~37,000 Gop/s nominal int32 issue"
                                  % (INT_OPS_PER_CTU * fps * CTUS / world / 1e9)},
             "check_total_bits": check_bits,
