@@ -15,6 +15,9 @@ using namespace fhc;
 #define FHC_BLOCK_THREADS (32 * FHC_WARPS_PER_BLOCK)
 extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 
+#if FHC_GROUP != 32
+#error "the persistent kernel assumes one picture per warp (FHC_GROUP 32): sub-warp groups serialise, see DESIGN.md 4"
+#endif
 #define FHC_PICS_PER_WARP (32 / FHC_GROUP)
 #define FHC_PICS_PER_BLOCK (FHC_PICS_PER_WARP * FHC_WARPS_PER_BLOCK)
 static size_t tables_smem_bytes() { return (sizeof(Tables) + 15) & ~(size_t)15; }

@@ -476,7 +476,7 @@ FHC_DH int tcoefm(const Tables& t, int n, int k, int j, int useDst)
 {
   // 4x4 DST-VII matrix or rows of the 32-point DCT matrix
   if (useDst) return t.dst4[k * 4 + j];
-  return t.T32[((k * 32) >> (n == 4 ? 2 : n == 8 ? 3 : n == 16 ? 4 : 5)) * 32 + j];
+  return t.T32[(k * (32 / n)) * 32 + j];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1278,30 +1278,6 @@ FHC_DH void last_ctx_params(int isChroma, int log2n, int* off, int* shift)
 }
 FHC_DH int group_idx(int p) { return p < 4 ? p : (p < 6 ? 4 : (p < 8 ? 5 : (p < 12 ? 6 : (p < 16 ? 7 : (p < 24 ? 8 : 9))))); }
 
-// Bit counter of one coefficient block: the fractional-bit sum and the bin count stay in registers and are added to
-// the coder once at the end (integer sums: the order does not matter); contexts are stepped in place.
-struct BinAcc { const int32_t* ebits; const uint8_t (*ns)[2]; uint8_t* ctx; uint64_t frac; uint32_t bins; };
-FHC_DH void acc_bin(BinAcc& a, int ctx, int bin)
-{
-  const uint8_t st = a.ctx[ctx];
-  a.frac += (uint64_t)a.ebits[st ^ bin];
-  a.ctx[ctx] = a.ns[st][bin];
-  a.bins++;
-}
-FHC_DH void acc_ep(BinAcc& a, int n) { a.bins += (uint32_t)n; a.frac += (uint64_t)32768 * (uint64_t)n; }
-FHC_DH void acc_remain(BinAcc& a, uint32_t symbol, uint32_t rParam)                              // TEncSbac.cpp:337
-{
-  int codeNumber = (int)symbol;
-  if (codeNumber < (3 << rParam)) acc_ep(a, (int)(((uint32_t)codeNumber >> rParam) + 1 + rParam));
-  else
-  {
-    uint32_t length = rParam;
-    codeNumber -= (3 << rParam);
-    while (codeNumber >= (1 << length)) codeNumber -= (1 << (length++));
-    acc_ep(a, (int)(3 + length + 1 - rParam + length));
-  }
-}
-
 FHC_DH void code_remain(Engine* e, uint32_t symbol, uint32_t rParam)                            // TEncSbac.cpp:337
 {
   int codeNumber = (int)symbol;
@@ -1320,8 +1296,6 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
-  BinAcc ba;
-  ba.ebits = e->t->entropyBits; ba.ns = e->t->nextState; ba.ctx = e->go->c; ba.frac = 0; ba.bins = 0;
   const int isChroma = comp != 0, n = 1 << log2n;
   const int scanType = coef_scan_idx(cu, relIdxComp, n, comp);
   const uint16_t* scan = scan_tab(*s->t, scanType, log2n);
@@ -1337,7 +1311,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
   uint8_t* cgFlag = e->cgFlagCode;
   int scanPosLast = -1, posLast = 0;
 
-  if (log2n == 2) acc_bin(ba, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
+  if (log2n == 2) enc_bin(e, CTX_TS + isChroma, cu->ts[comp][relIdxComp]);
   // non-zero map per coefficient group (COOP for TUs of 8x8 and up), then last position and group flags from the maps
   const uint16_t* nzMask = e->cgNzMask;
   {
@@ -1360,12 +1334,12 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
     const int gx = group_idx(posX), gy = group_idx(posY), gmax = group_idx(n - 1);
     last_ctx_params(isChroma, log2n, &off, &shift);
     const int bx = CTX_LASTX + (isChroma ? 15 : 0) + off, by = CTX_LASTY + (isChroma ? 15 : 0) + off;
-    FHC_NOUNROLL for (cc = 0; cc < gx; cc++) acc_bin(ba, bx + (cc >> shift), 1);
-    if (gx < gmax) acc_bin(ba, bx + (cc >> shift), 0);
-    FHC_NOUNROLL for (cc = 0; cc < gy; cc++) acc_bin(ba, by + (cc >> shift), 1);
-    if (gy < gmax) acc_bin(ba, by + (cc >> shift), 0);
-    if (gx > 3) acc_ep(ba, (gx - 2) >> 1);
-    if (gy > 3) acc_ep(ba, (gy - 2) >> 1);
+    FHC_NOUNROLL for (cc = 0; cc < gx; cc++) enc_bin(e, bx + (cc >> shift), 1);
+    if (gx < gmax) enc_bin(e, bx + (cc >> shift), 0);
+    FHC_NOUNROLL for (cc = 0; cc < gy; cc++) enc_bin(e, by + (cc >> shift), 1);
+    if (gy < gmax) enc_bin(e, by + (cc >> shift), 0);
+    if (gx > 3) enc_ep(e, (gx - 2) >> 1);
+    if (gy > 3) enc_ep(e, (gy - 2) >> 1);
   }
   {
     const int lastScanSet = scanPosLast >> 4;
@@ -1384,7 +1358,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
         numNonZero = 1; lastNZ = scanPosSig; firstNZ = scanPosSig; scanPosSig--;
       }
       if (subSet == lastScanSet || subSet == 0) cgFlag[cgBlk] = 1;
-      else acc_bin(ba, CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg), cgFlag[cgBlk] != 0);
+      else enc_bin(e, CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg), cgFlag[cgBlk] != 0);
       if (cgFlag[cgBlk])
       {
         const int pat = pattern_sig_ctx(cgFlag, cgX, cgY, wg);
@@ -1393,7 +1367,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
         {
           const int blkPos = scan[scanPosSig], sig = (int)((cgMask >> (scanPosSig - subPos)) & 1u);
           if (scanPosSig > subPos || subSet == 0 || numNonZero)
-            acc_bin(ba, sigBase + sig_ctx_inc(*s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
+            enc_bin(e, sigBase + sig_ctx_inc(*s->t, pat, firstSig, blkPos, log2n, isChroma), sig);
           if (sig)
           {
             absCoeff[numNonZero++] = iabs(coef[blkPos]);
@@ -1413,18 +1387,18 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
         FHC_NOUNROLL for (int idx = 0; idx < numC1; idx++)
         {
           const int sym = absCoeff[idx] > 1;
-          acc_bin(ba, CTX_ONE + 4 * ctxSet + (int)c1, sym);
+          enc_bin(e, CTX_ONE + 4 * ctxSet + (int)c1, sym);
           if (sym) { c1 = 0; if (firstC2 == -1) firstC2 = idx; else escape = 1; }
           else if (c1 < 3 && c1 > 0) c1++;
         }
         if (c1 == 0 && firstC2 != -1)
         {
           const int sym = absCoeff[firstC2] > 2;
-          acc_bin(ba, CTX_ABS + ctxSet, sym);
+          enc_bin(e, CTX_ABS + ctxSet, sym);
           if (sym) escape = 1;
         }
         escape = escape || (numNonZero > 8);
-        acc_ep(ba, signHidden ? numNonZero - 1 : numNonZero);
+        enc_ep(e, signHidden ? numNonZero - 1 : numNonZero);
         if (escape)
         {
           int firstCoeff2 = 1;
@@ -1433,7 +1407,7 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
             const int baseLevel = (idx < 8) ? (2 + firstCoeff2) : 1;
             if (absCoeff[idx] >= baseLevel)
             {
-              acc_remain(ba, (uint32_t)(absCoeff[idx] - baseLevel), goRice);
+              code_remain(e, (uint32_t)(absCoeff[idx] - baseLevel), goRice);
               if (absCoeff[idx] > (3 << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
             }
             if (absCoeff[idx] >= 2) firstCoeff2 = 0;
@@ -1442,7 +1416,6 @@ FHC_NOINLINE void code_coeff_nxn_impl(const Ctx& c, const CUMeta* cu, int relIdx
       }
     }
   }
-  e->go->frac += ba.frac; e->bins += ba.bins;
 }
 
 FHC_DH void code_coeff_nxn(const Ctx& c, const CUMeta* cu, int relIdxComp, const int16_t* coef, int log2n, int comp)
@@ -1473,7 +1446,7 @@ FHC_DH QpParam qp_param(const Ctx& c, int comp)                                 
 FHC_DH int quant_scale(int rem) { return rem == 0 ? 26214 : rem == 1 ? 23302 : rem == 2 ? 20560 : rem == 3 ? 18396 : rem == 4 ? 16384 : 14564; }
 FHC_DH int inv_quant_scale(int rem) { return rem == 0 ? 40 : rem == 1 ? 45 : rem == 2 ? 51 : rem == 3 ? 57 : rem == 4 ? 64 : 72; }
 
-FHC_DH int ic_rate(const int32_t* ebits, const uint8_t* ctxc, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx)
+FHC_DH int ic_rate(const Engine* e, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx, uint32_t c2Idx)
 {
   int rate = 32768;
   const uint32_t baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
@@ -1490,16 +1463,16 @@ FHC_DH int ic_rate(const int32_t* ebits, const uint8_t* ctxc, uint32_t absLevel,
     }
     if (c1Idx < 8)
     {
-      rate += ebits[ctxc[ctxOne] ^ 1];
-      if (c2Idx < 1) rate += ebits[ctxc[ctxAbs] ^ 1];
+      rate += ctx_bits(e, ctxOne, 1);
+      if (c2Idx < 1) rate += ctx_bits(e, ctxAbs, 1);
     }
   }
-  else if (absLevel == 1) rate += ebits[ctxc[ctxOne] ^ 0];
-  else if (absLevel == 2) { rate += ebits[ctxc[ctxOne] ^ 1]; rate += ebits[ctxc[ctxAbs] ^ 0]; }
+  else if (absLevel == 1) rate += ctx_bits(e, ctxOne, 0);
+  else if (absLevel == 2) { rate += ctx_bits(e, ctxOne, 1); rate += ctx_bits(e, ctxAbs, 0); }
   else rate = 0;
   return rate;
 }
-FHC_DH uint32_t coded_level(const int32_t* ebits, const uint8_t* ctxc, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
+FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, double* codedCost0, double* codedCostSig, int levelDouble,
                             uint32_t maxAbsLevel, double sigCost0, double sigCost1, int ctxOne, int ctxAbs, uint32_t goRice, uint32_t c1Idx,
                             uint32_t c2Idx, int qBits, double errScale, int isLast)
 {
@@ -1518,7 +1491,7 @@ FHC_DH uint32_t coded_level(const int32_t* ebits, const uint8_t* ctxc, double la
   FHC_NOUNROLL for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
   {
     const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
-    double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(ebits, ctxc, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
+    double cur = dadd(dmul(dmul(err, err), errScale), dmul(lambda, (double)ic_rate(e, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx, c2Idx)));
     cur = dadd(cur, currCostSig);
     if (cur < *codedCost) { best = (uint32_t)absLevel; *codedCost = cur; *codedCostSig = currCostSig; }
   }
@@ -1529,8 +1502,6 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
 {
   Shared* s = c.s;
   Engine* e = c.e; (void)e;
-  const int32_t* const ebits = e->t->entropyBits;       // contexts do not change while a TU is being quantised
-  const uint8_t* const ctxc = e->go->c;
   const int isChroma = comp != 0, n = 1 << log2n, numCoef = n * n, bd = c.s->fp.bitDepth;
   const QpParam q = qp_param(c, comp);
   const int qBits = 14 + q.per + (15 - bd - log2n);
@@ -1569,13 +1540,13 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
     const int nSig = isChroma ? 16 : 28;
     FHC_NOUNROLL for (int i = 0; i < nSig; i++)
     {
-      const int b0 = ebits[ctxc[sigBase + i] ^ 0], b1 = ebits[ctxc[sigBase + i] ^ 1];
+      const int b0 = ctx_bits(e, sigBase + i, 0), b1 = ctx_bits(e, sigBase + i, 1);
       sigC0[i] = dmul(lambda, (double)b0); sigC1[i] = dmul(lambda, (double)b1); sigDelta[i] = b1 - b0;
     }
   }
-#define FHC_SIGC0(sc) (useTab ? sigC0[sc] : dmul(lambda, (double)ebits[ctxc[sigBase + (sc)] ^ 0]))
-#define FHC_SIGC1(sc) (useTab ? sigC1[sc] : dmul(lambda, (double)ebits[ctxc[sigBase + (sc)] ^ 1]))
-#define FHC_SIGDELTA(sc) (useTab ? sigDelta[sc] : ebits[ctxc[sigBase + (sc)] ^ 1] - ebits[ctxc[sigBase + (sc)] ^ 0])
+#define FHC_SIGC0(sc) (useTab ? sigC0[sc] : dmul(lambda, (double)ctx_bits(e, sigBase + (sc), 0)))
+#define FHC_SIGC1(sc) (useTab ? sigC1[sc] : dmul(lambda, (double)ctx_bits(e, sigBase + (sc), 1)))
+#define FHC_SIGDELTA(sc) (useTab ? sigDelta[sc] : ctx_bits(e, sigBase + (sc), 1) - ctx_bits(e, sigBase + (sc), 0))
 
   FHC_NOUNROLL for (int cgScanPos = cgNum - 1; cgScanPos >= 0; cgScanPos--)
   {
@@ -1610,7 +1581,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
       ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && (cgScanPos - 1) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
       c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
       const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
-      const double cgc = dmul(lambda, (double)ebits[ctxc[cx] ^ 0]);
+      const double cgc = dmul(lambda, (double)ctx_bits(e, cx, 0));
       baseCost = dadd(baseCost, dsub(cgc, sigCost));
       costCGSig[cgScanPos] = cgc;
       continue;
@@ -1644,7 +1615,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         costSig[scanPos] = cs; costCoeff[scanPos] = cc;
         sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         deltaU[blkPos] = levelDouble >> (qBits - 8);
-        rateIncUp[blkPos] = ebits[ctxc[ctxOne] ^ 0]; rateIncDown[blkPos] = 0;
+        rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0); rateIncDown[blkPos] = 0;
         baseCost = dadd(baseCost, cc);
         if (posInCG == 0 && scanPos > 0)
         {
@@ -1661,23 +1632,23 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         costCoeff[scanPos] = 0; costSig[scanPos] = 0;
         rateIncUp[blkPos] = 0; rateIncDown[blkPos] = 0; sigRateDelta[blkPos] = 0;
         if (scanPos == lastScanPos)
-          level = coded_level(ebits, ctxc, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+          level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               0.0, 0.0, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
         else
         {
           const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
-          level = coded_level(ebits, ctxc, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
+          level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               FHC_SIGC0(sc), FHC_SIGC1(sc), ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
           sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
         if (level > 0)
         {
-          const int rateNow = ic_rate(ebits, ctxc, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
-          rateIncUp[blkPos] = ic_rate(ebits, ctxc, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
-          rateIncDown[blkPos] = ic_rate(ebits, ctxc, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+          const int rateNow = ic_rate(e, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
+          rateIncUp[blkPos] = ic_rate(e, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+          rateIncDown[blkPos] = ic_rate(e, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
         }
-        else rateIncUp[blkPos] = ebits[ctxc[ctxOne] ^ 0];
+        else rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0);
         dst[blkPos] = (int32_t)level;
         baseCost = dadd(baseCost, costCoeff[scanPos]);
         const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
@@ -1709,17 +1680,17 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         if (cgFlag[cgBlk] == 0)
         {
           const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
-          baseCost = dadd(baseCost, dsub(dmul(lambda, (double)ebits[ctxc[cx] ^ 0]), sigCost));
-          costCGSig[cgScanPos] = dmul(lambda, (double)ebits[ctxc[cx] ^ 0]);
+          baseCost = dadd(baseCost, dsub(dmul(lambda, (double)ctx_bits(e, cx, 0)), sigCost));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 0));
         }
         else if (cgScanPos < cgLastScanPos)
         {
           if (nnzBeforePos0 == 0) { baseCost = dsub(baseCost, sigCost0); sigCost = dsub(sigCost, sigCost0); }
           double costZeroCG = baseCost;
           const int cx = CTX_SIGCG + (isChroma ? 2 : 0) + sig_cg_ctx(cgFlag, cgX, cgY, wg);
-          baseCost = dadd(baseCost, dmul(lambda, (double)ebits[ctxc[cx] ^ 1]));
-          costZeroCG = dadd(costZeroCG, dmul(lambda, (double)ebits[ctxc[cx] ^ 0]));
-          costCGSig[cgScanPos] = dmul(lambda, (double)ebits[ctxc[cx] ^ 1]);
+          baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(e, cx, 1)));
+          costZeroCG = dadd(costZeroCG, dmul(lambda, (double)ctx_bits(e, cx, 0)));
+          costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 1));
           costZeroCG = dadd(costZeroCG, uncodedDist);
           costZeroCG = dsub(costZeroCG, codedLevelAndDist);
           costZeroCG = dsub(costZeroCG, sigCost);
@@ -1727,7 +1698,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
           {
             cgFlag[cgBlk] = 0;
             baseCost = costZeroCG;
-            costCGSig[cgScanPos] = dmul(lambda, (double)ebits[ctxc[cx] ^ 0]);
+            costCGSig[cgScanPos] = dmul(lambda, (double)ctx_bits(e, cx, 0));
             FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
             {
               const int scanPos = cgScanPos * 16 + posInCG;
@@ -1742,8 +1713,8 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
   }
   if (lastScanPos < 0) return 0;
 
-  double bestCost = dadd(blockUncoded, dmul(lambda, (double)ebits[ctxc[cbfCtx] ^ 0]));
-  baseCost = dadd(baseCost, dmul(lambda, (double)ebits[ctxc[cbfCtx] ^ 1]));
+  double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(e, cbfCtx, 0)));
+  baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(e, cbfCtx, 1)));
   {
     int foundLast = 0, off, shift;
     last_ctx_params(isChroma, log2n, &off, &shift);
@@ -1765,10 +1736,10 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
             const uint32_t lx = scanType == SCAN_VER ? posY : posX, ly = scanType == SCAN_VER ? posX : posY;
             const int gx = group_idx((int)lx), gy = group_idx((int)ly);
             int bx = 0, by = 0, cc;
-            FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ebits[ctxc[bx0 + (cc >> shift)] ^ 1];
-            if (gx < gmax) bx += ebits[ctxc[bx0 + (gx >> shift)] ^ 0];
-            FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ebits[ctxc[by0 + (cc >> shift)] ^ 1];
-            if (gy < gmax) by += ebits[ctxc[by0 + (gy >> shift)] ^ 0];
+            FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ctx_bits(e, bx0 + (cc >> shift), 1);
+            if (gx < gmax) bx += ctx_bits(e, bx0 + (gx >> shift), 0);
+            FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ctx_bits(e, by0 + (cc >> shift), 1);
+            if (gy < gmax) by += ctx_bits(e, by0 + (gy >> shift), 0);
             double cost = (double)(bx + by);
             if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
             if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
