@@ -93,6 +93,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"                  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_jobs = args.jobs if args.jobs > 0 else fh.pictures_in_flight(local_rank)
     # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
