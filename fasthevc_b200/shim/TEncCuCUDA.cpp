@@ -1,0 +1,152 @@
+// TEncCuCUDA.cpp - the TLibEncoderCUDA shim: host side of the drop-in boundary, written against the reference's own
+// classes (HM 16.14 as shipped in omricarmi/FastHEVC).  It is what INTEGRATION.md asks a maintainer to add to
+// source/Lib/TLibEncoderCUDA/: TEncCu::compressCtu (source/Lib/TLibEncoder/TEncCu.cpp:252-288) keeps its call
+// surface, the one call to xCompressCU(depth 0) (TEncCu.cpp:260) becomes fhc_shim_compress_ctu(this, pCtu), and
+// TEncTop / TEncGOP / TEncSlice, the cfg options and the bitstream writer stay as they are.
+//
+// What it does, per CTU:
+//   * first CTU of a picture: packs the original planes (TComPicYuv, Pel = int16 with margins) into the planar buffer
+//     of fhc_submit_frames and passes the doubles the unchanged host already computed (TEncSlice::setUpLambda,
+//     TEncSlice.cpp:112-144) bit for bit;
+//   * every CTU: fhc_fetch_ctu, then leaves behind exactly what xCompressCU leaves behind - the picture-level
+//     TComDataCU as TComDataCU::copyToPic fills it (TComDataCU.cpp:906-979) and the reconstruction in PicYuvRec as
+//     TEncCu::xCopyYuv2Pic does (TEncCu.cpp:1729).  The caller re-codes the CTU on RD[0][CI_CURR_BEST] itself
+//     (TEncSlice.cpp:886-893).
+// This demonstration shim submits one picture at a time; a production host reads fhc_pictures_in_flight() pictures
+// ahead (all-intra pictures are independent) so that the device is full.
+//
+// Error behaviour mirrors HM: print + exit (TEncSbac.cpp:1220-1235).
+//
+// Built only by oracle/build_ref.py against /root/reference (no reference source enters this repository); the build
+// reads two private members of TEncCu, which a maintainer would expose with a friend declaration instead.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdint.h>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <vector>
+#include <list>
+#include <map>
+#include <string>
+#include <algorithm>
+#include <deque>
+#include <bitset>
+#include <iomanip>
+#include <functional>
+#define private public
+#define protected public
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComSlice.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComTrQuant.h"
+#include "TLibEncoder/TEncCu.h"
+#undef private
+#undef protected
+#include "fasthevc_cuda.h"
+
+static fhc_ctx* g_ctx = NULL;
+static int g_width = 0, g_height = 0, g_bitDepth = 0;
+static std::vector<unsigned char> g_yuv;
+
+static void fhc_die(const char* what)
+{
+  fprintf(stderr, "TLibEncoderCUDA: %s failed: %s\n", what, fhc_last_error());
+  exit(1);
+}
+
+static void submit_picture(TEncCu* enc, TComDataCU* pCtu)
+{
+  TComPic* pic = pCtu->getPic();
+  TComSlice* slice = pCtu->getSlice();
+  const TComPicYuv* org = pic->getPicYuvOrg();
+  const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
+  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
+  if (g_ctx && (w != g_width || h != g_height || bd != g_bitDepth)) { fhc_destroy(g_ctx); g_ctx = NULL; }
+  if (!g_ctx)
+  {
+    fhc_seq_params p;
+    memset(&p, 0, sizeof(p));
+    p.width = w; p.height = h; p.bitDepth = bd; p.chromaFormat = 1;
+    p.ctuSize = 64; p.maxCuDepth = 4; p.tuLog2Max = 5; p.tuLog2Min = 2; p.tuMaxDepthIntra = 3;
+    p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
+    p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
+    p.maxFramesInFlight = 1;
+    if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
+    g_width = w; g_height = h; g_bitDepth = bd;
+  }
+  const int sampleBytes = bd > 8 ? 2 : 1;
+  g_yuv.resize((size_t)w * h * 3 / 2 * sampleBytes);
+  size_t pos = 0;
+  for (int c = 0; c < 3; c++)
+  {
+    const ComponentID id = ComponentID(c);
+    const int cw = org->getWidth(id), ch = org->getHeight(id), stride = org->getStride(id);
+    const Pel* src = org->getAddr(id);
+    for (int y = 0; y < ch; y++)
+      for (int x = 0; x < cw; x++)
+      {
+        const Pel v = src[y * stride + x];
+        if (sampleBytes == 1) g_yuv[pos++] = (unsigned char)v;
+        else { g_yuv[pos++] = (unsigned char)(v & 255); g_yuv[pos++] = (unsigned char)(v >> 8); }
+      }
+  }
+  fhc_slice_params sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.sliceQp = slice->getSliceQp();
+  sp.lambda = enc->m_pcRdCost->getLambda();
+  sp.sqrtLambda = enc->m_pcRdCost->getSqrtLambda();
+  sp.chromaDistWeight[0] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cb];
+  sp.chromaDistWeight[1] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cr];
+  for (int c = 0; c < 3; c++) sp.rdoqLambda[c] = enc->m_pcTrQuant->m_lambdas[c];
+  if (fhc_submit_frames(g_ctx, slice->getPOC(), 1, g_yuv.data(), sampleBytes, &sp) != FHC_OK) fhc_die("fhc_submit_frames");
+}
+
+void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
+{
+  static fhc_ctu_result r;
+  const int addr = (int)pCtu->getCtuRsAddr();
+  if (addr == 0) submit_picture(enc, pCtu);
+  if (fhc_fetch_ctu(g_ctx, pCtu->getSlice()->getPOC(), addr, &r) != FHC_OK) fhc_die("fhc_fetch_ctu");
+
+  // TComDataCU::copyToPic: the per-partition arrays an intra CTU decision changes (everything else keeps the values
+  // TComDataCU::initCtu gave it just before compressCtu, TEncSlice.cpp:797)
+  for (unsigned i = 0; i < 256; i++)
+  {
+    pCtu->getDepth()[i] = r.depth[i];
+    pCtu->getWidth()[i] = pCtu->getHeight()[i] = (UChar)(64 >> r.depth[i]);
+    pCtu->getPartitionSize()[i] = (SChar)r.partSize[i];
+    pCtu->getPredictionMode()[i] = (SChar)r.predMode[i];
+    pCtu->getIntraDir(CHANNEL_TYPE_LUMA)[i] = r.lumaDir[i];
+    pCtu->getIntraDir(CHANNEL_TYPE_CHROMA)[i] = r.chromaDir[i];
+    pCtu->getTransformIdx()[i] = r.trIdx[i];
+    for (unsigned c = 0; c < 3; c++)
+    {
+      pCtu->getCbf(ComponentID(c))[i] = r.cbf[c][i];
+      pCtu->getTransformSkip(ComponentID(c))[i] = r.transformSkip[c][i];
+    }
+  }
+  for (unsigned i = 0; i < 4096; i++) pCtu->getCoeff(COMPONENT_Y)[i] = r.coefY[i];
+  for (unsigned i = 0; i < 1024; i++) { pCtu->getCoeff(COMPONENT_Cb)[i] = r.coefCb[i]; pCtu->getCoeff(COMPONENT_Cr)[i] = r.coefCr[i]; }
+  pCtu->getTotalCost() = r.totalCost;
+  pCtu->getTotalDistortion() = r.totalDist;
+  pCtu->getTotalBits() = r.totalBits;
+  pCtu->getTotalBins() = r.totalBins;
+
+  // TEncCu::xCopyYuv2Pic: reconstruction of the CTU into the picture (samples inside the picture only)
+  TComPicYuv* rec = pCtu->getPic()->getPicYuvRec();
+  const int x0 = (int)pCtu->getCUPelX(), y0 = (int)pCtu->getCUPelY();
+  for (int c = 0; c < 3; c++)
+  {
+    const ComponentID id = ComponentID(c);
+    const int sh = c ? 1 : 0, n = 64 >> sh, stride = rec->getStride(id);
+    const int cw = rec->getWidth(id), ch = rec->getHeight(id);
+    Pel* dst = rec->getAddr(id, addr);
+    const int16_t* src = c == 0 ? r.recoY : (c == 1 ? r.recoCb : r.recoCr);
+    for (int y = 0; y < n && (y0 >> sh) + y < ch; y++)
+      for (int x = 0; x < n && (x0 >> sh) + x < cw; x++) dst[y * stride + x] = src[y * n + x];
+  }
+}

@@ -12,12 +12,17 @@ Outputs (all git-ignored, all under oracle/_ref/):
   TAppEncoder      stock encoder, HARP hooks removed
   TAppEncoderDump  same + oracle/ref_dump_hook.cpp (per-CTU golden dumps via FHC_DUMP=file)
   TAppDecoder      stock decoder (conformance checker: MD5 SEI)
+  TAppEncoderFHC   the reference encoder with the drop-in boundary wired in: TEncCu::compressCtu calls the
+                   TLibEncoderCUDA shim (fasthevc_b200/shim/TEncCuCUDA.cpp) instead of xCompressCU(depth 0) and is
+                   linked against libfasthevc_cuda.so (RUNPATH $ORIGIN/../../fasthevc_b200, so LD_LIBRARY_PATH can
+                   substitute the tests' emulated ABI) - whole-bitstream byte identity, end to end
   cfg/             the two cfg files the metric uses (tiny text files, needed on the GPU box)
 
 Patched sites (reference file:line):
   source/App/TAppEncoder/encmain.cpp:47-49,99-110   HARP includes + Global init + consts.json
   source/App/TAppEncoder/TAppEncCfg.cpp:49,1587     HARP include + Global.inputFilename
   source/Lib/TLibEncoder/TEncGOP.cpp:49,1562        HARP include + CShow_PredResiReco dump
+  source/Lib/TLibEncoder/TEncCu.cpp:260             (TAppEncoderFHC only) xCompressCU(depth 0) -> fhc_shim_compress_ctu
 """
 import os, re, shutil, subprocess, sys, concurrent.futures as cf
 
@@ -89,6 +94,21 @@ def dump_sources(scratch):
     return out
 
 
+def fhc_sources(scratch):
+    """TEncCu.cpp of the integrated encoder: the single call site of the hot path goes to the shim."""
+    src = os.path.join(REF, "source")
+    rel = "Lib/TLibEncoder/TEncCu.cpp"
+    t = open(os.path.join(src, rel)).read()
+    call = "xCompressCU( m_ppcBestCU[0], m_ppcTempCU[0], 0 DEBUG_STRING_PASS_INTO(sDebug) );"
+    assert t.count(call) == 1, t.count(call)
+    t = t.replace(call, "fhc_shim_compress_ctu(this, pCtu);")
+    t = t.replace("Void TEncCu::compressCtu( TComDataCU* pCtu )\n{", "void fhc_shim_compress_ctu(TEncCu*, TComDataCU*);\nVoid TEncCu::compressCtu( TComDataCU* pCtu )\n{", 1)
+    dst = os.path.join(scratch, "fhc", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    return {rel: dst}
+
+
 def compile_one(job):
     srcfile, obj, incs, extra = job
     if os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(srcfile):
@@ -114,6 +134,7 @@ def main():
     src = os.path.join(REF, "source")
     stub = patched_sources(scratch)
     dump = dump_sources(scratch)
+    fhc = fhc_sources(scratch)
     incs = ["-I" + os.path.join(src, "Lib"), "-I" + os.path.join(src, "App"), "-I" + os.path.join(src, "App/TAppEncoder")]
 
     def listing(d, exts=(".cpp", ".c")):
@@ -123,10 +144,13 @@ def main():
     enc = listing("Lib/TLibEncoder") + listing("App/TAppEncoder")
     dec = listing("Lib/TLibDecoder") + listing("App/TAppDecoder")
 
-    jobs, objs = [], {"enc": [], "dump": [], "dec": []}
+    jobs, objs = [], {"enc": [], "dump": [], "dec": [], "fhc": []}
     def add(rel, which):
         tagged = rel.replace("/", "_")
-        if which == "dump" and rel in dump:
+        if which == "fhc" and rel in fhc:
+            s, o = fhc[rel], os.path.join(objdir, "fhc_" + tagged + ".o")
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        elif which == "dump" and rel in dump:
             s, o = dump[rel], os.path.join(objdir, "dump_" + tagged + ".o")
             # quoted relative includes resolve against the original directory
             extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
@@ -141,14 +165,18 @@ def main():
         objs[which].append(o)
 
     for rel in common:
-        add(rel, "enc"); add(rel, "dump"); add(rel, "dec")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "dec"); add(rel, "fhc")
     for rel in enc:
-        add(rel, "enc"); add(rel, "dump")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "fhc")
     for rel in dec:
         add(rel, "dec")
     hook_o = os.path.join(objdir, "ref_dump_hook.o")
     jobs.append((os.path.join(HERE, "ref_dump_hook.cpp"), hook_o, incs, []))
     objs["dump"].append(hook_o)
+    repo = os.path.dirname(HERE)
+    shim_o = os.path.join(objdir, "TEncCuCUDA.o")
+    jobs.append((os.path.join(repo, "fasthevc_b200", "shim", "TEncCuCUDA.cpp"), shim_o, incs + ["-I" + os.path.join(repo, "include")], []))
+    objs["fhc"].append(shim_o)
 
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(compile_one, jobs))
@@ -158,6 +186,12 @@ def main():
     os.makedirs(os.path.join(OUT, "cfg"), exist_ok=True)
     for c in ("encoder_intra_main.cfg", "encoder_intra_main10.cfg"):
         shutil.copy(os.path.join(REF, "cfg", c), os.path.join(OUT, "cfg", c))
+    libdir = os.path.join(repo, "fasthevc_b200")
+    if os.path.exists(os.path.join(libdir, "libfasthevc_cuda.so")):
+        subprocess.check_call([CXX, "-O2", "-o", os.path.join(OUT, "TAppEncoderFHC")] + sorted(set(objs["fhc"])) +
+                              ["-L" + libdir, "-lfasthevc_cuda", "-Wl,--enable-new-dtags", "-Wl,-rpath,$ORIGIN/../../fasthevc_b200", "-lm"])
+    else:
+        print("build_ref: libfasthevc_cuda.so not built yet - TAppEncoderFHC skipped")
     shutil.rmtree(scratch, ignore_errors=True)
     shutil.rmtree(objdir, ignore_errors=True)
     print("build_ref: built", sorted(os.listdir(OUT)))

@@ -1,0 +1,42 @@
+// TEST INFRASTRUCTURE: the subset of include/fasthevc_cuda.h that the TLibEncoderCUDA shim calls, implemented on the
+// host emulation build of the kernel source (tests/emu_harness.cpp).  Lets the CPU suite run the reference encoder with
+// the shim (oracle/_ref/TAppEncoderFHC) and compare its bitstream with the stock reference without a GPU.  Built into
+// tests/_build/libfasthevc_cuda.so and selected with LD_LIBRARY_PATH by the test only; never shipped.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../include/fasthevc_cuda.h"
+
+extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                        const void* y, const void* cb, const void* cr, fhc_ctu_result* out);
+
+struct fhc_ctx { fhc_seq_params seq; int poc, numCtus; std::vector<fhc_ctu_result> out; };
+
+extern "C" {
+const char* fhc_last_error(void) { return "emulated ABI"; }
+int fhc_create(const fhc_seq_params* seq, int, fhc_ctx** out)
+{
+  fhc_ctx* c = new fhc_ctx();
+  c->seq = *seq; c->poc = -1;
+  c->numCtus = ((seq->width + 63) / 64) * ((seq->height + 63) / 64);
+  *out = c;
+  return FHC_OK;
+}
+int fhc_destroy(fhc_ctx* c) { delete c; return FHC_OK; }
+int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* sp)
+{
+  if (n != 1) return FHC_ERR_ARG;
+  const size_t luma = (size_t)c->seq.width * c->seq.height * sampleBytes;
+  const unsigned char* p = (const unsigned char*)yuv;
+  c->out.assign((size_t)c->numCtus, fhc_ctu_result());
+  c->poc = first_poc;
+  return fhc_emu_compress_picture(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, sp, p, p + luma, p + luma + luma / 4, c->out.data());
+}
+int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
+{
+  if (poc != c->poc || addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
+  *out = c->out[(size_t)addr];
+  return FHC_OK;
+}
+}

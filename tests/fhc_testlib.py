@@ -115,17 +115,36 @@ def have_ref():
     return os.path.exists(os.path.join(REF_DIR, "TAppEncoderDump"))
 
 
-def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dump=True, extra=()):
-    """Runs oracle/_ref/TAppEncoder[Dump]; returns (bitstream bytes, dump path or None, stdout)."""
-    exe = os.path.join(REF_DIR, "TAppEncoderDump" if dump else "TAppEncoder")
+def have_integrated():
+    return os.path.exists(os.path.join(REF_DIR, "TAppEncoderFHC")) and os.path.exists(os.path.join(REF_DIR, "TAppEncoder"))
+
+
+def build_emu_abi():
+    """Test-only libfasthevc_cuda.so: the ABI subset the shim calls, on the host emulation build of the kernel source."""
+    out_dir = os.path.join(ROOT, "tests", "_build", "abi")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libfasthevc_cuda.so")
+    srcs = [os.path.join(ROOT, "tests", "emu_abi.cpp"), os.path.join(ROOT, "tests", "emu_harness.cpp"),
+            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_core.cuh"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_tables.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, srcs[0], srcs[1], "-lm"])
+    return out_dir
+
+
+def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dump=True, extra=(), exe=None, lib_dir=None, tag=""):
+    """Runs oracle/_ref/TAppEncoder[Dump] (or `exe`); returns (bitstream bytes, dump path or None, stdout).
+    lib_dir: directory put in front of the library search path (the integrated encoder's libfasthevc_cuda.so)."""
+    exe = os.path.join(REF_DIR, exe or ("TAppEncoderDump" if dump else "TAppEncoder"))
     cfg = os.path.join(REF_DIR, "cfg", "encoder_intra_main.cfg" if bit_depth == 8 else "encoder_intra_main10.cfg")
-    bs = os.path.join(workdir, "out.bin")
+    bs = os.path.join(workdir, "out%s.bin" % tag)
     dp = os.path.join(workdir, "dump.bin")
     env = dict(os.environ)
+    if lib_dir:
+        env["LD_LIBRARY_PATH"] = lib_dir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
     if dump:
         env["FHC_DUMP"] = dp
     cmd = [exe, "-c", cfg, "-i", yuv_path, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),
-           "-q", str(qp), "-b", bs, "-o", os.path.join(workdir, "rec.yuv"), "--SEIDecodedPictureHash=1"]
+           "-q", str(qp), "-b", bs, "-o", os.path.join(workdir, "rec%s.yuv" % tag), "--SEIDecodedPictureHash=1"]
     if bit_depth != 8:
         cmd += ["--InputBitDepth=%d" % bit_depth]
     cmd += list(extra)
@@ -204,3 +223,10 @@ def emu_compress(params, y, u, v):
                                        planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data)
     assert rc == 0
     return out
+
+
+def decoder_md5_ok(bitstream_path, workdir):
+    """TAppDecoder on the bitstream: number of pictures whose MD5 SEI matched, and whether any mismatched."""
+    r = subprocess.run([os.path.join(REF_DIR, "TAppDecoder"), "-b", bitstream_path, "-o", os.path.join(workdir, "dec.yuv")],
+                       capture_output=True, text=True, cwd=workdir)
+    return r.stdout.count("(OK)"), ("ERROR" in r.stdout or r.returncode != 0)

@@ -225,3 +225,22 @@ def test_kernel_shared_memory_budget():
     warps = int(re.search(r"#define FHC_WARPS_PER_BLOCK (\d+)", src).group(1))
     total = emu.fhc_emu_shared_bytes() * warps + 8192            # tables (7.1 KB) + rendezvous words, rounded up
     assert total <= 227 * 1024, total
+
+
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC not built")
+@pytest.mark.parametrize("w,h,n,qp,bd,sigma", [(200, 136, 2, 27, 8, 12.0), (136, 72, 2, 32, 10, 10.0)])
+def test_integrated_encoder_bitstream_is_byte_identical_emulated(w, h, n, qp, bd, sigma):
+    """The reference encoder with TEncCu::compressCtu wired to the TLibEncoderCUDA shim (fasthevc_b200/shim), the
+    shim's C ABI served by the host emulation of the kernel source: the Annex-B bitstream and the reconstruction are
+    byte-identical to the stock reference's, and the decoder's MD5 SEI check passes.  Proves that what
+    fhc_fetch_ctu returns is everything the unchanged host needs (the GPU suite repeats this with the CUDA library)."""
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, bit_depth=bd, sigma=sigma, seed=11)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, bit_depth=bd, dump=False, tag="_ref")
+    got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, bit_depth=bd, dump=False, exe="TAppEncoderFHC",
+                                lib_dir=T.build_emu_abi(), tag="_fhc")
+    assert got == ref
+    assert open(os.path.join(d, "rec_fhc.yuv"), "rb").read() == open(os.path.join(d, "rec_ref.yuv"), "rb").read()
+    ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
+    assert ok == n and not bad

@@ -141,3 +141,20 @@ def test_full_size_1080p_properties():
     # the crop's below-left availability differs at the picture bottom (row 64 does not exist in the crop) -> only
     # compare when nothing differs; report instead of failing hard on that known geometric difference
     assert len(bad) < 30 * len(T.FIELDS)
+
+
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC did not travel")
+def test_integrated_encoder_bitstream_is_byte_identical_cuda():
+    """BASELINE configs[0] geometry (416x240, QP 32, boundary CTUs) through the reference encoder whose
+    TEncCu::compressCtu calls the TLibEncoderCUDA shim, linked against libfasthevc_cuda.so: the whole Annex-B bitstream
+    is byte-identical to the stock reference encoder's and decodes with matching MD5 SEI."""
+    w, h, n, qp = 416, 240, 2, 32
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, sigma=6.0)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, tag="_ref")
+    got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", tag="_fhc")
+    assert got == ref
+    assert open(os.path.join(d, "rec_fhc.yuv"), "rb").read() == open(os.path.join(d, "rec_ref.yuv"), "rb").read()
+    ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
+    assert ok == n and not bad
