@@ -12,8 +12,7 @@
 //     TComDataCU as TComDataCU::copyToPic fills it (TComDataCU.cpp:906-979) and the reconstruction in PicYuvRec as
 //     TEncCu::xCopyYuv2Pic does (TEncCu.cpp:1729).  The caller re-codes the CTU on RD[0][CI_CURR_BEST] itself
 //     (TEncSlice.cpp:886-893).
-// This demonstration shim submits one picture at a time; a production host reads fhc_pictures_in_flight() pictures
-// ahead (all-intra pictures are independent) so that the device is full.
+// With FHC_SHIM_INPUT set it reads ahead (see lookahead()) so that the device encodes many pictures at once.
 //
 // Error behaviour mirrors HM: print + exit (TEncSbac.cpp:1220-1235).
 //
@@ -49,8 +48,11 @@
 #include "fasthevc_cuda.h"
 
 static fhc_ctx* g_ctx = NULL;
-static int g_width = 0, g_height = 0, g_bitDepth = 0;
-static std::vector<unsigned char> g_yuv;
+static int g_width = 0, g_height = 0, g_bitDepth = 0, g_maxFrames = 0;
+static int g_batchFirst = -1, g_batchN = 0;          // POC range of the pictures the device holds
+static fhc_slice_params g_batchSp;
+static std::vector<unsigned char> g_yuv;              // the submitted batch, picture after picture
+static std::vector<unsigned char> g_cur;              // the picture the host is working on, packed the same way
 
 static void fhc_die(const char* what)
 {
@@ -58,29 +60,33 @@ static void fhc_die(const char* what)
   exit(1);
 }
 
-static void submit_picture(TEncCu* enc, TComDataCU* pCtu)
+// Read-ahead.  All-intra pictures are independent, so the device can encode pictures the host loop has not reached yet.
+// The unchanged host reads the input one frame at a time (TAppEncTop::encode), so the shim reads the following frames
+// itself from the same file (FHC_SHIM_INPUT, planar 4:2:0 in the internal bit depth, no frame skip) and submits up to
+// FHC_SHIM_LOOKAHEAD pictures (default fhc_pictures_in_flight) with the slice parameters of the first one - in the
+// all-intra cfg every picture has the same QP and lambdas.  Nothing is assumed, though: when the host reaches a
+// picture, its original planes and its slice parameters are compared with what was submitted, and the picture is
+// re-submitted alone if anything differs.  Without FHC_SHIM_INPUT the shim submits one picture at a time.
+static int lookahead()
 {
-  TComPic* pic = pCtu->getPic();
-  TComSlice* slice = pCtu->getSlice();
-  const TComPicYuv* org = pic->getPicYuvOrg();
-  const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
-  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
-  if (g_ctx && (w != g_width || h != g_height || bd != g_bitDepth)) { fhc_destroy(g_ctx); g_ctx = NULL; }
-  if (!g_ctx)
+  static int n = -1;
+  if (n < 0)
   {
-    fhc_seq_params p;
-    memset(&p, 0, sizeof(p));
-    p.width = w; p.height = h; p.bitDepth = bd; p.chromaFormat = 1;
-    p.ctuSize = 64; p.maxCuDepth = 4; p.tuLog2Max = 5; p.tuLog2Min = 2; p.tuMaxDepthIntra = 3;
-    p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
-    p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
-    p.maxFramesInFlight = 1;
-    if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
-    g_width = w; g_height = h; g_bitDepth = bd;
+    n = 1;
+    if (getenv("FHC_SHIM_INPUT"))
+    {
+      const char* e = getenv("FHC_SHIM_LOOKAHEAD");
+      n = e ? atoi(e) : fhc_pictures_in_flight(0);
+      if (n < 1) n = 1;
+    }
   }
-  const int sampleBytes = bd > 8 ? 2 : 1;
-  g_yuv.resize((size_t)w * h * 3 / 2 * sampleBytes);
+  return n;
+}
+
+static void pack_picture(const TComPicYuv* org, int sampleBytes, std::vector<unsigned char>& out)
+{
   size_t pos = 0;
+  out.resize((size_t)org->getWidth(COMPONENT_Y) * org->getHeight(COMPONENT_Y) * 3 / 2 * sampleBytes);
   for (int c = 0; c < 3; c++)
   {
     const ComponentID id = ComponentID(c);
@@ -90,10 +96,21 @@ static void submit_picture(TEncCu* enc, TComDataCU* pCtu)
       for (int x = 0; x < cw; x++)
       {
         const Pel v = src[y * stride + x];
-        if (sampleBytes == 1) g_yuv[pos++] = (unsigned char)v;
-        else { g_yuv[pos++] = (unsigned char)(v & 255); g_yuv[pos++] = (unsigned char)(v >> 8); }
+        if (sampleBytes == 1) out[pos++] = (unsigned char)v;
+        else { out[pos++] = (unsigned char)(v & 255); out[pos++] = (unsigned char)(v >> 8); }
       }
   }
+}
+
+static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
+{
+  TComPic* pic = pCtu->getPic();
+  TComSlice* slice = pCtu->getSlice();
+  const TComPicYuv* org = pic->getPicYuvOrg();
+  const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
+  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
+  const int sampleBytes = bd > 8 ? 2 : 1, poc = slice->getPOC();
+  const size_t frameBytes = (size_t)w * h * 3 / 2 * sampleBytes;
   fhc_slice_params sp;
   memset(&sp, 0, sizeof(sp));
   sp.sliceQp = slice->getSliceQp();
@@ -102,14 +119,52 @@ static void submit_picture(TEncCu* enc, TComDataCU* pCtu)
   sp.chromaDistWeight[0] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cb];
   sp.chromaDistWeight[1] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cr];
   for (int c = 0; c < 3; c++) sp.rdoqLambda[c] = enc->m_pcTrQuant->m_lambdas[c];
-  if (fhc_submit_frames(g_ctx, slice->getPOC(), 1, g_yuv.data(), sampleBytes, &sp) != FHC_OK) fhc_die("fhc_submit_frames");
+  pack_picture(org, sampleBytes, g_cur);
+
+  // already on the device, with these samples and these parameters?
+  if (g_ctx && poc >= g_batchFirst && poc < g_batchFirst + g_batchN && w == g_width && h == g_height && bd == g_bitDepth &&
+      memcmp(&sp, &g_batchSp, sizeof(sp)) == 0 && memcmp(g_cur.data(), g_yuv.data() + (size_t)(poc - g_batchFirst) * frameBytes, frameBytes) == 0)
+    return;
+
+  int n = lookahead();
+  const int left = enc->m_pcEncCfg->getFramesToBeEncoded() - poc;
+  if (n > left) n = left;
+  if (n < 1) n = 1;
+  if (g_ctx && (w != g_width || h != g_height || bd != g_bitDepth || n > g_maxFrames)) { fhc_destroy(g_ctx); g_ctx = NULL; }
+  if (!g_ctx)
+  {
+    fhc_seq_params p;
+    memset(&p, 0, sizeof(p));
+    p.width = w; p.height = h; p.bitDepth = bd; p.chromaFormat = 1;
+    p.ctuSize = 64; p.maxCuDepth = 4; p.tuLog2Max = 5; p.tuLog2Min = 2; p.tuMaxDepthIntra = 3;
+    p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
+    p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
+    p.maxFramesInFlight = n;
+    if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
+    g_width = w; g_height = h; g_bitDepth = bd; g_maxFrames = n;
+  }
+  g_yuv.resize(frameBytes * (size_t)n);
+  memcpy(g_yuv.data(), g_cur.data(), frameBytes);
+  if (n > 1)
+  {
+    // the following pictures straight from the input file; a short read just shortens the batch
+    FILE* fp = fopen(getenv("FHC_SHIM_INPUT"), "rb");
+    int got = 1;
+    if (fp && fseek(fp, (long)((size_t)(poc + 1) * frameBytes), SEEK_SET) == 0)
+      while (got < n && fread(g_yuv.data() + (size_t)got * frameBytes, 1, frameBytes, fp) == frameBytes) got++;
+    if (fp) fclose(fp);
+    n = got;
+  }
+  std::vector<fhc_slice_params> sps((size_t)n, sp);
+  if (fhc_submit_frames(g_ctx, poc, n, g_yuv.data(), sampleBytes, sps.data()) != FHC_OK) fhc_die("fhc_submit_frames");
+  g_batchFirst = poc; g_batchN = n; g_batchSp = sp;
 }
 
 void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
 {
   static fhc_ctu_result r;
   const int addr = (int)pCtu->getCtuRsAddr();
-  if (addr == 0) submit_picture(enc, pCtu);
+  if (addr == 0) submit_pictures(enc, pCtu);
   if (fhc_fetch_ctu(g_ctx, pCtu->getSlice()->getPOC(), addr, &r) != FHC_OK) fhc_die("fhc_fetch_ctu");
 
   // TComDataCU::copyToPic: the per-partition arrays an intra CTU decision changes (everything else keeps the values

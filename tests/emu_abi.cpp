@@ -11,7 +11,7 @@
 extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                         const void* y, const void* cb, const void* cr, fhc_ctu_result* out);
 
-struct fhc_ctx { fhc_seq_params seq; int poc, numCtus; std::vector<fhc_ctu_result> out; };
+struct fhc_ctx { fhc_seq_params seq; int poc, n, numCtus; std::vector<fhc_ctu_result> out; };
 
 extern "C" {
 const char* fhc_last_error(void) { return "emulated ABI"; }
@@ -24,19 +24,26 @@ int fhc_create(const fhc_seq_params* seq, int, fhc_ctx** out)
   return FHC_OK;
 }
 int fhc_destroy(fhc_ctx* c) { delete c; return FHC_OK; }
+int fhc_pictures_in_flight(int) { return 3; }
 int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* sp)
 {
-  if (n != 1) return FHC_ERR_ARG;
-  const size_t luma = (size_t)c->seq.width * c->seq.height * sampleBytes;
-  const unsigned char* p = (const unsigned char*)yuv;
-  c->out.assign((size_t)c->numCtus, fhc_ctu_result());
-  c->poc = first_poc;
-  return fhc_emu_compress_picture(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, sp, p, p + luma, p + luma + luma / 4, c->out.data());
+  if (n < 1 || n > c->seq.maxFramesInFlight) return FHC_ERR_ARG;
+  const size_t luma = (size_t)c->seq.width * c->seq.height * sampleBytes, frame = luma + luma / 2;
+  c->out.assign((size_t)c->numCtus * n, fhc_ctu_result());
+  c->poc = first_poc; c->n = n;
+  for (int k = 0; k < n; k++)
+  {
+    const unsigned char* p = (const unsigned char*)yuv + frame * k;
+    int rc = fhc_emu_compress_picture(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
+                                      c->out.data() + (size_t)c->numCtus * k);
+    if (rc) return rc;
+  }
+  return FHC_OK;
 }
 int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
 {
-  if (poc != c->poc || addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
-  *out = c->out[(size_t)addr];
+  if (poc < c->poc || poc >= c->poc + c->n || addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
+  *out = c->out[(size_t)(poc - c->poc) * c->numCtus + addr];
   return FHC_OK;
 }
 }

@@ -131,7 +131,8 @@ def build_emu_abi():
     return out_dir
 
 
-def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dump=True, extra=(), exe=None, lib_dir=None, tag=""):
+def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dump=True, extra=(), exe=None, lib_dir=None, tag="",
+                  env_extra=None):
     """Runs oracle/_ref/TAppEncoder[Dump] (or `exe`); returns (bitstream bytes, dump path or None, stdout).
     lib_dir: directory put in front of the library search path (the integrated encoder's libfasthevc_cuda.so)."""
     exe = os.path.join(REF_DIR, exe or ("TAppEncoderDump" if dump else "TAppEncoder"))
@@ -141,6 +142,7 @@ def run_reference(yuv_path, width, height, frames, qp, workdir, bit_depth=8, dum
     env = dict(os.environ)
     if lib_dir:
         env["LD_LIBRARY_PATH"] = lib_dir + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    env.update(env_extra or {})
     if dump:
         env["FHC_DUMP"] = dp
     cmd = [exe, "-c", cfg, "-i", yuv_path, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),

@@ -244,3 +244,20 @@ def test_integrated_encoder_bitstream_is_byte_identical_emulated(w, h, n, qp, bd
     assert open(os.path.join(d, "rec_fhc.yuv"), "rb").read() == open(os.path.join(d, "rec_ref.yuv"), "rb").read()
     ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
     assert ok == n and not bad
+
+
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC not built")
+def test_integrated_encoder_read_ahead_emulated():
+    """The shim's read-ahead (FHC_SHIM_INPUT): 7 pictures in batches of 3 + 3 + 1 read from the input file ahead of the
+    host loop - same bitstream; and with a WRONG file behind FHC_SHIM_INPUT the shim notices that the samples differ
+    from what the host hands it, re-submits, and the bitstream is still the reference's."""
+    w, h, n, qp = 136, 72, 7, 30
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, sigma=9.0, seed=5)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    write_yuv(os.path.join(d, "wrong.yuv"), Y[::-1], U[::-1], V[::-1])
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, tag="_ref")
+    for name in ("s.yuv", "wrong.yuv"):
+        got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", lib_dir=T.build_emu_abi(),
+                                    tag="_fhc", env_extra={"FHC_SHIM_INPUT": os.path.join(d, name)})
+        assert got == ref, name

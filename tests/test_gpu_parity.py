@@ -158,3 +158,19 @@ def test_integrated_encoder_bitstream_is_byte_identical_cuda():
     assert open(os.path.join(d, "rec_fhc.yuv"), "rb").read() == open(os.path.join(d, "rec_ref.yuv"), "rb").read()
     ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
     assert ok == n and not bad
+
+
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC did not travel")
+def test_integrated_encoder_read_ahead_cuda():
+    """The shim reading ahead (FHC_SHIM_INPUT): 24 pictures of 200x136 submitted to the device in one batch, encoded
+    side by side (two thread blocks), consumed by the unchanged host loop picture by picture: byte-identical bitstream."""
+    w, h, n, qp = 200, 136, 24, 34
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, sigma=8.0, seed=21)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, tag="_ref")
+    got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", tag="_fhc",
+                                env_extra={"FHC_SHIM_INPUT": os.path.join(d, "s.yuv")})
+    assert got == ref
+    ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
+    assert ok == n and not bad
