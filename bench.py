@@ -5,8 +5,10 @@
 
 A step = one pass of the hot path (TEncCu::xCompressCU and below, for every CTU of every picture) over one batch of
 synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, cycled to
-as many (picture, QP) jobs as the persistent kernel keeps in flight (`--jobs`, default fhc_pictures_in_flight = 148 SMs x
-20 pictures per block), one warp per picture.  Every timed step goes through the C ABI with host buffers (pinned H2D
+`--rounds` (default 1.0) times as many (picture, QP) jobs as the persistent kernel keeps in flight
+(fhc_pictures_in_flight = 148 SMs x 20 pictures per block, one warp per picture), QP-major = expensive first.  (More
+rounds let blocks that finish early pull further jobs, but a job is a whole picture = minutes: measured at 416x240,
+1.25 rounds take 1.53x the time of one.)  Every timed step goes through the C ABI with host buffers (pinned H2D
 of the pictures, kernel, D2H of every CTU record): `e2e` is the wall time of that, `value` the CUDA-event time of the
 kernel inside the same steps (inputs resident in HBM when it starts), max over ranks.  N > 1: one process per GPU
 (torchrun), every rank encodes its own contiguous frame group, no collective on the data path -
@@ -95,7 +97,8 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         os.environ["NCCL_DEBUG"] = "WARN"                  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_jobs = args.jobs if args.jobs > 0 else fh.pictures_in_flight(local_rank)
+    # one round by default: every resident warp gets one picture (see --rounds)
+    n_jobs = args.jobs if args.jobs > 0 else int(fh.pictures_in_flight(local_rank) * args.rounds)
     # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
     first, last = frame_group(CLIP * world, rank, world)
     jobs = job_list(first, last - first, n_jobs)
@@ -172,8 +175,9 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64 (u8 samples, i16 levels)",
             "data": "synthetic",
             "config": {"workload": "encoder_intra_main.cfg %dx%d 8-bit, 64-frame synthetic clip per GPU x QP{22,27,32,37}, cycled to " % (W, H) +
-                                   "%d picture jobs per GPU per step (= the pictures the persistent kernel keeps in flight, one warp "
-                                   "each); warm-up steps run the same kernel and job count on %dx%d strips" % (n_jobs, W, WARM_H),
+                                   "%d picture jobs per GPU per step, QP-major = expensive first (%.2f x the pictures the persistent kernel "
+                                   "keeps in flight, one warp each: blocks that finish early pull the remaining jobs); warm-up steps run "
+                                   "the same kernel and job count on %dx%d strips" % (n_jobs, args.rounds if args.jobs <= 0 else 0.0, W, WARM_H),
                        "jobs_per_gpu": n_jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective" % world,
                        "l2_policy": "inputs+results per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (n_jobs * (3.1 + 14.1) / 1e3)},
             "ctu_per_s": round(fps * CTUS, 1),
@@ -272,6 +276,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--jobs", type=int, default=0, help="picture jobs per GPU per step (0 = pictures the kernel keeps in flight)")
+    ap.add_argument("--rounds", type=float, default=1.0, help="jobs per GPU per step as a multiple of the pictures in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")
     args = ap.parse_args()

@@ -429,6 +429,11 @@ FHC_DH void mid_align(const Ctx& c) { block_align(c); }
 #else
 FHC_DH void mid_align(const Ctx& c) { (void)c; }
 #endif
+#ifdef FHC_EXTRA_ALIGN
+FHC_DH void extra_align(const Ctx& c) { block_align(c); }
+#else
+FHC_DH void extra_align(const Ctx& c) { (void)c; }
+#endif
 #ifndef FHC_FINE_ALIGN
 #define FHC_FINE_ALIGN 1         /* also align before every stage of a TU (measured at 20 warps per block: +3.6 %; neutral at 8) */
 #endif
@@ -446,6 +451,7 @@ FHC_DH void group_sync(const Ctx& c) { (void)c; }
 FHC_DH void block_align(const Ctx& c) { (void)c; }
 FHC_DH void mid_align(const Ctx& c) { (void)c; }
 FHC_DH void fine_align(const Ctx& c) { (void)c; }
+FHC_DH void extra_align(const Ctx& c) { (void)c; }
 // emulation: the group's lanes are executed one after the other, phase by phase
 FHC_DH void par(const Ctx& c, int op)
 {
@@ -2305,6 +2311,7 @@ FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
       FHC_TOC2(c, rp, PF_RMD_PAR);
     }
     FHC_TIC(rm);
+    extra_align(c);
     int preds[3];
     const int numCand = get_mpm(c, cu, partOffset, preds);
     {
@@ -2768,6 +2775,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
   const FrameGlobal* g = c.g;
   const int x = best_cu(s, depth)->x, y = best_cu(s, depth)->y, w = best_cu(s, depth)->width;
   const int boundary = !(x + w - 1 < s->fp.width && y + w - 1 < s->fp.height);
+  extra_align(c);
   if (!boundary)
   {
     cu_init_est(c, temp_cu(s, depth));
@@ -2801,6 +2809,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
         if (i == 0) sb_copy(c, slot_of(c, nd, CI_CURR_BEST), slot_of(c, depth, CI_CURR_BEST));
         else sb_copy(c, slot_of(c, nd, CI_CURR_BEST), slot_of(c, nd, CI_NEXT_BEST));
         compress_cu(c, nd);
+        extra_align(c);
         cu_copy_part_from(c, t, best_cu(s, nd), i, 1);
         copy_reco_to_parent(c, best_cu(s, nd), t, i);
       }
@@ -2828,6 +2837,7 @@ FHC_D void compress_cu(const Ctx& c, int depth)                                 
     sb_copy(c, slot_of(c, depth, CI_TEMP_BEST), e->go);
     check_best_mode(c, depth);
   }
+  extra_align(c);
   cu_copy_to_pic(c, best_cu(s, depth), 1);
   copy_reco_to_pic(c, best_cu(s, depth));
 }
@@ -3084,6 +3094,7 @@ FHC_D void compress_picture(const Ctx& c)
     reset_bits(e);
     {
       FHC_TIC(en);
+      extra_align(c);
       encode_ctu_rec(c, &s->cu[0][1 - s->bestIdx[0]], 0, 0);
       FHC_TOC2(c, en, PF_ENCODE);
     }
