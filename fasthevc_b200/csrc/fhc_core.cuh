@@ -1117,7 +1117,7 @@ FHC_DH double dadd(double a, double b) { return a + b; }
 FHC_DH double dsub(double a, double b) { return a - b; }
 #endif
 
-// context-set slots: the chain/CU-level slots live in shared memory (master); a thread engine aliases every depth of the
+// context-set slots: the chain/CU-level slots belong to the leader (chain_slot); a lane engine aliases every depth of the
 // TU-level slots (CI_QT_TRAFO_*, CI_TEMP_BEST) onto its private set - a task only ever uses one depth of them.
 FHC_DH Sbac* chain_slot(const Ctx& c, int depth, int ci)
 {
@@ -1873,7 +1873,7 @@ FHC_DH CUMeta* temp_cu(Shared* s, int d) { return &s->cu[d][1 - s->bestIdx[d]]; 
 FHC_DH int cu_buf_index(const Shared* s, const CUMeta* cu) { return (int)(cu - &s->cu[cu->depth][0]); }
 
 // ----------------------------------------------------------------------------------------------
-// reference samples: availability on the master, gather/substitute/filter on the workers
+// reference samples: availability flags by the calling engine, gather/substitute/filter as a COOP section
 // (TComPattern.cpp:115-745, TComDataCU.cpp:1090-1200)
 // ----------------------------------------------------------------------------------------------
 FHC_D void build_refs(const Ctx& c, const CUMeta* cu, int relIdx, int comp, int n, int wantFilt)
@@ -2298,7 +2298,7 @@ FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
     double bestPUCost = FHC_MAX_COST;
     const int pox = cu->x + rel_x(s, partOffset), poy = cu->y + rel_y(s, partOffset);
 
-    // ---- rough mode decision: 35 predictions + SATD on the workers (TEncSearch.cpp:2271-2295)
+    // ---- rough mode decision: 35 predictions + SATD as a COOP section (TEncSearch.cpp:2271-2295)
     block_align(c);
     build_refs(c, cu, partOffset, 0, puSize, 1);
     {
@@ -2355,7 +2355,7 @@ FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
     if (log2pu <= 3 && e->kind == ENG_MASTER)
     {
       // small PUs (4x4 of NxN, 8x8): every candidate is a single TU, independent of the others (same start contexts,
-      // neighbours outside the PU) -> one thread engine per candidate, results compared in list order afterwards
+      // neighbours outside the PU) -> one lane engine per candidate, results compared in list order afterwards
       TaskDesc& td = s->task;
       td.resBase = 0;
       td.tsSplit = (log2pu == 2);                     // a 4x4 PU exists only in an NxN CU: every candidate is a DCT/skip pair
@@ -2554,7 +2554,7 @@ FHC_DH void est_intra_chroma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t*
   FHC_NOUNROLL for (int i = 0; i < 4; i++) if (modeList[i] == cu->ldir[0]) { modeList[i] = 34; break; }      // getAllowedChromaDir
   if (log2cu == 3 && e->kind == ENG_MASTER)
   {
-    // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> thread engines
+    // 8x8 CU: one 4x4 block per chroma component and mode, the five modes are independent -> lane engines
     TaskDesc& td = s->task;
     // the 4x4 Cb / Cr blocks sit at the CU origin whatever the luma TU tree: their reference lines are built once
     FHC_NOUNROLL for (int cc = 1; cc < 3; cc++)
