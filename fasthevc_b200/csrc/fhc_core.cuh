@@ -1507,6 +1507,22 @@ FHC_DH uint32_t coded_level(const Engine* e, double lambda, double* codedCost, d
   return best;
 }
 
+// rateIncUp / rateIncDown of TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:2316-2326) for one coefficient, from the
+// state of the level coder (packed) and the level chosen when the coefficient was quantised.  Evaluated only for the
+// coefficient groups that sign bit hiding actually changes; contexts do not move while a TU is being quantised.
+FHC_DH void sbh_rate_inc(const Engine* e, int packed, int level, int* incUp, int* incDown)
+{
+  const int ctxOne = packed & 255, ctxAbs = (packed >> 8) & 255;
+  const uint32_t goRice = (uint32_t)(packed >> 16) & 7u, c1Idx = ((packed >> 20) & 1) ? 0u : 8u, c2Idx = ((packed >> 21) & 1) ? 0u : 1u;
+  if (level > 0)
+  {
+    const int rateNow = ic_rate(e, (uint32_t)level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
+    *incUp = ic_rate(e, (uint32_t)level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+    *incDown = ic_rate(e, (uint32_t)level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
+  }
+  else { *incUp = ctx_bits(e, ctxOne, 0); *incDown = 0; }
+}
+
 FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, int comp, int log2n, int cbfCtx)
 {
   Shared* s = c.s;
@@ -1624,7 +1640,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         costSig[scanPos] = cs; costCoeff[scanPos] = cc;
         sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         deltaU[blkPos] = levelDouble >> (qBits - 8);
-        rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0); rateIncDown[blkPos] = 0;
+        rateIncUp[blkPos] = ctxOne; rateIncDown[blkPos] = 0;          // level-coder state and level: see sbh_rate_inc
         baseCost = dadd(baseCost, cc);
         if (posInCG == 0 && scanPos > 0)
         {
@@ -1639,7 +1655,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         uint32_t level;
         const int ctxAbs = CTX_ABS + (int)ctxSet + c2;
         costCoeff[scanPos] = 0; costSig[scanPos] = 0;
-        rateIncUp[blkPos] = 0; rateIncDown[blkPos] = 0; sigRateDelta[blkPos] = 0;
+        sigRateDelta[blkPos] = 0;
         if (scanPos == lastScanPos)
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               0.0, 0.0, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
@@ -1651,13 +1667,10 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
           sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
-        if (level > 0)
-        {
-          const int rateNow = ic_rate(e, level, ctxOne, ctxAbs, goRice, c1Idx, c2Idx);
-          rateIncUp[blkPos] = ic_rate(e, level + 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
-          rateIncDown[blkPos] = ic_rate(e, level - 1, ctxOne, ctxAbs, goRice, c1Idx, c2Idx) - rateNow;
-        }
-        else rateIncUp[blkPos] = ctx_bits(e, ctxOne, 0);
+        // rate increments of level +-1 are only needed if sign bit hiding touches this group: keep the level-coder state
+        // and the level chosen here (TComTrQuant.cpp:2316-2326 computes them eagerly), sbh_rate_inc evaluates them
+        rateIncUp[blkPos] = ctxOne | (ctxAbs << 8) | ((int)goRice << 16) | ((c1Idx < 8) << 20) | ((c2Idx < 1) << 21);
+        rateIncDown[blkPos] = (int32_t)level;
         dst[blkPos] = (int32_t)level;
         baseCost = dadd(baseCost, costCoeff[scanPos]);
         const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
@@ -1822,8 +1835,10 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
             const uint32_t blkPos = scan[nn + subPos];
             if (dst[blkPos] != 0)
             {
-              const int64_t costUp = rdFactor * (-deltaU[blkPos]) + rateIncUp[blkPos];
-              int64_t costDown = rdFactor * (deltaU[blkPos]) + rateIncDown[blkPos] - ((iabs(dst[blkPos]) == 1) ? sigRateDelta[blkPos] : 0);
+              int incUp, incDown;
+              sbh_rate_inc(e, rateIncUp[blkPos], rateIncDown[blkPos], &incUp, &incDown);
+              const int64_t costUp = rdFactor * (-deltaU[blkPos]) + incUp;
+              int64_t costDown = rdFactor * (deltaU[blkPos]) + incDown - ((iabs(dst[blkPos]) == 1) ? sigRateDelta[blkPos] : 0);
               if (lastCG == 1 && lastNZ == nn && iabs(dst[blkPos]) == 1) costDown -= (4 << 15);
               if (costUp < costDown) { curCost = costUp; curChange = 1; }
               else
@@ -1835,7 +1850,9 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
             }
             else
             {
-              curCost = rdFactor * (-(iabs(deltaU[blkPos]))) + (1 << 15) + rateIncUp[blkPos] + sigRateDelta[blkPos];
+              int incUp, incDown;
+              sbh_rate_inc(e, rateIncUp[blkPos], rateIncDown[blkPos], &incUp, &incDown);
+              curCost = rdFactor * (-(iabs(deltaU[blkPos]))) + (1 << 15) + incUp + sigRateDelta[blkPos];
               curChange = 1;
               if (nn < firstNZ)
               {
