@@ -1638,7 +1638,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
         const double cs = FHC_SIGC0(sc), cc = dadd(costCoeff0[scanPos], cs);
         costSig[scanPos] = cs; costCoeff[scanPos] = cc;
-        sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
+        sigRateDelta[blkPos] = sc;                                     // context only: the delta is evaluated by sign bit hiding
         deltaU[blkPos] = levelDouble >> (qBits - 8);
         rateIncUp[blkPos] = ctxOne; rateIncDown[blkPos] = 0;          // level-coder state and level: see sbh_rate_inc
         baseCost = dadd(baseCost, cc);
@@ -1655,7 +1655,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
         uint32_t level;
         const int ctxAbs = CTX_ABS + (int)ctxSet + c2;
         costCoeff[scanPos] = 0; costSig[scanPos] = 0;
-        sigRateDelta[blkPos] = 0;
+        sigRateDelta[blkPos] = -1;                                     // last position: no sig_coeff_flag
         if (scanPos == lastScanPos)
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               0.0, 0.0, ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 1);
@@ -1664,7 +1664,7 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
           const int sc = sig_ctx_inc(*e->t, pat, firstSig, (int)blkPos, log2n, isChroma);
           level = coded_level(e, lambda, &costCoeff[scanPos], &costCoeff0[scanPos], &costSig[scanPos], levelDouble, maxAbsLevel,
                               FHC_SIGC0(sc), FHC_SIGC1(sc), ctxOne, ctxAbs, goRice, c1Idx, c2Idx, qBits, errScale, 0);
-          sigRateDelta[blkPos] = FHC_SIGDELTA(sc);
+          sigRateDelta[blkPos] = sc;
         }
         deltaU[blkPos] = (levelDouble - (int)(level << qBits)) >> (qBits - 8);
         // rate increments of level +-1 are only needed if sign bit hiding touches this group: keep the level-coder state
@@ -1838,7 +1838,8 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
               int incUp, incDown;
               sbh_rate_inc(e, rateIncUp[blkPos], rateIncDown[blkPos], &incUp, &incDown);
               const int64_t costUp = rdFactor * (-deltaU[blkPos]) + incUp;
-              int64_t costDown = rdFactor * (deltaU[blkPos]) + incDown - ((iabs(dst[blkPos]) == 1) ? sigRateDelta[blkPos] : 0);
+              const int sdc = sigRateDelta[blkPos], sigD = sdc < 0 ? 0 : FHC_SIGDELTA(sdc);
+              int64_t costDown = rdFactor * (deltaU[blkPos]) + incDown - ((iabs(dst[blkPos]) == 1) ? sigD : 0);
               if (lastCG == 1 && lastNZ == nn && iabs(dst[blkPos]) == 1) costDown -= (4 << 15);
               if (costUp < costDown) { curCost = costUp; curChange = 1; }
               else
@@ -1852,7 +1853,8 @@ FHC_DH uint32_t rdoq_pass_impl(const Ctx& c, const CUMeta* cu, int relIdxComp, i
             {
               int incUp, incDown;
               sbh_rate_inc(e, rateIncUp[blkPos], rateIncDown[blkPos], &incUp, &incDown);
-              curCost = rdFactor * (-(iabs(deltaU[blkPos]))) + (1 << 15) + incUp + sigRateDelta[blkPos];
+              const int sdc = sigRateDelta[blkPos], sigD = sdc < 0 ? 0 : FHC_SIGDELTA(sdc);
+              curCost = rdFactor * (-(iabs(deltaU[blkPos]))) + (1 << 15) + incUp + sigD;
               curChange = 1;
               if (nn < firstNZ)
               {
