@@ -13,7 +13,7 @@ of the pictures, kernel, D2H of every CTU record): `e2e` is the wall time of tha
 kernel inside the same steps (inputs resident in HBM when it starts), max over ranks.  N > 1: one process per GPU
 (torchrun), every rank encodes its own contiguous frame group, no collective on the data path -
 torch.distributed only provides the barrier and the max over ranks.  A 1080p picture is one dependent chain of 510 CTUs
-and takes minutes whatever the batch size, so a step takes minutes; warm-up steps use 1920x72 strips.
+and takes minutes whatever the batch size, so a step takes minutes; warm-up steps use 1920x64 strips.
 
 `--impl reference` times the UNMODIFIED reference encoder (oracle/_ref/TAppEncoder, HM 16.14 with the OpenCV dump
 stubbed) on the host cores: one process per core, one 1080p picture each per step.
@@ -37,7 +37,7 @@ CTUS = 30 * 17
 # algorithmic bytes per CTU = 6144 source + 12288 reconstruction + 12288 levels + ~6 KB metadata
 ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
 INT_OPS_PER_CTU = 40.0e6            # SURVEY.md 8(d) W_ctu (integer-equivalent ops, content dependent)
-WARM_H = 72                         # height of the warm-up strips
+WARM_H = 64                         # height of the warm-up strips (one CTU row)
 NCU_DRAM_BYTES_PER_CTU = (459.21e9 + 247.55e9) / 2960     # profiles/r01_final_w20_loaded.md
 
 
@@ -112,8 +112,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: the same kernel, the same number of pictures, on 1920x72 strips (one full CTU row + the 8-line bottom
-    # row) of the same content: a full 1080p step takes minutes because a picture is one dependent chain of 510 CTUs
+    # ---- warm-up: the same kernel, the same number of pictures, on one-CTU-row strips (1920x64)
+    # of the same content: a full 1080p step takes minutes because a picture is one dependent chain of 510 CTUs
     wenc = fh.Encoder(W, WARM_H, 8, max_frames=n_jobs, device=local_rank)
     wpacked = wenc.pack_frames(Y[:, :WARM_H], U[:, :WARM_H // 2], V[:, :WARM_H // 2])
     whost = wenc.pinned_array((n_jobs, wenc.frame_samples), np.uint8)
