@@ -481,6 +481,15 @@ FHC_DH int org_at(const FrameGlobal* g, int sampleBytes, int comp, int idx)
 FHC_DH int plane_stride(const Shared* s, int comp) { return s->fp.width >> (comp ? 1 : 0); }
 FHC_DH const uint16_t* scan_tab(const Tables& t, int type, int log2n) { return t.scan + t.scanOff[type][log2n - 2]; }
 FHC_DH const uint8_t* scan_cg(const Tables& t, int type, int log2n) { return t.scanCG[type] + cg_off(log2n - 2); }
+// the NxN transform matrix as a strided view: M(k, j) = tab[k * rowStride + j] (4x4 DST-VII or rows of the 32-point DCT)
+struct TMat { const int16_t* tab; int rowStride; };
+FHC_DH TMat tmat(const Tables& t, int n, int useDst)
+{
+  TMat m;
+  if (useDst) { m.tab = t.dst4; m.rowStride = 4; }
+  else { m.tab = t.T32; m.rowStride = (n == 4 ? 8 : n == 8 ? 4 : n == 16 ? 2 : 1) * 32; }
+  return m;
+}
 FHC_DH int tcoefm(const Tables& t, int n, int k, int j, int useDst)
 {
   // 4x4 DST-VII matrix or rows of the 32-point DCT matrix
@@ -597,6 +606,8 @@ FHC_DH void atomic_add_u32(uint32_t* p, uint32_t v, int nw)
 template <typename TIn, typename TOut>
 FHC_DH void lane_transform_stage(const Tables& t, int n, int useDst, int inverse, const TIn* in, TOut* out, int add, int shift)
 {
+  const TMat m = tmat(t, n, useDst);
+  const int sk = inverse ? 1 : m.rowStride, sq = inverse ? m.rowStride : 1;       // element (k, q): forward M(k,q), inverse M(q,k)
   for (int j = 0; j < n; j++)
   {
     int r[8];
@@ -611,7 +622,7 @@ FHC_DH void lane_transform_stage(const Tables& t, int n, int useDst, int inverse
 #pragma unroll
 #endif
       for (int q = 0; q < 8; q++)
-        if (q < n) acc += (inverse ? tcoefm(t, n, q, k, useDst) : tcoefm(t, n, k, q, useDst)) * r[q];
+        if (q < n) acc += m.tab[k * sk + q * sq] * r[q];
       const int v = (acc + add) >> shift;
       if (inverse) out[j * n + k] = (TOut)clip3(-32768, 32767, v);
       else out[k * n + j] = (TOut)v;
@@ -791,6 +802,7 @@ FHC_D void phase_fwd_quant(const Ctx& c, int phase, int w, int nw)
   // a0 log2n, a1 useDst, a2 transformSkip, a3 scanType, a4 quantCoef, a5 qBits, a6 chType(0/1), a7 qp rem
   // out: tcoef[] raster, lvlD[scanPos], rd.cost0[scanPos], tmp[blkPos] = uiMaxAbsLevel
   const int log2n = a[0], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
+  const TMat fm = tmat(*s->t, n, a[1]);
   if (a[2])
   {
     if (phase == 1)
@@ -808,7 +820,8 @@ FHC_D void phase_fwd_quant(const Ctx& c, int phase, int w, int nw)
     {
       const int k = i >> log2n, j = i & (n - 1);
       int acc = 0;
-      for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->resi[j * n + q];
+      const int16_t* row = fm.tab + k * fm.rowStride;
+      for (int q = 0; q < n; q++) acc += row[q] * e->resi[j * n + q];
       e->tmp[i] = (acc + add1) >> shift1;
     }
   }
@@ -821,7 +834,8 @@ FHC_D void phase_fwd_quant(const Ctx& c, int phase, int w, int nw)
     {
       const int k = i >> log2n, j = i & (n - 1);
       int acc = 0;
-      for (int q = 0; q < n; q++) acc += tcoefm(*s->t, n, k, q, a[1]) * e->tmp[j * n + q];
+      const int16_t* row = fm.tab + k * fm.rowStride;
+      for (int q = 0; q < n; q++) acc += row[q] * e->tmp[j * n + q];
       e->tcoef[i] = (acc + add2) >> shift2;
     }
   }
@@ -857,6 +871,7 @@ FHC_D void phase_inv_recon(const Ctx& c, int phase, int w, int nw)
   // a0 comp, a1 log2n, a2 useDst, a3 transformSkip, a4 absSum>0, a5 qp per, a6 qp rem,
   // a7 predYuv offset, a8 predYuv stride, a9 qt layer, a10 qtRec offset, a11 rec plane offset, a12 org plane offset
   const int comp = a[0], log2n = a[1], n = 1 << log2n, n2 = n * n, bd = s->fp.bitDepth;
+  const TMat im = tmat(*s->t, n, a[2]);
   if (a[4])
   {
     if (phase == 0)
@@ -891,7 +906,7 @@ FHC_D void phase_inv_recon(const Ctx& c, int phase, int w, int nw)
         {
           const int j = i >> log2n, q = i & (n - 1);
           int acc = 0;
-          for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->tcoef[k * n + j];
+          for (int k = 0; k < n; k++) acc += im.tab[k * im.rowStride + q] * e->tcoef[k * n + j];
           e->lvlD[i] = clip3(-32768, 32767, (acc + 64) >> 7);
         }
       }
@@ -907,7 +922,7 @@ FHC_D void phase_inv_recon(const Ctx& c, int phase, int w, int nw)
         {
           const int j = i >> log2n, q = i & (n - 1);
           int acc = 0;
-          for (int k = 0; k < n; k++) acc += tcoefm(*s->t, n, k, q, a[2]) * e->lvlD[k * n + j];
+          for (int k = 0; k < n; k++) acc += im.tab[k * im.rowStride + q] * e->lvlD[k * n + j];
           e->resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
         }
       }
