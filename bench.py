@@ -246,8 +246,8 @@ def cpu_reference_sample(steps, warmup):
         n += a
         t += b
     return {"value": round(n / t, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
-            "sample": "oracle/_ref/TAppEncoder (HM 16.14, g++ -O2 -msse4.1): %d step(s) of one 1080p picture per core, QP 22/27/32/37 "
-                      "cycled over cores, one process per core" % steps,
+            "sample": "oracle/_ref/TAppEncoder (HM 16.14, g++ -O2 -msse4.1): %d step(s) of one %dx%d picture per core, QP 22/27/32/37 "
+                      "cycled over cores, one process per core" % (steps, W, H),
             "ms_per_step": round(t / steps * 1e3, 1)}
 
 
