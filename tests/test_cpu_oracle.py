@@ -261,3 +261,16 @@ def test_integrated_encoder_read_ahead_emulated():
         got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", lib_dir=T.build_emu_abi(),
                                     tag="_fhc", env_extra={"FHC_SHIM_INPUT": os.path.join(d, name)})
         assert got == ref, name
+
+
+def test_kernel_source_emulation_4k_width_main10():
+    """BASELINE configs[3] geometry in one dimension: a 3840-wide Main10 strip (60 CTUs per row, two full rows + the
+    8-line bottom row) through the host emulation of the kernel source against the oracle - row-to-row neighbour and
+    above-right availability at the 4K row length, 10-bit scaling of SATD / SSE / transform shifts."""
+    w, h, qp, bd = 3840, 136, 27, 10
+    Y, U, V = synth_frames(w, h, 1, bit_depth=bd, sigma=8.0, seed=31)
+    p = T.params_from_qp(w, h, bd, qp)
+    got = T.emu_compress(p, Y[0], U[0], V[0])
+    ref = T.oracle_compress(p, Y[0], U[0], V[0])
+    assert len(ref) == 180
+    assert T.compare_ctus(got, ref, "4k strip") == []
