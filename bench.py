@@ -36,7 +36,7 @@ QPS = [22, 27, 32, 37]
 CTUS = 30 * 17
 # algorithmic bytes per CTU = 6144 source + 12288 reconstruction + 12288 levels + ~6 KB metadata
 ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
-INT_OPS_PER_CTU = 40.0e6            # SURVEY.md 8(d) W_ctu (integer-equivalent ops, content dependent)
+INT_OPS_PER_CTU = 42.1e6            # SURVEY.md 8(d) W_ctu, counted exactly on the bench mix: profiles/r01_work_counts.md
 WARM_H = 64                         # height of the warm-up strips (one CTU row)
 NCU_DRAM_BYTES_PER_CTU = (459.21e9 + 247.55e9) / 2960     # profiles/r01_final_w20_loaded.md
 

@@ -47,6 +47,17 @@
 
 namespace fhc {
 
+// Work counters of the host emulation build (tests/tools only; SURVEY.md 8d asks for the exact sample counts per
+// configuration): samples through the TU pipeline by component class and TU size, samples predicted + SATD'd by the
+// rough mode decision, and CABAC bins counted.  Compiled out of the device build.
+#ifndef FHC_DEVICE_BUILD
+struct EmuCounters { unsigned long long tqSamples[2][4], tuCalls[2][4], rmdSamples, bins; };
+static EmuCounters g_emuCounters;
+#define FHC_COUNT(stmt) do { stmt; } while (0)
+#else
+#define FHC_COUNT(stmt) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // constants
 // ----------------------------------------------------------------------------------------------
@@ -1090,11 +1101,12 @@ FHC_DH void enc_bin(Engine* e, int ctx, int bin)
 {
   const uint8_t st = e->go->c[ctx];
   e->bins++;
+  FHC_COUNT(g_emuCounters.bins++);
   e->go->frac += (uint64_t)e->t->entropyBits[st ^ bin];
   e->go->c[ctx] = e->t->nextState[st][bin];
 }
-FHC_DH void enc_ep(Engine* e, int n) { e->bins += (uint32_t)n; e->go->frac += (uint64_t)32768 * (uint64_t)n; }
-FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; e->go->frac += (uint64_t)e->t->entropyBits[126 ^ bin]; }
+FHC_DH void enc_ep(Engine* e, int n) { e->bins += (uint32_t)n; FHC_COUNT(g_emuCounters.bins += (unsigned)n); e->go->frac += (uint64_t)32768 * (uint64_t)n; }
+FHC_DH void enc_trm(Engine* e, int bin) { e->bins++; FHC_COUNT(g_emuCounters.bins++); e->go->frac += (uint64_t)e->t->entropyBits[126 ^ bin]; }
 FHC_DH void reset_bits(Engine* e) { e->go->frac &= 32767; e->bins = 0; }
 FHC_DH uint32_t num_bits(const Engine* e) { return (uint32_t)(e->go->frac >> 15); }
 FHC_DH int ctx_bits(const Engine* e, int ctx, int bin) { return e->t->entropyBits[e->go->c[ctx] ^ bin]; }
@@ -1974,6 +1986,7 @@ FHC_D uint32_t code_tu_block(const Ctx& c, CUMeta* cu, int relIdx, int comp, int
   const int n = 1 << log2n, isChroma = comp != 0;
   const int cuW = cu->width >> isChroma;
   block_align(c);
+  FHC_COUNT(g_emuCounters.tqSamples[isChroma][log2n - 2] += (unsigned)(n * n); g_emuCounters.tuCalls[isChroma][log2n - 2]++);
   const int bx = rel_x(s, relIdx) >> isChroma, by = rel_y(s, relIdx) >> isChroma;
   const int qtLayer = 5 - lumaLog2;
   const int picX = (cu->x >> isChroma) + bx, picY = (cu->y >> isChroma) + by;
@@ -2341,6 +2354,7 @@ FHC_DH void est_intra_luma(const Ctx& c, CUMeta* cu, int16_t* cuCoef, int16_t* c
       FHC_NOUNROLL for (int i = 0; i < 35; i++) s->satd[i] = 0;
       m.a[0] = log2pu; m.a[1] = poy * ps + pox; m.a[2] = mpg; m.a[15] = 2 * ((35 + mpg - 1) / mpg);
       FHC_TIC(rp);
+      FHC_COUNT(g_emuCounters.rmdSamples += 35ull << (2 * log2pu));
       par(c, OP_RMD);
       FHC_TOC2(c, rp, PF_RMD_PAR);
     }

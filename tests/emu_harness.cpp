@@ -34,4 +34,14 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
   free(g); free(s); free(t);
   return 0;
 }
+// work counters since the last reset: out[0..7] = TU-pipeline samples [luma,chroma][4x4,8x8,16x16,32x32], out[8..15] = TU codings
+// (same order), out[16] = samples of the rough mode decision, out[17] = CABAC bins counted
+extern "C" void fhc_emu_counters(unsigned long long* out, int reset)
+{
+  using namespace fhc;
+  for (int c = 0; c < 2; c++)
+    for (int k = 0; k < 4; k++) { out[c * 4 + k] = g_emuCounters.tqSamples[c][k]; out[8 + c * 4 + k] = g_emuCounters.tuCalls[c][k]; }
+  out[16] = g_emuCounters.rmdSamples; out[17] = g_emuCounters.bins;
+  if (reset) memset(&g_emuCounters, 0, sizeof(g_emuCounters));
+}
 extern "C" int fhc_emu_shared_bytes() { return (int)sizeof(fhc::Shared); }
