@@ -125,7 +125,7 @@ def build_emu_abi():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libfasthevc_cuda.so")
     srcs = [os.path.join(ROOT, "tests", "emu_abi.cpp"), os.path.join(ROOT, "tests", "emu_harness.cpp"),
-            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_core.cuh"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_tables.h")]
+            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_engine.cuh"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_rom.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, srcs[0], srcs[1], "-lm"])
     return out_dir
@@ -200,8 +200,8 @@ def build_emu():
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "fhc_emu.so")
-    srcs = [os.path.join(ROOT, "tests", "emu_harness.cpp"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_core.cuh"),
-            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_tables.h")]
+    srcs = [os.path.join(ROOT, "tests", "emu_harness.cpp"), os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_engine.cuh"),
+            os.path.join(ROOT, "fasthevc_b200", "csrc", "fhc_rom.h")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, srcs[0], "-lm"])
     return so
