@@ -7,7 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++14",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -38,7 +38,8 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
 
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
-           "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight"]
+           "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight", "fhc_poll_picture",
+           "fhc_fetch_picture_async", "fhc_fetch_sync"]
 
 
 def library_path():
@@ -48,7 +49,7 @@ def library_path():
 def build_library(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a; the .so stays in-tree (git-ignored) and travels with the snapshot."""
     so = library_path()
-    srcs = [os.path.join(_CSRC, f) for f in ("fasthevc_cuda.cu", "fhc_core.cuh", "fhc_tables.h")]
+    srcs = [os.path.join(_CSRC, f) for f in ("fasthevc_cuda.cu", "fhc_engine.cuh", "fhc_rom.h")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "fasthevc_cuda.h"))
     if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
@@ -82,6 +83,9 @@ def load_library():
     lib.fhc_host_free.argtypes = [C.c_void_p]
     lib.fhc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.fhc_pictures_in_flight.argtypes = [C.c_int]
+    lib.fhc_poll_picture.argtypes = [C.c_void_p, C.c_int]
+    lib.fhc_fetch_picture_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.fhc_fetch_sync.argtypes = [C.c_void_p]
     lib.fhc_last_error.restype = C.c_char_p
     lib.fhc_launch_count.restype = C.c_uint64
     _lib = lib
@@ -164,6 +168,20 @@ class Encoder:
             out = np.zeros(self.num_ctus, CTU_RESULT_DTYPE)
         self._check(self.lib.fhc_fetch_picture(self.ctx, poc, out.ctypes.data), "fhc_fetch_picture")
         return out
+
+    def poll_picture(self, poc):
+        """True when picture `poc` is finished on the device (non-blocking)."""
+        rc = self.lib.fhc_poll_picture(self.ctx, poc)
+        if rc < 0:
+            self._check(rc, "fhc_poll_picture")
+        return rc == 1
+
+    def fetch_picture_async(self, poc, out):
+        """Waits for picture `poc` only, then queues its device->host copy into `out` (page-locked); fetch_sync() completes it."""
+        self._check(self.lib.fhc_fetch_picture_async(self.ctx, poc, out.ctypes.data), "fhc_fetch_picture_async")
+
+    def fetch_sync(self):
+        self._check(self.lib.fhc_fetch_sync(self.ctx), "fhc_fetch_sync")
 
     def fetch_ctu(self, poc, addr):
         out = np.zeros(1, CTU_RESULT_DTYPE)

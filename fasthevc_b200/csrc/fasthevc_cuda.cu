@@ -5,78 +5,46 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <vector>
-#include "fhc_tables.h"
+#include "fhc_engine.cuh"
 
 using namespace fhc;
-#ifndef FHC_MIN_BLOCKS
-#define FHC_MIN_BLOCKS 1
-#endif
-#define FHC_BLOCK_THREADS (32 * FHC_WARPS_PER_BLOCK)
-extern "C" int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16);
 
-#if FHC_GROUP != 32
-#error "the persistent kernel assumes one picture per warp (FHC_GROUP 32): sub-warp groups serialise, see DESIGN.md 4"
+#ifndef FHC_BLOCKS_PER_SM
+#define FHC_BLOCKS_PER_SM 2
 #endif
-#define FHC_PICS_PER_WARP (32 / FHC_GROUP)
-#define FHC_PICS_PER_BLOCK (FHC_PICS_PER_WARP * FHC_WARPS_PER_BLOCK)
-static size_t tables_smem_bytes() { return (sizeof(Tables) + 15) & ~(size_t)15; }
-static size_t kernel_smem_bytes() { return tables_smem_bytes() + sizeof(Shared) * FHC_PICS_PER_BLOCK + 16 * FHC_WARPS_PER_BLOCK; }
+#define FHC_BATCHES 2                     /* submits that may be in flight: one running, one queued behind it */
 
 // ----------------------------------------------------------------------------------------------
-// kernel: persistent warps; a warp encodes FHC_PICS_PER_WARP pictures side by side (FHC_GROUP lanes each), the
-// groups of a warp start their pictures together so that they walk the same code at the same time
+// kernel: persistent blocks, one picture at a time per block, pulled from a queue
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_MIN_BLOCKS)
-fhc_compress_pictures_kernel(PicDesc* pics, int numPics, int* queue, FrameGlobal* scratch, const Tables* tables)
+__global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
+fhc_ctu_kernel(const PicDesc* pics, int numPics, int* queue, unsigned char* workspace, size_t wsPerBlock, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Tables* t = reinterpret_cast<Tables*>(smem_raw);
+  Blk* b = reinterpret_cast<Blk*>(smem_raw);
+  const int tid = threadIdx.x, nthr = blockDim.x;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(t);
-    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&b->t);
+    for (int i = tid; i < (int)(sizeof(Tables) / 4); i += nthr) dst[i] = src[i];
   }
-  int* rvz = reinterpret_cast<int*>(smem_raw + ((sizeof(Tables) + 15) & ~(size_t)15) + sizeof(Shared) * FHC_PICS_PER_BLOCK);
-  if (threadIdx.x < 4 * FHC_WARPS_PER_BLOCK) rvz[threadIdx.x] = 0;
+  if (tid == 0) init_block(b, smem_raw + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + (size_t)blockIdx.x * wsPerBlock);
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane / FHC_GROUP, slot = warp * FHC_PICS_PER_WARP + grp;
-  Shared* s = reinterpret_cast<Shared*>(smem_raw + ((sizeof(Tables) + 15) & ~(size_t)15)) + slot;
-  FrameGlobal* g = scratch + (size_t)blockIdx.x * FHC_PICS_PER_BLOCK + slot;
-  Ctx c;
-  c.g = g; c.s = s; c.e = &s->master; c.lane = lane % FHC_GROUP; c.nl = FHC_GROUP;
-  c.mask = (FHC_GROUP == 32) ? FHC_FULL_MASK : (((1u << FHC_GROUP) - 1u) << (grp * FHC_GROUP));
-  if (c.lane == 0) init_engines(g, s, t);
-  group_sync(c);
-  // Rounds: the block pulls FHC_PICS_PER_BLOCK pictures at a time, so that its pictures start together and can be
-  // kept aligned (block_align).  __syncthreads is safe here: every lane is back in this loop between rounds.
   for (;;)
   {
+    if (tid == 0) b->picIndex = atomicAdd(queue, 1);
     __syncthreads();
-    if (threadIdx.x == 0) rvz[0] = atomicAdd(queue, FHC_PICS_PER_BLOCK);
-    __syncthreads();
-    const int base = rvz[0];
-    if (base >= numPics) break;
-    const int active = (numPics - base < FHC_PICS_PER_BLOCK) ? numPics - base : FHC_PICS_PER_BLOCK;
-    const int p = base + slot;
-    if (p < numPics)
+    const int p = b->picIndex;
+    if (p >= numPics) break;
+    compress_picture(b, &pics[p], tid, nthr);
+    if (tid == 0)
     {
-      if (c.lane == 0)
-      {
-        // the group's leader walks the decision code; the other lanes serve its COOP sections and LANE dispatches
-        s->alignThreads = (FHC_GROUP == 32) ? 32 * active : 0;
-        load_picture(c, &pics[p]);
-        compress_picture(c);
-        release_followers(c);
-        for (int i = 0; i < 16; i++)
-        {
-          pics[p].prof[i] = g->prof[i]; pics[p].profN[i] = g->profN[i];
-          pics[p].prof2[i] = g->prof2[i]; pics[p].prof2N[i] = g->prof2N[i];
-        }
-      }
-      else follower_loop(c);
+      __threadfence_system();
+      *reinterpret_cast<volatile int32_t*>(pics[p].doneFlag) = 1;
     }
+    __syncthreads();
   }
 }
 
@@ -86,31 +54,46 @@ fhc_compress_pictures_kernel(PicDesc* pics, int numPics, int* queue, FrameGlobal
 static thread_local char g_err[512] = "";
 static uint64_t g_launches = 0;
 
-#define CK(call)                                                                                         \
+#define CKG(call, onfail)                                                                                \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
     if (e_ != cudaSuccess) {                                                                             \
       snprintf(g_err, sizeof(g_err), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      onfail;                                                                                            \
       return FHC_ERR_CUDA;                                                                               \
     }                                                                                                    \
   } while (0)
+#define CK(call) CKG(call, (void)0)
+
+// one submit's worth of device state
+struct Batch
+{
+  PicDesc* dPics = nullptr;               // [maxFrames]
+  uint8_t* dIn = nullptr;                 // maxFrames pictures, inBytesPerFrame each
+  size_t inBytesPerFrame = 0;
+  fhc_ctu_result* dOut = nullptr;         // [maxFrames * numCtus]
+  int16_t* dLines = nullptr;              // [maxFrames][2][2 * width]
+  uint8_t* dDepthRows = nullptr;          // [maxFrames][2][width / 4]
+  int32_t* hFlags = nullptr;              // [maxFrames] mapped pinned host memory: picture done
+  int32_t* dFlags = nullptr;              // device alias of hFlags
+  int32_t* hTrace = nullptr;              // [maxFrames] mapped pinned host memory: progress words (FHC_TRACE=1 in the environment)
+  int32_t* dTrace = nullptr;
+  int* dQueue = nullptr;
+  cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
+  int firstPoc = 0, n = 0, launched = 0;
+  uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
+};
 
 struct fhc_ctx
 {
   fhc_seq_params seq;
-  int device, numCtus, maxFrames;
-  size_t lumaSamples, frameSamples;       // per picture
-  PicDesc* dPics;                         // [maxFrames] picture queue of the current submit
-  FrameGlobal* dScratch;                  // [maxBlocks * FHC_WARPS_PER_BLOCK] per-warp scratch
-  int* dQueue;                            // next picture index
-  int maxBlocks;                          // resident blocks of the persistent kernel
-  Tables* dTables;
-  uint8_t* dIn;                           // maxFrames * frameSamples * 2 bytes
-  int16_t* dRec;                          // maxFrames * frameSamples
-  fhc_ctu_result* dOut;                   // maxFrames * numCtus
-  cudaStream_t stream;
-  cudaEvent_t evStart, evStop;
-  int firstPoc, nSubmitted, pending;
+  int device = 0, numCtus = 0, maxFrames = 0, maxBlocks = 0;
+  size_t lumaSamples = 0, frameSamples = 0, smemBytes = 0, wsPerBlock = 0;
+  Tables* dTables = nullptr;
+  unsigned char* dWorkspace = nullptr;
+  cudaStream_t compute = nullptr, copyIn = nullptr, copyOut = nullptr;
+  Batch batch[FHC_BATCHES];
+  uint64_t submits = 0;
   std::vector<PicDesc> hostPics;
 };
 
@@ -122,6 +105,46 @@ int fhc_slice_params_from_qp(int qp, fhc_slice_params* out)
 {
   if (!out || qp < 0 || qp > 51) return FHC_ERR_ARG;
   slice_params_from_qp(qp, out);
+  return FHC_OK;
+}
+
+static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, int* maxBlocks)
+{
+  cudaDeviceProp prop;
+  int perSm = 0;
+  block_footprint(smemBytes, wsPerBlock);
+  CK(cudaGetDeviceProperties(&prop, device));
+  CK(cudaFuncSetAttribute(fhc_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smemBytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_ctu_kernel, FHC_BLOCK_THREADS, *smemBytes));
+  if (perSm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit an SM (%zu bytes of shared memory)", *smemBytes); return FHC_ERR_CUDA; }
+  *maxBlocks = prop.multiProcessorCount * perSm;
+  return FHC_OK;
+}
+
+static void free_batch(Batch& bt)
+{
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue);
+  if (bt.hFlags) cudaFreeHost(bt.hFlags);
+  if (bt.hTrace) cudaFreeHost(bt.hTrace);
+  if (bt.evCopied) cudaEventDestroy(bt.evCopied);
+  if (bt.evStart) cudaEventDestroy(bt.evStart);
+  if (bt.evStop) cudaEventDestroy(bt.evStop);
+  bt = Batch();
+}
+
+int fhc_destroy(fhc_ctx* c)
+{
+  if (!c) return FHC_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (c->compute) cudaStreamSynchronize(c->compute);
+  if (c->copyIn) cudaStreamSynchronize(c->copyIn);
+  if (c->copyOut) cudaStreamSynchronize(c->copyOut);
+  for (int i = 0; i < FHC_BATCHES; i++) free_batch(c->batch[i]);
+  cudaFree(c->dTables); cudaFree(c->dWorkspace);
+  if (c->compute) cudaStreamDestroy(c->compute);
+  if (c->copyIn) cudaStreamDestroy(c->copyIn);
+  if (c->copyOut) cudaStreamDestroy(c->copyOut);
+  delete c;
   return FHC_OK;
 }
 
@@ -146,75 +169,106 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   c->maxFrames = seq->maxFramesInFlight;
   c->lumaSamples = (size_t)seq->width * seq->height;
   c->frameSamples = c->lumaSamples * 3 / 2;
-  c->firstPoc = 0; c->nSubmitted = 0; c->pending = 0;
   c->hostPics.resize((size_t)c->maxFrames);
+  // every failure below releases what was allocated so far (fhc_destroy is null-safe)
+  if (kernel_geometry(device, &c->smemBytes, &c->wsPerBlock, &c->maxBlocks) != FHC_OK) { fhc_destroy(c); return FHC_ERR_CUDA; }
+  if (c->maxBlocks > c->maxFrames) c->maxBlocks = c->maxFrames;
+  CKG(cudaMalloc(&c->dTables, sizeof(Tables)), fhc_destroy(c));
+  CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks), fhc_destroy(c));
+  CKG(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking), fhc_destroy(c));
+  CKG(cudaStreamCreateWithFlags(&c->copyIn, cudaStreamNonBlocking), fhc_destroy(c));
+  CKG(cudaStreamCreateWithFlags(&c->copyOut, cudaStreamNonBlocking), fhc_destroy(c));
+  const size_t inBytes = c->frameSamples * (size_t)(seq->bitDepth > 8 ? 2 : 1);
+  for (int i = 0; i < FHC_BATCHES; i++)
   {
-    // persistent grid: as many blocks as fit on the device, but never more warps than pictures
-    cudaDeviceProp prop;
-    int perSm = 0;
-    CK(cudaGetDeviceProperties(&prop, device));
-    CK(cudaFuncSetAttribute(fhc_compress_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kernel_smem_bytes()));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_compress_pictures_kernel, FHC_BLOCK_THREADS, kernel_smem_bytes()));
-    if (perSm < 1) { snprintf(g_err, sizeof(g_err), "fhc_create: kernel does not fit an SM"); delete c; return FHC_ERR_CUDA; }
-    const int need = (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
-    c->maxBlocks = prop.multiProcessorCount * perSm;
-    if (c->maxBlocks > need) c->maxBlocks = need;
+    Batch& bt = c->batch[i];
+    CKG(cudaMalloc(&bt.dPics, sizeof(PicDesc) * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dIn, inBytes * (size_t)c->maxFrames), fhc_destroy(c));
+    bt.inBytesPerFrame = inBytes;
+    CKG(cudaMalloc(&bt.dOut, sizeof(fhc_ctu_result) * (size_t)c->numCtus * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dLines, sizeof(int16_t) * 4 * (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dQueue, sizeof(int)), fhc_destroy(c));
+    CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
+    CKG(cudaHostGetDevicePointer(&bt.dFlags, bt.hFlags, 0), fhc_destroy(c));
+    if (getenv("FHC_TRACE"))
+    {
+      CKG(cudaHostAlloc(&bt.hTrace, sizeof(int32_t) * 8 * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
+      CKG(cudaHostGetDevicePointer(&bt.dTrace, bt.hTrace, 0), fhc_destroy(c));
+    }
+    CKG(cudaEventCreate(&bt.evCopied), fhc_destroy(c));
+    CKG(cudaEventCreate(&bt.evStart), fhc_destroy(c));
+    CKG(cudaEventCreate(&bt.evStop), fhc_destroy(c));
   }
-  CK(cudaMalloc(&c->dPics, sizeof(PicDesc) * (size_t)c->maxFrames));
-  CK(cudaMalloc(&c->dScratch, sizeof(FrameGlobal) * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK));
-  CK(cudaMalloc(&c->dQueue, sizeof(int)));
-  CK(cudaMalloc(&c->dTables, sizeof(Tables)));
-  CK(cudaMalloc(&c->dIn, c->frameSamples * 2 * (size_t)c->maxFrames));
-  CK(cudaMalloc(&c->dRec, c->frameSamples * sizeof(int16_t) * (size_t)c->maxFrames));
-  CK(cudaMalloc(&c->dOut, sizeof(fhc_ctu_result) * (size_t)c->numCtus * (size_t)c->maxFrames));
-  CK(cudaStreamCreate(&c->stream));
-  CK(cudaEventCreate(&c->evStart));
-  CK(cudaEventCreate(&c->evStop));
   Tables t;
   build_tables(&t, seq->bitDepth);
-  CK(cudaMemcpy(c->dTables, &t, sizeof(t), cudaMemcpyHostToDevice));
-  CK(cudaDeviceSetLimit(cudaLimitStackSize, 24576));
+  CKG(cudaMemcpy(c->dTables, &t, sizeof(t), cudaMemcpyHostToDevice), fhc_destroy(c));
   *out = c;
   return FHC_OK;
 }
 
-int fhc_destroy(fhc_ctx* c)
+// the batch a new submit goes to: the least recently used one, after its kernel has finished
+static int take_batch(fhc_ctx* c, Batch** out)
 {
-  if (!c) return FHC_ERR_ARG;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(c->dPics); cudaFree(c->dScratch); cudaFree(c->dQueue); cudaFree(c->dTables); cudaFree(c->dIn); cudaFree(c->dRec); cudaFree(c->dOut);
-  cudaEventDestroy(c->evStart); cudaEventDestroy(c->evStop);
-  cudaStreamDestroy(c->stream);
-  delete c;
+  Batch* bt = &c->batch[0];
+  for (int i = 1; i < FHC_BATCHES; i++) if (c->batch[i].serial < bt->serial) bt = &c->batch[i];
+  if (bt->launched) CK(cudaEventSynchronize(bt->evStop));
+  bt->launched = 0; bt->n = 0;
+  *out = bt;
   return FHC_OK;
 }
 
-// fills the picture queue and launches the persistent kernel on c->stream
-static int launch(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params* sp)
+// makes sure the batch's input buffer holds n pictures of sampleBytes samples
+static int ensure_input(fhc_ctx* c, Batch* bt, int sampleBytes)
 {
+  const size_t need = c->frameSamples * (size_t)sampleBytes;
+  if (need <= bt->inBytesPerFrame) return FHC_OK;
+  CK(cudaFree(bt->dIn));
+  bt->dIn = nullptr; bt->inBytesPerFrame = 0;
+  CK(cudaMalloc(&bt->dIn, need * (size_t)c->maxFrames));
+  bt->inBytesPerFrame = need;
+  return FHC_OK;
+}
+
+// fills the picture queue and launches the persistent kernel on the compute stream
+static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, const fhc_slice_params* sp)
+{
+  const int W = c->seq.width;
+  const size_t frameBytes = c->frameSamples * (size_t)sampleBytes;
   for (int i = 0; i < n; i++)
   {
-    const uint8_t* in = c->dIn + (size_t)i * c->frameSamples * (size_t)sampleBytes;
-    int16_t* rec = c->dRec + (size_t)i * c->frameSamples;
+    const uint8_t* in = bt->dIn + (size_t)i * frameBytes;
     PicDesc& d = c->hostPics[(size_t)i];
     memset(&d, 0, sizeof(d));
     d.org[0] = in; d.org[1] = in + c->lumaSamples * (size_t)sampleBytes; d.org[2] = in + (c->lumaSamples + c->lumaSamples / 4) * (size_t)sampleBytes;
-    d.rec[0] = rec; d.rec[1] = rec + c->lumaSamples; d.rec[2] = rec + c->lumaSamples + c->lumaSamples / 4;
-    d.out = c->dOut + (size_t)i * c->numCtus;
+    d.out = bt->dOut + (size_t)i * c->numCtus;
+    int16_t* ln = bt->dLines + (size_t)i * 4 * W;
+    uint8_t* dr = bt->dDepthRows + (size_t)i * W;
+    for (int k = 0; k < 2; k++)
+    {
+      d.line[k][0] = ln + (size_t)k * 2 * W; d.line[k][1] = d.line[k][0] + W; d.line[k][2] = d.line[k][1] + W / 2;
+      d.depthRow[k] = dr + (size_t)k * (W / 2);
+    }
     d.sp = sp[i];
-    d.width = c->seq.width; d.height = c->seq.height; d.bitDepth = c->seq.bitDepth; d.sampleBytes = sampleBytes;
-    d.wc = (c->seq.width + 63) / 64; d.hc = (c->seq.height + 63) / 64;
+    d.width = W; d.height = c->seq.height; d.bitDepth = c->seq.bitDepth; d.sampleBytes = sampleBytes;
+    d.wc = (W + 63) / 64; d.hc = (c->seq.height + 63) / 64;
+    d.doneFlag = bt->dFlags + i;
+    bt->hFlags[i] = 0;
+    if (bt->hTrace) { d.trace = bt->dTrace + 8 * i; memset(bt->hTrace + 8 * i, 0, 32); }
   }
-  CK(cudaMemcpyAsync(c->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->dQueue, 0, sizeof(int), c->stream));
-  int blocks = (n + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
-  if (blocks > c->maxBlocks) blocks = c->maxBlocks;
-  CK(cudaEventRecord(c->evStart, c->stream));
-  fhc_compress_pictures_kernel<<<blocks, FHC_BLOCK_THREADS, kernel_smem_bytes(), c->stream>>>(c->dPics, n, c->dQueue, c->dScratch, c->dTables);
+  // picture descriptors travel on the copy stream (pageable source: staged before the call returns), so a submit
+  // queued behind a running kernel does not wait for it on the host
+  CK(cudaMemcpyAsync(bt->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaEventRecord(bt->evCopied, c->copyIn));
+  CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
+  CK(cudaMemsetAsync(bt->dQueue, 0, sizeof(int), c->compute));
+  const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
+  CK(cudaEventRecord(bt->evStart, c->compute));
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes, c->compute>>>(bt->dPics, n, bt->dQueue, c->dWorkspace, c->wsPerBlock, c->dTables);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(c->evStop, c->stream));
+  CK(cudaEventRecord(bt->evStop, c->compute));
   g_launches++;
+  bt->firstPoc = first_poc; bt->n = n; bt->launched = 1; bt->serial = ++c->submits;
   return FHC_OK;
 }
 
@@ -223,93 +277,166 @@ int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sam
   if (!c || !yuv || !per_frame || n <= 0 || n > c->maxFrames || (sampleBytes != 1 && sampleBytes != 2)) return FHC_ERR_ARG;
   if (c->seq.bitDepth > 8 && sampleBytes != 2) return FHC_ERR_ARG;
   CK(cudaSetDevice(c->device));
-  if (c->pending) CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpyAsync(c->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  int rc = launch(c, n, sampleBytes, per_frame);
+  Batch* bt;
+  int rc = take_batch(c, &bt);
   if (rc != FHC_OK) return rc;
-  c->firstPoc = first_poc; c->nSubmitted = n; c->pending = 1;
+  rc = ensure_input(c, bt, sampleBytes);
+  if (rc != FHC_OK) return rc;
+  // the copy runs on its own stream, so it overlaps the kernel of the previous submit
+  CK(cudaMemcpyAsync(bt->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
+  return launch(c, bt, first_poc, n, sampleBytes, per_frame);
+}
+
+static Batch* find_batch(fhc_ctx* c, int poc, int* slot)
+{
+  Batch* best = nullptr;
+  for (int i = 0; i < FHC_BATCHES; i++)
+  {
+    Batch* bt = &c->batch[i];
+    if (bt->n > 0 && poc >= bt->firstPoc && poc < bt->firstPoc + bt->n && (!best || bt->serial > best->serial)) best = bt;
+  }
+  if (best) *slot = poc - best->firstPoc;
+  return best;
+}
+
+// waits until the device has set the picture's done flag (written by the kernel when the picture's last CTU is stored)
+static int wait_picture(fhc_ctx* c, Batch* bt, int slot)
+{
+  volatile int32_t* f = bt->hFlags + slot;
+  unsigned spins = 0;
+  const char* wd = getenv("FHC_WATCHDOG_S");
+  const double limit = wd ? atof(wd) : 0.0;
+  const clock_t t0 = clock();
+  while (!*f)
+  {
+    if ((++spins & 1023) == 0)
+    {
+      if (limit > 0 && (double)(clock() - t0) / CLOCKS_PER_SEC > limit)
+      {
+        // debugging aid: report where the picture's block is (FHC_TRACE=1) instead of spinning forever
+        const int32_t* tw = bt->hTrace ? bt->hTrace + 8 * slot : nullptr;
+        const int tr = tw ? tw[0] : -1;
+        snprintf(g_err, sizeof(g_err), "watchdog: picture slot %d not finished after %.0f s; trace ctu %d z %d stage %d; roles %d %d %d %d %d", slot, limit,
+                 tr >> 12, (tr >> 4) & 255, tr & 15, tw ? tw[1] : -1, tw ? tw[2] : -1, tw ? tw[3] : -1, tw ? tw[4] : -1, tw ? tw[5] : -1);
+        return FHC_ERR_CUDA;
+      }
+      const cudaError_t q = cudaEventQuery(bt->evStop);
+      if (q == cudaSuccess) { if (*f) break; snprintf(g_err, sizeof(g_err), "kernel finished without completing picture slot %d", slot); return FHC_ERR_CUDA; }
+      if (q != cudaErrorNotReady) { snprintf(g_err, sizeof(g_err), "kernel failed: %s", cudaGetErrorString(q)); return FHC_ERR_CUDA; }
+    }
+  }
+  (void)c;
   return FHC_OK;
 }
 
-static int wait_done(fhc_ctx* c)
+int fhc_poll_picture(fhc_ctx* c, int poc)
 {
-  if (c->pending)
-  {
-    CK(cudaStreamSynchronize(c->stream));
-    c->pending = 0;
-  }
-  return FHC_OK;
+  if (!c) return FHC_ERR_ARG;
+  int slot = 0;
+  Batch* bt = find_batch(c, poc, &slot);
+  if (!bt) return FHC_ERR_STATE;
+  return *(volatile int32_t*)(bt->hFlags + slot) ? 1 : 0;
 }
 
 int fhc_fetch_ctu(fhc_ctx* c, int poc, int ctuRsAddr, fhc_ctu_result* out)
 {
   if (!c || !out) return FHC_ERR_ARG;
-  if (c->nSubmitted == 0) return FHC_ERR_STATE;
-  const int slot = poc - c->firstPoc;
-  if (slot < 0 || slot >= c->nSubmitted || ctuRsAddr < 0 || ctuRsAddr >= c->numCtus) return FHC_ERR_ARG;
+  if (c->submits == 0) return FHC_ERR_STATE;
+  int slot = 0;
+  Batch* bt = find_batch(c, poc, &slot);
+  if (!bt || ctuRsAddr < 0 || ctuRsAddr >= c->numCtus) return FHC_ERR_ARG;
   CK(cudaSetDevice(c->device));
-  int rc = wait_done(c);
+  int rc = wait_picture(c, bt, slot);
   if (rc != FHC_OK) return rc;
-  CK(cudaMemcpy(out, c->dOut + (size_t)slot * c->numCtus + ctuRsAddr, sizeof(fhc_ctu_result), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(out, bt->dOut + (size_t)slot * c->numCtus + ctuRsAddr, sizeof(fhc_ctu_result), cudaMemcpyDeviceToHost, c->copyOut));
+  CK(cudaStreamSynchronize(c->copyOut));
   return FHC_OK;
 }
 
 int fhc_fetch_picture(fhc_ctx* c, int poc, fhc_ctu_result* out)
 {
   if (!c || !out) return FHC_ERR_ARG;
-  if (c->nSubmitted == 0) return FHC_ERR_STATE;
-  const int slot = poc - c->firstPoc;
-  if (slot < 0 || slot >= c->nSubmitted) return FHC_ERR_ARG;
+  if (c->submits == 0) return FHC_ERR_STATE;
+  int slot = 0;
+  Batch* bt = find_batch(c, poc, &slot);
+  if (!bt) return FHC_ERR_ARG;
   CK(cudaSetDevice(c->device));
-  int rc = wait_done(c);
+  int rc = wait_picture(c, bt, slot);
   if (rc != FHC_OK) return rc;
-  CK(cudaMemcpy(out, c->dOut + (size_t)slot * c->numCtus, sizeof(fhc_ctu_result) * (size_t)c->numCtus, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(out, bt->dOut + (size_t)slot * c->numCtus, sizeof(fhc_ctu_result) * (size_t)c->numCtus, cudaMemcpyDeviceToHost, c->copyOut));
+  CK(cudaStreamSynchronize(c->copyOut));
+  return FHC_OK;
+}
+
+int fhc_fetch_picture_async(fhc_ctx* c, int poc, fhc_ctu_result* out)
+{
+  if (!c || !out) return FHC_ERR_ARG;
+  if (c->submits == 0) return FHC_ERR_STATE;
+  int slot = 0;
+  Batch* bt = find_batch(c, poc, &slot);
+  if (!bt) return FHC_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = wait_picture(c, bt, slot);
+  if (rc != FHC_OK) return rc;
+  CK(cudaMemcpyAsync(out, bt->dOut + (size_t)slot * c->numCtus, sizeof(fhc_ctu_result) * (size_t)c->numCtus, cudaMemcpyDeviceToHost, c->copyOut));
+  return FHC_OK;
+}
+
+int fhc_fetch_sync(fhc_ctx* c)
+{
+  if (!c) return FHC_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->copyOut));
   return FHC_OK;
 }
 
 int fhc_device_input(fhc_ctx* c, void** dptr, uint64_t* bytes)
 {
   if (!c || !dptr) return FHC_ERR_ARG;
-  *dptr = c->dIn;
-  if (bytes) *bytes = (uint64_t)c->frameSamples * 2 * (uint64_t)c->maxFrames;
+  Batch* bt = &c->batch[0];
+  for (int i = 1; i < FHC_BATCHES; i++) if (c->batch[i].serial < bt->serial) bt = &c->batch[i];
+  *dptr = bt->dIn;
+  if (bytes) *bytes = (uint64_t)bt->inBytesPerFrame * (uint64_t)c->maxFrames;
   return FHC_OK;
 }
 
 int fhc_run_resident(fhc_ctx* c, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms)
 {
   if (!c || !per_frame || n <= 0 || n > c->maxFrames || (sampleBytes != 1 && sampleBytes != 2)) return FHC_ERR_ARG;
+  if (c->seq.bitDepth > 8 && sampleBytes != 2) return FHC_ERR_ARG;
   CK(cudaSetDevice(c->device));
-  if (c->pending) CK(cudaStreamSynchronize(c->stream));
-  int rc = launch(c, n, sampleBytes, per_frame);
+  Batch* bt;
+  int rc = take_batch(c, &bt);
   if (rc != FHC_OK) return rc;
-  CK(cudaStreamSynchronize(c->stream));
-  c->firstPoc = 0; c->nSubmitted = n; c->pending = 0;
-  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, c->evStart, c->evStop));
+  if (c->frameSamples * (size_t)sampleBytes > bt->inBytesPerFrame) return FHC_ERR_ARG;      // nothing resident at that sample size
+  rc = launch(c, bt, 0, n, sampleBytes, per_frame);
+  if (rc != FHC_OK) return rc;
+  CK(cudaEventSynchronize(bt->evStop));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, bt->evStart, bt->evStop));
   return FHC_OK;
 }
 
 int fhc_last_kernel_ms(fhc_ctx* c, float* kernel_ms)
 {
   if (!c || !kernel_ms) return FHC_ERR_ARG;
-  if (c->nSubmitted == 0) return FHC_ERR_STATE;
+  if (c->submits == 0) return FHC_ERR_STATE;
   CK(cudaSetDevice(c->device));
-  int rc = wait_done(c);
-  if (rc != FHC_OK) return rc;
-  CK(cudaEventElapsedTime(kernel_ms, c->evStart, c->evStop));
+  Batch* bt = &c->batch[0];
+  for (int i = 1; i < FHC_BATCHES; i++) if (c->batch[i].serial > bt->serial) bt = &c->batch[i];
+  CK(cudaEventSynchronize(bt->evStop));
+  CK(cudaEventElapsedTime(kernel_ms, bt->evStart, bt->evStop));
   return FHC_OK;
 }
 
 int fhc_pictures_in_flight(int device)
 {
-  int ndev = 0, perSm = 0;
-  cudaDeviceProp prop;
+  int ndev = 0, maxBlocks = 0;
+  size_t smemBytes = 0, ws = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return FHC_ERR_ARG;
   CK(cudaSetDevice(device));
-  CK(cudaGetDeviceProperties(&prop, device));
-  CK(cudaFuncSetAttribute(fhc_compress_pictures_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kernel_smem_bytes()));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_compress_pictures_kernel, FHC_BLOCK_THREADS, kernel_smem_bytes()));
-  return prop.multiProcessorCount * perSm * FHC_PICS_PER_BLOCK;
+  if (kernel_geometry(device, &smemBytes, &ws, &maxBlocks) != FHC_OK) return FHC_ERR_CUDA;
+  return maxBlocks;
 }
 
 int fhc_host_alloc(void** p, uint64_t bytes)
@@ -324,25 +451,10 @@ int fhc_host_free(void* p)
   return FHC_OK;
 }
 
-// debug: cycle counters of picture `slot` (FHC_PROFILE builds; zeros otherwise)
-int fhc_debug_profile(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
-{
-  if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
-  CK(cudaMemcpy(cycles16, c->dPics[slot].prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(counts16, c->dPics[slot].profN, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  return FHC_OK;
-}
-extern "C" int fhc_debug_profile2(fhc_ctx* c, int slot, long long* cycles16, long long* counts16)
-{
-  if (!c || slot < 0 || slot >= c->maxFrames) return FHC_ERR_ARG;
-  CK(cudaMemcpy(cycles16, c->dPics[slot].prof2, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(counts16, c->dPics[slot].prof2N, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-  return FHC_OK;
-}
-// debug: launch geometry {blocks, warps per block, dynamic shared memory bytes, per-warp global scratch bytes}
+// debug: launch geometry {resident blocks, threads per block, dynamic shared memory bytes, global workspace bytes per block}
 extern "C" int fhc_debug_geometry(fhc_ctx* c, long long* out4)
 {
   if (!c || !out4) return FHC_ERR_ARG;
-  out4[0] = c->maxBlocks; out4[1] = FHC_WARPS_PER_BLOCK * 1000 + FHC_GROUP; out4[2] = (long long)kernel_smem_bytes(); out4[3] = (long long)sizeof(FrameGlobal);
+  out4[0] = c->maxBlocks; out4[1] = FHC_BLOCK_THREADS; out4[2] = (long long)c->smemBytes; out4[3] = (long long)c->wsPerBlock;
   return FHC_OK;
 }

@@ -124,6 +124,7 @@ struct PicDesc                    // global memory, one per submitted picture (f
   fhc_slice_params sp;
   int32_t width, height, bitDepth, sampleBytes, wc, hc;
   int32_t* doneFlag;              // set to 1 (system scope) when the picture is finished
+  int32_t* trace;                 // optional progress word (host-mapped): ctu << 12 | region z << 4 | stage; 0 = off
   long long prof[16];             // clock64 counters (FHC_PROFILE builds)
 };
 
@@ -135,7 +136,16 @@ struct PicParams                  // hot copy of the picture header (shared memo
   uint8_t* depthRow[2];
   fhc_slice_params sp;
   int32_t width, height, bitDepth, sampleBytes, wc, hc;
+  int32_t* trace;
 };
+FHC_DH void trace_at(const PicParams& pp, int ctu, int z, int stage)
+{
+  if (pp.trace && FHC_LANE == 0) *(volatile int32_t*)pp.trace = (ctu << 12) | (z << 4) | stage;
+}
+FHC_DH void trace_role(const PicParams& pp, int ri, int stage)          // words 1..7 of the picture's trace record: one per role
+{
+  if (pp.trace && FHC_LANE == 0) *(volatile int32_t*)(pp.trace + 1 + ri) = stage;
+}
 
 // One role = one warp = one CU hypothesis under evaluation ("job").  Buffers are carved from the shared-memory arena
 // (depth 2, 3; the small hot state of depth 0, 1) or from the block's global workspace (sample / coefficient scratch
@@ -210,8 +220,9 @@ FHC_DH int yuv_off(int cuw, int comp) { return comp == 0 ? 0 : (comp == 1 ? cuw 
 // named-barrier hand-shake between the chain master and a role warp (device); the host build runs the job at the join
 // ----------------------------------------------------------------------------------------------
 #ifdef FHC_DEVICE_BUILD
-FHC_DH void bar_sync(int id) { asm volatile("barrier.sync %0, 64;" ::"r"(id) : "memory"); }
-FHC_DH void bar_arrive(int id) { asm volatile("barrier.arrive %0, 64;" ::"r"(id) : "memory"); }
+// aligned forms: the whole (converged) warp executes the instruction once and counts as 32 threads
+FHC_DH void bar_sync(int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+FHC_DH void bar_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 #endif
 FHC_DH int bar_start(int role) { return 1 + role; }
 FHC_DH int bar_done(int role) { return 1 + FHC_ROLES + role; }
@@ -1072,6 +1083,7 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   const int16_t* line = use_filtered_refs(t, comp, a.mode, log2n) ? a.refF : a.refU;
   const int16_t* src = b->src + a.srcOff;
   FHC_COUNT(if (g.gl == 0) { g_emuCounters.tqSamples[isChroma][log2n - 2] += (unsigned)n2; g_emuCounters.tuCalls[isChroma][log2n - 2]++; });
+  gsync(g);                                                            // every lane has consumed the accumulators of the previous TU
   if (g.gl == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; }
   // prediction + residual
   FHC_GLANES(g, i, n2)
@@ -1825,8 +1837,12 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
     if (w.gl == 0) r->dcVal = dc;
     warp_sync();
   }
+  const int ri = (int)(r - b->role);
+  trace_role(b->pp, ri, 16 + pu * 8 + 1);
   rmd_satd(b, r, log2pu, px, py);
+  trace_role(b->pp, ri, 16 + pu * 8 + 2);
   rmd_candidates(b, r, pu, log2pu);
+  trace_role(b->pp, ri, 16 + pu * 8 + 3);
   const int numCand = r->numCand, tasks = numCand * (log2pu == 2 ? 2 : 1);
   for_groups(tasks, [&](const Grp& g)
   {
@@ -1908,6 +1924,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
       }
     }
   });
+  trace_role(b->pp, ri, 16 + pu * 8 + 4);
   // winner: lowest cost, ties to the lowest task index = HM's sequential scan with strict <
   int best = 0;
   FHC_NOUNROLL for (int i = 1; i < tasks; i++) if (r->gCost[i] < r->gCost[best]) best = i;
@@ -2113,7 +2130,9 @@ FHC_D void run_job(Blk* b, Role* r)
   const int isNxN = r->partSize == SIZE_NxN, np = r->np;
   if (w.gl == 0) { r->dist = 0; r->ldir[0] = r->ldir[1] = r->ldir[2] = r->ldir[3] = DC_IDX; r->cdir = 0; }
   warp_sync();
-  for (int pu = 0; pu < (isNxN ? 4 : 1); pu++) search_luma_pu(b, r, pu);
+  const int ri = (int)(r - b->role);
+  trace_role(b->pp, ri, 1);
+  for (int pu = 0; pu < (isNxN ? 4 : 1); pu++) { search_luma_pu(b, r, pu); trace_role(b->pp, ri, 2 + pu); }
   if (isNxN)
   {
     // cbf of the CU level: set when any PU has coefficients (TEncSearch.cpp:2531-2548)
@@ -2124,6 +2143,7 @@ FHC_D void run_job(Blk* b, Role* r)
     warp_sync();
   }
   search_chroma(b, r);
+  trace_role(b->pp, ri, 6);
   // bits of the whole CU in real syntax order on the CI_CURR_BEST contexts (TEncCu.cpp:1564-1588)
   GScr s = group_scratch(r, 0);
   Hyp h = hyp_of(r, r->tridx, r->cbf[0], r->cbf[1], r->cbf[2], r->ts[0], r->ts[1], r->ts[2], r->bestCoef, s.nz);
@@ -2214,10 +2234,13 @@ FHC_D void region(Blk* b, int z)
   if (D == 3)
   {
     // 8x8 CU: 2Nx2N here, NxN on its own warp (both start from [3][CI_CURR_BEST], TEncCu.cpp:806-815)
+    trace_at(b->pp, b->ctuAddr, z, 1);
     start_job(b, ROLE_3B, z, SIZE_NxN);
     set_job(b, ROLE_3A, z, SIZE_2Nx2N);
     run_job(b, &b->role[ROLE_3A]);
+    trace_at(b->pp, b->ctuAddr, z, 2);
     join_job(b, ROLE_3B);
+    trace_at(b->pp, b->ctuAddr, z, 3);
     const Role* a = &b->role[ROLE_3A];
     const Role* n = &b->role[ROLE_3B];
     const Role* win = (n->cost < a->cost) ? n : a;                    // xCheckBestMode: strict <, 2Nx2N was first
@@ -2271,7 +2294,9 @@ FHC_D void region(Blk* b, int z)
   Role* r = &b->role[ri];
   if (inside)
   {
+    trace_at(b->pp, b->ctuAddr, z, 4 + D);
     join_job(b, ri);
+    trace_at(b->pp, b->ctuAddr, z, 8 + D);
     // the 2Nx2N hypothesis + split_cu_flag = 0 on its own contexts (TEncCu.cpp:839-848)
     if (w.gl == 0)
     {
@@ -2347,6 +2372,7 @@ FHC_D void encode_ctu(Blk* b)
 FHC_D void master_ctu(Blk* b)
 {
   region<0>(b, 0);
+  trace_at(b->pp, b->ctuAddr, 0, 12);
 #ifdef FHC_DEVICE_BUILD
   for (int ri = 1; ri < FHC_ROLES; ri++)
   {
@@ -2363,7 +2389,9 @@ FHC_D void role_loop(Blk* b, int ri)
 {
   for (;;)
   {
+    trace_role(b->pp, ri, 100);
     bar_sync(bar_start(ri));
+    trace_role(b->pp, ri, 101);
     if (!b->mailbox[ri]) break;
     run_job(b, &b->role[ri]);
     bar_arrive(bar_done(ri));
@@ -2388,7 +2416,7 @@ FHC_HD void role_config(Role* r, int ri)
   r->depth = depth; r->cuw = 64 >> depth; r->log2cu = 6 - depth; r->np = 256 >> (2 * depth); r->yuvSize = (r->cuw * r->cuw * 3) >> 1;
   r->maxGroups = ri == ROLE_3B ? 20 : (ri == ROLE_3A ? 10 : 5);
   r->tuCap = ri == ROLE_3B ? 16 : (r->cuw > 32 ? 1024 : r->cuw * r->cuw);
-  r->refCap = depth == 0 ? 132 : 2 * r->cuw + 4;
+  r->refCap = depth == 0 ? 132 : (depth == 3 ? 36 : 2 * r->cuw + 4);       // depth 3: 32 samples of transform-skip save area (search_chroma)
 }
 // carves the buffers of role ri; sm / gm may have p == 0 to only measure sizes
 FHC_HD void role_carve(Role* r, int ri, Arena* sm, Arena* gm)
@@ -2547,6 +2575,7 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
     pp.depthRow[0] = pd->depthRow[0]; pp.depthRow[1] = pd->depthRow[1];
     pp.out = pd->out; pp.sp = pd->sp;
     pp.width = pd->width; pp.height = pd->height; pp.bitDepth = pd->bitDepth; pp.sampleBytes = pd->sampleBytes; pp.wc = pd->wc; pp.hc = pd->hc;
+    pp.trace = pd->trace;
   }
 #ifdef FHC_DEVICE_BUILD
   __syncthreads();

@@ -79,16 +79,27 @@ int fhc_destroy(fhc_ctx* ctx);
 /* Hands n consecutive pictures (POC first_poc .. first_poc+n-1) to the device and starts
  * their mode decision.  yuv420_planar: n pictures, each Y then Cb then Cr, sampleBytes 1 or 2
  * (host memory).  Replaces the per-CTU calls of TEncSlice::compressSlice -> compressCtu
- * (TEncSlice.cpp:879) for those pictures. Asynchronous. */
+ * (TEncSlice.cpp:879) for those pictures.  Asynchronous; two submits may be outstanding (the second
+ * one's host->device copy overlaps the first one's kernel), a third waits for the oldest to finish,
+ * whose results are then no longer fetchable.  A page-locked yuv buffer must stay untouched until a
+ * fetch of one of its pictures has returned (pageable memory is staged before the call returns). */
 int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
                       const fhc_slice_params* per_frame);
 
-/* Blocks until picture `poc` is finished, then copies CTU `ctuRsAddr` into *out.
+/* Blocks until picture `poc` is finished (only that picture: the device sets a per-picture flag; other pictures of
+ * the submit may still be running), then copies CTU `ctuRsAddr` into *out.
  * This is the body of the replaced TEncCu::xCompressCU(depth 0) (TEncCu.cpp:496). */
 int fhc_fetch_ctu(fhc_ctx* ctx, int poc, int ctuRsAddr, fhc_ctu_result* out);
 
 /* Bulk variant: all CTUs of a picture in raster order (out has numCtus entries). */
 int fhc_fetch_picture(fhc_ctx* ctx, int poc, fhc_ctu_result* out);
+/* 1 when picture `poc` is finished on the device, 0 when not yet, negative = error.  Never blocks. */
+int fhc_poll_picture(fhc_ctx* ctx, int poc);
+/* Like fhc_fetch_picture, but only queues the device->host copy (out should be page-locked) on the
+ * library's copy stream, where it overlaps the kernel still working on other pictures;
+ * fhc_fetch_sync waits for all queued copies. */
+int fhc_fetch_picture_async(fhc_ctx* ctx, int poc, fhc_ctu_result* out);
+int fhc_fetch_sync(fhc_ctx* ctx);
 
 /* Number of CTUs per picture (TComPicSym::getNumberOfCtusInFrame). */
 int fhc_num_ctus(const fhc_ctx* ctx);
@@ -105,8 +116,8 @@ int fhc_device_input(fhc_ctx* ctx, void** dptr, uint64_t* bytes);
 int fhc_run_resident(fhc_ctx* ctx, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms);
 /* CUDA-event time of the kernel of the last submit (waits for it to finish). */
 int fhc_last_kernel_ms(fhc_ctx* ctx, float* kernel_ms);
-/* Number of pictures the persistent kernel encodes concurrently on `device` (SMs x resident blocks x pictures per
- * block): submits of at least this many pictures keep the whole device busy.  Negative = error. */
+/* Number of pictures the persistent kernel encodes concurrently on `device` (SMs x resident thread blocks, one
+ * picture per block): submits of at least this many pictures keep the whole device busy.  Negative = error. */
 int fhc_pictures_in_flight(int device);
 /* Page-locked host buffers for submit/fetch (optional; any host memory works). */
 int fhc_host_alloc(void** p, uint64_t bytes);
