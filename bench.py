@@ -3,17 +3,14 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A step = one pass of the hot path (TEncCu::xCompressCU and below, for every CTU of every picture) over one batch of
-synthetic 1920x1080 4:2:0 8-bit pictures per GPU: the 64-frame clip of BASELINE configs[1] at QP 22/27/32/37, cycled to
-`--rounds` (default 1.0) times as many (picture, QP) jobs as the persistent kernel keeps in flight
-(fhc_pictures_in_flight = 148 SMs x 20 pictures per block, one warp per picture), QP-major = expensive first.  (More
-rounds let blocks that finish early pull further jobs, but a job is a whole picture = minutes: measured at 416x240,
-1.25 rounds take 1.53x the time of one.)  Every timed step goes through the C ABI with host buffers (pinned H2D
-of the pictures, kernel, D2H of every CTU record): `e2e` is the wall time of that, `value` the CUDA-event time of the
-kernel inside the same steps (inputs resident in HBM when it starts), max over ranks.  N > 1: one process per GPU
-(torchrun), every rank encodes its own contiguous frame group, no collective on the data path -
-torch.distributed only provides the barrier and the max over ranks.  A 1080p picture is one dependent chain of 510 CTUs
-and takes minutes whatever the batch size, so a step takes minutes; warm-up steps use 1920x64 strips.
+Workload = BASELINE configs[1]: encoder_intra_main.cfg, 1920x1080 8-bit 4:2:0, the 64-frame synthetic clip at QP 22 / 27 /
+32 / 37 = 256 picture jobs per GPU.  A step = one pass of the hot path (TEncCu::xCompressCU and everything below it, for
+all 510 CTUs of every picture) over those 256 pictures, through the C ABI with HOST buffers: fhc_submit_frames (page-
+locked H2D of the 256 pictures), the persistent kernel (one thread block per picture chain), fhc_fetch_picture_async of
+every picture's CTU records (page-locked D2H).  `e2e` is the wall time of the steps, `value` the CUDA-event time of the
+kernel inside the same steps (inputs resident in HBM when it starts); both max over ranks.  N > 1: one process per GPU
+(torchrun), every rank encodes its own contiguous 64-frame group (configs[2]: 512 frames on 8 GPUs, weak scaling), no
+collective on the data path and no NCCL - a gloo group provides the barrier and the max over ranks.
 
 `--impl reference` times the UNMODIFIED reference encoder (oracle/_ref/TAppEncoder, HM 16.14 with the OpenCV dump
 stubbed) on the host cores: one process per core, one 1080p picture each per step.
@@ -34,19 +31,19 @@ sys.path.insert(0, ROOT)
 W, H, CLIP = 1920, 1080, 64
 QPS = [22, 27, 32, 37]
 CTUS = 30 * 17
+RING = 8                            # page-locked result slots the fetched pictures cycle through
 # algorithmic bytes per CTU = 6144 source + 12288 reconstruction + 12288 levels + ~6 KB metadata
 ALGO_BYTES_PER_CTU = 6144 + 12288 + 12288 + 6144
-INT_OPS_PER_CTU = 42.1e6            # SURVEY.md 8(d) W_ctu, counted exactly on the bench mix: profiles/r01_work_counts.md
-WARM_H = 64                         # height of the warm-up strips (one CTU row)
-NCU_DRAM_BYTES_PER_CTU = (459.21e9 + 247.55e9) / 2960     # profiles/r01_final_w20_loaded.md
+# SURVEY.md 8(d) W_ctu = 13 S_rmd + sum_size w_size S_tq,size + 30 bins, counted exactly on this workload's QP mix by
+# tools/work_count.py on the host emulation of the kernel source (profiles/r02_work_counts.md)
+INT_OPS_PER_CTU = 42.1e6
 
 
-def load_peaks():
+def load_json(name):
     try:
-        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return json.load(open(os.path.join(ROOT, name)))
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -77,12 +74,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def job_list(first_frame, n_frames, n_jobs):
-    """(frame, qp) jobs of one rank: its frame group at every QP, QP-major, truncated/cycled to n_jobs."""
-    all_jobs = [(first_frame + f, q) for q in QPS for f in range(n_frames)]
-    return [all_jobs[i % len(all_jobs)] for i in range(n_jobs)]
-
-
 def run_ours(args, rank, world, local_rank):
     import torch
     import fasthevc_b200 as fh
@@ -91,50 +82,51 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"                  # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # one round by default: every resident warp gets one picture (see --rounds)
-    n_jobs = args.jobs if args.jobs > 0 else int(fh.pictures_in_flight(local_rank) * args.rounds)
-    # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
-    first, last = frame_group(CLIP * world, rank, world)
-    jobs = job_list(first, last - first, n_jobs)
-    # distinct synthetic pictures are expensive to synthesise on the host: 8 distinct pictures per rank, cycled
-    n_distinct = 8
-    Y, U, V = synth_frames(W, H, n_distinct, first_frame=first)
-    sps = [fh.slice_params_from_qp(q) for _, q in jobs]
+        dist.init_process_group("gloo")                   # host-side barrier / max only: the data path has no collective
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
 
-    # ---- warm-up: the same kernel, the same number of pictures, on one-CTU-row strips (1920x64)
-    # of the same content: a full 1080p step takes minutes because a picture is one dependent chain of 510 CTUs
-    wenc = fh.Encoder(W, WARM_H, 8, max_frames=n_jobs, device=local_rank)
-    wpacked = wenc.pack_frames(Y[:, :WARM_H], U[:, :WARM_H // 2], V[:, :WARM_H // 2])
-    whost = wenc.pinned_array((n_jobs, wenc.frame_samples), np.uint8)
-    for j, (f, _) in enumerate(jobs):
-        whost[j] = wpacked[(f - first) % n_distinct]
-    wout = np.zeros(wenc.num_ctus, fh.CTU_RESULT_DTYPE)
-    for _ in range(args.warmup):
-        wenc.submit(whost, sps)
-        wenc.fetch_picture(n_jobs - 1, wout)
-    wenc.close()
+    # weak scaling: every rank owns a 64-frame group of the (64 * world)-frame sequence (configs[2]: 512 frames on 8 GPUs)
+    first, last = frame_group(args.frames * world, rank, world)
+    n_frames = last - first
+    jobs = [(f, q) for q in QPS for f in range(n_frames)]          # QP-major: the expensive pictures start first
+    n_jobs = len(jobs)
+    t_gen = time.perf_counter()
+    Y, U, V = synth_frames(W, H, n_frames, first_frame=first)
+    t_gen = time.perf_counter() - t_gen
+    sps = [fh.slice_params_from_qp(q) for _, q in jobs]
 
     enc = fh.Encoder(W, H, 8, max_frames=n_jobs, device=local_rank)
     host_in = enc.pinned_array((n_jobs, enc.frame_samples), np.uint8)
     packed = enc.pack_frames(Y, U, V)
     for j, (f, _) in enumerate(jobs):
-        host_in[j] = packed[(f - first) % n_distinct]
-    host_out = enc.pinned_array((enc.num_ctus,), fh.CTU_RESULT_DTYPE)      # one picture's records, reused
-    rec_bytes = int(host_out.nbytes)
+        host_in[j] = packed[f]
+    del packed, Y, U, V
+    host_out = enc.pinned_array((RING, enc.num_ctus), fh.CTU_RESULT_DTYPE)
+    rec_bytes = int(host_out[0].nbytes)
+    int_peak_gops, _ = fh.measure_int_issue(local_rank)
 
-    # ---- timed region: K steps through the C ABI with host buffers (pinned H2D of every picture, kernel, D2H of every
-    # CTU record).  `value` uses the CUDA-event time of the kernel of the same steps (inputs resident when it starts).
+    def step():
+        """One pass over the 256 pictures with host buffers; returns (kernel ms, sum of CTU bit counts)."""
+        bits = 0
+        enc.submit(host_in, sps)
+        for j in range(n_jobs):
+            enc.fetch_picture_async(j, host_out[j % RING])
+            if j % RING == RING - 1 or j == n_jobs - 1:
+                enc.fetch_sync()
+                bits += int(host_out[:(j % RING) + 1]["totalBits"].sum(dtype=np.int64))
+        return enc.last_kernel_ms(), bits
+
+    t_w = time.perf_counter()
+    for _ in range(args.warmup):
+        step()
+    t_w = time.perf_counter() - t_w
+
     sampler = ClockSampler(local_rank)
     launches0 = int(enc.lib.fhc_launch_count())
     check_bits, kernel_ms = 0, []
@@ -142,62 +134,71 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        enc.submit(host_in, sps)
-        for j in range(n_jobs):
-            enc.fetch_picture(j, host_out)
-            check_bits += int(host_out["totalBits"].sum(dtype=np.int64))
-        kernel_ms.append(enc.last_kernel_ms())
+        ms, bits = step()
+        kernel_ms.append(ms)
+        check_bits += bits
+    e2e_local = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
     launches = int(enc.lib.fhc_launch_count()) - launches0
+    in_flight = fh.pictures_in_flight(local_rank)
     enc.close()
 
     my_ms = float(np.sum(kernel_ms))
+    per_rank = [[my_ms / args.steps, e2e_local / args.steps]]
     if dist is not None:
-        t = torch.tensor([my_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([my_ms, e2e_ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor(per_rank[0], dtype=torch.float64))
+        per_rank = [[round(float(v), 1) for v in g.tolist()] for g in gathered]
         my_ms, e2e_ms = [float(v) for v in t.tolist()]
     if rank == 0:
         total_jobs = n_jobs * world
         ms_per_step = my_ms / args.steps
-        print("bench: %d jobs/GPU x %d GPU(s), kernel %.1f ms/step, e2e %.1f ms/step" % (n_jobs, world, ms_per_step, e2e_ms / args.steps),
-              file=sys.stderr, flush=True)
+        print("bench: %d jobs/GPU x %d GPU(s), kernel %.1f ms/step, e2e %.1f ms/step (synthesis %.1f s, warm-up %.1f s)"
+              % (n_jobs, world, ms_per_step, e2e_ms / args.steps, t_gen, t_w), file=sys.stderr, flush=True)
         fps = total_jobs / (ms_per_step / 1e3)
         e2e_fps = total_jobs / (e2e_ms / args.steps / 1e3)
-        peak, peak_src = load_peaks()
+        peaks = load_json("MEASURED_PEAKS.json")
+        hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
         ctus_per_launch = CTUS * n_jobs
-        achieved = ALGO_BYTES_PER_CTU * ctus_per_launch / (ms_per_step / 1e3) / 1e9      # per launch (= per rank)
+        launch_s = ms_per_step / 1e3
+        int_achieved = INT_OPS_PER_CTU * ctus_per_launch / launch_s / 1e12        # Tops/s per launch (= per rank)
+        hbm_achieved = ALGO_BYTES_PER_CTU * ctus_per_launch / launch_s / 1e9
+        prof = load_json(os.path.join("profiles", "r02_kernel_counters.json")) or {}
         line = {
             "metric": "1080p all-intra encode fps (byte-identical CTU decisions)" if (W, H) == (1920, 1080) else "SELF-TEST %dx%d (not the metric)" % (W, H),
             "value": round(fps, 4), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64 (u8 samples, i16 levels)",
             "data": "synthetic",
-            "config": {"workload": "encoder_intra_main.cfg %dx%d 8-bit, 64-frame synthetic clip per GPU x QP{22,27,32,37}, cycled to " % (W, H) +
-                                   "%d picture jobs per GPU per step, QP-major = expensive first (%.2f x the pictures the persistent kernel "
-                                   "keeps in flight, one warp each: blocks that finish early pull the remaining jobs); warm-up steps run "
-                                   "the same kernel and job count on %dx%d strips" % (n_jobs, args.rounds if args.jobs <= 0 else 0.0, W, WARM_H),
-                       "jobs_per_gpu": n_jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective" % world,
-                       "l2_policy": "inputs+results per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (n_jobs * (3.1 + 14.1) / 1e3)},
+            "config": {"workload": "BASELINE configs[1]: encoder_intra_main.cfg %dx%d 8-bit, %d-frame synthetic clip per GPU x QP{22,27,32,37} = "
+                                   "%d picture jobs per GPU per step (one kernel launch, one thread block per picture chain, %d chains "
+                                   "resident per GPU), QP-major = expensive first; warm-up steps are full steps" % (W, H, n_frames, n_jobs, in_flight),
+                       "jobs_per_gpu": n_jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective, no NCCL" % world,
+                       "l2_policy": "inputs + results of a step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (n_jobs * (3.1 + 14.1) / 1e3)},
             "ctu_per_s": round(fps * CTUS, 1),
+            "picture_latency_s": round(ms_per_step / 1e3 / max(1, -(-n_jobs // in_flight)), 3),
             "e2e": {"value": round(e2e_fps, 4), "unit": "frames/s", "h2d_bytes_per_step": int(host_in.nbytes) * world,
                     "d2h_bytes_per_step": rec_bytes * n_jobs * world, "ms_per_step": round(e2e_ms / args.steps, 2)},
+            "per_rank_ms_per_step": {"kernel_e2e": per_rank},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 4), "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": round(NCU_DRAM_BYTES_PER_CTU * ctus_per_launch), "peak_source": peak_src,
-                         "traffic_note": "dram read+write of the ncu --set full capture profiles/r01_final_w20_loaded.md (one launch of "
-                                         "2960 one-CTU pictures) scaled by the CTUs of this launch: per-warp scratch and stack traffic "
-                                         "that misses L2, ~6500x the algorithmic bytes, ~0.8 TB/s = 13 %% of the HBM peak",
-                         "note": "the kernel is bound by instruction delivery and memory latency of one dependent chain per "
-                                 "picture, not by HBM or the tensor pipe (DESIGN.md 4): ncu issue-slot utilisation 23.4 %%, long-scoreboard 41 %% of the stall samples; "
-                                 "integer-equivalent work %.1f Gop/s of ~37,000 Gop/s nominal int32 issue"
-                                 % (INT_OPS_PER_CTU * fps * CTUS / world / 1e9)},
+            "roofline": {"bound": "int_issue", "achieved": round(int_achieved, 4), "peak": round(int_peak_gops / 1e3, 3), "unit": "Tops/s",
+                         "frac": int_achieved / (int_peak_gops / 1e3),
+                         "traffic": prof.get("dram_bytes_per_ctu") and round(prof["dram_bytes_per_ctu"] * ctus_per_launch),
+                         "peak_source": "measured live by fhc_measure_int_issue (IMAD/IADD3/LOP3 mix at full occupancy); committed run: profiles/int_issue_peak.json",
+                         "work_per_ctu": INT_OPS_PER_CTU,
+                         "hbm": {"achieved": round(hbm_achieved, 4), "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                                 "bytes_per_ctu": ALGO_BYTES_PER_CTU},
+                         "note": "SURVEY.md 8(d): the path is integer-issue / latency bound, not HBM or tensor bound; achieved = W_ctu x "
+                                 "CTUs per launch / launch time, W_ctu counted by tools/work_count.py"},
             "check_total_bits": check_bits,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_sample(1, 0)
+            line["cpu_baseline"] = cpu_baseline_both_legs()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -212,20 +213,28 @@ def ref_paths():
     return os.path.join(d, "TAppEncoder"), os.path.join(d, "cfg", "encoder_intra_main.cfg")
 
 
-def cpu_reference_step(workdir, cores, step_idx):
-    """One picture per core, all cores in parallel; returns (pictures, seconds)."""
+def ref_clip(workdir):
     from fasthevc_b200.synth import synth_frames, write_yuv
-    exe, cfg = ref_paths()
-    procs = []
     yuv = os.path.join(workdir, "clip.yuv")
     if not os.path.exists(yuv):
         Y, U, V = synth_frames(W, H, 4)
         write_yuv(yuv, Y, U, V)
+    return yuv
+
+
+def ref_cmd(workdir, yuv, frame, qp, tag):
+    exe, cfg = ref_paths()
+    return [exe, "-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-fs", str(frame), "-f", "1", "-q", str(qp),
+            "-b", os.path.join(workdir, "o%s.bin" % tag), "-o", ""]
+
+
+def cpu_reference_step(workdir, cores, step_idx):
+    """One picture per core, all cores in parallel; returns (pictures, seconds)."""
+    yuv = ref_clip(workdir)
+    procs = []
     t0 = time.perf_counter()
     for c in range(cores):
-        qp = QPS[(c + step_idx) % 4]
-        cmd = [exe, "-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-fs", str(c % 4), "-f", "1", "-q", str(qp),
-               "-b", os.path.join(workdir, "o%d.bin" % c), "-o", ""]
+        cmd = ref_cmd(workdir, yuv, c % 4, QPS[(c + step_idx) % 4], str(c))
         procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=workdir))
     for p in procs:
         p.wait()
@@ -245,10 +254,28 @@ def cpu_reference_sample(steps, warmup):
         a, b = cpu_reference_step(d, cores, warmup + i)
         n += a
         t += b
-    return {"value": round(n / t, 4), "unit": "frames/s", "cores": cores, "kind": "reference",
+    return {"value": round(n / t, 4), "unit": "frames/s", "cores": cores, "kind": "reference", "ctu_per_s": round(n / t * CTUS, 1),
             "sample": "oracle/_ref/TAppEncoder (HM 16.14, g++ -O2 -msse4.1): %d step(s) of one %dx%d picture per core, QP 22/27/32/37 "
                       "cycled over cores, one process per core" % (steps, W, H),
             "ms_per_step": round(t / steps * 1e3, 1)}
+
+
+def cpu_baseline_both_legs():
+    """(A) single process on one core, (B) one process per host core; bounded samples."""
+    exe, _ = ref_paths()
+    if not os.path.exists(exe):
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/TAppEncoder not built"}
+    b = cpu_reference_sample(1, 0)
+    d = tempfile.mkdtemp()
+    yuv = ref_clip(d)
+    cmd = ref_cmd(d, yuv, 0, 32, "single")
+    core0 = sorted(os.sched_getaffinity(0))[0]
+    t0 = time.perf_counter()
+    subprocess.run(["taskset", "-c", str(core0)] + cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=d)
+    t1 = time.perf_counter() - t0
+    b["single_process"] = {"value": round(1.0 / t1, 4), "unit": "frames/s", "cores": 1, "ctu_per_s": round(CTUS / t1, 1),
+                           "sample": "one %dx%d picture, QP 32, taskset -c %d" % (W, H, core0)}
+    return b
 
 
 def run_reference(args, rank, world):
@@ -272,11 +299,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--jobs", type=int, default=0, help="picture jobs per GPU per step (0 = pictures the kernel keeps in flight)")
-    ap.add_argument("--rounds", type=float, default=1.0, help="jobs per GPU per step as a multiple of the pictures in flight")
+    ap.add_argument("--frames", type=int, default=CLIP, help="frames of the clip per GPU (64 = configs[1]; anything else is a self-test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")
     args = ap.parse_args()

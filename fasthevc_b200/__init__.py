@@ -7,7 +7,7 @@ tests and bench: a ctypes mirror of that ABI.  There is no CPU path: importing w
 without a GPU, every compute call raises if the CUDA library or a device is missing.
 """
 from .api import (Encoder, FhcError, SliceParams, SeqParams, CTU_RESULT_DTYPE, build_library, library_path, load_library,
-                  pictures_in_flight, slice_params_from_qp)
+                  pictures_in_flight, slice_params_from_qp, measure_int_issue)
 
 __all__ = ["Encoder", "FhcError", "SliceParams", "SeqParams", "CTU_RESULT_DTYPE", "build_library", "library_path",
-           "load_library", "pictures_in_flight", "slice_params_from_qp"]
+           "load_library", "pictures_in_flight", "slice_params_from_qp", "measure_int_issue"]

@@ -39,7 +39,7 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
            "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight", "fhc_poll_picture",
-           "fhc_fetch_picture_async", "fhc_fetch_sync"]
+           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue"]
 
 
 def library_path():
@@ -86,6 +86,7 @@ def load_library():
     lib.fhc_poll_picture.argtypes = [C.c_void_p, C.c_int]
     lib.fhc_fetch_picture_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fhc_fetch_sync.argtypes = [C.c_void_p]
+    lib.fhc_measure_int_issue.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fhc_last_error.restype = C.c_char_p
     lib.fhc_launch_count.restype = C.c_uint64
     _lib = lib
@@ -98,6 +99,15 @@ def pictures_in_flight(device=0):
     if n <= 0:
         raise FhcError("fhc_pictures_in_flight(%d) -> %d: %s" % (device, n, (load_library().fhc_last_error() or b"").decode()))
     return n
+
+
+def measure_int_issue(device=0):
+    """(Gop/s, ms): measured int32 issue roof of the device (IMAD / IADD3 / LOP3 mix at full occupancy)."""
+    g, ms = C.c_double(), C.c_double()
+    rc = load_library().fhc_measure_int_issue(int(device), C.byref(g), C.byref(ms))
+    if rc != 0:
+        raise FhcError("fhc_measure_int_issue -> %d: %s" % (rc, (load_library().fhc_last_error() or b"").decode()))
+    return g.value, ms.value
 
 
 def slice_params_from_qp(qp):

@@ -76,6 +76,7 @@ struct Batch
   uint8_t* dDepthRows = nullptr;          // [maxFrames][2][width / 4]
   int32_t* hFlags = nullptr;              // [maxFrames] mapped pinned host memory: picture done
   int32_t* dFlags = nullptr;              // device alias of hFlags
+  long long* dProf = nullptr;             // [maxFrames][64] cycle counters (FHC_PROFILE builds)
   int32_t* hTrace = nullptr;              // [maxFrames] mapped pinned host memory: progress words (FHC_TRACE=1 in the environment)
   int32_t* dTrace = nullptr;
   int* dQueue = nullptr;
@@ -123,7 +124,7 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue); cudaFree(bt.dProf);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -189,6 +190,8 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     CKG(cudaMalloc(&bt.dLines, sizeof(int16_t) * 4 * (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dQueue, sizeof(int)), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dProf, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMemset(bt.dProf, 0, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
     CKG(cudaHostGetDevicePointer(&bt.dFlags, bt.hFlags, 0), fhc_destroy(c));
     if (getenv("FHC_TRACE"))
@@ -253,6 +256,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
     d.width = W; d.height = c->seq.height; d.bitDepth = c->seq.bitDepth; d.sampleBytes = sampleBytes;
     d.wc = (W + 63) / 64; d.hc = (c->seq.height + 63) / 64;
     d.doneFlag = bt->dFlags + i;
+    d.prof = bt->dProf + 64 * (size_t)i;
     bt->hFlags[i] = 0;
     if (bt->hTrace) { d.trace = bt->dTrace + 8 * i; memset(bt->hTrace + 8 * i, 0, 32); }
   }
@@ -456,5 +460,81 @@ extern "C" int fhc_debug_geometry(fhc_ctx* c, long long* out4)
 {
   if (!c || !out4) return FHC_ERR_ARG;
   out4[0] = c->maxBlocks; out4[1] = FHC_BLOCK_THREADS; out4[2] = (long long)c->smemBytes; out4[3] = (long long)c->wsPerBlock;
+  return FHC_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// integer-issue roof (the binding roofline of this path is int32 instruction issue, and
+// MEASURED_PEAKS.json has no such figure): a microbenchmark of independent IMAD / IADD3 / LOP3 chains, one third
+// each, at full occupancy.  Reported in thread-level integer operations per second.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fhc_int_issue_kernel(int* out, int iters, int seed)
+{
+  int a0 = threadIdx.x + seed, a1 = a0 * 3 + 1, a2 = a0 ^ 0x55, a3 = a0 + 7, b0 = a0 * 5, b1 = a1 * 7, b2 = a2 + 11, b3 = a3 ^ 0x33;
+  int c0 = a0 - 9, c1 = a1 + 13, c2 = a2 * 3, c3 = a3 - 5;
+  const int m = (blockIdx.x | 1) + seed;
+  for (int i = 0; i < iters; i++)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+    {
+      asm volatile("mad.lo.s32 %0, %0, %4, %1;\n\tmad.lo.s32 %1, %1, %4, %2;\n\tmad.lo.s32 %2, %2, %4, %3;\n\tmad.lo.s32 %3, %3, %4, %0;"
+                   : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3) : "r"(m));
+      asm volatile("{ .reg .s32 t;\n\tadd.s32 t, %0, %1;\n\tadd.s32 %0, t, %4;\n\tadd.s32 t, %1, %2;\n\tadd.s32 %1, t, %4;\n\t"
+                   "add.s32 t, %2, %3;\n\tadd.s32 %2, t, %4;\n\tadd.s32 t, %3, %0;\n\tadd.s32 %3, t, %4; }"
+                   : "+r"(b0), "+r"(b1), "+r"(b2), "+r"(b3) : "r"(m));
+      asm volatile("lop3.b32 %0, %0, %1, %4, 0x96;\n\tlop3.b32 %1, %1, %2, %4, 0xe8;\n\tlop3.b32 %2, %2, %3, %4, 0x96;\n\tlop3.b32 %3, %3, %0, %4, 0xe8;"
+                   : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(m));
+    }
+  }
+  const int v = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3 ^ c0 ^ c1 ^ c2 ^ c3;
+  if (v == 0x7fffffff) out[0] = v;
+}
+
+// *gops = measured integer operations per second / 1e9 (each IMAD, IADD3 and LOP3 counts as one operation per thread)
+extern "C" int fhc_measure_int_issue(int device, double* gops, double* ms_out)
+{
+  if (!gops) return FHC_ERR_ARG;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  int* dOut = nullptr;
+  CK(cudaMalloc(&dOut, sizeof(int)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best = 0, bestMs = 0;
+  for (int rep = 0; rep < 5; rep++)
+  {
+    CK(cudaEventRecord(e0, 0));
+    fhc_int_issue_kernel<<<blocks, threads>>>(dOut, iters, rep);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    // per thread and iteration: 8 x (4 IMAD + 4 IADD3 + 4 LOP3); a 3-input add.s32 pair fuses into one IADD3
+    const double ops = (double)blocks * threads * (double)iters * 8.0 * 12.0;
+    const double g = ops / (ms * 1e-3) / 1e9;
+    if (rep > 0 && g > best) { best = g; bestMs = ms; }
+    g_launches++;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dOut);
+  *gops = best;
+  if (ms_out) *ms_out = bestMs;
+  return FHC_OK;
+}
+
+// debug: cycle counters of picture `poc` (FHC_PROFILE builds; zeros otherwise): out64[role * 8 + stage], out64[40] = picture total
+extern "C" int fhc_debug_profile(fhc_ctx* c, int poc, long long* out64)
+{
+  if (!c || !out64) return FHC_ERR_ARG;
+  int slot = 0;
+  Batch* bt = find_batch(c, poc, &slot);
+  if (!bt) return FHC_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(bt->evStop));
+  CK(cudaMemcpy(out64, bt->dProf + 64 * (size_t)slot, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   return FHC_OK;
 }

@@ -125,7 +125,7 @@ struct PicDesc                    // global memory, one per submitted picture (f
   int32_t width, height, bitDepth, sampleBytes, wc, hc;
   int32_t* doneFlag;              // set to 1 (system scope) when the picture is finished
   int32_t* trace;                 // optional progress word (host-mapped): ctu << 12 | region z << 4 | stage; 0 = off
-  long long prof[16];             // clock64 counters (FHC_PROFILE builds)
+  long long* prof;                // [64] clock64 counters of the picture's block (FHC_PROFILE builds): [role][stage]
 };
 
 struct PicParams                  // hot copy of the picture header (shared memory)
@@ -137,7 +137,19 @@ struct PicParams                  // hot copy of the picture header (shared memo
   fhc_slice_params sp;
   int32_t width, height, bitDepth, sampleBytes, wc, hc;
   int32_t* trace;
+  long long* prof;
 };
+// cycle counters per role (FHC_PROFILE builds; lane 0 of the role's warp): stage indices
+enum { PF_RMD = 0, PF_LUMA1, PF_LUMA2, PF_CHROMA, PF_SYNTAX, PF_JOB, PF_WAIT, PF_JOBS, PF_NUM = 8 };
+#if defined(FHC_DEVICE_BUILD) && defined(FHC_PROFILE)
+#define FHC_TIC(v) const long long v = clock64()
+#define FHC_TOC(r, stage, v) do { if (FHC_LANE == 0) (r)->prof[stage] += clock64() - (v); } while (0)
+#define FHC_CNT(r, stage) do { if (FHC_LANE == 0) (r)->prof[stage]++; } while (0)
+#else
+#define FHC_TIC(v) do { } while (0)
+#define FHC_TOC(r, stage, v) do { } while (0)
+#define FHC_CNT(r, stage) do { } while (0)
+#endif
 FHC_DH void trace_at(const PicParams& pp, int ctu, int z, int stage)
 {
   if (pp.trace && FHC_LANE == 0) *(volatile int32_t*)pp.trace = (ctu << 12) | (z << 4) | stage;
@@ -188,6 +200,7 @@ struct Role
   double rmdCost[36];
   int cand[FHC_MAX_CAND + 2]; int numCand;
   int mpm[3]; int dcVal;
+  long long prof[PF_NUM];
 };
 
 // chain totals of a decided region
@@ -1047,14 +1060,17 @@ struct GScr                       // a group's scratch (see Role)
   uint8_t* meta;                  // chroma cbf[2][np], ts[2][np]
   int16_t *refU, *refF;
 };
-FHC_DH GScr group_scratch(const Role* r, int idx)
+// planeStride: elements between the candidate planes of consecutive groups (the role's yuvSize, or 16 for the 4x4
+// luma candidates of the NxN role, which only ever hold one 4x4 block)
+FHC_DH GScr group_scratch(const Role* r, int idx, int planeStride)
 {
   GScr s;
   s.go = r->go + idx;
   s.A = r->tuA + idx * r->tuCap; s.B = r->tuB + idx * r->tuCap; s.resi = r->tuResi + idx * r->tuCap;
   s.cgCost = r->cgCost + idx * (r->tuCap >> 4); s.nz = r->nzMask + idx * (r->yuvSize >> 4); s.acc = r->gAcc + idx * 4;
-  s.rec = r->gRec + idx * r->yuvSize; s.coef = r->gCoef + idx * r->yuvSize;
-  s.meta = r->gMeta + idx * 4 * r->np;
+  s.rec = r->gRec + idx * planeStride; s.coef = r->gCoef + idx * planeStride;
+  s.meta = r->gMeta + (idx < 5 ? idx : 0) * 4 * r->np;
+  if (idx >= 5) idx = 0;                           // only the (at most five) chroma / 64x64 groups build reference lines of their own
   s.refU = r->gRefU + idx * r->refCap; s.refF = r->gRefF + idx * r->refCap;
   return s;
 }
@@ -1726,7 +1742,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
 {
   const Tables& t = b->t;
   const Grp w = whole_warp();
-  GScr s = group_scratch(r, 0);
+  GScr s = group_scratch(r, 0, r->yuvSize);
   const int L = r->log2cu, minTu = min_tu_log2(L, 0), LB = L - 1, nB = 1 << LB, LC = LB - 1, nC = 1 << LC;
   const int splitB = LB > minTu, partsB = r->np >> 2, partsC = partsB >> 2, cuw = r->cuw;
   Hyp h = hyp_of(r, r->cTridx, r->cCbf, r->cCbf, r->cCbf, r->cTs, r->cTs, r->cTs, r->curCoef, s.nz);
@@ -1839,14 +1855,17 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   }
   const int ri = (int)(r - b->role);
   trace_role(b->pp, ri, 16 + pu * 8 + 1);
+  FHC_TIC(tRmd);
   rmd_satd(b, r, log2pu, px, py);
   trace_role(b->pp, ri, 16 + pu * 8 + 2);
   rmd_candidates(b, r, pu, log2pu);
   trace_role(b->pp, ri, 16 + pu * 8 + 3);
+  FHC_TOC(r, PF_RMD, tRmd);
+  FHC_TIC(tL1);
   const int numCand = r->numCand, tasks = numCand * (log2pu == 2 ? 2 : 1);
   for_groups(tasks, [&](const Grp& g)
   {
-    const GScr s = group_scratch(r, g.idx);
+    const GScr s = group_scratch(r, g.idx, isNxN ? 16 : r->yuvSize);
     const int ci = (log2pu == 2) ? (g.idx >> 1) : g.idx, ts = (log2pu == 2) ? (g.idx & 1) : 0;
     const int mode = r->cand[ci];
     sb_copy_g(g, s.go, &b->curr[depth]);
@@ -1857,11 +1876,13 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
       a.comp = 0; a.log2n = log2pu; a.mode = mode; a.scanType = scan_idx_for(mode, log2pu, 0); a.ts = ts;
       a.cbfCtx = CTX_CBF + (isNxN ? 0 : 1);
       a.srcOff = py * 64 + px; a.srcStride = 64;
-      a.rec = s.rec + inY * cuw + inX; a.recStride = cuw; a.coef = s.coef + 16 * p0;
+      uint16_t* nzTu = isNxN ? s.nz : s.nz + p0;
+      if (isNxN) { a.rec = s.rec; a.recStride = 4; a.coef = s.coef; }                  // compact 4x4 candidate block
+      else { a.rec = s.rec + inY * cuw + inX; a.recStride = cuw; a.coef = s.coef + 16 * p0; }
       a.refU = r->refU; a.refF = r->refF; a.dcVal = r->dcVal;
       int cbf;
       const uint32_t dist = tu_eval(b, g, s, a, &cbf);
-      nz_masks_tu(g, t, a.coef, log2pu, a.scanType, s.nz + p0);
+      nz_masks_tu(g, t, a.coef, log2pu, a.scanType, nzTu);
       gsync(g);
       if (g.gl == 0)
       {
@@ -1874,7 +1895,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
           code_luma_dir1(e, mode, r->mpm);
           if (!isNxN) enc_bin(e, CTX_SUBDIV + (5 - log2pu), 0);        // split_transform_flag of the PU-sized TU (always coded for 8..32)
           enc_bin(e, a.cbfCtx, cbf);
-          if (cbf) code_coeff_serial(e, a.coef, log2pu, 0, a.scanType, ts, s.nz + p0);
+          if (cbf) code_coeff_serial(e, a.coef, log2pu, 0, a.scanType, ts, nzTu);
           cost = rd_cost(b, num_bits(e), dist);
         }
         r->gCost[g.idx] = cost; r->gDist[g.idx] = dist; r->gCbf[g.idx] = (uint32_t)cbf | ((uint32_t)ts << 8);
@@ -1925,6 +1946,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
     }
   });
   trace_role(b->pp, ri, 16 + pu * 8 + 4);
+  FHC_TOC(r, PF_LUMA1, tL1);
   // winner: lowest cost, ties to the lowest task index = HM's sequential scan with strict <
   int best = 0;
   FHC_NOUNROLL for (int i = 1; i < tasks; i++) if (r->gCost[i] < r->gCost[best]) best = i;
@@ -1934,12 +1956,12 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   const int bestMode = r->cand[(log2pu == 2) ? (best >> 1) : best];
   {
     // xSetIntraResultLumaQT (TEncSearch.cpp:1716) + the TU flags of the PU
-    const GScr s = group_scratch(r, best);
+    const GScr s = group_scratch(r, best, isNxN ? 16 : r->yuvSize);
     FHC_LANES(k, n * n)
     {
       const int o = (inY + (k >> log2pu)) * cuw + inX + (k & (n - 1));
-      r->bestRec[o] = s.rec[o];
-      r->bestCoef[16 * p0 + k] = s.coef[16 * p0 + k];
+      r->bestRec[o] = isNxN ? s.rec[k] : s.rec[o];
+      r->bestCoef[16 * p0 + k] = isNxN ? s.coef[k] : s.coef[16 * p0 + k];
     }
     FHC_LANES(k, puParts)
     {
@@ -1952,6 +1974,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
     }
     warp_sync();
   }
+  FHC_TIC(tL2);
   if (log2pu >= 3)
   {
     if (second_pass(b, r, bestMode, &bestCost, &bestDist))
@@ -1972,6 +1995,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   }
   if (w.gl == 0) { r->ldir[pu] = (uint8_t)bestMode; r->dist += bestDist; }
   warp_sync();
+  FHC_TOC(r, PF_LUMA2, tL2);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1986,7 +2010,7 @@ FHC_D void search_chroma(Blk* b, Role* r)
   allowed_chroma(r->ldir[0], modeList);
   for_groups(5, [&](const Grp& g)
   {
-    const GScr s = group_scratch(r, g.idx);
+    const GScr s = group_scratch(r, g.idx, r->yuvSize);
     const int cdir = modeList[g.idx], predMode = cdir == DM_CHROMA_IDX ? r->ldir[0] : cdir;
     uint8_t* cbfC[2] = { s.meta, s.meta + np };
     uint8_t* tsC[2] = { s.meta + 2 * np, s.meta + 3 * np };
@@ -2107,7 +2131,7 @@ FHC_D void search_chroma(Blk* b, Role* r)
   int best = 0;
   FHC_NOUNROLL for (int i = 1; i < 5; i++) if (r->gCost[i] < r->gCost[best]) best = i;
   {
-    const GScr s = group_scratch(r, best);
+    const GScr s = group_scratch(r, best, r->yuvSize);
     const int c0 = yuv_off(cuw, 1), cnt = (cuw * cuw) >> 1;
     FHC_LANES(k, cnt) { r->bestRec[c0 + k] = s.rec[c0 + k]; r->bestCoef[c0 + k] = s.coef[c0 + k]; }
     FHC_LANES(k, np)
@@ -2132,6 +2156,8 @@ FHC_D void run_job(Blk* b, Role* r)
   warp_sync();
   const int ri = (int)(r - b->role);
   trace_role(b->pp, ri, 1);
+  FHC_TIC(tJob);
+  FHC_CNT(r, PF_JOBS);
   for (int pu = 0; pu < (isNxN ? 4 : 1); pu++) { search_luma_pu(b, r, pu); trace_role(b->pp, ri, 2 + pu); }
   if (isNxN)
   {
@@ -2142,10 +2168,13 @@ FHC_D void run_job(Blk* b, Role* r)
     if (any) FHC_LANES(k, np) r->cbf[0][k] |= 1;
     warp_sync();
   }
+  FHC_TIC(tCh);
   search_chroma(b, r);
+  FHC_TOC(r, PF_CHROMA, tCh);
+  FHC_TIC(tSy);
   trace_role(b->pp, ri, 6);
   // bits of the whole CU in real syntax order on the CI_CURR_BEST contexts (TEncCu.cpp:1564-1588)
-  GScr s = group_scratch(r, 0);
+  GScr s = group_scratch(r, 0, r->yuvSize);
   Hyp h = hyp_of(r, r->tridx, r->cbf[0], r->cbf[1], r->cbf[2], r->ts[0], r->ts[1], r->ts[2], r->bestCoef, s.nz);
   nz_masks_range(t, w, h, 0, np, 1, 1);
   sb_copy_g(w, &r->endCtx, &b->curr[r->depth]);
@@ -2159,6 +2188,8 @@ FHC_D void run_job(Blk* b, Role* r)
     r->cost = rd_cost(b, r->bits, r->dist);
   }
   warp_sync();
+  FHC_TOC(r, PF_SYNTAX, tSy);
+  FHC_TOC(r, PF_JOB, tJob);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -2183,7 +2214,9 @@ FHC_DH void start_job(Blk* b, int ri, int z, int partSize)
 FHC_DH void join_job(Blk* b, int ri)
 {
 #ifdef FHC_DEVICE_BUILD
+  FHC_TIC(tW);
   bar_sync(bar_done(ri));
+  FHC_TOC(&b->role[ri], PF_WAIT, tW);
 #else
   run_job(b, &b->role[ri]);       // host build: the job runs at the join, i.e. after its sub-tree
 #endif
@@ -2381,7 +2414,9 @@ FHC_D void master_ctu(Blk* b)
     bar_arrive(bar_start(ri));
   }
 #endif
+  FHC_TIC(tEnc);
   encode_ctu(b);
+  FHC_TOC(&b->role[ROLE_3A], PF_WAIT, tEnc);            // role 0 never waits for itself: its slot holds the final CTU coding
 }
 
 #ifdef FHC_DEVICE_BUILD
@@ -2443,11 +2478,16 @@ FHC_HD void role_carve(Role* r, int ri, Arena* sm, Arena* gm)
   r->tuResi = (int16_t*)arena_take(big, 2 * cap * G);
   r->cgCost = (double*)arena_take(big, 8 * (cap >> 4) * G);
   r->nzMask = (uint16_t*)arena_take(big, 2 * (yuv >> 4) * G);
-  r->gRec = (int16_t*)arena_take(big, 2 * yuv * G);
-  r->gCoef = (int16_t*)arena_take(big, 2 * yuv * G);
-  r->gMeta = (uint8_t*)arena_take(big, 4 * np * G);
-  r->gRefU = (int16_t*)arena_take(big, 2 * r->refCap * G);
-  r->gRefF = (int16_t*)arena_take(big, 2 * r->refCap * G);
+  {
+    // candidate planes: full CU planes per group, except the NxN role's twenty 4x4 luma candidates (one 4x4 block each);
+    // its five chroma candidates use the same memory with full planes
+    const int planes = ri == ROLE_3B ? (5 * yuv > 16 * G ? 5 * yuv : 16 * G) : yuv * G;
+    r->gRec = (int16_t*)arena_take(big, 2 * planes);
+    r->gCoef = (int16_t*)arena_take(big, 2 * planes);
+  }
+  r->gMeta = (uint8_t*)arena_take(big, 4 * np * 5);
+  r->gRefU = (int16_t*)arena_take(big, 2 * r->refCap * 5);
+  r->gRefF = (int16_t*)arena_take(big, 2 * r->refCap * 5);
   r->curRec = (int16_t*)arena_take(big, 2 * yuv);
   r->curCoef = (int16_t*)arena_take(big, 2 * yuv);
   r->bestRec = (int16_t*)arena_take(big, 2 * yuv);
@@ -2575,10 +2615,14 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
     pp.depthRow[0] = pd->depthRow[0]; pp.depthRow[1] = pd->depthRow[1];
     pp.out = pd->out; pp.sp = pd->sp;
     pp.width = pd->width; pp.height = pd->height; pp.bitDepth = pd->bitDepth; pp.sampleBytes = pd->sampleBytes; pp.wc = pd->wc; pp.hc = pd->hc;
-    pp.trace = pd->trace;
+    pp.trace = pd->trace; pp.prof = pd->prof;
+    for (int ri = 0; ri < FHC_ROLES; ri++) for (int k = 0; k < PF_NUM; k++) b->role[ri].prof[k] = 0;
   }
 #ifdef FHC_DEVICE_BUILD
   __syncthreads();
+#ifdef FHC_PROFILE
+  const long long tPic = clock64();
+#endif
   if (tid < 32) sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);       // slice start: resetEntropy (TEncSlice.cpp:719-720)
   const int numCtus = b->pp.wc * b->pp.hc;
   for (int addr = 0; addr < numCtus; addr++)
@@ -2591,6 +2635,13 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
     shift_left_neighbour(b, tid, nthr);
     __syncthreads();
   }
+#ifdef FHC_PROFILE
+  if (tid == 0 && b->pp.prof)
+  {
+    for (int ri = 0; ri < FHC_ROLES; ri++) for (int k = 0; k < PF_NUM; k++) b->pp.prof[ri * PF_NUM + k] = b->role[ri].prof[k];
+    b->pp.prof[5 * PF_NUM] = clock64() - tPic;
+  }
+#endif
 #else
   sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);
   const int numCtus = b->pp.wc * b->pp.hc;

@@ -126,6 +126,9 @@ int fhc_host_free(void* p);
 const char* fhc_last_error(void);
 /* Number of kernels launched by this library so far (bench `gpu_launches`). */
 uint64_t fhc_launch_count(void);
+/* Measured int32 issue roof of `device`: independent IMAD / IADD3 / LOP3 chains, one third each, at full
+ * occupancy; *gops = thread-level integer operations per second / 1e9, *ms = duration of the timed launch (may be NULL). */
+int fhc_measure_int_issue(int device, double* gops, double* ms);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,23 @@ def oracle_compress(params, y, u, v):
     return out
 
 
+def _oracle_job(job):
+    (w, h, bd, qp), y, u, v = job
+    return oracle_compress(params_from_qp(w, h, bd, qp), y, u, v)
+
+
+def oracle_compress_parallel(jobs):
+    """jobs: list of ((width, height, bitDepth, qp), y, u, v); one oracle process per picture (a 1080p picture takes
+    ~20 s of one host core).  Returns the CTU_OUT_DT arrays in order."""
+    import multiprocessing as mp
+    build_oracle()
+    n = min(len(jobs), max(1, len(os.sched_getaffinity(0))))
+    if n <= 1:
+        return [_oracle_job(j) for j in jobs]
+    with mp.get_context("fork").Pool(n) as pool:
+        return pool.map(_oracle_job, jobs)
+
+
 def parse_dump(path):
     """Returns list of (slice_rec, ctu_recs) per picture."""
     raw = open(path, "rb").read()
