@@ -82,6 +82,15 @@ FHC_DH double dsub(double a, double b) { return a - b; }
 FHC_DH void warp_sync() { }
 #endif
 #define FHC_LANES(i, n) for (int i = FHC_LANE; i < (n); i += FHC_NL)
+// hides a compile-time constant from the optimiser: keeps ONE copy of the large shared functions instead of a clone per
+// constant argument pattern (the kernel is bound by instruction delivery, profiles/)
+FHC_DH int opq(int v)
+{
+#ifdef FHC_DEVICE_BUILD
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
 
 // A lane group: G consecutive lanes of a warp that evaluate one candidate together (host: one virtual lane).
 struct Grp { int gl, G, idx; unsigned mask; };
@@ -243,19 +252,24 @@ FHC_DH int bar_done(int role) { return 1 + FHC_ROLES + role; }
 // ----------------------------------------------------------------------------------------------
 // CABAC bit counter (TEncBinCoderCABACCounter.cpp:57-140)
 // ----------------------------------------------------------------------------------------------
-struct Coder { Sbac* sb; const Tables* t; uint32_t bins; };
+// The bit counter of a serial coding section: the fractional-bit accumulator lives in a register while the section
+// runs (coder_open .. coder_close); context states are stepped in place.  Functions that are real calls take the
+// caller's Coder by reference and work on a local copy, so that the accumulator stays in registers inside them too.
+struct Coder { Sbac* sb; const Tables* t; uint32_t bins; uint64_t frac; };
+FHC_DH Coder coder_open(Sbac* s, const Tables* tab) { Coder e; e.sb = s; e.t = tab; e.bins = 0; e.frac = s->frac; return e; }
+FHC_DH void coder_close(const Coder& e) { e.sb->frac = e.frac; }
 FHC_DH void enc_bin(Coder& e, int ctx, int bin)
 {
-  const uint8_t st = e.sb->c[ctx];
+  const uint32_t tr = e.t->cabac[e.sb->c[ctx] * 2 + bin];            // fractional bits | next state << 24
   e.bins++;
   FHC_COUNT(g_emuCounters.bins++);
-  e.sb->frac += (uint64_t)e.t->entropyBits[st ^ bin];
-  e.sb->c[ctx] = e.t->nextState[st][bin];
+  e.frac += (uint64_t)(tr & 0xffffffu);
+  e.sb->c[ctx] = (uint8_t)(tr >> 24);
 }
-FHC_DH void enc_ep(Coder& e, int n) { e.bins += (uint32_t)n; FHC_COUNT(g_emuCounters.bins += (unsigned)n); e.sb->frac += (uint64_t)32768 * (uint64_t)n; }
-FHC_DH void enc_trm(Coder& e, int bin) { e.bins++; FHC_COUNT(g_emuCounters.bins++); e.sb->frac += (uint64_t)e.t->entropyBits[126 ^ bin]; }
-FHC_DH void reset_bits(Coder& e) { e.sb->frac &= 32767; e.bins = 0; }                // TEncBinCoderCABAC.cpp:161-174
-FHC_DH uint32_t num_bits(const Coder& e) { return (uint32_t)(e.sb->frac >> 15); }
+FHC_DH void enc_ep(Coder& e, int n) { e.bins += (uint32_t)n; FHC_COUNT(g_emuCounters.bins += (unsigned)n); e.frac += (uint64_t)32768 * (uint64_t)n; }
+FHC_DH void enc_trm(Coder& e, int bin) { e.bins++; FHC_COUNT(g_emuCounters.bins++); e.frac += (uint64_t)e.t->entropyBits[126 ^ bin]; }
+FHC_DH void reset_bits(Coder& e) { e.frac &= 32767; e.bins = 0; }                    // TEncBinCoderCABAC.cpp:161-174
+FHC_DH uint32_t num_bits(const Coder& e) { return (uint32_t)(e.frac >> 15); }
 FHC_DH int ctx_bits(const Tables& t, const Sbac* sb, int ctx, int bin) { return t.entropyBits[sb->c[ctx] ^ bin]; }
 // context-set copies: by one lane, or striped over a group
 FHC_DH void sb_copy1(Sbac* d, const Sbac* s)
@@ -502,6 +516,12 @@ FHC_DH int pred_sample(const Tables& t, const int16_t* line, int n, int log2n, i
   }
 }
 
+// the one shared copy of the predictor (keeps the instruction footprint small: the kernel is bound by instruction delivery)
+FHC_D int pred_sample_call(const Tables& t, const int16_t* line, int n, int log2n, int mode, int x, int y, int isLuma, int bd, int dcval)
+{
+  return pred_sample(t, line, n, log2n, mode, x, y, isLuma, bd, dcval);
+}
+
 // ----------------------------------------------------------------------------------------------
 // quantisation parameters (TComTrQuant.cpp:71-119)
 // ----------------------------------------------------------------------------------------------
@@ -600,8 +620,9 @@ FHC_DH void code_remain(Coder& e, uint32_t symbol, uint32_t rParam)             
   }
 }
 // serial part; nzMask[] must describe coef (nz_masks_tu / nz_masks_range + group sync before the call)
-FHC_D void code_coeff_serial(Coder& e, const int16_t* coef, int log2n, int isChroma, int scanType, int tsFlag, const uint16_t* nzMask)
+FHC_D void code_coeff_serial(Coder& eio, const int16_t* coef, int log2n, int isChroma, int scanType, int tsFlag, const uint16_t* nzMask)
 {
+  Coder e = eio;                                                      // registers inside this call
   const Tables& t = *e.t;
   const int n = 1 << log2n, log2wg = log2n - 2, wg = n >> 2;
   const uint16_t* scan = scan_tab(t, scanType, log2n);
@@ -705,6 +726,7 @@ FHC_D void code_coeff_serial(Coder& e, const int16_t* coef, int log2n, int isChr
       }
     }
   }
+  eio = e;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -756,6 +778,161 @@ FHC_DH int pk_c1lt8(int pk) { return (pk >> 11) & 1; }
 FHC_DH int pk_c2lt1(int pk) { return (pk >> 12) & 1; }
 FHC_DH int pk_sig(int pk) { return (pk >> 13) & 63; }
 FHC_DH int pk_nosig(int pk) { return (pk >> 19) & 1; }
+
+struct RdoqState { double blockUncoded, baseCost; int cgLastScanPos, lastScanPos; uint64_t cgFlags; };
+FHC_D int ic_rate_call(const Tables& t, const Sbac* go, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, int c1Lt8, int c2Lt1)
+{
+  return ic_rate(t, go, absLevel, ctxOne, ctxAbs, goRice, c1Lt8, c2Lt1);
+}
+
+// best last position (TComTrQuant.cpp:2465-2524): walks down from the last candidate until a level above 1 is met.  The
+// per-coefficient costs of the main pass are re-evaluated from the packed coder state (same operations, same order).
+FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, const int16_t* coef,
+                        const double* costCGSig, const RdoqState& st)
+{
+  const Tables& t = b->t;
+  const int log2n = q.log2n, isChroma = q.isChroma, n = 1 << log2n, qBits = q.qBits;
+  const double errScale = q.errScale, lambda = q.lambda;
+  const uint16_t* scan = scan_tab(t, q.scanType, log2n);
+  const uint8_t* scanCG = scan_cg(t, q.scanType, log2n);
+  const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
+  const int cgLastScanPos = st.cgLastScanPos, lastScanPos = st.lastScanPos;
+  const uint64_t cgFlags = st.cgFlags;
+  const double blockUncoded = st.blockUncoded;
+  double baseCost = st.baseCost;
+  int bestLastIdxP1 = 0;
+    double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(t, go, q.cbfCtx, 0)));
+    baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(t, go, q.cbfCtx, 1)));
+    int foundLast = 0, off, shift;
+    last_ctx_params(isChroma, log2n, &off, &shift);
+    const int bx0 = CTX_LASTX + (isChroma ? 15 : 0) + off, by0 = CTX_LASTY + (isChroma ? 15 : 0) + off, gmax = group_idx(n - 1);
+    FHC_NOUNROLL for (int cgScanPos = cgLastScanPos; cgScanPos >= 0 && !foundLast; cgScanPos--)
+    {
+      const int cgBlk = scanCG[cgScanPos];
+      baseCost = dsub(baseCost, costCGSig[cgScanPos]);
+      if (!((cgFlags >> cgBlk) & 1)) continue;
+      FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
+      {
+        const int scanPos = cgScanPos * 16 + posInCG;
+        if (scanPos > lastScanPos) continue;
+        const int blkPos = scan[scanPos];
+        const int level = coef[blkPos], pk = B[scanPos];
+        if (level)
+        {
+          const double costSigP = pk_nosig(pk) ? 0.0 : dmul(lambda, (double)ctx_bits(t, go, sigBase + pk_sig(pk), 1));
+          const int posY = blkPos >> log2n, posX = blkPos - (posY << log2n);
+          const int lx = q.scanType == SCAN_VER ? posY : posX, ly = q.scanType == SCAN_VER ? posX : posY;
+          const int gx = group_idx(lx), gy = group_idx(ly);
+          int bx = 0, by = 0, cc;
+          FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ctx_bits(t, go, bx0 + (cc >> shift), 1);
+          if (gx < gmax) bx += ctx_bits(t, go, bx0 + (gx >> shift), 0);
+          FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ctx_bits(t, go, by0 + (cc >> shift), 1);
+          if (gy < gmax) by += ctx_bits(t, go, by0 + (gy >> shift), 0);
+          double cost = (double)(bx + by);
+          if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
+          if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
+          const double costLast = dmul(lambda, cost);
+          const double totalCost = dsub(dadd(baseCost, costLast), costSigP);
+          if (totalCost < bestCost) { bestLastIdxP1 = scanPos + 1; bestCost = totalCost; }
+          if (level > 1) { foundLast = 1; break; }
+          // level == 1: costCoeff of this position as the main pass computed it, and its uncoded cost
+          const int ld = iabs(A[scanPos]);
+          const double err = (double)(ld - (int)(1u << qBits)), err0 = (double)ld;
+          double cur = dadd(dmul(dmul(err, err), errScale),
+                            dmul(lambda, (double)ic_rate_call(t, go, 1u, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk))));
+          cur = dadd(cur, costSigP);
+          baseCost = dsub(baseCost, cur);
+          baseCost = dadd(baseCost, dmul(dmul(err0, err0), errScale));
+        }
+        else baseCost = dsub(baseCost, dmul(lambda, (double)ctx_bits(t, go, sigBase + pk_sig(pk), 0)));
+      }
+    }
+  return bestLastIdxP1;
+}
+
+// sign bit hiding (TComTrQuant.cpp:2530-2660); rate increments of level +-1 are re-evaluated from the packed coder state
+FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, int16_t* coef, int numCodedCG)
+{
+  const Tables& t = b->t;
+  const int log2n = q.log2n, isChroma = q.isChroma, qBits = q.qBits;
+  const double lambda = q.lambda;
+  const uint16_t* scan = scan_tab(t, q.scanType, log2n);
+  const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
+    const double invQ = (double)inv_quant_scale(q.rem);
+#ifdef FHC_DEVICE_BUILD
+    const double f = __dadd_rn(__ddiv_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(__dmul_rn(invQ, invQ), (double)(1 << (2 * q.per))), lambda), 16.0),
+                                         (double)(1 << (2 * (q.bd - 8)))), 0.5);
+#else
+    const double f = invQ * invQ * (double)(1 << (2 * q.per)) / lambda / 16 / (double)(1 << (2 * (q.bd - 8))) + 0.5;
+#endif
+    const int64_t rdFactor = (int64_t)f;
+    int lastCG = -1;
+    FHC_NOUNROLL for (int subSet = numCodedCG - 1; subSet >= 0; subSet--)
+    {
+      const int subPos = subSet << 4;
+      uint32_t mask = 0;
+      int sum = 0;
+      FHC_NOUNROLL for (int i = 0; i < 16; i++)
+      {
+        const int lv = coef[scan[subPos + i]];
+        if (lv) { mask |= 1u << i; sum += lv; }
+      }
+      if (!mask) continue;
+      const int lastNZ = msb_index(mask), firstNZ = lsb_index(mask);
+      if (lastCG == -1) lastCG = 1;
+      if (lastNZ - firstNZ >= 4)
+      {
+        const uint32_t signbit = A[subPos + firstNZ] >= 0 ? 0u : 1u;             // sign of the first non-zero level = sign of its coefficient
+        if (signbit != (uint32_t)(sum & 1))
+        {
+          int64_t minCostInc = INT64_MAX, curCost = INT64_MAX;
+          int minPos = -1, finalChange = 0, curChange = 0;
+          FHC_NOUNROLL for (int nn = (lastCG == 1 ? lastNZ : 15); nn >= 0; --nn)
+          {
+            const int scanPos = nn + subPos, blkPos = scan[scanPos];
+            const int lv = coef[blkPos], pk = B[scanPos], a = A[scanPos], ld = iabs(a);
+            const int deltaU = (ld - (int)((uint32_t)lv << qBits)) >> (qBits - 8);
+            const int sigD = pk_nosig(pk) ? 0 : ctx_bits(t, go, sigBase + pk_sig(pk), 1) - ctx_bits(t, go, sigBase + pk_sig(pk), 0);
+            if (lv != 0)
+            {
+              const int rateNow = ic_rate_call(t, go, (uint32_t)lv, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk));
+              const int incUp = ic_rate_call(t, go, (uint32_t)lv + 1, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk)) - rateNow;
+              const int incDown = ic_rate_call(t, go, (uint32_t)lv - 1, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk)) - rateNow;
+              const int64_t costUp = rdFactor * (-deltaU) + incUp;
+              int64_t costDown = rdFactor * (deltaU) + incDown - ((lv == 1) ? sigD : 0);
+              if (lastCG == 1 && lastNZ == nn && lv == 1) costDown -= (4 << 15);
+              if (costUp < costDown) { curCost = costUp; curChange = 1; }
+              else
+              {
+                curChange = -1;
+                if (nn == firstNZ && lv == 1) curCost = INT64_MAX;
+                else curCost = costDown;
+              }
+            }
+            else
+            {
+              curCost = rdFactor * (-(iabs(deltaU))) + (1 << 15) + ctx_bits(t, go, pk_one(pk), 0) + sigD;
+              curChange = 1;
+              if (nn < firstNZ)
+              {
+                const uint32_t thisSign = a >= 0 ? 0u : 1u;
+                if (thisSign != signbit) curCost = INT64_MAX;
+              }
+            }
+            if (curCost < minCostInc) { minCostInc = curCost; finalChange = curChange; minPos = scanPos; }
+          }
+          {
+            const int blkPos = scan[minPos];
+            int lv = coef[blkPos];
+            if (lv == 32767 && A[minPos] >= 0) finalChange = -1;       // HM tests the signed level against 32767 / -32768
+            lv += finalChange;
+            coef[blkPos] = (int16_t)lv;
+          }
+        }
+      }
+      if (lastCG == 1) lastCG = 0;
+    }
+}
 
 FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, int32_t* B, int16_t* coef, double* costCGSig,
                            uint32_t cgNZ0, uint32_t cgNZ1)
@@ -906,138 +1083,16 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
   if (lastScanPos < 0) return 0;
 
   // best last position (TComTrQuant.cpp:2465-2524)
-  int bestLastIdxP1 = 0;
-  {
-    double bestCost = dadd(blockUncoded, dmul(lambda, (double)ctx_bits(t, go, q.cbfCtx, 0)));
-    baseCost = dadd(baseCost, dmul(lambda, (double)ctx_bits(t, go, q.cbfCtx, 1)));
-    int foundLast = 0, off, shift;
-    last_ctx_params(isChroma, log2n, &off, &shift);
-    const int bx0 = CTX_LASTX + (isChroma ? 15 : 0) + off, by0 = CTX_LASTY + (isChroma ? 15 : 0) + off, gmax = group_idx(n - 1);
-    FHC_NOUNROLL for (int cgScanPos = cgLastScanPos; cgScanPos >= 0 && !foundLast; cgScanPos--)
-    {
-      const int cgBlk = scanCG[cgScanPos];
-      baseCost = dsub(baseCost, costCGSig[cgScanPos]);
-      if (!((cgFlags >> cgBlk) & 1)) continue;
-      FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
-      {
-        const int scanPos = cgScanPos * 16 + posInCG;
-        if (scanPos > lastScanPos) continue;
-        const int blkPos = scan[scanPos];
-        const int level = coef[blkPos], pk = B[scanPos];
-        if (level)
-        {
-          const double costSigP = pk_nosig(pk) ? 0.0 : dmul(lambda, (double)ctx_bits(t, go, sigBase + pk_sig(pk), 1));
-          const int posY = blkPos >> log2n, posX = blkPos - (posY << log2n);
-          const int lx = q.scanType == SCAN_VER ? posY : posX, ly = q.scanType == SCAN_VER ? posX : posY;
-          const int gx = group_idx(lx), gy = group_idx(ly);
-          int bx = 0, by = 0, cc;
-          FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ctx_bits(t, go, bx0 + (cc >> shift), 1);
-          if (gx < gmax) bx += ctx_bits(t, go, bx0 + (gx >> shift), 0);
-          FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ctx_bits(t, go, by0 + (cc >> shift), 1);
-          if (gy < gmax) by += ctx_bits(t, go, by0 + (gy >> shift), 0);
-          double cost = (double)(bx + by);
-          if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
-          if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
-          const double costLast = dmul(lambda, cost);
-          const double totalCost = dsub(dadd(baseCost, costLast), costSigP);
-          if (totalCost < bestCost) { bestLastIdxP1 = scanPos + 1; bestCost = totalCost; }
-          if (level > 1) { foundLast = 1; break; }
-          // level == 1: costCoeff of this position as the main pass computed it, and its uncoded cost
-          const int ld = iabs(A[scanPos]);
-          const double err = (double)(ld - (int)(1u << qBits)), err0 = (double)ld;
-          double cur = dadd(dmul(dmul(err, err), errScale),
-                            dmul(lambda, (double)ic_rate(t, go, 1u, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk))));
-          cur = dadd(cur, costSigP);
-          baseCost = dsub(baseCost, cur);
-          baseCost = dadd(baseCost, dmul(dmul(err0, err0), errScale));
-        }
-        else baseCost = dsub(baseCost, dmul(lambda, (double)ctx_bits(t, go, sigBase + pk_sig(pk), 0)));
-      }
-    }
-  }
+  RdoqState st;
+  st.blockUncoded = blockUncoded; st.baseCost = baseCost; st.cgLastScanPos = cgLastScanPos; st.lastScanPos = lastScanPos; st.cgFlags = cgFlags;
+  const int bestLastIdxP1 = rdoq_last_pos(b, go, q, A, B, coef, costCGSig, st);
   // signs; per coefficient group of the coded range the non-zero map and the parity of the level sum
   uint32_t absSum = 0;
   const int numCodedCG = (bestLastIdxP1 + 15) >> 4;
   FHC_NOUNROLL for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) coef[scan[scanPos]] = 0;
   FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++) absSum += (uint32_t)coef[scan[scanPos]];
 
-  if (absSum >= 2)                                                             // sign bit hiding (TComTrQuant.cpp:2530-2660)
-  {
-    const double invQ = (double)inv_quant_scale(q.rem);
-#ifdef FHC_DEVICE_BUILD
-    const double f = __dadd_rn(__ddiv_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(__dmul_rn(invQ, invQ), (double)(1 << (2 * q.per))), lambda), 16.0),
-                                         (double)(1 << (2 * (q.bd - 8)))), 0.5);
-#else
-    const double f = invQ * invQ * (double)(1 << (2 * q.per)) / lambda / 16 / (double)(1 << (2 * (q.bd - 8))) + 0.5;
-#endif
-    const int64_t rdFactor = (int64_t)f;
-    int lastCG = -1;
-    FHC_NOUNROLL for (int subSet = numCodedCG - 1; subSet >= 0; subSet--)
-    {
-      const int subPos = subSet << 4;
-      uint32_t mask = 0;
-      int sum = 0;
-      FHC_NOUNROLL for (int i = 0; i < 16; i++)
-      {
-        const int lv = coef[scan[subPos + i]];
-        if (lv) { mask |= 1u << i; sum += lv; }
-      }
-      if (!mask) continue;
-      const int lastNZ = msb_index(mask), firstNZ = lsb_index(mask);
-      if (lastCG == -1) lastCG = 1;
-      if (lastNZ - firstNZ >= 4)
-      {
-        const uint32_t signbit = A[subPos + firstNZ] >= 0 ? 0u : 1u;             // sign of the first non-zero level = sign of its coefficient
-        if (signbit != (uint32_t)(sum & 1))
-        {
-          int64_t minCostInc = INT64_MAX, curCost = INT64_MAX;
-          int minPos = -1, finalChange = 0, curChange = 0;
-          FHC_NOUNROLL for (int nn = (lastCG == 1 ? lastNZ : 15); nn >= 0; --nn)
-          {
-            const int scanPos = nn + subPos, blkPos = scan[scanPos];
-            const int lv = coef[blkPos], pk = B[scanPos], a = A[scanPos], ld = iabs(a);
-            const int deltaU = (ld - (int)((uint32_t)lv << qBits)) >> (qBits - 8);
-            const int sigD = pk_nosig(pk) ? 0 : ctx_bits(t, go, sigBase + pk_sig(pk), 1) - ctx_bits(t, go, sigBase + pk_sig(pk), 0);
-            if (lv != 0)
-            {
-              const int rateNow = ic_rate(t, go, (uint32_t)lv, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk));
-              const int incUp = ic_rate(t, go, (uint32_t)lv + 1, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk)) - rateNow;
-              const int incDown = ic_rate(t, go, (uint32_t)lv - 1, pk_one(pk), pk_abs(pk), pk_rice(pk), pk_c1lt8(pk), pk_c2lt1(pk)) - rateNow;
-              const int64_t costUp = rdFactor * (-deltaU) + incUp;
-              int64_t costDown = rdFactor * (deltaU) + incDown - ((lv == 1) ? sigD : 0);
-              if (lastCG == 1 && lastNZ == nn && lv == 1) costDown -= (4 << 15);
-              if (costUp < costDown) { curCost = costUp; curChange = 1; }
-              else
-              {
-                curChange = -1;
-                if (nn == firstNZ && lv == 1) curCost = INT64_MAX;
-                else curCost = costDown;
-              }
-            }
-            else
-            {
-              curCost = rdFactor * (-(iabs(deltaU))) + (1 << 15) + ctx_bits(t, go, pk_one(pk), 0) + sigD;
-              curChange = 1;
-              if (nn < firstNZ)
-              {
-                const uint32_t thisSign = a >= 0 ? 0u : 1u;
-                if (thisSign != signbit) curCost = INT64_MAX;
-              }
-            }
-            if (curCost < minCostInc) { minCostInc = curCost; finalChange = curChange; minPos = scanPos; }
-          }
-          {
-            const int blkPos = scan[minPos];
-            int lv = coef[blkPos];
-            if (lv == 32767 && A[minPos] >= 0) finalChange = -1;       // HM tests the signed level against 32767 / -32768
-            lv += finalChange;
-            coef[blkPos] = (int16_t)lv;
-          }
-        }
-      }
-      if (lastCG == 1) lastCG = 0;
-    }
-  }
+  if (absSum >= 2) rdoq_sbh(b, go, q, A, B, coef, numCodedCG);          // sign bit hiding (TComTrQuant.cpp:2530-2660)
   // apply the signs
   FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
   {
@@ -1105,7 +1160,7 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   FHC_GLANES(g, i, n2)
   {
     const int x = i & (n - 1), y = i >> log2n;
-    const int v = pred_sample(t, line, n, log2n, a.mode, x, y, comp == 0, bd, a.dcVal);
+    const int v = pred_sample_call(t, line, n, log2n, a.mode, x, y, comp == 0, bd, a.dcVal);
     a.rec[y * a.recStride + x] = (int16_t)v;
     s.resi[i] = (int16_t)(src[y * a.srcStride + x] - v);
   }
@@ -1120,19 +1175,35 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   {
     const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
     const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
+    // M(k, q) = mat[k * rs + q]; its transpose Mt(q, k) = matT[q * rsT + k * ksT] (lanes that differ in k read neighbouring words)
+    const int16_t* mat = useDst ? t.dst4 : t.T32;
+    const int16_t* matT = useDst ? t.dst4t : t.T32t;
+    const int rs = useDst ? 4 : (1 << (10 - log2n)), rsT = useDst ? 4 : 32, ksT = useDst ? 1 : (1 << (5 - log2n));
+    // rows of the residual: A[j][k] = sum_q M(k, q) * resi[j][q]  (stored transposed w.r.t. HM's tmp[k][j]: coalesced both ways)
     FHC_GLANES(g, i, n2)
     {
-      const int k = i >> log2n, j = i & (n - 1);
+      const int j = i >> log2n, k = i & (n - 1);
+      const int16_t* m = matT + k * ksT;
+      const int16_t* in = s.resi + j * n;
       int acc = 0;
-      FHC_NOUNROLL for (int q = 0; q < n; q++) acc += tmat_at(t, n, useDst, k, q) * s.resi[j * n + q];
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+      for (int q = 0; q < n; q++) acc += m[q * rsT] * in[q];
       s.A[i] = (acc + add1) >> shift1;
     }
     gsync(g);
+    // columns: B[k2][j2] = sum_q M(k2, q) * A[q][j2]
     FHC_GLANES(g, i, n2)
     {
-      const int k = i >> log2n, j = i & (n - 1);
+      const int k2 = i >> log2n, j2 = i & (n - 1);
+      const int16_t* m = mat + k2 * rs;
+      const int32_t* in = s.A + j2;
       int acc = 0;
-      FHC_NOUNROLL for (int q = 0; q < n; q++) acc += tmat_at(t, n, useDst, k, q) * s.A[j * n + q];
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+      for (int q = 0; q < n; q++) acc += m[q] * in[q * n];
       s.B[i] = (acc + add2) >> shift2;
     }
   }
@@ -1188,19 +1259,31 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     {
       // xITrMxN (TComTrQuant.cpp:927): columns first, clipping after each stage
       const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
+      const int16_t* mat = useDst ? t.dst4 : t.T32;
+      const int rs = useDst ? 4 : (1 << (10 - log2n));
       FHC_GLANES(g, i, n2)
       {
         const int j = i >> log2n, q = i & (n - 1);
+        const int16_t* m = mat + q;
+        const int32_t* in = s.A + j;
         int acc = 0;
-        FHC_NOUNROLL for (int k = 0; k < n; k++) acc += tmat_at(t, n, useDst, k, q) * s.A[k * n + j];
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+        for (int k = 0; k < n; k++) acc += m[k * rs] * in[k * n];
         s.B[i] = clip3(-32768, 32767, (acc + 64) >> 7);
       }
       gsync(g);
       FHC_GLANES(g, i, n2)
       {
         const int j = i >> log2n, q = i & (n - 1);
+        const int16_t* m = mat + q;
+        const int32_t* in = s.B + j;
         int acc = 0;
-        FHC_NOUNROLL for (int k = 0; k < n; k++) acc += tmat_at(t, n, useDst, k, q) * s.B[k * n + j];
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+        for (int k = 0; k < n; k++) acc += m[k * rs] * in[k * n];
         s.resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
       }
     }
@@ -1383,12 +1466,13 @@ FHC_DH void code_coeff_of(Coder& e, const Hyp& h, int comp, int p, int log2n)   
   const int off = comp ? 4 * p : 16 * p;
   const int pu = h.partSize == SIZE_NxN ? (p / (h.np >> 2)) : 0;
   const int dir = comp ? chroma_pred_mode(h) : h.ldir[pu];
-  code_coeff_serial(e, h.coefc[comp] + off, log2n, comp != 0, scan_idx_for(dir, log2n, comp != 0), h.ts[comp][p], h.nzc[comp] + (off >> 4));
+  code_coeff_serial(e, h.coefc[comp] + off, log2n, opq(comp != 0), scan_idx_for(dir, log2n, comp != 0), h.ts[comp][p], h.nzc[comp] + (off >> 4));
 }
 
 // xEncSubdivCbfQT (TEncSearch.cpp:881) over the sub-tree rooted at partition p0, transform depth t0
-FHC_D void enc_subdiv_cbf(Coder& e, const Hyp& h, int p0, int t0, int bLuma, int bChroma)
+FHC_D void enc_subdiv_cbf(Coder& eio, const Hyp& h, int p0, int t0, int bLuma, int bChroma)
 {
+  Coder e = eio;
   const int cnt = h.np >> (2 * t0);
   FHC_NOUNROLL for (int p = p0; p < p0 + cnt;)
   {
@@ -1404,11 +1488,13 @@ FHC_D void enc_subdiv_cbf(Coder& e, const Hyp& h, int p0, int t0, int bLuma, int
     }
     p += h.np >> (2 * T);
   }
+  eio = e;
 }
 // xEncCoeffQT (TEncSearch.cpp:958) for one component over a sub-tree; search-time order: the 4x4 chroma block of an
 // 8x8 luma area split into four 4x4 TUs goes with the FIRST quadrant
-FHC_D void enc_coeff_qt(Coder& e, const Hyp& h, int p0, int t0, int comp)
+FHC_D void enc_coeff_qt(Coder& eio, const Hyp& h, int p0, int t0, int comp)
 {
+  Coder e = eio;
   const int cnt = h.np >> (2 * t0);
   FHC_NOUNROLL for (int p = p0; p < p0 + cnt;)
   {
@@ -1423,6 +1509,7 @@ FHC_D void enc_coeff_qt(Coder& e, const Hyp& h, int p0, int t0, int comp)
     }
     p += h.np >> (2 * T);
   }
+  eio = e;
 }
 // luma-dir part of xEncIntraHeader for the node at partition p0 / depth t0 (TEncSearch.cpp:1002)
 FHC_DH void enc_intra_header_luma(Coder& e, const Blk* b, const Hyp& h, int cuZ, int p0, int t0)
@@ -1441,29 +1528,34 @@ FHC_DH void enc_intra_header_luma(Coder& e, const Blk* b, const Hyp& h, int cuZ,
   }
 }
 // xGetIntraBitsQT, luma only (TEncSearch.cpp:1067)
-FHC_D uint32_t intra_bits_luma(Coder& e, const Blk* b, const Hyp& h, int cuZ, int p0, int t0)
+FHC_D uint32_t intra_bits_luma(Coder& eio, const Blk* b, const Hyp& h, int cuZ, int p0, int t0)
 {
+  Coder e = eio;
   reset_bits(e);
   enc_intra_header_luma(e, b, h, cuZ, p0, t0);
   enc_subdiv_cbf(e, h, p0, t0, 1, 0);
   enc_coeff_qt(e, h, p0, t0, 0);
+  eio = e;
   return num_bits(e);
 }
 // xGetIntraBitsQT, chroma only, whole CU
-FHC_D uint32_t intra_bits_chroma(Coder& e, const Hyp& h)
+FHC_D uint32_t intra_bits_chroma(Coder& eio, const Hyp& h)
 {
+  Coder e = eio;
   reset_bits(e);
   code_chroma_dir(e, h.cdir);
   enc_subdiv_cbf(e, h, 0, 0, 0, 1);
   enc_coeff_qt(e, h, 0, 0, 1);
   enc_coeff_qt(e, h, 0, 0, 2);
+  eio = e;
   return num_bits(e);
 }
 // encodePredInfo + encodeCoeff of a CU in real syntax order (TEncEntropy.cpp:200-448): the CU-level bit count of
 // xCheckRDCostIntra (TEncCu.cpp:1564-1582) and the chain advance of xEncodeCU.  The 4x4 chroma block of a split 8x8
 // luma area goes with the LAST quadrant here.
-FHC_D void encode_cu_syntax(Coder& e, const Blk* b, const Hyp& h, int cuZ)
+FHC_D void encode_cu_syntax(Coder& eio, const Blk* b, const Hyp& h, int cuZ)
 {
+  Coder e = eio;
   if (h.depth == 3) enc_bin(e, CTX_PART, h.partSize == SIZE_2Nx2N ? 1 : 0);
   {
     const int numPU = h.partSize == SIZE_NxN ? 4 : 1;
@@ -1502,7 +1594,10 @@ FHC_D void encode_cu_syntax(Coder& e, const Blk* b, const Hyp& h, int cuZ)
     }
     p += h.np >> (2 * T);
   }
+  eio = e;
 }
+
+// one shared copy of the luma predictor for the rough mode decision (keeps the instruction footprint small)
 
 // ----------------------------------------------------------------------------------------------
 // rough mode decision of one luma PU (TEncSearch.cpp:2271-2295): 35 predictions + Hadamard SATD (xGetHADs,
@@ -1555,67 +1650,61 @@ FHC_D void rmd_satd(Blk* b, Role* r, int log2n, int x0, int y0)
   const int lane = FHC_LANE;
   if (n >= 8)
   {
-    const int ltpr = log2n - 3, tiles = 1 << (2 * ltpr), items = 35 * tiles;
-    const int sub = lane >> 3, rr = lane & 7;
-    FHC_NOUNROLL for (int it0 = 0; it0 < items; it0 += 4)
+    // the whole warp works on one 8x8 tile of one mode: lane (rr, c) holds the samples (x = c, y = rr) and (c, rr + 4)
+    const int ltpr = log2n - 3, tiles = 1 << (2 * ltpr);
+    const int c = lane & 7, rr = lane >> 3;
+    FHC_NOUNROLL for (int mode = 0; mode < 35; mode++)
     {
-      const int it = imin(it0 + sub, items - 1);
-      const int mode = it >> (2 * ltpr), tile = it & (tiles - 1), ty = tile >> ltpr, tx = tile & ((1 << ltpr) - 1);
       const int16_t* line = use_filtered_refs(t, 0, mode, log2n) ? r->refF : r->refU;
-      const int y = ty * 8 + rr;
-      int d[8];
+      uint32_t total = 0;
+      FHC_NOUNROLL for (int tile = 0; tile < tiles; tile++)
+      {
+        const int x = ((tile & ((1 << ltpr) - 1)) << 3) + c, y = ((tile >> ltpr) << 3) + rr;
+        int a = src[y * 64 + x] - pred_sample_call(t, line, n, log2n, mode, x, y, 1, bd, r->dcVal);
+        int bb = src[(y + 4) * 64 + x] - pred_sample_call(t, line, n, log2n, mode, x, y + 4, 1, bd, r->dcVal);
+        // rows: across the 8 lanes of a row
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        d[j] = src[y * 64 + tx * 8 + j] - pred_sample(t, line, n, log2n, mode, tx * 8 + j, y, 1, bd, r->dcVal);
-      // row transform in registers
-#pragma unroll
-      for (int k = 1; k < 8; k <<= 1)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          if (!(j & k)) { const int a = d[j], bb = d[j + k]; d[j] = a + bb; d[j + k] = a - bb; }
-      // column transform across the 8 lanes of the tile
-#pragma unroll
-      for (int k = 1; k < 8; k <<= 1)
-#pragma unroll
-        for (int j = 0; j < 8; j++)
+        for (int k = 1; k < 8; k <<= 1)
         {
-          const int o = __shfl_xor_sync(0xffffffffu, d[j], k);
-          d[j] = (rr & k) ? o - d[j] : d[j] + o;
+          const int oa = __shfl_xor_sync(0xffffffffu, a, k), ob = __shfl_xor_sync(0xffffffffu, bb, k);
+          a = (c & k) ? oa - a : a + oa;
+          bb = (c & k) ? ob - bb : bb + ob;
         }
-      int s = 0;
+        // columns: rows y and y + 4 are in this lane, the other two stages run across the lanes
+        { const int t0 = a + bb, t1 = a - bb; a = t0; bb = t1; }
 #pragma unroll
-      for (int j = 0; j < 8; j++) s += iabs(d[j]);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (rr == 0 && it0 + sub < items) atomicAdd(&r->satd[mode], (uint32_t)((s + 2) >> 2));
+        for (int k = 8; k < 32; k <<= 1)
+        {
+          const int oa = __shfl_xor_sync(0xffffffffu, a, k), ob = __shfl_xor_sync(0xffffffffu, bb, k);
+          a = (lane & k) ? oa - a : a + oa;
+          bb = (lane & k) ? ob - bb : bb + ob;
+        }
+        int sm = iabs(a) + iabs(bb);
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, k);
+        total += (uint32_t)((sm + 2) >> 2);
+      }
+      if (lane == 0) r->satd[mode] = total;
     }
   }
   else
   {
-    const int sub = lane >> 2, rr = lane & 3;
-    FHC_NOUNROLL for (int it0 = 0; it0 < 35; it0 += 8)
+    // two modes per pass, one sample per lane
+    const int half = lane >> 4, x = lane & 3, y = (lane >> 2) & 3;
+    FHC_NOUNROLL for (int m0 = 0; m0 < 35; m0 += 2)
     {
-      const int mode = imin(it0 + sub, 34);
-      int d[4];
+      const int mode = imin(m0 + half, 34);
+      int a = src[y * 64 + x] - pred_sample_call(t, r->refU, 4, 2, mode, x, y, 1, bd, r->dcVal);
 #pragma unroll
-      for (int j = 0; j < 4; j++) d[j] = src[rr * 64 + j] - pred_sample(t, r->refU, 4, 2, mode, j, rr, 1, bd, r->dcVal);
+      for (int k = 1; k < 16; k <<= 1)
       {
-        const int a = d[0] + d[3], bb = d[1] + d[2], cc = d[1] - d[2], dd = d[0] - d[3];
-        d[0] = a + bb; d[1] = a - bb; d[2] = dd + cc; d[3] = dd - cc;
+        const int o = __shfl_xor_sync(0xffffffffu, a, k);
+        a = (lane & k) ? o - a : a + o;
       }
+      int sm = iabs(a);
 #pragma unroll
-      for (int k = 1; k < 4; k <<= 1)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-        {
-          const int o = __shfl_xor_sync(0xffffffffu, d[j], k);
-          d[j] = (rr & k) ? o - d[j] : d[j] + o;
-        }
-      int s = iabs(d[0]) + iabs(d[1]) + iabs(d[2]) + iabs(d[3]);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (rr == 0 && it0 + sub < 35) r->satd[mode] = (uint32_t)((s + 1) >> 1);
+      for (int k = 1; k < 16; k <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, k);
+      if ((lane & 15) == 0 && m0 + half < 35) r->satd[mode] = (uint32_t)((sm + 1) >> 1);
     }
   }
 #else
@@ -1764,13 +1853,13 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
     a.srcOff = (r->y + by) * 64 + r->x + bx; a.srcStride = 64;
     a.rec = r->curRec + by * cuw + bx; a.recStride = cuw; a.coef = r->curCoef + 16 * pB;
     a.refU = r->refU; a.refF = r->refF;
-    a.dcVal = build_refs(b, w, view, 0, nB, r->x + bx, r->y + by, LB >= 3, r->refU, r->refF);
+    a.dcVal = build_refs(b, w, view, opq(0), nB, r->x + bx, r->y + by, LB >= 3, r->refU, r->refF);
     int cbfS;
     const uint32_t dS = tu_eval(b, w, s, a, &cbfS);
     FHC_LANES(k, partsB) r->cCbf[pB + k] = (uint8_t)(cbfS << 1);
     nz_masks_tu(w, t, a.coef, LB, a.scanType, h.nzc[0] + pB);
     warp_sync();
-    if (w.gl == 0) { Coder e = { s.go, &t, 0 }; s.acc[3] = intra_bits_luma(e, b, h, r->zidx, pB, 1); }
+    if (w.gl == 0) { Coder e = coder_open(s.go, &t); s.acc[3] = intra_bits_luma(e, b, h, r->zidx, pB, 1); coder_close(e); }
     warp_sync();
     const double costS = rd_cost(b, s.acc[3], dS);
     uint32_t distB = dS;
@@ -1793,21 +1882,21 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
         c.srcOff = (r->y + cy) * 64 + r->x + cx; c.srcStride = 64;
         c.rec = r->curRec + cy * cuw + cx; c.recStride = cuw; c.coef = r->curCoef + 16 * pC;
         c.refU = r->refU; c.refF = r->refF;
-        c.dcVal = build_refs(b, w, view, 0, nC, r->x + cx, r->y + cy, LC >= 3, r->refU, r->refF);
+        c.dcVal = build_refs(b, w, view, opq(0), nC, r->x + cx, r->y + cy, LC >= 3, r->refU, r->refF);
         int cbfC;
         dSp += tu_eval(b, w, s, c, &cbfC);
         cbfAny |= cbfC;
         FHC_LANES(k, partsC) r->cCbf[pC + k] = (uint8_t)(cbfC << 2);
         nz_masks_tu(w, t, c.coef, LC, c.scanType, h.nzc[0] + pC);
         warp_sync();
-        if (w.gl == 0) { Coder e = { s.go, &t, 0 }; intra_bits_luma(e, b, h, r->zidx, pC, 2); }
+        if (w.gl == 0) { Coder e = coder_open(s.go, &t); intra_bits_luma(e, b, h, r->zidx, pC, 2); coder_close(e); }
         warp_sync();
       }
       if (cbfAny) FHC_LANES(k, partsB) r->cCbf[pB + k] |= 2;
       warp_sync();
       sb_copy_g(w, s.go, rootB);
       warp_sync();
-      if (w.gl == 0) { Coder e = { s.go, &t, 0 }; s.acc[3] = intra_bits_luma(e, b, h, r->zidx, pB, 1); }
+      if (w.gl == 0) { Coder e = coder_open(s.go, &t); s.acc[3] = intra_bits_luma(e, b, h, r->zidx, pB, 1); coder_close(e); }
       warp_sync();
       const double costSp = rd_cost(b, s.acc[3], dSp);
       if (costSp < costS) distB = dSp;
@@ -1827,7 +1916,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
   nz_masks_range(t, w, h, 0, r->np, 1, 0);
   sb_copy_g(w, s.go, &b->curr[r->depth]);
   warp_sync();
-  if (w.gl == 0) { Coder e = { s.go, &t, 0 }; s.acc[3] = intra_bits_luma(e, b, h, r->zidx, 0, 0); }
+  if (w.gl == 0) { Coder e = coder_open(s.go, &t); s.acc[3] = intra_bits_luma(e, b, h, r->zidx, 0, 0); coder_close(e); }
   warp_sync();
   const double cost = rd_cost(b, s.acc[3], splitDist);
   if (cost < *bestCost) { *bestCost = cost; *bestDist = splitDist; return 1; }
@@ -1849,7 +1938,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   const int px = r->x + inX, py = r->y + inY;                                         // CTU-relative
   {
     const RecView view = { r->curRec, r->x, r->y, cuw };
-    const int dc = build_refs(b, w, view, 0, n, px, py, log2pu >= 3, r->refU, r->refF);
+    const int dc = build_refs(b, w, view, opq(0), n, px, py, log2pu >= 3, r->refU, r->refF);
     if (w.gl == 0) r->dcVal = dc;
     warp_sync();
   }
@@ -1889,14 +1978,15 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
         double cost = FHC_MAX_COST;
         if (!(ts && !cbf))                                            // transform skip with cbf = 0 is not allowed (TEncSearch.cpp:1515)
         {
-          Coder e = { s.go, &t, 0 };
+          Coder e = coder_open(s.go, &t);
           reset_bits(e);
           if (p0 == 0 && depth == 3) enc_bin(e, CTX_PART, isNxN ? 0 : 1);
           code_luma_dir1(e, mode, r->mpm);
           if (!isNxN) enc_bin(e, CTX_SUBDIV + (5 - log2pu), 0);        // split_transform_flag of the PU-sized TU (always coded for 8..32)
           enc_bin(e, a.cbfCtx, cbf);
-          if (cbf) code_coeff_serial(e, a.coef, log2pu, 0, a.scanType, ts, nzTu);
+          if (cbf) code_coeff_serial(e, a.coef, log2pu, opq(0), a.scanType, ts, nzTu);
           cost = rd_cost(b, num_bits(e), dist);
+          coder_close(e);
         }
         r->gCost[g.idx] = cost; r->gDist[g.idx] = dist; r->gCbf[g.idx] = (uint32_t)cbf | ((uint32_t)ts << 8);
       }
@@ -1914,7 +2004,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
         a.srcOff = (r->y + ty) * 64 + r->x + tx; a.srcStride = 64;
         a.rec = s.rec + ty * 64 + tx; a.recStride = 64; a.coef = s.coef + 16 * pk;
         a.refU = s.refU; a.refF = s.refF;
-        a.dcVal = build_refs(b, g, gv, 0, 32, r->x + tx, r->y + ty, 1, s.refU, s.refF);
+        a.dcVal = build_refs(b, g, gv, opq(0), opq(32), r->x + tx, r->y + ty, opq(1), s.refU, s.refF);
         int cbf;
         dist += tu_eval(b, g, s, a, &cbf);
         cbfBits |= (uint32_t)cbf << k;
@@ -1922,12 +2012,13 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
         gsync(g);
         if (g.gl == 0)
         {
-          Coder e = { s.go, &t, 0 };
+          Coder e = coder_open(s.go, &t);
           reset_bits(e);
           if (k == 0) code_luma_dir1(e, mode, r->mpm);
           enc_bin(e, CTX_SUBDIV + 0, 0);
           enc_bin(e, CTX_CBF + 0, cbf);
-          if (cbf) code_coeff_serial(e, a.coef, 5, 0, SCAN_DIAG, 0, s.nz + pk);
+          if (cbf) code_coeff_serial(e, a.coef, opq(5), opq(0), opq(SCAN_DIAG), opq(0), s.nz + pk);
+          coder_close(e);
         }
         gsync(g);
       }
@@ -1935,13 +2026,14 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
       gsync(g);
       if (g.gl == 0)
       {
-        Coder e = { s.go, &t, 0 };
+        Coder e = coder_open(s.go, &t);
         reset_bits(e);
         code_luma_dir1(e, mode, r->mpm);
         for (int k = 0; k < 4; k++) { enc_bin(e, CTX_SUBDIV + 0, 0); enc_bin(e, CTX_CBF + 0, (cbfBits >> k) & 1); }
         for (int k = 0; k < 4; k++)
-          if ((cbfBits >> k) & 1) code_coeff_serial(e, s.coef + 16 * 64 * k, 5, 0, SCAN_DIAG, 0, s.nz + 64 * k);
+          if ((cbfBits >> k) & 1) code_coeff_serial(e, s.coef + 16 * 64 * k, opq(5), opq(0), opq(SCAN_DIAG), opq(0), s.nz + 64 * k);
         r->gCost[g.idx] = rd_cost(b, num_bits(e), dist); r->gDist[g.idx] = dist; r->gCbf[g.idx] = cbfBits;
+        coder_close(e);
       }
     }
   });
@@ -2039,7 +2131,7 @@ FHC_D void search_chroma(Blk* b, Role* r)
           a.srcOff = comp_off64(c) + ((r->y >> 1) + cyin) * 32 + (r->x >> 1) + cxin; a.srcStride = 32;
           a.rec = plane + cyin * cw + cxin; a.recStride = cw; a.coef = s.coef + yuv_off(cuw, c) + 4 * p;
           a.refU = s.refU; a.refF = s.refU;
-          a.dcVal = build_refs(b, g, cv, c, cn, (r->x >> 1) + cxin, (r->y >> 1) + cyin, 0, s.refU, s.refF);
+          a.dcVal = build_refs(b, g, cv, c, cn, (r->x >> 1) + cxin, (r->y >> 1) + cyin, opq(0), s.refU, s.refF);
           uint16_t* nzTu = s.nz + ((yuv_off(cuw, c) + 4 * p) >> 4);
           int cbf, tsBest = 0;
           if (!checkTS) dist += tu_eval(b, g, s, a, &cbf);
@@ -2056,10 +2148,11 @@ FHC_D void search_chroma(Blk* b, Role* r)
             gsync(g);
             if (g.gl == 0)
             {
-              Coder e = { s.go, &t, 0 };
+              Coder e = coder_open(s.go, &t);
               reset_bits(e);
-              if (cbf0) code_coeff_serial(e, a.coef, 2, 1, a.scanType, 0, nzTu);
+              if (cbf0) code_coeff_serial(e, a.coef, opq(2), opq(1), a.scanType, opq(0), nzTu);
               s.acc[3] = num_bits(e);
+              coder_close(e);
             }
             gsync(g);
             const double cost0 = rd_cost(b, s.acc[3], d0);
@@ -2077,10 +2170,11 @@ FHC_D void search_chroma(Blk* b, Role* r)
               gsync(g);
               if (g.gl == 0)
               {
-                Coder e = { s.go, &t, 0 };
+                Coder e = coder_open(s.go, &t);
                 reset_bits(e);
-                code_coeff_serial(e, a.coef, 2, 1, a.scanType, 1, nzTu);
+                code_coeff_serial(e, a.coef, opq(2), opq(1), a.scanType, opq(1), nzTu);
                 s.acc[3] = num_bits(e);
+                coder_close(e);
               }
               gsync(g);
               cost1 = rd_cost(b, s.acc[3], d1);
@@ -2123,8 +2217,9 @@ FHC_D void search_chroma(Blk* b, Role* r)
     gsync(g);
     if (g.gl == 0)
     {
-      Coder e = { s.go, &t, 0 };
+      Coder e = coder_open(s.go, &t);
       const uint32_t bits = intra_bits_chroma(e, h);
+      coder_close(e);
       r->gCost[g.idx] = rd_cost(b, bits, dist); r->gDist[g.idx] = dist;
     }
   });
@@ -2181,9 +2276,10 @@ FHC_D void run_job(Blk* b, Role* r)
   warp_sync();
   if (w.gl == 0)
   {
-    Coder e = { &r->endCtx, &t, 0 };
+    Coder e = coder_open(&r->endCtx, &t);
     reset_bits(e);
     encode_cu_syntax(e, b, h, r->zidx);
+    coder_close(e);
     r->bits = num_bits(e); r->bins = e.bins;
     r->cost = rd_cost(b, r->bits, r->dist);
   }
@@ -2314,9 +2410,10 @@ FHC_D void region(Blk* b, int z)
   {
     if (w.gl == 0)
     {
-      Coder e = { &b->tmp[D], &t, 0 };
+      Coder e = coder_open(&b->tmp[D], &t);
       reset_bits(e);
       enc_bin(e, CTX_SPLIT + ctx_split(b, z, D), 1);
+      coder_close(e);
       b->scal[0] = num_bits(e); b->scal[1] = e.bins;
     }
     warp_sync();
@@ -2333,9 +2430,10 @@ FHC_D void region(Blk* b, int z)
     // the 2Nx2N hypothesis + split_cu_flag = 0 on its own contexts (TEncCu.cpp:839-848)
     if (w.gl == 0)
     {
-      Coder e = { &r->endCtx, &t, 0 };
+      Coder e = coder_open(&r->endCtx, &t);
       reset_bits(e);
       enc_bin(e, CTX_SPLIT + ctx_split(b, z, D), 0);
+      coder_close(e);
       r->bits += num_bits(e); r->bins += e.bins;
       r->cost = rd_cost(b, r->bits, r->dist);
     }
@@ -2383,7 +2481,7 @@ FHC_D void encode_ctu(Blk* b)
     warp_sync();
     if (w.gl == 0)
     {
-      Coder e = { go, &t, 0 };
+      Coder e = coder_open(go, &t);
       // split_cu_flag of every quad-tree node that starts here (not coded for nodes crossing the picture edge)
       int dd = 0;
       if (z) { dd = 1; while (z & ((256 >> (2 * dd)) - 1)) dd++; }
@@ -2396,6 +2494,7 @@ FHC_D void encode_ctu(Blk* b)
       // finishCU (TEncCu.cpp:1066): terminating bin after the last CU of the CTU unless it is the slice's last CTU
       const int lastInCtu = ((px + wd >= W) || (x + wd == 64)) && ((py + wd >= H) || (y + wd == 64));
       if (lastInCtu && b->ctuAddr != b->pp.wc * b->pp.hc - 1) enc_trm(e, 0);
+      coder_close(e);
     }
     warp_sync();
     z += np;

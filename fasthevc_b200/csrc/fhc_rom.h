@@ -34,10 +34,13 @@ struct Tables
   uint16_t scanOff[3][4];
   uint8_t  scanCG[3][88];         // per type: 1,4,16,64 entries at offsets 0,1,5,21
   int16_t  T32[32 * 32];
+  int16_t  T32t[32 * 32];         // transpose of T32
   int32_t  entropyBits[128];
   uint8_t  nextState[128][2];
+  uint32_t cabac[256];            // [state * 2 + bin]: entropyBits[state ^ bin] | nextState[state][bin] << 24
   uint8_t  ctxInit[NUM_CTX];
   int16_t  dst4[16];              // 4x4 DST-VII (TComRom.cpp g_as_DST_MAT_4)
+  int16_t  dst4t[16];             // its transpose
   int16_t  angTable[9], invAngTable[9];
   uint8_t  chromaScale[58];       // g_aucChromaScale[CHROMA_420]
   uint8_t  ctxIndMap4x4[16];
@@ -107,6 +110,8 @@ static void build_tables(Tables* t, int bitDepth)
     }
   static const int16_t dst4[16] = { 29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29 };
   memcpy(t->dst4, dst4, sizeof(dst4));
+  for (int k = 0; k < 4; k++) for (int q = 0; q < 4; q++) t->dst4t[q * 4 + k] = dst4[k * 4 + q];
+  for (int k = 0; k < 32; k++) for (int q = 0; q < 32; q++) t->T32t[q * 32 + k] = t->T32[k * 32 + q];
   static const int16_t ang[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 }, inv[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
   memcpy(t->angTable, ang, sizeof(ang)); memcpy(t->invAngTable, inv, sizeof(inv));
   static const uint8_t cs[58] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32,
@@ -151,6 +156,8 @@ static void build_tables(Tables* t, int bitDepth)
     t->entropyBits[i] = ebits[i];
     for (int b = 0; b < 2; b++) t->nextState[i][b] = ((i & 1) == b) ? nextMps[i] : nextLps[i];
   }
+  for (int i = 0; i < 128; i++)
+    for (int b = 0; b < 2; b++) t->cabac[i * 2 + b] = (uint32_t)ebits[i ^ b] | ((uint32_t)t->nextState[i][b] << 24);
   static const uint8_t ctxInit[NUM_CTX] = {
     139, 141, 157, 184, 184, 63, 139,
     111, 141, 154, 154, 154, 94, 138, 182, 154, 154,

@@ -63,6 +63,8 @@ if __name__ == "__main__":
         perf(416, 240, 32, [32])
         perf(416, 240, 296, [32])
         perf(416, 240, 296, [22, 27, 32, 37])
+    if "ncucase" in what:
+        perf(136, 72, 296, [22, 27, 32, 37])
     if "perf1080" in what:
         perf(1920, 1080, 8, [22, 27, 32, 37])
         perf(1920, 1080, 256, [22, 27, 32, 37], distinct=16)
