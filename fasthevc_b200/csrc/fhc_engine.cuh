@@ -182,7 +182,6 @@ struct Role
   // per-group arenas
   Sbac* go;                       // [maxGroups] coder under work
   int32_t *tuA, *tuB;             // [maxGroups][tuCap]
-  int16_t* tuResi;                // [maxGroups][tuCap]
   double* cgCost;                 // [maxGroups][tuCap / 16] costCGSig of RDOQ
   uint16_t* nzMask;               // [maxGroups][yuvSize / 16] non-zero map per coefficient group (coefficient coding)
   uint32_t* gAcc;                 // [maxGroups][4]: sse accumulator, cgNZ[2], broadcast word
@@ -806,6 +805,17 @@ FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int
     int foundLast = 0, off, shift;
     last_ctx_params(isChroma, log2n, &off, &shift);
     const int bx0 = CTX_LASTX + (isChroma ? 15 : 0) + off, by0 = CTX_LASTY + (isChroma ? 15 : 0) + off, gmax = group_idx(n - 1);
+    // bits of the last-position prefixes per group index (estLastSignificantPositionBit, TEncSbac.cpp:1862)
+    int tabX[10], tabY[10];
+    {
+      int ax = 0, ay = 0;
+      FHC_NOUNROLL for (int gi = 0; gi <= gmax; gi++)
+      {
+        tabX[gi] = ax + (gi < gmax ? ctx_bits(t, go, bx0 + (gi >> shift), 0) : 0);
+        tabY[gi] = ay + (gi < gmax ? ctx_bits(t, go, by0 + (gi >> shift), 0) : 0);
+        if (gi < gmax) { ax += ctx_bits(t, go, bx0 + (gi >> shift), 1); ay += ctx_bits(t, go, by0 + (gi >> shift), 1); }
+      }
+    }
     FHC_NOUNROLL for (int cgScanPos = cgLastScanPos; cgScanPos >= 0 && !foundLast; cgScanPos--)
     {
       const int cgBlk = scanCG[cgScanPos];
@@ -823,12 +833,7 @@ FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int
           const int posY = blkPos >> log2n, posX = blkPos - (posY << log2n);
           const int lx = q.scanType == SCAN_VER ? posY : posX, ly = q.scanType == SCAN_VER ? posX : posY;
           const int gx = group_idx(lx), gy = group_idx(ly);
-          int bx = 0, by = 0, cc;
-          FHC_NOUNROLL for (cc = 0; cc < gx; cc++) bx += ctx_bits(t, go, bx0 + (cc >> shift), 1);
-          if (gx < gmax) bx += ctx_bits(t, go, bx0 + (gx >> shift), 0);
-          FHC_NOUNROLL for (cc = 0; cc < gy; cc++) by += ctx_bits(t, go, by0 + (cc >> shift), 1);
-          if (gy < gmax) by += ctx_bits(t, go, by0 + (gy >> shift), 0);
-          double cost = (double)(bx + by);
+          double cost = (double)(tabX[gx] + tabY[gy]);
           if (gx > 3) cost = dadd(cost, dmul(32768.0, (double)((gx - 2) >> 1)));
           if (gy > 3) cost = dadd(cost, dmul(32768.0, (double)((gy - 2) >> 1)));
           const double costLast = dmul(lambda, cost);
@@ -851,7 +856,7 @@ FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int
 }
 
 // sign bit hiding (TComTrQuant.cpp:2530-2660); rate increments of level +-1 are re-evaluated from the packed coder state
-FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, int16_t* coef, int numCodedCG)
+FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, int16_t* coef, uint32_t* cgInfo, int numCodedCG)
 {
   const Tables& t = b->t;
   const int log2n = q.log2n, isChroma = q.isChroma, qBits = q.qBits;
@@ -870,13 +875,8 @@ FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t
     FHC_NOUNROLL for (int subSet = numCodedCG - 1; subSet >= 0; subSet--)
     {
       const int subPos = subSet << 4;
-      uint32_t mask = 0;
-      int sum = 0;
-      FHC_NOUNROLL for (int i = 0; i < 16; i++)
-      {
-        const int lv = coef[scan[subPos + i]];
-        if (lv) { mask |= 1u << i; sum += lv; }
-      }
+      const uint32_t mask = cgInfo[subSet] & 0xffffu;
+      const int sum = (int)(cgInfo[subSet] >> 16);                      // only its parity is used
       if (!mask) continue;
       const int lastNZ = msb_index(mask), firstNZ = lsb_index(mask);
       if (lastCG == -1) lastCG = 1;
@@ -927,6 +927,7 @@ FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t
             if (lv == 32767 && A[minPos] >= 0) finalChange = -1;       // HM tests the signed level against 32767 / -32768
             lv += finalChange;
             coef[blkPos] = (int16_t)lv;
+            if (lv) cgInfo[subSet] |= 1u << (minPos - subPos); else cgInfo[subSet] &= ~(1u << (minPos - subPos));
           }
         }
       }
@@ -1086,18 +1087,35 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
   RdoqState st;
   st.blockUncoded = blockUncoded; st.baseCost = baseCost; st.cgLastScanPos = cgLastScanPos; st.lastScanPos = lastScanPos; st.cgFlags = cgFlags;
   const int bestLastIdxP1 = rdoq_last_pos(b, go, q, A, B, coef, costCGSig, st);
-  // signs; per coefficient group of the coded range the non-zero map and the parity of the level sum
+  // per coefficient group of the coded range: non-zero map (bits 0..15) and parity of the level sum (bit 16), kept in
+  // the group-cost scratch (no longer needed); consumed by sign bit hiding and by the sign pass
   uint32_t absSum = 0;
   const int numCodedCG = (bestLastIdxP1 + 15) >> 4;
+  uint32_t* cgInfo = (uint32_t*)costCGSig;
   FHC_NOUNROLL for (int scanPos = bestLastIdxP1; scanPos <= lastScanPos; scanPos++) coef[scan[scanPos]] = 0;
-  FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++) absSum += (uint32_t)coef[scan[scanPos]];
-
-  if (absSum >= 2) rdoq_sbh(b, go, q, A, B, coef, numCodedCG);          // sign bit hiding (TComTrQuant.cpp:2530-2660)
-  // apply the signs
-  FHC_NOUNROLL for (int scanPos = 0; scanPos < bestLastIdxP1; scanPos++)
+  FHC_NOUNROLL for (int cg = 0; cg < numCodedCG; cg++)
   {
-    const int blkPos = scan[scanPos];
-    if (A[scanPos] < 0) coef[blkPos] = (int16_t)(-coef[blkPos]);
+    const int p0 = cg << 4, cnt = imin(16, bestLastIdxP1 - p0);
+    uint32_t mask = 0, sum = 0;
+    FHC_NOUNROLL for (int i = 0; i < cnt; i++)
+    {
+      const uint32_t lv = (uint32_t)coef[scan[p0 + i]];
+      if (lv) { mask |= 1u << i; sum += lv; }
+    }
+    absSum += sum;
+    cgInfo[cg] = mask | ((sum & 1u) << 16);
+  }
+  if (absSum >= 2) rdoq_sbh(b, go, q, A, B, coef, cgInfo, numCodedCG);  // sign bit hiding (TComTrQuant.cpp:2530-2660)
+  // apply the signs of the coefficients to the non-zero levels
+  FHC_NOUNROLL for (int cg = 0; cg < numCodedCG; cg++)
+  {
+    uint32_t m = cgInfo[cg] & 0xffffu;
+    FHC_NOUNROLL while (m)
+    {
+      const int i = lsb_index(m);
+      m &= m - 1;
+      if (A[(cg << 4) + i] < 0) { const int blkPos = scan[(cg << 4) + i]; coef[blkPos] = (int16_t)(-coef[blkPos]); }
+    }
   }
   return absSum;
 }
@@ -1109,7 +1127,7 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
 struct GScr                       // a group's scratch (see Role)
 {
   Sbac* go;
-  int32_t *A, *B; int16_t* resi;
+  int32_t *A, *B;
   double* cgCost; uint16_t* nz; uint32_t* acc;     // acc[0] sse, acc[1..2] cgNZ, acc[3] broadcast word
   int16_t *rec, *coef;            // candidate planes (yuv layout of the role's CU)
   uint8_t* meta;                  // chroma cbf[2][np], ts[2][np]
@@ -1121,7 +1139,7 @@ FHC_DH GScr group_scratch(const Role* r, int idx, int planeStride)
 {
   GScr s;
   s.go = r->go + idx;
-  s.A = r->tuA + idx * r->tuCap; s.B = r->tuB + idx * r->tuCap; s.resi = r->tuResi + idx * r->tuCap;
+  s.A = r->tuA + idx * r->tuCap; s.B = r->tuB + idx * r->tuCap;
   s.cgCost = r->cgCost + idx * (r->tuCap >> 4); s.nz = r->nzMask + idx * (r->yuvSize >> 4); s.acc = r->gAcc + idx * 4;
   s.rec = r->gRec + idx * planeStride; s.coef = r->gCoef + idx * planeStride;
   s.meta = r->gMeta + (idx < 5 ? idx : 0) * 4 * r->np;
@@ -1144,6 +1162,29 @@ FHC_DH int tmat_at(const Tables& t, int n, int useDst, int k, int q)
   return useDst ? t.dst4[k * 4 + q] : t.T32[(k * (32 / n)) * 32 + q];
 }
 
+// One stage of a separable NxN transform, striped over the group's lanes:
+//   out[i] = post((sum_q m[q * ms] * in[q * is] + add) >> shift),  i = hi * N + lo,
+//   m = mbase + hi * mHi + lo * mLo, in = ibase + hi * iHi + lo * iLo; post = clipping to 16 bits for the inverse stages
+// (xTrMxN / xITrMxN, TComTrQuant.cpp:860-985).  One copy serves all four stages.
+FHC_D void mat_stage(const Grp& g, int log2n, const int16_t* mbase, int mHi, int mLo, int ms, const int32_t* ibase, int iHi, int iLo, int is,
+                     int32_t* out, int add, int shift, int clip)
+{
+  const int n = 1 << log2n, n2 = n * n;
+  FHC_GLANES(g, i, n2)
+  {
+    const int hi = i >> log2n, lo = i & (n - 1);
+    const int16_t* m = mbase + hi * mHi + lo * mLo;
+    const int32_t* in = ibase + hi * iHi + lo * iLo;
+    int acc = 0;
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+    for (int q = 0; q < n; q++) acc += m[q * ms] * in[q * is];
+    acc = (acc + add) >> shift;
+    out[i] = clip ? clip3(-32768, 32767, acc) : acc;
+  }
+}
+
 // returns the distortion (chroma: weighted, TComRdCost.cpp:352); *cbfOut = uiAbsSum > 0.  All lanes of the group
 // return the same values.
 FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int* cbfOut)
@@ -1153,59 +1194,37 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   const int useDst = (comp == 0 && log2n == 2);
   const int16_t* line = use_filtered_refs(t, comp, a.mode, log2n) ? a.refF : a.refU;
   const int16_t* src = b->src + a.srcOff;
+  // M(k, q) = mat[k * rs + q]; its transpose Mt(q, k) = matT[q * rsT + k * ksT] (lanes that differ in k read neighbouring words)
+  const int16_t* mat = useDst ? t.dst4 : t.T32;
+  const int16_t* matT = useDst ? t.dst4t : t.T32t;
+  const int rs = useDst ? 4 : (1 << (10 - log2n)), rsT = useDst ? 4 : 32, ksT = useDst ? 1 : (1 << (5 - log2n));
   FHC_COUNT(if (g.gl == 0) { g_emuCounters.tqSamples[isChroma][log2n - 2] += (unsigned)n2; g_emuCounters.tuCalls[isChroma][log2n - 2]++; });
   gsync(g);                                                            // every lane has consumed the accumulators of the previous TU
   if (g.gl == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; }
-  // prediction + residual
+  // prediction + residual -> B
   FHC_GLANES(g, i, n2)
   {
     const int x = i & (n - 1), y = i >> log2n;
     const int v = pred_sample_call(t, line, n, log2n, a.mode, x, y, comp == 0, bd, a.dcVal);
     a.rec[y * a.recStride + x] = (int16_t)v;
-    s.resi[i] = (int16_t)(src[y * a.srcStride + x] - v);
+    s.B[i] = src[y * a.srcStride + x] - v;
   }
   gsync(g);
   // forward transform (xTrMxN, TComTrQuant.cpp:860) or transform skip (:2011) -> B (raster)
   if (a.ts)
   {
     const int shift = 15 - bd - log2n;
-    FHC_GLANES(g, i, n2) s.B[i] = (int32_t)s.resi[i] << shift;
+    FHC_GLANES(g, i, n2) s.B[i] = (int32_t)((uint32_t)s.B[i] << shift);
   }
   else
   {
     const int shift1 = log2n + bd + 6 - 15, add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0;
     const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
-    // M(k, q) = mat[k * rs + q]; its transpose Mt(q, k) = matT[q * rsT + k * ksT] (lanes that differ in k read neighbouring words)
-    const int16_t* mat = useDst ? t.dst4 : t.T32;
-    const int16_t* matT = useDst ? t.dst4t : t.T32t;
-    const int rs = useDst ? 4 : (1 << (10 - log2n)), rsT = useDst ? 4 : 32, ksT = useDst ? 1 : (1 << (5 - log2n));
-    // rows of the residual: A[j][k] = sum_q M(k, q) * resi[j][q]  (stored transposed w.r.t. HM's tmp[k][j]: coalesced both ways)
-    FHC_GLANES(g, i, n2)
-    {
-      const int j = i >> log2n, k = i & (n - 1);
-      const int16_t* m = matT + k * ksT;
-      const int16_t* in = s.resi + j * n;
-      int acc = 0;
-#ifdef FHC_DEVICE_BUILD
-#pragma unroll 4
-#endif
-      for (int q = 0; q < n; q++) acc += m[q * rsT] * in[q];
-      s.A[i] = (acc + add1) >> shift1;
-    }
+    // rows of the residual: A[j][k] = sum_q M(k, q) * resi[j][q] (stored transposed w.r.t. HM's tmp[k][j]: coalesced both ways),
+    // then columns: B[k2][j2] = sum_q M(k2, q) * A[q][j2]
+    mat_stage(g, log2n, matT, 0, ksT, rsT, s.B, n, 0, 1, s.A, add1, shift1, 0);
     gsync(g);
-    // columns: B[k2][j2] = sum_q M(k2, q) * A[q][j2]
-    FHC_GLANES(g, i, n2)
-    {
-      const int k2 = i >> log2n, j2 = i & (n - 1);
-      const int16_t* m = mat + k2 * rs;
-      const int32_t* in = s.A + j2;
-      int acc = 0;
-#ifdef FHC_DEVICE_BUILD
-#pragma unroll 4
-#endif
-      for (int q = 0; q < n; q++) acc += m[q] * in[q * n];
-      s.B[i] = (acc + add2) >> shift2;
-    }
+    mat_stage(g, log2n, mat, rs, 0, 1, s.A, 0, 1, n, s.B, add2, shift2, 0);
   }
   gsync(g);
   // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient: A[p] = signed lLevelDouble
@@ -1250,42 +1269,18 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
       s.A[i] = clip3(-32768, 32767, v);
     }
     gsync(g);
+    // inverse transform skip (:2060) or xITrMxN (:927, columns first, clipping after each stage) -> residual in A
     if (a.ts)
     {
       const int shift = transformShift, off = shift == 0 ? 0 : (1 << (shift - 1));
-      FHC_GLANES(g, i, n2) s.resi[i] = (int16_t)((s.A[i] + off) >> shift);
+      FHC_GLANES(g, i, n2) s.A[i] = (int16_t)((s.A[i] + off) >> shift);
     }
     else
     {
-      // xITrMxN (TComTrQuant.cpp:927): columns first, clipping after each stage
-      const int shift2 = 12 - (bd - 8), add2 = 1 << (shift2 - 1);
-      const int16_t* mat = useDst ? t.dst4 : t.T32;
-      const int rs = useDst ? 4 : (1 << (10 - log2n));
-      FHC_GLANES(g, i, n2)
-      {
-        const int j = i >> log2n, q = i & (n - 1);
-        const int16_t* m = mat + q;
-        const int32_t* in = s.A + j;
-        int acc = 0;
-#ifdef FHC_DEVICE_BUILD
-#pragma unroll 4
-#endif
-        for (int k = 0; k < n; k++) acc += m[k * rs] * in[k * n];
-        s.B[i] = clip3(-32768, 32767, (acc + 64) >> 7);
-      }
+      const int shift2 = 12 - (bd - 8);
+      mat_stage(g, log2n, mat, 0, 1, rs, s.A, 1, 0, n, s.B, 64, 7, 1);
       gsync(g);
-      FHC_GLANES(g, i, n2)
-      {
-        const int j = i >> log2n, q = i & (n - 1);
-        const int16_t* m = mat + q;
-        const int32_t* in = s.B + j;
-        int acc = 0;
-#ifdef FHC_DEVICE_BUILD
-#pragma unroll 4
-#endif
-        for (int k = 0; k < n; k++) acc += m[k * rs] * in[k * n];
-        s.resi[i] = (int16_t)clip3(-32768, 32767, (acc + add2) >> shift2);
-      }
+      mat_stage(g, log2n, mat, 0, 1, rs, s.B, 1, 0, n, s.A, 1 << (shift2 - 1), shift2, 1);
     }
   }
   else
@@ -1300,7 +1295,7 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     FHC_GLANES(g, i, n2)
     {
       const int x = i & (n - 1), y = i >> log2n;
-      const int v = clip3(0, maxv, a.rec[y * a.recStride + x] + (coded ? (int)s.resi[i] : 0));
+      const int v = clip3(0, maxv, a.rec[y * a.recStride + x] + (coded ? s.A[i] : 0));
       a.rec[y * a.recStride + x] = (int16_t)v;
       const int d = v - src[y * a.srcStride + x];
       acc += (uint32_t)((d * d) >> shift);
@@ -2574,7 +2569,6 @@ FHC_HD void role_carve(Role* r, int ri, Arena* sm, Arena* gm)
   }
   r->tuA = (int32_t*)arena_take(big, 4 * cap * G);
   r->tuB = (int32_t*)arena_take(big, 4 * cap * G);
-  r->tuResi = (int16_t*)arena_take(big, 2 * cap * G);
   r->cgCost = (double*)arena_take(big, 8 * (cap >> 4) * G);
   r->nzMask = (uint16_t*)arena_take(big, 2 * (yuv >> 4) * G);
   {
