@@ -12,7 +12,7 @@
 using namespace fhc;
 
 #ifndef FHC_BLOCKS_PER_SM
-#define FHC_BLOCKS_PER_SM 2
+#define FHC_BLOCKS_PER_SM (2 / FHC_PICS_PER_BLOCK)      /* two picture chains per SM either way */
 #endif
 #define FHC_BATCHES 2                     /* submits that may be in flight: one running, one queued behind it */
 
@@ -20,29 +20,40 @@ using namespace fhc;
 // kernel: persistent blocks, one picture at a time per block, pulled from a queue
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
-fhc_ctu_kernel(const PicDesc* pics, int numPics, int* queue, unsigned char* workspace, size_t wsPerBlock, const Tables* tables)
+fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, unsigned char* workspace, size_t wsPerChain, size_t smemPerChain,
+               const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Blk* b = reinterpret_cast<Blk*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
+  const int inst = threadIdx.x / FHC_INST_THREADS, tid = threadIdx.x - inst * FHC_INST_THREADS, nthr = FHC_INST_THREADS;
+  unsigned char* mine = smem_raw + (size_t)inst * smemPerChain;
+  Blk* b = reinterpret_cast<Blk*>(mine);
+  Blk* b0 = reinterpret_cast<Blk*>(smem_raw);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&b->t);
     for (int i = tid; i < (int)(sizeof(Tables) / 4); i += nthr) dst[i] = src[i];
   }
-  if (tid == 0) init_block(b, smem_raw + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + (size_t)blockIdx.x * wsPerBlock);
+  if (tid == 0)
+  {
+    init_block(b, mine + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + ((size_t)blockIdx.x * FHC_PICS_PER_BLOCK + inst) * wsPerChain);
+    b->inst = inst;
+  }
   __syncthreads();
   for (;;)
   {
-    if (tid == 0) b->picIndex = atomicAdd(queue, 1);
+    if (threadIdx.x == 0) b0->picIndex = atomicAdd(queue, FHC_PICS_PER_BLOCK);
     __syncthreads();
-    const int p = b->picIndex;
-    if (p >= numPics) break;
-    compress_picture(b, &pics[p], tid, nthr);
-    if (tid == 0)
+    const int base = b0->picIndex;
+    if (base >= numPics) break;
+    const int p = base + inst;
+    const PicDesc* pd = p < numPics ? &pics[p] : nullptr;
+    if (tid == 0) b->twin = (FHC_PICS_PER_BLOCK > 1) && (base + 1 < numPics);
+    compress_picture(b, pd, numCtus, tid, nthr);
+    if (tid == 0 && pd)
     {
       __threadfence_system();
-      *reinterpret_cast<volatile int32_t*>(pics[p].doneFlag) = 1;
+      *reinterpret_cast<volatile int32_t*>(pd->doneFlag) = 1;
     }
     __syncthreads();
   }
@@ -89,7 +100,7 @@ struct fhc_ctx
 {
   fhc_seq_params seq;
   int device = 0, numCtus = 0, maxFrames = 0, maxBlocks = 0;
-  size_t lumaSamples = 0, frameSamples = 0, smemBytes = 0, wsPerBlock = 0;
+  size_t lumaSamples = 0, frameSamples = 0, smemBytes = 0, wsPerBlock = 0;   // smemBytes / wsPerBlock: per picture chain
   Tables* dTables = nullptr;
   unsigned char* dWorkspace = nullptr;
   cudaStream_t compute = nullptr, copyIn = nullptr, copyOut = nullptr;
@@ -115,9 +126,10 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
   int perSm = 0;
   block_footprint(smemBytes, wsPerBlock);
   CK(cudaGetDeviceProperties(&prop, device));
-  CK(cudaFuncSetAttribute(fhc_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smemBytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_ctu_kernel, FHC_BLOCK_THREADS, *smemBytes));
-  if (perSm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit an SM (%zu bytes of shared memory)", *smemBytes); return FHC_ERR_CUDA; }
+  const size_t blockSmem = *smemBytes * FHC_PICS_PER_BLOCK;
+  CK(cudaFuncSetAttribute(fhc_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blockSmem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_ctu_kernel, FHC_BLOCK_THREADS, blockSmem));
+  if (perSm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit an SM (%zu bytes of shared memory)", blockSmem); return FHC_ERR_CUDA; }
   *maxBlocks = prop.multiProcessorCount * perSm;
   return FHC_OK;
 }
@@ -173,9 +185,9 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   c->hostPics.resize((size_t)c->maxFrames);
   // every failure below releases what was allocated so far (fhc_destroy is null-safe)
   if (kernel_geometry(device, &c->smemBytes, &c->wsPerBlock, &c->maxBlocks) != FHC_OK) { fhc_destroy(c); return FHC_ERR_CUDA; }
-  if (c->maxBlocks > c->maxFrames) c->maxBlocks = c->maxFrames;
+  if (c->maxBlocks > (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK) c->maxBlocks = (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
   CKG(cudaMalloc(&c->dTables, sizeof(Tables)), fhc_destroy(c));
-  CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks), fhc_destroy(c));
+  CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->copyIn, cudaStreamNonBlocking), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->copyOut, cudaStreamNonBlocking), fhc_destroy(c));
@@ -266,9 +278,11 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
   CK(cudaMemsetAsync(bt->dQueue, 0, sizeof(int), c->compute));
-  const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
+  const int want = (n + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
+  const int blocks = want < c->maxBlocks ? want : c->maxBlocks;
   CK(cudaEventRecord(bt->evStart, c->compute));
-  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes, c->compute>>>(bt->dPics, n, bt->dQueue, c->dWorkspace, c->wsPerBlock, c->dTables);
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, c->dWorkspace,
+                                                                                            c->wsPerBlock, c->smemBytes, c->dTables);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));
   g_launches++;
@@ -440,7 +454,7 @@ int fhc_pictures_in_flight(int device)
   if (device < 0 || device >= ndev) return FHC_ERR_ARG;
   CK(cudaSetDevice(device));
   if (kernel_geometry(device, &smemBytes, &ws, &maxBlocks) != FHC_OK) return FHC_ERR_CUDA;
-  return maxBlocks;
+  return maxBlocks * FHC_PICS_PER_BLOCK;
 }
 
 int fhc_host_alloc(void** p, uint64_t bytes)
@@ -459,7 +473,7 @@ int fhc_host_free(void* p)
 extern "C" int fhc_debug_geometry(fhc_ctx* c, long long* out4)
 {
   if (!c || !out4) return FHC_ERR_ARG;
-  out4[0] = c->maxBlocks; out4[1] = FHC_BLOCK_THREADS; out4[2] = (long long)c->smemBytes; out4[3] = (long long)c->wsPerBlock;
+  out4[0] = c->maxBlocks; out4[1] = FHC_BLOCK_THREADS; out4[2] = (long long)c->smemBytes * FHC_PICS_PER_BLOCK; out4[3] = (long long)c->wsPerBlock * FHC_PICS_PER_BLOCK;
   return FHC_OK;
 }
 

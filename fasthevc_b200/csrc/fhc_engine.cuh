@@ -44,7 +44,11 @@
 namespace fhc {
 
 #define FHC_ROLES 5              /* warps per block: 0 = chain master + depth-3 2Nx2N, 1 = depth-3 NxN, 2 = depth 2, 3 = depth 1, 4 = depth 0 */
-#define FHC_BLOCK_THREADS (32 * FHC_ROLES)
+#ifndef FHC_PICS_PER_BLOCK
+#define FHC_PICS_PER_BLOCK 2     /* picture chains per thread block; 2 = "twins": the same-role warps of the two pictures are kept on the same routine */
+#endif
+#define FHC_INST_THREADS (32 * FHC_ROLES)
+#define FHC_BLOCK_THREADS (FHC_INST_THREADS * FHC_PICS_PER_BLOCK)
 #define FHC_MAX_CAND 10          /* 8 RMD survivors + 2 MPMs */
 enum { ROLE_3A = 0, ROLE_3B = 1, ROLE_2 = 2, ROLE_1 = 3, ROLE_0 = 4 };
 
@@ -232,6 +236,8 @@ struct Blk                        // shared memory of a block
   uint32_t scal[8];               // scalar broadcast words of the chain master
   Role role[FHC_ROLES];
   int mailbox[FHC_ROLES];         // job command per role: 1 = run, 0 = end of CTU
+  int jobSeq[FHC_ROLES], doneSeq[FHC_ROLES];   // jobs started by the master / finished by the role (join = the two are equal)
+  int inst, twin;                 // index of this picture chain inside the block; twin != 0: the other chain of the block is active too
 };
 
 FHC_DH int comp_off64(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
@@ -245,8 +251,23 @@ FHC_DH int yuv_off(int cuw, int comp) { return comp == 0 ? 0 : (comp == 1 ? cuw 
 FHC_DH void bar_sync(int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 FHC_DH void bar_arrive(int id) { __syncwarp(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 #endif
-FHC_DH int bar_start(int role) { return 1 + role; }
-FHC_DH int bar_done(int role) { return 1 + FHC_ROLES + role; }
+FHC_DH int bar_start(const Blk* b, int role) { return b->inst * (FHC_ROLES - 1) + role; }      // ids 1 .. 8 (roles 1..4 of chain 0 / 1)
+FHC_DH int bar_twin(int role) { return 2 * (FHC_ROLES - 1) + 1 + role; }                       // ids 9 .. 13
+
+// TWIN ALIGNMENT.  The kernel is bound by instruction delivery: an SM hands only ~0.4 instructions per cycle in total to
+// warps that run different code, but warps that run the same code share their fetches (profiles/r02_icache_probe.md).
+// The two picture chains of a block have the same geometry, are started together and advance CTU by CTU in lockstep,
+// so their same-role warps ("twins") walk the same static schedule of routines; a named barrier at the entry of each
+// routine of that schedule keeps them on the same code at the same time.  Only call sites whose count per CTU does not
+// depend on the picture content may align (jobs, PUs, the four second-pass nodes, chroma and syntax entry).
+FHC_DH void twin_align(const Blk* b, int role)
+{
+#if defined(FHC_DEVICE_BUILD) && FHC_PICS_PER_BLOCK > 1
+  if (b->twin) bar_sync(bar_twin(role));
+#else
+  (void)b; (void)role;
+#endif
+}
 
 // ----------------------------------------------------------------------------------------------
 // CABAC bit counter (TEncBinCoderCABACCounter.cpp:57-140)
@@ -1841,6 +1862,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
   FHC_NOUNROLL for (int i = 0; i < 4; i++)
   {
     const int pB = i * partsB, bx = (i & 1) * nB, by = (i >> 1) * nB;
+    twin_align(b, (int)(r - b->role));
     if (splitB) sb_copy_g(w, rootB, s.go);
     FHC_LANES(k, partsB) { r->cTridx[pB + k] = 1; r->cTs[pB + k] = 0; }
     TuArgs a;
@@ -1939,12 +1961,14 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   }
   const int ri = (int)(r - b->role);
   trace_role(b->pp, ri, 16 + pu * 8 + 1);
+  twin_align(b, ri);
   FHC_TIC(tRmd);
   rmd_satd(b, r, log2pu, px, py);
   trace_role(b->pp, ri, 16 + pu * 8 + 2);
   rmd_candidates(b, r, pu, log2pu);
   trace_role(b->pp, ri, 16 + pu * 8 + 3);
   FHC_TOC(r, PF_RMD, tRmd);
+  twin_align(b, ri);
   FHC_TIC(tL1);
   const int numCand = r->numCand, tasks = numCand * (log2pu == 2 ? 2 : 1);
   for_groups(tasks, [&](const Grp& g)
@@ -2062,6 +2086,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
     warp_sync();
   }
   FHC_TIC(tL2);
+  twin_align(b, ri);
   if (log2pu >= 3)
   {
     if (second_pass(b, r, bestMode, &bestCost, &bestDist))
@@ -2246,6 +2271,7 @@ FHC_D void run_job(Blk* b, Role* r)
   warp_sync();
   const int ri = (int)(r - b->role);
   trace_role(b->pp, ri, 1);
+  twin_align(b, ri);
   FHC_TIC(tJob);
   FHC_CNT(r, PF_JOBS);
   for (int pu = 0; pu < (isNxN ? 4 : 1); pu++) { search_luma_pu(b, r, pu); trace_role(b->pp, ri, 2 + pu); }
@@ -2258,9 +2284,11 @@ FHC_D void run_job(Blk* b, Role* r)
     if (any) FHC_LANES(k, np) r->cbf[0][k] |= 1;
     warp_sync();
   }
+  twin_align(b, ri);
   FHC_TIC(tCh);
   search_chroma(b, r);
   FHC_TOC(r, PF_CHROMA, tCh);
+  twin_align(b, ri);
   FHC_TIC(tSy);
   trace_role(b->pp, ri, 6);
   // bits of the whole CU in real syntax order on the CI_CURR_BEST contexts (TEncCu.cpp:1564-1588)
@@ -2292,21 +2320,25 @@ FHC_DH int role_of_depth(int d) { return d == 0 ? ROLE_0 : (d == 1 ? ROLE_1 : RO
 FHC_DH void set_job(Blk* b, int ri, int z, int partSize)
 {
   Role* r = &b->role[ri];
-  if (FHC_LANE == 0) { r->zidx = z; r->x = zx(b->t, z); r->y = zy(b->t, z); r->partSize = partSize; b->mailbox[ri] = 1; }
+  if (FHC_LANE == 0) { r->zidx = z; r->x = zx(b->t, z); r->y = zy(b->t, z); r->partSize = partSize; b->mailbox[ri] = 1; b->jobSeq[ri]++; }
   warp_sync();
 }
 FHC_DH void start_job(Blk* b, int ri, int z, int partSize)
 {
   set_job(b, ri, z, partSize);
 #ifdef FHC_DEVICE_BUILD
-  bar_arrive(bar_start(ri));
+  bar_arrive(bar_start(b, ri));
 #endif
 }
 FHC_DH void join_job(Blk* b, int ri)
 {
 #ifdef FHC_DEVICE_BUILD
   FHC_TIC(tW);
-  bar_sync(bar_done(ri));
+  // the role publishes the sequence number of the job it finished; the master rarely gets here first
+  const int want = b->jobSeq[ri];
+  while (((volatile int*)b->doneSeq)[ri] != want) __nanosleep(40);
+  __threadfence_block();
+  __syncwarp();
   FHC_TOC(&b->role[ri], PF_WAIT, tW);
 #else
   run_job(b, &b->role[ri]);       // host build: the job runs at the join, i.e. after its sub-tree
@@ -2505,7 +2537,7 @@ FHC_D void master_ctu(Blk* b)
   {
     if (FHC_LANE == 0) b->mailbox[ri] = 0;
     __syncwarp();
-    bar_arrive(bar_start(ri));
+    bar_arrive(bar_start(b, ri));
   }
 #endif
   FHC_TIC(tEnc);
@@ -2519,11 +2551,12 @@ FHC_D void role_loop(Blk* b, int ri)
   for (;;)
   {
     trace_role(b->pp, ri, 100);
-    bar_sync(bar_start(ri));
+    bar_sync(bar_start(b, ri));
     trace_role(b->pp, ri, 101);
     if (!b->mailbox[ri]) break;
     run_job(b, &b->role[ri]);
-    bar_arrive(bar_done(ri));
+    if (FHC_LANE == 0) { __threadfence_block(); ((volatile int*)b->doneSeq)[ri] = b->jobSeq[ri]; }
+    __syncwarp();
   }
 }
 #endif
@@ -2699,9 +2732,12 @@ FHC_D void init_block(Blk* b, unsigned char* smemArena, unsigned char* globalAre
   for (int ri = 0; ri < FHC_ROLES; ri++) role_carve(&b->role[ri], ri, &sm, &gm);
 }
 
-FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
+// One picture on one chain of a block.  Device: called by all threads of the block at the same time (tid / nthr are the
+// thread index / count inside the chain); the chains of a block advance CTU by CTU in lockstep (__syncthreads), a chain
+// without a picture (pd == 0, odd tail of the queue) only takes part in the barriers.
+FHC_D void compress_picture(Blk* b, const PicDesc* pd, int numCtus, int tid, int nthr)
 {
-  if (tid == 0)
+  if (tid == 0 && pd)
   {
     PicParams& pp = b->pp;
     for (int c = 0; c < 3; c++) { pp.org[c] = pd->org[c]; pp.line[0][c] = pd->line[0][c]; pp.line[1][c] = pd->line[1][c]; }
@@ -2709,27 +2745,25 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
     pp.out = pd->out; pp.sp = pd->sp;
     pp.width = pd->width; pp.height = pd->height; pp.bitDepth = pd->bitDepth; pp.sampleBytes = pd->sampleBytes; pp.wc = pd->wc; pp.hc = pd->hc;
     pp.trace = pd->trace; pp.prof = pd->prof;
-    for (int ri = 0; ri < FHC_ROLES; ri++) for (int k = 0; k < PF_NUM; k++) b->role[ri].prof[k] = 0;
+    for (int ri = 0; ri < FHC_ROLES; ri++) { for (int k = 0; k < PF_NUM; k++) b->role[ri].prof[k] = 0; b->jobSeq[ri] = 0; b->doneSeq[ri] = 0; }
   }
 #ifdef FHC_DEVICE_BUILD
   __syncthreads();
 #ifdef FHC_PROFILE
   const long long tPic = clock64();
 #endif
-  if (tid < 32) sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);       // slice start: resetEntropy (TEncSlice.cpp:719-720)
-  const int numCtus = b->pp.wc * b->pp.hc;
+  if (pd && tid < 32) sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);       // slice start: resetEntropy (TEncSlice.cpp:719-720)
   for (int addr = 0; addr < numCtus; addr++)
   {
-    load_ctu(b, addr, tid, nthr);
+    if (pd) load_ctu(b, addr, tid, nthr);
     __syncthreads();
-    if (tid < 32) master_ctu(b); else role_loop(b, tid >> 5);
+    if (pd) { if (tid < 32) master_ctu(b); else role_loop(b, tid >> 5); }
     __syncthreads();
-    store_ctu(b, tid, nthr);
-    shift_left_neighbour(b, tid, nthr);
+    if (pd) { store_ctu(b, tid, nthr); shift_left_neighbour(b, tid, nthr); }
     __syncthreads();
   }
 #ifdef FHC_PROFILE
-  if (tid == 0 && b->pp.prof)
+  if (tid == 0 && pd && b->pp.prof)
   {
     for (int ri = 0; ri < FHC_ROLES; ri++) for (int k = 0; k < PF_NUM; k++) b->pp.prof[ri * PF_NUM + k] = b->role[ri].prof[k];
     b->pp.prof[5 * PF_NUM] = clock64() - tPic;
@@ -2737,7 +2771,6 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int tid, int nthr)
 #endif
 #else
   sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);
-  const int numCtus = b->pp.wc * b->pp.hc;
   for (int addr = 0; addr < numCtus; addr++)
   {
     load_ctu(b, addr, 0, 1);

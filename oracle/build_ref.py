@@ -194,6 +194,13 @@ def main():
         print("build_ref: libfasthevc_cuda.so not built yet - TAppEncoderFHC skipped")
     shutil.rmtree(scratch, ignore_errors=True)
     shutil.rmtree(objdir, ignore_errors=True)
+    # provenance of the binaries that travel to the GPU box (they are git-ignored): sha256 next to them
+    import hashlib
+    with open(os.path.join(OUT, "SHA256SUMS"), "w") as f:
+        for name in sorted(os.listdir(OUT)):
+            path = os.path.join(OUT, name)
+            if os.path.isfile(path) and name != "SHA256SUMS":
+                f.write("%s  %s\n" % (hashlib.sha256(open(path, "rb").read()).hexdigest(), name))
     print("build_ref: built", sorted(os.listdir(OUT)))
     return 0
 

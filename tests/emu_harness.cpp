@@ -33,7 +33,8 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
     pd.line[k][2] = pd.line[k][1] + width / 2;
     pd.depthRow[k] = depthRows.data() + (size_t)k * (width / 2);
   }
-  compress_picture(b, &pd, 0, 1);
+  b->inst = 0; b->twin = 0;
+  compress_picture(b, &pd, pd.wc * pd.hc, 0, 1);
   free(sm); free(gm);
   return 0;
 }
