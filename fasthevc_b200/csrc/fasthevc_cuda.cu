@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
+#include <algorithm>
 #include <vector>
 #include "fhc_engine.cuh"
 
@@ -20,8 +21,8 @@ using namespace fhc;
 // kernel: persistent blocks, one picture at a time per block, pulled from a queue
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
-fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, unsigned char* workspace, size_t wsPerChain, size_t smemPerChain,
-               const Tables* tables)
+fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const int* assign, unsigned char* workspace, size_t wsPerChain,
+               size_t smemPerChain, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
@@ -40,15 +41,28 @@ fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, unsign
     b->inst = inst;
   }
   __syncthreads();
-  for (;;)
+  // first round: the host's balanced assignment (assign[block][chain], -1 = none); afterwards pictures come from the queue
+  for (int round = 0;; round++)
   {
-    if (threadIdx.x == 0) b0->picIndex = atomicAdd(queue, FHC_PICS_PER_BLOCK);
+    int p;
+    if (round == 0) p = assign[blockIdx.x * FHC_PICS_PER_BLOCK + inst];
+    else
+    {
+      if (threadIdx.x == 0) b0->picIndex = atomicAdd(queue, FHC_PICS_PER_BLOCK);
+      __syncthreads();
+      const int base = b0->picIndex;
+      if (base >= numPics) break;
+      p = base + inst < numPics ? base + inst : -1;
+    }
+    const PicDesc* pd = p >= 0 ? &pics[p] : nullptr;
+    if (tid == 0) b->active = pd != nullptr;
     __syncthreads();
-    const int base = b0->picIndex;
-    if (base >= numPics) break;
-    const int p = base + inst;
-    const PicDesc* pd = p < numPics ? &pics[p] : nullptr;
-    if (tid == 0) b->twin = (FHC_PICS_PER_BLOCK > 1) && (base + 1 < numPics);
+    if (tid == 0)
+    {
+      int n = 0;
+      for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) n += reinterpret_cast<Blk*>(smem_raw + (size_t)k * smemPerChain)->active;
+      b->twin = n > 1;
+    }
     compress_picture(b, pd, numCtus, tid, nthr);
     if (tid == 0 && pd)
     {
@@ -91,6 +105,7 @@ struct Batch
   int32_t* hTrace = nullptr;              // [maxFrames] mapped pinned host memory: progress words (FHC_TRACE=1 in the environment)
   int32_t* dTrace = nullptr;
   int* dQueue = nullptr;
+  int* dAssign = nullptr;                 // [maxBlocks][FHC_PICS_PER_BLOCK] first-round pictures of every block
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
   int firstPoc = 0, n = 0, launched = 0;
   uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
@@ -107,6 +122,8 @@ struct fhc_ctx
   Batch batch[FHC_BATCHES];
   uint64_t submits = 0;
   std::vector<PicDesc> hostPics;
+  std::vector<int> hostAssign;
+  int hostQueueStart = 0;
 };
 
 const char* fhc_last_error(void) { return g_err; }
@@ -136,7 +153,7 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue); cudaFree(bt.dProf);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue); cudaFree(bt.dAssign); cudaFree(bt.dProf);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -185,7 +202,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   c->hostPics.resize((size_t)c->maxFrames);
   // every failure below releases what was allocated so far (fhc_destroy is null-safe)
   if (kernel_geometry(device, &c->smemBytes, &c->wsPerBlock, &c->maxBlocks) != FHC_OK) { fhc_destroy(c); return FHC_ERR_CUDA; }
-  if (c->maxBlocks > (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK) c->maxBlocks = (c->maxFrames + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
+  if (c->maxBlocks > c->maxFrames) c->maxBlocks = c->maxFrames;
   CKG(cudaMalloc(&c->dTables, sizeof(Tables)), fhc_destroy(c));
   CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking), fhc_destroy(c));
@@ -202,6 +219,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     CKG(cudaMalloc(&bt.dLines, sizeof(int16_t) * 4 * (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dQueue, sizeof(int)), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dAssign, sizeof(int) * FHC_PICS_PER_BLOCK * (size_t)c->maxBlocks), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dProf, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMemset(bt.dProf, 0, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
@@ -277,11 +295,39 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaMemcpyAsync(bt->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
-  CK(cudaMemsetAsync(bt->dQueue, 0, sizeof(int), c->compute));
-  const int want = (n + FHC_PICS_PER_BLOCK - 1) / FHC_PICS_PER_BLOCK;
-  const int blocks = want < c->maxBlocks ? want : c->maxBlocks;
+  // Work distribution.  A chain is busy for a whole picture (seconds), and an SM is saturated by instruction delivery
+  // whether it runs one chain or two, so what matters is that every SM has work all the time: with
+  // fewer pictures than chains, every block gets one picture before any block gets two; the most expensive pictures
+  // (lowest QP) run alone, the others are paired expensive-with-cheap.  Pictures beyond the first round are pulled
+  // from the queue in submit order.
+  const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
+  int firstRound = 0;
+  {
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[a].sliceQp < sp[b2].sliceQp; });    // expensive first
+    c->hostAssign.assign((size_t)c->maxBlocks * FHC_PICS_PER_BLOCK, -1);
+    firstRound = n < blocks * FHC_PICS_PER_BLOCK ? n : blocks * FHC_PICS_PER_BLOCK;
+    // the first-round pictures are the first `firstRound` of the submit (the queue hands out the rest in order)
+    std::vector<int> first;
+    for (int i = 0; i < n; i++) if (order[(size_t)i] < firstRound) first.push_back(order[(size_t)i]);
+    const int pairs = firstRound - blocks > 0 ? firstRound - blocks : 0, singles = blocks - pairs;
+    int lo = 0, hi = firstRound - 1;
+    for (int bk = 0; bk < blocks; bk++)
+    {
+      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = first[(size_t)lo++];
+      if (FHC_PICS_PER_BLOCK > 1 && bk >= singles) c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK + 1] = first[(size_t)hi--];
+    }
+  }
+  // (both small copies go through the copy stream: pageable sources are staged before the call returns, and the copy
+  // stream is never behind a running kernel)
+  c->hostQueueStart = firstRound;
+  CK(cudaMemcpyAsync(bt->dAssign, c->hostAssign.data(), sizeof(int) * (size_t)blocks * FHC_PICS_PER_BLOCK, cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaMemcpyAsync(bt->dQueue, &c->hostQueueStart, sizeof(int), cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaEventRecord(bt->evCopied, c->copyIn));
+  CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
   CK(cudaEventRecord(bt->evStart, c->compute));
-  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, c->dWorkspace,
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, bt->dAssign, c->dWorkspace,
                                                                                             c->wsPerBlock, c->smemBytes, c->dTables);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));

@@ -237,7 +237,7 @@ struct Blk                        // shared memory of a block
   Role role[FHC_ROLES];
   int mailbox[FHC_ROLES];         // job command per role: 1 = run, 0 = end of CTU
   int jobSeq[FHC_ROLES], doneSeq[FHC_ROLES];   // jobs started by the master / finished by the role (join = the two are equal)
-  int inst, twin;                 // index of this picture chain inside the block; twin != 0: the other chain of the block is active too
+  int inst, twin, active;         // index of this picture chain inside the block; active: it has a picture; twin: so has the other chain
 };
 
 FHC_DH int comp_off64(int comp) { return comp == 0 ? 0 : (comp == 1 ? 4096 : 5120); }
@@ -1176,7 +1176,10 @@ struct TuArgs
   int16_t* rec; int recStride;    // prediction -> reconstruction (block origin)
   int16_t* coef;                  // level block of this TU (n*n, raster)
   const int16_t *refU, *refF; int dcVal;
+  int phases;                     // TU_FRONT | TU_RDOQ | TU_BACK: which parts of the evaluation this call runs (state stays in the group scratch)
+  int alignRole;                  // >= 0: whole-warp call of that role, twin-aligned before the RDOQ pass and before the reconstruction
 };
+enum { TU_FRONT = 1, TU_RDOQ = 2, TU_BACK = 4, TU_ALL = 7 };
 
 FHC_DH int tmat_at(const Tables& t, int n, int useDst, int k, int q)
 {
@@ -1206,6 +1209,61 @@ FHC_D void mat_stage(const Grp& g, int log2n, const int16_t* mbase, int mHi, int
   }
 }
 
+// The DCT matrices are even / odd symmetric, M(k, N-1-q) = (-1)^k M(k, q), which halves the multiplications exactly as
+// HM's partial butterflies do (TComTrQuant.cpp:507-840; integer sums, so the result is identical):
+// fold_stage replaces (x[q], x[N-1-q]) by (x[q] + x[N-1-q], x[q] - x[N-1-q]) along one axis of an N x N int32 block;
+FHC_D void fold_stage(const Grp& g, int log2n, int32_t* buf, int sa, int sq)
+{
+  const int n = 1 << log2n, half = n >> 1;
+  FHC_GLANES(g, i, n * half)
+  {
+    const int a = i >> (log2n - 1), q = i & (half - 1);
+    int32_t* x = buf + a * sa + q * sq;
+    int32_t* y = buf + a * sa + (n - 1 - q) * sq;
+    const int u = *x, v = *y;
+    *x = u + v; *y = u - v;
+  }
+}
+// fwd_stage: out[i] = (sum_{q < N/2} M(k, q) * f[a][k even ? q : N-1-q] + add) >> shift on a folded input f, where
+// (k, a) = (lo, hi) or (hi, lo) of i = hi * N + lo; M(k, q) = mbase[k * mk + q * mq], f[a][q'] = in[a * ia + q' * iq];
+FHC_D void fwd_stage(const Grp& g, int log2n, int kIsLo, const int16_t* mbase, int mk, int mq, const int32_t* in, int ia, int iq,
+                     int32_t* out, int add, int shift)
+{
+  const int n = 1 << log2n, n2 = n * n, half = n >> 1;
+  FHC_GLANES(g, i, n2)
+  {
+    const int hi = i >> log2n, lo = i & (n - 1), k = kIsLo ? lo : hi, a = kIsLo ? hi : lo;
+    const int16_t* m = mbase + k * mk;
+    const int32_t* f = in + a * ia + ((k & 1) ? (n - 1) * iq : 0);
+    const int fs = (k & 1) ? -iq : iq;
+    int acc = 0;
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 4
+#endif
+    for (int q = 0; q < half; q++) acc += m[q * mq] * f[q * fs];
+    out[i] = (acc + add) >> shift;
+  }
+}
+// inv_stage: one lane computes out[j][i] and out[j][N-1-i] = clip((E +- O + add) >> shift) with E / O the sums over
+// the even / odd rows k of M(k, i) * in[k][j]  (xITrMxN, TComTrQuant.cpp:927; partialButterflyInverse*, :476-840).
+FHC_D void inv_stage(const Grp& g, int log2n, const int16_t* mat, int rs, const int32_t* in, int32_t* out, int add, int shift)
+{
+  const int n = 1 << log2n, half = n >> 1;
+  FHC_GLANES(g, idx, n * half)
+  {
+    const int j = idx >> (log2n - 1), i = idx & (half - 1);
+    const int16_t* m = mat + i;
+    const int32_t* c = in + j;
+    int e = 0, o = 0;
+#ifdef FHC_DEVICE_BUILD
+#pragma unroll 2
+#endif
+    for (int k = 0; k < n; k += 2) { e += m[k * rs] * c[k * n]; o += m[(k + 1) * rs] * c[(k + 1) * n]; }
+    out[j * n + i] = clip3(-32768, 32767, (e + o + add) >> shift);
+    out[j * n + n - 1 - i] = clip3(-32768, 32767, (e - o + add) >> shift);
+  }
+}
+
 // returns the distortion (chroma: weighted, TComRdCost.cpp:352); *cbfOut = uiAbsSum > 0.  All lanes of the group
 // return the same values.
 FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int* cbfOut)
@@ -1219,6 +1277,10 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   const int16_t* mat = useDst ? t.dst4 : t.T32;
   const int16_t* matT = useDst ? t.dst4t : t.T32t;
   const int rs = useDst ? 4 : (1 << (10 - log2n)), rsT = useDst ? 4 : 32, ksT = useDst ? 1 : (1 << (5 - log2n));
+  const QpParam qp = qp_param(b, comp);
+  const int qBits = 14 + qp.per + (15 - bd - log2n);
+  if (a.phases & TU_FRONT)
+  {
   FHC_COUNT(if (g.gl == 0) { g_emuCounters.tqSamples[isChroma][log2n - 2] += (unsigned)n2; g_emuCounters.tuCalls[isChroma][log2n - 2]++; });
   gsync(g);                                                            // every lane has consumed the accumulators of the previous TU
   if (g.gl == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; }
@@ -1243,14 +1305,25 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     const int shift2 = log2n + 6, add2 = 1 << (shift2 - 1);
     // rows of the residual: A[j][k] = sum_q M(k, q) * resi[j][q] (stored transposed w.r.t. HM's tmp[k][j]: coalesced both ways),
     // then columns: B[k2][j2] = sum_q M(k2, q) * A[q][j2]
-    mat_stage(g, log2n, matT, 0, ksT, rsT, s.B, n, 0, 1, s.A, add1, shift1, 0);
-    gsync(g);
-    mat_stage(g, log2n, mat, rs, 0, 1, s.A, 0, 1, n, s.B, add2, shift2, 0);
+    if (log2n == 2)
+    {
+      mat_stage(g, log2n, matT, 0, ksT, rsT, s.B, n, 0, 1, s.A, add1, shift1, 0);
+      gsync(g);
+      mat_stage(g, log2n, mat, rs, 0, 1, s.A, 0, 1, n, s.B, add2, shift2, 0);
+    }
+    else
+    {
+      fold_stage(g, log2n, s.B, n, 1);                                  // along the rows of the residual
+      gsync(g);
+      fwd_stage(g, log2n, 1, matT, ksT, rsT, s.B, n, 1, s.A, add1, shift1);
+      gsync(g);
+      fold_stage(g, log2n, s.A, 1, n);                                  // along the columns of the intermediate block
+      gsync(g);
+      fwd_stage(g, log2n, 0, mat, rs, 1, s.A, 1, n, s.B, add2, shift2);
+    }
   }
   gsync(g);
   // RDOQ pre-quantisation (TComTrQuant.cpp:2244-2262), independent per coefficient: A[p] = signed lLevelDouble
-  const QpParam qp = qp_param(b, comp);
-  const int qBits = 14 + qp.per + (15 - bd - log2n);
   {
     const uint16_t* scan = scan_tab(t, a.scanType, log2n);
     const int quantCoef = quant_scale(qp.rem);
@@ -1265,13 +1338,17 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     }
   }
   gsync(g);
-  if (g.gl == 0)
+  }
+  if (a.alignRole >= 0) twin_align(b, a.alignRole);
+  if ((a.phases & TU_RDOQ) && g.gl == 0)
   {
     RdoqIn q;
     q.log2n = log2n; q.isChroma = isChroma; q.scanType = a.scanType; q.cbfCtx = a.cbfCtx; q.qBits = qBits; q.per = qp.per; q.rem = qp.rem; q.bd = bd;
     q.lambda = b->pp.sp.rdoqLambda[comp]; q.errScale = t.errScale[isChroma][log2n - 2][qp.rem];
     s.acc[3] = rdoq_serial(b, s.go, q, s.A, s.B, a.coef, s.cgCost, s.acc[1], s.acc[2]);
   }
+  if (a.alignRole >= 0) twin_align(b, a.alignRole);
+  if (!(a.phases & TU_BACK)) return 0;
   gsync(g);
   const int coded = s.acc[3] > 0;
   if (coded)
@@ -1299,9 +1376,18 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     else
     {
       const int shift2 = 12 - (bd - 8);
-      mat_stage(g, log2n, mat, 0, 1, rs, s.A, 1, 0, n, s.B, 64, 7, 1);
-      gsync(g);
-      mat_stage(g, log2n, mat, 0, 1, rs, s.B, 1, 0, n, s.A, 1 << (shift2 - 1), shift2, 1);
+      if (log2n == 2)
+      {
+        mat_stage(g, log2n, mat, 0, 1, rs, s.A, 1, 0, n, s.B, 64, 7, 1);
+        gsync(g);
+        mat_stage(g, log2n, mat, 0, 1, rs, s.B, 1, 0, n, s.A, 1 << (shift2 - 1), shift2, 1);
+      }
+      else
+      {
+        inv_stage(g, log2n, mat, rs, s.A, s.B, 64, 7);
+        gsync(g);
+        inv_stage(g, log2n, mat, rs, s.B, s.A, 1 << (shift2 - 1), shift2);
+      }
     }
   }
   else
@@ -1869,7 +1955,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
     a.comp = 0; a.log2n = LB; a.mode = mode; a.scanType = scan_idx_for(mode, LB, 0); a.ts = 0; a.cbfCtx = CTX_CBF + 0;
     a.srcOff = (r->y + by) * 64 + r->x + bx; a.srcStride = 64;
     a.rec = r->curRec + by * cuw + bx; a.recStride = cuw; a.coef = r->curCoef + 16 * pB;
-    a.refU = r->refU; a.refF = r->refF;
+    a.refU = r->refU; a.refF = r->refF; a.phases = TU_ALL; a.alignRole = (int)(r - b->role);
     a.dcVal = build_refs(b, w, view, opq(0), nB, r->x + bx, r->y + by, LB >= 3, r->refU, r->refF);
     int cbfS;
     const uint32_t dS = tu_eval(b, w, s, a, &cbfS);
@@ -1898,7 +1984,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
         c.comp = 0; c.log2n = LC; c.mode = mode; c.scanType = scan_idx_for(mode, LC, 0); c.ts = 0; c.cbfCtx = CTX_CBF + 0;
         c.srcOff = (r->y + cy) * 64 + r->x + cx; c.srcStride = 64;
         c.rec = r->curRec + cy * cuw + cx; c.recStride = cuw; c.coef = r->curCoef + 16 * pC;
-        c.refU = r->refU; c.refF = r->refF;
+        c.refU = r->refU; c.refF = r->refF; c.phases = TU_ALL; c.alignRole = (int)(r - b->role);
         c.dcVal = build_refs(b, w, view, opq(0), nC, r->x + cx, r->y + cy, LC >= 3, r->refU, r->refF);
         int cbfC;
         dSp += tu_eval(b, w, s, c, &cbfC);
@@ -1971,23 +2057,47 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
   twin_align(b, ri);
   FHC_TIC(tL1);
   const int numCand = r->numCand, tasks = numCand * (log2pu == 2 ? 2 : 1);
-  for_groups(tasks, [&](const Grp& g)
+  // The dispatch runs in three parts - sample stages up to the pre-quantisation, the sequential RDOQ passes, then
+  // reconstruction + distortion + bit counting - with a twin alignment between them: the RDOQ passes (most of the
+  // instructions of a dispatch) of the two pictures of the block then run at the same time.  The state of a candidate
+  // stays in its group's scratch between the parts.
+  if (log2pu <= 5)
   {
-    const GScr s = group_scratch(r, g.idx, isNxN ? 16 : r->yuvSize);
-    const int ci = (log2pu == 2) ? (g.idx >> 1) : g.idx, ts = (log2pu == 2) ? (g.idx & 1) : 0;
-    const int mode = r->cand[ci];
-    sb_copy_g(g, s.go, &b->curr[depth]);
-    gsync(g);
-    if (log2pu <= 5)
+    auto args = [&](const Grp& g, const GScr& s, int phases)
     {
+      const int ci = (log2pu == 2) ? (g.idx >> 1) : g.idx;
+      const int mode = r->cand[ci];
       TuArgs a;
-      a.comp = 0; a.log2n = log2pu; a.mode = mode; a.scanType = scan_idx_for(mode, log2pu, 0); a.ts = ts;
+      a.comp = 0; a.log2n = log2pu; a.mode = mode; a.scanType = scan_idx_for(mode, log2pu, 0); a.ts = (log2pu == 2) ? (g.idx & 1) : 0;
       a.cbfCtx = CTX_CBF + (isNxN ? 0 : 1);
       a.srcOff = py * 64 + px; a.srcStride = 64;
-      uint16_t* nzTu = isNxN ? s.nz : s.nz + p0;
       if (isNxN) { a.rec = s.rec; a.recStride = 4; a.coef = s.coef; }                  // compact 4x4 candidate block
       else { a.rec = s.rec + inY * cuw + inX; a.recStride = cuw; a.coef = s.coef + 16 * p0; }
       a.refU = r->refU; a.refF = r->refF; a.dcVal = r->dcVal;
+      a.phases = phases; a.alignRole = -1;
+      return a;
+    };
+    for_groups(tasks, [&](const Grp& g)
+    {
+      const GScr s = group_scratch(r, g.idx, isNxN ? 16 : r->yuvSize);
+      sb_copy_g(g, s.go, &b->curr[depth]);
+      gsync(g);
+      int cbf;
+      tu_eval(b, g, s, args(g, s, TU_FRONT), &cbf);
+    });
+    twin_align(b, ri);
+    for_groups(tasks, [&](const Grp& g)
+    {
+      const GScr s = group_scratch(r, g.idx, isNxN ? 16 : r->yuvSize);
+      int cbf;
+      tu_eval(b, g, s, args(g, s, TU_RDOQ), &cbf);
+    });
+    twin_align(b, ri);
+    for_groups(tasks, [&](const Grp& g)
+    {
+      const GScr s = group_scratch(r, g.idx, isNxN ? 16 : r->yuvSize);
+      const TuArgs a = args(g, s, TU_BACK);
+      uint16_t* nzTu = isNxN ? s.nz : s.nz + p0;
       int cbf;
       const uint32_t dist = tu_eval(b, g, s, a, &cbf);
       nz_masks_tu(g, t, a.coef, log2pu, a.scanType, nzTu);
@@ -1995,67 +2105,101 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
       if (g.gl == 0)
       {
         double cost = FHC_MAX_COST;
-        if (!(ts && !cbf))                                            // transform skip with cbf = 0 is not allowed (TEncSearch.cpp:1515)
+        if (!(a.ts && !cbf))                                          // transform skip with cbf = 0 is not allowed (TEncSearch.cpp:1515)
         {
           Coder e = coder_open(s.go, &t);
           reset_bits(e);
           if (p0 == 0 && depth == 3) enc_bin(e, CTX_PART, isNxN ? 0 : 1);
-          code_luma_dir1(e, mode, r->mpm);
+          code_luma_dir1(e, a.mode, r->mpm);
           if (!isNxN) enc_bin(e, CTX_SUBDIV + (5 - log2pu), 0);        // split_transform_flag of the PU-sized TU (always coded for 8..32)
           enc_bin(e, a.cbfCtx, cbf);
-          if (cbf) code_coeff_serial(e, a.coef, log2pu, opq(0), a.scanType, ts, nzTu);
+          if (cbf) code_coeff_serial(e, a.coef, log2pu, opq(0), a.scanType, a.ts, nzTu);
           cost = rd_cost(b, num_bits(e), dist);
           coder_close(e);
         }
-        r->gCost[g.idx] = cost; r->gDist[g.idx] = dist; r->gCbf[g.idx] = (uint32_t)cbf | ((uint32_t)ts << 8);
+        r->gCost[g.idx] = cost; r->gDist[g.idx] = dist; r->gCbf[g.idx] = (uint32_t)cbf | ((uint32_t)a.ts << 8);
       }
-    }
-    else
+    });
+  }
+  else
+  {
+    // 64x64 PU: four 32x32 TUs in z-order, contexts chained from TU to TU (xRecurIntraCodingLumaQT at 64: split only)
+    auto args = [&](const Grp& g, const GScr& s, int k, int phases)
     {
-      // 64x64 PU: four 32x32 TUs in z-order, contexts chained from TU to TU (xRecurIntraCodingLumaQT at 64: split only)
-      uint32_t dist = 0, cbfBits = 0;
-      const RecView gv = { s.rec, r->x, r->y, 64 };
-      FHC_NOUNROLL for (int k = 0; k < 4; k++)
+      const int tx = (k & 1) * 32, ty = (k >> 1) * 32;
+      TuArgs a;
+      a.comp = 0; a.log2n = 5; a.mode = r->cand[g.idx]; a.scanType = SCAN_DIAG; a.ts = 0; a.cbfCtx = CTX_CBF + 0;
+      a.srcOff = (r->y + ty) * 64 + r->x + tx; a.srcStride = 64;
+      a.rec = s.rec + ty * 64 + tx; a.recStride = 64; a.coef = s.coef + 16 * 64 * k;
+      a.refU = s.refU; a.refF = s.refF; a.dcVal = 0;
+      a.phases = phases; a.alignRole = -1;
+      return a;
+    };
+    FHC_LANES(k, tasks) { r->gDist[k] = 0; r->gCbf[k] = 0; }
+    for_groups(tasks, [&](const Grp& g)
+    {
+      const GScr s = group_scratch(r, g.idx, r->yuvSize);
+      sb_copy_g(g, s.go, &b->curr[depth]);
+    });
+    FHC_NOUNROLL for (int k = 0; k < 4; k++)
+    {
+      for_groups(tasks, [&](const Grp& g)
       {
-        const int tx = (k & 1) * 32, ty = (k >> 1) * 32, pk = k * 64;
-        TuArgs a;
-        a.comp = 0; a.log2n = 5; a.mode = mode; a.scanType = SCAN_DIAG; a.ts = 0; a.cbfCtx = CTX_CBF + 0;
-        a.srcOff = (r->y + ty) * 64 + r->x + tx; a.srcStride = 64;
-        a.rec = s.rec + ty * 64 + tx; a.recStride = 64; a.coef = s.coef + 16 * pk;
-        a.refU = s.refU; a.refF = s.refF;
-        a.dcVal = build_refs(b, g, gv, opq(0), opq(32), r->x + tx, r->y + ty, opq(1), s.refU, s.refF);
+        const GScr s = group_scratch(r, g.idx, r->yuvSize);
+        const RecView gv = { s.rec, r->x, r->y, 64 };
+        TuArgs a = args(g, s, k, TU_FRONT);
+        a.dcVal = build_refs(b, g, gv, opq(0), opq(32), r->x + (k & 1) * 32, r->y + (k >> 1) * 32, opq(1), s.refU, s.refF);
         int cbf;
-        dist += tu_eval(b, g, s, a, &cbf);
-        cbfBits |= (uint32_t)cbf << k;
-        nz_masks_tu(g, t, a.coef, 5, SCAN_DIAG, s.nz + pk);
+        tu_eval(b, g, s, a, &cbf);
+      });
+      twin_align(b, ri);
+      for_groups(tasks, [&](const Grp& g)
+      {
+        const GScr s = group_scratch(r, g.idx, r->yuvSize);
+        int cbf;
+        tu_eval(b, g, s, args(g, s, k, TU_RDOQ), &cbf);
+      });
+      twin_align(b, ri);
+      for_groups(tasks, [&](const Grp& g)
+      {
+        const GScr s = group_scratch(r, g.idx, r->yuvSize);
+        const TuArgs a = args(g, s, k, TU_BACK);
+        int cbf;
+        const uint32_t dist = tu_eval(b, g, s, a, &cbf);
+        nz_masks_tu(g, t, a.coef, 5, SCAN_DIAG, s.nz + 64 * k);
         gsync(g);
         if (g.gl == 0)
         {
+          r->gDist[g.idx] += dist; r->gCbf[g.idx] |= (uint32_t)cbf << k;
           Coder e = coder_open(s.go, &t);
           reset_bits(e);
-          if (k == 0) code_luma_dir1(e, mode, r->mpm);
+          if (k == 0) code_luma_dir1(e, a.mode, r->mpm);
           enc_bin(e, CTX_SUBDIV + 0, 0);
           enc_bin(e, CTX_CBF + 0, cbf);
-          if (cbf) code_coeff_serial(e, a.coef, opq(5), opq(0), opq(SCAN_DIAG), opq(0), s.nz + pk);
+          if (cbf) code_coeff_serial(e, a.coef, opq(5), opq(0), opq(SCAN_DIAG), opq(0), s.nz + 64 * k);
           coder_close(e);
         }
-        gsync(g);
-      }
+      });
+    }
+    for_groups(tasks, [&](const Grp& g)
+    {
+      const GScr s = group_scratch(r, g.idx, r->yuvSize);
       sb_copy_g(g, s.go, &b->curr[depth]);
       gsync(g);
       if (g.gl == 0)
       {
+        const uint32_t cbfBits = r->gCbf[g.idx];
         Coder e = coder_open(s.go, &t);
         reset_bits(e);
-        code_luma_dir1(e, mode, r->mpm);
+        code_luma_dir1(e, r->cand[g.idx], r->mpm);
         for (int k = 0; k < 4; k++) { enc_bin(e, CTX_SUBDIV + 0, 0); enc_bin(e, CTX_CBF + 0, (cbfBits >> k) & 1); }
         for (int k = 0; k < 4; k++)
           if ((cbfBits >> k) & 1) code_coeff_serial(e, s.coef + 16 * 64 * k, opq(5), opq(0), opq(SCAN_DIAG), opq(0), s.nz + 64 * k);
-        r->gCost[g.idx] = rd_cost(b, num_bits(e), dist); r->gDist[g.idx] = dist; r->gCbf[g.idx] = cbfBits;
+        r->gCost[g.idx] = rd_cost(b, num_bits(e), r->gDist[g.idx]);
         coder_close(e);
       }
-    }
-  });
+    });
+  }
   trace_role(b->pp, ri, 16 + pu * 8 + 4);
   FHC_TOC(r, PF_LUMA1, tL1);
   // winner: lowest cost, ties to the lowest task index = HM's sequential scan with strict <
@@ -2150,7 +2294,7 @@ FHC_D void search_chroma(Blk* b, Role* r)
           a.comp = c; a.log2n = cl; a.mode = predMode; a.scanType = scan_idx_for(predMode, cl, 1); a.ts = 0; a.cbfCtx = CTX_CBF + 5 + T;
           a.srcOff = comp_off64(c) + ((r->y >> 1) + cyin) * 32 + (r->x >> 1) + cxin; a.srcStride = 32;
           a.rec = plane + cyin * cw + cxin; a.recStride = cw; a.coef = s.coef + yuv_off(cuw, c) + 4 * p;
-          a.refU = s.refU; a.refF = s.refU;
+          a.refU = s.refU; a.refF = s.refU; a.phases = TU_ALL; a.alignRole = -1;
           a.dcVal = build_refs(b, g, cv, c, cn, (r->x >> 1) + cxin, (r->y >> 1) + cyin, opq(0), s.refU, s.refF);
           uint16_t* nzTu = s.nz + ((yuv_off(cuw, c) + 4 * p) >> 4);
           int cbf, tsBest = 0;

@@ -65,6 +65,10 @@ if __name__ == "__main__":
         perf(416, 240, 296, [22, 27, 32, 37])
     if "ncucase" in what:
         perf(136, 72, 296, [22, 27, 32, 37])
+    if "perf256" in what:
+        perf(416, 240, 256, [22, 27, 32, 37])
+        # QP-major order as in bench.py
+        import fasthevc_b200 as fh2
     if "perf1080" in what:
         perf(1920, 1080, 8, [22, 27, 32, 37])
         perf(1920, 1080, 256, [22, 27, 32, 37], distinct=16)
