@@ -21,8 +21,8 @@ using namespace fhc;
 // kernel: persistent blocks, one picture at a time per block, pulled from a queue
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
-fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const int* assign, unsigned char* workspace, size_t wsPerChain,
-               size_t smemPerChain, const Tables* tables)
+fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const int* assign, const int* order, unsigned char* workspace,
+               size_t wsPerChain, size_t smemPerChain, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
@@ -48,11 +48,18 @@ fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const 
     if (round == 0) p = assign[blockIdx.x * FHC_PICS_PER_BLOCK + inst];
     else
     {
-      if (threadIdx.x == 0) b0->picIndex = atomicAdd(queue, FHC_PICS_PER_BLOCK);
+      // next picture(s) in cost order; a second one only while enough are left for every block to get one as well
+      if (threadIdx.x == 0)
+      {
+        const int q0 = atomicAdd(queue, 1);
+        int q1 = numPics;
+        if (FHC_PICS_PER_BLOCK > 1 && q0 < numPics && numPics - q0 - 1 >= (int)gridDim.x) q1 = atomicAdd(queue, 1);
+        b0->picIndex = q0; b0->picIndex2 = q1;
+      }
       __syncthreads();
-      const int base = b0->picIndex;
-      if (base >= numPics) break;
-      p = base + inst < numPics ? base + inst : -1;
+      const int q = inst == 0 ? b0->picIndex : b0->picIndex2;
+      if (b0->picIndex >= numPics) break;
+      p = q < numPics ? order[q] : -1;
     }
     const PicDesc* pd = p >= 0 ? &pics[p] : nullptr;
     if (tid == 0) b->active = pd != nullptr;
@@ -219,7 +226,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     CKG(cudaMalloc(&bt.dLines, sizeof(int16_t) * 4 * (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dQueue, sizeof(int)), fhc_destroy(c));
-    CKG(cudaMalloc(&bt.dAssign, sizeof(int) * FHC_PICS_PER_BLOCK * (size_t)c->maxBlocks), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dAssign, sizeof(int) * (FHC_PICS_PER_BLOCK * (size_t)c->maxBlocks + (size_t)c->maxFrames)), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dProf, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMemset(bt.dProf, 0, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
@@ -295,39 +302,48 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaMemcpyAsync(bt->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
-  // Work distribution.  A chain is busy for a whole picture (seconds), and an SM is saturated by instruction delivery
-  // whether it runs one chain or two, so what matters is that every SM has work all the time: with
-  // fewer pictures than chains, every block gets one picture before any block gets two; the most expensive pictures
-  // (lowest QP) run alone, the others are paired expensive-with-cheap.  Pictures beyond the first round are pulled
-  // from the queue in submit order.
+  // Work distribution.  A chain is busy for a whole picture (seconds) and an SM delivers about the same instruction
+  // throughput to one chain as to two aligned ones, so what matters is that every SM has work all the
+  // time and that the blocks finish together.  First round (static): with fewer pictures than chains every block
+  // gets one picture before any block gets two; the most expensive pictures (lowest QP) run alone, the others are
+  // paired expensive-with-cheap (measured: 1131 ms against 1258 ms for "one each, then pull" and 1168 ms against
+  // 1218 ms for equal-cost pairs on 256 / 296 pictures of 416x240).  Pictures beyond the first round are pulled from
+  // the queue in cost order - a pair only while enough pictures are left for every block (see the kernel).
   const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
   int firstRound = 0;
   {
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; i++) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[a].sliceQp < sp[b2].sliceQp; });    // expensive first
-    c->hostAssign.assign((size_t)c->maxBlocks * FHC_PICS_PER_BLOCK, -1);
+    c->hostAssign.assign((size_t)c->maxBlocks * FHC_PICS_PER_BLOCK + (size_t)n, -1);
     firstRound = n < blocks * FHC_PICS_PER_BLOCK ? n : blocks * FHC_PICS_PER_BLOCK;
-    // the first-round pictures are the first `firstRound` of the submit (the queue hands out the rest in order)
-    std::vector<int> first;
-    for (int i = 0; i < n; i++) if (order[(size_t)i] < firstRound) first.push_back(order[(size_t)i]);
     const int pairs = firstRound - blocks > 0 ? firstRound - blocks : 0, singles = blocks - pairs;
+    const char* pe = getenv("FHC_PAIRING");                  // experiment switch: 0 extremes (default), 1 halves, 2 neighbours
+    const int pairing = pe ? atoi(pe) : 0;
     int lo = 0, hi = firstRound - 1;
     for (int bk = 0; bk < blocks; bk++)
     {
-      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = first[(size_t)lo++];
-      if (FHC_PICS_PER_BLOCK > 1 && bk >= singles) c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK + 1] = first[(size_t)hi--];
+      if (bk < singles || FHC_PICS_PER_BLOCK == 1) { c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = order[(size_t)lo++]; continue; }
+      const int k = bk - singles;
+      int a, b2;
+      if (pairing == 1) { a = singles + k; b2 = singles + pairs + k; }
+      else if (pairing == 2) { a = singles + 2 * k; b2 = a + 1; }
+      else { a = lo++; b2 = hi--; }
+      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = order[(size_t)a];
+      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK + 1] = order[(size_t)b2];
     }
+    // the queue hands out the remaining pictures in cost order: queue position q -> picture order[q]
+    for (int i = 0; i < n; i++) c->hostAssign[(size_t)c->maxBlocks * FHC_PICS_PER_BLOCK + i] = order[(size_t)i];
   }
   // (both small copies go through the copy stream: pageable sources are staged before the call returns, and the copy
   // stream is never behind a running kernel)
   c->hostQueueStart = firstRound;
-  CK(cudaMemcpyAsync(bt->dAssign, c->hostAssign.data(), sizeof(int) * (size_t)blocks * FHC_PICS_PER_BLOCK, cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaMemcpyAsync(bt->dAssign, c->hostAssign.data(), sizeof(int) * c->hostAssign.size(), cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaMemcpyAsync(bt->dQueue, &c->hostQueueStart, sizeof(int), cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
   CK(cudaEventRecord(bt->evStart, c->compute));
-  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, bt->dAssign, c->dWorkspace,
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, bt->dAssign, bt->dAssign + (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK, c->dWorkspace,
                                                                                             c->wsPerBlock, c->smemBytes, c->dTables);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));

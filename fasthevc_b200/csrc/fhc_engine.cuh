@@ -222,7 +222,7 @@ struct Blk                        // shared memory of a block
 {
   Tables t;
   PicParams pp;
-  int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY, picIndex;
+  int ctuAddr, ctuX, ctuY, ctuPelX, ctuPelY, picIndex, picIndex2;
   int16_t src[6144];              // source CTU, yuv layout of a 64x64 CU
   int16_t pic[6144];              // best-so-far reconstruction of the CTU ("picture" as the search sees it)
   int16_t topY[1 + 128], topC[2][1 + 64];     // row above the CTU, x = -1 .. 127 (luma)
@@ -536,10 +536,56 @@ FHC_DH int pred_sample(const Tables& t, const int16_t* line, int n, int log2n, i
   }
 }
 
-// the one shared copy of the predictor (keeps the instruction footprint small: the kernel is bound by instruction delivery)
-FHC_D int pred_sample_call(const Tables& t, const int16_t* line, int n, int log2n, int mode, int x, int y, int isLuma, int bd, int dcval)
+// The same predictor with everything that depends only on (mode, block size) hoisted out of the sample loop.
+struct PredMode { int kind, s, angle, invAngle, edge, shift; };    // kind: 0 planar, 1 DC, 2 pure horizontal / vertical, 3 angular
+FHC_DH PredMode pred_mode(const Tables& t, int mode, int n, int log2n, int isLuma)
 {
-  return pred_sample(t, line, n, log2n, mode, x, y, isLuma, bd, dcval);
+  PredMode p;
+  p.edge = isLuma && n <= 16; p.shift = log2n + 1; p.s = 1; p.angle = 0; p.invAngle = 0;
+  if (mode == PLANAR_IDX) { p.kind = 0; return p; }
+  if (mode == DC_IDX) { p.kind = 1; return p; }
+  const int isVer = mode >= 18;
+  const int angMode = isVer ? mode - VER_IDX : -(mode - HOR_IDX);
+  const int absA = iabs(angMode);
+  p.angle = angMode < 0 ? -t.angTable[absA] : t.angTable[absA];
+  p.invAngle = t.invAngTable[absA];
+  p.s = isVer ? 1 : -1;
+  p.kind = p.angle == 0 ? 2 : 3;
+  return p;
+}
+FHC_DH int pred_at(const PredMode& p, const int16_t* line, int n, int x, int y, int bd, int dcval)
+{
+  const int c = 2 * n;
+  if (p.kind == 0)
+  {
+    const int left = line[c - 1 - y], top = line[c + 1 + x], topRight = line[c + 1 + n], bottomLeft = line[c - 1 - n];
+    return ((n - 1 - x) * left + (x + 1) * topRight + (n - 1 - y) * top + (y + 1) * bottomLeft + n) >> p.shift;
+  }
+  if (p.kind == 1)
+  {
+    if (p.edge)
+    {
+      if (x == 0 && y == 0) return (line[c + 1] + line[c - 1] + 2 * dcval + 2) >> 2;
+      if (y == 0) return (line[c + 1 + x] + 3 * dcval + 2) >> 2;
+      if (x == 0) return (line[c - 1 - y] + 3 * dcval + 2) >> 2;
+    }
+    return dcval;
+  }
+  const int s = p.s;                                  // main(k) = line[c + s*k], side(j) = line[c - s*j]
+  const int u = s > 0 ? x : y, v = s > 0 ? y : x;
+  if (p.kind == 2)
+  {
+    int val = line[c + s * (u + 1)];
+    if (p.edge && u == 0) val = clip3(0, (1 << bd) - 1, val + ((line[c - s * (v + 1)] - line[c]) >> 1));
+    return val;
+  }
+  const int deltaPos = (v + 1) * p.angle, deltaInt = deltaPos >> 5, fract = deltaPos & 31;
+  const int k0 = u + deltaInt + 1;
+  const int a = (k0 >= 0) ? line[c + s * k0] : line[c - s * ((128 + (-k0) * p.invAngle) >> 8)];
+  if (!fract) return a;
+  const int k1 = k0 + 1;
+  const int bb = (k1 >= 0) ? line[c + s * k1] : line[c - s * ((128 + (-k1) * p.invAngle) >> 8)];
+  return ((32 - fract) * a + fract * bb + 16) >> 5;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1285,10 +1331,11 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   gsync(g);                                                            // every lane has consumed the accumulators of the previous TU
   if (g.gl == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; }
   // prediction + residual -> B
+  const PredMode pm = pred_mode(t, a.mode, n, log2n, comp == 0);
   FHC_GLANES(g, i, n2)
   {
     const int x = i & (n - 1), y = i >> log2n;
-    const int v = pred_sample_call(t, line, n, log2n, a.mode, x, y, comp == 0, bd, a.dcVal);
+    const int v = pred_at(pm, line, n, x, y, bd, a.dcVal);
     a.rec[y * a.recStride + x] = (int16_t)v;
     s.B[i] = src[y * a.srcStride + x] - v;
   }
@@ -1758,12 +1805,14 @@ FHC_D void rmd_satd(Blk* b, Role* r, int log2n, int x0, int y0)
     FHC_NOUNROLL for (int mode = 0; mode < 35; mode++)
     {
       const int16_t* line = use_filtered_refs(t, 0, mode, log2n) ? r->refF : r->refU;
+      const PredMode pm = pred_mode(t, mode, n, log2n, 1);
+      const int dcv = r->dcVal;
       uint32_t total = 0;
       FHC_NOUNROLL for (int tile = 0; tile < tiles; tile++)
       {
         const int x = ((tile & ((1 << ltpr) - 1)) << 3) + c, y = ((tile >> ltpr) << 3) + rr;
-        int a = src[y * 64 + x] - pred_sample_call(t, line, n, log2n, mode, x, y, 1, bd, r->dcVal);
-        int bb = src[(y + 4) * 64 + x] - pred_sample_call(t, line, n, log2n, mode, x, y + 4, 1, bd, r->dcVal);
+        int a = src[y * 64 + x] - pred_at(pm, line, n, x, y, bd, dcv);
+        int bb = src[(y + 4) * 64 + x] - pred_at(pm, line, n, x, y + 4, bd, dcv);
         // rows: across the 8 lanes of a row
 #pragma unroll
         for (int k = 1; k < 8; k <<= 1)
@@ -1796,7 +1845,8 @@ FHC_D void rmd_satd(Blk* b, Role* r, int log2n, int x0, int y0)
     FHC_NOUNROLL for (int m0 = 0; m0 < 35; m0 += 2)
     {
       const int mode = imin(m0 + half, 34);
-      int a = src[y * 64 + x] - pred_sample_call(t, r->refU, 4, 2, mode, x, y, 1, bd, r->dcVal);
+      const PredMode pm = pred_mode(t, mode, 4, 2, 1);
+      int a = src[y * 64 + x] - pred_at(pm, r->refU, 4, x, y, bd, r->dcVal);
 #pragma unroll
       for (int k = 1; k < 16; k <<= 1)
       {

@@ -65,6 +65,8 @@ if __name__ == "__main__":
         perf(416, 240, 296, [22, 27, 32, 37])
     if "ncucase" in what:
         perf(136, 72, 296, [22, 27, 32, 37])
+    if "ncucase2" in what:
+        perf(416, 240, 296, [22, 27, 32, 37])
     if "perf256" in what:
         perf(416, 240, 256, [22, 27, 32, 37])
         # QP-major order as in bench.py
