@@ -30,12 +30,14 @@
 #ifdef FHC_DEVICE_BUILD
 #define FHC_DH __device__ __forceinline__
 #define FHC_D __device__ __noinline__
+#define FHC_SHARED(p) __builtin_assume(__isShared(p))      // address-space hint: the pointer is in shared memory (LDS / STS instead of generic accesses)
 #define FHC_LANE ((int)(threadIdx.x & 31))
 #define FHC_NL 32
 #define FHC_NOUNROLL _Pragma("unroll 1")
 #else
 #define FHC_DH static inline
 #define FHC_D static
+#define FHC_SHARED(p) ((void)0)
 #define FHC_LANE 0
 #define FHC_NL 1
 #define FHC_NOUNROLL
@@ -407,6 +409,7 @@ FHC_DH RefAvail ref_avail(const Blk* b, int comp, int n, int x0, int y0)
 // the group's lanes; optionally the smoothed copy (TComPattern.cpp:191-296).  Returns the DC value of the unfiltered line.
 FHC_D int build_refs(const Blk* b, const Grp& g, const RecView& v, int comp, int n, int x0, int y0, int wantFilt, int16_t* refU, int16_t* refF)
 {
+  FHC_SHARED(b);
   const RefAvail a = ref_avail(b, comp, n, x0, y0);
   const int total = 4 * n + 1;
   const int dc = 1 << (b->pp.bitDepth - 1);
@@ -611,14 +614,6 @@ FHC_DH int inv_quant_scale(int rem) { return rem == 0 ? 40 : rem == 1 ? 45 : rem
 // ----------------------------------------------------------------------------------------------
 // coefficient-level context derivation (TComTrQuant.cpp:2672-2760, TComChromaFormat.cpp:100-160)
 // ----------------------------------------------------------------------------------------------
-FHC_DH int sig_ctx_inc(const Tables& t, int pat, int firstCtx, int rasterPos, int log2n, int isChroma)
-{
-  if (rasterPos == 0) return 0;
-  if (log2n == 2) return firstCtx + t.ctxIndMap4x4[rasterPos];
-  const int posY = rasterPos >> log2n, posX = rasterPos - (posY << log2n);
-  const int cnt = t.sigCnt[pat][((posY & 3) << 2) | (posX & 3)];
-  return firstCtx + ((((posX | posY) >> 2) != 0 && !isChroma) ? 3 : 0) + cnt;
-}
 FHC_DH int first_sig_ctx(int log2n, int scanType, int isChroma)
 {
   if (log2n == 2) return 0;
@@ -689,6 +684,7 @@ FHC_DH void code_remain(Coder& e, uint32_t symbol, uint32_t rParam)             
 FHC_D void code_coeff_serial(Coder& eio, const int16_t* coef, int log2n, int isChroma, int scanType, int tsFlag, const uint16_t* nzMask)
 {
   Coder e = eio;                                                      // registers inside this call
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   const Tables& t = *e.t;
   const int n = 1 << log2n, log2wg = log2n - 2, wg = n >> 2;
   const uint16_t* scan = scan_tab(t, scanType, log2n);
@@ -734,13 +730,15 @@ FHC_D void code_coeff_serial(Coder& eio, const int16_t* coef, int log2n, int isC
       // sig_coeff_flag of the positions below the last one; the flag at position 0 of a group is inferred when it is
       // the group's only non-zero candidate (no non-zero above it) - except in the DC group
       const int pat = pattern_sig_ctx(cgFlags, cgX, cgY, log2wg);
+      const uint8_t* sigRow = t.sigScan[scanType][log2n == 2 ? 4 : pat];
+      const int sigAdd = sigBase + firstSig + ((log2n != 2 && cgBlk != 0 && !isChroma) ? 3 : 0);
       int p = (subSet == lastScanSet) ? (scanPosLast - subPos - 1) : 15;
       uint32_t above = (subSet == lastScanSet) ? 1u : 0u;       // a non-zero coefficient was seen in this group
       FHC_NOUNROLL for (; p >= 0; p--)
       {
         const int sig = (int)((cgMask >> p) & 1u);
         if (p > 0 || subSet == 0 || above)
-          enc_bin(e, sigBase + sig_ctx_inc(t, pat, firstSig, scan[subPos + p], log2n, isChroma), sig);
+          enc_bin(e, (subPos + p) ? sigAdd + sigRow[p] : sigBase, sig);
         above |= (uint32_t)sig;
       }
     }
@@ -848,6 +846,7 @@ FHC_DH int pk_nosig(int pk) { return (pk >> 19) & 1; }
 struct RdoqState { double blockUncoded, baseCost; int cgLastScanPos, lastScanPos; uint64_t cgFlags; };
 FHC_D int ic_rate_call(const Tables& t, const Sbac* go, uint32_t absLevel, int ctxOne, int ctxAbs, uint32_t goRice, int c1Lt8, int c2Lt1)
 {
+  FHC_SHARED(go); FHC_SHARED(&t);
   return ic_rate(t, go, absLevel, ctxOne, ctxAbs, goRice, c1Lt8, c2Lt1);
 }
 
@@ -856,6 +855,7 @@ FHC_D int ic_rate_call(const Tables& t, const Sbac* go, uint32_t absLevel, int c
 FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, const int16_t* coef,
                         const double* costCGSig, const RdoqState& st)
 {
+  FHC_SHARED(b); FHC_SHARED(go);
   const Tables& t = b->t;
   const int log2n = q.log2n, isChroma = q.isChroma, n = 1 << log2n, qBits = q.qBits;
   const double errScale = q.errScale, lambda = q.lambda;
@@ -925,6 +925,7 @@ FHC_D int rdoq_last_pos(const Blk* b, const Sbac* go, const RdoqIn& q, const int
 // sign bit hiding (TComTrQuant.cpp:2530-2660); rate increments of level +-1 are re-evaluated from the packed coder state
 FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, const int32_t* B, int16_t* coef, uint32_t* cgInfo, int numCodedCG)
 {
+  FHC_SHARED(b); FHC_SHARED(go);
   const Tables& t = b->t;
   const int log2n = q.log2n, isChroma = q.isChroma, qBits = q.qBits;
   const double lambda = q.lambda;
@@ -1005,6 +1006,7 @@ FHC_D void rdoq_sbh(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t
 FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const int32_t* A, int32_t* B, int16_t* coef, double* costCGSig,
                            uint32_t cgNZ0, uint32_t cgNZ1)
 {
+  FHC_SHARED(b); FHC_SHARED(go);
   const Tables& t = b->t;
   const int log2n = q.log2n, isChroma = q.isChroma, n = 1 << log2n, numCoef = n * n, log2wg = log2n - 2;
   const int qBits = q.qBits;
@@ -1016,7 +1018,7 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
   const int sigBase = CTX_SIG + (isChroma ? 28 : 0);
   const int cgBase = CTX_SIGCG + (isChroma ? 2 : 0);
   double blockUncoded = 0, baseCost = 0;
-  int cgLastScanPos = -1, lastScanPos = -1, c1 = 1, c2 = 0;
+  int cgLastScanPos = -1, lastScanPos = -1, c1 = 1, c2 = 0, stPack = 0;   // stPack: the coder state as it is stored in B[] (bits 0..12)
   uint32_t ctxSet = 0, c1Idx = 0, c2Idx = 0, goRice = 0;
   uint64_t cgFlags = 0;
 
@@ -1042,6 +1044,9 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
       continue;
     }
     const int pat = pattern_sig_ctx(cgFlags, cgX, cgY, log2wg);
+    // sig_coeff_flag context increment of position p of this group = sigAdd + sigRow[p] (0 for the DC coefficient)
+    const uint8_t* sigRow = t.sigScan[q.scanType][log2n == 2 ? 4 : pat];
+    const int sigAdd = firstSig + ((log2n != 2 && cgBlk != 0 && !isChroma) ? 3 : 0);
     double sigCost = 0, sigCost0 = 0, codedLevelAndDist = 0, uncodedDist = 0;
     int nnzBeforePos0 = 0, cgHasLevel = 0;
     FHC_NOUNROLL for (int posInCG = 15; posInCG >= 0; posInCG--)
@@ -1060,56 +1065,68 @@ FHC_D uint32_t rdoq_serial(const Blk* b, const Sbac* go, const RdoqIn& q, const 
         lastScanPos = scanPos;
         ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && (scanPos >> 4) > 0) ? 2 : 0));
         cgLastScanPos = cgScanPos;
+        stPack = (int)(4 * ctxSet + 1) | ((int)ctxSet << 5) | (3 << 11);   // c1 = 1, c2 = 0, goRice = 0, c1Idx < 8, c2Idx < 1
       }
       const int isLast = scanPos == lastScanPos;
-      const int ctxOne = CTX_ONE + 4 * (int)ctxSet + c1, ctxAbs = CTX_ABS + (int)ctxSet + c2;
-      const int sc = isLast ? 0 : sig_ctx_inc(t, pat, firstSig, blkPos, log2n, isChroma);
-      B[scanPos] = (ctxOne - CTX_ONE) | ((ctxAbs - CTX_ABS) << 5) | ((int)goRice << 8) | ((c1Idx < 8) << 11) | ((c2Idx < 1) << 12) | (sc << 13) | (isLast << 19);
-      // xGetCodedLevel (TComTrQuant.cpp:2812)
-      double codedCost, codedCostSig = 0;
-      uint32_t level = 0;
-      if (!isLast && maxAbsLevel < 3)
+      const int sc = (isLast || scanPos == 0) ? 0 : sigAdd + sigRow[posInCG];
+      B[scanPos] = stPack | (sc << 13) | (isLast << 19);
+      if (maxAbsLevel == 0)
       {
-        codedCostSig = dmul(lambda, (double)ctx_bits(t, go, sigBase + sc, 0));
-        codedCost = dadd(c0, codedCostSig);
+        // level 0 (never the last position): only the significance flag is paid for; the coder state does not move
+        const double s0 = dmul(lambda, (double)ctx_bits(t, go, sigBase + sc, 0));
+        coef[blkPos] = 0;
+        baseCost = dadd(baseCost, dadd(c0, s0));
+        sigCost = dadd(sigCost, s0);
+        if (posInCG == 0) sigCost0 = s0;
       }
-      else codedCost = FHC_MAX_COST;
-      if (maxAbsLevel != 0)
+      else
       {
-        const double currCostSig = isLast ? 0.0 : dmul(lambda, (double)ctx_bits(t, go, sigBase + sc, 1));
-        const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
-        FHC_NOUNROLL for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
+        const int ctxOne = CTX_ONE + 4 * (int)ctxSet + c1, ctxAbs = CTX_ABS + (int)ctxSet + c2;
+        // xGetCodedLevel (TComTrQuant.cpp:2812)
+        double codedCost, codedCostSig = 0;
+        uint32_t level = 0;
+        if (!isLast && maxAbsLevel < 3)
         {
-          const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
-          double cur = dadd(dmul(dmul(err, err), errScale),
-                            dmul(lambda, (double)ic_rate(t, go, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx < 8, c2Idx < 1)));
-          cur = dadd(cur, currCostSig);
-          if (cur < codedCost) { level = (uint32_t)absLevel; codedCost = cur; codedCostSig = currCostSig; }
+          codedCostSig = dmul(lambda, (double)ctx_bits(t, go, sigBase + sc, 0));
+          codedCost = dadd(c0, codedCostSig);
+        }
+        else codedCost = FHC_MAX_COST;
+        {
+          const double currCostSig = isLast ? 0.0 : dmul(lambda, (double)ctx_bits(t, go, sigBase + sc, 1));
+          const uint32_t minAbs = maxAbsLevel > 1 ? maxAbsLevel - 1 : 1;
+          FHC_NOUNROLL for (int absLevel = (int)maxAbsLevel; absLevel >= (int)minAbs; absLevel--)
+          {
+            const double err = (double)(levelDouble - (int)((uint32_t)absLevel << qBits));
+            double cur = dadd(dmul(dmul(err, err), errScale),
+                              dmul(lambda, (double)ic_rate(t, go, (uint32_t)absLevel, ctxOne, ctxAbs, goRice, c1Idx < 8, c2Idx < 1)));
+            cur = dadd(cur, currCostSig);
+            if (cur < codedCost) { level = (uint32_t)absLevel; codedCost = cur; codedCostSig = currCostSig; }
+          }
+        }
+        coef[blkPos] = (int16_t)level;
+        baseCost = dadd(baseCost, codedCost);
+        sigCost = dadd(sigCost, codedCostSig);
+        if (posInCG == 0) sigCost0 = codedCostSig;
+        if (level)
+        {
+          const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
+          if ((int)level >= baseLevel)
+            if (level > 3u * (1u << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
+          c1Idx++;
+          if (level > 1) { c1 = 0; c2 += (c2 < 2); c2Idx++; }
+          else if (c1 < 3 && c1 > 0) c1++;
+          stPack = (4 * (int)ctxSet + c1) | (((int)ctxSet + c2) << 5) | ((int)goRice << 8) | ((c1Idx < 8) << 11) | ((c2Idx < 1) << 12);
+          cgHasLevel = 1;
+          codedLevelAndDist = dadd(codedLevelAndDist, dsub(codedCost, codedCostSig));
+          uncodedDist = dadd(uncodedDist, c0);
+          if (posInCG != 0) nnzBeforePos0++;
         }
       }
-      coef[blkPos] = (int16_t)level;
-      baseCost = dadd(baseCost, codedCost);
+      if (posInCG == 0 && scanPos > 0)
       {
-        const int baseLevel = (c1Idx < 8) ? (2 + (c2Idx < 1)) : 1;
-        if ((int)level >= baseLevel)
-          if (level > 3u * (1u << goRice)) goRice = goRice + 1 < 4 ? goRice + 1 : 4;
-        if (level >= 1) c1Idx++;
-        if (level > 1) { c1 = 0; c2 += (c2 < 2); c2Idx++; }
-        else if (c1 < 3 && c1 > 0 && level) c1++;
-        if ((scanPos & 15) == 0 && scanPos > 0)
-        {
-          ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && ((scanPos - 1) >> 4) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
-          c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
-        }
-      }
-      sigCost = dadd(sigCost, codedCostSig);
-      if (posInCG == 0) sigCost0 = codedCostSig;
-      if (level)
-      {
-        cgHasLevel = 1;
-        codedLevelAndDist = dadd(codedLevelAndDist, dsub(codedCost, codedCostSig));
-        uncodedDist = dadd(uncodedDist, c0);
-        if (posInCG != 0) nnzBeforePos0++;
+        ctxSet = (uint32_t)((isChroma ? 4 : 0) + ((!isChroma && ((scanPos - 1) >> 4) > 0) ? 2 : 0) + (c1 == 0 ? 1 : 0));
+        c1 = 1; c2 = 0; c1Idx = 0; c2Idx = 0; goRice = 0;
+        stPack = (int)(4 * ctxSet + 1) | ((int)ctxSet << 5) | (3 << 11);
       }
     }
     if (cgLastScanPos >= 0)
@@ -1212,6 +1229,7 @@ FHC_DH GScr group_scratch(const Role* r, int idx, int planeStride)
   s.meta = r->gMeta + (idx < 5 ? idx : 0) * 4 * r->np;
   if (idx >= 5) idx = 0;                           // only the (at most five) chroma / 64x64 groups build reference lines of their own
   s.refU = r->gRefU + idx * r->refCap; s.refF = r->gRefF + idx * r->refCap;
+  FHC_SHARED(s.go); FHC_SHARED(s.acc);
   return s;
 }
 
@@ -1239,6 +1257,7 @@ FHC_DH int tmat_at(const Tables& t, int n, int useDst, int k, int q)
 FHC_D void mat_stage(const Grp& g, int log2n, const int16_t* mbase, int mHi, int mLo, int ms, const int32_t* ibase, int iHi, int iLo, int is,
                      int32_t* out, int add, int shift, int clip)
 {
+  FHC_SHARED(mbase);
   const int n = 1 << log2n, n2 = n * n;
   FHC_GLANES(g, i, n2)
   {
@@ -1275,6 +1294,7 @@ FHC_D void fold_stage(const Grp& g, int log2n, int32_t* buf, int sa, int sq)
 FHC_D void fwd_stage(const Grp& g, int log2n, int kIsLo, const int16_t* mbase, int mk, int mq, const int32_t* in, int ia, int iq,
                      int32_t* out, int add, int shift)
 {
+  FHC_SHARED(mbase);
   const int n = 1 << log2n, n2 = n * n, half = n >> 1;
   FHC_GLANES(g, i, n2)
   {
@@ -1294,6 +1314,7 @@ FHC_D void fwd_stage(const Grp& g, int log2n, int kIsLo, const int16_t* mbase, i
 // the even / odd rows k of M(k, i) * in[k][j]  (xITrMxN, TComTrQuant.cpp:927; partialButterflyInverse*, :476-840).
 FHC_D void inv_stage(const Grp& g, int log2n, const int16_t* mat, int rs, const int32_t* in, int32_t* out, int add, int shift)
 {
+  FHC_SHARED(mat);
   const int n = 1 << log2n, half = n >> 1;
   FHC_GLANES(g, idx, n * half)
   {
@@ -1314,7 +1335,11 @@ FHC_D void inv_stage(const Grp& g, int log2n, const int16_t* mat, int rs, const 
 // return the same values.
 FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int* cbfOut)
 {
+  FHC_SHARED(b);
   const Tables& t = b->t;
+  Sbac* const sgo = s.go;
+  uint32_t* const sacc = s.acc;
+  FHC_SHARED(sgo); FHC_SHARED(sacc);
   const int comp = a.comp, log2n = a.log2n, n = 1 << log2n, n2 = n * n, bd = b->pp.bitDepth, isChroma = comp != 0;
   const int useDst = (comp == 0 && log2n == 2);
   const int16_t* line = use_filtered_refs(t, comp, a.mode, log2n) ? a.refF : a.refU;
@@ -1329,7 +1354,7 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
   {
   FHC_COUNT(if (g.gl == 0) { g_emuCounters.tqSamples[isChroma][log2n - 2] += (unsigned)n2; g_emuCounters.tuCalls[isChroma][log2n - 2]++; });
   gsync(g);                                                            // every lane has consumed the accumulators of the previous TU
-  if (g.gl == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; }
+  if (g.gl == 0) { sacc[0] = 0; sacc[1] = 0; sacc[2] = 0; }
   // prediction + residual -> B
   const PredMode pm = pred_mode(t, a.mode, n, log2n, comp == 0);
   FHC_GLANES(g, i, n2)
@@ -1381,7 +1406,7 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
       const int64_t tl = (int64_t)iabs(c) * quantCoef;
       const int ld = (int)(tl < cap ? tl : cap);
       s.A[p] = c < 0 ? -ld : ld;
-      if ((ld + (1 << (qBits - 1))) >> qBits) gor_u32(g, &s.acc[1 + (p >> 9)], 1u << ((p >> 4) & 31));
+      if ((ld + (1 << (qBits - 1))) >> qBits) gor_u32(g, &sacc[1 + (p >> 9)], 1u << ((p >> 4) & 31));
     }
   }
   gsync(g);
@@ -1392,12 +1417,12 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
     RdoqIn q;
     q.log2n = log2n; q.isChroma = isChroma; q.scanType = a.scanType; q.cbfCtx = a.cbfCtx; q.qBits = qBits; q.per = qp.per; q.rem = qp.rem; q.bd = bd;
     q.lambda = b->pp.sp.rdoqLambda[comp]; q.errScale = t.errScale[isChroma][log2n - 2][qp.rem];
-    s.acc[3] = rdoq_serial(b, s.go, q, s.A, s.B, a.coef, s.cgCost, s.acc[1], s.acc[2]);
+    sacc[3] = rdoq_serial(b, sgo, q, s.A, s.B, a.coef, s.cgCost, sacc[1], sacc[2]);
   }
   if (a.alignRole >= 0) twin_align(b, a.alignRole);
   if (!(a.phases & TU_BACK)) return 0;
   gsync(g);
-  const int coded = s.acc[3] > 0;
+  const int coded = sacc[3] > 0;
   if (coded)
   {
     // xDeQuant (TComTrQuant.cpp:1308, flat scaling) -> A (raster)
@@ -1454,10 +1479,10 @@ FHC_D uint32_t tu_eval(Blk* b, const Grp& g, const GScr& s, const TuArgs& a, int
       const int d = v - src[y * a.srcStride + x];
       acc += (uint32_t)((d * d) >> shift);
     }
-    if (acc) gadd_u32(g, &s.acc[0], acc);
+    if (acc) gadd_u32(g, &sacc[0], acc);
   }
   gsync(g);
-  uint32_t dist = s.acc[0];
+  uint32_t dist = sacc[0];
   if (isChroma) dist = (uint32_t)dmul(b->pp.sp.chromaDistWeight[comp - 1], (double)dist);
   *cbfOut = coded;
   return dist;
@@ -1488,6 +1513,7 @@ FHC_DH int chroma_pred_mode(const Hyp& h) { return h.cdir == DM_CHROMA_IDX ? h.l
 // luma partitions = luma coefficient groups; every 4th one also does the co-located chroma groups).
 FHC_D void nz_masks_range(const Tables& t, const Grp& g, const Hyp& h, int p0, int cnt, int doLuma, int doChroma)
 {
+  FHC_SHARED(&t);
   FHC_GLANES(g, k, cnt)
   {
     const int p = p0 + k;
@@ -1528,6 +1554,7 @@ FHC_D void nz_masks_range(const Tables& t, const Grp& g, const Hyp& h, int p0, i
 // partitions [cuZ, cuZ + cuNp); its own luma modes are cuLdir[pu].  Returns *piMode (1 or 2: the number of MPMs HM appends).
 FHC_D int get_mpm(const Blk* b, int cuZ, int cuNp, int isNxN, const uint8_t* cuLdir, int zabs, int mpm[3])
 {
+  FHC_SHARED(b);
   const Tables& t = b->t;
   const int r = t.z2r[zabs];
   int l, a;
@@ -1622,6 +1649,7 @@ FHC_DH void code_coeff_of(Coder& e, const Hyp& h, int comp, int p, int log2n)   
 FHC_D void enc_subdiv_cbf(Coder& eio, const Hyp& h, int p0, int t0, int bLuma, int bChroma)
 {
   Coder e = eio;
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   const int cnt = h.np >> (2 * t0);
   FHC_NOUNROLL for (int p = p0; p < p0 + cnt;)
   {
@@ -1644,6 +1672,7 @@ FHC_D void enc_subdiv_cbf(Coder& eio, const Hyp& h, int p0, int t0, int bLuma, i
 FHC_D void enc_coeff_qt(Coder& eio, const Hyp& h, int p0, int t0, int comp)
 {
   Coder e = eio;
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   const int cnt = h.np >> (2 * t0);
   FHC_NOUNROLL for (int p = p0; p < p0 + cnt;)
   {
@@ -1679,7 +1708,9 @@ FHC_DH void enc_intra_header_luma(Coder& e, const Blk* b, const Hyp& h, int cuZ,
 // xGetIntraBitsQT, luma only (TEncSearch.cpp:1067)
 FHC_D uint32_t intra_bits_luma(Coder& eio, const Blk* b, const Hyp& h, int cuZ, int p0, int t0)
 {
+  FHC_SHARED(b);
   Coder e = eio;
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   reset_bits(e);
   enc_intra_header_luma(e, b, h, cuZ, p0, t0);
   enc_subdiv_cbf(e, h, p0, t0, 1, 0);
@@ -1691,6 +1722,7 @@ FHC_D uint32_t intra_bits_luma(Coder& eio, const Blk* b, const Hyp& h, int cuZ, 
 FHC_D uint32_t intra_bits_chroma(Coder& eio, const Hyp& h)
 {
   Coder e = eio;
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   reset_bits(e);
   code_chroma_dir(e, h.cdir);
   enc_subdiv_cbf(e, h, 0, 0, 0, 1);
@@ -1704,7 +1736,9 @@ FHC_D uint32_t intra_bits_chroma(Coder& eio, const Hyp& h)
 // luma area goes with the LAST quadrant here.
 FHC_D void encode_cu_syntax(Coder& eio, const Blk* b, const Hyp& h, int cuZ)
 {
+  FHC_SHARED(b);
   Coder e = eio;
+  FHC_SHARED(e.sb); FHC_SHARED(e.t);
   if (h.depth == 3) enc_bin(e, CTX_PART, h.partSize == SIZE_2Nx2N ? 1 : 0);
   {
     const int numPU = h.partSize == SIZE_NxN ? 4 : 1;
@@ -1789,6 +1823,7 @@ static uint32_t had4_ref(const int* d)
 
 FHC_D void rmd_satd(Blk* b, Role* r, int log2n, int x0, int y0)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const int n = 1 << log2n, bd = b->pp.bitDepth;
   const int16_t* src = b->src + y0 * 64 + x0;
@@ -1894,6 +1929,7 @@ FHC_D void rmd_satd(Blk* b, Role* r, int log2n, int x0, int y0)
 // stable sort by cost) plus the first 1 or 2 MPMs (TEncSearch.cpp:2297-2320).  r->cand[], r->numCand.
 FHC_D void rmd_candidates(Blk* b, Role* r, int pu, int log2pu)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const int isNxN = r->partSize == SIZE_NxN;
   const int zabs = r->zidx + pu * (r->np >> 2) * (isNxN ? 1 : 0);
   int mpm[3];
@@ -1981,6 +2017,7 @@ FHC_DH Hyp hyp_of(const Role* r, const uint8_t* tridx, const uint8_t* cbf0, cons
 // ----------------------------------------------------------------------------------------------
 FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bestDist)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const Grp w = whole_warp();
   GScr s = group_scratch(r, 0, r->yuvSize);
@@ -2082,6 +2119,7 @@ FHC_D int second_pass(Blk* b, Role* r, int mode, double* bestCost, uint32_t* bes
 // ----------------------------------------------------------------------------------------------
 FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const Grp w = whole_warp();
   const int isNxN = r->partSize == SIZE_NxN, depth = r->depth, cuw = r->cuw;
@@ -2310,6 +2348,7 @@ FHC_D void search_luma_pu(Blk* b, Role* r, int pu)
 // ----------------------------------------------------------------------------------------------
 FHC_D void search_chroma(Blk* b, Role* r)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const int np = r->np, cuw = r->cuw, cw = cuw >> 1, depth = r->depth;
   int modeList[5];
@@ -2458,6 +2497,7 @@ FHC_D void search_chroma(Blk* b, Role* r)
 // ----------------------------------------------------------------------------------------------
 FHC_D void run_job(Blk* b, Role* r)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const Grp w = whole_warp();
   const int isNxN = r->partSize == SIZE_NxN, np = r->np;
@@ -2542,6 +2582,7 @@ FHC_DH void join_job(Blk* b, int ri)
 // the job's hypothesis becomes the best-so-far state of its region: copyToPic + xCopyYuv2Pic (TEncCu.cpp:1043-1045)
 FHC_D void commit_job(Blk* b, const Role* r)
 {
+  FHC_SHARED(b); FHC_SHARED(r);
   const Tables& t = b->t;
   const int cuw = r->cuw, np = r->np, z0 = r->zidx, isNxN = r->partSize == SIZE_NxN, lg = r->log2cu;
   fhc_ctu_result* o = &b->pp.out[b->ctuAddr];
@@ -2578,6 +2619,7 @@ FHC_DH void set_totals(Blk* b, int d, uint32_t dist, uint32_t bits, uint32_t bin
 template <int D>
 FHC_D void region(Blk* b, int z)
 {
+  FHC_SHARED(b);
   const Tables& t = b->t;
   const Grp w = whole_warp();
   const int W = b->pp.width, H = b->pp.height;
@@ -2678,6 +2720,7 @@ FHC_D void region(Blk* b, int z)
 // xEncodeCU on the finished CTU (TEncCu.cpp:1124-1228, called from TEncSlice.cpp:886-893): advances the chain coder
 FHC_D void encode_ctu(Blk* b)
 {
+  FHC_SHARED(b);
   const Tables& t = b->t;
   const Grp w = whole_warp();
   const int W = b->pp.width, H = b->pp.height;
@@ -2724,6 +2767,7 @@ FHC_D void encode_ctu(Blk* b)
 
 FHC_D void master_ctu(Blk* b)
 {
+  FHC_SHARED(b);
   region<0>(b, 0);
   trace_at(b->pp, b->ctuAddr, 0, 12);
 #ifdef FHC_DEVICE_BUILD
@@ -2742,6 +2786,7 @@ FHC_D void master_ctu(Blk* b)
 #ifdef FHC_DEVICE_BUILD
 FHC_D void role_loop(Blk* b, int ri)
 {
+  FHC_SHARED(b);
   for (;;)
   {
     trace_role(b->pp, ri, 100);
@@ -2830,6 +2875,7 @@ FHC_HD void block_footprint(size_t* smemBytes, size_t* globalBytes)
 // ----------------------------------------------------------------------------------------------
 FHC_D void load_ctu(Blk* b, int addr, int tid, int nthr)
 {
+  FHC_SHARED(b);
   const PicParams& pp = b->pp;
   const int W = pp.width, H = pp.height;
   const int cx = addr % pp.wc, cy = addr / pp.wc, x0 = cx * 64, y0 = cy * 64;
@@ -2874,6 +2920,7 @@ FHC_D void load_ctu(Blk* b, int addr, int tid, int nthr)
 
 FHC_D void store_ctu(Blk* b, int tid, int nthr)
 {
+  FHC_SHARED(b);
   const PicParams& pp = b->pp;
   const int W = pp.width, H = pp.height, x0 = b->ctuPelX, y0 = b->ctuPelY, cy = b->ctuY;
   fhc_ctu_result* o = &pp.out[b->ctuAddr];
@@ -2904,6 +2951,7 @@ FHC_D void store_ctu(Blk* b, int tid, int nthr)
 // after store_ctu and a block barrier: the CTU's right column becomes the left neighbour of the next CTU
 FHC_D void shift_left_neighbour(Blk* b, int tid, int nthr)
 {
+  FHC_SHARED(b);
   for (int i = tid; i < 128; i += nthr)
   {
     if (i < 64) b->leftY[i] = b->pic[i * 64 + 63];
@@ -2922,6 +2970,7 @@ FHC_D void shift_left_neighbour(Blk* b, int tid, int nthr)
 // ----------------------------------------------------------------------------------------------
 FHC_D void init_block(Blk* b, unsigned char* smemArena, unsigned char* globalArena)
 {
+  FHC_SHARED(b);
   Arena sm = { smemArena, 0 }, gm = { globalArena, 0 };
   for (int ri = 0; ri < FHC_ROLES; ri++) role_carve(&b->role[ri], ri, &sm, &gm);
 }
@@ -2931,6 +2980,7 @@ FHC_D void init_block(Blk* b, unsigned char* smemArena, unsigned char* globalAre
 // without a picture (pd == 0, odd tail of the queue) only takes part in the barriers.
 FHC_D void compress_picture(Blk* b, const PicDesc* pd, int numCtus, int tid, int nthr)
 {
+  FHC_SHARED(b);
   if (tid == 0 && pd)
   {
     PicParams& pp = b->pp;

@@ -45,6 +45,7 @@ struct Tables
   uint8_t  chromaScale[58];       // g_aucChromaScale[CHROMA_420]
   uint8_t  ctxIndMap4x4[16];
   uint8_t  sigCnt[4][16];         // getSigCtxInc neighbourhood term by (patternSigCtx, position inside the 4x4 group)
+  uint8_t  sigScan[3][5][16];     // the same by (scan type, patternSigCtx, position inside the group in SCAN order); row 4 = ctxIndMap4x4
   uint8_t  intraFilterThr[5];
   double   errScale[2][4][6];     // [chType][log2-2][qp rem]
 };
@@ -130,6 +131,13 @@ static void build_tables(Tables* t, int bitDepth)
         else cnt = 2;
         t->sigCnt[pat][yy * 4 + xx] = (uint8_t)cnt;
       }
+  for (int type = 0; type < 3; type++)
+    for (int i = 0; i < 16; i++)
+    {
+      const int pos = t->scan[t->scanOff[type][0] + i];                 // raster position inside the 4x4 group
+      for (int pat = 0; pat < 4; pat++) t->sigScan[type][pat][i] = t->sigCnt[pat][pos];
+      t->sigScan[type][4][i] = map4[pos];
+    }
   static const uint8_t thr[5] = { 10, 7, 1, 0, 10 };
   memcpy(t->intraFilterThr, thr, sizeof(thr));
   static const uint8_t nextMps[128] = {
