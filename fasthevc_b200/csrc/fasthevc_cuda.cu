@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <time.h>
 #include <algorithm>
+#include <math.h>
 #include <vector>
 #include "fhc_engine.cuh"
 
@@ -18,18 +19,55 @@ using namespace fhc;
 #define FHC_BATCHES 2                     /* submits that may be in flight: one running, one queued behind it */
 
 // ----------------------------------------------------------------------------------------------
-// kernel: persistent blocks, one picture at a time per block, pulled from a queue
+// kernel: persistent blocks; the unit of scheduling is one CTU row of one picture
+//
+// A picture is a sequential chain (CABAC contexts, neighbours), but nothing ties it to one SM: at a CTU row boundary
+// the chain consists of the contexts (PicState), the line buffers and the results, all in global memory.  After every
+// row a chain slot gives its picture back and takes the ready picture with the most work left (rows left x the
+// host's cost weight): the pictures that would finish last run all the time, the cheap ones fill the gaps, and the
+// blocks finish together.  The `lone` most expensive pictures are different: two chains of a block each run at
+// little more than half the speed of a lone one, and the longest pictures set the makespan - they stay
+// on the slot that takes them, alone in their block, until they are finished.
+// sched[SC_FINISHED] = finished pictures, sched[SC_WEIGHT + p] = cost weight of picture p | SC_LONE_BIT.
 // ----------------------------------------------------------------------------------------------
+enum { SC_FINISHED = 0, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
+enum { ST_READY = 0, ST_RUNNING = 1, ST_FINISHED = 2 };
+
+// picture index, -1 = nothing ready now, -2 = every picture is finished
+__device__ __forceinline__ int sched_take(PicState* states, int* sched, int numPics, int rowsPerPic, int allowLone, int* lone)
+{
+  for (;;)
+  {
+    int best = -1, bestLone = 0;
+    long long bestPrio = -1;
+    for (int p = 0; p < numPics; p++)
+    {
+      if (*reinterpret_cast<volatile int32_t*>(&states[p].status) != ST_READY) continue;
+      const int w = __ldg(sched + SC_WEIGHT + p), isLone = (w & SC_LONE_BIT) != 0;
+      if (isLone && !allowLone) continue;
+      const long long prio = (long long)(rowsPerPic - *reinterpret_cast<volatile int32_t*>(&states[p].nextRow)) * (w & (SC_LONE_BIT - 1)) + ((long long)isLone << 50);
+      if (prio > bestPrio) { bestPrio = prio; best = p; bestLone = isLone; }
+    }
+    if (best < 0) return *reinterpret_cast<volatile int*>(sched + SC_FINISHED) >= numPics ? -2 : -1;
+    if (atomicCAS(&states[best].status, ST_READY, ST_RUNNING) == ST_READY)
+    {
+      __threadfence();
+      *lone = bestLone;
+      return best;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
-fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const int* assign, const int* order, unsigned char* workspace,
-               size_t wsPerChain, size_t smemPerChain, const Tables* tables)
+fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPic, int ctusPerRow, int* sched, unsigned char* workspace, size_t wsPerChain,
+               size_t smemPerChain, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit;
   // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
   const int inst = threadIdx.x / FHC_INST_THREADS, tid = threadIdx.x - inst * FHC_INST_THREADS, nthr = FHC_INST_THREADS;
   unsigned char* mine = smem_raw + (size_t)inst * smemPerChain;
   Blk* b = reinterpret_cast<Blk*>(mine);
-  Blk* b0 = reinterpret_cast<Blk*>(smem_raw);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&b->t);
@@ -40,41 +78,65 @@ fhc_ctu_kernel(const PicDesc* pics, int numPics, int numCtus, int* queue, const 
     init_block(b, mine + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + ((size_t)blockIdx.x * FHC_PICS_PER_BLOCK + inst) * wsPerChain);
     b->inst = inst;
   }
+  if (threadIdx.x == 0) { sPinned = 0; sExit = 0; for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) sItem[k] = -1; }
   __syncthreads();
-  // first round: the host's balanced assignment (assign[block][chain], -1 = none); afterwards pictures come from the queue
-  for (int round = 0;; round++)
+  for (;;)
   {
-    int p;
-    if (round == 0) p = assign[blockIdx.x * FHC_PICS_PER_BLOCK + inst];
-    else
+    if (threadIdx.x == 0)
     {
-      // next picture(s) in cost order; a second one only while enough are left for every block to get one as well
-      if (threadIdx.x == 0)
+      for (;;)
       {
-        const int q0 = atomicAdd(queue, 1);
-        int q1 = numPics;
-        if (FHC_PICS_PER_BLOCK > 1 && q0 < numPics && numPics - q0 - 1 >= (int)gridDim.x) q1 = atomicAdd(queue, 1);
-        b0->picIndex = q0; b0->picIndex2 = q1;
+        int any = 0, never = 0;
+        for (int k = 0; k < FHC_PICS_PER_BLOCK; k++)
+        {
+          if (sPinned) { if (k == 0) any = 1; else sItem[k] = -1; continue; }      // slot 0 keeps its lone picture, the others stay empty
+          int lone = 0;
+          const int item = sched_take(states, sched, numPics, rowsPerPic, k == 0, &lone);
+          sItem[k] = item >= 0 ? item : -1;
+          if (item >= 0) { any = 1; if (lone) sPinned = 1; }
+          else if (item == -2) never = 1;
+        }
+        if (any) break;
+        if (never) { sExit = 1; break; }
+        __nanosleep(5000);
       }
-      __syncthreads();
-      const int q = inst == 0 ? b0->picIndex : b0->picIndex2;
-      if (b0->picIndex >= numPics) break;
-      p = q < numPics ? order[q] : -1;
     }
+    __syncthreads();
+    if (sExit) break;
+    const int p = sItem[inst];
     const PicDesc* pd = p >= 0 ? &pics[p] : nullptr;
-    if (tid == 0) b->active = pd != nullptr;
+    const int row = pd ? *reinterpret_cast<volatile int32_t*>(&states[p].nextRow) : 0;
+    // the chains of a block align their role warps at fixed points of a CTU's schedule; the schedule depends on the CTU's
+    // shape (cut off at the picture's bottom edge or not), so only chains on rows of the same kind are aligned
+    if (tid == 0) { b->active = pd != nullptr; sShape[inst] = pd ? (row + 1 == rowsPerPic) : -1; }
     __syncthreads();
     if (tid == 0)
     {
-      int n = 0;
-      for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) n += reinterpret_cast<Blk*>(smem_raw + (size_t)k * smemPerChain)->active;
-      b->twin = n > 1;
+      int n = 0, same = 1;
+      for (int k = 0; k < FHC_PICS_PER_BLOCK; k++)
+      {
+        n += reinterpret_cast<Blk*>(smem_raw + (size_t)k * smemPerChain)->active;
+        if (sShape[k] >= 0 && sShape[k] != sShape[inst]) same = 0;
+      }
+      b->twin = n > 1 && same;
     }
-    compress_picture(b, pd, numCtus, tid, nthr);
+    compress_picture(b, pd, row * ctusPerRow, ctusPerRow, tid, nthr);
     if (tid == 0 && pd)
     {
-      __threadfence_system();
-      *reinterpret_cast<volatile int32_t*>(pd->doneFlag) = 1;
+      if (row + 1 == rowsPerPic)
+      {
+        __threadfence_system();
+        *reinterpret_cast<volatile int32_t*>(pd->doneFlag) = 1;
+        *reinterpret_cast<volatile int32_t*>(&states[p].status) = ST_FINISHED;
+        __threadfence();
+        atomicAdd(sched + SC_FINISHED, 1);
+        if (inst == 0) sPinned = 0;
+      }
+      else
+      {
+        *reinterpret_cast<volatile int32_t*>(&states[p].nextRow) = row + 1;
+        if (!(inst == 0 && sPinned)) { __threadfence(); *reinterpret_cast<volatile int32_t*>(&states[p].status) = ST_READY; }
+      }
     }
     __syncthreads();
   }
@@ -111,8 +173,8 @@ struct Batch
   long long* dProf = nullptr;             // [maxFrames][64] cycle counters (FHC_PROFILE builds)
   int32_t* hTrace = nullptr;              // [maxFrames] mapped pinned host memory: progress words (FHC_TRACE=1 in the environment)
   int32_t* dTrace = nullptr;
-  int* dQueue = nullptr;
-  int* dAssign = nullptr;                 // [maxBlocks][FHC_PICS_PER_BLOCK] first-round pictures of every block
+  int* dSched = nullptr;                  // scheduler words + ring of ready rows (see the kernel)
+  PicState* dState = nullptr;             // [maxFrames] where every picture chain continues
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
   int firstPoc = 0, n = 0, launched = 0;
   uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
@@ -129,8 +191,7 @@ struct fhc_ctx
   Batch batch[FHC_BATCHES];
   uint64_t submits = 0;
   std::vector<PicDesc> hostPics;
-  std::vector<int> hostAssign;
-  int hostQueueStart = 0;
+  std::vector<int> hostSched;
 };
 
 const char* fhc_last_error(void) { return g_err; }
@@ -154,13 +215,14 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
   CK(cudaFuncSetAttribute(fhc_ctu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blockSmem));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fhc_ctu_kernel, FHC_BLOCK_THREADS, blockSmem));
   if (perSm < 1) { snprintf(g_err, sizeof(g_err), "kernel does not fit an SM (%zu bytes of shared memory)", blockSmem); return FHC_ERR_CUDA; }
+  if (const char* e = getenv("FHC_MAX_BLOCKS_PER_SM")) { const int cap = atoi(e); if (cap >= 1 && cap < perSm) perSm = cap; }   // experiments
   *maxBlocks = prop.multiProcessorCount * perSm;
   return FHC_OK;
 }
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dQueue); cudaFree(bt.dAssign); cudaFree(bt.dProf);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dProf);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -225,8 +287,8 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     CKG(cudaMalloc(&bt.dOut, sizeof(fhc_ctu_result) * (size_t)c->numCtus * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dLines, sizeof(int16_t) * 4 * (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
-    CKG(cudaMalloc(&bt.dQueue, sizeof(int)), fhc_destroy(c));
-    CKG(cudaMalloc(&bt.dAssign, sizeof(int) * (FHC_PICS_PER_BLOCK * (size_t)c->maxBlocks + (size_t)c->maxFrames)), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dSched, sizeof(int) * (SC_WEIGHT + (size_t)c->maxFrames)), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dState, sizeof(PicState) * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dProf, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMemset(bt.dProf, 0, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
@@ -270,7 +332,37 @@ static int ensure_input(fhc_ctx* c, Batch* bt, int sampleBytes)
   return FHC_OK;
 }
 
-// fills the picture queue and launches the persistent kernel on the compute stream
+// How many of the most expensive pictures run alone in their block (twin builds).  Two chains that share a block each
+// advance at FHC_TWIN_RATE of a lone chain's speed; the kernel finishes when the slowest picture does.  Cost model:
+// relative time of a picture by QP (measured on the bench clip: the time roughly halves every 12 QP steps).  Pick the
+// count that minimises max(longest lone picture, longest shared picture / rate, remaining work / remaining capacity).
+static double picture_weight(int qp) { return exp2((32.0 - qp) / 12.0); }
+static int lone_pictures(const fhc_slice_params* sp, const std::vector<int>& order, int n, int blocks)
+{
+  if (FHC_PICS_PER_BLOCK == 1) return 0;
+  if (const char* e = getenv("FHC_LONE")) { const int v = atoi(e); return v < 0 ? 0 : (v > blocks ? blocks : (v > n ? n : v)); }
+  const double rate = 0.59;
+  std::vector<double> w((size_t)n);
+  double total = 0;
+  for (int i = 0; i < n; i++) { w[(size_t)i] = picture_weight(sp[order[(size_t)i]].sliceQp); total += w[(size_t)i]; }
+  int best = 0;
+  double bestT = 1e300, loneWork = 0;
+  for (int k = 0; k <= n && k <= blocks; k++)
+  {
+    // k lone pictures on k blocks; the others share the remaining blocks, two chains each
+    double t = k ? w[0] : 0.0;
+    if (k < n)
+    {
+      if (k == blocks) break;
+      t = std::max(t, std::max(w[(size_t)k] / rate, (total - loneWork) / ((blocks - k) * 2 * rate)));
+    }
+    if (t < bestT - 1e-12) { bestT = t; best = k; }
+    if (k < n) loneWork += w[(size_t)k];
+  }
+  return best;
+}
+
+// fills the ring of ready rows and launches the persistent kernel on the compute stream
 static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, const fhc_slice_params* sp)
 {
   const int W = c->seq.width;
@@ -293,6 +385,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
     d.width = W; d.height = c->seq.height; d.bitDepth = c->seq.bitDepth; d.sampleBytes = sampleBytes;
     d.wc = (W + 63) / 64; d.hc = (c->seq.height + 63) / 64;
     d.doneFlag = bt->dFlags + i;
+    d.state = bt->dState + i;
     d.prof = bt->dProf + 64 * (size_t)i;
     bt->hFlags[i] = 0;
     if (bt->hTrace) { d.trace = bt->dTrace + 8 * i; memset(bt->hTrace + 8 * i, 0, 32); }
@@ -302,49 +395,30 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaMemcpyAsync(bt->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
-  // Work distribution.  A chain is busy for a whole picture (seconds) and an SM delivers about the same instruction
-  // throughput to one chain as to two aligned ones, so what matters is that every SM has work all the
-  // time and that the blocks finish together.  First round (static): with fewer pictures than chains every block
-  // gets one picture before any block gets two; the most expensive pictures (lowest QP) run alone, the others are
-  // paired expensive-with-cheap (measured: 1131 ms against 1258 ms for "one each, then pull" and 1168 ms against
-  // 1218 ms for equal-cost pairs on 256 / 296 pictures of 416x240).  Pictures beyond the first round are pulled from
-  // the queue in cost order - a pair only while enough pictures are left for every block (see the kernel).
+  // Work distribution (see the kernel): the ring starts with every picture's first row, most expensive (lowest QP)
+  // picture first; the scheduler words and the ring's initial part travel on the copy stream (pageable source: staged
+  // before the call returns, and the copy stream is never behind a running kernel).
+  const int rows = (c->seq.height + 63) / 64, ctusPerRow = (W + 63) / 64;
   const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
-  int firstRound = 0;
   {
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; i++) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[a].sliceQp < sp[b2].sliceQp; });    // expensive first
-    c->hostAssign.assign((size_t)c->maxBlocks * FHC_PICS_PER_BLOCK + (size_t)n, -1);
-    firstRound = n < blocks * FHC_PICS_PER_BLOCK ? n : blocks * FHC_PICS_PER_BLOCK;
-    const int pairs = firstRound - blocks > 0 ? firstRound - blocks : 0, singles = blocks - pairs;
-    const char* pe = getenv("FHC_PAIRING");                  // experiment switch: 0 extremes (default), 1 halves, 2 neighbours
-    const int pairing = pe ? atoi(pe) : 0;
-    int lo = 0, hi = firstRound - 1;
-    for (int bk = 0; bk < blocks; bk++)
-    {
-      if (bk < singles || FHC_PICS_PER_BLOCK == 1) { c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = order[(size_t)lo++]; continue; }
-      const int k = bk - singles;
-      int a, b2;
-      if (pairing == 1) { a = singles + k; b2 = singles + pairs + k; }
-      else if (pairing == 2) { a = singles + 2 * k; b2 = a + 1; }
-      else { a = lo++; b2 = hi--; }
-      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK] = order[(size_t)a];
-      c->hostAssign[(size_t)bk * FHC_PICS_PER_BLOCK + 1] = order[(size_t)b2];
-    }
-    // the queue hands out the remaining pictures in cost order: queue position q -> picture order[q]
-    for (int i = 0; i < n; i++) c->hostAssign[(size_t)c->maxBlocks * FHC_PICS_PER_BLOCK + i] = order[(size_t)i];
+    const int lone = lone_pictures(sp, order, n, blocks);
+    c->hostSched.assign((size_t)SC_WEIGHT + (size_t)n, 0);
+    for (int i = 0; i < n; i++)
+      c->hostSched[(size_t)SC_WEIGHT + (size_t)order[(size_t)i]] = (int)(1000.0 * picture_weight(sp[order[(size_t)i]].sliceQp)) | (i < lone ? SC_LONE_BIT : 0);
   }
-  // (both small copies go through the copy stream: pageable sources are staged before the call returns, and the copy
-  // stream is never behind a running kernel)
-  c->hostQueueStart = firstRound;
-  CK(cudaMemcpyAsync(bt->dAssign, c->hostAssign.data(), sizeof(int) * c->hostAssign.size(), cudaMemcpyHostToDevice, c->copyIn));
-  CK(cudaMemcpyAsync(bt->dQueue, &c->hostQueueStart, sizeof(int), cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaMemcpyAsync(bt->dSched, c->hostSched.data(), sizeof(int) * c->hostSched.size(), cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaMemsetAsync(bt->dState, 0, sizeof(PicState) * (size_t)n, c->copyIn));
+#ifdef FHC_PROFILE
+  CK(cudaMemsetAsync(bt->dProf, 0, sizeof(long long) * 64 * (size_t)n, c->copyIn));
+#endif
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
   CK(cudaEventRecord(bt->evStart, c->compute));
-  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, n, c->numCtus, bt->dQueue, bt->dAssign, bt->dAssign + (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK, c->dWorkspace,
-                                                                                            c->wsPerBlock, c->smemBytes, c->dTables);
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, bt->dState, n, rows, ctusPerRow, bt->dSched, c->dWorkspace, c->wsPerBlock,
+                                                                                            c->smemBytes, c->dTables);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));
   g_launches++;

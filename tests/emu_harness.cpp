@@ -14,11 +14,19 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
   using namespace fhc;
   size_t smemBytes, globalBytes;
   block_footprint(&smemBytes, &globalBytes);
-  unsigned char* sm = (unsigned char*)calloc(1, smemBytes);
-  unsigned char* gm = (unsigned char*)calloc(1, globalBytes);
-  Blk* b = (Blk*)sm;
-  build_tables(&b->t, bitDepth);
-  init_block(b, sm + ((sizeof(Blk) + 15) & ~(size_t)15), gm);
+  // two blocks that take the CTU rows of the picture in turn, as two SMs may on the device: nothing but PicState,
+  // the line buffers and the results may carry over from one row to the next
+  unsigned char *sm[2], *gm[2];
+  Blk* blk[2];
+  for (int k = 0; k < 2; k++)
+  {
+    sm[k] = (unsigned char*)calloc(1, smemBytes);
+    gm[k] = (unsigned char*)calloc(1, globalBytes);
+    blk[k] = (Blk*)sm[k];
+    build_tables(&blk[k]->t, bitDepth);
+    init_block(blk[k], sm[k] + ((sizeof(Blk) + 15) & ~(size_t)15), gm[k]);
+    blk[k]->inst = 0; blk[k]->twin = 0;
+  }
   PicDesc pd;
   memset(&pd, 0, sizeof(pd));
   pd.org[0] = y; pd.org[1] = cb; pd.org[2] = cr;
@@ -33,9 +41,11 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
     pd.line[k][2] = pd.line[k][1] + width / 2;
     pd.depthRow[k] = depthRows.data() + (size_t)k * (width / 2);
   }
-  b->inst = 0; b->twin = 0;
-  compress_picture(b, &pd, pd.wc * pd.hc, 0, 1);
-  free(sm); free(gm);
+  PicState state;
+  memset(&state, 0, sizeof(state));
+  pd.state = &state;
+  for (int row = 0; row < pd.hc; row++) compress_picture(blk[row & 1], &pd, row * pd.wc, pd.wc, 0, 1);
+  for (int k = 0; k < 2; k++) { free(sm[k]); free(gm[k]); }
   return 0;
 }
 // work counters since the last reset: out[0..7] = TU-pipeline samples [luma,chroma][4x4,8x8,16x16,32x32], out[8..15] = TU codings

@@ -71,6 +71,15 @@ if __name__ == "__main__":
         perf(416, 240, 256, [22, 27, 32, 37])
         # QP-major order as in bench.py
         import fasthevc_b200 as fh2
+    if "ab" in what:                      # three repetitions of both loaded cases (library comparisons on the same box via FHC_LIBRARY)
+        for _ in range(3):
+            perf(416, 240, 296, [22, 27, 32, 37])
+            perf(416, 240, 256, [22, 27, 32, 37])
+    if "lonecase" in what:                # every picture alone in its block (ncu target for the lone-chain profile)
+        perf(416, 240, 148, [27])
+    if "lone" in what:                    # one / two / three pictures per SM
+        for n in (148, 296, 444):
+            perf(416, 240, n, [22, 27, 32, 37])
     if "perf1080" in what:
         perf(1920, 1080, 8, [22, 27, 32, 37])
         perf(1920, 1080, 256, [22, 27, 32, 37], distinct=16)
