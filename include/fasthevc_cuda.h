@@ -82,7 +82,10 @@ int fhc_destroy(fhc_ctx* ctx);
  * (TEncSlice.cpp:879) for those pictures.  Asynchronous; two submits may be outstanding (the second
  * one's host->device copy overlaps the first one's kernel), a third waits for the oldest to finish,
  * whose results are then no longer fetchable.  A page-locked yuv buffer must stay untouched until a
- * fetch of one of its pictures has returned (pageable memory is staged before the call returns). */
+ * fetch of one of its pictures has returned (pageable memory is staged before the call returns).
+ * The pictures of a submit finish in no particular order: the device works on the pictures with the most work left
+ * first (per_frame[i].sliceQp is its cost estimate), so that a submit with more pictures than fhc_pictures_in_flight
+ * finishes as a whole as early as possible - its pictures then complete close together, towards the end. */
 int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
                       const fhc_slice_params* per_frame);
 
@@ -116,8 +119,9 @@ int fhc_device_input(fhc_ctx* ctx, void** dptr, uint64_t* bytes);
 int fhc_run_resident(fhc_ctx* ctx, int n, int sampleBytes, const fhc_slice_params* per_frame, float* kernel_ms);
 /* CUDA-event time of the kernel of the last submit (waits for it to finish). */
 int fhc_last_kernel_ms(fhc_ctx* ctx, float* kernel_ms);
-/* Number of pictures the persistent kernel encodes concurrently on `device` (SMs x resident thread blocks, one
- * picture per block): submits of at least this many pictures keep the whole device busy.  Negative = error. */
+/* Number of pictures the persistent kernel encodes concurrently on `device` (SMs x chain slots per SM; a picture is a
+ * sequential chain whose CTU rows are scheduled over the slots): submits of at least this many pictures keep the whole
+ * device busy.  Negative = error. */
 int fhc_pictures_in_flight(int device);
 /* Page-locked host buffers for submit/fetch (optional; any host memory works). */
 int fhc_host_alloc(void** p, uint64_t bytes);
