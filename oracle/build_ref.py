@@ -16,6 +16,7 @@ Outputs (all git-ignored, all under oracle/_ref/):
                    TLibEncoderCUDA shim (fasthevc_b200/shim/TEncCuCUDA.cpp) instead of xCompressCU(depth 0) and is
                    linked against libfasthevc_cuda.so (RUNPATH $ORIGIN/../../fasthevc_b200, so LD_LIBRARY_PATH can
                    substitute the tests' emulated ABI) - whole-bitstream byte identity, end to end
+  harp_json_ref    oracle/harp_json_ref.cpp + the reference's vendored jsoncpp: serialises one CU record of the dataset dumper
   cfg/             the two cfg files the metric uses (tiny text files, needed on the GPU box)
 
 Patched sites (reference file:line):
@@ -192,6 +193,10 @@ def main():
                               ["-L" + libdir, "-lfasthevc_cuda", "-Wl,--enable-new-dtags", "-Wl,-rpath,$ORIGIN/../../fasthevc_b200", "-lm"])
     else:
         print("build_ref: libfasthevc_cuda.so not built yet - TAppEncoderFHC skipped")
+    # the reference's vendored jsoncpp (compiled where it lies) + oracle/harp_json_ref.cpp: the serialiser of the dataset
+    # dumper's CU records, used to generate tests/golden/harp_cu_json.json
+    subprocess.check_call([CXX, "-std=c++11", "-O1", "-w", "-I" + os.path.join(REF, "Src_HARP"), "-o", os.path.join(OUT, "harp_json_ref"),
+                           os.path.join(HERE, "harp_json_ref.cpp"), os.path.join(REF, "Src_HARP", "jsoncpp.cpp")])
     shutil.rmtree(scratch, ignore_errors=True)
     shutil.rmtree(objdir, ignore_errors=True)
     # provenance of the binaries that travel to the GPU box (they are git-ignored): sha256 next to them
