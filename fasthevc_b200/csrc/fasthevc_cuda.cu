@@ -28,9 +28,12 @@ using namespace fhc;
 // blocks finish together.  The `lone` most expensive pictures are different: two chains of a block each run at
 // little more than half the speed of a lone one, and the longest pictures set the makespan - they stay
 // on the slot that takes them, alone in their block, until they are finished.
-// sched[SC_FINISHED] = finished pictures, sched[SC_WEIGHT + p] = cost weight of picture p | SC_LONE_BIT.
+// The same holds dynamically: while some block has found nothing to do (sched[SC_IDLE] > 0), no block takes a second
+// chain, so that towards the end of a submit (or with fewer pictures than slots) the chains spread out over the blocks.
+// sched[SC_FINISHED] = finished pictures, sched[SC_IDLE] = blocks without a chain, sched[SC_WEIGHT + p] = cost weight of
+// picture p | SC_LONE_BIT.
 // ----------------------------------------------------------------------------------------------
-enum { SC_FINISHED = 0, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
+enum { SC_FINISHED = 0, SC_IDLE = 1, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
 enum { ST_READY = 0, ST_RUNNING = 1, ST_FINISHED = 2 };
 
 // picture index, -1 = nothing ready now, -2 = every picture is finished
@@ -63,7 +66,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
                size_t smemPerChain, const Tables* tables)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit;
+  __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit, sIdle;
   // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
   const int inst = threadIdx.x / FHC_INST_THREADS, tid = threadIdx.x - inst * FHC_INST_THREADS, nthr = FHC_INST_THREADS;
   unsigned char* mine = smem_raw + (size_t)inst * smemPerChain;
@@ -78,7 +81,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
     init_block(b, mine + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + ((size_t)blockIdx.x * FHC_PICS_PER_BLOCK + inst) * wsPerChain);
     b->inst = inst;
   }
-  if (threadIdx.x == 0) { sPinned = 0; sExit = 0; for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) sItem[k] = -1; }
+  if (threadIdx.x == 0) { sPinned = 0; sExit = 0; sIdle = 0; for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) sItem[k] = -1; }
   __syncthreads();
   for (;;)
   {
@@ -90,14 +93,21 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
         for (int k = 0; k < FHC_PICS_PER_BLOCK; k++)
         {
           if (sPinned) { if (k == 0) any = 1; else sItem[k] = -1; continue; }      // slot 0 keeps its lone picture, the others stay empty
+          if (k > 0 && *reinterpret_cast<volatile int*>(sched + SC_IDLE) > 0) { sItem[k] = -1; continue; }   // a block without any chain goes first
           int lone = 0;
           const int item = sched_take(states, sched, numPics, rowsPerPic, k == 0, &lone);
           sItem[k] = item >= 0 ? item : -1;
-          if (item >= 0) { any = 1; if (lone) sPinned = 1; }
+          if (item >= 0)
+          {
+            any = 1;
+            if (lone) sPinned = 1;
+            if (sIdle) { sIdle = 0; atomicSub(sched + SC_IDLE, 1); }
+          }
           else if (item == -2) never = 1;
         }
         if (any) break;
         if (never) { sExit = 1; break; }
+        if (!sIdle) { sIdle = 1; atomicAdd(sched + SC_IDLE, 1); }
         __nanosleep(5000);
       }
     }
@@ -606,6 +616,18 @@ int fhc_host_free(void* p)
 }
 
 // debug: launch geometry {resident blocks, threads per block, dynamic shared memory bytes, global workspace bytes per block}
+// diagnostics: how many of n pictures with the given slice QPs the scheduler would run alone in their block on `blocks` blocks
+// (host arithmetic only: no device needed)
+extern "C" int fhc_debug_lone_pictures(const int* qps, int n, int blocks)
+{
+  if (!qps || n <= 0 || blocks <= 0) return FHC_ERR_ARG;
+  std::vector<fhc_slice_params> sp((size_t)n);
+  std::vector<int> order((size_t)n);
+  for (int i = 0; i < n; i++) { memset(&sp[(size_t)i], 0, sizeof(fhc_slice_params)); sp[(size_t)i].sliceQp = qps[i]; order[(size_t)i] = i; }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[(size_t)a].sliceQp < sp[(size_t)b2].sliceQp; });
+  return lone_pictures(sp.data(), order, n, blocks < n ? blocks : n);
+}
+
 extern "C" int fhc_debug_geometry(fhc_ctx* c, long long* out4)
 {
   if (!c || !out4) return FHC_ERR_ARG;

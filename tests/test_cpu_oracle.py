@@ -215,6 +215,26 @@ def test_two_rank_sharding_gloo():
     assert "SHARD_OK" in r.stdout
 
 
+def test_scheduler_lone_picture_model():
+    """Host side of the row-wise scheduler (fasthevc_cuda.cu lone_pictures): which pictures run alone in their block.
+    Twin builds only: a lone chain is ~1.7x faster than a chain that shares its block, and the slowest picture ends the
+    kernel - few pictures all run alone, the bench mix (64 frames x 4 QPs on 148 blocks) keeps its 64 most expensive
+    pictures alone, a submit that fills every slot with equal pictures shares everything."""
+    import ctypes as C
+    import fasthevc_b200.api as api
+    lib = C.CDLL(api.library_path())
+    lib.fhc_debug_lone_pictures.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int]
+
+    def lone(qps, blocks=148):
+        a = (C.c_int * len(qps))(*qps)
+        return lib.fhc_debug_lone_pictures(a, len(qps), blocks)
+
+    assert lone([32]) == 1 and lone([32, 32]) == 2 and lone([22, 37]) in (1, 2) and lone([32] * 148) == 148
+    assert lone([q for q in (22, 27, 32, 37) for _ in range(64)]) == 64
+    assert lone([32] * 296) == 0 and lone([32] * 1000) == 0
+    assert lone([32] * 10, blocks=4) in (0, 1, 2)
+
+
 def test_kernel_shared_memory_budget():
     """Two picture chains share a thread block (one block per SM): twice the chain's shared memory (Blk + role arenas,
     computed by the same block_footprint() the launch uses) plus the 1 KB the system reserves per block must fit the

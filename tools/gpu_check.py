@@ -80,6 +80,11 @@ if __name__ == "__main__":
     if "lone" in what:                    # one / two / three pictures per SM
         for n in (148, 296, 444):
             perf(416, 240, n, [22, 27, 32, 37])
+    if "perf2160" in what:                # BASELINE configs[3]: 3840x2160 Main10, 32 frames at QP 27 (every picture alone in its block)
+        Yd, Ud, Vd = synth_frames(3840, 2160, 4, bit_depth=10, sigma=6.0)
+        idx = np.arange(32) % 4
+        got, dt, ms = run(3840, 2160, 10, [27], Yd[idx], Ud[idx], Vd[idx])
+        print("perf 3840x2160 Main10 n=32 qp=27: kernel %.1f ms -> %.2f fps, %.0f CTU/s" % (ms, 32 / (ms / 1e3), 32 * T.n_ctus(3840, 2160) / (ms / 1e3)), flush=True)
     if "perf1080" in what:
         perf(1920, 1080, 8, [22, 27, 32, 37])
         perf(1920, 1080, 256, [22, 27, 32, 37], distinct=16)
