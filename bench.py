@@ -172,7 +172,10 @@ def run_ours(args, rank, world, local_rank):
         launch_s = ms_per_step / 1e3
         int_achieved = INT_OPS_PER_CTU * ctus_per_launch / launch_s / 1e12        # Tops/s per launch (= per rank)
         hbm_achieved = ALGO_BYTES_PER_CTU * ctus_per_launch / launch_s / 1e9
-        prof = load_json(os.path.join("profiles", "r02_kernel_counters.json")) or {}
+        # DRAM bytes of one launch from the committed ncu capture of this very command (profiles/r02_launches_bench.csv),
+        # scaled by the CTUs of the launch when the job count differs
+        prof = (load_json(os.path.join("profiles", "r02_kernel_counters.json")) or {}).get("bench_launch")
+        traffic = prof and round((prof["dram_bytes_read"] + prof["dram_bytes_written"]) * ctus_per_launch / prof["ctus"])
         line = {
             "metric": "1080p all-intra encode fps (byte-identical CTU decisions)" if (W, H) == (1920, 1080) else "SELF-TEST %dx%d (not the metric)" % (W, H),
             "value": round(fps, 4), "unit": "frames/s",
@@ -194,13 +197,14 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "roofline": {"bound": "int_issue", "achieved": round(int_achieved, 4), "peak": round(int_peak_gops / 1e3, 3), "unit": "Tops/s",
                          "frac": int_achieved / (int_peak_gops / 1e3),
-                         "traffic": prof.get("dram_bytes_per_ctu") and round(prof["dram_bytes_per_ctu"] * ctus_per_launch),
+                         "traffic": traffic,
                          "peak_source": "measured live by fhc_measure_int_issue (IMAD/IADD3/LOP3 mix at full occupancy); committed run: profiles/int_issue_peak.json",
                          "work_per_ctu": INT_OPS_PER_CTU,
                          "hbm": {"achieved": round(hbm_achieved, 4), "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                                  "bytes_per_ctu": ALGO_BYTES_PER_CTU},
                          "note": "SURVEY.md 8(d): the path is integer-issue / latency bound, not HBM or tensor bound; achieved = W_ctu x "
-                                 "CTUs per launch / launch time, W_ctu counted by tools/work_count.py"},
+                                 "CTUs per launch / launch time, W_ctu counted by tools/work_count.py; traffic = DRAM read + write of one launch "
+                                 "(ncu), almost all of it L2 write-backs of the chains' scratch (12 GB/s), see DESIGN.md 3"},
             "check_total_bits": check_bits,
         }
         if world == 1 and not args.no_cpu_baseline:
