@@ -12,6 +12,8 @@ Outputs (all git-ignored, all under oracle/_ref/):
   TAppEncoder      stock encoder, HARP hooks removed
   TAppEncoderDump  same + oracle/ref_dump_hook.cpp (per-CTU golden dumps via FHC_DUMP=file)
   TAppDecoder      stock decoder (conformance checker: MD5 SEI)
+  TAppEncoderStages stock encoder with HM's debug switches DEBUG_INTRA_SEARCH_COSTS / DEBUG_TRANSFORM_AND_QUANTISE on
+                   (per-stage golden vectors, tests/golden/make_stage_golden.py)
   TAppEncoderFHC   the reference encoder with the drop-in boundary wired in: TEncCu::compressCtu calls the
                    TLibEncoderCUDA shim (fasthevc_b200/shim/TEncCuCUDA.cpp) instead of xCompressCU(depth 0) and is
                    linked against libfasthevc_cuda.so (RUNPATH $ORIGIN/../../fasthevc_b200, so LD_LIBRARY_PATH can
@@ -95,6 +97,24 @@ def dump_sources(scratch):
     return out
 
 
+def stages_sources(scratch):
+    """TAppEncoderStages: the stock encoder with HM's own debug switches DEBUG_INTRA_SEARCH_COSTS and
+    DEBUG_TRANSFORM_AND_QUANTISE (TypeDef.h:58-59) turned on in the two files that use them: it prints every first-pass
+    mode cost and every TU on its way through transform and quantiser (tests/golden/make_stage_golden.py)."""
+    src = os.path.join(REF, "source")
+    out = {}
+    for rel, macro in (("Lib/TLibEncoder/TEncSearch.cpp", "DEBUG_INTRA_SEARCH_COSTS"), ("Lib/TLibCommon/TComTrQuant.cpp", "DEBUG_TRANSFORM_AND_QUANTISE")):
+        t = open(os.path.join(src, rel)).read()
+        marker = "//! \\ingroup"
+        assert t.count(marker) >= 1, rel
+        t = t.replace(marker, "#undef %s\n#define %s 1\n#include <iostream>\n%s" % (macro, macro, marker), 1)
+        dst = os.path.join(scratch, "stages", rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        open(dst, "w").write(t)
+        out[rel] = dst
+    return out
+
+
 def fhc_sources(scratch):
     """TEncCu.cpp of the integrated encoder: the single call site of the hot path goes to the shim."""
     src = os.path.join(REF, "source")
@@ -136,6 +156,7 @@ def main():
     stub = patched_sources(scratch)
     dump = dump_sources(scratch)
     fhc = fhc_sources(scratch)
+    stages = stages_sources(scratch)
     incs = ["-I" + os.path.join(src, "Lib"), "-I" + os.path.join(src, "App"), "-I" + os.path.join(src, "App/TAppEncoder")]
 
     def listing(d, exts=(".cpp", ".c")):
@@ -145,11 +166,14 @@ def main():
     enc = listing("Lib/TLibEncoder") + listing("App/TAppEncoder")
     dec = listing("Lib/TLibDecoder") + listing("App/TAppDecoder")
 
-    jobs, objs = [], {"enc": [], "dump": [], "dec": [], "fhc": []}
+    jobs, objs = [], {"enc": [], "dump": [], "dec": [], "fhc": [], "stages": []}
     def add(rel, which):
         tagged = rel.replace("/", "_")
         if which == "fhc" and rel in fhc:
             s, o = fhc[rel], os.path.join(objdir, "fhc_" + tagged + ".o")
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        elif which == "stages" and rel in stages:
+            s, o = stages[rel], os.path.join(objdir, "stages_" + tagged + ".o")
             extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
         elif which == "dump" and rel in dump:
             s, o = dump[rel], os.path.join(objdir, "dump_" + tagged + ".o")
@@ -166,9 +190,9 @@ def main():
         objs[which].append(o)
 
     for rel in common:
-        add(rel, "enc"); add(rel, "dump"); add(rel, "dec"); add(rel, "fhc")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "dec"); add(rel, "fhc"); add(rel, "stages")
     for rel in enc:
-        add(rel, "enc"); add(rel, "dump"); add(rel, "fhc")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "fhc"); add(rel, "stages")
     for rel in dec:
         add(rel, "dec")
     hook_o = os.path.join(objdir, "ref_dump_hook.o")
@@ -182,7 +206,7 @@ def main():
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(compile_one, jobs))
 
-    for name, key in (("TAppEncoder", "enc"), ("TAppEncoderDump", "dump"), ("TAppDecoder", "dec")):
+    for name, key in (("TAppEncoder", "enc"), ("TAppEncoderDump", "dump"), ("TAppDecoder", "dec"), ("TAppEncoderStages", "stages")):
         subprocess.check_call([CXX, "-O2", "-o", os.path.join(OUT, name)] + sorted(set(objs[key])) + ["-lm"])
     os.makedirs(os.path.join(OUT, "cfg"), exist_ok=True)
     for c in ("encoder_intra_main.cfg", "encoder_intra_main10.cfg"):

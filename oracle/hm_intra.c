@@ -97,6 +97,25 @@ static const int kInvAngTable[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256
 static const uint8_t kNumModesFullRD[6] = { 3, 8, 8, 3, 3, 3 };                                /* TComRom.cpp:545 */
 
 /* generated tables */
+/* Optional stage trace (tests only): the quantities HM prints with DEBUG_INTRA_SEARCH_COSTS and
+ * DEBUG_TRANSFORM_AND_QUANTISE (TypeDef.h:58-59), in the order HM evaluates them, as binary records
+ *   'R' mode sad modeBits            first-pass candidate of a PU (TEncSearch.cpp:2290)
+ *   'P' lumaMode cost(double)        full-RD cost of a candidate (TEncSearch.cpp:2370)
+ *   'T' n comp + 3 n*n int32 blocks  residual, transform output, quantiser output of a TU (TComTrQuant.cpp:1496-1526)
+ * compared with tests/golden/stages_*.npz by tests/test_cpu_oracle.py. */
+static FILE* g_trace = NULL;
+void hm_intra_set_trace(const char* path)
+{
+  if (g_trace) { fclose(g_trace); g_trace = NULL; }
+  if (path && *path) g_trace = fopen(path, "wb");
+}
+static void trace_ints(int tag, int a, int b, int c)
+{
+  int32_t r[4];
+  r[0] = tag; r[1] = a; r[2] = b; r[3] = c;
+  fwrite(r, sizeof(r), 1, g_trace);
+}
+
 static int g_init = 0;
 static uint8_t  g_z2r[256], g_r2z[256];           /* z-scan <-> raster on the 16x16 grid of 4x4 partitions */
 static uint16_t g_scan[3][4][1024];               /* [scanType][log2N-2][scanPos] -> raster pos, 4x4-grouped */
@@ -1401,6 +1420,15 @@ static uint32_t code_tu_block(Enc* e, CU* cu, Yuv* predYuv, int relIdx, int comp
     const int cbfCtx = CTX_CBF + (isChroma ? 5 + trDepthBit : (trDepthBit == 0 ? 1 : 0));
     absSum = rdoq(e, cu, relIdx, comp, log2n, tcoef_, coef, cbfCtx);
   }
+  if (g_trace)
+  {
+    int32_t r32[32 * 32];
+    for (y = 0; y < n * n; y++) r32[y] = e->resiBuf[y];
+    trace_ints('T', n, comp, 0);
+    fwrite(r32, sizeof(int32_t), (size_t)(n * n), g_trace);
+    fwrite(tcoef_, sizeof(int32_t), (size_t)(n * n), g_trace);
+    fwrite(coef, sizeof(int32_t), (size_t)(n * n), g_trace);
+  }
   set_range(cu->cbf[comp], relIdx, numParts, (absSum > 0 ? 1 : 0) << trDepthBit);
 
   /* inverse */
@@ -1418,6 +1446,14 @@ static uint32_t code_tu_block(Enc* e, CU* cu, Yuv* predYuv, int relIdx, int comp
   {
     memset(coef, 0, sizeof(int32_t) * (size_t)(n * n));
     memset(e->resiBuf, 0, sizeof(int16_t) * (size_t)(n * n));
+    memset(deq, 0, sizeof(int32_t) * (size_t)(n * n));
+  }
+  if (g_trace)
+  {
+    int32_t r32[32 * 32];
+    for (y = 0; y < n * n; y++) r32[y] = e->resiBuf[y];
+    fwrite(deq, sizeof(int32_t), (size_t)(n * n), g_trace);          /* dequantiser output, inverse-transform output (0 when not coded) */
+    fwrite(r32, sizeof(int32_t), (size_t)(n * n), g_trace);
   }
 
   /* reconstruction into the three destinations (TEncSearch.cpp:1380-1393) */
@@ -1734,6 +1770,7 @@ static void est_intra_luma(Enc* e, CU* cu, Yuv* predYuv, Yuv* recoYuv)
       sad = hm_satd(org, e->stride[0], e->predBuf, 64, puSize, e->bd);
       modeBits = mode_bits_luma(e, cu, mode, partOffset);
       cost = (double)sad + (double)modeBits * e->p->sqrtLambda;
+      if (g_trace) trace_ints('R', mode, (int)sad, (int)modeBits);
       /* xUpdateCandList (TEncSearch.cpp:5385) */
       while (shift < numModesForFullRD && cost < candCost[numModesForFullRD - 1 - shift]) shift++;
       if (shift != 0)
@@ -1768,6 +1805,7 @@ static void est_intra_luma(Enc* e, CU* cu, Yuv* predYuv, Yuv* recoYuv)
       set_range(cu->ldir, partOffset, puParts, (int)orgMode);
       sb_copy(&e->go, &e->slot[depth][CI_CURR_BEST]);
       recur_luma_qt(e, cu, predYuv, partOffset, log2pu, initTrDepth, second ? 0 : 1, &puDist, &puCost);
+      if (g_trace && !second) { trace_ints('P', (int)orgMode, 0, 0); fwrite(&puCost, sizeof(double), 1, g_trace); }
       if (puCost < bestPUCost)
       {
         bestPUMode = orgMode; bestPUDist = puDist; bestPUCost = puCost;

@@ -50,6 +50,9 @@ void hm_params_from_qp(hm_params* p, int width, int height, int bitDepth, int qp
 int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb,
                               const uint16_t* orgCr, hm_ctu_out* out);
 
+/* Stage trace for tests (see hm_intra.c): records go to `path` until it is called again with NULL. */
+void hm_intra_set_trace(const char* path);
+
 /* --- leaf kernels exposed for unit tests --------------------------------- */
 /* 35-mode prediction of an NxN block from a reference line of 4N+1 samples
  * (index 0 = bottom-most below-left, 2N = corner, 4N = right-most above-right). */

@@ -15,7 +15,7 @@ import pytest
 import fhc_testlib as T
 from fasthevc_b200.synth import synth_frames, write_yuv
 
-GOLDEN = sorted(glob.glob(os.path.join(T.GOLDEN, "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith("stages_"))
 
 
 def load_golden(path):
@@ -213,6 +213,63 @@ def test_two_rank_sharding_gloo():
                         "--master-port", "29713", script], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARD_OK" in r.stdout
+
+
+def read_oracle_trace(path):
+    """Parses the oracle's binary stage trace (oracle/hm_intra.c, hm_intra_set_trace)."""
+    import zlib
+    raw = np.fromfile(path, dtype="<i4")
+    tags, rmd, p2, tu, full = [], [], [], [], []
+    i = 0
+    while i < len(raw):
+        tag, a, b, _ = (int(v) for v in raw[i:i + 4])
+        i += 4
+        tags.append(tag)
+        if tag == ord("R"):
+            rmd.append([a, raw[i - 2], raw[i - 1]])
+        elif tag == ord("P"):
+            p2.append([a, float(raw[i:i + 2].view("<f8")[0])])
+            i += 2
+        elif tag == ord("T"):
+            n2 = a * a
+            blocks = [raw[i + k * n2:i + (k + 1) * n2] for k in range(5)]
+            i += 5 * n2
+            coded = bool(np.any(blocks[2]))
+            tu.append([a, b] + [zlib.crc32(np.ascontiguousarray(x).tobytes()) for x in blocks[:3]] +
+                      [zlib.crc32(np.ascontiguousarray(x).tobytes()) if coded else 0 for x in blocks[3:]])
+            if len(full) < 6:
+                full.append([x.reshape(a, a).copy() for x in blocks[:3]])
+        else:
+            raise AssertionError("bad trace tag %d at word %d" % (tag, i - 4))
+    return np.array(tags, np.uint8), np.array(rmd, np.int64), np.array(p2, np.float64), np.array(tu, np.int64), full
+
+
+def test_oracle_stage_trace_matches_reference():
+    """Per-stage pin of the oracle: for one CTU, every first-pass SATD / mode-bit pair, every candidate's full-RD cost and
+    every TU's residual, transform output, RDOQ output, dequantiser and inverse-transform output - in the order the
+    reference evaluates them - equal what the real reference prints with its own debug switches
+    (tests/golden/stages_64x64_qp32.npz, made by tests/golden/make_stage_golden.py from oracle/_ref/TAppEncoderStages)."""
+    g = np.load(os.path.join(T.GOLDEN, "stages_64x64_qp32.npz"))
+    w, h, qp, bd, seed = (int(v) for v in g["params"])
+    Y, U, V = synth_frames(w, h, 1, bit_depth=bd, sigma=float(g["sigma"][0]), seed=seed)
+    lib = T.oracle()
+    lib.hm_intra_set_trace.argtypes = [C.c_char_p]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "trace.bin")
+        lib.hm_intra_set_trace(path.encode())
+        try:
+            T.oracle_compress(T.params_from_qp(w, h, bd, qp), Y[0], U[0], V[0])
+        finally:
+            lib.hm_intra_set_trace(None)
+        tags, rmd, p2, tu, full = read_oracle_trace(path)
+    assert len(tags) == len(g["tags"]) and np.array_equal(tags, g["tags"]), "the oracle evaluates stages in a different order than the reference"
+    assert np.array_equal(rmd, g["rmd"])                                    # mode, SATD, mode bits: exact
+    assert np.array_equal(p2[:, 0], g["pass2"][:, 0])
+    assert np.allclose(p2[:, 1], g["pass2"][:, 1], rtol=2e-5, atol=0)       # the reference prints six significant digits
+    assert np.array_equal(tu, g["tu"])                                      # size, component, five CRC-32s per TU: exact
+    for k, blocks in enumerate(full):
+        for key, blk in zip(("resi", "tr", "q"), blocks):
+            assert np.array_equal(blk, g["full%d_%s" % (k, key)]), (k, key)
 
 
 def test_scheduler_lone_picture_model():
