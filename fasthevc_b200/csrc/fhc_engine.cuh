@@ -227,6 +227,10 @@ struct Role
   int cand[FHC_MAX_CAND + 2]; int numCand;
   int mpm[3]; int dcVal;
   long long prof[PF_NUM];
+  // scratch that holds nothing once a job has produced its result (everything but best* / nzMask / gMeta): whole 128-byte lines
+  unsigned char* dead[10];
+  uint32_t deadLines[10];
+  int numDead;
 };
 
 // chain totals of a decided region
@@ -2504,6 +2508,21 @@ FHC_D void search_chroma(Blk* b, Role* r)
   }
 }
 
+// The job's scratch is dead now: tell the L2 not to write those lines back (the chains' scratch is rewritten all the time;
+// without this its dirty lines leave the L2 for DRAM whenever the picture / result stream pushes them out).  The host
+// emulation fills the ranges with garbage instead, which proves that no job reads what an earlier job left there.
+FHC_DH void role_discard(const Role* r)
+{
+#ifdef FHC_DEVICE_BUILD
+  for (int k = 0; k < r->numDead; k++)
+    for (uint32_t i = FHC_LANE; i < r->deadLines[k]; i += 32)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(r->dead[k] + ((size_t)i << 7)) : "memory");
+  __syncwarp();
+#else
+  for (int k = 0; k < r->numDead; k++) memset(r->dead[k], 0xA5, (size_t)r->deadLines[k] << 7);
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // one CU hypothesis = xCheckRDCostIntra (TEncCu.cpp:1528-1593): luma search, chroma search, CU syntax bits, J
 // ----------------------------------------------------------------------------------------------
@@ -2553,6 +2572,7 @@ FHC_D void run_job(Blk* b, Role* r)
     r->cost = rd_cost(b, r->bits, r->dist);
   }
   warp_sync();
+  role_discard(r);
   FHC_TOC(r, PF_SYNTAX, tSy);
   FHC_TOC(r, PF_JOB, tJob);
 }
@@ -2817,9 +2837,9 @@ FHC_D void role_loop(Blk* b, int ri)
 // live in the shared-memory arena behind Blk; the sample / coefficient scratch is in the chain's global workspace.
 // ----------------------------------------------------------------------------------------------
 struct Arena { unsigned char* p; size_t used; };
-FHC_HD void* arena_take(Arena* a, size_t bytes)
+FHC_HD void* arena_take(Arena* a, size_t bytes, size_t align = 16)
 {
-  const size_t off = (a->used + 15) & ~(size_t)15;
+  const size_t off = (a->used + align - 1) & ~(align - 1);
   a->used = off + bytes;
   return a->p ? (void*)(a->p + off) : (void*)0;
 }
@@ -2853,26 +2873,37 @@ FHC_HD void role_carve(Role* r, int ri, Arena* sm, Arena* gm)
     for (int c = 0; c < 3; c++) { r->cbf[c] = m + (1 + c) * np; r->ts[c] = m + (4 + c) * np; }
     r->cTridx = m + 7 * np; r->cCbf = m + 8 * np; r->cTs = m + 9 * np;
   }
-  r->tuA = (int32_t*)arena_take(big, 4 * cap * G);
-  r->tuB = (int32_t*)arena_take(big, 4 * cap * G);
-  r->cgCost = (double*)arena_take(big, 8 * (cap >> 4) * G);
-  r->nzMask = (uint16_t*)arena_take(big, 2 * (yuv >> 4) * G);
+  // (line-aligned: dead ranges are dropped from the L2 line by line, see role_discard)
+  r->numDead = 0;
+  const size_t tuBytes = (size_t)4 * cap * G;
+  r->tuA = (int32_t*)arena_take(big, tuBytes, 128);
+  r->tuB = (int32_t*)arena_take(big, tuBytes, 128);
+  const size_t cgBytes = (size_t)8 * (cap >> 4) * G;
+  r->cgCost = (double*)arena_take(big, cgBytes, 128);
+  r->nzMask = (uint16_t*)arena_take(big, 2 * (yuv >> 4) * G, 128);
+  // candidate planes: full CU planes per group, except the NxN role's twenty 4x4 luma candidates (one 4x4 block each);
+  // its five chroma candidates use the same memory with full planes
+  const int planes = ri == ROLE_3B ? (5 * yuv > 16 * G ? 5 * yuv : 16 * G) : yuv * G;
+  r->gRec = (int16_t*)arena_take(big, 2 * planes, 128);
+  r->gCoef = (int16_t*)arena_take(big, 2 * planes, 128);
+  r->gMeta = (uint8_t*)arena_take(big, 4 * np * 5, 128);
+  r->gRefU = (int16_t*)arena_take(big, 2 * r->refCap * 5, 128);
+  r->gRefF = (int16_t*)arena_take(big, 2 * r->refCap * 5, 128);
+  r->curRec = (int16_t*)arena_take(big, 2 * yuv, 128);
+  r->curCoef = (int16_t*)arena_take(big, 2 * yuv, 128);
+  r->bestRec = (int16_t*)arena_take(big, 2 * yuv, 128);
+  r->bestCoef = (int16_t*)arena_take(big, 2 * yuv, 128);
+  const size_t altBytes = (size_t)2 * (r->cuw >> 1) * (r->cuw >> 1);
+  r->altRec = (int16_t*)arena_take(big, altBytes, 128);
+  r->altCoef = (int16_t*)arena_take(big, altBytes, 128);
+  arena_take(big, 0, 128);                                                 // the next role starts on a line of its own
   {
-    // candidate planes: full CU planes per group, except the NxN role's twenty 4x4 luma candidates (one 4x4 block each);
-    // its five chroma candidates use the same memory with full planes
-    const int planes = ri == ROLE_3B ? (5 * yuv > 16 * G ? 5 * yuv : 16 * G) : yuv * G;
-    r->gRec = (int16_t*)arena_take(big, 2 * planes);
-    r->gCoef = (int16_t*)arena_take(big, 2 * planes);
+    struct { void* p; size_t bytes; } d[] = { { r->tuA, tuBytes }, { r->tuB, tuBytes }, { r->cgCost, cgBytes }, { r->gRec, (size_t)2 * planes },
+                                              { r->gCoef, (size_t)2 * planes }, { r->curRec, (size_t)2 * yuv }, { r->curCoef, (size_t)2 * yuv },
+                                              { r->altRec, altBytes }, { r->altCoef, altBytes } };
+    for (int k = 0; k < 9; k++)
+      if (d[k].bytes >= 128) { r->dead[r->numDead] = (unsigned char*)d[k].p; r->deadLines[r->numDead] = (uint32_t)(d[k].bytes >> 7); r->numDead++; }
   }
-  r->gMeta = (uint8_t*)arena_take(big, 4 * np * 5);
-  r->gRefU = (int16_t*)arena_take(big, 2 * r->refCap * 5);
-  r->gRefF = (int16_t*)arena_take(big, 2 * r->refCap * 5);
-  r->curRec = (int16_t*)arena_take(big, 2 * yuv);
-  r->curCoef = (int16_t*)arena_take(big, 2 * yuv);
-  r->bestRec = (int16_t*)arena_take(big, 2 * yuv);
-  r->bestCoef = (int16_t*)arena_take(big, 2 * yuv);
-  r->altRec = (int16_t*)arena_take(big, 2 * (r->cuw >> 1) * (r->cuw >> 1));
-  r->altCoef = (int16_t*)arena_take(big, 2 * (r->cuw >> 1) * (r->cuw >> 1));
 }
 // bytes of shared memory (Blk + arena) and of global workspace one block needs
 FHC_HD void block_footprint(size_t* smemBytes, size_t* globalBytes)
