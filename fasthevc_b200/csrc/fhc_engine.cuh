@@ -278,10 +278,15 @@ FHC_DH int bar_twin(int role) { return 2 * (FHC_ROLES - 1) + 1 + role; }        
 // so their same-role warps ("twins") walk the same static schedule of routines; a named barrier at the entry of each
 // routine of that schedule keeps them on the same code at the same time.  Only call sites whose count per CTU does not
 // depend on the picture content may align (jobs, PUs, the four second-pass nodes, chroma and syntax entry).
+#ifndef FHC_DEVICE_BUILD
+static unsigned long long g_emuAlignCalls[8];       // per role: the emulation counts what the device would wait on (tests: the count of a
+#endif                                               // picture depends on its geometry only, or twins would deadlock)
 FHC_DH void twin_align(const Blk* b, int role)
 {
 #if defined(FHC_DEVICE_BUILD) && FHC_PICS_PER_BLOCK > 1
   if (b->twin) bar_sync(bar_twin(role));
+#elif !defined(FHC_DEVICE_BUILD)
+  (void)b; g_emuAlignCalls[role]++;
 #else
   (void)b; (void)role;
 #endif

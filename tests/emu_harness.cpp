@@ -58,5 +58,11 @@ extern "C" void fhc_emu_counters(unsigned long long* out, int reset)
   out[16] = g_emuCounters.rmdSamples; out[17] = g_emuCounters.bins;
   if (reset) memset(&g_emuCounters, 0, sizeof(g_emuCounters));
 }
+// twin_align calls per role since the last reset (roles 3A, 3B, 2, 1, 0)
+extern "C" void fhc_emu_align_counts(unsigned long long* out5, int reset)
+{
+  for (int k = 0; k < 5; k++) out5[k] = fhc::g_emuAlignCalls[k];
+  if (reset) memset(fhc::g_emuAlignCalls, 0, sizeof(fhc::g_emuAlignCalls));
+}
 extern "C" int fhc_emu_shared_bytes() { size_t s, g; fhc::block_footprint(&s, &g); return (int)s; }
 extern "C" int fhc_emu_global_bytes() { size_t s, g; fhc::block_footprint(&s, &g); return (int)g; }

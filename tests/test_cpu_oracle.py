@@ -272,6 +272,27 @@ def test_oracle_stage_trace_matches_reference():
             assert np.array_equal(blk, g["full%d_%s" % (k, key)]), (k, key)
 
 
+def test_twin_alignment_schedule_depends_on_geometry_only():
+    """The two chains of a block wait for each other at every twin_align call of their same-role warps, so the number of
+    calls per role and CTU must not depend on the picture content - a data-dependent call would deadlock the block. The
+    emulation counts the calls: a smooth picture at QP 37 and a noisy one at QP 22 (different split decisions, candidate
+    counts, transform-skip choices, cbf patterns) of the same size must agree role by role."""
+    import ctypes as C
+    emu = C.CDLL(T.build_emu())
+    emu.fhc_emu_align_counts.argtypes = [C.c_void_p, C.c_int]
+    w, h = 200, 136                                      # boundary CTUs in both directions
+    counts = []
+    for qp, sigma, seed in ((37, 1.5, 3), (22, 28.0, 4), (30, 9.0, 5)):
+        Y, U, V = synth_frames(w, h, 1, sigma=sigma, seed=seed)
+        out = (C.c_ulonglong * 5)()
+        emu.fhc_emu_align_counts(out, 1)
+        T.emu_compress(T.params_from_qp(w, h, 8, qp), Y[0], U[0], V[0])
+        emu.fhc_emu_align_counts(out, 1)
+        counts.append(list(out))
+    assert counts[0] == counts[1] == counts[2], counts
+    assert all(c > 0 for c in counts[0])
+
+
 def test_scheduler_lone_picture_model():
     """Host side of the row-wise scheduler (fasthevc_cuda.cu lone_pictures): which pictures run alone in their block.
     Twin builds only: a lone chain is ~1.7x faster than a chain that shares its block, and the slowest picture ends the
