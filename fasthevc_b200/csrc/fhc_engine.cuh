@@ -33,7 +33,9 @@
 #define FHC_SHARED(p) __builtin_assume(__isShared(p))      // address-space hint: the pointer is in shared memory (LDS / STS instead of generic accesses)
 #define FHC_LANE ((int)(threadIdx.x & 31))
 #define FHC_NL 32
+#ifndef FHC_NOUNROLL
 #define FHC_NOUNROLL _Pragma("unroll 1")
+#endif
 #else
 #define FHC_DH static inline
 #define FHC_D static
