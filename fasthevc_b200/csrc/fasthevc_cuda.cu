@@ -26,7 +26,7 @@ using namespace fhc;
 // row a chain slot gives its picture back and takes the ready picture with the most work left (rows left x the
 // host's cost weight): the pictures that would finish last run all the time, the cheap ones fill the gaps, and the
 // blocks finish together.  The `lone` most expensive pictures are different: two chains of a block each run at
-// little more than half the speed of a lone one, and the longest pictures set the makespan - they stay
+// about two thirds of the speed of a lone one, and the longest pictures set the makespan - they stay
 // on the slot that takes them, alone in their block, until they are finished.
 // The same holds dynamically: while some block has found nothing to do (sched[SC_IDLE] > 0), no block takes a second
 // chain, so that towards the end of a submit (or with fewer pictures than slots) the chains spread out over the blocks.
@@ -68,7 +68,20 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit, sIdle;
   // chain = one picture at a time on 5 role warps; a block holds FHC_PICS_PER_BLOCK chains that advance in lockstep
+#if FHC_PICS_PER_BLOCK == 2 && !defined(FHC_PLAIN_WARP_ORDER)
+  // Warp w runs on sub-partition w % 4 of the SM, each with its own scheduler and first-level instruction cache.  The
+  // twins of a role share a sub-partition (they run the same routine at the same time, see twin_align), and the two
+  // warps on a chain's critical path - the depth-3 pair - have theirs to themselves:
+  //   sub-partition 2: 3A of chain 0 / 1 (warps 2, 6)     sub-partition 0: depth 2 of both chains + depth 0 of chain 0 (warps 0, 4, 8)
+  //   sub-partition 3: 3B of chain 0 / 1 (warps 3, 7)     sub-partition 1: depth 1 of both chains + depth 0 of chain 1 (warps 1, 5, 9)
+  const int warp = threadIdx.x >> 5;
+  const int inst = warp < 8 ? (warp >> 2) : warp - 8;
+  const int role = warp >= 8 ? ROLE_0 : ((warp & 3) == 0 ? ROLE_2 : ((warp & 3) == 1 ? ROLE_1 : ((warp & 3) == 2 ? ROLE_3A : ROLE_3B)));
+  const int tid = (role << 5) | (threadIdx.x & 31), nthr = FHC_INST_THREADS;
+#else
   const int inst = threadIdx.x / FHC_INST_THREADS, tid = threadIdx.x - inst * FHC_INST_THREADS, nthr = FHC_INST_THREADS;
+#endif
+  const bool scheduler = inst == 0 && tid == 0;            // the block's scheduling thread
   unsigned char* mine = smem_raw + (size_t)inst * smemPerChain;
   Blk* b = reinterpret_cast<Blk*>(mine);
   {
@@ -81,11 +94,11 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
     init_block(b, mine + ((sizeof(Blk) + 15) & ~(size_t)15), workspace + ((size_t)blockIdx.x * FHC_PICS_PER_BLOCK + inst) * wsPerChain);
     b->inst = inst;
   }
-  if (threadIdx.x == 0) { sPinned = 0; sExit = 0; sIdle = 0; for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) sItem[k] = -1; }
+  if (scheduler) { sPinned = 0; sExit = 0; sIdle = 0; for (int k = 0; k < FHC_PICS_PER_BLOCK; k++) sItem[k] = -1; }
   __syncthreads();
   for (;;)
   {
-    if (threadIdx.x == 0)
+    if (scheduler)
     {
       for (;;)
       {
@@ -343,7 +356,7 @@ static int ensure_input(fhc_ctx* c, Batch* bt, int sampleBytes)
 }
 
 // How many of the most expensive pictures run alone in their block (twin builds).  Two chains that share a block each
-// advance at FHC_TWIN_RATE of a lone chain's speed; the kernel finishes when the slowest picture does.  Cost model:
+// advance at about two thirds (`rate`) of a lone chain's speed; the kernel finishes when the slowest picture does.  Cost model:
 // relative time of a picture by QP (measured on the bench clip: the time roughly halves every 12 QP steps).  Pick the
 // count that minimises max(longest lone picture, longest shared picture / rate, remaining work / remaining capacity).
 static double picture_weight(int qp) { return exp2((32.0 - qp) / 12.0); }
@@ -351,7 +364,7 @@ static int lone_pictures(const fhc_slice_params* sp, const std::vector<int>& ord
 {
   if (FHC_PICS_PER_BLOCK == 1) return 0;
   if (const char* e = getenv("FHC_LONE")) { const int v = atoi(e); return v < 0 ? 0 : (v > blocks ? blocks : (v > n ? n : v)); }
-  const double rate = 0.59;
+  const double rate = 0.66;
   std::vector<double> w((size_t)n);
   double total = 0;
   for (int i = 0; i < n; i++) { w[(size_t)i] = picture_weight(sp[order[(size_t)i]].sliceQp); total += w[(size_t)i]; }
