@@ -148,6 +148,9 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_flag = True
     launches = int(enc.lib.fhc_launch_count()) - launches0
     in_flight = fh.pictures_in_flight(local_rank)
+    guided = None
+    if rank == 0 and world == 1 and not args.no_cnn:
+        guided = cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, local_rank)
     enc.close()
 
     my_ms = float(np.sum(kernel_ms))
@@ -207,12 +210,58 @@ def run_ours(args, rank, world, local_rank):
                                  "(ncu), almost all of it L2 write-backs of the chains' scratch (12 GB/s), see DESIGN.md 3"},
             "check_total_bits": check_bits,
         }
+        if guided is not None:
+            line["cnn_guided"] = guided
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_both_legs()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device):
+    """BASELINE configs[4] ("C2 with CNN-guided split"), one extra step after the timed region - NOT part of `value`:
+    the tcgen05 split predictor (libfasthevc_cnn.so) runs on the pictures resident in the engine's input buffer, its
+    decisions become fhc_submit_frames_hinted's hints, and the same 256 jobs are searched with them.  Nothing trained
+    exists: seeded random weights, the two logits centred on this input so that about half of the depth-1
+    CUs are split; the decisions equal those of the reference carrying the hook patch (tests/test_hints.py), not HM's."""
+    from fasthevc_b200 import cnn
+    wts = cnn.seeded_weights()
+    dptr, _ = enc.device_picture_ptr(0)
+    sp = cnn.SplitPredictor(wts, device)
+    logits, _ = sp.predict_device(dptr, 1, 8, W, H, n_jobs)
+    wts["fc_b"] = np.array([0.0, -float(np.median(logits[..., 1] - logits[..., 0]))], np.float32)
+    sp.close()
+    sp = cnn.SplitPredictor(wts, device)
+    t0 = time.perf_counter()
+    logits, split = sp.predict_device(dptr, 1, 8, W, H, n_jobs)
+    cnn_wall = time.perf_counter() - t0
+    cnn_ms = sp.rerun_resident(10)
+    cus = int(split.size)
+    sp.close()
+    hints = cnn.hints_from_split(W, H, split)
+    t0 = time.perf_counter()
+    enc.submit(host_in, sps, first_poc=n_jobs, hints=hints)
+    for j in range(n_jobs):
+        enc.fetch_picture_async(n_jobs + j, host_out[j % RING])
+        if j % RING == RING - 1 or j == n_jobs - 1:
+            enc.fetch_sync()
+    wall = time.perf_counter() - t0
+    ms = enc.last_kernel_ms()
+    peaks = load_json("MEASURED_PEAKS.json") or {}
+    tens_peak = float(peaks.get("bf16_dense_tflops", peaks.get("bf16_tflops", 0)) or 0) or None
+    tflops = 5.62e6 * cus / (cnn_ms / 1e3) / 1e12
+    return {"value": round(n_jobs / (ms / 1e3), 4), "unit": "frames/s", "ms_per_step": round(ms, 2), "steps": 1,
+            "e2e": {"value": round(n_jobs / (wall + cnn_wall), 4), "unit": "frames/s", "note": "hinted submit + fetch of every picture + the predictor call (logits D2H)"},
+            "split_fraction": round(float(split.mean()), 4),
+            "predictor": {"cus": cus, "kernel_ms": round(cnn_ms, 4), "cus_per_s": round(cus / (cnn_ms / 1e3), 1),
+                          "roofline": {"bound": "tensor", "achieved": round(tflops, 3), "peak": tens_peak, "unit": "TFLOP/s",
+                                       "frac": (tflops / tens_peak) if tens_peak else None, "flop_per_cu": 5.62e6,
+                                       "note": "2.81 M MAC per 32x32 CU (SURVEY 8 a20); fp16 operands, fp32 accumulation in tensor memory; "
+                                               "the whole network of a CU stays in shared / tensor memory, so the kernel is bound by its "
+                                               "per-CU epilogues and barriers, not by the tensor pipe"}},
+            "note": "one step of the 256 jobs with CNN hints, seeded weights, logits centred on this input; not the headline metric"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -314,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CLIP, help="frames of the clip per GPU (64 = configs[1]; anything else is a self-test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cnn", action="store_true", help="skip the extra CNN-guided step (BASELINE configs[4]) after the timed region")
     ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")
     args = ap.parse_args()
     global W, H, CTUS

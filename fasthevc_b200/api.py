@@ -39,7 +39,7 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
            "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight", "fhc_poll_picture",
-           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue"]
+           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue", "fhc_submit_frames_hinted", "fhc_device_picture"]
 
 
 def library_path():
@@ -73,6 +73,8 @@ def load_library():
     lib.fhc_create.argtypes = [C.POINTER(SeqParams), C.c_int, C.POINTER(C.c_void_p)]
     lib.fhc_destroy.argtypes = [C.c_void_p]
     lib.fhc_submit_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams)]
+    lib.fhc_submit_frames_hinted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams), C.c_void_p]
+    lib.fhc_device_picture.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.fhc_fetch_ctu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.fhc_fetch_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.fhc_num_ctus.argtypes = [C.c_void_p]
@@ -166,12 +168,26 @@ class Encoder:
         n = Y.shape[0]
         return np.concatenate([Y.reshape(n, -1), U.reshape(n, -1), V.reshape(n, -1)], axis=1)
 
-    def submit(self, yuv, slice_params, first_poc=0):
-        """yuv: contiguous (n, frame_samples) uint8/uint16 host array; slice_params: list of SliceParams."""
+    def submit(self, yuv, slice_params, first_poc=0, hints=None):
+        """yuv: contiguous (n, frame_samples) uint8/uint16 host array; slice_params: list of SliceParams; hints: None or
+        uint8 [n][numCtus][4] CU-split hints (fhc_submit_frames_hinted: 0 none, 1 do not split, 2 split)."""
         n = len(slice_params)
         arr = (SliceParams * n)(*slice_params)
         assert yuv.flags["C_CONTIGUOUS"] and yuv.dtype.itemsize == self.sample_bytes and yuv.size == n * self.frame_samples
-        self._check(self.lib.fhc_submit_frames(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr), "fhc_submit_frames")
+        if hints is None:
+            self._check(self.lib.fhc_submit_frames(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr), "fhc_submit_frames")
+            return
+        hints = np.ascontiguousarray(hints, dtype=np.uint8)
+        if hints.size != n * self.num_ctus * 4:
+            raise FhcError("hints: %d bytes, expected %d" % (hints.size, n * self.num_ctus * 4))
+        self._check(self.lib.fhc_submit_frames_hinted(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr, hints.ctypes.data),
+                    "fhc_submit_frames_hinted")
+
+    def device_picture_ptr(self, poc):
+        """Device address of submitted picture `poc` (and the bytes from there to the end of its submit)."""
+        p, b = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.fhc_device_picture(self.ctx, int(poc), C.byref(p), C.byref(b)), "fhc_device_picture")
+        return p.value, b.value
 
     def fetch_picture(self, poc, out=None):
         if out is None:

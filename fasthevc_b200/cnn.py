@@ -178,3 +178,40 @@ class SplitPredictor:
         a2 = buf[2 * 432 * 16:2 * 432 * 16 + 4 * 160 * 16].view(np.float16).reshape(4, 160, 8)
         ft = buf[2 * 432 * 16 + 4 * 160 * 16:].view(np.float32).reshape(64, 64)
         return a1, a2, ft
+
+
+def hints_from_split(width, height, split):
+    """CNN decisions [n][numCus] (the predictor's order: CTUs in raster order, the depth-1 CUs inside the picture in
+    z-order) -> hint bytes [n][numCtus][4] for fhc_submit_frames_hinted: 1 = do not split, 2 = split, 0 = CU cut by the
+    picture edge (HM splits those without a decision, TEncCu.cpp:519-521)."""
+    split = np.asarray(split, np.uint8)
+    if split.ndim == 1:
+        split = split[None]
+    wc, hc = (width + 63) // 64, (height + 63) // 64
+    xy = cu_positions(width, height)
+    if split.shape[1] != len(xy):
+        raise FhcError("split has %d entries per picture, expected %d" % (split.shape[1], len(xy)))
+    hints = np.zeros((split.shape[0], wc * hc, 4), np.uint8)
+    ctu = (xy[:, 1] // 64) * wc + xy[:, 0] // 64
+    k = (xy[:, 0] % 64) // 32 + 2 * ((xy[:, 1] % 64) // 32)
+    hints[:, ctu, k] = 1 + split
+    return hints
+
+
+def seeded_weights(seed=20240):
+    """Random-init weights of the architecture (He-initialised convolutions, identity batch normalisation): for benchmarks
+    and smoke runs - nothing trained exists.  The activations are kept O(1) by scaling each layer's BN
+    variance to the fan-in; the two logits are NOT centred: see bench.py, which centres them on its own input."""
+    rng = np.random.default_rng(seed)
+    w = {"bn_eps": np.float32(1e-5), "mean": np.full((32, 32), 128.0, np.float32)}
+    scale = 40.0                                    # typical deviation of a luma sample from the mean image
+    for i, (cin, cout) in enumerate(((3, 16), (16, 32), (32, 64))):
+        w["conv%d_w" % i] = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (cin * 9))).astype(np.float32)
+        w["conv%d_b" % i] = np.zeros(cout, np.float32)
+        w["bn%d_gamma" % i] = np.ones(cout, np.float32)
+        w["bn%d_beta" % i] = np.zeros(cout, np.float32)
+        w["bn%d_mean" % i] = np.zeros(cout, np.float32)
+        w["bn%d_var" % i] = np.full(cout, scale * scale if i == 0 else 1.0, np.float32)
+    w["fc_w"] = (rng.standard_normal((2, 4096)) / 64.0).astype(np.float32)
+    w["fc_b"] = np.zeros(2, np.float32)
+    return w

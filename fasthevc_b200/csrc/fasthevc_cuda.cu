@@ -63,7 +63,7 @@ __device__ __forceinline__ int sched_take(PicState* states, int* sched, int numP
 
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
 fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPic, int ctusPerRow, int* sched, unsigned char* workspace, size_t wsPerChain,
-               size_t smemPerChain, const Tables* tables)
+               size_t smemPerChain, const Tables* tables, int chainsPerBlock)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit, sIdle;
@@ -106,6 +106,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
         for (int k = 0; k < FHC_PICS_PER_BLOCK; k++)
         {
           if (sPinned) { if (k == 0) any = 1; else sItem[k] = -1; continue; }      // slot 0 keeps its lone picture, the others stay empty
+          if (k >= chainsPerBlock) { sItem[k] = -1; continue; }                    // experiments: fewer chains per block
           if (k > 0 && *reinterpret_cast<volatile int*>(sched + SC_IDLE) > 0) { sItem[k] = -1; continue; }   // a block without any chain goes first
           int lone = 0;
           const int item = sched_take(states, sched, numPics, rowsPerPic, k == 0, &lone);
@@ -131,7 +132,8 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
     const int row = pd ? *reinterpret_cast<volatile int32_t*>(&states[p].nextRow) : 0;
     // the chains of a block align their role warps at fixed points of a CTU's schedule; the schedule depends on the CTU's
     // shape (cut off at the picture's bottom edge or not), so only chains on rows of the same kind are aligned
-    if (tid == 0) { b->active = pd != nullptr; sShape[inst] = pd ? (row + 1 == rowsPerPic) : -1; }
+    // (a picture with CU-split hints has a content-dependent schedule: it gets a shape of its own and is never aligned)
+    if (tid == 0) { b->active = pd != nullptr; sShape[inst] = pd ? (pd->hints ? 2 + inst : (row + 1 == rowsPerPic)) : -1; }
     __syncthreads();
     if (tid == 0)
     {
@@ -196,6 +198,7 @@ struct Batch
   long long* dProf = nullptr;             // [maxFrames][64] cycle counters (FHC_PROFILE builds)
   int32_t* hTrace = nullptr;              // [maxFrames] mapped pinned host memory: progress words (FHC_TRACE=1 in the environment)
   int32_t* dTrace = nullptr;
+  uint8_t* dHints = nullptr;              // [maxFrames][numCtus][4] CU-split hints of the last hinted submit (allocated on first use)
   int* dSched = nullptr;                  // scheduler words + ring of ready rows (see the kernel)
   PicState* dState = nullptr;             // [maxFrames] where every picture chain continues
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
@@ -245,7 +248,7 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dProf);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dProf); cudaFree(bt.dHints);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -386,7 +389,7 @@ static int lone_pictures(const fhc_slice_params* sp, const std::vector<int>& ord
 }
 
 // fills the ring of ready rows and launches the persistent kernel on the compute stream
-static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, const fhc_slice_params* sp)
+static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, const fhc_slice_params* sp, bool hinted = false)
 {
   const int W = c->seq.width;
   const size_t frameBytes = c->frameSamples * (size_t)sampleBytes;
@@ -410,6 +413,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
     d.doneFlag = bt->dFlags + i;
     d.state = bt->dState + i;
     d.prof = bt->dProf + 64 * (size_t)i;
+    d.hints = hinted ? bt->dHints + (size_t)i * 4 * (size_t)c->numCtus : nullptr;
     bt->hFlags[i] = 0;
     if (bt->hTrace) { d.trace = bt->dTrace + 8 * i; memset(bt->hTrace + 8 * i, 0, 32); }
   }
@@ -439,9 +443,14 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
 #endif
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
   CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
+  // The schedule of a hinted picture depends on its content, so its role warps cannot be twin-aligned with another chain's.
+  // Measured on the bench workload with CNN hints (256 jobs, profiles/r02_c5_chains.txt): pairs + lone pictures 14.7 s, one
+  // chain per block 15.5 s, pairs without lone pictures 15.9 s - the pairing stays (FHC_HINTED_CHAINS=1: one chain per block).
+  int chains = FHC_PICS_PER_BLOCK;
+  if (hinted) { const char* e = getenv("FHC_HINTED_CHAINS"); if (e && atoi(e) == 1) chains = 1; }
   CK(cudaEventRecord(bt->evStart, c->compute));
   fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, bt->dState, n, rows, ctusPerRow, bt->dSched, c->dWorkspace, c->wsPerBlock,
-                                                                                            c->smemBytes, c->dTables);
+                                                                                            c->smemBytes, c->dTables, chains);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));
   g_launches++;
@@ -462,6 +471,47 @@ int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sam
   // the copy runs on its own stream, so it overlaps the kernel of the previous submit
   CK(cudaMemcpyAsync(bt->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   return launch(c, bt, first_poc, n, sampleBytes, per_frame);
+}
+
+int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* per_frame,
+                             const uint8_t* hints)
+{
+  if (!hints) return fhc_submit_frames(c, first_poc, n, yuv, sampleBytes, per_frame);
+  if (!c || !yuv || !per_frame || n <= 0 || n > c->maxFrames || (sampleBytes != 1 && sampleBytes != 2)) return FHC_ERR_ARG;
+  if (c->seq.bitDepth > 8 && sampleBytes != 2) return FHC_ERR_ARG;
+  const size_t hintBytes = (size_t)n * 4 * (size_t)c->numCtus;
+  for (size_t i = 0; i < hintBytes; i++)
+    if (hints[i] > FHC_HINT_SPLIT) { snprintf(g_err, sizeof(g_err), "fhc_submit_frames_hinted: hint %zu has the value %d", i, hints[i]); return FHC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  Batch* bt;
+  int rc = take_batch(c, &bt);
+  if (rc != FHC_OK) return rc;
+  rc = ensure_input(c, bt, sampleBytes);
+  if (rc != FHC_OK) return rc;
+  if (!bt->dHints) CK(cudaMalloc(&bt->dHints, (size_t)c->maxFrames * 4 * (size_t)c->numCtus));
+  CK(cudaMemcpyAsync(bt->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
+  CK(cudaMemcpyAsync(bt->dHints, hints, hintBytes, cudaMemcpyHostToDevice, c->copyIn));
+  return launch(c, bt, first_poc, n, sampleBytes, per_frame, true);
+}
+
+int fhc_device_picture(fhc_ctx* c, int poc, void** dptr, uint64_t* bytes)
+{
+  if (!c || !dptr) return FHC_ERR_ARG;
+  Batch* best = nullptr;
+  for (int i = 0; i < FHC_BATCHES; i++)
+  {
+    Batch* bt = &c->batch[i];
+    if (bt->n > 0 && poc >= bt->firstPoc && poc < bt->firstPoc + bt->n && (!best || bt->serial > best->serial)) best = bt;
+  }
+  if (!best) return FHC_ERR_STATE;
+  const size_t frameBytes = c->frameSamples * (size_t)(c->seq.bitDepth > 8 ? 2 : 1);
+  if (frameBytes > best->inBytesPerFrame) return FHC_ERR_STATE;
+  // the copy of the submit that carried the picture has been queued; make sure it has landed before the caller reads
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(best->evCopied));
+  *dptr = best->dIn + (size_t)(poc - best->firstPoc) * frameBytes;
+  if (bytes) *bytes = (uint64_t)frameBytes * (uint64_t)(best->firstPoc + best->n - poc);
+  return FHC_OK;
 }
 
 static Batch* find_batch(fhc_ctx* c, int poc, int* slot)

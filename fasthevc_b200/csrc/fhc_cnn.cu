@@ -167,9 +167,9 @@ fhc_cnn_split_kernel(const DevParams* __restrict__ prm, const uint8_t* __restric
   {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    logitAcc[0] = 0.f;
-    logitAcc[1] = 0.f;
+    for (int k = 0; k < 6; k++) logitAcc[k] = 0.f;
   }
+  __syncwarp();
   if (warp == 0)
   {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemPtr)), "r"(TMEM_COLS)
@@ -387,22 +387,20 @@ fhc_cnn_split_kernel(const DevParams* __restrict__ prm, const uint8_t* __restric
         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
-      if (lane == 0)
+      if (lane == 0)      // one partial sum per warp, added in a fixed order below: the logits are reproducible bit for bit
       {
-        atomicAdd(&logitAcc[0], s0);
-        atomicAdd(&logitAcc[1], s1);
+        logitAcc[2 * warp] = s0;
+        logitAcc[2 * warp + 1] = s1;
       }
     }
     tc_fence_before();
     __syncthreads();
     if (tid == 0)
     {
-      const float l0 = logitAcc[0] + prm->fcb[0], l1 = logitAcc[1] + prm->fcb[1];
+      const float l0 = ((logitAcc[0] + logitAcc[2]) + logitAcc[4]) + prm->fcb[0], l1 = ((logitAcc[1] + logitAcc[3]) + logitAcc[5]) + prm->fcb[1];
       logits[2 * (long long)cu] = l0;
       logits[2 * (long long)cu + 1] = l1;
       split[cu] = l1 > l0 ? 1 : 0;
-      logitAcc[0] = 0.f;
-      logitAcc[1] = 0.f;
     }
   }
   tc_fence_before();

@@ -155,6 +155,7 @@ struct PicDesc                    // global memory, one per submitted picture (f
   PicState* state;                // row-wise scheduling state (device builds; the emulation may pass its own)
   int32_t* trace;                 // optional progress word (host-mapped): ctu << 12 | region z << 4 | stage; 0 = off
   long long* prof;                // [64] clock64 counters of the picture's block (FHC_PROFILE builds): [role][stage]
+  const uint8_t* hints;           // CU-split hints of the CNN predictor [numCtus][4] (fasthevc_cuda.h: FHC_HINT_*) or null
 };
 
 struct PicParams                  // hot copy of the picture header (shared memory)
@@ -167,6 +168,7 @@ struct PicParams                  // hot copy of the picture header (shared memo
   int32_t width, height, bitDepth, sampleBytes, wc, hc;
   int32_t* trace;
   long long* prof;
+  const uint8_t* hints;
 };
 // cycle counters per role (FHC_PROFILE builds; lane 0 of the role's warp): stage indices
 enum { PF_RMD = 0, PF_LUMA1, PF_LUMA2, PF_CHROMA, PF_SYNTAX, PF_JOB, PF_WAIT, PF_JOBS, PF_NUM = 8 };
@@ -2685,9 +2687,15 @@ FHC_D void region(Blk* b, int z)
   const int px = b->ctuPelX + zx(t, z), py = b->ctuPelY + zy(t, z);
   const int inside = (px + wd <= W) && (py + wd <= H);
   const int ri = role_of_depth(D);
-  if (inside) start_job(b, ri, z, SIZE_2Nx2N);
+  // CU-split hint of the CNN predictor (this repository's hook): depth-1 CUs inside the picture only.
+  // FHC_HINT_SPLIT: the CU's own modes are not evaluated (TEncCu.cpp:806, :839-848); FHC_HINT_NOSPLIT: its sub-branch is
+  // not searched (TEncCu.cpp:892-894).
+  const int hint = (D == 1 && inside && b->pp.hints) ? b->pp.hints[b->ctuAddr * 4 + (z >> 6)] : FHC_HINT_NONE;
+  const int own = inside && hint != FHC_HINT_SPLIT;
+  if (own) start_job(b, ri, z, SIZE_2Nx2N);
   uint32_t aDist = 0, aBits = 0, aBins = 0;
-  FHC_NOUNROLL for (int i = 0; i < 4; i++)
+  const int search = hint != FHC_HINT_NOSPLIT;
+  FHC_NOUNROLL for (int i = 0; i < (search ? 4 : 0); i++)
   {
     const int cz = z + i * (np >> 2);
     if (b->ctuPelX + zx(t, cz) < W && b->ctuPelY + zy(t, cz) < H)
@@ -2708,7 +2716,7 @@ FHC_D void region(Blk* b, int z)
   // split hypothesis: contexts after the last sub-CU, plus split_cu_flag = 1 (TEncCu.cpp:956-979)
   sb_copy_g(w, &b->tmp[D], &b->next[D + 1]);
   warp_sync();
-  if (inside)
+  if (inside && search)
   {
     if (w.gl == 0)
     {
@@ -2722,9 +2730,9 @@ FHC_D void region(Blk* b, int z)
     aBits += b->scal[0]; aBins += b->scal[1];
   }
   const double aCost = rd_cost(b, aBits, aDist);
-  int splitWins = 1;
+  int splitWins = search;
   Role* r = &b->role[ri];
-  if (inside)
+  if (own)
   {
     trace_at(b->pp, b->ctuAddr, z, 4 + D);
     join_job(b, ri);
@@ -2740,7 +2748,7 @@ FHC_D void region(Blk* b, int z)
       r->cost = rd_cost(b, r->bits, r->dist);
     }
     warp_sync();
-    splitWins = aCost < r->cost;                                      // xCheckBestMode (TEncCu.cpp:1036, :1661)
+    splitWins = search && aCost < r->cost;                            // xCheckBestMode (TEncCu.cpp:1036, :1661)
   }
   if (splitWins)
   {
@@ -3042,7 +3050,7 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int firstCtu, int count, 
     pp.depthRow[0] = pd->depthRow[0]; pp.depthRow[1] = pd->depthRow[1];
     pp.out = pd->out; pp.sp = pd->sp;
     pp.width = pd->width; pp.height = pd->height; pp.bitDepth = pd->bitDepth; pp.sampleBytes = pd->sampleBytes; pp.wc = pd->wc; pp.hc = pd->hc;
-    pp.trace = pd->trace; pp.prof = pd->prof;
+    pp.trace = pd->trace; pp.prof = pd->prof; pp.hints = pd->hints;
     for (int ri = 0; ri < FHC_ROLES; ri++) { for (int k = 0; k < PF_NUM; k++) b->role[ri].prof[k] = 0; b->jobSeq[ri] = 0; b->doneSeq[ri] = 0; }
   }
   const int lastOfPicture = pd && firstCtu + count == pd->wc * pd->hc;

@@ -156,7 +156,32 @@ static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
     n = got;
   }
   std::vector<fhc_slice_params> sps((size_t)n, sp);
-  if (fhc_submit_frames(g_ctx, poc, n, g_yuv.data(), sampleBytes, sps.data()) != FHC_OK) fhc_die("fhc_submit_frames");
+  // CU-split hints of the CNN predictor (fhc_submit_frames_hinted): a file of [POC][numCtus][4] bytes named by
+  // FHC_HINTS - what fhc_cnn_predict + the scatter of INTEGRATION.md produce for the sequence; pictures beyond the file
+  // are searched in full
+  static std::vector<uint8_t> allHints;
+  static bool hintsLoaded = false;
+  if (!hintsLoaded)
+  {
+    hintsLoaded = true;
+    if (const char* hp = getenv("FHC_HINTS"))
+      if (FILE* hf = fopen(hp, "rb"))
+      {
+        int ch;
+        while ((ch = fgetc(hf)) != EOF) allHints.push_back((uint8_t)ch);
+        fclose(hf);
+      }
+  }
+  const size_t perPic = 4 * (size_t)((w + 63) / 64) * (size_t)((h + 63) / 64);
+  std::vector<uint8_t> hints;
+  if (!allHints.empty())
+  {
+    hints.assign(perPic * (size_t)n, FHC_HINT_NONE);
+    for (size_t i = 0; i < hints.size(); i++)
+      if ((size_t)poc * perPic + i < allHints.size()) hints[i] = allHints[(size_t)poc * perPic + i];
+  }
+  if (fhc_submit_frames_hinted(g_ctx, poc, n, g_yuv.data(), sampleBytes, sps.data(), hints.empty() ? NULL : hints.data()) != FHC_OK)
+    fhc_die("fhc_submit_frames");
   g_batchFirst = poc; g_batchN = n; g_batchSp = sp;
 }
 

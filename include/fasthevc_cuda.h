@@ -89,6 +89,26 @@ int fhc_destroy(fhc_ctx* ctx);
 int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
                       const fhc_slice_params* per_frame);
 
+/* fhc_submit_frames with CU-split hints from the CNN predictor (include/fasthevc_cnn.h; BASELINE configs[4], SURVEY 8
+ * a20 / 8c).  The reference has no such hook; this is the one this repository defines, a two-condition patch
+ * of TEncCu::xCompressCU shown in INTEGRATION.md: for a depth-1 CU (32x32) lying completely inside the picture,
+ *   FHC_HINT_NOSPLIT  the sub-branch is not searched (TEncCu.cpp:892-894 bSubBranch = false),
+ *   FHC_HINT_SPLIT    the CU's own modes are not evaluated (TEncCu.cpp:806 xCheckRDCostIntra and :839-848),
+ *   FHC_HINT_NONE     HM's full search.
+ * hints: host memory, [n][numCtus][4] bytes, the four depth-1 CUs of a CTU in z-order; entries of CUs cut by the
+ * picture edge are ignored.  hints == NULL is fhc_submit_frames.  Results are identical to the reference encoder
+ * carrying that patch (oracle/_ref/TAppEncoderDumpHinted), not to the unpatched one. */
+#define FHC_HINT_NONE    0
+#define FHC_HINT_NOSPLIT 1
+#define FHC_HINT_SPLIT   2
+int fhc_submit_frames_hinted(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
+                             const fhc_slice_params* per_frame, const uint8_t* hints);
+
+/* Device address of the input planes of submitted picture `poc` (layout as submitted; the pictures of one submit follow
+ * each other, *bytes = bytes from there to the end of that submit).  Lets the CNN predictor run on the resident pictures
+ * (fhc_cnn_predict_device) without a second host->device copy.  Valid until the submit slot is reused. */
+int fhc_device_picture(fhc_ctx* ctx, int poc, void** dptr, uint64_t* bytes);
+
 /* Blocks until picture `poc` is finished (only that picture: the device sets a per-picture flag; other pictures of
  * the submit may still be running), then copies CTU `ctuRsAddr` into *out.
  * This is the body of the replaced TEncCu::xCompressCU(depth 0) (TEncCu.cpp:496). */

@@ -14,6 +14,8 @@ Outputs (all git-ignored, all under oracle/_ref/):
   TAppDecoder      stock decoder (conformance checker: MD5 SEI)
   TAppEncoderStages stock encoder with HM's debug switches DEBUG_INTRA_SEARCH_COSTS / DEBUG_TRANSFORM_AND_QUANTISE on
                    (per-stage golden vectors, tests/golden/make_stage_golden.py)
+  TAppEncoderDumpHinted  TAppEncoderDump + the CU-split hint hook (two conditions in TEncCu::xCompressCU, hints from $FHC_HINTS):
+                   pins the oracle's hinted mode (hm_intra_compress_picture_hinted) against the reference's own arithmetic
   TAppEncoderFHC   the reference encoder with the drop-in boundary wired in: TEncCu::compressCtu calls the
                    TLibEncoderCUDA shim (fasthevc_b200/shim/TEncCuCUDA.cpp) instead of xCompressCU(depth 0) and is
                    linked against libfasthevc_cuda.so (RUNPATH $ORIGIN/../../fasthevc_b200, so LD_LIBRARY_PATH can
@@ -97,6 +99,29 @@ def dump_sources(scratch):
     return out
 
 
+def hinted_sources(scratch, dump):
+    """TAppEncoderDumpHinted: the dump variant plus the CU-split hint hook exactly as INTEGRATION.md states it - two
+    conditions in TEncCu::xCompressCU (TEncCu.cpp:576: the CU's own modes are skipped on 'split'; :892: the sub-branch
+    is skipped on 'do not split'), for depth-1 CUs inside the picture; hints come from the file $FHC_HINTS."""
+    rel = "Lib/TLibEncoder/TEncCu.cpp"
+    t = open(dump[rel]).read()
+    t = t.replace("void fhc_dump_ctu(TComDataCU*);", "void fhc_dump_ctu(TComDataCU*);\nint fhc_hint(TComDataCU*);", 1)
+    a = "    if ( !bBoundary )\n    {\n        for (Int iQP=iMinQP; iQP<=iMaxQP; iQP++)"
+    assert t.count(a) == 1, t.count(a)
+    t = t.replace(a, "    const int fhcHint = (uiDepth == 1 && !bBoundary) ? fhc_hint(rpcBestCU) : 0;\n" + a.replace("!bBoundary", "!bBoundary && fhcHint != 2"))
+    b = "const Bool bSubBranch = bBoundary || "
+    assert t.count(b) == 1, t.count(b)
+    t = t.replace(b, "const Bool bSubBranch = (fhcHint != 1) && ")
+    c = "rpcBestCU->isSkipped(0) );"
+    i = t.index("const Bool bSubBranch")
+    j = t.index(c, i)
+    t = t[:i] + t[i:j].replace("(fhcHint != 1) && ", "(fhcHint != 1) && ( bBoundary || ") + "rpcBestCU->isSkipped(0) ) );" + t[j + len(c):]
+    dst = os.path.join(scratch, "hinted", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    return {rel: dst}
+
+
 def stages_sources(scratch):
     """TAppEncoderStages: the stock encoder with HM's own debug switches DEBUG_INTRA_SEARCH_COSTS and
     DEBUG_TRANSFORM_AND_QUANTISE (TypeDef.h:58-59) turned on in the two files that use them: it prints every first-pass
@@ -157,6 +182,7 @@ def main():
     dump = dump_sources(scratch)
     fhc = fhc_sources(scratch)
     stages = stages_sources(scratch)
+    hinted = hinted_sources(scratch, dump)
     incs = ["-I" + os.path.join(src, "Lib"), "-I" + os.path.join(src, "App"), "-I" + os.path.join(src, "App/TAppEncoder")]
 
     def listing(d, exts=(".cpp", ".c")):
@@ -166,11 +192,17 @@ def main():
     enc = listing("Lib/TLibEncoder") + listing("App/TAppEncoder")
     dec = listing("Lib/TLibDecoder") + listing("App/TAppDecoder")
 
-    jobs, objs = [], {"enc": [], "dump": [], "dec": [], "fhc": [], "stages": []}
+    jobs, objs = [], {"enc": [], "dump": [], "dec": [], "fhc": [], "stages": [], "hinted": []}
     def add(rel, which):
         tagged = rel.replace("/", "_")
         if which == "fhc" and rel in fhc:
             s, o = fhc[rel], os.path.join(objdir, "fhc_" + tagged + ".o")
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        elif which == "hinted" and rel in hinted:
+            s, o = hinted[rel], os.path.join(objdir, "hinted_" + tagged + ".o")
+            extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
+        elif which == "hinted" and rel in dump:
+            s, o = dump[rel], os.path.join(objdir, "dump_" + tagged + ".o")
             extra = ["-iquote", os.path.dirname(os.path.join(src, rel))]
         elif which == "stages" and rel in stages:
             s, o = stages[rel], os.path.join(objdir, "stages_" + tagged + ".o")
@@ -190,14 +222,15 @@ def main():
         objs[which].append(o)
 
     for rel in common:
-        add(rel, "enc"); add(rel, "dump"); add(rel, "dec"); add(rel, "fhc"); add(rel, "stages")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "dec"); add(rel, "fhc"); add(rel, "stages"); add(rel, "hinted")
     for rel in enc:
-        add(rel, "enc"); add(rel, "dump"); add(rel, "fhc"); add(rel, "stages")
+        add(rel, "enc"); add(rel, "dump"); add(rel, "fhc"); add(rel, "stages"); add(rel, "hinted")
     for rel in dec:
         add(rel, "dec")
     hook_o = os.path.join(objdir, "ref_dump_hook.o")
     jobs.append((os.path.join(HERE, "ref_dump_hook.cpp"), hook_o, incs, []))
     objs["dump"].append(hook_o)
+    objs["hinted"].append(hook_o)
     repo = os.path.dirname(HERE)
     shim_o = os.path.join(objdir, "TEncCuCUDA.o")
     jobs.append((os.path.join(repo, "fasthevc_b200", "shim", "TEncCuCUDA.cpp"), shim_o, incs + ["-I" + os.path.join(repo, "include")], []))
@@ -206,7 +239,8 @@ def main():
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         list(ex.map(compile_one, jobs))
 
-    for name, key in (("TAppEncoder", "enc"), ("TAppEncoderDump", "dump"), ("TAppDecoder", "dec"), ("TAppEncoderStages", "stages")):
+    for name, key in (("TAppEncoder", "enc"), ("TAppEncoderDump", "dump"), ("TAppDecoder", "dec"), ("TAppEncoderStages", "stages"),
+                      ("TAppEncoderDumpHinted", "hinted")):
         subprocess.check_call([CXX, "-O2", "-o", os.path.join(OUT, name)] + sorted(set(objs[key])) + ["-lm"])
     os.makedirs(os.path.join(OUT, "cfg"), exist_ok=True)
     for c in ("encoder_intra_main.cfg", "encoder_intra_main10.cfg"):

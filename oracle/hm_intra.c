@@ -236,6 +236,7 @@ typedef struct
   int16_t refU[4 * 64 + 1], refF[4 * 64 + 1];     /* m_piYuvExt unfiltered / filtered as a line */
   double rdoqLambdaSel;                           /* TComTrQuant::m_dLambda after selectLambda */
   double errScale[2][4][6];                       /* [chType][log2-2][rem]: TComTrQuant::setErrScaleCoeff */
+  const uint8_t* hints;                           /* depth-1 split hints [numCtus][4] (z-order) or NULL: see compress_cu */
 } Enc;
 
 /* ------------------------------------------------------------------------- */
@@ -2193,8 +2194,12 @@ static void compress_cu(Enc* e, int depth)
   CU* b = e->best[depth];
   const int x = b->x, y = b->y, w = b->width;
   const int boundary = !(x + w - 1 < e->W && y + w - 1 < e->H);
+  /* CU-split hint of the CNN predictor (this repository's definition - the reference has no hook, F1): only
+   * for depth-1 CUs inside the picture.  HM_HINT_NOSPLIT: the sub-branch (TEncCu.cpp:892-894) is not searched;
+   * HM_HINT_SPLIT: the CU's own modes (TEncCu.cpp:806, and with them the split_cu_flag = 0 costing :839-848) are not. */
+  const int hint = (depth == 1 && !boundary && e->hints) ? e->hints[e->ctuAddr * 4 + (b->zidx >> 6)] : HM_HINT_NONE;
 
-  if (!boundary)
+  if (!boundary && hint != HM_HINT_SPLIT)
   {
     cu_init_est(e->temp[depth]);
     check_rd_cost_intra(e, depth, SIZE_2Nx2N);
@@ -2214,7 +2219,7 @@ static void compress_cu(Enc* e, int depth)
     sb_copy(&e->slot[depth][CI_NEXT_BEST], &e->go);
   }
 
-  if (depth < 3)
+  if (depth < 3 && hint != HM_HINT_NOSPLIT)
   {
     const int nd = depth + 1;
     CU* t = e->temp[depth];
@@ -2323,6 +2328,12 @@ void hm_params_from_qp(hm_params* p, int width, int height, int bitDepth, int qp
 int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb, const uint16_t* orgCr,
                               hm_ctu_out* out)
 {
+  return hm_intra_compress_picture_hinted(p, orgY, orgCb, orgCr, out, NULL);
+}
+
+int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb, const uint16_t* orgCr,
+                                     hm_ctu_out* out, const uint8_t* hints)
+{
   Enc* e = (Enc*)calloc(1, sizeof(Enc));
   const uint16_t* src[3];
   int c, i, d, addr;
@@ -2332,6 +2343,7 @@ int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const ui
   e->p = p; e->W = p->width; e->H = p->height; e->bd = p->bitDepth;
   e->wc = (e->W + 63) / 64; e->hc = (e->H + 63) / 64;
   e->out = out;
+  e->hints = hints;
   for (c = 0; c < 3; c++)
   {
     const int w = e->W >> (c ? 1 : 0), h = e->H >> (c ? 1 : 0);

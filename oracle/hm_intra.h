@@ -50,6 +50,17 @@ void hm_params_from_qp(hm_params* p, int width, int height, int bitDepth, int qp
 int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb,
                               const uint16_t* orgCr, hm_ctu_out* out);
 
+/* The same with CU-split hints of the CNN predictor (the hook is THIS repository's definition, the reference
+ * has none - F1): hints[ctuRsAddr * 4 + k] for the k-th (z-order) depth-1 CU of a CTU, consulted only for CUs that lie
+ * completely inside the picture.  HM_HINT_NOSPLIT: the sub-branch of the CU is not searched (TEncCu.cpp:892-894);
+ * HM_HINT_SPLIT: its 2Nx2N check is skipped (TEncCu.cpp:806).  NULL or all HM_HINT_NONE = hm_intra_compress_picture.
+ * Pinned against the real reference carrying exactly this patch (oracle/_ref/TAppEncoderDumpHinted, build_ref.py). */
+#define HM_HINT_NONE    0
+#define HM_HINT_NOSPLIT 1
+#define HM_HINT_SPLIT   2
+int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb,
+                                     const uint16_t* orgCr, hm_ctu_out* out, const uint8_t* hints);
+
 /* Stage trace for tests (see hm_intra.c): records go to `path` until it is called again with NULL. */
 void hm_intra_set_trace(const char* path);
 

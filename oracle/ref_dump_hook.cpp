@@ -138,3 +138,29 @@ void fhc_dump_ctu(TComDataCU* pCtu)
   fwrite(&r, sizeof(r), 1, fp);
   fflush(fp);
 }
+
+// CU-split hints for the hinted variant of the instrumented encoder (oracle/_ref/TAppEncoderDumpHinted): the file named
+// by FHC_HINTS holds one byte per depth-1 CU, [POC][ctuRsAddr][4 in z-order]: 0 = none, 1 = do not split, 2 = split.
+// The build recipe patches the two sites of TEncCu::xCompressCU this value steers (TEncCu.cpp:576 and :892); this is how
+// the oracle's hinted mode is pinned against the reference's own arithmetic.
+int fhc_hint(TComDataCU* cu)
+{
+  static std::vector<unsigned char> hints;
+  static bool loaded = false;
+  if (!loaded)
+  {
+    loaded = true;
+    if (const char* p = getenv("FHC_HINTS"))
+    {
+      if (FILE* f = fopen(p, "rb"))
+      {
+        int ch;
+        while ((ch = fgetc(f)) != EOF) hints.push_back((unsigned char)ch);
+        fclose(f);
+      }
+    }
+  }
+  const size_t ctus = cu->getPic()->getNumberOfCtusInFrame();
+  const size_t i = ((size_t)cu->getSlice()->getPOC() * ctus + cu->getCtuRsAddr()) * 4 + (cu->getZorderIdxInCtu() >> 6);
+  return i < hints.size() ? hints[i] : 0;
+}

@@ -8,8 +8,8 @@
 #include <vector>
 #include "../include/fasthevc_cuda.h"
 
-extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
-                                        const void* y, const void* cb, const void* cr, fhc_ctu_result* out);
+extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                               const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints);
 
 struct fhc_ctx { fhc_seq_params seq; int poc, n, numCtus; std::vector<fhc_ctu_result> out; };
 
@@ -25,7 +25,12 @@ int fhc_create(const fhc_seq_params* seq, int, fhc_ctx** out)
 }
 int fhc_destroy(fhc_ctx* c) { delete c; return FHC_OK; }
 int fhc_pictures_in_flight(int) { return 3; }
+int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* sp, const uint8_t* hints);
 int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* sp)
+{
+  return fhc_submit_frames_hinted(c, first_poc, n, yuv, sampleBytes, sp, NULL);
+}
+int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, int sampleBytes, const fhc_slice_params* sp, const uint8_t* hints)
 {
   if (n < 1 || n > c->seq.maxFramesInFlight) return FHC_ERR_ARG;
   const size_t luma = (size_t)c->seq.width * c->seq.height * sampleBytes, frame = luma + luma / 2;
@@ -34,8 +39,8 @@ int fhc_submit_frames(fhc_ctx* c, int first_poc, int n, const void* yuv, int sam
   for (int k = 0; k < n; k++)
   {
     const unsigned char* p = (const unsigned char*)yuv + frame * k;
-    int rc = fhc_emu_compress_picture(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
-                                      c->out.data() + (size_t)c->numCtus * k);
+    int rc = fhc_emu_compress_picture_hinted(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
+                                             c->out.data() + (size_t)c->numCtus * k, hints ? hints + (size_t)4 * c->numCtus * k : NULL);
     if (rc) return rc;
   }
   return FHC_OK;

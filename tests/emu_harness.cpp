@@ -8,8 +8,15 @@
 #include <vector>
 #include "../fasthevc_b200/csrc/fhc_engine.cuh"
 
+extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                               const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints);
 extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                         const void* y, const void* cb, const void* cr, fhc_ctu_result* out)
+{
+  return fhc_emu_compress_picture_hinted(width, height, bitDepth, sampleBytes, sp, y, cb, cr, out, nullptr);
+}
+extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                               const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints)
 {
   using namespace fhc;
   size_t smemBytes, globalBytes;
@@ -32,6 +39,7 @@ extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int
   pd.org[0] = y; pd.org[1] = cb; pd.org[2] = cr;
   pd.out = out; pd.sp = *sp; pd.width = width; pd.height = height; pd.bitDepth = bitDepth; pd.sampleBytes = sampleBytes;
   pd.wc = (width + 63) / 64; pd.hc = (height + 63) / 64;
+  pd.hints = hints;
   std::vector<int16_t> lines((size_t)width * 4);
   std::vector<uint8_t> depthRows((size_t)width);
   for (int k = 0; k < 2; k++)

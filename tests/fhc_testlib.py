@@ -57,6 +57,8 @@ def oracle():
         lib.hm_params_from_qp.argtypes = [C.POINTER(HmParams), C.c_int, C.c_int, C.c_int, C.c_int]
         lib.hm_intra_compress_picture.argtypes = [C.POINTER(HmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hm_intra_compress_picture.restype = C.c_int
+        lib.hm_intra_compress_picture_hinted.argtypes = [C.POINTER(HmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hm_intra_compress_picture_hinted.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -81,20 +83,44 @@ def n_ctus(width, height):
     return ((width + 63) // 64) * ((height + 63) // 64)
 
 
-def oracle_compress(params, y, u, v):
-    """y,u,v: 2-D arrays (any integer dtype).  Returns CTU_OUT_DT array."""
+def oracle_compress(params, y, u, v, hints=None):
+    """y,u,v: 2-D arrays (any integer dtype); hints: None or uint8 [numCtus][4] (0 none / 1 do not split / 2 split, the
+    depth-1 CUs of a CTU in z-order).  Returns CTU_OUT_DT array."""
     n = n_ctus(params.width, params.height)
     out = np.zeros(n, CTU_OUT_DT)
     planes = [np.ascontiguousarray(p, dtype=np.uint16) for p in (y, u, v)]
-    rc = oracle().hm_intra_compress_picture(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data,
-                                            planes[2].ctypes.data, out.ctypes.data)
+    if hints is None:
+        rc = oracle().hm_intra_compress_picture(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data,
+                                                planes[2].ctypes.data, out.ctypes.data)
+    else:
+        hints = np.ascontiguousarray(hints, dtype=np.uint8)
+        assert hints.size == 4 * n
+        rc = oracle().hm_intra_compress_picture_hinted(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data,
+                                                       planes[2].ctypes.data, out.ctypes.data, hints.ctypes.data)
     assert rc == 0
     return out
 
 
+def hints_from_split(width, height, split):
+    """CNN decisions of one picture ([numCus] in the predictor's order: CTUs in raster order, the depth-1 CUs inside the
+    picture in z-order) -> hint bytes [numCtus][4]: 1 = do not split, 2 = split, 0 for CUs cut by the picture edge."""
+    wc, hc = (width + 63) // 64, (height + 63) // 64
+    hints = np.zeros((wc * hc, 4), np.uint8)
+    i = 0
+    for cy in range(hc):
+        for cx in range(wc):
+            for k in range(4):
+                x, y = cx * 64 + 32 * (k & 1), cy * 64 + 32 * (k >> 1)
+                if x + 32 <= width and y + 32 <= height:
+                    hints[cy * wc + cx, k] = 2 if split[i] else 1
+                    i += 1
+    assert i == len(split)
+    return hints
+
+
 def _oracle_job(job):
-    (w, h, bd, qp), y, u, v = job
-    return oracle_compress(params_from_qp(w, h, bd, qp), y, u, v)
+    (w, h, bd, qp), y, u, v = job[:4]
+    return oracle_compress(params_from_qp(w, h, bd, qp), y, u, v, job[4] if len(job) > 4 else None)
 
 
 def oracle_compress_parallel(jobs):
@@ -227,19 +253,27 @@ def build_emu():
 _emu = None
 
 
-def emu_compress(params, y, u, v):
+def emu_compress(params, y, u, v, hints=None):
     global _emu
     if _emu is None:
         _emu = C.CDLL(build_emu())
         _emu.fhc_emu_compress_picture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p, C.c_void_p]
+        _emu.fhc_emu_compress_picture_hinted.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     sb = 1 if params.bitDepth == 8 else 2
     dt = np.uint8 if sb == 1 else np.uint16
     planes = [np.ascontiguousarray(p, dtype=dt) for p in (y, u, v)]
     out = np.zeros(n_ctus(params.width, params.height), CTU_OUT_DT)
     sp = slice_params_from_hm(params)
-    rc = _emu.fhc_emu_compress_picture(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
-                                       planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data)
+    if hints is None:
+        rc = _emu.fhc_emu_compress_picture(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
+                                           planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data)
+    else:
+        hints = np.ascontiguousarray(hints, dtype=np.uint8)
+        assert hints.size == 4 * len(out)
+        rc = _emu.fhc_emu_compress_picture_hinted(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
+                                                  planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data, hints.ctypes.data)
     assert rc == 0
     return out
 

@@ -181,7 +181,7 @@ def test_gpu_golden_fixture():
 @pytest.mark.gpu
 def test_gpu_main10_and_device_resident():
     """10-bit input (>> 2, as the 8-bit training-set dump does) and pictures already resident on the device (the
-    buffer of the mode-decision engine: fhc_device_input)."""
+    buffer of the mode-decision engine: fhc_device_picture)."""
     w = cs.make_weights()
     wd, ht, n = 200, 136, 3
     Y, U, V = synth_frames(wd, ht, n, sigma=12.0, bit_depth=10)
@@ -193,12 +193,16 @@ def test_gpu_main10_and_device_resident():
     try:
         logits, split = sp.predict(yuv, 2, 10, wd, ht, n)
         _check(logits, split, ref, "main10 host")
-        enc.submit(yuv, [fh.slice_params_from_qp(32)] * n)
-        enc.fetch_picture(n - 1)
-        dptr, nbytes = enc.device_input_ptr()
-        assert nbytes >= yuv.nbytes
+        enc.submit(yuv, [fh.slice_params_from_qp(32)] * n, first_poc=5)
+        dptr, nbytes = enc.device_picture_ptr(5)
+        assert nbytes == yuv.nbytes
         l2, s2 = sp.predict_device(dptr, 2, 10, wd, ht, n)
         assert np.array_equal(l2, logits) and np.array_equal(s2, split)
+        d1, b1 = enc.device_picture_ptr(6)
+        assert d1 == dptr + yuv.nbytes // n and b1 == yuv.nbytes - yuv.nbytes // n
+        l3, s3 = sp.predict_device(d1, 2, 10, wd, ht, n - 1)
+        assert np.array_equal(l3, logits[1:]) and np.array_equal(s3, split[1:])
+        enc.fetch_picture(5 + n - 1)
     finally:
         enc.close()
         sp.close()
