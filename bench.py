@@ -148,9 +148,11 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_flag = True
     launches = int(enc.lib.fhc_launch_count()) - launches0
     in_flight = fh.pictures_in_flight(local_rank)
-    guided = None
+    guided = wavefront = None
     if rank == 0 and world == 1 and not args.no_cnn:
         guided = cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, local_rank)
+    if rank == 0 and world == 1 and not args.no_wpp:
+        wavefront = wavefront_leg(fh, host_in, host_out, sps, n_jobs, local_rank)
     enc.close()
 
     my_ms = float(np.sum(kernel_ms))
@@ -212,12 +214,46 @@ def run_ours(args, rank, world, local_rank):
         }
         if guided is not None:
             line["cnn_guided"] = guided
+        if wavefront is not None:
+            line["wavefront"] = wavefront
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_both_legs()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def wavefront_leg(fh, host_in, host_out, sps, n_jobs, device):
+    """SURVEY 8f rank 4, one extra step after the timed region - NOT part of `value`: the same 256 jobs with
+    --WaveFrontSynchro=1 (fhc_seq_params.waveFrontSynchro).  A different bitstream than the headline's (the reference run
+    with that flag writes the same one, tests/test_wpp.py): the CTU rows of a picture are chains of their own, so no
+    picture has to run alone in its block, and one picture alone finishes in a fraction of the time."""
+    enc = fh.Encoder(W, H, 8, max_frames=n_jobs, device=device, wpp=True)
+    try:
+        t0 = time.perf_counter()
+        enc.submit(host_in, sps)
+        first = None
+        for j in range(n_jobs):
+            enc.fetch_picture_async(j, host_out[j % RING])
+            if j % RING == RING - 1 or j == n_jobs - 1:
+                enc.fetch_sync()
+                if first is None:
+                    first = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
+        ms = enc.last_kernel_ms()
+        # latency of one picture alone on the device (QP 22, the most expensive one)
+        enc.submit(host_in[:1], sps[:1], first_poc=n_jobs)
+        enc.fetch_picture_async(n_jobs, host_out[0])
+        enc.fetch_sync()
+        ms1 = enc.last_kernel_ms()
+    finally:
+        enc.close()
+    return {"value": round(n_jobs / (ms / 1e3), 4), "unit": "frames/s", "ms_per_step": round(ms, 2), "steps": 1,
+            "e2e": {"value": round(n_jobs / wall, 4), "unit": "frames/s"}, "first_results_s": round(first, 3),
+            "single_picture_ms": round(ms1, 1),
+            "note": "one step of the 256 jobs with --WaveFrontSynchro=1 (the reference's own option; another bitstream than the "
+                    "headline's, byte-identical to the reference run with the flag); single_picture_ms = one QP-22 picture alone on the device"}
 
 
 def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device):
@@ -363,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CLIP, help="frames of the clip per GPU (64 = configs[1]; anything else is a self-test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wpp", action="store_true", help="skip the extra wavefront step (--WaveFrontSynchro=1) after the timed region")
     ap.add_argument("--no-cnn", action="store_true", help="skip the extra CNN-guided step (BASELINE configs[4]) after the timed region")
     ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")
     args = ap.parse_args()

@@ -26,7 +26,7 @@ class SeqParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitDepth", "chromaFormat", "ctuSize", "maxCuDepth", "tuLog2Max",
                                          "tuLog2Min", "tuMaxDepthIntra", "useRdoq", "useRdoqTs", "useTransformSkip",
                                          "useTransformSkipFast", "signHideFlag", "strongIntraSmoothing", "fastUdiUseMpm",
-                                         "maxFramesInFlight")]
+                                         "maxFramesInFlight", "waveFrontSynchro")]
 
 
 # fhc_ctu_result
@@ -123,9 +123,10 @@ def slice_params_from_qp(qp):
 class Encoder:
     """One fhc_ctx: the mode-decision engine for one sequence geometry on one device."""
 
-    def __init__(self, width, height, bit_depth=8, max_frames=1, device=0):
+    def __init__(self, width, height, bit_depth=8, max_frames=1, device=0, wpp=False):
+        """wpp: --WaveFrontSynchro=1 (the CTU rows of a picture are searched concurrently; results = the reference's with that flag)."""
         self.lib = load_library()
-        sq = SeqParams(width, height, bit_depth, 1, 64, 4, 5, 2, 3, 1, 1, 1, 1, 1, 1, 1, max_frames)
+        sq = SeqParams(width, height, bit_depth, 1, 64, 4, 5, 2, 3, 1, 1, 1, 1, 1, 1, 1, max_frames, 1 if wpp else 0)
         self.seq = sq
         self.ctx = C.c_void_p()
         self._check(self.lib.fhc_create(C.byref(sq), device, C.byref(self.ctx)), "fhc_create")

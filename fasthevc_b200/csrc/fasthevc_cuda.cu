@@ -34,7 +34,6 @@ using namespace fhc;
 // picture p | SC_LONE_BIT.
 // ----------------------------------------------------------------------------------------------
 enum { SC_FINISHED = 0, SC_IDLE = 1, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
-enum { ST_READY = 0, ST_RUNNING = 1, ST_FINISHED = 2 };
 
 // picture index, -1 = nothing ready now, -2 = every picture is finished
 __device__ __forceinline__ int sched_take(PicState* states, int* sched, int numPics, int rowsPerPic, int allowLone, int* lone)
@@ -63,7 +62,7 @@ __device__ __forceinline__ int sched_take(PicState* states, int* sched, int numP
 
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
 fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPic, int ctusPerRow, int* sched, unsigned char* workspace, size_t wsPerChain,
-               size_t smemPerChain, const Tables* tables, int chainsPerBlock)
+               size_t smemPerChain, const Tables* tables, int chainsPerBlock, int wpp)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit, sIdle;
@@ -145,7 +144,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
       }
       b->twin = n > 1 && same;
     }
-    compress_picture(b, pd, row * ctusPerRow, ctusPerRow, tid, nthr);
+    compress_picture(b, pd, row * ctusPerRow, ctusPerRow, tid, nthr, wpp);
     if (tid == 0 && pd)
     {
       if (row + 1 == rowsPerPic)
@@ -157,7 +156,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
         atomicAdd(sched + SC_FINISHED, 1);
         if (inst == 0) sPinned = 0;
       }
-      else
+      else if (!wpp)                       // (wavefront pictures: the row itself released the next one when it was two CTUs ahead)
       {
         *reinterpret_cast<volatile int32_t*>(&states[p].nextRow) = row + 1;
         if (!(inst == 0 && sPinned)) { __threadfence(); *reinterpret_cast<volatile int32_t*>(&states[p].status) = ST_READY; }
@@ -201,6 +200,7 @@ struct Batch
   uint8_t* dHints = nullptr;              // [maxFrames][numCtus][4] CU-split hints of the last hinted submit (allocated on first use)
   int* dSched = nullptr;                  // scheduler words + ring of ready rows (see the kernel)
   PicState* dState = nullptr;             // [maxFrames] where every picture chain continues
+  RowState* dRows = nullptr;              // wavefront sequences: [maxFrames][rows]
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
   int firstPoc = 0, n = 0, launched = 0;
   uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
@@ -248,7 +248,7 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dProf); cudaFree(bt.dHints);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dRows); cudaFree(bt.dProf); cudaFree(bt.dHints);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -279,7 +279,8 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   if (seq->width <= 0 || seq->height <= 0 || (seq->width & 7) || (seq->height & 7) || (seq->bitDepth != 8 && seq->bitDepth != 10) ||
       seq->chromaFormat != 1 || seq->ctuSize != 64 || seq->maxCuDepth != 4 || seq->tuLog2Max != 5 || seq->tuLog2Min != 2 ||
       seq->tuMaxDepthIntra != 3 || !seq->useRdoq || !seq->useRdoqTs || !seq->useTransformSkip || !seq->useTransformSkipFast ||
-      !seq->signHideFlag || !seq->strongIntraSmoothing || !seq->fastUdiUseMpm || seq->maxFramesInFlight <= 0)
+      !seq->signHideFlag || !seq->strongIntraSmoothing || !seq->fastUdiUseMpm || seq->maxFramesInFlight <= 0 ||
+      (seq->waveFrontSynchro != 0 && seq->waveFrontSynchro != 1))
   {
     snprintf(g_err, sizeof(g_err), "fhc_create: unsupported configuration (only the encoder_intra_main[10].cfg tool set is implemented)");
     return FHC_ERR_ARG;
@@ -297,7 +298,10 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   c->hostPics.resize((size_t)c->maxFrames);
   // every failure below releases what was allocated so far (fhc_destroy is null-safe)
   if (kernel_geometry(device, &c->smemBytes, &c->wsPerBlock, &c->maxBlocks) != FHC_OK) { fhc_destroy(c); return FHC_ERR_CUDA; }
-  if (c->maxBlocks > c->maxFrames) c->maxBlocks = c->maxFrames;
+  {
+    const long long chains = (long long)c->maxFrames * (seq->waveFrontSynchro ? (seq->height + 63) / 64 : 1);    // wavefront: every CTU row is a chain
+    if (c->maxBlocks > chains) c->maxBlocks = (int)chains;
+  }
   CKG(cudaMalloc(&c->dTables, sizeof(Tables)), fhc_destroy(c));
   CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking), fhc_destroy(c));
@@ -315,6 +319,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     CKG(cudaMalloc(&bt.dDepthRows, (size_t)seq->width * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dSched, sizeof(int) * (SC_WEIGHT + (size_t)c->maxFrames)), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dState, sizeof(PicState) * (size_t)c->maxFrames), fhc_destroy(c));
+    if (seq->waveFrontSynchro) CKG(cudaMalloc(&bt.dRows, sizeof(RowState) * (size_t)c->maxFrames * (size_t)((seq->height + 63) / 64)), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dProf, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaMemset(bt.dProf, 0, sizeof(long long) * 64 * (size_t)c->maxFrames), fhc_destroy(c));
     CKG(cudaHostAlloc(&bt.hFlags, sizeof(int32_t) * (size_t)c->maxFrames, cudaHostAllocMapped), fhc_destroy(c));
@@ -391,7 +396,7 @@ static int lone_pictures(const fhc_slice_params* sp, const std::vector<int>& ord
 // fills the ring of ready rows and launches the persistent kernel on the compute stream
 static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, const fhc_slice_params* sp, bool hinted = false)
 {
-  const int W = c->seq.width;
+  const int W = c->seq.width, wpp = c->seq.waveFrontSynchro;
   const size_t frameBytes = c->frameSamples * (size_t)sampleBytes;
   for (int i = 0; i < n; i++)
   {
@@ -414,6 +419,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
     d.state = bt->dState + i;
     d.prof = bt->dProf + 64 * (size_t)i;
     d.hints = hinted ? bt->dHints + (size_t)i * 4 * (size_t)c->numCtus : nullptr;
+    d.rows = wpp ? bt->dRows + (size_t)i * (size_t)((c->seq.height + 63) / 64) : nullptr;
     bt->hFlags[i] = 0;
     if (bt->hTrace) { d.trace = bt->dTrace + 8 * i; memset(bt->hTrace + 8 * i, 0, 32); }
   }
@@ -426,18 +432,21 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   // picture first; the scheduler words and the ring's initial part travel on the copy stream (pageable source: staged
   // before the call returns, and the copy stream is never behind a running kernel).
   const int rows = (c->seq.height + 63) / 64, ctusPerRow = (W + 63) / 64;
-  const int blocks = n < c->maxBlocks ? n : c->maxBlocks;
+  // blocks: one per picture is enough without wavefronts (a picture is one chain); with them every row is a chain
+  const long long chainsWanted = wpp ? (long long)n * rows : n;
+  const int blocks = chainsWanted < c->maxBlocks ? (int)chainsWanted : c->maxBlocks;
   {
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; i++) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[a].sliceQp < sp[b2].sliceQp; });    // expensive first
-    const int lone = lone_pictures(sp, order, n, blocks);
+    const int lone = wpp ? 0 : lone_pictures(sp, order, n, blocks);         // (wavefront: a picture is many chains, none of them pinned)
     c->hostSched.assign((size_t)SC_WEIGHT + (size_t)n, 0);
     for (int i = 0; i < n; i++)
       c->hostSched[(size_t)SC_WEIGHT + (size_t)order[(size_t)i]] = (int)(1000.0 * picture_weight(sp[order[(size_t)i]].sliceQp)) | (i < lone ? SC_LONE_BIT : 0);
   }
   CK(cudaMemcpyAsync(bt->dSched, c->hostSched.data(), sizeof(int) * c->hostSched.size(), cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaMemsetAsync(bt->dState, 0, sizeof(PicState) * (size_t)n, c->copyIn));
+  if (wpp) CK(cudaMemsetAsync(bt->dRows, 0, sizeof(RowState) * (size_t)n * (size_t)rows, c->copyIn));
 #ifdef FHC_PROFILE
   CK(cudaMemsetAsync(bt->dProf, 0, sizeof(long long) * 64 * (size_t)n, c->copyIn));
 #endif
@@ -450,7 +459,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   if (hinted) { const char* e = getenv("FHC_HINTED_CHAINS"); if (e && atoi(e) == 1) chains = 1; }
   CK(cudaEventRecord(bt->evStart, c->compute));
   fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, bt->dState, n, rows, ctusPerRow, bt->dSched, c->dWorkspace, c->wsPerBlock,
-                                                                                            c->smemBytes, c->dTables, chains);
+                                                                                            c->smemBytes, c->dTables, chains, wpp);
   CK(cudaGetLastError());
   CK(cudaEventRecord(bt->evStop, c->compute));
   g_launches++;

@@ -142,6 +142,15 @@ struct Sbac { uint8_t c[NUM_CTX]; uint64_t frac; };       // TEncSbac contexts +
 // Where a picture chain continues: pictures are scheduled CTU row by CTU row (a row may run on any block), so the one
 // thing that crosses a row boundary besides the line buffers - the CABAC contexts - is parked here in between.
 struct PicState { int32_t nextRow, status, pad[2]; Sbac ctx; };   // status: see the kernel's scheduler
+enum { ST_READY = 0, ST_RUNNING = 1, ST_FINISHED = 2 };
+// Wavefront pictures (entropy_coding_sync, HM --WaveFrontSynchro=1): the CTU rows of a picture are chains of their own.
+// TEncSlice::compressSlice resets the RD coder at the start of every CTU row - contexts AND the fractional-bit carry
+// (TEncSbac::resetEntropy -> TEncBinCABAC::start, TEncBinCoderCABAC.cpp:69-79 with FAST_BIT_EST) - and, when the
+// picture is at least two CTUs wide, loads the contexts saved after the second CTU of the row above
+// (TEncSlice.cpp:808-823, :925-928).  A row therefore depends on the row above only through those contexts and through
+// the neighbouring samples / CU depths of the CTUs up to above-right: CTU (r, x) may start when row r-1 has finished
+// min(x + 2, wc) CTUs.  progress = CTUs of the row finished (published after the results are visible).
+struct RowState { int32_t progress, pad[3]; Sbac sync; Sbac ctx; };   // ctx: where a row continues when a range ends inside it (emulation only)
 
 struct PicDesc                    // global memory, one per submitted picture (filled by the host)
 {
@@ -156,6 +165,7 @@ struct PicDesc                    // global memory, one per submitted picture (f
   int32_t* trace;                 // optional progress word (host-mapped): ctu << 12 | region z << 4 | stage; 0 = off
   long long* prof;                // [64] clock64 counters of the picture's block (FHC_PROFILE builds): [role][stage]
   const uint8_t* hints;           // CU-split hints of the CNN predictor [numCtus][4] (fasthevc_cuda.h: FHC_HINT_*) or null
+  RowState* rows;                 // wavefront pictures: [hc] per-row state (zeroed by the host); null = one chain per picture
 };
 
 struct PicParams                  // hot copy of the picture header (shared memory)
@@ -3040,7 +3050,7 @@ FHC_D void init_block(Blk* b, unsigned char* smemArena, unsigned char* globalAre
 // chains of a block advance CTU by CTU in lockstep (__syncthreads), a chain without work (pd == 0) only takes part in
 // the barriers.  The contexts come from the slice start (firstCtu == 0) or from pd->state, and go back there unless
 // the range ends the picture.
-FHC_D void compress_picture(Blk* b, const PicDesc* pd, int firstCtu, int count, int tid, int nthr)
+FHC_D void compress_picture(Blk* b, const PicDesc* pd, int firstCtu, int count, int tid, int nthr, int wpp = 0)   // wpp: the same for every chain of the launch
 {
   FHC_SHARED(b);
   if (tid == 0 && pd)
@@ -3059,28 +3069,78 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int firstCtu, int count, 
 #ifdef FHC_PROFILE
   const long long tPic = clock64();
 #endif
+  RowState* const rows = pd ? pd->rows : nullptr;                              // wavefront picture: this range lies inside one CTU row
+  const int wc = pd ? pd->wc : 1, row = firstCtu / wc;
   if (pd && tid < 32)
   {
-    if (firstCtu == 0) sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);      // slice start: resetEntropy (TEncSlice.cpp:719-720)
+    if (rows ? firstCtu == row * wc : firstCtu == 0)
+    {
+      sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);                         // slice start / wavefront row start: resetEntropy (TEncSlice.cpp:719-720, :815)
+      if (rows && row > 0 && wc >= 2)                                          // contexts after the second CTU of the row above (TEncSlice.cpp:817-827); the bit carry stays 0
+      {
+        __syncwarp();
+        while (*reinterpret_cast<volatile int32_t*>(&rows[row - 1].progress) < 2) __nanosleep(200);
+        __threadfence();
+        const int32_t* src = reinterpret_cast<const int32_t*>(rows[row - 1].sync.c);
+        int32_t* dst = reinterpret_cast<int32_t*>(b->curr[0].c);
+        for (int i = tid; i < NUM_CTX / 4; i += 32) dst[i] = ld_l2(src + i);
+        for (int i = (NUM_CTX & ~3) + tid; i < NUM_CTX; i += 32) b->curr[0].c[i] = (uint8_t)ld_l2(&rows[row - 1].sync.c[i]);
+      }
+    }
     else
     {
-      const int32_t* src = reinterpret_cast<const int32_t*>(&pd->state->ctx);
+      const int32_t* src = reinterpret_cast<const int32_t*>(rows ? &rows[row].ctx : &pd->state->ctx);
       int32_t* dst = reinterpret_cast<int32_t*>(&b->curr[0]);
       for (int i = tid; i < (int)(sizeof(Sbac) / 4); i += 32) dst[i] = ld_l2(src + i);
     }
   }
   for (int addr = firstCtu; addr < firstCtu + count; addr++)
   {
+    if (wpp)
+    {
+      // wavefront lag: the row above must have finished the CTU above-right of this one (the barrier is taken by every
+      // chain of the block, with or without a picture: the chains advance in lockstep)
+      if (rows && row > 0 && tid == 0)
+      {
+        const int need = imin(addr - row * wc + 2, wc);
+        while (*reinterpret_cast<volatile int32_t*>(&rows[row - 1].progress) < need) __nanosleep(200);
+        __threadfence();
+      }
+      __syncthreads();
+    }
     if (pd) load_ctu(b, addr, tid, nthr);
     __syncthreads();
     if (pd) { if (tid < 32) master_ctu(b); else role_loop(b, tid >> 5); }
     __syncthreads();
     if (pd) { store_ctu(b, tid, nthr); shift_left_neighbour(b, tid, nthr); }
+    if (wpp)
+    {
+      const int x = addr - row * wc;
+      if (rows && x == 1 && tid < 32)                                          // TEncSlice.cpp:925-928
+      {
+        const int32_t* src = reinterpret_cast<const int32_t*>(&b->curr[0]);
+        int32_t* dst = reinterpret_cast<int32_t*>(&rows[row].sync);
+        for (int i = tid; i < (int)(sizeof(Sbac) / 4); i += 32) dst[i] = src[i];
+      }
+      __threadfence();                   // this CTU's results, line-buffer segment and sync contexts are visible before its progress is
+      __syncthreads();
+      if (rows && tid == 0)
+      {
+        *reinterpret_cast<volatile int32_t*>(&rows[row].progress) = x + 1;
+        // the picture's next row may start on any chain slot once this one is two CTUs ahead
+        if (x + 1 == imin(2, wc) && row + 1 < pd->hc)
+        {
+          *reinterpret_cast<volatile int32_t*>(&pd->state->nextRow) = row + 1;
+          __threadfence();
+          *reinterpret_cast<volatile int32_t*>(&pd->state->status) = ST_READY;
+        }
+      }
+    }
     __syncthreads();
   }
   if (pd)
   {
-    if (!lastOfPicture && tid < 32)
+    if (!lastOfPicture && !rows && tid < 32)
     {
       const int32_t* src = reinterpret_cast<const int32_t*>(&b->curr[0]);
       int32_t* dst = reinterpret_cast<int32_t*>(&pd->state->ctx);
@@ -3097,16 +3157,34 @@ FHC_D void compress_picture(Blk* b, const PicDesc* pd, int firstCtu, int count, 
   }
 #endif
 #else
-  if (firstCtu == 0) sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);
-  else b->curr[0] = pd->state->ctx;
+  RowState* const rows = pd->rows;
+  const int wc = pd->wc, row = firstCtu / wc;
+  if (rows ? firstCtu == row * wc : firstCtu == 0)
+  {
+    sbac_reset(b->t, &b->curr[0], b->pp.sp.sliceQp);
+    if (rows && row > 0 && wc >= 2)
+    {
+      if (rows[row - 1].progress < 2) abort();                                 // the caller broke the wavefront order
+      for (int i = 0; i < NUM_CTX; i++) b->curr[0].c[i] = rows[row - 1].sync.c[i];
+    }
+  }
+  else b->curr[0] = rows ? rows[row].ctx : pd->state->ctx;
   for (int addr = firstCtu; addr < firstCtu + count; addr++)
   {
+    const int x = addr - row * wc;
+    if (rows && row > 0 && rows[row - 1].progress < imin(x + 2, wc)) abort();
     load_ctu(b, addr, 0, 1);
     master_ctu(b);
     store_ctu(b, 0, 1);
     shift_left_neighbour(b, 0, 1);
+    if (rows)
+    {
+      if (x == 1) rows[row].sync = b->curr[0];
+      rows[row].progress = x + 1;
+    }
   }
-  if (!lastOfPicture) pd->state->ctx = b->curr[0];
+  if (rows) { if (firstCtu + count < (row + 1) * wc) rows[row].ctx = b->curr[0]; }
+  else if (!lastOfPicture) pd->state->ctx = b->curr[0];
 #endif
 }
 

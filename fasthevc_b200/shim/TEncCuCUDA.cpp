@@ -140,6 +140,7 @@ static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
     p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
     p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
     p.maxFramesInFlight = n;
+    p.waveFrontSynchro = enc->m_pcEncCfg->getEntropyCodingSyncEnabledFlag() ? 1 : 0;
     if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
     g_width = w; g_height = h; g_bitDepth = bd; g_maxFrames = n;
   }

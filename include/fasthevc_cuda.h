@@ -43,6 +43,10 @@ typedef struct fhc_seq_params
   int32_t strongIntraSmoothing;     /* must be 1 */
   int32_t fastUdiUseMpm;            /* must be 1 */
   int32_t maxFramesInFlight;        /* device buffers are sized for this many pictures per submit */
+  int32_t waveFrontSynchro;         /* 0, or 1 = --WaveFrontSynchro=1 (entropy_coding_sync_enabled_flag): the RD coder is
+                                     * reset at every CTU row start and synchronised with the row above
+                                     * (TEncSlice.cpp:808-823, :925-928), so the CTU rows of a picture are searched
+                                     * concurrently with a two-CTU lag.  Results equal the reference run with the same flag. */
 } fhc_seq_params;
 
 /* Per-picture parameters computed by the UNCHANGED host code

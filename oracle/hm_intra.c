@@ -2334,7 +2334,14 @@ int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const ui
 int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb, const uint16_t* orgCr,
                                      hm_ctu_out* out, const uint8_t* hints)
 {
+  return hm_intra_compress_picture_ex(p, orgY, orgCb, orgCr, out, hints, 0);
+}
+
+int hm_intra_compress_picture_ex(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb, const uint16_t* orgCr,
+                                 hm_ctu_out* out, const uint8_t* hints, int waveFrontSynchro)
+{
   Enc* e = (Enc*)calloc(1, sizeof(Enc));
+  Sbac syncState;                                   /* TEncSlice::m_entropyCodingSyncContextState */
   const uint16_t* src[3];
   int c, i, d, addr;
   static CU view;
@@ -2378,6 +2385,14 @@ int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, c
     /* initCtu (TComDataCU.cpp:422) */
     memset(o, 0, sizeof(*o));
     memset(o->partSize, SIZE_NONE, 256); memset(o->predMode, MODE_NONE, 256); memset(o->lumaDir, DC_IDX, 256);
+    if (waveFrontSynchro && e->ctuX == 0 && addr > 0)
+    {
+      /* TEncSlice.cpp:812-827: reset (TEncSbac::resetEntropy ends in TEncBinCABAC::start, which with FAST_BIT_EST also
+       * clears the fractional-bit carry, TEncBinCoderCABAC.cpp:69-79), then the contexts saved after the second CTU of
+       * the row above when the above-right CTU exists (loadContexts copies the context models only) */
+      sbac_reset(&e->slot[0][CI_CURR_BEST], p->qp);
+      if (e->wc >= 2) memcpy(e->slot[0][CI_CURR_BEST].c, syncState.c, sizeof(syncState.c));
+    }
     sb_copy(&e->go, &e->slot[0][CI_CURR_BEST]);                      /* TEncSlice.cpp:829 */
     for (d = 0; d < 2; d++)
     {
@@ -2391,6 +2406,7 @@ int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, c
     reset_bits(e);
     encode_ctu_rec(e, &view, 0, 0);
     sb_copy(&e->slot[0][CI_CURR_BEST], &e->go);
+    if (waveFrontSynchro && e->ctuX == 1) sb_copy(&syncState, &e->slot[0][CI_CURR_BEST]);      /* TEncSlice.cpp:925-928 */
     /* reconstruction of the CTU area for the record */
     for (c = 0; c < 3; c++)
     {

@@ -61,6 +61,12 @@ int hm_intra_compress_picture(const hm_params* p, const uint16_t* orgY, const ui
 int hm_intra_compress_picture_hinted(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb,
                                      const uint16_t* orgCr, hm_ctu_out* out, const uint8_t* hints);
 
+/* General form: hints as above (or NULL); waveFrontSynchro = 1 restates --WaveFrontSynchro=1
+ * (TEncSlice.cpp:808-827, :925-928: the RD coder is reset at every CTU row start and takes the contexts saved after
+ * the second CTU of the row above).  Pinned against oracle/_ref/TAppEncoderDump run with that flag. */
+int hm_intra_compress_picture_ex(const hm_params* p, const uint16_t* orgY, const uint16_t* orgCb,
+                                 const uint16_t* orgCr, hm_ctu_out* out, const uint8_t* hints, int waveFrontSynchro);
+
 /* Stage trace for tests (see hm_intra.c): records go to `path` until it is called again with NULL. */
 void hm_intra_set_trace(const char* path);
 

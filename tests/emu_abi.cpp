@@ -8,8 +8,9 @@
 #include <vector>
 #include "../include/fasthevc_cuda.h"
 
-extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
-                                               const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints);
+extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                           const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
+                                           int wpp, int order);
 
 struct fhc_ctx { fhc_seq_params seq; int poc, n, numCtus; std::vector<fhc_ctu_result> out; };
 
@@ -39,8 +40,9 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
   for (int k = 0; k < n; k++)
   {
     const unsigned char* p = (const unsigned char*)yuv + frame * k;
-    int rc = fhc_emu_compress_picture_hinted(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
-                                             c->out.data() + (size_t)c->numCtus * k, hints ? hints + (size_t)4 * c->numCtus * k : NULL);
+    int rc = fhc_emu_compress_picture_ex(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
+                                         c->out.data() + (size_t)c->numCtus * k, hints ? hints + (size_t)4 * c->numCtus * k : NULL,
+                                         c->seq.waveFrontSynchro, 2);
     if (rc) return rc;
   }
   return FHC_OK;

@@ -10,22 +10,41 @@
 
 extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                                const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints);
+extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                           const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
+                                           int wpp, int order);
 extern "C" int fhc_emu_compress_picture(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                         const void* y, const void* cb, const void* cr, fhc_ctu_result* out)
 {
-  return fhc_emu_compress_picture_hinted(width, height, bitDepth, sampleBytes, sp, y, cb, cr, out, nullptr);
+  return fhc_emu_compress_picture_ex(width, height, bitDepth, sampleBytes, sp, y, cb, cr, out, nullptr, 0, 0);
 }
 extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                                const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints)
 {
+  return fhc_emu_compress_picture_ex(width, height, bitDepth, sampleBytes, sp, y, cb, cr, out, hints, 0, 0);
+}
+// wpp = 1: wavefront picture (PicDesc::rows).  order: 0 = row after row; 1 / 2 = the tightest interleaving the device may
+// produce - every row exactly two CTUs behind the row above, one CTU per call, each row on a block of its own - with
+// the rows of a time step visited top-down (1) or bottom-up (2).  The engine aborts if a call breaks the wavefront lag.
+extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
+                                           const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
+                                           int wpp, int order)
+{
   using namespace fhc;
   size_t smemBytes, globalBytes;
   block_footprint(&smemBytes, &globalBytes);
-  // two blocks that take the CTU rows of the picture in turn, as two SMs may on the device: nothing but PicState,
-  // the line buffers and the results may carry over from one row to the next
-  unsigned char *sm[2], *gm[2];
-  Blk* blk[2];
-  for (int k = 0; k < 2; k++)
+  PicDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.org[0] = y; pd.org[1] = cb; pd.org[2] = cr;
+  pd.out = out; pd.sp = *sp; pd.width = width; pd.height = height; pd.bitDepth = bitDepth; pd.sampleBytes = sampleBytes;
+  pd.wc = (width + 63) / 64; pd.hc = (height + 63) / 64;
+  pd.hints = hints;
+  // blocks that take the CTU rows of the picture in turn, as different SMs may on the device: nothing but PicState /
+  // RowState, the line buffers and the results may carry over from one row to the next
+  const int nblk = (wpp && order) ? pd.hc : 2;
+  std::vector<unsigned char*> sm((size_t)nblk), gm((size_t)nblk);
+  std::vector<Blk*> blk((size_t)nblk);
+  for (int k = 0; k < nblk; k++)
   {
     sm[k] = (unsigned char*)calloc(1, smemBytes);
     gm[k] = (unsigned char*)calloc(1, globalBytes);
@@ -34,12 +53,6 @@ extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDep
     init_block(blk[k], sm[k] + ((sizeof(Blk) + 15) & ~(size_t)15), gm[k]);
     blk[k]->inst = 0; blk[k]->twin = 0;
   }
-  PicDesc pd;
-  memset(&pd, 0, sizeof(pd));
-  pd.org[0] = y; pd.org[1] = cb; pd.org[2] = cr;
-  pd.out = out; pd.sp = *sp; pd.width = width; pd.height = height; pd.bitDepth = bitDepth; pd.sampleBytes = sampleBytes;
-  pd.wc = (width + 63) / 64; pd.hc = (height + 63) / 64;
-  pd.hints = hints;
   std::vector<int16_t> lines((size_t)width * 4);
   std::vector<uint8_t> depthRows((size_t)width);
   for (int k = 0; k < 2; k++)
@@ -52,8 +65,22 @@ extern "C" int fhc_emu_compress_picture_hinted(int width, int height, int bitDep
   PicState state;
   memset(&state, 0, sizeof(state));
   pd.state = &state;
-  for (int row = 0; row < pd.hc; row++) compress_picture(blk[row & 1], &pd, row * pd.wc, pd.wc, 0, 1);
-  for (int k = 0; k < 2; k++) { free(sm[k]); free(gm[k]); }
+  std::vector<RowState> rows((size_t)pd.hc);
+  memset(rows.data(), 0, sizeof(RowState) * rows.size());
+  if (wpp) pd.rows = rows.data();
+  if (!(wpp && order))
+    for (int row = 0; row < pd.hc; row++) compress_picture(blk[row & 1], &pd, row * pd.wc, pd.wc, 0, 1, wpp);
+  else
+  {
+    const int lag = pd.wc >= 2 ? 2 : 1;
+    for (int t = 0; t < pd.wc + lag * (pd.hc - 1); t++)
+      for (int k = 0; k < pd.hc; k++)
+      {
+        const int row = order == 1 ? k : pd.hc - 1 - k, x = t - lag * row;
+        if (x >= 0 && x < pd.wc) compress_picture(blk[row], &pd, row * pd.wc + x, 1, 0, 1, wpp);
+      }
+  }
+  for (int k = 0; k < nblk; k++) { free(sm[k]); free(gm[k]); }
   return 0;
 }
 // work counters since the last reset: out[0..7] = TU-pipeline samples [luma,chroma][4x4,8x8,16x16,32x32], out[8..15] = TU codings

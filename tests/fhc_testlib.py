@@ -59,6 +59,8 @@ def oracle():
         lib.hm_intra_compress_picture.restype = C.c_int
         lib.hm_intra_compress_picture_hinted.argtypes = [C.POINTER(HmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hm_intra_compress_picture_hinted.restype = C.c_int
+        lib.hm_intra_compress_picture_ex.argtypes = [C.POINTER(HmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.hm_intra_compress_picture_ex.restype = C.c_int
         _oracle = lib
     return _oracle
 
@@ -83,13 +85,19 @@ def n_ctus(width, height):
     return ((width + 63) // 64) * ((height + 63) // 64)
 
 
-def oracle_compress(params, y, u, v, hints=None):
+def oracle_compress(params, y, u, v, hints=None, wpp=False):
     """y,u,v: 2-D arrays (any integer dtype); hints: None or uint8 [numCtus][4] (0 none / 1 do not split / 2 split, the
     depth-1 CUs of a CTU in z-order).  Returns CTU_OUT_DT array."""
     n = n_ctus(params.width, params.height)
     out = np.zeros(n, CTU_OUT_DT)
     planes = [np.ascontiguousarray(p, dtype=np.uint16) for p in (y, u, v)]
-    if hints is None:
+    if wpp:
+        if hints is not None:
+            hints = np.ascontiguousarray(hints, dtype=np.uint8)
+            assert hints.size == 4 * n
+        rc = oracle().hm_intra_compress_picture_ex(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data,
+                                                   out.ctypes.data, hints.ctypes.data if hints is not None else None, 1)
+    elif hints is None:
         rc = oracle().hm_intra_compress_picture(C.byref(params), planes[0].ctypes.data, planes[1].ctypes.data,
                                                 planes[2].ctypes.data, out.ctypes.data)
     else:
@@ -120,7 +128,7 @@ def hints_from_split(width, height, split):
 
 def _oracle_job(job):
     (w, h, bd, qp), y, u, v = job[:4]
-    return oracle_compress(params_from_qp(w, h, bd, qp), y, u, v, job[4] if len(job) > 4 else None)
+    return oracle_compress(params_from_qp(w, h, bd, qp), y, u, v, job[4] if len(job) > 4 else None, job[5] if len(job) > 5 else False)
 
 
 def oracle_compress_parallel(jobs):
@@ -224,7 +232,7 @@ class FhcSeqParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitDepth", "chromaFormat", "ctuSize", "maxCuDepth", "tuLog2Max",
                                          "tuLog2Min", "tuMaxDepthIntra", "useRdoq", "useRdoqTs", "useTransformSkip",
                                          "useTransformSkipFast", "signHideFlag", "strongIntraSmoothing", "fastUdiUseMpm",
-                                         "maxFramesInFlight")]
+                                         "maxFramesInFlight", "waveFrontSynchro")]
 
 
 def slice_params_from_hm(p):
@@ -253,7 +261,7 @@ def build_emu():
 _emu = None
 
 
-def emu_compress(params, y, u, v, hints=None):
+def emu_compress(params, y, u, v, hints=None, wpp=False, order=0):
     global _emu
     if _emu is None:
         _emu = C.CDLL(build_emu())
@@ -261,12 +269,21 @@ def emu_compress(params, y, u, v, hints=None):
                                                   C.c_void_p, C.c_void_p, C.c_void_p]
         _emu.fhc_emu_compress_picture_hinted.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _emu.fhc_emu_compress_picture_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     sb = 1 if params.bitDepth == 8 else 2
     dt = np.uint8 if sb == 1 else np.uint16
     planes = [np.ascontiguousarray(p, dtype=dt) for p in (y, u, v)]
     out = np.zeros(n_ctus(params.width, params.height), CTU_OUT_DT)
     sp = slice_params_from_hm(params)
-    if hints is None:
+    if wpp:
+        if hints is not None:
+            hints = np.ascontiguousarray(hints, dtype=np.uint8)
+            assert hints.size == 4 * len(out)
+        rc = _emu.fhc_emu_compress_picture_ex(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
+                                              planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data,
+                                              hints.ctypes.data if hints is not None else None, 1, int(order))
+    elif hints is None:
         rc = _emu.fhc_emu_compress_picture(params.width, params.height, params.bitDepth, sb, C.byref(sp), planes[0].ctypes.data,
                                            planes[1].ctypes.data, planes[2].ctypes.data, out.ctypes.data)
     else:
@@ -283,3 +300,63 @@ def decoder_md5_ok(bitstream_path, workdir):
     r = subprocess.run([os.path.join(REF_DIR, "TAppDecoder"), "-b", bitstream_path, "-o", os.path.join(workdir, "dec.yuv")],
                        capture_output=True, text=True, cwd=workdir)
     return r.stdout.count("(OK)"), ("ERROR" in r.stdout or r.returncode != 0)
+
+
+# --- full-size expectations: per-CTU CRC-32 fixtures of the ORACLE's records ----------------------------------------
+# A 2160p picture costs the oracle minutes of one host core; the GPU box's minutes are better spent on the GPU.  The
+# oracle's records for the full-size test pictures are therefore computed in the container (tests/golden/
+# make_fullsize_crc.py) and committed as one CRC-32 per CTU over every compared field; a mismatch falls back to the
+# oracle itself to name the field.
+FULLSIZE_CASES = {
+    # tag: (width, height, bit depth, sigma, seed, [qp per picture], wavefront)
+    "1080p": (1920, 1080, 8, 6.0, 1234, [22, 27, 32, 37], False),
+    "2160p_main10": (3840, 2160, 10, 6.0, 31, [27], False),
+    "1080p_wpp": (1920, 1080, 8, 6.0, 1234, [22, 27, 32, 37], True),
+    "2160p_main10_wpp": (3840, 2160, 10, 6.0, 31, [27], True),
+}
+
+
+def ctu_crcs(recs):
+    import zlib
+    out = np.zeros(len(recs), np.uint32)
+    for i in range(len(recs)):
+        c = 0
+        for f in FIELDS:
+            a = recs[i][f]
+            a = np.float64(a) if f == "totalCost" else np.asarray(a).astype(np.int32)
+            c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+        out[i] = c
+    return out
+
+
+def fullsize_frames(tag):
+    from fasthevc_b200.synth import synth_frames
+    w, h, bd, sigma, seed, qps, wpp = FULLSIZE_CASES[tag]
+    return synth_frames(w, h, len(qps), bit_depth=bd, sigma=sigma, seed=seed)
+
+
+def fullsize_jobs(tag):
+    w, h, bd, sigma, seed, qps, wpp = FULLSIZE_CASES[tag]
+    Y, U, V = fullsize_frames(tag)
+    return [((w, h, bd, qps[k]), Y[k], U[k], V[k], None, wpp) for k in range(len(qps))]
+
+
+def check_fullsize(tag, got):
+    """got: list of CTU record arrays, one per picture of the case.  Returns the list of mismatches."""
+    path = os.path.join(GOLDEN, "fullsize_%s.npz" % tag)
+    jobs = fullsize_jobs(tag)
+    if os.path.exists(path):
+        want = np.load(path)["crc"]
+        assert want.shape == (len(got), len(got[0]))
+        wrong = [k for k in range(len(got)) if not np.array_equal(ctu_crcs(got[k]), want[k])]
+        if not wrong:
+            return []
+        bad = []
+        for k in wrong:
+            bad += compare_ctus(got[k], _oracle_job(jobs[k]), "%s pic%d" % (tag, k)) or ["%s pic%d: CRC differs" % (tag, k)]
+        return bad
+    ref = oracle_compress_parallel(jobs)
+    bad = []
+    for k in range(len(got)):
+        bad += compare_ctus(got[k], ref[k], "%s pic%d" % (tag, k))
+    return bad

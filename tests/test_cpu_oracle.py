@@ -15,7 +15,7 @@ import pytest
 import fhc_testlib as T
 from fasthevc_b200.synth import synth_frames, write_yuv
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_", "wpp_", "fullsize_")))
 
 
 def load_golden(path):
