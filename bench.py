@@ -112,36 +112,56 @@ def run_ours(args, rank, world, local_rank):
     int_peak_gops, _ = fh.measure_int_issue(local_rank)
 
     first_result_s = []
+    # Pipelined submits (fhc_configure FHC_OPT_PIPELINED_SUBMITS): step s+1 is submitted before the results of step s are
+    # fetched, so its host->device copy and the head of its kernel overlap the tail of step s (two submits may be outstanding).
+    enc.set_pipelined(not args.no_pipeline)
+    poc_next = [0]
 
-    def step():
-        """One pass over the 256 pictures with host buffers; returns (kernel ms, sum of CTU bit counts)."""
+    def submit_step():
+        first = poc_next[0]
+        poc_next[0] += n_jobs
+        enc.submit(host_in, sps, first_poc=first)
+        return first, time.perf_counter()
+
+    def fetch_step(first, t_sub):
         bits = 0
-        t_sub = time.perf_counter()
-        enc.submit(host_in, sps)
         for j in range(n_jobs):
-            enc.fetch_picture_async(j, host_out[j % RING])
+            enc.fetch_picture_async(first + j, host_out[j % RING])
             if j % RING == RING - 1 or j == n_jobs - 1:
                 enc.fetch_sync()
                 if j < RING:
                     first_result_s.append(time.perf_counter() - t_sub)
                 bits += int(host_out[:(j % RING) + 1]["totalBits"].sum(dtype=np.int64))
-        return enc.last_kernel_ms(), bits
+        return bits
+
+    def run_steps(k):
+        """k passes over the 256 pictures with host buffers; returns the sum of the CTU bit counts."""
+        bits = 0
+        pending = submit_step()
+        for _ in range(1, k):
+            if args.no_pipeline:
+                bits += fetch_step(*pending)
+                pending = submit_step()
+            else:
+                nxt = submit_step()
+                bits += fetch_step(*pending)
+                pending = nxt
+        return bits + fetch_step(*pending)
 
     t_w = time.perf_counter()
-    for _ in range(args.warmup):
-        step()
+    if args.warmup:
+        run_steps(args.warmup)
     t_w = time.perf_counter() - t_w
 
     sampler = ClockSampler(local_rank)
     launches0 = int(enc.lib.fhc_launch_count())
-    check_bits, kernel_ms = 0, []
+    del first_result_s[:]
     sampler.start()
     barrier()
+    enc.span_begin()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ms, bits = step()
-        kernel_ms.append(ms)
-        check_bits += bits
+    check_bits = run_steps(args.steps)
+    my_ms = enc.span_ms()                      # device time from the first kernel's start to the last kernel's end
     e2e_local = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -150,12 +170,11 @@ def run_ours(args, rank, world, local_rank):
     in_flight = fh.pictures_in_flight(local_rank)
     guided = wavefront = None
     if rank == 0 and world == 1 and not args.no_cnn:
-        guided = cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, local_rank)
+        guided = cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, local_rank, poc_next[0] - n_jobs, poc_next[0])
     if rank == 0 and world == 1 and not args.no_wpp:
         wavefront = wavefront_leg(fh, host_in, host_out, sps, n_jobs, local_rank)
     enc.close()
 
-    my_ms = float(np.sum(kernel_ms))
     per_rank = [[my_ms / args.steps, e2e_local / args.steps]]
     if dist is not None:
         t = torch.tensor([my_ms, e2e_ms], dtype=torch.float64)
@@ -190,11 +209,13 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "BASELINE configs[1]: encoder_intra_main.cfg %dx%d 8-bit, %d-frame synthetic clip per GPU x QP{22,27,32,37} = "
                                    "%d picture jobs per GPU per step (one kernel launch; picture chains are scheduled CTU row by CTU row "
                                    "over %d chain slots per GPU, most work left first, the most expensive pictures alone in their block); "
-                                   "warm-up steps are full steps" % (W, H, n_frames, n_jobs, in_flight),
+                                   "warm-up steps are full steps; %s" % (W, H, n_frames, n_jobs, in_flight,
+                                                                   "one submit at a time" if args.no_pipeline else "steps are pipelined: step s+1 is submitted before the results of step s are fetched (two submits in flight, their kernels overlap at the tail)"),
                        "jobs_per_gpu": n_jobs, "ctus_per_picture": CTUS, "parallelism": "frame-group dp%d, no collective, no NCCL" % world,
                        "l2_policy": "inputs + results of a step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (n_jobs * (3.1 + 14.1) / 1e3)},
             "ctu_per_s": round(fps * CTUS, 1),
-            "first_results_s": round(float(np.median(first_result_s)), 3),      # submit -> first 8 pictures on the host (the scheduler lets pictures finish together)
+            "first_results_s": round(float(first_result_s[0]), 3),      # first submit of the timed region -> first 8 pictures on the host (the scheduler lets pictures finish together)
+            "pipelined_submits": not args.no_pipeline,
             "e2e": {"value": round(e2e_fps, 4), "unit": "frames/s", "h2d_bytes_per_step": int(host_in.nbytes) * world,
                     "d2h_bytes_per_step": rec_bytes * n_jobs * world, "ms_per_step": round(e2e_ms / args.steps, 2)},
             "per_rank_ms_per_step": {"kernel_e2e": per_rank},
@@ -256,7 +277,7 @@ def wavefront_leg(fh, host_in, host_out, sps, n_jobs, device):
                     "headline's, byte-identical to the reference run with the flag); single_picture_ms = one QP-22 picture alone on the device"}
 
 
-def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device):
+def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device, resident_poc, free_poc):
     """BASELINE configs[4] ("C2 with CNN-guided split"), one extra step after the timed region - NOT part of `value`:
     the tcgen05 split predictor (libfasthevc_cnn.so) runs on the pictures resident in the engine's input buffer, its
     decisions become fhc_submit_frames_hinted's hints, and the same 256 jobs are searched with them.  Nothing trained
@@ -264,7 +285,7 @@ def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device):
     CUs are split; the decisions equal those of the reference carrying the hook patch (tests/test_hints.py), not HM's."""
     from fasthevc_b200 import cnn
     wts = cnn.seeded_weights()
-    dptr, _ = enc.device_picture_ptr(0)
+    dptr, _ = enc.device_picture_ptr(resident_poc)          # the pictures of the last timed step are still on the device
     sp = cnn.SplitPredictor(wts, device)
     logits, _ = sp.predict_device(dptr, 1, 8, W, H, n_jobs)
     wts["fc_b"] = np.array([0.0, -float(np.median(logits[..., 1] - logits[..., 0]))], np.float32)
@@ -278,9 +299,9 @@ def cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, device):
     sp.close()
     hints = cnn.hints_from_split(W, H, split)
     t0 = time.perf_counter()
-    enc.submit(host_in, sps, first_poc=n_jobs, hints=hints)
+    enc.submit(host_in, sps, first_poc=free_poc, hints=hints)
     for j in range(n_jobs):
-        enc.fetch_picture_async(n_jobs + j, host_out[j % RING])
+        enc.fetch_picture_async(free_poc + j, host_out[j % RING])
         if j % RING == RING - 1 or j == n_jobs - 1:
             enc.fetch_sync()
     wall = time.perf_counter() - t0
@@ -399,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CLIP, help="frames of the clip per GPU (64 = configs[1]; anything else is a self-test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one submit at a time: a step ends before the next one is submitted")
     ap.add_argument("--no-wpp", action="store_true", help="skip the extra wavefront step (--WaveFrontSynchro=1) after the timed region")
     ap.add_argument("--no-cnn", action="store_true", help="skip the extra CNN-guided step (BASELINE configs[4]) after the timed region")
     ap.add_argument("--size", default="1920x1080", help="picture size; anything but the default is a script self-test, not the metric")

@@ -33,7 +33,7 @@ using namespace fhc;
 // sched[SC_FINISHED] = finished pictures, sched[SC_IDLE] = blocks without a chain, sched[SC_WEIGHT + p] = cost weight of
 // picture p | SC_LONE_BIT.
 // ----------------------------------------------------------------------------------------------
-enum { SC_FINISHED = 0, SC_IDLE = 1, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
+enum { SC_FINISHED = 0, SC_IDLE = 1, SC_ALIVE = 2, SC_WEIGHT = 8, SC_LONE_BIT = 1 << 30 };
 
 // picture index, -1 = nothing ready now, -2 = every picture is finished
 __device__ __forceinline__ int sched_take(PicState* states, int* sched, int numPics, int rowsPerPic, int allowLone, int* lone)
@@ -62,7 +62,7 @@ __device__ __forceinline__ int sched_take(PicState* states, int* sched, int numP
 
 __global__ void __launch_bounds__(FHC_BLOCK_THREADS, FHC_BLOCKS_PER_SM)
 fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPic, int ctusPerRow, int* sched, unsigned char* workspace, size_t wsPerChain,
-               size_t smemPerChain, const Tables* tables, int chainsPerBlock, int wpp)
+               size_t smemPerChain, const Tables* tables, int chainsPerBlock, int wpp, int packTail)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sItem[FHC_PICS_PER_BLOCK], sShape[FHC_PICS_PER_BLOCK], sPinned, sExit, sIdle;
@@ -106,7 +106,7 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
         {
           if (sPinned) { if (k == 0) any = 1; else sItem[k] = -1; continue; }      // slot 0 keeps its lone picture, the others stay empty
           if (k >= chainsPerBlock) { sItem[k] = -1; continue; }                    // experiments: fewer chains per block
-          if (k > 0 && *reinterpret_cast<volatile int*>(sched + SC_IDLE) > 0) { sItem[k] = -1; continue; }   // a block without any chain goes first
+          if (k > 0 && !packTail && *reinterpret_cast<volatile int*>(sched + SC_IDLE) > 0) { sItem[k] = -1; continue; }   // a block without any chain goes first
           int lone = 0;
           const int item = sched_take(states, sched, numPics, rowsPerPic, k == 0, &lone);
           sItem[k] = item >= 0 ? item : -1;
@@ -120,6 +120,16 @@ fhc_ctu_kernel(const PicDesc* pics, PicState* states, int numPics, int rowsPerPi
         }
         if (any) break;
         if (never) { sExit = 1; break; }
+        if (packTail)
+        {
+          // Pipelined submits: the next submit's kernel is queued behind this one and starts on whatever SMs this one
+          // frees.  A block that finds nothing to do leaves as soon as the pictures still unfinished fit into the chain
+          // slots of the blocks that stay (the invariant alive * chainsPerBlock >= unfinished holds at every exit).
+          const int unfinished = numPics - *reinterpret_cast<volatile int*>(sched + SC_FINISHED);
+          const int old = atomicSub(sched + SC_ALIVE, 1);
+          if ((old - 1) * chainsPerBlock >= unfinished) { sExit = 1; break; }
+          atomicAdd(sched + SC_ALIVE, 1);
+        }
         if (!sIdle) { sIdle = 1; atomicAdd(sched + SC_IDLE, 1); }
         __nanosleep(5000);
       }
@@ -201,6 +211,8 @@ struct Batch
   int* dSched = nullptr;                  // scheduler words + ring of ready rows (see the kernel)
   PicState* dState = nullptr;             // [maxFrames] where every picture chain continues
   RowState* dRows = nullptr;              // wavefront sequences: [maxFrames][rows]
+  cudaStream_t compute = nullptr;         // the batch's kernel stream: kernels of two submits may overlap (pipelined submits)
+  unsigned char* dWorkspace = nullptr;    // per-chain scratch of the batch's kernel
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
   int firstPoc = 0, n = 0, launched = 0;
   uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
@@ -212,8 +224,10 @@ struct fhc_ctx
   int device = 0, numCtus = 0, maxFrames = 0, maxBlocks = 0;
   size_t lumaSamples = 0, frameSamples = 0, smemBytes = 0, wsPerBlock = 0;   // smemBytes / wsPerBlock: per picture chain
   Tables* dTables = nullptr;
-  unsigned char* dWorkspace = nullptr;
-  cudaStream_t compute = nullptr, copyIn = nullptr, copyOut = nullptr;
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  int pipelined = 0;                       // FHC_OPT_PIPELINED_SUBMITS
+  cudaEvent_t evSpan = nullptr;            // fhc_span_begin: recorded before the next launch's kernel
+  int spanArmed = 0, spanOpen = 0;
   Batch batch[FHC_BATCHES];
   uint64_t submits = 0;
   std::vector<PicDesc> hostPics;
@@ -248,7 +262,8 @@ static int kernel_geometry(int device, size_t* smemBytes, size_t* wsPerBlock, in
 
 static void free_batch(Batch& bt)
 {
-  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dRows); cudaFree(bt.dProf); cudaFree(bt.dHints);
+  cudaFree(bt.dPics); cudaFree(bt.dIn); cudaFree(bt.dOut); cudaFree(bt.dLines); cudaFree(bt.dDepthRows); cudaFree(bt.dSched); cudaFree(bt.dState); cudaFree(bt.dRows); cudaFree(bt.dProf); cudaFree(bt.dHints); cudaFree(bt.dWorkspace);
+  if (bt.compute) cudaStreamDestroy(bt.compute);
   if (bt.hFlags) cudaFreeHost(bt.hFlags);
   if (bt.hTrace) cudaFreeHost(bt.hTrace);
   if (bt.evCopied) cudaEventDestroy(bt.evCopied);
@@ -261,12 +276,12 @@ int fhc_destroy(fhc_ctx* c)
 {
   if (!c) return FHC_ERR_ARG;
   cudaSetDevice(c->device);
-  if (c->compute) cudaStreamSynchronize(c->compute);
+  for (int i = 0; i < FHC_BATCHES; i++) if (c->batch[i].compute) cudaStreamSynchronize(c->batch[i].compute);
   if (c->copyIn) cudaStreamSynchronize(c->copyIn);
   if (c->copyOut) cudaStreamSynchronize(c->copyOut);
   for (int i = 0; i < FHC_BATCHES; i++) free_batch(c->batch[i]);
-  cudaFree(c->dTables); cudaFree(c->dWorkspace);
-  if (c->compute) cudaStreamDestroy(c->compute);
+  cudaFree(c->dTables);
+  if (c->evSpan) cudaEventDestroy(c->evSpan);
   if (c->copyIn) cudaStreamDestroy(c->copyIn);
   if (c->copyOut) cudaStreamDestroy(c->copyOut);
   delete c;
@@ -303,8 +318,7 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
     if (c->maxBlocks > chains) c->maxBlocks = (int)chains;
   }
   CKG(cudaMalloc(&c->dTables, sizeof(Tables)), fhc_destroy(c));
-  CKG(cudaMalloc(&c->dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK), fhc_destroy(c));
-  CKG(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking), fhc_destroy(c));
+  CKG(cudaEventCreate(&c->evSpan), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->copyIn, cudaStreamNonBlocking), fhc_destroy(c));
   CKG(cudaStreamCreateWithFlags(&c->copyOut, cudaStreamNonBlocking), fhc_destroy(c));
   const size_t inBytes = c->frameSamples * (size_t)(seq->bitDepth > 8 ? 2 : 1);
@@ -312,6 +326,8 @@ int fhc_create(const fhc_seq_params* seq, int device, fhc_ctx** out)
   {
     Batch& bt = c->batch[i];
     CKG(cudaMalloc(&bt.dPics, sizeof(PicDesc) * (size_t)c->maxFrames), fhc_destroy(c));
+    CKG(cudaMalloc(&bt.dWorkspace, c->wsPerBlock * (size_t)c->maxBlocks * FHC_PICS_PER_BLOCK), fhc_destroy(c));
+    CKG(cudaStreamCreateWithFlags(&bt.compute, cudaStreamNonBlocking), fhc_destroy(c));
     CKG(cudaMalloc(&bt.dIn, inBytes * (size_t)c->maxFrames), fhc_destroy(c));
     bt.inBytesPerFrame = inBytes;
     CKG(cudaMalloc(&bt.dOut, sizeof(fhc_ctu_result) * (size_t)c->numCtus * (size_t)c->maxFrames), fhc_destroy(c));
@@ -427,7 +443,7 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   // queued behind a running kernel does not wait for it on the host
   CK(cudaMemcpyAsync(bt->dPics, c->hostPics.data(), sizeof(PicDesc) * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
-  CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
+  CK(cudaStreamWaitEvent(bt->compute, bt->evCopied, 0));
   // Work distribution (see the kernel): the ring starts with every picture's first row, most expensive (lowest QP)
   // picture first; the scheduler words and the ring's initial part travel on the copy stream (pageable source: staged
   // before the call returns, and the copy stream is never behind a running kernel).
@@ -435,12 +451,18 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   // blocks: one per picture is enough without wavefronts (a picture is one chain); with them every row is a chain
   const long long chainsWanted = wpp ? (long long)n * rows : n;
   const int blocks = chainsWanted < c->maxBlocks ? (int)chainsWanted : c->maxBlocks;
+  // Pipelined submits (FHC_OPT_PIPELINED_SUBMITS): the host keeps a second submit queued, so what counts is the throughput
+  // across submits, not the makespan of one.  No picture runs alone in its block (pairs of twin-aligned chains get the
+  // most out of an SM), and the blocks of a kernel leave as soon as the remaining pictures fit into the
+  // others, so that the next submit's kernel - queued on its own stream, with its own scratch - fills the freed SMs.
+  const int pack = c->pipelined && !hinted ? 1 : 0;
   {
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; i++) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return sp[a].sliceQp < sp[b2].sliceQp; });    // expensive first
-    const int lone = wpp ? 0 : lone_pictures(sp, order, n, blocks);         // (wavefront: a picture is many chains, none of them pinned)
+    const int lone = (wpp || pack) ? 0 : lone_pictures(sp, order, n, blocks);         // (wavefront: a picture is many chains, none of them pinned; pipelined: see below)
     c->hostSched.assign((size_t)SC_WEIGHT + (size_t)n, 0);
+    c->hostSched[SC_ALIVE] = blocks;
     for (int i = 0; i < n; i++)
       c->hostSched[(size_t)SC_WEIGHT + (size_t)order[(size_t)i]] = (int)(1000.0 * picture_weight(sp[order[(size_t)i]].sliceQp)) | (i < lone ? SC_LONE_BIT : 0);
   }
@@ -451,17 +473,18 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaMemsetAsync(bt->dProf, 0, sizeof(long long) * 64 * (size_t)n, c->copyIn));
 #endif
   CK(cudaEventRecord(bt->evCopied, c->copyIn));
-  CK(cudaStreamWaitEvent(c->compute, bt->evCopied, 0));
+  CK(cudaStreamWaitEvent(bt->compute, bt->evCopied, 0));
   // The schedule of a hinted picture depends on its content, so its role warps cannot be twin-aligned with another chain's.
   // Measured on the bench workload with CNN hints (256 jobs, profiles/r02_c5_chains.txt): pairs + lone pictures 14.7 s, one
   // chain per block 15.5 s, pairs without lone pictures 15.9 s - the pairing stays (FHC_HINTED_CHAINS=1: one chain per block).
   int chains = FHC_PICS_PER_BLOCK;
   if (hinted) { const char* e = getenv("FHC_HINTED_CHAINS"); if (e && atoi(e) == 1) chains = 1; }
-  CK(cudaEventRecord(bt->evStart, c->compute));
-  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, c->compute>>>(bt->dPics, bt->dState, n, rows, ctusPerRow, bt->dSched, c->dWorkspace, c->wsPerBlock,
-                                                                                            c->smemBytes, c->dTables, chains, wpp);
+  if (c->spanArmed) { CK(cudaEventRecord(c->evSpan, bt->compute)); c->spanArmed = 0; c->spanOpen = 1; }
+  CK(cudaEventRecord(bt->evStart, bt->compute));
+  fhc_ctu_kernel<<<blocks, FHC_BLOCK_THREADS, c->smemBytes * FHC_PICS_PER_BLOCK, bt->compute>>>(bt->dPics, bt->dState, n, rows, ctusPerRow, bt->dSched, bt->dWorkspace, c->wsPerBlock,
+                                                                                            c->smemBytes, c->dTables, chains, wpp, pack);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(bt->evStop, c->compute));
+  CK(cudaEventRecord(bt->evStop, bt->compute));
   g_launches++;
   bt->firstPoc = first_poc; bt->n = n; bt->launched = 1; bt->serial = ++c->submits;
   return FHC_OK;
@@ -501,6 +524,38 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
   CK(cudaMemcpyAsync(bt->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaMemcpyAsync(bt->dHints, hints, hintBytes, cudaMemcpyHostToDevice, c->copyIn));
   return launch(c, bt, first_poc, n, sampleBytes, per_frame, true);
+}
+
+int fhc_configure(fhc_ctx* c, int option, int value)
+{
+  if (!c) return FHC_ERR_ARG;
+  if (option == FHC_OPT_PIPELINED_SUBMITS) { c->pipelined = value ? 1 : 0; return FHC_OK; }
+  snprintf(g_err, sizeof(g_err), "fhc_configure: unknown option %d", option);
+  return FHC_ERR_ARG;
+}
+
+int fhc_span_begin(fhc_ctx* c)
+{
+  if (!c) return FHC_ERR_ARG;
+  c->spanArmed = 1; c->spanOpen = 0;
+  return FHC_OK;
+}
+
+int fhc_span_ms(fhc_ctx* c, float* ms)
+{
+  if (!c || !ms) return FHC_ERR_ARG;
+  if (!c->spanOpen) { snprintf(g_err, sizeof(g_err), "fhc_span_ms: no launch since fhc_span_begin"); return FHC_ERR_STATE; }
+  Batch* last = nullptr;
+  for (int i = 0; i < FHC_BATCHES; i++) if (c->batch[i].launched && (!last || c->batch[i].serial > last->serial)) last = &c->batch[i];
+  if (!last) return FHC_ERR_STATE;
+  CK(cudaSetDevice(c->device));
+  for (int i = 0; i < FHC_BATCHES; i++) if (c->batch[i].launched) CK(cudaEventSynchronize(c->batch[i].evStop));
+  // kernels of different submits run on different streams: the span ends with whichever finished last
+  float best = 0.f;
+  for (int i = 0; i < FHC_BATCHES; i++)
+    if (c->batch[i].launched) { float t = 0.f; if (cudaEventElapsedTime(&t, c->evSpan, c->batch[i].evStop) == cudaSuccess && t > best) best = t; }
+  *ms = best;
+  return FHC_OK;
 }
 
 int fhc_device_picture(fhc_ctx* c, int poc, void** dptr, uint64_t* bytes)

@@ -108,6 +108,19 @@ int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_pla
 int fhc_submit_frames_hinted(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
                              const fhc_slice_params* per_frame, const uint8_t* hints);
 
+/* Options.  FHC_OPT_PIPELINED_SUBMITS = 1: the host promises to keep a second submit queued behind the running one
+ * (submit k+1 before fetching the results of submit k).  The scheduler then optimises the throughput across submits
+ * instead of the completion time of one: no picture runs alone in its block, the blocks of a kernel leave as soon as the
+ * pictures still unfinished fit into the others, and the next submit's kernel (own stream, own scratch) starts on the
+ * freed SMs.  Results are unaffected. */
+#define FHC_OPT_PIPELINED_SUBMITS 1
+int fhc_configure(fhc_ctx* ctx, int option, int value);
+/* Device time across several submits (their kernels may overlap): fhc_span_begin arms a CUDA event that the next submit
+ * records in front of its kernel; fhc_span_ms waits for every kernel launched so far and returns the time from that
+ * event to the end of the last one. */
+int fhc_span_begin(fhc_ctx* ctx);
+int fhc_span_ms(fhc_ctx* ctx, float* ms);
+
 /* Device address of the input planes of submitted picture `poc` (layout as submitted; the pictures of one submit follow
  * each other, *bytes = bytes from there to the end of that submit).  Lets the CNN predictor run on the resident pictures
  * (fhc_cnn_predict_device) without a second host->device copy.  Valid until the submit slot is reused. */

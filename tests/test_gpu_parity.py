@@ -208,3 +208,47 @@ def test_integrated_encoder_read_ahead_cuda():
     assert got == ref
     ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
     assert ok == n and not bad
+
+
+def test_pipelined_submits_equal_oracle_and_plain():
+    """FHC_OPT_PIPELINED_SUBMITS: two submits queued back to back, their kernels on separate streams with separate scratch,
+    blocks leaving early when the rest fits into the others.  Small case against the oracle; a case with more pictures than
+    chain slots (2 x 320 pictures of 416x240) against the same pictures searched one submit at a time."""
+    import fasthevc_b200 as fh
+    w, h, n = 200, 136, 12
+    Y, U, V = synth_frames(w, h, 2 * n, sigma=11.0, seed=41)
+    qps = [22 + 5 * (k % 4) for k in range(2 * n)]
+    ps = [T.params_from_qp(w, h, 8, q) for q in qps]
+    sps = [T.slice_params_from_hm(p) for p in ps]
+    enc = fh.Encoder(w, h, 8, max_frames=n, device=0)
+    enc.set_pipelined(True)
+    enc.span_begin()
+    enc.submit(enc.pack_frames(Y[:n], U[:n], V[:n]), sps[:n], first_poc=0)
+    enc.submit(enc.pack_frames(Y[n:], U[n:], V[n:]), sps[n:], first_poc=n)
+    got = [enc.fetch_picture(k) for k in range(2 * n)]
+    assert enc.span_ms() > 0
+    enc.close()
+    ref = T.oracle_compress_parallel([((w, h, 8, qps[k]), Y[k], U[k], V[k]) for k in range(2 * n)])
+    for k in range(2 * n):
+        assert T.compare_ctus(got[k], ref[k], "poc%d" % k) == []
+
+    w, h, n = 416, 240, 320
+    Y, U, V = synth_frames(w, h, 16, sigma=9.0, seed=43)
+    idx = [k % 16 for k in range(n)]
+    sps = [fh.slice_params_from_qp(22 + 5 * ((k // 16) % 4)) for k in range(n)]
+    enc = fh.Encoder(w, h, 8, max_frames=n, device=0)
+    yuv = enc.pack_frames(Y[idx], U[idx], V[idx])
+    enc.submit(yuv, sps, first_poc=0)
+    plain = [enc.fetch_picture(k).copy() for k in range(n)]
+    t_plain = enc.last_kernel_ms()
+    enc.set_pipelined(True)
+    enc.span_begin()
+    enc.submit(yuv, sps, first_poc=1000)
+    enc.submit(yuv, sps, first_poc=2000)
+    enc.submit(yuv, sps, first_poc=3000)             # waits for the first one's slot
+    for first in (2000, 3000):
+        for k in range(n):
+            assert enc.fetch_picture(first + k).tobytes() == plain[k].tobytes(), (first, k)
+    t_span = enc.span_ms()
+    enc.close()
+    print("320 pictures 416x240: one submit %.0f ms; three pipelined submits %.0f ms (%.0f ms each)" % (t_plain, t_span, t_span / 3))
