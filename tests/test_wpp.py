@@ -140,7 +140,7 @@ def test_cuda_wpp_full_size_1080p_and_latency():
     got, ms = _cuda_wpp(w, h, 8, [fh.slice_params_from_qp(q) for q in qps], Y, U, V)
     assert T.check_fullsize("1080p_wpp", got) == []
     one, ms1 = _cuda_wpp(w, h, 8, [fh.slice_params_from_qp(qps[2])], Y[2:3], U[2:3], V[2:3])
-    assert one[0].tobytes() == got[2].tobytes()
+    assert np.array_equal(T.ctu_crcs(one[0]), T.ctu_crcs(got[2]))
     print("1080p wavefront: 4 pictures %.0f ms, one QP-32 picture %.0f ms" % (ms, ms1))
     assert ms1 < 4000           # as one chain: ~7.4 s
 
