@@ -49,9 +49,19 @@
 
 static fhc_ctx* g_ctx = NULL;
 static int g_width = 0, g_height = 0, g_bitDepth = 0, g_maxFrames = 0;
-static int g_batchFirst = -1, g_batchN = 0;          // POC range of the pictures the device holds
-static fhc_slice_params g_batchSp;
-static std::vector<unsigned char> g_yuv;              // the submitted batch, picture after picture
+// The pictures the device holds: two batches, as the library keeps two submits (fhc_submit_frames while the previous
+// submit is still being consumed).  While the host loop works through batch k - fetching its CTUs and running the
+// unchanged per-picture tail (deblocking, SAO, final CABAC, MD5: TEncGOP.cpp:1619-1870) - the device already searches
+// batch k+1, so the encoder's wall time is bounded by the slower of the two, not by their sum.
+struct ShimBatch
+{
+  int first, n;                                       // POC range
+  fhc_slice_params sp;
+  std::vector<unsigned char> yuv;                     // the submitted pictures, one after the other
+  ShimBatch() : first(-1), n(0) {}
+};
+static ShimBatch g_batch[2];
+static int g_newest = 1;                              // index of the batch submitted last
 static std::vector<unsigned char> g_cur;              // the picture the host is working on, packed the same way
 
 static void fhc_die(const char* what)
@@ -102,60 +112,24 @@ static void pack_picture(const TComPicYuv* org, int sampleBytes, std::vector<uns
   }
 }
 
-static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
+// Submits pictures [first, first + n): the first one from `head` when given (the picture the host just handed over),
+// the others straight from the input file; a short read just shortens the batch.
+static void submit_batch(int first, int n, const std::vector<unsigned char>* head, int sampleBytes, size_t frameBytes, const fhc_slice_params& sp, int w, int h)
 {
-  TComPic* pic = pCtu->getPic();
-  TComSlice* slice = pCtu->getSlice();
-  const TComPicYuv* org = pic->getPicYuvOrg();
-  const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
-  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
-  const int sampleBytes = bd > 8 ? 2 : 1, poc = slice->getPOC();
-  const size_t frameBytes = (size_t)w * h * 3 / 2 * sampleBytes;
-  fhc_slice_params sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.sliceQp = slice->getSliceQp();
-  sp.lambda = enc->m_pcRdCost->getLambda();
-  sp.sqrtLambda = enc->m_pcRdCost->getSqrtLambda();
-  sp.chromaDistWeight[0] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cb];
-  sp.chromaDistWeight[1] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cr];
-  for (int c = 0; c < 3; c++) sp.rdoqLambda[c] = enc->m_pcTrQuant->m_lambdas[c];
-  pack_picture(org, sampleBytes, g_cur);
-
-  // already on the device, with these samples and these parameters?
-  if (g_ctx && poc >= g_batchFirst && poc < g_batchFirst + g_batchN && w == g_width && h == g_height && bd == g_bitDepth &&
-      memcmp(&sp, &g_batchSp, sizeof(sp)) == 0 && memcmp(g_cur.data(), g_yuv.data() + (size_t)(poc - g_batchFirst) * frameBytes, frameBytes) == 0)
-    return;
-
-  int n = lookahead();
-  const int left = enc->m_pcEncCfg->getFramesToBeEncoded() - poc;
-  if (n > left) n = left;
-  if (n < 1) n = 1;
-  if (g_ctx && (w != g_width || h != g_height || bd != g_bitDepth || n > g_maxFrames)) { fhc_destroy(g_ctx); g_ctx = NULL; }
-  if (!g_ctx)
+  ShimBatch& bt = g_batch[g_newest ^ 1];
+  bt.n = 0;
+  bt.yuv.resize(frameBytes * (size_t)n);
+  int got = 0;
+  if (head) { memcpy(bt.yuv.data(), head->data(), frameBytes); got = 1; }
+  if (got < n)
   {
-    fhc_seq_params p;
-    memset(&p, 0, sizeof(p));
-    p.width = w; p.height = h; p.bitDepth = bd; p.chromaFormat = 1;
-    p.ctuSize = 64; p.maxCuDepth = 4; p.tuLog2Max = 5; p.tuLog2Min = 2; p.tuMaxDepthIntra = 3;
-    p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
-    p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
-    p.maxFramesInFlight = n;
-    p.waveFrontSynchro = enc->m_pcEncCfg->getEntropyCodingSyncEnabledFlag() ? 1 : 0;
-    if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
-    g_width = w; g_height = h; g_bitDepth = bd; g_maxFrames = n;
-  }
-  g_yuv.resize(frameBytes * (size_t)n);
-  memcpy(g_yuv.data(), g_cur.data(), frameBytes);
-  if (n > 1)
-  {
-    // the following pictures straight from the input file; a short read just shortens the batch
     FILE* fp = fopen(getenv("FHC_SHIM_INPUT"), "rb");
-    int got = 1;
-    if (fp && fseek(fp, (long)((size_t)(poc + 1) * frameBytes), SEEK_SET) == 0)
-      while (got < n && fread(g_yuv.data() + (size_t)got * frameBytes, 1, frameBytes, fp) == frameBytes) got++;
+    if (fp && fseek(fp, (long)((size_t)(first + got) * frameBytes), SEEK_SET) == 0)
+      while (got < n && fread(bt.yuv.data() + (size_t)got * frameBytes, 1, frameBytes, fp) == frameBytes) got++;
     if (fp) fclose(fp);
-    n = got;
   }
+  if (got == 0) return;
+  n = got;
   std::vector<fhc_slice_params> sps((size_t)n, sp);
   // CU-split hints of the CNN predictor (fhc_submit_frames_hinted): a file of [POC][numCtus][4] bytes named by
   // FHC_HINTS - what fhc_cnn_predict + the scatter of INTEGRATION.md produce for the sequence; pictures beyond the file
@@ -179,11 +153,79 @@ static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
   {
     hints.assign(perPic * (size_t)n, FHC_HINT_NONE);
     for (size_t i = 0; i < hints.size(); i++)
-      if ((size_t)poc * perPic + i < allHints.size()) hints[i] = allHints[(size_t)poc * perPic + i];
+      if ((size_t)first * perPic + i < allHints.size()) hints[i] = allHints[(size_t)first * perPic + i];
   }
-  if (fhc_submit_frames_hinted(g_ctx, poc, n, g_yuv.data(), sampleBytes, sps.data(), hints.empty() ? NULL : hints.data()) != FHC_OK)
+  if (fhc_submit_frames_hinted(g_ctx, first, n, bt.yuv.data(), sampleBytes, sps.data(), hints.empty() ? NULL : hints.data()) != FHC_OK)
     fhc_die("fhc_submit_frames");
-  g_batchFirst = poc; g_batchN = n; g_batchSp = sp;
+  bt.first = first; bt.n = n; bt.sp = sp;
+  g_newest ^= 1;
+}
+
+static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
+{
+  TComPic* pic = pCtu->getPic();
+  TComSlice* slice = pCtu->getSlice();
+  const TComPicYuv* org = pic->getPicYuvOrg();
+  const int w = org->getWidth(COMPONENT_Y), h = org->getHeight(COMPONENT_Y);
+  const int bd = slice->getSPS()->getBitDepth(CHANNEL_TYPE_LUMA);
+  const int sampleBytes = bd > 8 ? 2 : 1, poc = slice->getPOC();
+  const size_t frameBytes = (size_t)w * h * 3 / 2 * sampleBytes;
+  fhc_slice_params sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.sliceQp = slice->getSliceQp();
+  sp.lambda = enc->m_pcRdCost->getLambda();
+  sp.sqrtLambda = enc->m_pcRdCost->getSqrtLambda();
+  sp.chromaDistWeight[0] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cb];
+  sp.chromaDistWeight[1] = enc->m_pcRdCost->m_distortionWeight[COMPONENT_Cr];
+  for (int c = 0; c < 3; c++) sp.rdoqLambda[c] = enc->m_pcTrQuant->m_lambdas[c];
+  pack_picture(org, sampleBytes, g_cur);
+
+  const int total = enc->m_pcEncCfg->getFramesToBeEncoded();
+  int n = lookahead();
+  // already on the device, with these samples and these parameters?
+  ShimBatch* have = NULL;
+  for (int k = 0; k < 2; k++)
+  {
+    ShimBatch& bt = g_batch[k];
+    if (g_ctx && bt.n > 0 && poc >= bt.first && poc < bt.first + bt.n && w == g_width && h == g_height && bd == g_bitDepth &&
+        memcmp(&sp, &bt.sp, sizeof(sp)) == 0 && memcmp(g_cur.data(), bt.yuv.data() + (size_t)(poc - bt.first) * frameBytes, frameBytes) == 0)
+      have = &bt;
+  }
+  if (have)
+  {
+    // first picture of a batch: queue the batch after it, so that the device works while the host runs this batch's tail
+    const int next = have->first + have->n;
+    if (n > g_maxFrames) n = g_maxFrames;
+    if (n > 1 && poc == have->first && next < total && g_batch[0].first != next && g_batch[1].first != next)
+      submit_batch(next, n < total - next ? n : total - next, NULL, sampleBytes, frameBytes, sp, w, h);
+    return;
+  }
+
+  const int left = total - poc;
+  if (n > left) n = left;
+  if (n < 1) n = 1;
+  if (g_ctx && (w != g_width || h != g_height || bd != g_bitDepth || n > g_maxFrames)) { fhc_destroy(g_ctx); g_ctx = NULL; g_batch[0].n = g_batch[1].n = 0; }
+  if (!g_ctx)
+  {
+    fhc_seq_params p;
+    memset(&p, 0, sizeof(p));
+    p.width = w; p.height = h; p.bitDepth = bd; p.chromaFormat = 1;
+    p.ctuSize = 64; p.maxCuDepth = 4; p.tuLog2Max = 5; p.tuLog2Min = 2; p.tuMaxDepthIntra = 3;
+    p.useRdoq = p.useRdoqTs = p.useTransformSkip = p.useTransformSkipFast = 1;
+    p.signHideFlag = p.strongIntraSmoothing = p.fastUdiUseMpm = 1;
+    p.maxFramesInFlight = n;
+    p.waveFrontSynchro = enc->m_pcEncCfg->getEntropyCodingSyncEnabledFlag() ? 1 : 0;
+    if (fhc_create(&p, 0, &g_ctx) != FHC_OK) fhc_die("fhc_create");
+    if (n > 1 && fhc_configure(g_ctx, FHC_OPT_PIPELINED_SUBMITS, 1) != FHC_OK) fhc_die("fhc_configure");
+    g_width = w; g_height = h; g_bitDepth = bd; g_maxFrames = n;
+  }
+  // a stale batch that claims this POC (wrong samples / parameters) must not be found again
+  for (int k = 0; k < 2; k++) if (g_batch[k].n > 0 && poc >= g_batch[k].first && poc < g_batch[k].first + g_batch[k].n) g_batch[k].n = poc - g_batch[k].first;
+  submit_batch(poc, n, &g_cur, sampleBytes, frameBytes, sp, w, h);
+  // ... and the batch after it right away: two submits in flight from the start
+  const ShimBatch& cur = g_batch[g_newest];
+  const int next = cur.first + cur.n;
+  if (n > 1 && cur.n == n && next < total) submit_batch(next, n < total - next ? n : total - next, NULL, sampleBytes, frameBytes, sp, w, h);
 }
 
 void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)

@@ -12,14 +12,21 @@ extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, 
                                            const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
                                            int wpp, int order);
 
-struct fhc_ctx { fhc_seq_params seq; int poc, n, numCtus; std::vector<fhc_ctu_result> out; };
+struct emu_batch { int poc, n; std::vector<fhc_ctu_result> out; emu_batch() : poc(-1), n(0) {} };
+struct fhc_ctx { fhc_seq_params seq; int numCtus, newest, pipelined; emu_batch b[2]; };     // two submit slots, as in the library
+
+// FHC_EMU_LOG=<file>: one line per submit / per picture's first fetch, so that a test can see the order of the shim's calls
+static void emu_log(const char* what, int a, int b)
+{
+  if (const char* p = getenv("FHC_EMU_LOG")) if (FILE* f = fopen(p, "a")) { fprintf(f, "%s %d %d\n", what, a, b); fclose(f); }
+}
 
 extern "C" {
 const char* fhc_last_error(void) { return "emulated ABI"; }
 int fhc_create(const fhc_seq_params* seq, int, fhc_ctx** out)
 {
   fhc_ctx* c = new fhc_ctx();
-  c->seq = *seq; c->poc = -1;
+  c->seq = *seq; c->newest = 1; c->pipelined = 0;
   c->numCtus = ((seq->width + 63) / 64) * ((seq->height + 63) / 64);
   *out = c;
   return FHC_OK;
@@ -35,13 +42,16 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
 {
   if (n < 1 || n > c->seq.maxFramesInFlight) return FHC_ERR_ARG;
   const size_t luma = (size_t)c->seq.width * c->seq.height * sampleBytes, frame = luma + luma / 2;
-  c->out.assign((size_t)c->numCtus * n, fhc_ctu_result());
-  c->poc = first_poc; c->n = n;
+  emu_log("submit", first_poc, n);
+  emu_batch& bt = c->b[c->newest ^ 1];
+  bt.out.assign((size_t)c->numCtus * n, fhc_ctu_result());
+  bt.poc = first_poc; bt.n = n;
+  c->newest ^= 1;
   for (int k = 0; k < n; k++)
   {
     const unsigned char* p = (const unsigned char*)yuv + frame * k;
     int rc = fhc_emu_compress_picture_ex(c->seq.width, c->seq.height, c->seq.bitDepth, sampleBytes, &sp[k], p, p + luma, p + luma + luma / 4,
-                                         c->out.data() + (size_t)c->numCtus * k, hints ? hints + (size_t)4 * c->numCtus * k : NULL,
+                                         bt.out.data() + (size_t)c->numCtus * k, hints ? hints + (size_t)4 * c->numCtus * k : NULL,
                                          c->seq.waveFrontSynchro, 2);
     if (rc) return rc;
   }
@@ -49,8 +59,14 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
 }
 int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
 {
-  if (poc < c->poc || poc >= c->poc + c->n || addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
-  *out = c->out[(size_t)(poc - c->poc) * c->numCtus + addr];
-  return FHC_OK;
+  if (addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
+  if (addr == 0) emu_log("fetch", poc, c->pipelined);
+  for (int k = 0; k < 2; k++)                       // the newer submit first, as the library does
+  {
+    const emu_batch& bt = c->b[k ? c->newest ^ 1 : c->newest];
+    if (poc >= bt.poc && poc < bt.poc + bt.n) { *out = bt.out[(size_t)(poc - bt.poc) * c->numCtus + addr]; return FHC_OK; }
+  }
+  return FHC_ERR_ARG;
 }
+int fhc_configure(fhc_ctx* c, int option, int value) { if (option != FHC_OPT_PIPELINED_SUBMITS) return FHC_ERR_ARG; c->pipelined = value; return FHC_OK; }
 }

@@ -362,6 +362,27 @@ def test_integrated_encoder_read_ahead_emulated():
         assert got == ref, name
 
 
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC not built")
+def test_integrated_encoder_keeps_two_submits_in_flight_emulated():
+    """the shim queues the batch after the one the host is consuming (two submits in flight, pipelined
+    option set), so the device searches batch k+1 while the host runs batch k's per-picture tail; same bitstream."""
+    w, h, n, qp = 136, 72, 7, 33
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, sigma=9.0, seed=6)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    log = os.path.join(d, "calls.log")
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, tag="_ref")
+    got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", lib_dir=T.build_emu_abi(), tag="_fhc",
+                                env_extra={"FHC_SHIM_INPUT": os.path.join(d, "s.yuv"), "FHC_SHIM_LOOKAHEAD": "3", "FHC_EMU_LOG": log})
+    assert got == ref
+    calls = [l.split() for l in open(log).read().splitlines()]
+    # [0..2] and [3..5] go out before the first fetch; [6] when the host reaches picture 3; every picture is fetched once
+    assert calls[:3] == [["submit", "0", "3"], ["submit", "3", "3"], ["fetch", "0", "1"]]
+    assert [c for c in calls if c[0] == "submit"] == [["submit", "0", "3"], ["submit", "3", "3"], ["submit", "6", "1"]]
+    assert calls.index(["submit", "6", "1"]) == calls.index(["fetch", "3", "1"]) - 1
+    assert [c[1] for c in calls if c[0] == "fetch"] == [str(k) for k in range(n)]
+
+
 def test_kernel_source_emulation_4k_width_main10():
     """BASELINE configs[3] geometry in one dimension: a 3840-wide Main10 strip (60 CTUs per row, two full rows + the
     8-line bottom row) through the host emulation of the kernel source against the oracle - row-to-row neighbour and

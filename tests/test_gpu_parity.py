@@ -252,3 +252,27 @@ def test_pipelined_submits_equal_oracle_and_plain():
     t_span = enc.span_ms()
     enc.close()
     print("320 pictures 416x240: one submit %.0f ms; three pipelined submits %.0f ms (%.0f ms each)" % (t_plain, t_span, t_span / 3))
+
+
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC did not travel")
+@pytest.mark.parametrize("wpp", [False, True], ids=["plain", "wavefront"])
+def test_integrated_encoder_1080p_pipeline_cuda(wpp):
+    """SURVEY 8f-2 end to end: the reference encoder with the shim on the CUDA library, 24 pictures of 1920x1080 in
+    batches of 12, two submits in flight (the device searches batch k+1 while the unchanged single-threaded host runs
+    batch k's deblocking / SAO / final CABAC / MD5).  Every picture decodes with matching MD5 SEI; the wall time is
+    printed (the stock encoder needs ~5.6 s per picture on one core at this QP)."""
+    import time
+    w, h, n, qp = 1920, 1080, 24, 32
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, 6, sigma=6.0)
+    idx = [k % 6 for k in range(n)]
+    write_yuv(os.path.join(d, "s.yuv"), Y[idx], U[idx], V[idx])
+    t0 = time.perf_counter()
+    got, _, out = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", tag="_fhc",
+                                  env_extra={"FHC_SHIM_INPUT": os.path.join(d, "s.yuv"), "FHC_SHIM_LOOKAHEAD": "12"},
+                                  extra=["--WaveFrontSynchro=1"] if wpp else [])
+    wall = time.perf_counter() - t0
+    ok, bad = T.decoder_md5_ok(os.path.join(d, "out_fhc.bin"), d)
+    assert ok == n and not bad
+    print("integrated encoder, %s: %d pictures 1080p QP %d in %.1f s = %.2f fps (whole bitstream, %d bytes)"
+          % ("wavefront" if wpp else "plain", n, qp, wall, n / wall, len(got)))
