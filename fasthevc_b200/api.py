@@ -39,7 +39,7 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
            "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight", "fhc_poll_picture",
-           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue", "fhc_submit_frames_hinted", "fhc_device_picture", "fhc_configure", "fhc_span_begin", "fhc_span_ms"]
+           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue", "fhc_submit_frames_hinted", "fhc_device_picture", "fhc_configure", "fhc_span_begin", "fhc_span_ms", "fhc_deblock_pictures", "fhc_last_deblock_ms"]
 
 
 def library_path():
@@ -74,6 +74,8 @@ def load_library():
     lib.fhc_destroy.argtypes = [C.c_void_p]
     lib.fhc_submit_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams)]
     lib.fhc_submit_frames_hinted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams), C.c_void_p]
+    lib.fhc_deblock_pictures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.fhc_last_deblock_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.fhc_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fhc_span_begin.argtypes = [C.c_void_p]
     lib.fhc_span_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -186,6 +188,16 @@ class Encoder:
             raise FhcError("hints: %d bytes, expected %d" % (hints.size, n * self.num_ctus * 4))
         self._check(self.lib.fhc_submit_frames_hinted(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr, hints.ctypes.data),
                     "fhc_submit_frames_hinted")
+
+    def deblock_pictures(self, first_poc, n, out=None):
+        """fhc_deblock_pictures: the deblocked pictures [first_poc, first_poc + n) as an (n, frame_samples) array in the
+        input layout; also returns the CUDA-event time of the kernels."""
+        if out is None:
+            out = np.zeros((n, self.frame_samples), np.uint8 if self.sample_bytes == 1 else np.uint16)
+        self._check(self.lib.fhc_deblock_pictures(self.ctx, int(first_poc), int(n), out.ctypes.data, self.sample_bytes), "fhc_deblock_pictures")
+        ms = C.c_float()
+        self._check(self.lib.fhc_last_deblock_ms(self.ctx, C.byref(ms)), "fhc_last_deblock_ms")
+        return out, ms.value
 
     def set_pipelined(self, on=True):
         """FHC_OPT_PIPELINED_SUBMITS: the caller keeps a second submit queued behind the running one."""

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <vector>
 #include "fhc_engine.cuh"
+#include "fhc_deblock.cuh"
 
 using namespace fhc;
 
@@ -215,6 +216,7 @@ struct Batch
   unsigned char* dWorkspace = nullptr;    // per-chain scratch of the batch's kernel
   cudaEvent_t evCopied = nullptr, evStart = nullptr, evStop = nullptr;
   int firstPoc = 0, n = 0, launched = 0;
+  std::vector<int> qps;                   // slice QP per picture of the submit (deblocking)
   uint64_t serial = 0;                    // submit counter value of this batch (0 = never used)
 };
 
@@ -226,6 +228,9 @@ struct fhc_ctx
   Tables* dTables = nullptr;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   int pipelined = 0;                       // FHC_OPT_PIPELINED_SUBMITS
+  // deblocking (fhc_deblock_pictures): working planes, packed output and picture table, sized for the largest call so far
+  int16_t* dDbkPlanes = nullptr; uint8_t* dDbkOut = nullptr; DbkPic* dDbkPics = nullptr; int dbkCap = 0, dbkSampleBytes = 0;
+  cudaEvent_t evDbk0 = nullptr, evDbk1 = nullptr; float dbkMs = 0.f;
   cudaEvent_t evSpan = nullptr;            // fhc_span_begin: recorded before the next launch's kernel
   int spanArmed = 0, spanOpen = 0;
   Batch batch[FHC_BATCHES];
@@ -280,8 +285,10 @@ int fhc_destroy(fhc_ctx* c)
   if (c->copyIn) cudaStreamSynchronize(c->copyIn);
   if (c->copyOut) cudaStreamSynchronize(c->copyOut);
   for (int i = 0; i < FHC_BATCHES; i++) free_batch(c->batch[i]);
-  cudaFree(c->dTables);
+  cudaFree(c->dTables); cudaFree(c->dDbkPlanes); cudaFree(c->dDbkOut); cudaFree(c->dDbkPics);
   if (c->evSpan) cudaEventDestroy(c->evSpan);
+  if (c->evDbk0) cudaEventDestroy(c->evDbk0);
+  if (c->evDbk1) cudaEventDestroy(c->evDbk1);
   if (c->copyIn) cudaStreamDestroy(c->copyIn);
   if (c->copyOut) cudaStreamDestroy(c->copyOut);
   delete c;
@@ -487,6 +494,8 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   CK(cudaEventRecord(bt->evStop, bt->compute));
   g_launches++;
   bt->firstPoc = first_poc; bt->n = n; bt->launched = 1; bt->serial = ++c->submits;
+  bt->qps.resize((size_t)n);
+  for (int i = 0; i < n; i++) bt->qps[(size_t)i] = sp[i].sliceQp;
   return FHC_OK;
 }
 
@@ -524,6 +533,71 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
   CK(cudaMemcpyAsync(bt->dIn, yuv, c->frameSamples * (size_t)sampleBytes * (size_t)n, cudaMemcpyHostToDevice, c->copyIn));
   CK(cudaMemcpyAsync(bt->dHints, hints, hintBytes, cudaMemcpyHostToDevice, c->copyIn));
   return launch(c, bt, first_poc, n, sampleBytes, per_frame, true);
+}
+
+// ----------------------------------------------------------------------------------------------
+// deblocking of finished pictures (first stage of the per-picture tail)
+// ----------------------------------------------------------------------------------------------
+static Batch* find_batch(fhc_ctx* c, int poc, int* slot);
+static int wait_picture(fhc_ctx* c, Batch* bt, int slot);
+
+int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes)
+{
+  if (!c || !out || n <= 0 || (sampleBytes != 1 && sampleBytes != 2) || (c->seq.bitDepth > 8 && sampleBytes != 2)) return FHC_ERR_ARG;
+  if (c->submits == 0) return FHC_ERR_STATE;
+  int slot = 0;
+  Batch* bt = find_batch(c, first_poc, &slot);
+  if (!bt || slot + n > bt->n) { snprintf(g_err, sizeof(g_err), "fhc_deblock_pictures: pictures %d..%d are not in one submit", first_poc, first_poc + n - 1); return FHC_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  for (int i = 0; i < n; i++) { int rc = wait_picture(c, bt, slot + i); if (rc != FHC_OK) return rc; }
+  const int W = c->seq.width, H = c->seq.height, wc = (W + 63) / 64;
+  const size_t frame = c->frameSamples;
+  if (n > c->dbkCap || sampleBytes > c->dbkSampleBytes)
+  {
+    cudaFree(c->dDbkPlanes); cudaFree(c->dDbkOut); cudaFree(c->dDbkPics);
+    c->dDbkPlanes = nullptr; c->dDbkOut = nullptr; c->dDbkPics = nullptr; c->dbkCap = 0;
+    CK(cudaMalloc(&c->dDbkPlanes, sizeof(int16_t) * frame * (size_t)n));
+    CK(cudaMalloc(&c->dDbkOut, frame * (size_t)n * (size_t)sampleBytes));
+    CK(cudaMalloc(&c->dDbkPics, sizeof(DbkPic) * (size_t)n));
+    c->dbkCap = n; c->dbkSampleBytes = sampleBytes;
+    if (!c->evDbk0) { CK(cudaEventCreate(&c->evDbk0)); CK(cudaEventCreate(&c->evDbk1)); }
+  }
+  std::vector<DbkPic> hp((size_t)n);
+  for (int i = 0; i < n; i++)
+  {
+    DbkPic& d = hp[(size_t)i];
+    d.ctus = bt->dOut + (size_t)(slot + i) * c->numCtus;
+    d.plane[0] = c->dDbkPlanes + frame * (size_t)i;
+    d.plane[1] = d.plane[0] + c->lumaSamples;
+    d.plane[2] = d.plane[1] + c->lumaSamples / 4;
+    d.out = c->dDbkOut + frame * (size_t)i * (size_t)sampleBytes;
+    d.qp = bt->qps[(size_t)(slot + i)]; d.pad = 0;
+  }
+  // on the copy-out stream: behind the device->host copies already queued, next to the running kernel
+  CK(cudaMemcpyAsync(c->dDbkPics, hp.data(), sizeof(DbkPic) * (size_t)n, cudaMemcpyHostToDevice, c->copyOut));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int perPic = std::max(1, (prop.multiProcessorCount * 16 + n - 1) / n);      // grid = a multiple of the SM count over all pictures
+  const dim3 grid((unsigned)perPic, (unsigned)n);
+  CK(cudaEventRecord(c->evDbk0, c->copyOut));
+  fhc_dbk_gather_kernel<<<grid, FHC_DBK_THREADS, 0, c->copyOut>>>(c->dDbkPics, W, H, wc);
+  fhc_dbk_edges_kernel<<<grid, FHC_DBK_THREADS, 0, c->copyOut>>>(c->dDbkPics, W, H, wc, c->seq.bitDepth, 0);
+  fhc_dbk_edges_kernel<<<grid, FHC_DBK_THREADS, 0, c->copyOut>>>(c->dDbkPics, W, H, wc, c->seq.bitDepth, 1);
+  fhc_dbk_pack_kernel<<<grid, FHC_DBK_THREADS, 0, c->copyOut>>>(c->dDbkPics, W, H, sampleBytes);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->evDbk1, c->copyOut));
+  g_launches += 4;
+  CK(cudaMemcpyAsync(out, c->dDbkOut, frame * (size_t)n * (size_t)sampleBytes, cudaMemcpyDeviceToHost, c->copyOut));
+  CK(cudaStreamSynchronize(c->copyOut));
+  CK(cudaEventElapsedTime(&c->dbkMs, c->evDbk0, c->evDbk1));
+  return FHC_OK;
+}
+
+int fhc_last_deblock_ms(fhc_ctx* c, float* ms)
+{
+  if (!c || !ms) return FHC_ERR_ARG;
+  *ms = c->dbkMs;
+  return FHC_OK;
 }
 
 int fhc_configure(fhc_ctx* c, int option, int value)

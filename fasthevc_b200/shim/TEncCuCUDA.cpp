@@ -43,6 +43,7 @@
 #include "TLibCommon/TComRdCost.h"
 #include "TLibCommon/TComTrQuant.h"
 #include "TLibEncoder/TEncCu.h"
+#include "TLibCommon/TComLoopFilter.h"
 #undef private
 #undef protected
 #include "fasthevc_cuda.h"
@@ -271,5 +272,33 @@ void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
     const int16_t* src = c == 0 ? r.recoY : (c == 1 ? r.recoCb : r.recoCr);
     for (int y = 0; y < n && (y0 >> sh) + y < ch; y++)
       for (int x = 0; x < n && (x0 >> sh) + x < cw; x++) dst[y * stride + x] = src[y * n + x];
+  }
+}
+
+// The deblocking filter of a finished picture (TEncGOP.cpp:1619 calls this instead of m_pcLoopFilter->loopFilterPic):
+// fhc_deblock_pictures filters the picture on the device from the CTU records it already holds and returns the planes,
+// which replace PicYuvRec.  FHC_SHIM_DEBLOCK=0 keeps the host filter.
+void fhc_shim_loop_filter(TComLoopFilter* lf, TComPic* pic)
+{
+  static const bool onDevice = !(getenv("FHC_SHIM_DEBLOCK") && atoi(getenv("FHC_SHIM_DEBLOCK")) == 0);
+  if (!onDevice || !g_ctx) { lf->loopFilterPic(pic); return; }
+  TComPicYuv* rec = pic->getPicYuvRec();
+  const int w = rec->getWidth(COMPONENT_Y), h = rec->getHeight(COMPONENT_Y);
+  const int sampleBytes = g_bitDepth > 8 ? 2 : 1;
+  static std::vector<unsigned char> planes;
+  planes.resize((size_t)w * h * 3 / 2 * sampleBytes);
+  if (fhc_deblock_pictures(g_ctx, pic->getPOC(), 1, planes.data(), sampleBytes) != FHC_OK) fhc_die("fhc_deblock_pictures");
+  size_t pos = 0;
+  for (int c = 0; c < 3; c++)
+  {
+    const ComponentID id = ComponentID(c);
+    const int cw = rec->getWidth(id), ch = rec->getHeight(id), stride = rec->getStride(id);
+    Pel* dst = rec->getAddr(id);
+    for (int y = 0; y < ch; y++)
+      for (int x = 0; x < cw; x++)
+      {
+        if (sampleBytes == 1) dst[y * stride + x] = (Pel)planes[pos++];
+        else { dst[y * stride + x] = (Pel)(planes[pos] | (planes[pos + 1] << 8)); pos += 2; }
+      }
   }
 }

@@ -108,6 +108,15 @@ int fhc_submit_frames(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_pla
 int fhc_submit_frames_hinted(fhc_ctx* ctx, int first_poc, int n, const void* yuv420_planar, int sampleBytes,
                              const fhc_slice_params* per_frame, const uint8_t* hints);
 
+/* First stage of the per-picture tail on the device: TComLoopFilter::loopFilterPic
+ * (TComLoopFilter.cpp:130, called from TEncGOP.cpp:1619) for pictures [first_poc, first_poc + n) of one submit, from the CTU
+ * records in device memory.  Waits for those pictures, filters them (all vertical edges, then all horizontal ones) and
+ * writes the deblocked pictures to `out` (host memory) in the layout of fhc_submit_frames (Y, Cb, Cr planes per picture,
+ * sampleBytes each).  Equals the reference's reconstruction with --SAO=0 sample for sample. */
+int fhc_deblock_pictures(fhc_ctx* ctx, int first_poc, int n, void* yuv420_planar_out, int sampleBytes);
+/* CUDA-event time of the four deblocking kernels of the last call. */
+int fhc_last_deblock_ms(fhc_ctx* ctx, float* ms);
+
 /* Options.  FHC_OPT_PIPELINED_SUBMITS = 1: the host promises to keep a second submit queued behind the running one
  * (submit k+1 before fetching the results of submit k).  The scheduler then optimises the throughput across submits
  * instead of the completion time of one: no picture runs alone in its block, the blocks of a kernel leave as soon as the

@@ -28,6 +28,7 @@ Patched sites (reference file:line):
   source/App/TAppEncoder/TAppEncCfg.cpp:49,1587     HARP include + Global.inputFilename
   source/Lib/TLibEncoder/TEncGOP.cpp:49,1562        HARP include + CShow_PredResiReco dump
   source/Lib/TLibEncoder/TEncCu.cpp:260             (TAppEncoderFHC only) xCompressCU(depth 0) -> fhc_shim_compress_ctu
+  source/Lib/TLibEncoder/TEncGOP.cpp:1619           (TAppEncoderFHC only) m_pcLoopFilter->loopFilterPic -> fhc_shim_loop_filter
 """
 import os, re, shutil, subprocess, sys, concurrent.futures as cf
 
@@ -140,7 +141,7 @@ def stages_sources(scratch):
     return out
 
 
-def fhc_sources(scratch):
+def fhc_sources(scratch, patched):
     """TEncCu.cpp of the integrated encoder: the single call site of the hot path goes to the shim."""
     src = os.path.join(REF, "source")
     rel = "Lib/TLibEncoder/TEncCu.cpp"
@@ -152,7 +153,20 @@ def fhc_sources(scratch):
     dst = os.path.join(scratch, "fhc", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     open(dst, "w").write(t)
-    return {rel: dst}
+    out = {rel: dst}
+    # first stage of the per-picture tail on the device: the one call of the deblocking filter in
+    # TEncGOP::compressGOP (TEncGOP.cpp:1619) goes to the shim (fhc_deblock_pictures; FHC_SHIM_DEBLOCK=0 keeps the host filter)
+    rel = "Lib/TLibEncoder/TEncGOP.cpp"
+    t = open(patched[rel]).read()
+    call = "    m_pcLoopFilter->loopFilterPic( pcPic );\n\n    /////"
+    assert t.count(call) == 1, t.count(call)
+    t = t.replace(call, "    fhc_shim_loop_filter( m_pcLoopFilter, pcPic );\n\n    /////")
+    t = t.replace("Void TEncGOP::compressGOP(", "void fhc_shim_loop_filter(TComLoopFilter*, TComPic*);\nVoid TEncGOP::compressGOP(", 1)
+    dst = os.path.join(scratch, "fhc", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+    return out
 
 
 def compile_one(job):
@@ -180,7 +194,7 @@ def main():
     src = os.path.join(REF, "source")
     stub = patched_sources(scratch)
     dump = dump_sources(scratch)
-    fhc = fhc_sources(scratch)
+    fhc = fhc_sources(scratch, stub)
     stages = stages_sources(scratch)
     hinted = hinted_sources(scratch, dump)
     incs = ["-I" + os.path.join(src, "Lib"), "-I" + os.path.join(src, "App"), "-I" + os.path.join(src, "App/TAppEncoder")]

@@ -7,12 +7,13 @@
 #include <string.h>
 #include <vector>
 #include "../include/fasthevc_cuda.h"
+#include "../fasthevc_b200/csrc/fhc_deblock.cuh"
 
 extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                            const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
                                            int wpp, int order);
 
-struct emu_batch { int poc, n; std::vector<fhc_ctu_result> out; emu_batch() : poc(-1), n(0) {} };
+struct emu_batch { int poc, n; std::vector<fhc_ctu_result> out; std::vector<int> qps; emu_batch() : poc(-1), n(0) {} };
 struct fhc_ctx { fhc_seq_params seq; int numCtus, newest, pipelined; emu_batch b[2]; };     // two submit slots, as in the library
 
 // FHC_EMU_LOG=<file>: one line per submit / per picture's first fetch, so that a test can see the order of the shim's calls
@@ -46,6 +47,8 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
   emu_batch& bt = c->b[c->newest ^ 1];
   bt.out.assign((size_t)c->numCtus * n, fhc_ctu_result());
   bt.poc = first_poc; bt.n = n;
+  bt.qps.resize((size_t)n);
+  for (int k = 0; k < n; k++) bt.qps[(size_t)k] = sp[k].sliceQp;
   c->newest ^= 1;
   for (int k = 0; k < n; k++)
   {
@@ -65,6 +68,39 @@ int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
   {
     const emu_batch& bt = c->b[k ? c->newest ^ 1 : c->newest];
     if (poc >= bt.poc && poc < bt.poc + bt.n) { *out = bt.out[(size_t)(poc - bt.poc) * c->numCtus + addr]; return FHC_OK; }
+  }
+  return FHC_ERR_ARG;
+}
+// the deblocking passes of fasthevc_b200/csrc/fhc_deblock.cuh, run segment by segment on the host
+int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes)
+{
+  using namespace fhc;
+  static const DbkTables tables = FHC_DBK_TABLES;
+  const int W = c->seq.width, H = c->seq.height, wc = (W + 63) / 64;
+  const long long luma = (long long)W * H, frame = luma * 3 / 2;
+  emu_log("deblock", first_poc, n);
+  for (int k = 0; k < 2; k++)
+  {
+    const emu_batch& bt = c->b[k ? c->newest ^ 1 : c->newest];
+    if (first_poc < bt.poc || first_poc + n > bt.poc + bt.n) continue;
+    std::vector<int16_t> planes((size_t)frame);
+    for (int i = 0; i < n; i++)
+    {
+      DbkPic pic;
+      pic.ctus = bt.out.data() + (size_t)(first_poc - bt.poc + i) * c->numCtus;
+      pic.plane[0] = planes.data(); pic.plane[1] = planes.data() + luma; pic.plane[2] = planes.data() + luma + luma / 4;
+      pic.out = NULL; pic.qp = bt.qps[(size_t)(first_poc - bt.poc + i)]; pic.pad = 0;
+      for (long long s = 0; s < frame; s++) { int comp; long long idx; const int16_t v = dbk_record_sample(pic.ctus, W, H, wc, s, &comp, &idx); pic.plane[comp][idx] = v; }
+      for (int dir = 0; dir < 2; dir++)
+        for (int y = 0; y < H; y += dir == 0 ? 4 : 8)
+          for (int x = 0; x < W; x += dir == 0 ? 8 : 4) dbk_segment(tables, pic, W, wc, c->seq.bitDepth, x, y, dir);
+      for (long long s = 0; s < frame; s++)
+      {
+        if (sampleBytes == 1) ((unsigned char*)out)[(size_t)i * frame + s] = (unsigned char)planes[(size_t)s];
+        else ((unsigned short*)out)[(size_t)i * frame + s] = (unsigned short)planes[(size_t)s];
+      }
+    }
+    return FHC_OK;
   }
   return FHC_ERR_ARG;
 }

@@ -40,6 +40,10 @@ class HmParams(C.Structure):
 
 
 def build_oracle():
+    so2 = os.path.join(ORACLE_DIR, "libhm_deblock_oracle.so")
+    src2 = os.path.join(ORACLE_DIR, "hm_deblock.c")
+    if not os.path.exists(so2) or os.path.getmtime(so2) < os.path.getmtime(src2):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so2, src2, "-lm"])
     so = os.path.join(ORACLE_DIR, "libhm_intra_oracle.so")
     src = os.path.join(ORACLE_DIR, "hm_intra.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
@@ -360,3 +364,34 @@ def check_fullsize(tag, got):
     for k in range(len(got)):
         bad += compare_ctus(got[k], ref[k], "%s pic%d" % (tag, k))
     return bad
+
+
+# --- deblocking oracle (oracle/hm_deblock.c) --------------------------------------------------------------------------
+_dbk = None
+
+
+def oracle_deblock(width, height, bit_depth, qp, records):
+    """TComLoopFilter::loopFilterPic restated on CTU records -> (Y, Cb, Cr) int16 planes."""
+    global _dbk
+    if _dbk is None:
+        so = os.path.join(ORACLE_DIR, "libhm_deblock_oracle.so")
+        src = os.path.join(ORACLE_DIR, "hm_deblock.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+        _dbk = C.CDLL(so)
+        _dbk.hm_deblock_picture.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4
+    recs = np.ascontiguousarray(records)
+    assert recs.dtype == CTU_OUT_DT and len(recs) == n_ctus(width, height)
+    y = np.zeros((height, width), np.int16)
+    u = np.zeros((height // 2, width // 2), np.int16)
+    v = np.zeros((height // 2, width // 2), np.int16)
+    rc = _dbk.hm_deblock_picture(width, height, bit_depth, qp, recs.ctypes.data, y.ctypes.data, u.ctypes.data, v.ctypes.data)
+    assert rc == 0
+    return y, u, v
+
+
+def planes_of(packed, width, height):
+    """One picture in the planar 4:2:0 layout -> (Y, Cb, Cr) int16 planes."""
+    p = np.asarray(packed).reshape(-1).astype(np.int16)
+    l = width * height
+    return p[:l].reshape(height, width), p[l:l + l // 4].reshape(height // 2, width // 2), p[l + l // 4:].reshape(height // 2, width // 2)

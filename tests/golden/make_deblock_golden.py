@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Writes tests/golden/deblock_*.npz by RUNNING THE REAL REFERENCE (oracle/_ref/TAppEncoderDump) with --SAO=0: the
+reconstruction file then holds the pictures exactly as TComLoopFilter::loopFilterPic leaves them.  Each fixture holds the
+deblocked planes and what the deblocking oracle / kernel need as input (CU depth, transform index, pre-deblocking
+reconstruction of every CTU, taken from the reference's per-CTU dump)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import fhc_testlib as T  # noqa: E402
+from fasthevc_b200.synth import synth_frames, write_yuv  # noqa: E402
+
+for name, w, h, qp, bd, sigma in (("deblock_264x200_qp34", 264, 200, 34, 8, 5.0), ("deblock_main10_136x72_qp37", 136, 72, 37, 10, 6.0)):
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, 1, bit_depth=bd, sigma=sigma)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    bs, dump, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, 1, qp, d, bit_depth=bd, extra=["--SAO=0"])
+    s, ctus = T.parse_dump(dump)[0]
+    rec = np.fromfile(os.path.join(d, "rec.yuv"), dtype=np.uint8 if bd == 8 else np.uint16)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array([w, h, 1, qp, bd], np.int32), sigma=np.array([sigma]),
+                        depth=ctus["depth"], trIdx=ctus["trIdx"], recoY=ctus["recoY"], recoCb=ctus["recoCb"], recoCr=ctus["recoCr"],
+                        deblocked=rec)
+    print(name, len(rec))

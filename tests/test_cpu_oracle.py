@@ -15,7 +15,7 @@ import pytest
 import fhc_testlib as T
 from fasthevc_b200.synth import synth_frames, write_yuv
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_", "wpp_", "fullsize_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_", "wpp_", "fullsize_", "deblock_")))
 
 
 def load_golden(path):
@@ -381,6 +381,8 @@ def test_integrated_encoder_keeps_two_submits_in_flight_emulated():
     assert [c for c in calls if c[0] == "submit"] == [["submit", "0", "3"], ["submit", "3", "3"], ["submit", "6", "1"]]
     assert calls.index(["submit", "6", "1"]) == calls.index(["fetch", "3", "1"]) - 1
     assert [c[1] for c in calls if c[0] == "fetch"] == [str(k) for k in range(n)]
+    # the deblocking filter of every picture ran through the boundary too (TEncGOP.cpp:1619 -> fhc_deblock_pictures)
+    assert [c for c in calls if c[0] == "deblock"] == [["deblock", str(k), "1"] for k in range(n)]
 
 
 def test_kernel_source_emulation_4k_width_main10():

@@ -11,7 +11,7 @@ import fhc_testlib as T
 from fasthevc_b200.synth import synth_frames, write_yuv
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_", "wpp_", "fullsize_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(T.GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("stages_", "cnn_", "hinted_", "wpp_", "fullsize_", "deblock_")))
 
 
 def cuda_compress(w, h, bd, sps, Y, U, V):
