@@ -168,7 +168,9 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop_flag = True
     launches = int(enc.lib.fhc_launch_count()) - launches0
     in_flight = fh.pictures_in_flight(local_rank)
-    guided = wavefront = None
+    guided = wavefront = deblock = None
+    if rank == 0 and world == 1 and not args.no_deblock:
+        deblock = deblock_leg(enc, n_jobs, poc_next[0] - n_jobs)
     if rank == 0 and world == 1 and not args.no_cnn:
         guided = cnn_guided_leg(enc, host_in, host_out, sps, n_jobs, local_rank, poc_next[0] - n_jobs, poc_next[0])
     if rank == 0 and world == 1 and not args.no_wpp:
@@ -237,12 +239,36 @@ def run_ours(args, rank, world, local_rank):
             line["cnn_guided"] = guided
         if wavefront is not None:
             line["wavefront"] = wavefront
+        if deblock is not None:
+            line["deblock"] = deblock
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_both_legs()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def deblock_leg(enc, n_jobs, first_poc):
+    """SURVEY 8f rank 1, first stage of the per-picture tail - NOT part of `value`: TComLoopFilter::loopFilterPic for the 256
+    pictures of the last timed step, on the device from the CTU records (fhc_deblock_pictures).  HBM-bound byte work:
+    algorithmic bytes per picture = the records' reconstruction read (2 B / sample) + depth / trIdx (512 B / CTU) + the
+    deblocked picture written (1 B / sample)."""
+    out = enc.pinned_array((n_jobs, enc.frame_samples), np.uint8)
+    enc.deblock_pictures(first_poc, n_jobs, out)                  # warm-up (allocates the planes)
+    t0 = time.perf_counter()
+    _, ms = enc.deblock_pictures(first_poc, n_jobs, out)
+    wall = time.perf_counter() - t0
+    algo = n_jobs * (enc.frame_samples * 3 + CTUS * 512)
+    peaks = load_json("MEASURED_PEAKS.json") or {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = algo / (ms / 1e3) / 1e9
+    return {"value": round(n_jobs / (ms / 1e3), 1), "unit": "frames/s", "kernel_ms": round(ms, 3), "pictures": n_jobs,
+            "e2e": {"value": round(n_jobs / wall, 1), "unit": "frames/s", "d2h_bytes": int(out.nbytes)},
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bytes_per_picture": algo // n_jobs,
+                         "note": "four kernels (gather, vertical edges, horizontal edges, pack); the passes re-read and re-write the int16 planes, "
+                                 "so DRAM traffic is about 3x the algorithmic bytes"},
+            "checksum": int(out[::37, ::101].sum(dtype=np.int64))}
 
 
 def wavefront_leg(fh, host_in, host_out, sps, n_jobs, device):
@@ -420,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=CLIP, help="frames of the clip per GPU (64 = configs[1]; anything else is a self-test)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-deblock", action="store_true", help="skip the extra deblocking step (fhc_deblock_pictures) after the timed region")
     ap.add_argument("--no-pipeline", action="store_true", help="one submit at a time: a step ends before the next one is submitted")
     ap.add_argument("--no-wpp", action="store_true", help="skip the extra wavefront step (--WaveFrontSynchro=1) after the timed region")
     ap.add_argument("--no-cnn", action="store_true", help="skip the extra CNN-guided step (BASELINE configs[4]) after the timed region")
