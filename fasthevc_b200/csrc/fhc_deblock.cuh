@@ -139,18 +139,62 @@ FHC_DBK_HD void dbk_segment(const DbkTables& t, const DbkPic& pic, int W, int wc
   }
 }
 
-// sample i of the planar 4:2:0 picture (Y, Cb, Cr): component, position, and where the records keep it
-FHC_DBK_HD int16_t dbk_record_sample(const fhc_ctu_result* ctus, int W, int H, int wc, long long i, int* comp, long long* planeIdx)
+// The copy passes move groups of four neighbouring samples (8 bytes of int16): picture widths are multiples of 8, so a
+// group never straddles a CTU, a row or a plane, and every access is 8-byte aligned (records are 8-byte aligned, a
+// record row is 128 / 64 bytes).  Group g of the planar 4:2:0 picture (Y, Cb, Cr) -> component and position.
+struct DbkGroup { int comp, x, y, w; };
+FHC_DBK_HD DbkGroup dbk_group(int W, int H, int g)
 {
-  const long long luma = (long long)W * H;
-  const int c = i < luma ? 0 : (i < luma + luma / 4 ? 1 : 2);
-  const long long k = i - (c == 0 ? 0 : (c == 1 ? luma : luma + luma / 4));
-  const int sh = c ? 1 : 0, w = W >> sh, n = 64 >> sh;
-  const int x = (int)(k % w), y = (int)(k / w);
-  const fhc_ctu_result* o = &ctus[(y / n) * wc + x / n];
-  const int16_t* src = c == 0 ? o->recoY : (c == 1 ? o->recoCb : o->recoCr);
-  *comp = c; *planeIdx = k;
-  return src[(y % n) * n + (x % n)];
+  const int lumaGroups = W * H / 4, chromaGroups = lumaGroups / 4;
+  DbkGroup r;
+  r.comp = g < lumaGroups ? 0 : (g < lumaGroups + chromaGroups ? 1 : 2);
+  const int k = g - (r.comp == 0 ? 0 : (r.comp == 1 ? lumaGroups : lumaGroups + chromaGroups));
+  r.w = r.comp ? W >> 1 : W;
+  const int gw = r.w >> 2;
+  r.y = k / gw; r.x = (k - r.y * gw) << 2;
+  return r;
+}
+struct DbkQuad { uint32_t lo, hi; };                 // four int16 samples in two words (little endian: sample 0 in the low half of lo)
+FHC_DBK_HD DbkQuad dbk_load4(const int16_t* p)
+{
+  DbkQuad q;
+#if defined(__CUDA_ARCH__)
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  q.lo = v.x; q.hi = v.y;
+#else
+  q.lo = (uint32_t)(uint16_t)p[0] | ((uint32_t)(uint16_t)p[1] << 16);
+  q.hi = (uint32_t)(uint16_t)p[2] | ((uint32_t)(uint16_t)p[3] << 16);
+#endif
+  return q;
+}
+FHC_DBK_HD void dbk_store4(int16_t* p, const DbkQuad& q)
+{
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint2*>(p) = make_uint2(q.lo, q.hi);
+#else
+  p[0] = (int16_t)(q.lo & 0xFFFF); p[1] = (int16_t)(q.lo >> 16); p[2] = (int16_t)(q.hi & 0xFFFF); p[3] = (int16_t)(q.hi >> 16);
+#endif
+}
+// pass 0: the records' reconstruction (64x64 / 32x32 blocks per CTU) -> planes
+FHC_DBK_HD void dbk_gather4(const DbkPic& pic, int W, int H, int wc, int g)
+{
+  const DbkGroup r = dbk_group(W, H, g);
+  const int n = r.comp ? 32 : 64, lg = r.comp ? 5 : 6;
+  const fhc_ctu_result* o = &pic.ctus[(r.y >> lg) * wc + (r.x >> lg)];
+  const int16_t* src = r.comp == 0 ? o->recoY : (r.comp == 1 ? o->recoCb : o->recoCr);
+  dbk_store4(pic.plane[r.comp] + (size_t)r.y * r.w + r.x, dbk_load4(src + (r.y & (n - 1)) * n + (r.x & (n - 1))));
+}
+// pass 3: planes -> packed output in the layout of the input pictures (4 or 8 bytes per group)
+FHC_DBK_HD void dbk_pack4(const DbkPic& pic, int W, int H, int sampleBytes, int g)
+{
+  const DbkGroup r = dbk_group(W, H, g);
+  const DbkQuad q = dbk_load4(pic.plane[r.comp] + (size_t)r.y * r.w + r.x);
+  if (sampleBytes == 1)
+  {
+    const uint32_t packed = (q.lo & 255u) | ((q.lo >> 8) & 0xFF00u) | ((q.hi & 255u) << 16) | ((q.hi << 8) & 0xFF000000u);
+    static_cast<uint32_t*>(pic.out)[g] = packed;                  // little endian: sample k at byte k
+  }
+  else dbk_store4(static_cast<int16_t*>(pic.out) + (size_t)g * 4, q);
 }
 
 #if defined(__CUDACC__) && defined(FHC_DEVICE_BUILD)
@@ -159,23 +203,18 @@ __constant__ DbkTables g_dbkTables = FHC_DBK_TABLES;
 // kernel (320 threads x 168 registers = 53.8 K of 64 K), so finished pictures are filtered while later ones are searched.
 #define FHC_DBK_THREADS 128
 
-// pass 0: the records' reconstruction (64x64 blocks per CTU) -> planes.  blockIdx.y = picture.
+// pass 0 (blockIdx.y = picture): a thread per group of four samples, consecutive threads on consecutive groups
 __global__ void __launch_bounds__(FHC_DBK_THREADS) fhc_dbk_gather_kernel(const DbkPic* pics, int W, int H, int wc)
 {
-  const DbkPic pic = pics[blockIdx.y];
-  const long long total = (long long)W * H * 3 / 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-  {
-    int c; long long k;
-    const int16_t v = dbk_record_sample(pic.ctus, W, H, wc, i, &c, &k);
-    pic.plane[c][k] = v;
-  }
+  const DbkPic& pic = pics[blockIdx.y];
+  const int total = W * H * 3 / 8;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) dbk_gather4(pic, W, H, wc, g);
 }
 // passes 1 / 2: one thread per candidate edge segment; neighbouring threads take neighbouring segments along the edge
 // direction's perpendicular so that a warp's accesses stay within a few rows.
 __global__ void __launch_bounds__(FHC_DBK_THREADS) fhc_dbk_edges_kernel(const DbkPic* pics, int W, int H, int wc, int bd, int dir)
 {
-  const DbkPic pic = pics[blockIdx.y];
+  const DbkPic& pic = pics[blockIdx.y];
   const int nx = dir == 0 ? W / 8 : W / 4, ny = dir == 0 ? H / 4 : H / 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx * ny; i += gridDim.x * blockDim.x)
   {
@@ -183,18 +222,12 @@ __global__ void __launch_bounds__(FHC_DBK_THREADS) fhc_dbk_edges_kernel(const Db
     dbk_segment(g_dbkTables, pic, W, wc, bd, dir == 0 ? sx * 8 : sx * 4, dir == 0 ? sy * 4 : sy * 8, dir);
   }
 }
-// pass 3: planes -> packed output in the layout of the input pictures
+// pass 3
 __global__ void __launch_bounds__(FHC_DBK_THREADS) fhc_dbk_pack_kernel(const DbkPic* pics, int W, int H, int sampleBytes)
 {
-  const DbkPic pic = pics[blockIdx.y];
-  const long long luma = (long long)W * H, total = luma * 3 / 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-  {
-    const int c = i < luma ? 0 : (i < luma + luma / 4 ? 1 : 2);
-    const long long k = i - (c == 0 ? 0 : (c == 1 ? luma : luma + luma / 4));
-    const int16_t v = pic.plane[c][k];
-    if (sampleBytes == 1) static_cast<uint8_t*>(pic.out)[i] = (uint8_t)v; else static_cast<uint16_t*>(pic.out)[i] = (uint16_t)v;
-  }
+  const DbkPic& pic = pics[blockIdx.y];
+  const int total = W * H * 3 / 8;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) dbk_pack4(pic, W, H, sampleBytes, g);
 }
 #endif
 

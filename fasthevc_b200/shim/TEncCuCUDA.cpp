@@ -231,10 +231,16 @@ static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
 
 void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
 {
-  static fhc_ctu_result r;
+  // one device->host copy per picture (fhc_fetch_picture waits for that picture only), served CTU by CTU
+  static std::vector<fhc_ctu_result> picture;
   const int addr = (int)pCtu->getCtuRsAddr();
-  if (addr == 0) submit_pictures(enc, pCtu);
-  if (fhc_fetch_ctu(g_ctx, pCtu->getSlice()->getPOC(), addr, &r) != FHC_OK) fhc_die("fhc_fetch_ctu");
+  if (addr == 0)
+  {
+    submit_pictures(enc, pCtu);
+    picture.resize((size_t)pCtu->getPic()->getNumberOfCtusInFrame());
+    if (fhc_fetch_picture(g_ctx, pCtu->getSlice()->getPOC(), picture.data()) != FHC_OK) fhc_die("fhc_fetch_picture");
+  }
+  const fhc_ctu_result& r = picture[(size_t)addr];
 
   // TComDataCU::copyToPic: the per-partition arrays an intra CTU decision changes (everything else keeps the values
   // TComDataCU::initCtu gave it just before compressCtu, TEncSlice.cpp:797)

@@ -63,7 +63,6 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
 int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
 {
   if (addr < 0 || addr >= c->numCtus) return FHC_ERR_ARG;
-  if (addr == 0) emu_log("fetch", poc, c->pipelined);
   for (int k = 0; k < 2; k++)                       // the newer submit first, as the library does
   {
     const emu_batch& bt = c->b[k ? c->newest ^ 1 : c->newest];
@@ -89,18 +88,25 @@ int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sample
       DbkPic pic;
       pic.ctus = bt.out.data() + (size_t)(first_poc - bt.poc + i) * c->numCtus;
       pic.plane[0] = planes.data(); pic.plane[1] = planes.data() + luma; pic.plane[2] = planes.data() + luma + luma / 4;
-      pic.out = NULL; pic.qp = bt.qps[(size_t)(first_poc - bt.poc + i)]; pic.pad = 0;
-      for (long long s = 0; s < frame; s++) { int comp; long long idx; const int16_t v = dbk_record_sample(pic.ctus, W, H, wc, s, &comp, &idx); pic.plane[comp][idx] = v; }
+      pic.qp = bt.qps[(size_t)(first_poc - bt.poc + i)]; pic.pad = 0;
+      for (int g = 0; g < (int)(frame / 4); g++) dbk_gather4(pic, W, H, wc, g);
       for (int dir = 0; dir < 2; dir++)
         for (int y = 0; y < H; y += dir == 0 ? 4 : 8)
           for (int x = 0; x < W; x += dir == 0 ? 8 : 4) dbk_segment(tables, pic, W, wc, c->seq.bitDepth, x, y, dir);
-      for (long long s = 0; s < frame; s++)
-      {
-        if (sampleBytes == 1) ((unsigned char*)out)[(size_t)i * frame + s] = (unsigned char)planes[(size_t)s];
-        else ((unsigned short*)out)[(size_t)i * frame + s] = (unsigned short)planes[(size_t)s];
-      }
+      pic.out = (unsigned char*)out + (size_t)i * frame * sampleBytes;
+      for (int g = 0; g < (int)(frame / 4); g++) dbk_pack4(pic, W, H, sampleBytes, g);
     }
     return FHC_OK;
+  }
+  return FHC_ERR_ARG;
+}
+int fhc_fetch_picture(fhc_ctx* c, int poc, fhc_ctu_result* out)
+{
+  emu_log("fetch", poc, c->pipelined);
+  for (int k = 0; k < 2; k++)
+  {
+    const emu_batch& bt = c->b[k ? c->newest ^ 1 : c->newest];
+    if (poc >= bt.poc && poc < bt.poc + bt.n) { memcpy(out, bt.out.data() + (size_t)(poc - bt.poc) * c->numCtus, sizeof(fhc_ctu_result) * (size_t)c->numCtus); return FHC_OK; }
   }
   return FHC_ERR_ARG;
 }
