@@ -11,6 +11,10 @@ fhc_fetch_picture_async of every picture's CTU records (page-locked D2H).  `e2e`
 kernel inside the same steps (inputs resident in HBM when it starts); both max over ranks.  N > 1: one process per GPU
 (torchrun), every rank encodes its own contiguous 64-frame group (configs[2]: 512 frames on 8 GPUs, weak scaling), no
 collective on the data path and no NCCL - a gloo group provides the barrier and the max over ranks.
+Steps are pipelined (step s+1 is submitted before the results of step s are fetched: two submits in flight, their kernels
+overlap at the tail); `value` is then the CUDA-event time from the first kernel's start to the last kernel's end.  At
+N = 1 three extra objects follow from one more step each after the timed region (not part of `value`): `deblock`
+(fhc_deblock_pictures on the last step's pictures), `cnn_guided` (BASELINE configs[4]) and `wavefront` (--WaveFrontSynchro=1).
 
 `--impl reference` times the UNMODIFIED reference encoder (oracle/_ref/TAppEncoder, HM 16.14 with the OpenCV dump
 stubbed) on the host cores: one process per core, one 1080p picture each per step.

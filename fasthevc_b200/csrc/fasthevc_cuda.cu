@@ -462,7 +462,8 @@ static int launch(fhc_ctx* c, Batch* bt, int first_poc, int n, int sampleBytes, 
   // across submits, not the makespan of one.  No picture runs alone in its block (pairs of twin-aligned chains get the
   // most out of an SM), and the blocks of a kernel leave as soon as the remaining pictures fit into the
   // others, so that the next submit's kernel - queued on its own stream, with its own scratch - fills the freed SMs.
-  const int pack = c->pipelined && !hinted ? 1 : 0;
+  // (not for wavefront pictures: a picture then keeps many chain slots busy, and counting pictures would send blocks away too early)
+  const int pack = c->pipelined && !hinted && !wpp ? 1 : 0;
   {
     std::vector<int> order((size_t)n);
     for (int i = 0; i < n; i++) order[(size_t)i] = i;
