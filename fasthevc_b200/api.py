@@ -36,10 +36,13 @@ CTU_RESULT_DTYPE = np.dtype([("depth", "u1", 256), ("partSize", "u1", 256), ("pr
                              ("recoY", "<i2", 4096), ("recoCb", "<i2", 1024), ("recoCr", "<i2", 1024),
                              ("totalCost", "<f8"), ("totalDist", "<u4"), ("totalBits", "<u4"), ("totalBins", "<u4")], align=True)
 
+# fhc_sao_stats
+SAO_STATS_DTYPE = np.dtype([("eoDiff", "<i4", (4, 5)), ("eoCount", "<i4", (4, 5)), ("boDiff", "<i4", 32), ("boCount", "<i4", 32)])
+
 EXPORTS = ["fhc_create", "fhc_destroy", "fhc_submit_frames", "fhc_fetch_ctu", "fhc_fetch_picture", "fhc_num_ctus",
            "fhc_slice_params_from_qp", "fhc_device_input", "fhc_run_resident", "fhc_host_alloc", "fhc_host_free",
            "fhc_last_error", "fhc_launch_count", "fhc_last_kernel_ms", "fhc_pictures_in_flight", "fhc_poll_picture",
-           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue", "fhc_submit_frames_hinted", "fhc_device_picture", "fhc_configure", "fhc_span_begin", "fhc_span_ms", "fhc_deblock_pictures", "fhc_last_deblock_ms"]
+           "fhc_fetch_picture_async", "fhc_fetch_sync", "fhc_measure_int_issue", "fhc_submit_frames_hinted", "fhc_device_picture", "fhc_configure", "fhc_span_begin", "fhc_span_ms", "fhc_deblock_pictures", "fhc_last_deblock_ms", "fhc_deblock_pictures_stats"]
 
 
 def library_path():
@@ -75,6 +78,7 @@ def load_library():
     lib.fhc_submit_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams)]
     lib.fhc_submit_frames_hinted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(SliceParams), C.c_void_p]
     lib.fhc_deblock_pictures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.fhc_deblock_pictures_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.fhc_last_deblock_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.fhc_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fhc_span_begin.argtypes = [C.c_void_p]
@@ -188,6 +192,15 @@ class Encoder:
             raise FhcError("hints: %d bytes, expected %d" % (hints.size, n * self.num_ctus * 4))
         self._check(self.lib.fhc_submit_frames_hinted(self.ctx, first_poc, n, yuv.ctypes.data, self.sample_bytes, arr, hints.ctypes.data),
                     "fhc_submit_frames_hinted")
+
+    def deblock_pictures_stats(self, first_poc, n, out=None):
+        """fhc_deblock_pictures_stats: (deblocked pictures, SAO statistics [n][numCtus][3] of SAO_STATS_DTYPE)."""
+        if out is None:
+            out = np.zeros((n, self.frame_samples), np.uint8 if self.sample_bytes == 1 else np.uint16)
+        stats = np.zeros((n, self.num_ctus, 3), SAO_STATS_DTYPE)
+        self._check(self.lib.fhc_deblock_pictures_stats(self.ctx, int(first_poc), int(n), out.ctypes.data, self.sample_bytes, stats.ctypes.data),
+                    "fhc_deblock_pictures_stats")
+        return out, stats
 
     def deblock_pictures(self, first_poc, n, out=None):
         """fhc_deblock_pictures: the deblocked pictures [first_poc, first_poc + n) as an (n, frame_samples) array in the

@@ -11,6 +11,7 @@
 #include <vector>
 #include "fhc_engine.cuh"
 #include "fhc_deblock.cuh"
+#include "fhc_sao.cuh"
 
 using namespace fhc;
 
@@ -231,6 +232,7 @@ struct fhc_ctx
   // deblocking (fhc_deblock_pictures): working planes, packed output and picture table, sized for the largest call so far
   int16_t* dDbkPlanes = nullptr; uint8_t* dDbkOut = nullptr; DbkPic* dDbkPics = nullptr; int dbkCap = 0, dbkSampleBytes = 0;
   cudaEvent_t evDbk0 = nullptr, evDbk1 = nullptr; float dbkMs = 0.f;
+  fhc_sao_stats* dSaoStats = nullptr; SaoPic* dSaoPics = nullptr; int saoCap = 0;     // SAO statistics of the last call
   cudaEvent_t evSpan = nullptr;            // fhc_span_begin: recorded before the next launch's kernel
   int spanArmed = 0, spanOpen = 0;
   Batch batch[FHC_BATCHES];
@@ -285,7 +287,7 @@ int fhc_destroy(fhc_ctx* c)
   if (c->copyIn) cudaStreamSynchronize(c->copyIn);
   if (c->copyOut) cudaStreamSynchronize(c->copyOut);
   for (int i = 0; i < FHC_BATCHES; i++) free_batch(c->batch[i]);
-  cudaFree(c->dTables); cudaFree(c->dDbkPlanes); cudaFree(c->dDbkOut); cudaFree(c->dDbkPics);
+  cudaFree(c->dTables); cudaFree(c->dDbkPlanes); cudaFree(c->dDbkOut); cudaFree(c->dDbkPics); cudaFree(c->dSaoStats); cudaFree(c->dSaoPics);
   if (c->evSpan) cudaEventDestroy(c->evSpan);
   if (c->evDbk0) cudaEventDestroy(c->evDbk0);
   if (c->evDbk1) cudaEventDestroy(c->evDbk1);
@@ -542,7 +544,9 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
 static Batch* find_batch(fhc_ctx* c, int poc, int* slot);
 static int wait_picture(fhc_ctx* c, Batch* bt, int slot);
 
-int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes)
+int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes) { return fhc_deblock_pictures_stats(c, first_poc, n, out, sampleBytes, nullptr); }
+
+int fhc_deblock_pictures_stats(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes, fhc_sao_stats* saoStats)
 {
   if (!c || !out || n <= 0 || (sampleBytes != 1 && sampleBytes != 2) || (c->seq.bitDepth > 8 && sampleBytes != 2)) return FHC_ERR_ARG;
   if (c->submits == 0) return FHC_ERR_STATE;
@@ -588,6 +592,34 @@ int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sample
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->evDbk1, c->copyOut));
   g_launches += 4;
+  if (saoStats)
+  {
+    // SAO statistics from the deblocked planes and the submitted originals (still resident: same lifetime as the records)
+    const size_t inSb = (size_t)(c->seq.bitDepth > 8 ? 2 : 1), perPicStats = (size_t)c->numCtus * 3;
+    if (frame * inSb > bt->inBytesPerFrame) { snprintf(g_err, sizeof(g_err), "fhc_deblock_pictures_stats: the submitted pictures are not resident"); return FHC_ERR_STATE; }
+    if (n > c->saoCap)
+    {
+      cudaFree(c->dSaoStats); cudaFree(c->dSaoPics);
+      c->dSaoStats = nullptr; c->dSaoPics = nullptr; c->saoCap = 0;
+      CK(cudaMalloc(&c->dSaoStats, sizeof(fhc_sao_stats) * perPicStats * (size_t)n));
+      CK(cudaMalloc(&c->dSaoPics, sizeof(SaoPic) * (size_t)n));
+      c->saoCap = n;
+    }
+    std::vector<SaoPic> sp((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+      SaoPic& d = sp[(size_t)i];
+      const uint8_t* in = bt->dIn + (size_t)(slot + i) * frame * inSb;
+      for (int k = 0; k < 3; k++) d.plane[k] = hp[(size_t)i].plane[k];
+      d.org[0] = in; d.org[1] = in + c->lumaSamples * inSb; d.org[2] = in + (c->lumaSamples + c->lumaSamples / 4) * inSb;
+      d.stats = c->dSaoStats + perPicStats * (size_t)i;
+    }
+    CK(cudaMemcpyAsync(c->dSaoPics, sp.data(), sizeof(SaoPic) * (size_t)n, cudaMemcpyHostToDevice, c->copyOut));
+    fhc_sao_stats_kernel<<<dim3((unsigned)c->numCtus, 3, (unsigned)n), 128, 0, c->copyOut>>>(c->dSaoPics, W, H, c->seq.bitDepth, (int)inSb);
+    CK(cudaGetLastError());
+    g_launches += 1;
+    CK(cudaMemcpyAsync(saoStats, c->dSaoStats, sizeof(fhc_sao_stats) * perPicStats * (size_t)n, cudaMemcpyDeviceToHost, c->copyOut));
+  }
   CK(cudaMemcpyAsync(out, c->dDbkOut, frame * (size_t)n * (size_t)sampleBytes, cudaMemcpyDeviceToHost, c->copyOut));
   CK(cudaStreamSynchronize(c->copyOut));
   CK(cudaEventElapsedTime(&c->dbkMs, c->evDbk0, c->evDbk1));

@@ -284,6 +284,31 @@ void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
 // The deblocking filter of a finished picture (TEncGOP.cpp:1619 calls this instead of m_pcLoopFilter->loopFilterPic):
 // fhc_deblock_pictures filters the picture on the device from the CTU records it already holds and returns the planes,
 // which replace PicYuvRec.  FHC_SHIM_DEBLOCK=0 keeps the host filter.
+static std::vector<fhc_sao_stats> g_saoStats;         // statistics of picture g_saoPoc, [ctu][component]
+static int g_saoPoc = -1;
+
+// TEncSampleAdaptiveOffset::SAOProcess calls this instead of getStatistics (TEncSampleAdaptiveOffset.cpp:253): fills
+// m_statData ([ctu][component][type] {Int64 diff[32], count[32]}) from the device's statistics; returns false (the host
+// computes them) when the device did not filter this picture.
+bool fhc_shim_sao_statistics(void* statData, TComPic* pic)
+{
+  if (g_saoPoc != pic->getPOC()) return false;
+  struct Stat { long long diff[32]; long long count[32]; };
+  Stat*** s = (Stat***)statData;
+  const int numCtus = (int)pic->getNumberOfCtusInFrame();
+  for (int c = 0; c < numCtus; c++)
+    for (int comp = 0; comp < 3; comp++)
+    {
+      const fhc_sao_stats& d = g_saoStats[(size_t)c * 3 + comp];
+      for (int t = 0; t < 5; t++) memset(&s[c][comp][t], 0, sizeof(Stat));
+      for (int t = 0; t < 4; t++)
+        for (int k = 0; k < 5; k++) { s[c][comp][t].diff[k] = d.eoDiff[t][k]; s[c][comp][t].count[k] = d.eoCount[t][k]; }
+      for (int k = 0; k < 32; k++) { s[c][comp][4].diff[k] = d.boDiff[k]; s[c][comp][4].count[k] = d.boCount[k]; }
+    }
+  g_saoPoc = -1;
+  return true;
+}
+
 void fhc_shim_loop_filter(TComLoopFilter* lf, TComPic* pic)
 {
   static const bool onDevice = !(getenv("FHC_SHIM_DEBLOCK") && atoi(getenv("FHC_SHIM_DEBLOCK")) == 0);
@@ -293,7 +318,11 @@ void fhc_shim_loop_filter(TComLoopFilter* lf, TComPic* pic)
   const int sampleBytes = g_bitDepth > 8 ? 2 : 1;
   static std::vector<unsigned char> planes;
   planes.resize((size_t)w * h * 3 / 2 * sampleBytes);
-  if (fhc_deblock_pictures(g_ctx, pic->getPOC(), 1, planes.data(), sampleBytes) != FHC_OK) fhc_die("fhc_deblock_pictures");
+  // the SAO statistics of the deblocked picture come back with it (fhc_shim_sao_statistics hands them to SAOProcess)
+  g_saoStats.resize((size_t)pic->getNumberOfCtusInFrame() * 3);
+  g_saoPoc = -1;
+  if (fhc_deblock_pictures_stats(g_ctx, pic->getPOC(), 1, planes.data(), sampleBytes, g_saoStats.data()) != FHC_OK) fhc_die("fhc_deblock_pictures_stats");
+  g_saoPoc = pic->getPOC();
   size_t pos = 0;
   for (int c = 0; c < 3; c++)
   {

@@ -114,6 +114,18 @@ int fhc_submit_frames_hinted(fhc_ctx* ctx, int first_poc, int n, const void* yuv
  * writes the deblocked pictures to `out` (host memory) in the layout of fhc_submit_frames (Y, Cb, Cr planes per picture,
  * sampleBytes each).  Equals the reference's reconstruction with --SAO=0 sample for sample. */
 int fhc_deblock_pictures(fhc_ctx* ctx, int first_poc, int n, void* yuv420_planar_out, int sampleBytes);
+/* Second stage: the SAO statistics of the deblocked pictures (TEncSampleAdaptiveOffset::getStatistics,
+ * TEncSampleAdaptiveOffset.cpp:287, the first step of SAOProcess :253) computed on the device in the same call, from the
+ * deblocked planes and the submitted originals.  sao_stats: host memory, [n][numCtus][3 components] records (or NULL:
+ * fhc_deblock_pictures).  Per record the five types of HM's SAOStatData in compact form: edge offset 0 / 90 / 135 / 45
+ * degrees with classes 0..4 (HM's diff[2 + edgeType]), band offset with bands 0..31; diff = sum of (original -
+ * deblocked), count = samples.  The RD decision that consumes them (decideBlkParams :782) stays on the host. */
+typedef struct fhc_sao_stats
+{
+  int32_t eoDiff[4][5], eoCount[4][5];
+  int32_t boDiff[32], boCount[32];
+} fhc_sao_stats;
+int fhc_deblock_pictures_stats(fhc_ctx* ctx, int first_poc, int n, void* yuv420_planar_out, int sampleBytes, fhc_sao_stats* sao_stats);
 /* CUDA-event time of the four deblocking kernels of the last call. */
 int fhc_last_deblock_ms(fhc_ctx* ctx, float* ms);
 

@@ -29,6 +29,8 @@ Patched sites (reference file:line):
   source/Lib/TLibEncoder/TEncGOP.cpp:49,1562        HARP include + CShow_PredResiReco dump
   source/Lib/TLibEncoder/TEncCu.cpp:260             (TAppEncoderFHC only) xCompressCU(depth 0) -> fhc_shim_compress_ctu
   source/Lib/TLibEncoder/TEncGOP.cpp:1619           (TAppEncoderFHC only) m_pcLoopFilter->loopFilterPic -> fhc_shim_loop_filter
+  source/Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp:253  (TAppEncoderFHC) getStatistics skipped when the shim has the device's statistics;
+                                                    (TAppEncoderDump) fhc_dump_sao_stats after it
 """
 import os, re, shutil, subprocess, sys, concurrent.futures as cf
 
@@ -93,6 +95,18 @@ def dump_sources(scratch):
     assert t.count(marker) == 1, t.count(marker)
     t = t.replace(marker, "  fhc_dump_slice(pcPic, pcSlice, m_pcRdCost, m_pcTrQuant);\n" + marker)
     t = t.replace("Void TEncSlice::compressSlice(", "void fhc_dump_slice(TComPic*, TComSlice*, TComRdCost*, TComTrQuant*);\nVoid TEncSlice::compressSlice(", 1)
+    dst = os.path.join(scratch, "dump", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+
+    # SAO statistics of every picture (pins oracle/hm_sao.c): one call after getStatistics in SAOProcess
+    rel = "Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp"
+    t = open(os.path.join(src, rel)).read()
+    call = "  getStatistics(m_statData, orgYuv, srcYuv, pPic);\n"
+    assert t.count(call) == 1, t.count(call)
+    t = t.replace(call, call + "  fhc_dump_sao_stats((void*)m_statData, m_numCTUsPic);\n")
+    t = t.replace("Void TEncSampleAdaptiveOffset::SAOProcess(", "void fhc_dump_sao_stats(void*, int);\nVoid TEncSampleAdaptiveOffset::SAOProcess(", 1)
     dst = os.path.join(scratch, "dump", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     open(dst, "w").write(t)
@@ -162,6 +176,18 @@ def fhc_sources(scratch, patched):
     assert t.count(call) == 1, t.count(call)
     t = t.replace(call, "    fhc_shim_loop_filter( m_pcLoopFilter, pcPic );\n\n    /////")
     t = t.replace("Void TEncGOP::compressGOP(", "void fhc_shim_loop_filter(TComLoopFilter*, TComPic*);\nVoid TEncGOP::compressGOP(", 1)
+    dst = os.path.join(scratch, "fhc", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+    # second stage: the SAO statistics come from the device with the deblocked picture; the one getStatistics call of
+    # SAOProcess (TEncSampleAdaptiveOffset.cpp:253) is skipped when the shim has them
+    rel = "Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp"
+    t = open(os.path.join(src, rel)).read()
+    call = "  getStatistics(m_statData, orgYuv, srcYuv, pPic);\n"
+    assert t.count(call) == 1, t.count(call)
+    t = t.replace(call, "  if (!fhc_shim_sao_statistics((void*)m_statData, pPic)) getStatistics(m_statData, orgYuv, srcYuv, pPic);\n")
+    t = t.replace("Void TEncSampleAdaptiveOffset::SAOProcess(", "bool fhc_shim_sao_statistics(void*, TComPic*);\nVoid TEncSampleAdaptiveOffset::SAOProcess(", 1)
     dst = os.path.join(scratch, "fhc", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     open(dst, "w").write(t)

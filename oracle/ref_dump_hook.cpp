@@ -164,3 +164,19 @@ int fhc_hint(TComDataCU* cu)
   const size_t i = ((size_t)cu->getSlice()->getPOC() * ctus + cu->getCtuRsAddr()) * 4 + (cu->getZorderIdxInCtu() >> 6);
   return i < hints.size() ? hints[i] : 0;
 }
+
+// SAO statistics of a picture (TEncSampleAdaptiveOffset::getStatistics, TEncSampleAdaptiveOffset.cpp:287): the dump variant
+// calls this right after getStatistics in SAOProcess (:253).  FHC_SAO_DUMP=<file>: per picture the raw
+// [ctu][component][type] {Int64 diff[32]; Int64 count[32]} records, appended.
+void fhc_dump_sao_stats(void* statData, int numCtus)
+{
+  const char* p = getenv("FHC_SAO_DUMP");
+  if (!p) return;
+  struct Stat { long long diff[32]; long long count[32]; };
+  Stat*** s = (Stat***)statData;
+  FILE* f = fopen(p, "ab");
+  if (!f) return;
+  for (int c = 0; c < numCtus; c++)
+    for (int comp = 0; comp < 3; comp++) fwrite(s[c][comp], sizeof(Stat), 5, f);
+  fclose(f);
+}

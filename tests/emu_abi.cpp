@@ -8,12 +8,13 @@
 #include <vector>
 #include "../include/fasthevc_cuda.h"
 #include "../fasthevc_b200/csrc/fhc_deblock.cuh"
+#include "../fasthevc_b200/csrc/fhc_sao.cuh"
 
 extern "C" int fhc_emu_compress_picture_ex(int width, int height, int bitDepth, int sampleBytes, const fhc_slice_params* sp,
                                            const void* y, const void* cb, const void* cr, fhc_ctu_result* out, const uint8_t* hints,
                                            int wpp, int order);
 
-struct emu_batch { int poc, n; std::vector<fhc_ctu_result> out; std::vector<int> qps; emu_batch() : poc(-1), n(0) {} };
+struct emu_batch { int poc, n; std::vector<fhc_ctu_result> out; std::vector<int> qps; std::vector<unsigned char> yuv; emu_batch() : poc(-1), n(0) {} };
 struct fhc_ctx { fhc_seq_params seq; int numCtus, newest, pipelined; emu_batch b[2]; };     // two submit slots, as in the library
 
 // FHC_EMU_LOG=<file>: one line per submit / per picture's first fetch, so that a test can see the order of the shim's calls
@@ -47,6 +48,7 @@ int fhc_submit_frames_hinted(fhc_ctx* c, int first_poc, int n, const void* yuv, 
   emu_batch& bt = c->b[c->newest ^ 1];
   bt.out.assign((size_t)c->numCtus * n, fhc_ctu_result());
   bt.poc = first_poc; bt.n = n;
+  bt.yuv.assign((const unsigned char*)yuv, (const unsigned char*)yuv + frame * n);
   bt.qps.resize((size_t)n);
   for (int k = 0; k < n; k++) bt.qps[(size_t)k] = sp[k].sliceQp;
   c->newest ^= 1;
@@ -70,8 +72,10 @@ int fhc_fetch_ctu(fhc_ctx* c, int poc, int addr, fhc_ctu_result* out)
   }
   return FHC_ERR_ARG;
 }
-// the deblocking passes of fasthevc_b200/csrc/fhc_deblock.cuh, run segment by segment on the host
-int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes)
+// the deblocking passes of fasthevc_b200/csrc/fhc_deblock.cuh and the SAO statistics of fhc_sao.cuh, run sample by sample on the host
+int fhc_deblock_pictures_stats(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes, fhc_sao_stats* saoStats);
+int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes) { return fhc_deblock_pictures_stats(c, first_poc, n, out, sampleBytes, NULL); }
+int fhc_deblock_pictures_stats(fhc_ctx* c, int first_poc, int n, void* out, int sampleBytes, fhc_sao_stats* saoStats)
 {
   using namespace fhc;
   static const DbkTables tables = FHC_DBK_TABLES;
@@ -95,6 +99,14 @@ int fhc_deblock_pictures(fhc_ctx* c, int first_poc, int n, void* out, int sample
           for (int x = 0; x < W; x += dir == 0 ? 8 : 4) dbk_segment(tables, pic, W, wc, c->seq.bitDepth, x, y, dir);
       pic.out = (unsigned char*)out + (size_t)i * frame * sampleBytes;
       for (int g = 0; g < (int)(frame / 4); g++) dbk_pack4(pic, W, H, sampleBytes, g);
+      if (saoStats)
+      {
+        const int inSb = c->seq.bitDepth > 8 ? 2 : 1;
+        const unsigned char* in = bt.yuv.data() + (size_t)(first_poc - bt.poc + i) * frame * inSb;
+        const int16_t* pl[3] = { pic.plane[0], pic.plane[1], pic.plane[2] };
+        const void* org[3] = { in, in + luma * inSb, in + (luma + luma / 4) * inSb };
+        sao_stats_host(W, H, c->seq.bitDepth, pl, org, inSb, saoStats + (size_t)i * c->numCtus * 3);
+      }
     }
     return FHC_OK;
   }

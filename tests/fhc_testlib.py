@@ -40,6 +40,10 @@ class HmParams(C.Structure):
 
 
 def build_oracle():
+    so3 = os.path.join(ORACLE_DIR, "libhm_sao_oracle.so")
+    src3 = os.path.join(ORACLE_DIR, "hm_sao.c")
+    if not os.path.exists(so3) or os.path.getmtime(so3) < os.path.getmtime(src3):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-o", so3, src3])
     so2 = os.path.join(ORACLE_DIR, "libhm_deblock_oracle.so")
     src2 = os.path.join(ORACLE_DIR, "hm_deblock.c")
     if not os.path.exists(so2) or os.path.getmtime(so2) < os.path.getmtime(src2):
@@ -395,3 +399,39 @@ def planes_of(packed, width, height):
     p = np.asarray(packed).reshape(-1).astype(np.int16)
     l = width * height
     return p[:l].reshape(height, width), p[l:l + l // 4].reshape(height // 2, width // 2), p[l + l // 4:].reshape(height // 2, width // 2)
+
+
+# --- SAO statistics oracle (oracle/hm_sao.c) --------------------------------------------------------------------------
+_sao = None
+SAO_HM_DT = np.dtype([("diff", "<i8", 32), ("count", "<i8", 32)])            # HM's SAOStatData
+SAO_STATS_DT = np.dtype([("eoDiff", "<i4", (4, 5)), ("eoCount", "<i4", (4, 5)), ("boDiff", "<i4", 32), ("boCount", "<i4", 32)])   # fhc_sao_stats
+
+
+def oracle_sao_stats(width, height, bit_depth, deblocked, original):
+    """TEncSampleAdaptiveOffset::getStatistics restated; deblocked / original: (Y, Cb, Cr) planes.  Returns [numCtus][3][5] SAO_HM_DT."""
+    global _sao
+    if _sao is None:
+        so = os.path.join(ORACLE_DIR, "libhm_sao_oracle.so")
+        src = os.path.join(ORACLE_DIR, "hm_sao.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-o", so, src])
+        _sao = C.CDLL(so)
+        _sao.hm_sao_statistics.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3
+    src_p = [np.ascontiguousarray(a, dtype=np.int16) for a in deblocked]
+    org_p = [np.ascontiguousarray(a, dtype=np.int16) for a in original]
+    out = np.zeros((n_ctus(width, height), 3, 5), SAO_HM_DT)
+    sp = (C.c_void_p * 3)(*[a.ctypes.data for a in src_p])
+    op = (C.c_void_p * 3)(*[a.ctypes.data for a in org_p])
+    assert _sao.hm_sao_statistics(width, height, bit_depth, sp, op, out.ctypes.data) == 0
+    return out
+
+
+def sao_compact_to_hm(stats):
+    """fhc_sao_stats records [numCtus][3] -> HM's layout [numCtus][3][5] (EO classes at diff[0..4], BO bands at diff[0..31])."""
+    stats = np.asarray(stats)
+    out = np.zeros(stats.shape + (5,), SAO_HM_DT)
+    out["diff"][..., :4, :5] = stats["eoDiff"]
+    out["count"][..., :4, :5] = stats["eoCount"]
+    out["diff"][..., 4, :] = stats["boDiff"]
+    out["count"][..., 4, :] = stats["boCount"]
+    return out

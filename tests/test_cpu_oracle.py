@@ -385,6 +385,27 @@ def test_integrated_encoder_keeps_two_submits_in_flight_emulated():
     assert [c for c in calls if c[0] == "deblock"] == [["deblock", str(k), "1"] for k in range(n)]
 
 
+@pytest.mark.skipif(not T.have_integrated(), reason="oracle/_ref/TAppEncoderFHC not built")
+def test_integrated_encoder_on_replayed_oracle_records():
+    """tests/replay_abi.cpp (the measurement aid of tools/host_tail.py: a libfasthevc_cuda.so that serves precomputed CTU
+    records): the integrated encoder fed with the ORACLE's records writes the stock reference's bitstream - the boundary
+    carries everything the host needs, whoever computes the records."""
+    w, h, n, qp = 136, 72, 3, 31
+    d = tempfile.mkdtemp()
+    Y, U, V = synth_frames(w, h, n, sigma=9.0, seed=8)
+    write_yuv(os.path.join(d, "s.yuv"), Y, U, V)
+    lib_dir = os.path.join(T.ROOT, "tests", "_build", "replay")
+    os.makedirs(lib_dir, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-o", os.path.join(lib_dir, "libfasthevc_cuda.so"),
+                           os.path.join(T.ROOT, "tests", "replay_abi.cpp")])
+    p = T.params_from_qp(w, h, 8, qp)
+    np.concatenate([T.oracle_compress(p, Y[k], U[k], V[k]) for k in range(n)]).tofile(os.path.join(d, "records.bin"))
+    ref, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, tag="_ref")
+    got, _, _ = T.run_reference(os.path.join(d, "s.yuv"), w, h, n, qp, d, dump=False, exe="TAppEncoderFHC", lib_dir=lib_dir, tag="_fhc",
+                                env_extra={"FHC_REPLAY": os.path.join(d, "records.bin")})
+    assert got == ref
+
+
 def test_kernel_source_emulation_4k_width_main10():
     """BASELINE configs[3] geometry in one dimension: a 3840-wide Main10 strip (60 CTUs per row, two full rows + the
     8-line bottom row) through the host emulation of the kernel source against the oracle - row-to-row neighbour and

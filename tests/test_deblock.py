@@ -150,3 +150,64 @@ def test_cuda_deblock_1080p_and_while_a_kernel_runs():
     gb = n * w * h * 1.5 * (2 + 1) / 1e9
     print("deblock 4 x 1080p: %.3f ms alone (%.0f GB/s of records in + pictures out), %.3f ms beside the running kernel (%s)"
           % (ms, gb / (ms / 1e3), ms2, "still running" if running else "kernel had finished"))
+
+
+# ------------------------------------------------------------------ SAO statistics ------------------------------------------
+def _org_planes(w, h, bd, sigma, seed=1234):
+    Y, U, V = synth_frames(w, h, 1, bit_depth=bd, sigma=sigma, seed=seed)
+    return Y[0], U[0], V[0]
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_sao_statistics_oracle_matches_reference_golden(path):
+    """oracle/hm_sao.c (HM's line-buffer loops restated) against the reference's m_statData of the same picture."""
+    z = np.load(path)
+    (w, h, qp, bd), recs = _records(z)
+    got = T.oracle_sao_stats(w, h, bd, T.planes_of(z["deblocked"], w, h), _org_planes(w, h, bd, float(z["sigma"][0])))
+    assert np.array_equal(got["diff"], z["sao_diff"]) and np.array_equal(got["count"], z["sao_count"])
+    assert got["count"].sum() > 4 * w * h               # every type counts most samples
+
+
+def test_kernel_source_sao_statistics_emulated_matches_oracle():
+    """The closed-form per-sample membership / class functions of fasthevc_b200/csrc/fhc_sao.cuh (what the kernel runs)
+    against the oracle's restatement of HM's loops: pictures with boundary CTUs in both directions, one CTU, Main10."""
+    lib = C.CDLL(os.path.join(T.build_emu_abi(), "libfasthevc_cuda.so"))
+    lib.fhc_create.argtypes = [C.POINTER(T.FhcSeqParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.fhc_submit_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fhc_deblock_pictures_stats.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.fhc_destroy.argtypes = [C.c_void_p]
+    for (w, h, bd, qp) in ((200, 136, 8, 34), (64, 64, 8, 30), (72, 136, 10, 36)):
+        Y, U, V = synth_frames(w, h, 1, bit_depth=bd, sigma=5.0, seed=h)
+        sq = T.FhcSeqParams(w, h, bd, 1, 64, 4, 5, 2, 3, 1, 1, 1, 1, 1, 1, 1, 1, 0)
+        ctx = C.c_void_p()
+        assert lib.fhc_create(C.byref(sq), 0, C.byref(ctx)) == 0
+        p = T.params_from_qp(w, h, bd, qp)
+        sp = T.slice_params_from_hm(p)
+        dt = np.uint8 if bd == 8 else np.uint16
+        yuv = np.concatenate([Y.reshape(1, -1), U.reshape(1, -1), V.reshape(1, -1)], axis=1).astype(dt)
+        assert lib.fhc_submit_frames(ctx, 0, 1, yuv.ctypes.data, yuv.itemsize, C.byref(sp)) == 0
+        out = np.zeros((1, w * h * 3 // 2), dt)
+        stats = np.zeros((T.n_ctus(w, h), 3), T.SAO_STATS_DT)
+        assert lib.fhc_deblock_pictures_stats(ctx, 0, 1, out.ctypes.data, yuv.itemsize, stats.ctypes.data) == 0
+        lib.fhc_destroy(ctx)
+        want = T.oracle_sao_stats(w, h, bd, T.planes_of(out[0], w, h), (Y[0], U[0], V[0]))
+        got = T.sao_compact_to_hm(stats)
+        assert np.array_equal(got["diff"], want["diff"]) and np.array_equal(got["count"], want["count"]), (w, h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,bd,sigma", [(416, 240, 5, 8, 6.0), (200, 136, 3, 10, 5.0), (64, 64, 1, 8, 5.0), (1920, 1080, 2, 8, 6.0)])
+def test_cuda_sao_statistics_match_oracle(w, h, n, bd, sigma):
+    import fasthevc_b200 as fh
+    Y, U, V = synth_frames(w, h, n, bit_depth=bd, sigma=sigma, seed=23)
+    qps = [37 - 5 * (k % 2) for k in range(n)]
+    enc = fh.Encoder(w, h, bd, max_frames=n, device=0, wpp=True)
+    enc.submit(enc.pack_frames(Y, U, V), [fh.slice_params_from_qp(q) for q in qps])
+    out, stats = enc.deblock_pictures_stats(0, n)
+    out2, _ = enc.deblock_pictures(0, n)
+    assert np.array_equal(out, out2)
+    enc.close()
+    for k in range(n):
+        want = T.oracle_sao_stats(w, h, bd, T.planes_of(out[k], w, h), (Y[k], U[k], V[k]))
+        got = T.sao_compact_to_hm(stats[k])
+        assert np.array_equal(got["diff"], want["diff"]) and np.array_equal(got["count"], want["count"]), k
