@@ -1,8 +1,8 @@
 // fhc_sao.cuh - SAO statistics of deblocked pictures on the device (second stage of the per-picture
 // tail): TEncSampleAdaptiveOffset::getStatistics / getBlkStats (source/Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp:287-332,
 // :911-1290) for the encoder's default set-up (statistics from the deblocked picture; skip lines 5 / 4 luma, 3 / 2
-// chroma, :124-131).  Two thirds of the SAO encoder's time on the host; the RD decision that consumes the numbers
-// (decideBlkParams :782) stays there.  Included by fasthevc_cuda.cu and by the test-only host builds.
+// chroma, :124-131).  More than half of the SAO encoder's time on the host (about 40 of 70 ms per 1080p picture,
+// profiles/r02_host_tail_cpu.txt); the RD decision that consumes the numbers (decideBlkParams :782) stays there.  Included by fasthevc_cuda.cu and by the test-only host builds.
 //
 // HM walks a CTU line by line with sign line buffers; the result is a pure function of the samples, so here every
 // sample decides for itself: for each of the five types, is it counted in this CTU (sao_member: the start / end columns

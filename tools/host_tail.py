@@ -32,7 +32,8 @@ t0 = time.perf_counter()
 recs = T.oracle_compress_parallel([((w, h, 8, qp), Y[k], U[k], V[k]) for k in range(distinct)])
 print("oracle: %d pictures in %.1f s" % (distinct, time.perf_counter() - t0))
 np.concatenate(recs).tofile(os.path.join(d, "records.bin"))
-for tag, env in (("device deblocking replaced by its host build", {}), ("host deblocking (FHC_SHIM_DEBLOCK=0)", {"FHC_SHIM_DEBLOCK": "0"})):
+for tag, env in (("deblocking + SAO statistics of the kernel source, on the host", {}), ("the host's own deblocking and getStatistics (FHC_SHIM_DEBLOCK=0)", {"FHC_SHIM_DEBLOCK": "0"}),
+                 ("deblocking on the host build, SAO statistics at no cost (zeros: timing only, another bitstream)", {"FHC_REPLAY_FAKE_SAO": "1"})):
     e = {"FHC_REPLAY": os.path.join(d, "records.bin"), "FHC_SHIM_INPUT": os.path.join(d, "s.yuv"), "FHC_SHIM_LOOKAHEAD": "4"}
     e.update(env)
     t0 = time.perf_counter()
