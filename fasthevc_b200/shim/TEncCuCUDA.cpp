@@ -65,6 +65,23 @@ static ShimBatch g_batch[2];
 static int g_newest = 1;                              // index of the batch submitted last
 static std::vector<unsigned char> g_cur;              // the picture the host is working on, packed the same way
 
+// FHC_SHIM_TIMING=1: wall time spent inside the shim's entry points, printed at exit (where the host side of the
+// boundary spends its time; the device calls are included in the entry that makes them)
+#include <chrono>
+struct ShimTimer
+{
+  double submit, fetchCopy, filter; bool on;
+  ShimTimer() : submit(0), fetchCopy(0), filter(0), on(getenv("FHC_SHIM_TIMING") != NULL) {}
+  ~ShimTimer() { if (on) fprintf(stderr, "TLibEncoderCUDA timing: submit (pack / compare / read ahead / fhc_submit) %.3f s, compressCtu (fetch + copy into TComDataCU) %.3f s, loop filter + SAO statistics %.3f s\n", submit, fetchCopy, filter); }
+};
+static ShimTimer g_timer;
+struct ShimScope
+{
+  double* acc; std::chrono::steady_clock::time_point t0;
+  explicit ShimScope(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~ShimScope() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 static void fhc_die(const char* what)
 {
   fprintf(stderr, "TLibEncoderCUDA: %s failed: %s\n", what, fhc_last_error());
@@ -96,20 +113,18 @@ static int lookahead()
 
 static void pack_picture(const TComPicYuv* org, int sampleBytes, std::vector<unsigned char>& out)
 {
-  size_t pos = 0;
   out.resize((size_t)org->getWidth(COMPONENT_Y) * org->getHeight(COMPONENT_Y) * 3 / 2 * sampleBytes);
+  unsigned char* dst = out.data();
   for (int c = 0; c < 3; c++)
   {
     const ComponentID id = ComponentID(c);
     const int cw = org->getWidth(id), ch = org->getHeight(id), stride = org->getStride(id);
     const Pel* src = org->getAddr(id);
-    for (int y = 0; y < ch; y++)
-      for (int x = 0; x < cw; x++)
-      {
-        const Pel v = src[y * stride + x];
-        if (sampleBytes == 1) out[pos++] = (unsigned char)v;
-        else { out[pos++] = (unsigned char)(v & 255); out[pos++] = (unsigned char)(v >> 8); }
-      }
+    for (int y = 0; y < ch; y++, src += stride)
+    {
+      if (sampleBytes == 1) { for (int x = 0; x < cw; x++) dst[x] = (unsigned char)src[x]; dst += cw; }      // row loops the compiler vectorises
+      else { uint16_t* d16 = reinterpret_cast<uint16_t*>(dst); for (int x = 0; x < cw; x++) d16[x] = (uint16_t)src[x]; dst += 2 * cw; }
+    }
   }
 }
 
@@ -234,9 +249,10 @@ void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
   // one device->host copy per picture (fhc_fetch_picture waits for that picture only), served CTU by CTU
   static std::vector<fhc_ctu_result> picture;
   const int addr = (int)pCtu->getCtuRsAddr();
+  ShimScope scope(&g_timer.fetchCopy);
   if (addr == 0)
   {
-    submit_pictures(enc, pCtu);
+    { ShimScope s2(&g_timer.submit); submit_pictures(enc, pCtu); }
     picture.resize((size_t)pCtu->getPic()->getNumberOfCtusInFrame());
     if (fhc_fetch_picture(g_ctx, pCtu->getSlice()->getPOC(), picture.data()) != FHC_OK) fhc_die("fhc_fetch_picture");
   }
@@ -244,23 +260,28 @@ void fhc_shim_compress_ctu(TEncCu* enc, TComDataCU* pCtu)
 
   // TComDataCU::copyToPic: the per-partition arrays an intra CTU decision changes (everything else keeps the values
   // TComDataCU::initCtu gave it just before compressCtu, TEncSlice.cpp:797)
-  for (unsigned i = 0; i < 256; i++)
   {
-    pCtu->getDepth()[i] = r.depth[i];
-    pCtu->getWidth()[i] = pCtu->getHeight()[i] = (UChar)(64 >> r.depth[i]);
-    pCtu->getPartitionSize()[i] = (SChar)r.partSize[i];
-    pCtu->getPredictionMode()[i] = (SChar)r.predMode[i];
-    pCtu->getIntraDir(CHANNEL_TYPE_LUMA)[i] = r.lumaDir[i];
-    pCtu->getIntraDir(CHANNEL_TYPE_CHROMA)[i] = r.chromaDir[i];
-    pCtu->getTransformIdx()[i] = r.trIdx[i];
+    UChar* depth = pCtu->getDepth(); UChar* wd = pCtu->getWidth(); UChar* ht = pCtu->getHeight();
+    SChar* part = pCtu->getPartitionSize(); SChar* pred = pCtu->getPredictionMode();
+    for (unsigned i = 0; i < 256; i++)
+    {
+      depth[i] = r.depth[i];
+      wd[i] = ht[i] = (UChar)(64 >> r.depth[i]);
+      part[i] = (SChar)r.partSize[i];
+      pred[i] = (SChar)r.predMode[i];
+    }
+    memcpy(pCtu->getIntraDir(CHANNEL_TYPE_LUMA), r.lumaDir, 256);
+    memcpy(pCtu->getIntraDir(CHANNEL_TYPE_CHROMA), r.chromaDir, 256);
+    memcpy(pCtu->getTransformIdx(), r.trIdx, 256);
     for (unsigned c = 0; c < 3; c++)
     {
-      pCtu->getCbf(ComponentID(c))[i] = r.cbf[c][i];
-      pCtu->getTransformSkip(ComponentID(c))[i] = r.transformSkip[c][i];
+      memcpy(pCtu->getCbf(ComponentID(c)), r.cbf[c], 256);
+      memcpy(pCtu->getTransformSkip(ComponentID(c)), r.transformSkip[c], 256);
     }
+    TCoeff* cy = pCtu->getCoeff(COMPONENT_Y); TCoeff* cb = pCtu->getCoeff(COMPONENT_Cb); TCoeff* cr = pCtu->getCoeff(COMPONENT_Cr);
+    for (unsigned i = 0; i < 4096; i++) cy[i] = r.coefY[i];
+    for (unsigned i = 0; i < 1024; i++) { cb[i] = r.coefCb[i]; cr[i] = r.coefCr[i]; }
   }
-  for (unsigned i = 0; i < 4096; i++) pCtu->getCoeff(COMPONENT_Y)[i] = r.coefY[i];
-  for (unsigned i = 0; i < 1024; i++) { pCtu->getCoeff(COMPONENT_Cb)[i] = r.coefCb[i]; pCtu->getCoeff(COMPONENT_Cr)[i] = r.coefCr[i]; }
   pCtu->getTotalCost() = r.totalCost;
   pCtu->getTotalDistortion() = r.totalDist;
   pCtu->getTotalBits() = r.totalBits;
@@ -312,6 +333,7 @@ bool fhc_shim_sao_statistics(void* statData, TComPic* pic)
 void fhc_shim_loop_filter(TComLoopFilter* lf, TComPic* pic)
 {
   static const bool onDevice = !(getenv("FHC_SHIM_DEBLOCK") && atoi(getenv("FHC_SHIM_DEBLOCK")) == 0);
+  ShimScope scope(&g_timer.filter);
   if (!onDevice || !g_ctx) { lf->loopFilterPic(pic); return; }
   TComPicYuv* rec = pic->getPicYuvRec();
   const int w = rec->getWidth(COMPONENT_Y), h = rec->getHeight(COMPONENT_Y);
@@ -329,11 +351,10 @@ void fhc_shim_loop_filter(TComLoopFilter* lf, TComPic* pic)
     const ComponentID id = ComponentID(c);
     const int cw = rec->getWidth(id), ch = rec->getHeight(id), stride = rec->getStride(id);
     Pel* dst = rec->getAddr(id);
-    for (int y = 0; y < ch; y++)
-      for (int x = 0; x < cw; x++)
-      {
-        if (sampleBytes == 1) dst[y * stride + x] = (Pel)planes[pos++];
-        else { dst[y * stride + x] = (Pel)(planes[pos] | (planes[pos + 1] << 8)); pos += 2; }
-      }
+    for (int y = 0; y < ch; y++, dst += stride)
+    {
+      if (sampleBytes == 1) { const unsigned char* p8 = planes.data() + pos; for (int x = 0; x < cw; x++) dst[x] = (Pel)p8[x]; pos += (size_t)cw; }
+      else { const uint16_t* p16 = reinterpret_cast<const uint16_t*>(planes.data() + pos); for (int x = 0; x < cw; x++) dst[x] = (Pel)p16[x]; pos += 2 * (size_t)cw; }
+    }
   }
 }
