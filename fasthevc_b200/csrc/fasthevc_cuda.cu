@@ -229,6 +229,7 @@ struct fhc_ctx
   Tables* dTables = nullptr;
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   int pipelined = 0;                       // FHC_OPT_PIPELINED_SUBMITS
+  int numSms = 0;
   // deblocking (fhc_deblock_pictures): working planes, packed output and picture table, sized for the largest call so far
   int16_t* dDbkPlanes = nullptr; uint8_t* dDbkOut = nullptr; DbkPic* dDbkPics = nullptr; int dbkCap = 0, dbkSampleBytes = 0;
   cudaEvent_t evDbk0 = nullptr, evDbk1 = nullptr; float dbkMs = 0.f;
@@ -580,9 +581,8 @@ int fhc_deblock_pictures_stats(fhc_ctx* c, int first_poc, int n, void* out, int 
   }
   // on the copy-out stream: behind the device->host copies already queued, next to the running kernel
   CK(cudaMemcpyAsync(c->dDbkPics, hp.data(), sizeof(DbkPic) * (size_t)n, cudaMemcpyHostToDevice, c->copyOut));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, c->device));
-  const int perPic = std::max(1, (prop.multiProcessorCount * 16 + n - 1) / n);      // grid = a multiple of the SM count over all pictures
+  if (c->numSms <= 0) CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, c->device));
+  const int perPic = std::max(1, (c->numSms * 16 + n - 1) / n);      // grid = a multiple of the SM count over all pictures
   const dim3 grid((unsigned)perPic, (unsigned)n);
   CK(cudaEventRecord(c->evDbk0, c->copyOut));
   fhc_dbk_gather_kernel<<<grid, FHC_DBK_THREADS, 0, c->copyOut>>>(c->dDbkPics, W, H, wc);
