@@ -87,7 +87,7 @@ def cu_positions(width, height):
 class SplitPredictor:
     """One predictor instance = weights folded and resident on one device.
 
-    `weights`: dict with the keys of oracle-independent layout (same names PyTorch / MATLAB exports use here):
+    `weights`: dict in the layouts PyTorch / MATLAB export:
     mean [32][32]; conv{i}_w [Cout][Cin][3][3], conv{i}_b, bn{i}_gamma/beta/mean/var [Cout] for i = 0..2; bn_eps;
     fc_w [2][4096] (c, y, x), fc_b [2]."""
 

@@ -176,7 +176,7 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("GPU present")
     with pytest.raises(fh.FhcError):
         fh.Encoder(64, 64, 8, max_frames=1)
-    src = open(os.path.join(T.ROOT, "fasthevc_b200", "api.py")).read() + open(os.path.join(T.ROOT, "fasthevc_b200", "__init__.py")).read()
+    src = open(os.path.join(T.ROOT, "fasthevc_b200", "api.py")).read() + open(os.path.join(T.ROOT, "fasthevc_b200", "__init__.py")).read() + open(os.path.join(T.ROOT, "fasthevc_b200", "cnn.py")).read()
     assert "oracle" not in src.replace("no oracle", "") and "emu" not in src
 
 
