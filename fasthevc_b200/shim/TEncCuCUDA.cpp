@@ -196,7 +196,8 @@ static void submit_pictures(TEncCu* enc, TComDataCU* pCtu)
   for (int c = 0; c < 3; c++) sp.rdoqLambda[c] = enc->m_pcTrQuant->m_lambdas[c];
   pack_picture(org, sampleBytes, g_cur);
 
-  const int total = enc->m_pcEncCfg->getFramesToBeEncoded();
+  // (FHC_POC_BASE: this instance encodes a frame group that starts in the middle of the sequence, see build_ref.py)
+  const int total = enc->m_pcEncCfg->getFramesToBeEncoded() + (getenv("FHC_POC_BASE") ? atoi(getenv("FHC_POC_BASE")) : 0);
   int n = lookahead();
   // already on the device, with these samples and these parameters?
   ShimBatch* have = NULL;

@@ -29,6 +29,7 @@ Patched sites (reference file:line):
   source/Lib/TLibEncoder/TEncGOP.cpp:49,1562        HARP include + CShow_PredResiReco dump
   source/Lib/TLibEncoder/TEncCu.cpp:260             (TAppEncoderFHC only) xCompressCU(depth 0) -> fhc_shim_compress_ctu
   source/Lib/TLibEncoder/TEncGOP.cpp:1619           (TAppEncoderFHC only) m_pcLoopFilter->loopFilterPic -> fhc_shim_loop_filter
+  source/Lib/TLibEncoder/TEncTop.cpp:57             (TAppEncoderFHC only) first POC from FHC_POC_BASE (frame groups on several host processes)
   source/Lib/TLibEncoder/TEncSampleAdaptiveOffset.cpp:253  (TAppEncoderFHC) getStatistics skipped when the shim has the device's statistics;
                                                     (TAppEncoderDump) fhc_dump_sao_stats after it
 """
@@ -176,6 +177,10 @@ def fhc_sources(scratch, patched):
     assert t.count(call) == 1, t.count(call)
     t = t.replace(call, "    fhc_shim_loop_filter( m_pcLoopFilter, pcPic );\n\n    /////")
     t = t.replace("Void TEncGOP::compressGOP(", "void fhc_shim_loop_filter(TComLoopFilter*, TComPic*);\nVoid TEncGOP::compressGOP(", 1)
+    # (frame groups, see TEncTop.cpp below: the end-of-sequence test counts pictures of this instance, not absolute POCs)
+    eos = "    if(pocCurr>=m_pcCfg->getFramesToBeEncoded())\n"
+    assert t.count(eos) == 1, t.count(eos)
+    t = t.replace(eos, "    if(pocCurr - (getenv(\"FHC_POC_BASE\") ? atoi(getenv(\"FHC_POC_BASE\")) : 0) >= m_pcCfg->getFramesToBeEncoded())\n")
     dst = os.path.join(scratch, "fhc", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     open(dst, "w").write(t)
@@ -188,6 +193,32 @@ def fhc_sources(scratch, patched):
     assert t.count(call) == 1, t.count(call)
     t = t.replace(call, "  if (!fhc_shim_sao_statistics((void*)m_statData, pPic)) getStatistics(m_statData, orgYuv, srcYuv, pPic);\n")
     t = t.replace("Void TEncSampleAdaptiveOffset::SAOProcess(", "bool fhc_shim_sao_statistics(void*, TComPic*);\nVoid TEncSampleAdaptiveOffset::SAOProcess(", 1)
+    dst = os.path.join(scratch, "fhc", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+    # frame groups on several host processes: an encoder instance that starts in the middle of the sequence
+    # (--FrameSkip k) numbers its pictures from POC k instead of 0 when FHC_POC_BASE=k is set (TEncTop.cpp:57); with the
+    # all-intra cfg every access unit is self-contained (CRA + ReWriteParamSetsFlag), so the groups' bitstreams concatenate
+    # to the single-process bitstream
+    # (the per-frame delta-QP table is indexed by absolute POC: TAppEncCfg.cpp:1404 sizes it for the group's first POC too)
+    rel = "App/TAppEncoder/TAppEncCfg.cpp"
+    t = open(patched[rel]).read()
+    a1 = "m_aidQP = new Int[ m_framesToBeEncoded + m_iGOPSize + 1 ];"
+    a2 = "::memset( m_aidQP, 0, sizeof(Int)*( m_framesToBeEncoded + m_iGOPSize + 1 ) );"
+    assert t.count(a1) == 1 and t.count(a2) == 1
+    base = "(getenv(\"FHC_POC_BASE\") ? atoi(getenv(\"FHC_POC_BASE\")) : 0)"
+    t = t.replace(a1, "m_aidQP = new Int[ m_framesToBeEncoded + m_iGOPSize + 1 + %s ];" % base)
+    t = t.replace(a2, "::memset( m_aidQP, 0, sizeof(Int)*( m_framesToBeEncoded + m_iGOPSize + 1 + %s ) );" % base)
+    dst = os.path.join(scratch, "fhc", rel)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    open(dst, "w").write(t)
+    out[rel] = dst
+    rel = "Lib/TLibEncoder/TEncTop.cpp"
+    t = open(os.path.join(src, rel)).read()
+    init = "  m_iPOCLast          = -1;\n"
+    assert t.count(init) == 1, t.count(init)
+    t = t.replace(init, "  m_iPOCLast          = (getenv(\"FHC_POC_BASE\") ? atoi(getenv(\"FHC_POC_BASE\")) : 0) - 1;\n")
     dst = os.path.join(scratch, "fhc", rel)
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     open(dst, "w").write(t)
