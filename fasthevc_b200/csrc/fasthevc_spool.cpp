@@ -7,7 +7,7 @@
 // and the SAO statistics of all pictures on the GPU and writes one spool file per picture; N encoder processes
 // (oracle/_ref/TAppEncoderFHC, each on a contiguous frame group: --FrameSkip k, FHC_POC_BASE=k) link this library in
 // place of libfasthevc_cuda.so, read the device's results from the spool and run the unchanged tail; their bitstreams
-// concatenate to the single-process bitstream byte for byte (tests/test_pipeline.py).
+// concatenate to the single-process bitstream byte for byte (tests/test_zpipeline.py).
 //
 // This library computes nothing: every entry point either hands out what the device wrote or fails.  It implements the
 // subset of include/fasthevc_cuda.h that the shim (fasthevc_b200/shim/TEncCuCUDA.cpp) calls.

@@ -13,7 +13,7 @@ unit is self-contained, so the tail is spread over host PROCESSES:
     libfasthevc_spool.so in place of libfasthevc_cuda.so: it hands the device's results out of the spool and computes
     nothing; the processes start at once and wait for the pictures they need;
   * the groups' bitstreams are concatenated in order: byte-identical to the single-process bitstream
-    (reference: the splice of TAppEncTop::xWriteOutput, TAppEncTop.cpp:629-693; tests/test_pipeline.py).
+    (reference: the splice of TAppEncTop::xWriteOutput, TAppEncTop.cpp:629-693; tests/test_zpipeline.py).
 
 Python here is host plumbing (process control, file I/O); the device work goes through the C ABI as everywhere else.
 """
